@@ -1,0 +1,77 @@
+"""Mirror of Params (halo2_proofs/src/poly/commitment.rs:23-29, 129-222) over the C ABI."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _fr
+from ._lib import B2_ERR_ARG, B2Error, as_fr, as_fr1, check, lib, ptr, require_gpu
+from .arithmetic import Srs, best_multiexp_gpu_cond, gpu_multiexp_bound_and_fft, gpu_multiexp_single_gpu_with_bound
+
+
+class Params:
+    """KZG prover parameters with both bases resident in HBM.
+
+    g / g_lagrange: (n,8) uint64 affine arrays (as Params::read would produce), or Srs
+    objects that are already resident."""
+
+    def __init__(self, k: int, g, g_lagrange):
+        self.k = k
+        self.n = 1 << k
+        self.g = g if isinstance(g, Srs) else Srs.register(g)
+        self.g_lagrange = g_lagrange if isinstance(g_lagrange, Srs) else Srs.register(g_lagrange)
+        if len(self.g) != self.n or len(self.g_lagrange) != self.n:
+            raise B2Error(B2_ERR_ARG, "g and g_lagrange must hold 2^k points")
+
+    def commit(self, poly) -> np.ndarray:
+        """:129-133"""
+        p = as_fr(poly)
+        size = p.shape[0]
+        if len(self.g) < size:
+            raise B2Error(B2_ERR_ARG, "assert!(self.g.len() >= size)")
+        return best_multiexp_gpu_cond(p, self.g[0:size])
+
+    def commit_lagrange(self, poly) -> np.ndarray:
+        """:138-142"""
+        p = as_fr(poly)
+        size = p.shape[0]
+        if len(self.g) < size:
+            raise B2Error(B2_ERR_ARG, "assert!(self.g.len() >= size)")
+        return best_multiexp_gpu_cond(p, self.g_lagrange[0:size])
+
+    def commit_lagrange_with_bound(self, poly, max_bits: int) -> np.ndarray:
+        """:199-222.  The reference first drops zero scalars on the CPU (:204-212); zero
+        scalars produce no bucket entries here, so the same point comes out without that
+        pass.  max_bits is a contract: a larger scalar raises (B2_ERR_BOUND)."""
+        p = as_fr(poly)
+        return gpu_multiexp_single_gpu_with_bound(p, self.g_lagrange[0:p.shape[0]], max_bits)
+
+    def commit_lagrange_and_ifft(self, poly: np.ndarray, omega_inv, ifft_divisor):
+        """:144-170 (cuda flavour): returns (coefficients, commitment); `poly` is consumed
+        (overwritten with its coefficient form), as the reference moves the Vec."""
+        c = gpu_multiexp_bound_and_fft(poly, self.g_lagrange, _fr.NUM_BITS, omega_inv, ifft_divisor, self.k)
+        return poly, c
+
+    def commit_lagrange_batch(self, cols: np.ndarray, max_bits: int = _fr.NUM_BITS, ifft=None):
+        """The prover's per-column commits (plonk/prover.rs:293-299, 470-501, 561-593) as one
+        call: cols (columns, n, 4) -> (columns, 12).  ifft=(omega_inv, divisor) also replaces
+        every column by its coefficient form (commit_lagrange_and_ifft per column)."""
+        if cols.ndim != 3 or cols.shape[2] != 4 or cols.shape[1] > self.n:
+            raise B2Error(B2_ERR_ARG, "expected (columns, n, 4)")
+        if not (cols.flags.c_contiguous and cols.dtype == np.uint64):
+            raise B2Error(B2_ERR_ARG, "cols must be C-contiguous uint64")
+        require_gpu()
+        out = np.zeros((cols.shape[0], 12), dtype=np.uint64)
+        if ifft is None:
+            check(lib().b2_commit_batch(self.g_lagrange.handle, ptr(cols), cols.shape[0], cols.shape[1],
+                                        int(max_bits), 0, None, None, self.k, ptr(out)))
+        else:
+            om, dv = as_fr1(ifft[0]), as_fr1(ifft[1])
+            check(lib().b2_commit_batch(self.g_lagrange.handle, ptr(cols), cols.shape[0], cols.shape[1],
+                                        int(max_bits), 1, ptr(om), ptr(dv), self.k, ptr(out)))
+        return out
+
+    def free(self) -> None:
+        self.g.free()
+        self.g_lagrange.free()

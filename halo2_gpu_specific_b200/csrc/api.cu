@@ -1,0 +1,996 @@
+// api.cu -- host runtime + extern "C" entry points declared in include/b2pcs.h.
+//
+// One DeviceCtx per GPU: a stream, a grow-only workspace (no cudaMalloc on the hot path
+// after the first call of a given size), resident SRS buffers, cached NTT plans
+// (twiddle tables per (omega, log_n, divisor)) and CUDA-event timing.  Calls on one device
+// are serialised by the context mutex, which is what the reference does with
+// acquire_gpu/release_gpu (halo2_proofs/src/arithmetic.rs:313-331).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b2pcs.h"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+using namespace b2;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local int g_dev = 0;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(e_ == cudaErrorMemoryAllocation ? B2_ERR_OOM : B2_ERR_CUDA, "%s:%d %s: %s", \
+                        __FILE__, __LINE__, #call, cudaGetErrorString(e_));                         \
+    } while (0)
+
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + (bytes >> 3);  // slack so sweeps do not realloc every size
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B2_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        }
+        cap = want;
+        return B2_OK;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct Srs {
+    int device;
+    char* d;
+    size_t n;
+};
+
+struct NttPlan {
+    uint32_t log_n = 0;
+    int npass = 0;
+    uint32_t mm[NTT_MAX_PASSES] = {0, 0, 0, 0};
+    uint32_t tw_h = 0;
+    Fr* tw_sub[NTT_MAX_PASSES] = {nullptr, nullptr, nullptr, nullptr};
+    Fr* tw_lo = nullptr;
+    Fr* tw_hi = nullptr;         // unscaled
+    Fr* tw_hi_scaled = nullptr;  // times divisor (pass 0 of an iNTT); == tw_hi when no divisor
+    bool has_div = false;
+    Fr div;
+    std::vector<void*> owned;
+};
+
+struct DeviceCtx {
+    int dev = -1;
+    bool ready = false;
+    std::mutex mu;
+    cudaStream_t stream = nullptr;
+    int sms = 0;
+    int acc_blocks_per_sm = 1;
+    uint64_t launches = 0;
+    // MSM workspace
+    Buf scalars, codes, sorted, counts, offsets, cursor, buckets, part_pt, part_bucket, block_out, window_sums,
+        out96, errflag, tmp_bases, partials;
+    // NTT workspace
+    Buf ntt_in, ntt_work, ntt_out;
+    std::map<std::string, NttPlan*> plans;
+    // timing
+    cudaEvent_t ev[16];
+    double last_kernel_ms = 0, last_total_ms = 0;
+    double phases[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+constexpr int MAX_DEV = 16;
+DeviceCtx g_ctx[MAX_DEV];
+std::mutex g_srs_mu;
+std::map<b2_handle_t, Srs> g_srs;
+b2_handle_t g_next_handle = 1;
+
+int ctx_get(DeviceCtx** out) {
+    int dev = g_dev;
+    if (dev < 0 || dev >= MAX_DEV) return fail(B2_ERR_ARG, "bad device %d", dev);
+    DeviceCtx& c = g_ctx[dev];
+    CK(cudaSetDevice(dev));
+    if (!c.ready) {
+        std::lock_guard<std::mutex> lk(c.mu);
+        if (!c.ready) {
+            c.dev = dev;
+            CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            cudaDeviceProp prop;
+            CK(cudaGetDeviceProperties(&prop, dev));
+            c.sms = prop.multiProcessorCount;
+            CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
+            c.acc_blocks_per_sm = nb > 0 ? nb : 1;
+            for (auto& e : c.ev) CK(cudaEventCreate(&e));
+            c.ready = true;
+        }
+    }
+    *out = &c;
+    return B2_OK;
+}
+
+#define LAUNCH(ctx, kernel, grid, block, smem, st, ...)                                                    \
+    do {                                                                                                   \
+        kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                            \
+        (ctx).launches++;                                                                                  \
+        cudaError_t le_ = cudaGetLastError();                                                              \
+        if (le_ != cudaSuccess)                                                                            \
+            return fail(B2_ERR_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #kernel,                   \
+                        cudaGetErrorString(le_));                                                          \
+    } while (0)
+
+Fr fr_from_bytes(const void* p) {
+    Fr r;
+    memcpy(r.v, p, 32);
+    return r;
+}
+
+// ---------------------------------------------------------------------------- MSM
+void msm_pick_config(size_t n, uint32_t max_bits, uint32_t* c_out, uint32_t* W_out) {
+    if (max_bits > 254) max_bits = 254;
+    uint32_t lg = 0;
+    while ((2ull << lg) <= n) lg++;
+    int c = (int)lg - 4;
+    if (c < 8) c = 8;
+    if (c > 16) c = 16;
+    if (const char* e = getenv("B2_MSM_C")) {
+        int v = atoi(e);
+        if (v >= 8 && v <= 22) c = v;
+    }
+    uint32_t W = max_bits / (uint32_t)c + 1;
+    if (W > 32) {  // cannot happen for c >= 8 and max_bits <= 254
+        c = 8;
+        W = max_bits / 8 + 1;
+    }
+    *c_out = (uint32_t)c;
+    *W_out = W;
+}
+
+// device-pointer MSM on ctx.stream-compatible stream `st`; writes 96 B (normalised) to d_out
+int msm_run(DeviceCtx& ctx, const char* d_bases, const void* d_scalars, size_t n, uint32_t max_bits,
+            void* d_out, cudaStream_t st, bool record_phases, bool reset_flag = true) {
+    if (max_bits > 254) max_bits = 254;
+    MsmGeom g;
+    msm_pick_config(n, max_bits, &g.c, &g.W);
+    g.B = 1u << (g.c - 1);
+    g.n = (uint32_t)n;
+    const size_t nb = (size_t)g.W * g.B;
+    const uint32_t T = (uint32_t)ctx.sms * (uint32_t)ctx.acc_blocks_per_sm * 128u;
+    const uint32_t bpw = (g.B + MSM_RT * MSM_RM - 1) / (MSM_RT * MSM_RM);
+
+    int rc;
+    if ((rc = ctx.codes.reserve((size_t)g.W * n * 4))) return rc;
+    if ((rc = ctx.sorted.reserve((size_t)g.W * n * 4))) return rc;
+    if ((rc = ctx.counts.reserve(nb * 4))) return rc;
+    if ((rc = ctx.offsets.reserve((nb + 1) * 4))) return rc;
+    if ((rc = ctx.cursor.reserve(nb * 4))) return rc;
+    if ((rc = ctx.buckets.reserve(nb * 128))) return rc;
+    if ((rc = ctx.part_pt.reserve((size_t)2 * T * 128))) return rc;
+    if ((rc = ctx.part_bucket.reserve((size_t)2 * T * 4))) return rc;
+    if ((rc = ctx.block_out.reserve((size_t)g.W * bpw * 128))) return rc;
+    if ((rc = ctx.window_sums.reserve(32 * 128))) return rc;
+    if ((rc = ctx.errflag.reserve(16))) return rc;
+
+    cudaEvent_t* ev = ctx.ev;
+    if (record_phases) CK(cudaEventRecord(ev[0], st));
+    CK(cudaMemsetAsync(ctx.counts.p, 0, nb * 4, st));
+    if (reset_flag) CK(cudaMemsetAsync(ctx.errflag.p, 0, 4, st));
+    LAUNCH(ctx, msm_digits_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4*)d_scalars,
+           ctx.codes.as<uint32_t>(), ctx.counts.as<uint32_t>(), g, max_bits, ctx.errflag.as<int>());
+    if (record_phases) CK(cudaEventRecord(ev[1], st));
+    LAUNCH(ctx, msm_scan_kernel, 1, 1024, 0, st, ctx.counts.as<uint32_t>(), ctx.offsets.as<uint32_t>(),
+           ctx.cursor.as<uint32_t>(), (uint32_t)nb);
+    if (record_phases) CK(cudaEventRecord(ev[2], st));
+    LAUNCH(ctx, msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), g.W), 256, 0, st,
+           ctx.codes.as<uint32_t>(), ctx.cursor.as<uint32_t>(), ctx.sorted.as<uint32_t>(), g);
+    if (record_phases) CK(cudaEventRecord(ev[3], st));
+    // chunk is sized from the upper bound n*W; threads past the real entry count exit
+    uint64_t emax = (uint64_t)n * g.W;
+    uint32_t chunk = (uint32_t)((emax + T - 1) / T);
+    if (chunk < 16) chunk = 16;
+    LAUNCH(ctx, msm_accumulate_kernel, T / 128, 128, 0, st, d_bases, 64u, ctx.sorted.as<uint32_t>(),
+           ctx.offsets.as<uint32_t>(), (uint32_t)nb, chunk, T, ctx.buckets.as<char>(), ctx.part_pt.as<char>(),
+           ctx.part_bucket.as<uint32_t>());
+    if (record_phases) CK(cudaEventRecord(ev[4], st));
+    LAUNCH(ctx, msm_fixup_kernel, (2 * T + 127) / 128, 128, 0, st, ctx.part_pt.as<char>(),
+           ctx.part_bucket.as<uint32_t>(), 2 * T, ctx.buckets.as<char>());
+    if (record_phases) CK(cudaEventRecord(ev[5], st));
+    LAUNCH(ctx, msm_reduce_kernel, g.W * bpw, MSM_RT, MSM_RT * 128, st, ctx.buckets.as<char>(),
+           ctx.offsets.as<uint32_t>(), g, bpw, ctx.block_out.as<char>());
+    if (record_phases) CK(cudaEventRecord(ev[6], st));
+    LAUNCH(ctx, msm_final_kernel, 1, 32, 0, st, ctx.block_out.as<char>(), g, bpw, ctx.window_sums.as<char>(),
+           (char*)d_out, 1);
+    if (record_phases) CK(cudaEventRecord(ev[7], st));
+    return B2_OK;
+}
+
+int msm_collect_phases(DeviceCtx& ctx) {
+    for (int i = 0; i < 7; i++) {
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx.ev[i], ctx.ev[i + 1]));
+        ctx.phases[i] = ms;
+    }
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx.ev[0], ctx.ev[7]));
+    ctx.phases[7] = ms;
+    ctx.last_kernel_ms = ms;
+    return B2_OK;
+}
+
+int write_identity(DeviceCtx& ctx, void* d_out, cudaStream_t st) {
+    // (0, 1, 0) in Montgomery form
+    uint32_t h[24];
+    memset(h, 0, sizeof h);
+    const uint32_t one[8] = {FqParams::one0, FqParams::one1, FqParams::one2, FqParams::one3,
+                             FqParams::one4, FqParams::one5, FqParams::one6, FqParams::one7};
+    memcpy(h + 8, one, 32);
+    CK(cudaMemcpyAsync(d_out, h, 96, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    (void)ctx;
+    return B2_OK;
+}
+
+int srs_lookup(b2_handle_t h, Srs* out) {
+    std::lock_guard<std::mutex> lk(g_srs_mu);
+    auto it = g_srs.find(h);
+    if (it == g_srs.end()) return fail(B2_ERR_HANDLE, "unknown SRS handle %llu", (unsigned long long)h);
+    *out = it->second;
+    return B2_OK;
+}
+
+constexpr size_t MSM_MAX_N = (size_t)1 << 26;  // per launch (entry offsets are 32-bit)
+
+// host wrapper pieces: MSM over possibly > MSM_MAX_N points by splitting; all on ctx.stream
+int msm_run_split(DeviceCtx& ctx, const char* d_bases, const char* d_scalars, size_t n, uint32_t max_bits,
+                  void* d_out, cudaStream_t st, bool record, bool reset_flag = true) {
+    if (n <= MSM_MAX_N) return msm_run(ctx, d_bases, d_scalars, n, max_bits, d_out, st, record, reset_flag);
+    size_t parts = (n + MSM_MAX_N - 1) / MSM_MAX_N;
+    int rc;
+    if ((rc = ctx.partials.reserve(parts * 96))) return rc;
+    for (size_t p = 0; p < parts; p++) {
+        size_t lo = p * MSM_MAX_N, cnt = std::min(MSM_MAX_N, n - lo);
+        if ((rc = msm_run(ctx, d_bases + lo * 64, d_scalars + lo * 32, cnt, max_bits,
+                          ctx.partials.as<char>() + p * 96, st, record && p == 0, reset_flag && p == 0)))
+            return rc;
+    }
+    LAUNCH(ctx, g1_sum_kernel, 1, 32, 0, st, ctx.partials.as<char>(), (uint32_t)parts, (char*)d_out);
+    return B2_OK;
+}
+
+int check_bound_flag(DeviceCtx& ctx, cudaStream_t st) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, ctx.errflag.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if (flag) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
+    return B2_OK;
+}
+
+// ---------------------------------------------------------------------------- NTT
+int ntt_table(DeviceCtx& ctx, NttPlan* pl, Fr** out, const Fr& base, unsigned long long mult, uint32_t count,
+              bool scaled, const Fr& scale) {
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)count * 32));
+    pl->owned.push_back(p);
+    LAUNCH(ctx, ntt_pow_table_kernel, (count + 127) / 128, 128, 0, ctx.stream, (Fr*)p, base, mult, count,
+           scaled ? 1 : 0, scale);
+    *out = (Fr*)p;
+    return B2_OK;
+}
+
+int ntt_get_plan(DeviceCtx& ctx, const void* omega, const void* divisor, uint32_t log_n, NttPlan** out) {
+    std::string key((const char*)omega, 32);
+    key.append((const char*)&log_n, 4);
+    if (divisor) {
+        key.push_back(1);
+        key.append((const char*)divisor, 32);
+    } else {
+        key.push_back(0);
+    }
+    auto it = ctx.plans.find(key);
+    if (it != ctx.plans.end()) {
+        *out = it->second;
+        return B2_OK;
+    }
+    NttPlan* pl = new NttPlan();
+    pl->log_n = log_n;
+    uint32_t maxm = 11;
+    if (const char* e = getenv("B2_NTT_MAXM")) {
+        int v = atoi(e);
+        if (v >= 3 && v <= 12) maxm = (uint32_t)v;
+    }
+    int P = (int)((log_n + maxm - 1) / maxm);
+    if (maxm == 11 && (log_n == 12 || log_n == 23 || log_n == 24)) P = (int)((log_n + 11) / 12);
+    if (P > NTT_MAX_PASSES) {
+        delete pl;
+        return fail(B2_ERR_ARG, "log_n %u needs more than %d passes", log_n, NTT_MAX_PASSES);
+    }
+    pl->npass = P;
+    for (int i = 0; i < P; i++) pl->mm[i] = log_n / P + ((uint32_t)i < log_n % P ? 1 : 0);
+    pl->tw_h = (log_n + 1) / 2;
+    Fr w = fr_from_bytes(omega);
+    Fr none = fr_from_bytes(omega);
+    int rc;
+    for (int i = 0; i < P; i++) {
+        bool found = false;
+        for (int j = 0; j < i; j++)
+            if (pl->mm[j] == pl->mm[i]) {
+                pl->tw_sub[i] = pl->tw_sub[j];
+                found = true;
+                break;
+            }
+        if (found) continue;
+        uint32_t cnt = pl->mm[i] >= 1 ? (1u << (pl->mm[i] - 1)) : 1u;
+        if ((rc = ntt_table(ctx, pl, &pl->tw_sub[i], w, 1ull << (log_n - pl->mm[i]), cnt, false, none))) return rc;
+    }
+    if (P > 1) {
+        if ((rc = ntt_table(ctx, pl, &pl->tw_lo, w, 1ull, 1u << pl->tw_h, false, none))) return rc;
+        if ((rc = ntt_table(ctx, pl, &pl->tw_hi, w, 1ull << pl->tw_h, 1u << (log_n - pl->tw_h), false, none)))
+            return rc;
+        pl->tw_hi_scaled = pl->tw_hi;
+    }
+    if (divisor) {
+        pl->has_div = true;
+        pl->div = fr_from_bytes(divisor);
+        if (P > 1) {
+            if ((rc = ntt_table(ctx, pl, &pl->tw_hi_scaled, w, 1ull << pl->tw_h, 1u << (log_n - pl->tw_h), true,
+                                pl->div)))
+                return rc;
+        }
+    }
+    CK(cudaStreamSynchronize(ctx.stream));
+    ctx.plans[key] = pl;
+    *out = pl;
+    return B2_OK;
+}
+
+// all-device NTT of `cols` columns.  in -> (work) -> out.  `work` must hold cols * 2^log_n
+// elements when npass > 1.  out may alias in.
+int ntt_run_dev(DeviceCtx& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, uint64_t n_in, void* d_out,
+                uint64_t out_stride, uint64_t n_out, void* d_work, uint64_t cols, const Fr* coset_in,
+                const Fr* coset_out, cudaStream_t st) {
+    const uint32_t k = pl->log_n;
+    const uint64_t N = 1ull << k;
+    uint32_t s_lo = k;
+    for (int p = 0; p < pl->npass; p++) {
+        NttPassArgs a;
+        memset(&a, 0, sizeof a);
+        const bool first = (p == 0), last = (p + 1 == pl->npass);
+        s_lo -= pl->mm[p];
+        a.in = (const uint4*)(first ? d_in : d_work);
+        a.in_col_stride = first ? in_stride : N;
+        a.out = (uint4*)(last ? d_out : d_work);
+        a.out_col_stride = last ? out_stride : N;
+        a.n_in = first ? n_in : N;
+        a.n_out = last ? n_out : N;
+        a.log_n = k;
+        a.m = pl->mm[p];
+        a.s_lo = s_lo;
+        a.pass = (uint32_t)p;
+        a.npass = (uint32_t)pl->npass;
+        for (int i = 0; i < NTT_MAX_PASSES; i++) a.mm[i] = pl->mm[i];
+        a.tw_h = pl->tw_h;
+        a.tw_sub = pl->tw_sub[p];
+        a.tw_lo = pl->tw_lo;
+        a.tw_hi = first ? pl->tw_hi_scaled : pl->tw_hi;
+        if (first && coset_in) {
+            a.coset_in = 1;
+            a.zin1 = coset_in[0];
+            a.zin2 = coset_in[1];
+        }
+        if (last && coset_out) {
+            a.coset_out = 1;
+            a.zout1 = coset_out[0];
+            a.zout2 = coset_out[1];
+        }
+        if (last && pl->npass == 1 && pl->has_div) {
+            a.scale_out = 1;
+            a.scale = pl->div;
+        }
+        const uint32_t threads = std::max(32u, 1u << (a.m >= 3 ? a.m - 3 : 0));
+        const size_t smem = ((size_t)32 << a.m);
+        const uint64_t lines = N >> a.m;
+        for (uint64_t c0 = 0; c0 < cols; c0 += 65535) {
+            const uint64_t cc = std::min<uint64_t>(65535, cols - c0);
+            NttPassArgs b = a;
+            b.in = a.in + 2ull * c0 * a.in_col_stride;
+            b.out = a.out + 2ull * c0 * a.out_col_stride;
+            LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+        }
+    }
+    return B2_OK;
+}
+
+size_t ntt_scratch_limit() {
+    size_t gb = 24;
+    if (const char* e = getenv("B2_NTT_SCRATCH_GB")) {
+        int v = atoi(e);
+        if (v >= 1 && v <= 160) gb = (size_t)v;
+    }
+    return gb << 30;
+}
+
+int copy2d(void* dst, uint64_t dst_stride, const void* src, uint64_t src_stride, uint64_t width, uint64_t rows,
+           cudaMemcpyKind kind, cudaStream_t st) {
+    if (rows == 0 || width == 0) return B2_OK;
+    if (dst_stride == width && src_stride == width) {
+        CK(cudaMemcpyAsync(dst, src, (size_t)width * rows * 32, kind, st));
+    } else {
+        CK(cudaMemcpy2DAsync(dst, (size_t)dst_stride * 32, src, (size_t)src_stride * 32, (size_t)width * 32,
+                             (size_t)rows, kind, st));
+    }
+    return B2_OK;
+}
+
+}  // namespace
+
+// ============================================================================ C ABI
+extern "C" {
+
+int b2_version(void) { return 100; }
+const char* b2_last_error(void) { return g_err.c_str(); }
+
+int b2_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int b2_set_device(int device) {
+    int n = b2_device_count();
+    if (device < 0 || device >= n || device >= MAX_DEV) return fail(B2_ERR_ARG, "device %d of %d", device, n);
+    g_dev = device;
+    return B2_OK;
+}
+int b2_get_device(void) { return g_dev; }
+int b2_synchronize(void) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaDeviceSynchronize());
+    return B2_OK;
+}
+uint64_t b2_launch_count(int reset) {
+    DeviceCtx* ctx;
+    if (ctx_get(&ctx)) return 0;
+    uint64_t v = ctx->launches;
+    if (reset) ctx->launches = 0;
+    return v;
+}
+
+// ---- SRS
+int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_t* out) {
+    if (!bases || !out || n == 0 || stride_bytes < 64) return fail(B2_ERR_ARG, "srs_register: bad arguments");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    char* d = nullptr;
+    CK(cudaMalloc(&d, n * 64));
+    cudaError_t e;
+    if (stride_bytes == 64)
+        e = cudaMemcpy(d, bases, n * 64, cudaMemcpyHostToDevice);
+    else
+        e = cudaMemcpy2D(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(d);
+        return fail(B2_ERR_CUDA, "srs upload: %s", cudaGetErrorString(e));
+    }
+    std::lock_guard<std::mutex> lk2(g_srs_mu);
+    b2_handle_t h = g_next_handle++;
+    g_srs[h] = Srs{ctx->dev, d, n};
+    *out = h;
+    return B2_OK;
+}
+int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t* out) {
+    if (!out || n == 0) return fail(B2_ERR_ARG, "srs_synthetic: bad arguments");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    char* d = nullptr;
+    CK(cudaMalloc(&d, n * 64));
+    LAUNCH(*ctx, srs_synth_kernel, (unsigned)((n + 127) / 128), 128, 0, ctx->stream, d, (unsigned long long)n,
+           (unsigned long long)first_index, (unsigned long long)seed);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::lock_guard<std::mutex> lk2(g_srs_mu);
+    b2_handle_t h = g_next_handle++;
+    g_srs[h] = Srs{ctx->dev, d, n};
+    *out = h;
+    return B2_OK;
+}
+int b2_srs_len(b2_handle_t srs, size_t* n) {
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    *n = s.n;
+    return B2_OK;
+}
+int b2_srs_read(b2_handle_t srs, size_t offset, size_t count, void* out_affine64) {
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (offset + count > s.n) return fail(B2_ERR_ARG, "srs_read out of range");
+    CK(cudaSetDevice(s.device));
+    CK(cudaMemcpy(out_affine64, s.d + offset * 64, count * 64, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+int b2_srs_free(b2_handle_t srs) {
+    std::lock_guard<std::mutex> lk(g_srs_mu);
+    auto it = g_srs.find(srs);
+    if (it == g_srs.end()) return fail(B2_ERR_HANDLE, "unknown SRS handle");
+    cudaSetDevice(it->second.device);
+    cudaFree(it->second.d);
+    g_srs.erase(it);
+    return B2_OK;
+}
+
+// ---- MSM
+int b2_msm_config(size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows) {
+    msm_pick_config(n, max_bits, c, windows);
+    return B2_OK;
+}
+
+int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, uint32_t max_bits,
+               void* d_out_jac96, void* stream) {
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (offset + n > s.n) return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
+    DeviceCtx* ctx;
+    if ((rc = ctx_get(&ctx))) return rc;
+    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if (n == 0 || max_bits == 0) return write_identity(*ctx, d_out_jac96, st);
+    return msm_run_split(*ctx, s.d + offset * 64, (const char*)d_scalars, n, max_bits, d_out_jac96, st, true);
+}
+
+int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96) {
+    if (!out_jac96 || (n && !scalars)) return fail(B2_ERR_ARG, "msm: null pointer");
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (offset + n > s.n) return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
+    DeviceCtx* ctx;
+    if ((rc = ctx_get(&ctx))) return rc;
+    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    if (n == 0 || max_bits == 0) {
+        if ((rc = write_identity(*ctx, ctx->out96.p, st))) return rc;
+        CK(cudaMemcpy(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost));
+        return B2_OK;
+    }
+    if ((rc = ctx->scalars.reserve(n * 32))) return rc;
+    CK(cudaEventRecord(ctx->ev[8], st));
+    CK(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+    if ((rc = msm_run_split(*ctx, s.d + offset * 64, ctx->scalars.as<char>(), n, max_bits, ctx->out96.p, st, true)))
+        return rc;
+    CK(cudaMemcpyAsync(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[9], st));
+    if ((rc = check_bound_flag(*ctx, st))) return rc;
+    if ((rc = msm_collect_phases(*ctx))) return rc;
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+    ctx->last_total_ms = ms;
+    return B2_OK;
+}
+
+int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_jac96) {
+    if (!out_jac96 || (n && (!coeffs || !bases))) return fail(B2_ERR_ARG, "best_multiexp: null pointer");
+    b2_handle_t h = 0;
+    if (n == 0) {
+        DeviceCtx* ctx;
+        int rc = ctx_get(&ctx);
+        if (rc) return rc;
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if ((rc = ctx->out96.reserve(96))) return rc;
+        if ((rc = write_identity(*ctx, ctx->out96.p, ctx->stream))) return rc;
+        CK(cudaMemcpy(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost));
+        return B2_OK;
+    }
+    int rc = b2_srs_register(bases, n, 64, &h);
+    if (rc) return rc;
+    rc = b2_msm(h, 0, coeffs, n, 254, out_jac96);
+    b2_srs_free(h);
+    return rc;
+}
+
+int b2_g1_sum(const void* jac96, size_t count, void* out_jac96) {
+    if (!out_jac96 || (count && !jac96)) return fail(B2_ERR_ARG, "g1_sum: null pointer");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->partials.reserve(std::max<size_t>(count, 1) * 96))) return rc;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    if (count) CK(cudaMemcpyAsync(ctx->partials.p, jac96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
+    LAUNCH(*ctx, g1_sum_kernel, 1, 32, 0, ctx->stream, ctx->partials.as<char>(), (uint32_t)count,
+           ctx->out96.as<char>());
+    CK(cudaMemcpyAsync(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return B2_OK;
+}
+
+// ---- NTT
+int b2_ntt_exec(const b2_ntt_desc* d) {
+    if (!d || !d->omega || !d->in || !d->out) return fail(B2_ERR_ARG, "ntt: null pointer");
+    if (d->log_n < 1 || d->log_n > 28) return fail(B2_ERR_ARG, "ntt: log_n %u out of range [1, 28]", d->log_n);
+    const uint64_t N = 1ull << d->log_n;
+    if (d->n_in == 0 || d->n_in > N || d->n_out == 0 || d->n_out > N)
+        return fail(B2_ERR_ARG, "ntt: n_in/n_out must be in [1, 2^log_n]");
+    if (d->columns == 0) return B2_OK;
+    if (d->in_stride < d->n_in || d->out_stride < d->n_out) return fail(B2_ERR_ARG, "ntt: stride shorter than column");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    NttPlan* pl;
+    if ((rc = ntt_get_plan(*ctx, d->omega, d->divisor, d->log_n, &pl))) return rc;
+    Fr cin[2], cout[2];
+    if (d->coset_in) { cin[0] = fr_from_bytes(d->coset_in); cin[1] = fr_from_bytes((const char*)d->coset_in + 32); }
+    if (d->coset_out) { cout[0] = fr_from_bytes(d->coset_out); cout[1] = fr_from_bytes((const char*)d->coset_out + 32); }
+    const Fr* pcin = d->coset_in ? cin : nullptr;
+    const Fr* pcout = d->coset_out ? cout : nullptr;
+
+    // sub-batch so that the scratch stays bounded
+    const size_t col_bytes = (size_t)N * 32;
+    const size_t limit = ntt_scratch_limit();
+    uint64_t sub = std::max<uint64_t>(1, limit / (col_bytes * (d->location == 0 ? 2 : 1)));
+    sub = std::min<uint64_t>(sub, d->columns);
+    cudaStream_t st = (d->location == 1 && d->stream) ? (cudaStream_t)d->stream : ctx->stream;
+    float k_ms_total = 0;
+    CK(cudaEventRecord(ctx->ev[8], st));
+    for (uint64_t c0 = 0; c0 < d->columns; c0 += sub) {
+        const uint64_t cc = std::min<uint64_t>(sub, d->columns - c0);
+        if (d->location == 1) {
+            if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
+            const char* in = (const char*)d->in + c0 * d->in_stride * 32;
+            char* out = (char*)d->out + c0 * d->out_stride * 32;
+            CK(cudaEventRecord(ctx->ev[10], st));
+            if ((rc = ntt_run_dev(*ctx, pl, in, d->in_stride, d->n_in, out, d->out_stride, d->n_out, ctx->ntt_work.p,
+                                  cc, pcin, pcout, st)))
+                return rc;
+            CK(cudaEventRecord(ctx->ev[11], st));
+        } else {
+            // host: stage in (compact), transform, stage out
+            if ((rc = ctx->ntt_in.reserve(cc * col_bytes))) return rc;  // sized N so it can hold the output too
+            if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
+            const char* hin = (const char*)d->in + c0 * d->in_stride * 32;
+            char* hout = (char*)d->out + c0 * d->out_stride * 32;
+            if ((rc = copy2d(ctx->ntt_in.p, d->n_in, hin, d->in_stride, d->n_in, cc, cudaMemcpyHostToDevice, st))) return rc;
+            CK(cudaEventRecord(ctx->ev[10], st));
+            void* dout = ctx->ntt_in.p;
+            uint64_t dout_stride = N;
+            if (pl->npass == 1 && d->n_in < N) {
+                // single pass reads and writes in one kernel: a compact input cannot share the buffer
+                if ((rc = ctx->ntt_out.reserve(cc * col_bytes))) return rc;
+                dout = ctx->ntt_out.p;
+            } else if (pl->npass == 1) {
+                dout_stride = N;
+            }
+            if ((rc = ntt_run_dev(*ctx, pl, ctx->ntt_in.p, d->n_in, d->n_in, dout, dout_stride, d->n_out,
+                                  ctx->ntt_work.p, cc, pcin, pcout, st)))
+                return rc;
+            CK(cudaEventRecord(ctx->ev[11], st));
+            if ((rc = copy2d(hout, d->out_stride, dout, dout_stride, d->n_out, cc, cudaMemcpyDeviceToHost, st))) return rc;
+        }
+        if (d->location == 0 || !d->stream) {
+            CK(cudaStreamSynchronize(st));
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
+            k_ms_total += ms;
+        }
+    }
+    CK(cudaEventRecord(ctx->ev[9], st));
+    if (d->location == 0 || !d->stream) {
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+        ctx->last_total_ms = ms;
+        ctx->last_kernel_ms = k_ms_total;
+    }
+    return B2_OK;
+}
+
+int b2_best_fft(void* a, const void* omega, uint32_t log_n) {
+    b2_ntt_desc d;
+    memset(&d, 0, sizeof d);
+    d.log_n = log_n;
+    d.omega = omega;
+    d.n_in = d.n_out = d.in_stride = d.out_stride = 1ull << log_n;
+    d.columns = 1;
+    d.in = a;
+    d.out = a;
+    return b2_ntt_exec(&d);
+}
+int b2_gpu_ifft(void* a, const void* omega_inv, uint32_t log_n, const void* divisor) {
+    if (!divisor) return fail(B2_ERR_ARG, "gpu_ifft: divisor is required");
+    b2_ntt_desc d;
+    memset(&d, 0, sizeof d);
+    d.log_n = log_n;
+    d.omega = omega_inv;
+    d.divisor = divisor;
+    d.n_in = d.n_out = d.in_stride = d.out_stride = 1ull << log_n;
+    d.columns = 1;
+    d.in = a;
+    d.out = a;
+    return b2_ntt_exec(&d);
+}
+int b2_coeff_to_extended(const void* a, void* out, uint64_t columns, uint32_t k, uint32_t ext_k, const void* zeta,
+                         const void* zeta_sq, const void* ext_omega) {
+    if (!zeta || !zeta_sq || ext_k < k) return fail(B2_ERR_ARG, "coeff_to_extended: bad arguments");
+    char z[64];
+    memcpy(z, zeta, 32);
+    memcpy(z + 32, zeta_sq, 32);
+    b2_ntt_desc d;
+    memset(&d, 0, sizeof d);
+    d.log_n = ext_k;
+    d.omega = ext_omega;
+    d.coset_in = z;
+    d.n_in = d.in_stride = 1ull << k;
+    d.n_out = d.out_stride = 1ull << ext_k;
+    d.columns = columns;
+    d.in = a;
+    d.out = out;
+    return b2_ntt_exec(&d);
+}
+int b2_extended_to_coeff(const void* a, void* out, uint64_t n_out, uint32_t ext_k, const void* zeta,
+                         const void* zeta_sq, const void* ext_omega_inv, const void* ext_divisor) {
+    if (!zeta || !zeta_sq || !ext_divisor) return fail(B2_ERR_ARG, "extended_to_coeff: bad arguments");
+    char z[64];  // moving out of the coset: {zeta^2, zeta}
+    memcpy(z, zeta_sq, 32);
+    memcpy(z + 32, zeta, 32);
+    b2_ntt_desc d;
+    memset(&d, 0, sizeof d);
+    d.log_n = ext_k;
+    d.omega = ext_omega_inv;
+    d.divisor = ext_divisor;
+    d.coset_out = z;
+    d.n_in = d.in_stride = 1ull << ext_k;
+    d.n_out = d.out_stride = n_out;
+    d.columns = 1;
+    d.in = a;
+    d.out = out;
+    return b2_ntt_exec(&d);
+}
+int b2_divide_by_vanishing_poly(void* a, uint32_t ext_k, const void* t_evaluations, uint32_t t_len) {
+    if (!a || !t_evaluations || t_len == 0 || (t_len & (t_len - 1))) return fail(B2_ERR_ARG, "divide: bad arguments");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const uint64_t N = 1ull << ext_k;
+    if ((rc = ctx->ntt_in.reserve(N * 32))) return rc;
+    if ((rc = ctx->ntt_out.reserve((size_t)t_len * 32))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->ntt_in.p, a, N * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ntt_out.p, t_evaluations, (size_t)t_len * 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(*ctx, fr_scale_periodic_kernel, (unsigned)std::min<uint64_t>((N + 255) / 256, ctx->sms * 16), 256, 0, st,
+           ctx->ntt_in.as<uint4>(), ctx->ntt_out.as<Fr>(), (unsigned long long)N, t_len - 1);
+    CK(cudaMemcpyAsync(a, ctx->ntt_in.p, N * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+// ---- fused commit + iNTT
+int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits, int do_ifft,
+                    const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96) {
+    if (!columns_data || !out_jac96 || n == 0) return fail(B2_ERR_ARG, "commit_batch: bad arguments");
+    if (do_ifft && (!omega_inv || !divisor || n != ((size_t)1 << log_n)))
+        return fail(B2_ERR_ARG, "commit_batch: ifft needs n == 2^log_n, omega_inv and divisor");
+    if (columns == 0) return B2_OK;
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (n > s.n) return fail(B2_ERR_ARG, "commit_batch: column length %zu exceeds SRS length %zu", n, s.n);
+    DeviceCtx* ctx;
+    if ((rc = ctx_get(&ctx))) return rc;
+    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    NttPlan* pl = nullptr;
+    if (do_ifft && (rc = ntt_get_plan(*ctx, omega_inv, divisor, log_n, &pl))) return rc;
+    const size_t col_bytes = n * 32;
+    uint64_t sub = std::max<uint64_t>(1, ntt_scratch_limit() / (2 * col_bytes));
+    sub = std::min<uint64_t>(sub, columns);
+    if ((rc = ctx->partials.reserve(columns * 96))) return rc;
+    if (max_bits > 254) max_bits = 254;
+    float kms = 0;
+    int bound_flag_any = 0;
+    CK(cudaEventRecord(ctx->ev[8], st));
+    for (uint64_t c0 = 0; c0 < columns; c0 += sub) {
+        const uint64_t cc = std::min<uint64_t>(sub, columns - c0);
+        if ((rc = ctx->ntt_in.reserve(cc * col_bytes))) return rc;
+        if (do_ifft && pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
+        char* h = (char*)columns_data + c0 * col_bytes;
+        CK(cudaMemcpyAsync(ctx->ntt_in.p, h, cc * col_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[10], st));
+        for (uint64_t c = 0; c < cc; c++) {
+            char* dout = ctx->partials.as<char>() + (c0 + c) * 96;
+            if (max_bits == 0) {
+                if ((rc = write_identity(*ctx, dout, st))) return rc;
+                continue;
+            }
+            // the bound flag is sticky across the whole batch (reset once, read once)
+            if ((rc = msm_run_split(*ctx, s.d, ctx->ntt_in.as<char>() + c * col_bytes, n, max_bits, dout, st, false,
+                                    c0 == 0 && c == 0)))
+                return rc;
+        }
+        if (do_ifft) {
+            if ((rc = ntt_run_dev(*ctx, pl, ctx->ntt_in.p, n, n, ctx->ntt_in.p, n, n, ctx->ntt_work.p, cc, nullptr,
+                                  nullptr, st)))
+                return rc;
+        }
+        CK(cudaEventRecord(ctx->ev[11], st));
+        if (do_ifft) CK(cudaMemcpyAsync(h, ctx->ntt_in.p, cc * col_bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
+        kms += ms;
+    }
+    CK(cudaMemcpyAsync(out_jac96, ctx->partials.p, columns * 96, cudaMemcpyDeviceToHost, st));
+    if (max_bits != 0) CK(cudaMemcpyAsync(&bound_flag_any, ctx->errflag.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ctx->ev[9], st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+    ctx->last_total_ms = ms;
+    ctx->last_kernel_ms = kms;
+    if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
+    return B2_OK;
+}
+
+int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void* omega_inv, const void* divisor,
+                    uint32_t log_n, void* out_jac96) {
+    return b2_commit_batch(srs, coeffs, 1, (size_t)1 << log_n, max_bits, 1, omega_inv, divisor, log_n, out_jac96);
+}
+
+// ---- memory helpers
+int b2_host_alloc(size_t bytes, void** out) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    cudaError_t e = cudaMallocHost(out, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2_ERR_OOM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return B2_OK;
+}
+int b2_host_free(void* p) {
+    CK(cudaFreeHost(p));
+    return B2_OK;
+}
+int b2_dev_alloc(size_t bytes, void** out) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    CK(cudaMalloc(out, bytes));
+    return B2_OK;
+}
+int b2_dev_free(void* p) {
+    CK(cudaFree(p));
+    return B2_OK;
+}
+int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    return B2_OK;
+}
+int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    CK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
+    return B2_OK;
+}
+
+// ---- diagnostics
+int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out) {
+    if (!a || !b || !out || op < 0 || op > 3 || field < 0 || field > 1) return fail(B2_ERR_ARG, "field_vec: bad arguments");
+    if (n == 0) return B2_OK;
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->ntt_in.reserve(n * 32))) return rc;
+    if ((rc = ctx->ntt_work.reserve(n * 32))) return rc;
+    if ((rc = ctx->ntt_out.reserve(n * 32))) return rc;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->ntt_in.p, a, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->ntt_work.p, b, n * 32, cudaMemcpyHostToDevice, st));
+    if (field == 0)
+        LAUNCH(*ctx, field_vec_kernel<FrParams>, (unsigned)((n + 127) / 128), 128, 0, st, ctx->ntt_in.as<uint4>(),
+               ctx->ntt_work.as<uint4>(), ctx->ntt_out.as<uint4>(), (unsigned long long)n, op);
+    else
+        LAUNCH(*ctx, field_vec_kernel<FqParams>, (unsigned)((n + 127) / 128), 128, 0, st, ctx->ntt_in.as<uint4>(),
+               ctx->ntt_work.as<uint4>(), ctx->ntt_out.as<uint4>(), (unsigned long long)n, op);
+    CK(cudaMemcpyAsync(out, ctx->ntt_out.p, n * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    cudaStream_t st = ctx->stream;
+    const int iters = 2000, ILP = 4;
+    const int blocks = ctx->sms * 8, threads = 256;
+    LAUNCH(*ctx, imad_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<uint4>(), 50);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, imad_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<uint4>(), iters);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        double muls = (double)blocks * threads * (double)iters * ILP;
+        double rate = muls / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    if (modmuls_per_s) *modmuls_per_s = best;
+    if (wide_macs_per_s) *wide_macs_per_s = best * 136.0;
+    return B2_OK;
+}
+
+int b2_last_timing(double* kernel_ms, double* total_ms) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
+    if (total_ms) *total_ms = ctx->last_total_ms;
+    return B2_OK;
+}
+int b2_last_msm_phases(double* phases) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    for (int i = 0; i < 8; i++) phases[i] = ctx->phases[i];
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,431 @@
+// msm.cuh -- BN254 G1 multi-scalar multiplication (signed-digit windowed Pippenger).
+//
+// Replaces multiexp_serial / best_multiexp / gpu_multiexp_single_gpu_with_bound
+// (halo2_proofs/src/arithmetic.rs:20-108, 334-367, 465-492).  The result is the same
+// group element the reference computes; it is returned normalised (Z = 1), and parity is
+// defined on the affine point because projective representatives are not unique
+// (the reference normalises before the transcript, plonk/prover.rs:130,304,484).
+//
+// Pipeline (all on one stream, no host round trips):
+//   1. msm_digits_kernel   scalar: Montgomery -> canonical, + K (signed-digit bias), W digits
+//                          of c bits; writes one 32-bit code per (window, scalar) and
+//                          histograms bucket sizes (counting sort, pass 1)
+//   2. msm_scan_kernel     exclusive scan of the W * 2^(c-1) bucket sizes
+//   3. msm_scatter_kernel  counting sort, pass 2: point index | sign<<31 into bucket order
+//   4. msm_accumulate_kernel  fixed-size chunks of the bucket-sorted entry list per thread
+//                          (perfect load balance for any scalar distribution: zeros,
+//                          16-bit advice values, all-equal scalars); mixed XYZZ adds;
+//                          buckets wholly inside a chunk are written directly, the <= 2
+//                          buckets cut by a chunk boundary become partial records
+//   5. msm_fixup_kernel    sums the partial records of each cut bucket
+//   6. msm_reduce_kernel   per window: sum_j (j+1) * B_j with per-thread running sums,
+//                          a block-level suffix scan (no scalar multiplications) and one
+//                          small multiply per block
+//   7. msm_final_kernel    sums block results per window, Horner over windows
+//                          (c doublings each), normalises to Z = 1
+#pragma once
+#include "curve.cuh"
+
+namespace b2 {
+
+struct MsmGeom {
+    uint32_t c;          // window bits
+    uint32_t W;          // number of windows
+    uint32_t B;          // buckets per window = 2^(c-1)
+    uint32_t n;          // number of scalars / points
+};
+
+// ---------------------------------------------------------------- 1. digits + histogram
+// code[w * n + i] = (|d| << 1) | (d < 0), 0 when the digit is zero.
+// Signed digits: add K = sum_{w < W-1} 2^(c*w + c - 1) once, then digit_w = window_w - 2^(c-1)
+// for w < W-1 and the top window is taken unsigned (it has at most c-1 significant bits
+// because W = floor(max_bits / c) + 1).
+__global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ codes,
+                                  uint32_t* __restrict__ counts, MsmGeom g, uint32_t max_bits,
+                                  int* __restrict__ err_flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    Fr s = fp_from_mont<FrParams>(fp_load_nc<FrParams>(scalars + 2ull * i));
+    // contract check: scalar < 2^max_bits
+    if (max_bits < 256) {
+        uint32_t over = 0;
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            const int lo_bit = l * 32;
+            if ((int)max_bits <= lo_bit) over |= s.v[l];
+            else if ((int)max_bits < lo_bit + 32) over |= s.v[l] >> (max_bits - lo_bit);
+        }
+        if (over) atomicExch(err_flag, 1);
+    }
+    // s += K
+    {
+        uint32_t k[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) k[l] = 0;
+        for (uint32_t w = 0; w + 1 < g.W; w++) {
+            const uint32_t bit = g.c * w + g.c - 1;
+            if (bit < 256) k[bit >> 5] |= 1u << (bit & 31);
+        }
+        asm("add.cc.u32 %0, %0, %8;\n\t"
+            "addc.cc.u32 %1, %1, %9;\n\t"
+            "addc.cc.u32 %2, %2, %10;\n\t"
+            "addc.cc.u32 %3, %3, %11;\n\t"
+            "addc.cc.u32 %4, %4, %12;\n\t"
+            "addc.cc.u32 %5, %5, %13;\n\t"
+            "addc.cc.u32 %6, %6, %14;\n\t"
+            "addc.u32 %7, %7, %15;"
+            : "+r"(s.v[0]), "+r"(s.v[1]), "+r"(s.v[2]), "+r"(s.v[3]), "+r"(s.v[4]), "+r"(s.v[5]), "+r"(s.v[6]),
+              "+r"(s.v[7])
+            : "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
+    }
+    const uint32_t half = 1u << (g.c - 1);
+    const uint32_t mask = (g.c == 32) ? 0xffffffffu : ((1u << g.c) - 1u);
+    for (uint32_t w = 0; w < g.W; w++) {
+        const uint32_t bit = g.c * w;
+        uint32_t raw = 0;
+        if (bit < 256) {
+            const uint32_t limb = bit >> 5, off = bit & 31;
+            uint64_t two = s.v[limb];
+            if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+            raw = (uint32_t)(two >> off) & mask;
+        }
+        int32_t d = (w + 1 < g.W) ? (int32_t)raw - (int32_t)half : (int32_t)raw;
+        uint32_t code = 0;
+        if (d != 0) {
+            const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+            code = (mag << 1) | (d < 0 ? 1u : 0u);
+            atomicAdd(&counts[(size_t)w * g.B + (mag - 1)], 1u);
+        }
+        codes[(size_t)w * g.n + i] = code;
+    }
+}
+
+// ---------------------------------------------------------------- 2. exclusive scan
+// Single block; offsets[0..total] with offsets[total] = number of entries.  Also copies the
+// exclusive offsets into `cursor` for the scatter pass.
+__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                uint32_t* __restrict__ cursor, uint32_t total) {
+    __shared__ uint32_t sums[1024];
+    const uint32_t t = threadIdx.x, T = blockDim.x;
+    const uint32_t per = (total + T - 1) / T;
+    const uint32_t lo = t * per, hi = min(lo + per, total);
+    uint32_t s = 0;
+    for (uint32_t j = lo; j < hi; j++) s += counts[j];
+    sums[t] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over T partial sums
+    for (uint32_t d = 1; d < T; d <<= 1) {
+        uint32_t v = (t >= d) ? sums[t - d] : 0;
+        __syncthreads();
+        sums[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = (t == 0) ? 0 : sums[t - 1];
+    for (uint32_t j = lo; j < hi; j++) {
+        offsets[j] = run;
+        cursor[j] = run;
+        run += counts[j];
+    }
+    if (t == T - 1) offsets[total] = sums[T - 1];
+}
+
+// ---------------------------------------------------------------- 3. scatter
+__global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint32_t* __restrict__ cursor,
+                                   uint32_t* __restrict__ sorted, MsmGeom g) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = blockIdx.y;
+    if (i >= g.n) return;
+    const uint32_t code = codes[(size_t)w * g.n + i];
+    if (code == 0) return;
+    const uint32_t mag = code >> 1;
+    const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.B + (mag - 1)], 1u);
+    sorted[pos] = i | ((code & 1u) << 31);
+}
+
+// ---------------------------------------------------------------- 4. accumulate
+__device__ __forceinline__ Affine msm_load_point(const char* __restrict__ bases, uint32_t stride, uint32_t ent) {
+    const uint32_t idx = ent & 0x7fffffffu;
+    Affine p = affine_load(bases + (size_t)idx * stride);
+    if (ent >> 31) p.y = fp_neg<FqParams>(p.y);
+    return p;
+}
+
+// Thread t owns entries [t*L, min((t+1)*L, E)).  offsets[] has nb+1 entries.
+// part_pt[2t], part_pt[2t+1]: head / tail partial sums; part_bucket = bucket id or 0xffffffff.
+__global__ void __launch_bounds__(128)
+msm_accumulate_kernel(const char* __restrict__ bases, uint32_t base_stride, const uint32_t* __restrict__ sorted,
+                      const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
+                      uint32_t nthreads_total, char* __restrict__ buckets, char* __restrict__ part_pt,
+                      uint32_t* __restrict__ part_bucket) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads_total) return;
+    const uint32_t E = offsets[nb];
+    const uint64_t lo64 = (uint64_t)t * chunk;
+    uint32_t slot = 0;
+    part_bucket[2 * t] = 0xffffffffu;
+    part_bucket[2 * t + 1] = 0xffffffffu;
+    if (lo64 >= E) return;
+    const uint32_t lo = (uint32_t)lo64;
+    const uint32_t hi = (uint32_t)min((uint64_t)E, lo64 + chunk);
+
+    // bucket containing entry lo: largest b with offsets[b] <= lo  (then skip empties)
+    uint32_t bl = 0, bh = nb;  // invariant: offsets[bl] <= lo < offsets[bh]
+    while (bh - bl > 1) {
+        const uint32_t mid = (bl + bh) >> 1;
+        if (offsets[mid] <= lo) bl = mid; else bh = mid;
+    }
+    uint32_t b = bl;
+    uint32_t e = lo;
+    while (e < hi) {
+        const uint32_t b_begin = offsets[b];
+        const uint32_t b_end = offsets[b + 1];
+        if (b_end <= e) { b++; continue; }       // empty bucket (or already consumed)
+        const uint32_t stop = min(b_end, hi);
+        XYZZ acc = XYZZ::identity();
+        Affine p = msm_load_point(bases, base_stride, sorted[e]);
+        for (; e < stop; e++) {
+            Affine cur = p;
+            if (e + 1 < stop) p = msm_load_point(bases, base_stride, sorted[e + 1]);  // prefetch
+            xyzz_madd(acc, cur);
+        }
+        if (b_begin >= lo && b_end <= hi) {
+            xyzz_store(buckets + (size_t)b * 128, acc);
+        } else {
+            // cut bucket: at most one at the head and one at the tail of a chunk
+            xyzz_store(part_pt + (size_t)(2 * t + slot) * 128, acc);
+            part_bucket[2 * t + slot] = b;
+            slot++;
+        }
+        b++;
+    }
+}
+
+// ---------------------------------------------------------------- 5. fix-up of cut buckets
+// Partial records are ordered by (thread, slot) and their bucket ids are non-decreasing, so
+// the records of one bucket are contiguous (unused slots, id 0xffffffff, may be interleaved).
+__global__ void msm_fixup_kernel(const char* __restrict__ part_pt, const uint32_t* __restrict__ part_bucket,
+                                 uint32_t nrec, char* __restrict__ buckets) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrec) return;
+    const uint32_t b = part_bucket[r];
+    if (b == 0xffffffffu) return;
+    // leader = first record of this bucket
+    for (int64_t q = (int64_t)r - 1; q >= 0; q--) {
+        const uint32_t pb = part_bucket[q];
+        if (pb == 0xffffffffu) continue;
+        if (pb == b) return;  // not the leader
+        break;
+    }
+    XYZZ acc = xyzz_load(part_pt + (size_t)r * 128);
+    for (uint32_t q = r + 1; q < nrec; q++) {
+        const uint32_t nb_ = part_bucket[q];
+        if (nb_ == 0xffffffffu) continue;
+        if (nb_ != b) break;
+        XYZZ o = xyzz_load(part_pt + (size_t)q * 128);
+        xyzz_add_ni(acc, o);
+    }
+    xyzz_store(buckets + (size_t)b * 128, acc);
+}
+
+// ---------------------------------------------------------------- 6. bucket reduction
+// Block of RT threads handles RT*RM consecutive buckets of one window; bucket j (0-based
+// inside the window) has weight j+1.  Output per block: sum_j (j+1) B_j over its range.
+constexpr int MSM_RT = 128;  // threads per reduce block
+constexpr int MSM_RM = 4;    // buckets per thread
+
+__global__ void __launch_bounds__(MSM_RT)
+msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__ offsets, MsmGeom g,
+                  uint32_t blocks_per_window, char* __restrict__ block_out) {
+    extern __shared__ uint4 red_smem[];   // MSM_RT XYZZ points (128 B each)
+    char* sm = reinterpret_cast<char*>(red_smem);
+    const uint32_t w = blockIdx.x / blocks_per_window;
+    const uint32_t blk = blockIdx.x % blocks_per_window;
+    const uint32_t t = threadIdx.x;
+    const uint32_t j0 = (blk * MSM_RT + t) * MSM_RM;   // first bucket of this thread (in-window)
+    XYZZ run = XYZZ::identity(), sum = XYZZ::identity();
+    for (int i = MSM_RM - 1; i >= 0; i--) {
+        const uint32_t j = j0 + (uint32_t)i;
+        if (j < g.B) {
+            const size_t gb = (size_t)w * g.B + j;
+            if (offsets[gb + 1] > offsets[gb]) {
+                XYZZ bk = xyzz_load(buckets + gb * 128);
+                xyzz_add_ni(run, bk);
+            }
+        }
+        xyzz_add_ni(sum, run);
+    }
+    // thread value: sum_i (i+1) B_{j0+i} = sum;  run = sum_i B_{j0+i}
+    // block total = sum_t [ sum_t + (t*RM) * run_t ]  (+ blk offset handled below)
+    // S_t = suffix sum of run over threads >= t  ->  sum_t t*run_t = sum_{t>=1} S_t
+    xyzz_store(sm + (size_t)t * 128, run);
+    __syncthreads();
+    for (uint32_t d = 1; d < MSM_RT; d <<= 1) {
+        XYZZ o = XYZZ::identity();
+        const bool has = (t + d < MSM_RT);
+        if (has) o = xyzz_load(sm + (size_t)(t + d) * 128);
+        __syncthreads();
+        if (has) {
+            xyzz_add_ni(run, o);
+            xyzz_store(sm + (size_t)t * 128, run);
+        }
+        __syncthreads();
+    }
+    // run == S_t now.  total_run = S_0.
+    XYZZ total_run = xyzz_load(sm);
+    __syncthreads();
+    // v_t = sum_t + RM * S_t (t >= 1)
+    XYZZ v = sum;
+    if (t >= 1) {
+        XYZZ s = run;
+#pragma unroll 1
+        for (int i = 1; i < MSM_RM; i <<= 1) xyzz_dbl_ni(s);
+        xyzz_add_ni(v, s);
+    }
+    xyzz_store(sm + (size_t)t * 128, v);
+    __syncthreads();
+    for (uint32_t d = MSM_RT / 2; d >= 1; d >>= 1) {
+        if (t < d) {
+            XYZZ o = xyzz_load(sm + (size_t)(t + d) * 128);
+            xyzz_add_ni(v, o);
+            xyzz_store(sm + (size_t)t * 128, v);
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        // + (blk * RT * RM) * total_run
+        XYZZ off = total_run;
+        xyzz_mul_small(off, blk * MSM_RT * MSM_RM);
+        xyzz_add_ni(v, off);
+        xyzz_store(block_out + (size_t)blockIdx.x * 128, v);
+    }
+}
+
+// ---------------------------------------------------------------- 7. window combine
+// One block of 32 threads: lane w sums the block results of window w, then lane 0 runs
+// Horner over windows and normalises.  out: 96 B Jacobian with Z = 1 (or the identity
+// (0, 1, 0)).  If `accumulate` != 0 the previous value of `out` is added first
+// (used when an MSM is split into several launches).
+__global__ void msm_final_kernel(const char* __restrict__ block_out, MsmGeom g, uint32_t blocks_per_window,
+                                 char* __restrict__ window_sums, char* __restrict__ out, int normalise) {
+    const uint32_t w = threadIdx.x;
+    if (w < g.W) {
+        XYZZ acc = XYZZ::identity();
+        for (uint32_t b = 0; b < blocks_per_window; b++) {
+            XYZZ o = xyzz_load(block_out + ((size_t)w * blocks_per_window + b) * 128);
+            xyzz_add_ni(acc, o);
+        }
+        xyzz_store(window_sums + (size_t)w * 128, acc);
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    XYZZ acc = XYZZ::identity();
+    for (int w2 = (int)g.W - 1; w2 >= 0; w2--) {
+        for (uint32_t i = 0; i < g.c; i++) xyzz_dbl_ni(acc);
+        XYZZ o = xyzz_load(window_sums + (size_t)w2 * 128);
+        xyzz_add_ni(acc, o);
+    }
+    if (normalise) {
+        Affine a = xyzz_to_affine(acc);
+        if (acc.is_identity()) {
+            fp_store<FqParams>(out, Fq::zero());
+            fp_store<FqParams>(out + 32, Fq::one());
+            fp_store<FqParams>(out + 64, Fq::zero());
+        } else {
+            fp_store<FqParams>(out, a.x);
+            fp_store<FqParams>(out + 32, a.y);
+            fp_store<FqParams>(out + 64, Fq::one());
+        }
+    } else {
+        xyzz_store(out, acc);
+    }
+}
+
+// Sum of `count` Jacobian points (96 B each) -> normalised Jacobian.  Single thread.
+// (combine of per-GPU / per-chunk partials: arithmetic.rs:428-435 does this on the host)
+__global__ void g1_sum_kernel(const char* __restrict__ pts, uint32_t count, char* __restrict__ out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t i = 0; i < count; i++) {
+        const char* p = pts + (size_t)i * 96;
+        XYZZ o = xyzz_from_jacobian(fp_load<FqParams>(p), fp_load<FqParams>(p + 32), fp_load<FqParams>(p + 64));
+        xyzz_add_ni(acc, o);
+    }
+    Affine a = xyzz_to_affine(acc);
+    if (acc.is_identity()) {
+        fp_store<FqParams>(out, Fq::zero());
+        fp_store<FqParams>(out + 32, Fq::one());
+        fp_store<FqParams>(out + 64, Fq::zero());
+    } else {
+        fp_store<FqParams>(out, a.x);
+        fp_store<FqParams>(out + 32, a.y);
+        fp_store<FqParams>(out + 64, Fq::one());
+    }
+}
+
+// ---------------------------------------------------------------- synthetic SRS
+// bases[i] = [h(seed, i)] G with h a 64-bit splitmix64 hash (never 0), affine, Montgomery.
+// Used by the benchmark and the full-size property tests: MSM(s, bases) must equal
+// [sum_i s_i * h_i mod r] G, which the host can check with O(n) field work.
+__device__ __forceinline__ unsigned long long msm_splitmix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__global__ void __launch_bounds__(128)
+srs_synth_kernel(char* __restrict__ bases, unsigned long long n, unsigned long long first, unsigned long long seed) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long h = msm_splitmix(seed ^ msm_splitmix(first + i));
+    if (h == 0) h = 1;
+    Affine gen;
+    gen.x = Fq::one();
+    gen.y = fp_dbl<FqParams>(Fq::one());
+    XYZZ acc = XYZZ::identity();
+    for (int b = 63; b >= 0; b--) {
+        xyzz_dbl_ni(acc);
+        if ((h >> b) & 1ull) xyzz_madd(acc, gen);
+    }
+    Affine a = xyzz_to_affine(acc);
+    fp_store<FqParams>(bases + i * 64, a.x);
+    fp_store<FqParams>(bases + i * 64 + 32, a.y);
+}
+
+// ---------------------------------------------------------------- element-wise test kernels
+// op: 0 mul, 1 add, 2 sub, 3 sqr
+template <class P>
+__global__ void field_vec_kernel(const uint4* a, const uint4* b, uint4* o, unsigned long long n, int op) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<P> x = fp_load<P>(a + 2 * i), y = fp_load<P>(b + 2 * i), r;
+    switch (op) {
+    case 0: r = fp_mul<P>(x, y); break;
+    case 1: r = fp_add<P>(x, y); break;
+    case 2: r = fp_sub<P>(x, y); break;
+    default: r = fp_sqr<P>(x); break;
+    }
+    fp_store<P>(o + 2 * i, r);
+}
+
+// Wide-MAC throughput probe: every thread runs `iters` dependent Montgomery products on
+// ILP independent chains (the MSM / NTT instruction mix: IMAD.WIDE with carry).
+template <int ILP>
+__global__ void __launch_bounds__(256) imad_probe_kernel(uint4* sink, int iters) {
+    Fq x[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+        x[j] = Fq::one();
+        x[j].v[0] ^= threadIdx.x + j;
+    }
+    Fq y = Fq::r2();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = fp_mul<FqParams>(x[j], y);
+    }
+    Fq acc = x[0];
+#pragma unroll
+    for (int j = 1; j < ILP; j++) acc = fp_add<FqParams>(acc, x[j]);
+    if (acc.v[0] == 0x12345678u && acc.v[7] == 0x9abcdef0u) fp_store<FqParams>(sink, acc);
+}
+
+}  // namespace b2

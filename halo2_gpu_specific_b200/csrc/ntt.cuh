@@ -1,0 +1,250 @@
+// ntt.cuh -- radix-2 NTT over BN254 Fr, natural order in -> natural order out.
+//
+// Replaces best_fft / gpu_fft / gpu_ifft (halo2_proofs/src/arithmetic.rs:495-645) and
+// the transforms of EvaluationDomain (poly/domain.rs:233-414).  Field elements are
+// canonical, so any exact DFT is bit-identical to the reference's DIT loop.
+//
+// Decomposition: N = 2^k is split into P digits of m_1..m_P bits (m_i <= 12).  Pass p
+// runs, for every setting of the other index bits, one 2^m_p-point sub-NTT that lives
+// entirely in shared memory (bit-reversed on load, DIT stages grouped three at a time so
+// each thread keeps 8 elements in registers between shared-memory exchanges), then
+// multiplies by the inter-pass twiddle w_N^(i_{p+1} * o_partial) taken from a two-level
+// table (w^lo * w^hi).  Passes 1..P-1 work in place; the last pass writes each result to
+// its digit-reversed (= natural) position, so it needs out != in when P > 1.
+//
+// Fused into the passes (reference does each as a separate sweep):
+//   first pass : zero padding n_in -> 2^k (domain.rs:280) and the period-3 coset scaling
+//                {1, zeta, zeta^2}[i % 3] (distribute_powers_zeta, domain.rs:382-398)
+//   1st twiddle: the iNTT divisor 2^-k (domain.rs:404-409) is folded into the hi table
+//   last pass  : the inverse period-3 scaling and truncation of extended_to_coeff
+//                (domain.rs:341-347)
+#pragma once
+#include "fp.cuh"
+
+namespace b2 {
+
+constexpr int NTT_MAX_PASSES = 4;
+
+struct NttPassArgs {
+    const uint4* in;
+    uint4* out;
+    unsigned long long in_col_stride;   // elements between batch columns
+    unsigned long long out_col_stride;
+    unsigned long long n_in;            // first pass: elements present in `in` (rest read as zero)
+    unsigned long long n_out;           // last pass: only outputs with index < n_out are stored
+    uint32_t log_n;
+    uint32_t m;                         // digit size of this pass
+    uint32_t s_lo;                      // number of index bits below this digit
+    uint32_t pass, npass;
+    uint32_t mm[NTT_MAX_PASSES];        // digit sizes m_1..m_P
+    uint32_t tw_h;                      // split of the two-level table: e = hi * 2^tw_h + lo
+    const Fr* tw_sub;                   // w_{2^m}^j, j < 2^(m-1)
+    const Fr* tw_lo;                    // w_N^j, j < 2^tw_h
+    const Fr* tw_hi;                    // w_N^(j * 2^tw_h) (times the divisor for pass 0 of an iNTT)
+    int coset_in;                       // first pass: multiply x[i] by zin[i % 3 - 1]
+    int coset_out;                      // last pass : multiply X[o] by zout[o % 3 - 1]
+    int scale_out;                      // last pass : multiply everything by `scale` (P == 1 iNTT)
+    Fr zin1, zin2, zout1, zout2, scale;
+};
+
+__device__ __forceinline__ uint32_t ntt_swz(uint32_t i, uint32_t hs) {
+    return i ^ ((i >> 3) & 7u) ^ ((i >> hs) & 7u);
+}
+
+__device__ __forceinline__ Fr sm_ld(const uint4* lo, const uint4* hi, uint32_t idx) {
+    uint4 a = lo[idx], b = hi[idx];
+    Fr r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+}
+__device__ __forceinline__ void sm_st(uint4* lo, uint4* hi, uint32_t idx, const Fr& x) {
+    lo[idx] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    hi[idx] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+}
+
+__device__ __forceinline__ void ntt_bfly(Fr& a, Fr& b, const Fr& tw) {
+    Fr t = fp_mul<FrParams>(b, tw);
+    b = fp_sub<FrParams>(a, t);
+    a = fp_add<FrParams>(a, t);
+}
+__device__ __forceinline__ void ntt_bfly1(Fr& a, Fr& b) {  // twiddle == 1
+    Fr t = b;
+    b = fp_sub<FrParams>(a, t);
+    a = fp_add<FrParams>(a, t);
+}
+
+// One group of R consecutive DIT stages (s0+1 .. s0+R) on the shared-memory tile.
+template <int R, bool FIRST>
+__device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* __restrict__ tw, uint32_t m,
+                                         uint32_t s0, uint32_t hs) {
+    constexpr int E = 1 << R;
+    const uint32_t items = 1u << (m - R);
+    for (uint32_t w = threadIdx.x; w < items; w += blockDim.x) {
+        const uint32_t low = w & ((1u << s0) - 1u);
+        const uint32_t base = ((w >> s0) << (s0 + R)) | low;
+        Fr x[E];
+#pragma unroll
+        for (int q = 0; q < E; q++) x[q] = sm_ld(s_lo4, s_hi4, ntt_swz(base + ((uint32_t)q << s0), hs));
+#pragma unroll
+        for (int st = 0; st < R; st++) {
+            // stage s = s0 + st + 1: partner differs in bit `st` of q; twiddle exponent
+            // jj = low + (q & (2^st - 1)) * 2^s0, table index jj << (m - s)
+            const uint32_t sh = m - (s0 + st + 1);
+#pragma unroll
+            for (int q = 0; q < E; q++) {
+                if (q & (1 << st)) continue;
+                const int lowq = q & ((1 << st) - 1);
+                if (FIRST && lowq == 0) {
+                    ntt_bfly1(x[q], x[q | (1 << st)]);
+                } else {
+                    const uint32_t jj = low + ((uint32_t)lowq << s0);
+                    Fr t = fp_load_nc<FrParams>(tw + ((size_t)jj << sh));
+                    ntt_bfly(x[q], x[q | (1 << st)], t);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < E; q++) sm_st(s_lo4, s_hi4, ntt_swz(base + ((uint32_t)q << s0), hs), x[q]);
+    }
+}
+
+// digit-reverse: position bits (high -> low) hold o_1 .. o_np; the natural output index
+// has o_1 as its LEAST significant digit.
+__device__ __forceinline__ uint64_t ntt_digit_reverse(uint64_t v, const uint32_t* mm, int np) {
+    uint64_t r = 0;
+    uint32_t placed = 0;
+    // peel digits from the low end of v: o_np first
+    uint32_t total = 0;
+    for (int i = 0; i < np; i++) total += mm[i];
+    uint32_t below = total;
+    (void)placed;
+    for (int i = np - 1; i >= 0; i--) {
+        uint64_t d = v & ((1ull << mm[i]) - 1ull);
+        v >>= mm[i];
+        below -= mm[i];          // bits occupied by digits 0..i-1 in the reversed number
+        r |= d << below;
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
+    extern __shared__ uint4 ntt_smem[];
+    const uint32_t m = a.m, N = 1u << m;
+    uint4* s_lo4 = ntt_smem;
+    uint4* s_hi4 = ntt_smem + N;
+    const uint32_t hs = (m >= 9) ? (m - 3) : 31u;
+
+    const uint64_t line = blockIdx.x;
+    const uint64_t col = blockIdx.y;
+    const uint64_t L = line & ((1ull << a.s_lo) - 1ull);
+    const uint64_t H = line >> a.s_lo;
+    const uint64_t base_pos = (H << (m + a.s_lo)) | L;
+    const uint4* in = a.in + 2ull * col * a.in_col_stride;
+    uint4* out = a.out + 2ull * col * a.out_col_stride;
+    const bool first = (a.pass == 0), last = (a.pass + 1 == a.npass);
+
+    // ---- load (bit-reversed into the tile) ----
+    for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
+        const uint64_t pos = base_pos + ((uint64_t)j << a.s_lo);
+        Fr x;
+        if (!first || pos < a.n_in) {
+            x = fp_load<FrParams>(in + 2ull * pos);
+            if (first && a.coset_in) {
+                const uint32_t r3 = (uint32_t)(pos % 3ull);
+                if (r3 == 1) x = fp_mul<FrParams>(x, a.zin1);
+                else if (r3 == 2) x = fp_mul<FrParams>(x, a.zin2);
+            }
+        } else {
+            x = Fr::zero();
+        }
+        const uint32_t jr = __brev(j) >> (32 - m);
+        sm_st(s_lo4, s_hi4, ntt_swz(jr, hs), x);
+    }
+    __syncthreads();
+
+    // ---- DIT stages, three per shared-memory round trip ----
+    uint32_t s0 = 0;
+    {
+        const uint32_t r = m < 3 ? m : 3;
+        if (r == 3) ntt_step<3, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
+        else if (r == 2) ntt_step<2, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
+        else ntt_step<1, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
+        s0 = r;
+        __syncthreads();
+    }
+    while (s0 < m) {
+        const uint32_t r = (m - s0) < 3 ? (m - s0) : 3;
+        if (r == 3) ntt_step<3, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
+        else if (r == 2) ntt_step<2, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
+        else ntt_step<1, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
+        s0 += r;
+        __syncthreads();
+    }
+
+    // ---- store ----
+    if (!last) {
+        // twiddle exponent = i_next * digit_reverse(H, j) * 2^(k - (m_1+..+m_{p+1}))
+        const uint32_t m_next = a.mm[a.pass + 1];
+        const uint64_t i_next = L >> (a.s_lo - m_next);
+        const uint32_t shift = a.s_lo - m_next;
+        const uint64_t lo_mask = (1ull << a.tw_h) - 1ull;
+        for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
+            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(j, hs));
+            const uint64_t opart = ntt_digit_reverse((H << m) | j, a.mm, (int)a.pass + 1);
+            const uint64_t e = (i_next * opart) << shift;
+            if (e != 0) {
+                Fr t = fp_mul<FrParams>(fp_load_nc<FrParams>(a.tw_lo + (e & lo_mask)),
+                                        fp_load_nc<FrParams>(a.tw_hi + (e >> a.tw_h)));
+                x = fp_mul<FrParams>(x, t);
+            } else if (first) {
+                x = fp_mul<FrParams>(x, fp_load_nc<FrParams>(a.tw_hi));  // carries the iNTT divisor (or 1)
+            }
+            const uint64_t pos = base_pos + ((uint64_t)j << a.s_lo);
+            fp_store<FrParams>(out + 2ull * pos, x);
+        }
+    } else {
+        for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
+            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(j, hs));
+            const uint64_t o = ntt_digit_reverse((H << m) | j, a.mm, (int)a.npass);
+            if (o >= a.n_out) continue;
+            if (a.scale_out) x = fp_mul<FrParams>(x, a.scale);
+            if (a.coset_out) {
+                const uint32_t r3 = (uint32_t)(o % 3ull);
+                if (r3 == 1) x = fp_mul<FrParams>(x, a.zout1);
+                else if (r3 == 2) x = fp_mul<FrParams>(x, a.zout2);
+            }
+            fp_store<FrParams>(out + 2ull * o, x);
+        }
+    }
+}
+
+// out[j] = base^(j * mult) * (scale if has_scale), j < count
+__global__ void ntt_pow_table_kernel(Fr* out, const Fr base, unsigned long long mult, uint32_t count,
+                                     int has_scale, const Fr scale) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    unsigned long long e = (unsigned long long)j * mult;
+    Fr acc = Fr::one();
+    Fr b = base;
+    while (e) {
+        if (e & 1ull) acc = fp_mul<FrParams>(acc, b);
+        b = fp_sqr<FrParams>(b);
+        e >>= 1;
+    }
+    if (has_scale) acc = fp_mul<FrParams>(acc, scale);
+    fp_store<FrParams>(out + j, acc);
+}
+
+// a[i] *= t[i % period]  (divide_by_vanishing_poly, poly/domain.rs:354-373)
+__global__ void fr_scale_periodic_kernel(uint4* a, const Fr* __restrict__ t, unsigned long long n, uint32_t period_mask) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        Fr x = fp_load<FrParams>(a + 2ull * i);
+        x = fp_mul<FrParams>(x, fp_load_nc<FrParams>(t + (i & period_mask)));
+        fp_store<FrParams>(a + 2ull * i, x);
+    }
+}
+
+}  // namespace b2

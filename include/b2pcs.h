@@ -1,0 +1,174 @@
+/*
+ * b2pcs.h -- C ABI of the B200-native polynomial-commitment engine (BN254 / KZG).
+ *
+ * This is the drop-in boundary for the one hot path of halo2_proofs as used by
+ * DelphinusLab/halo2-gpu-specific: the G1 MSM behind best_multiexp / Params::commit*,
+ * and the radix-2 NTT over Fr behind best_fft / EvaluationDomain::{lagrange_to_coeff,
+ * coeff_to_extended, extended_to_coeff}.  The reference has no C ABI: under its `cuda`
+ * feature the Rust functions cited below transmute their slices to BN254 types and call
+ * the ec-gpu-gen Rust API.  Each entry point here names the reference function whose body
+ * it replaces (paths relative to halo2_proofs/src); INTEGRATION.md shows the Rust
+ * `extern "C"` block and the shim bodies.
+ *
+ * Data layout (all little-endian, identical to the reference's in-memory types):
+ *   Fr, Fq      4 x u64 limbs, Montgomery form a * 2^256 mod p          (32 bytes)
+ *   G1Affine    x || y in Fq; the identity is encoded as (0, 0)         (64 bytes;
+ *               b2_srs_register takes a stride so a 72-byte struct with a trailing
+ *               flag also works)
+ *   G1          X || Y || Z Jacobian, x = X/Z^2, y = Y/Z^3; identity Z=0 (96 bytes).
+ *               Results are returned NORMALISED (Z = 1 in Montgomery form, or
+ *               (0, 1, 0) for the identity): projective representatives are not
+ *               unique and the reference always normalises before the transcript.
+ *
+ * Conventions: every function returns B2_OK (0) or a negative error code and never
+ * panics/aborts; b2_last_error() returns a thread-local message.  The library never
+ * keeps a caller pointer past the call.  All functions are thread-safe; calls on one
+ * device are serialised internally (the reference serialises per device with
+ * acquire_gpu/release_gpu, arithmetic.rs:313-331).  There is NO CPU fallback: without a
+ * usable CUDA device every compute entry point returns B2_ERR_CUDA.
+ */
+#ifndef B2PCS_H
+#define B2PCS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)      /* bad argument / length mismatch (reference: assert_eq!, arithmetic.rs:466,569) */
+#define B2_ERR_CUDA (-2)     /* CUDA runtime error (reference: .unwrap()/.expect panics, arithmetic.rs:356-360,509) */
+#define B2_ERR_OOM (-3)      /* device or pinned-host allocation failed */
+#define B2_ERR_BOUND (-4)    /* a scalar exceeded the max_bits contract of *_with_bound */
+#define B2_ERR_HANDLE (-5)   /* unknown / freed handle */
+
+typedef uint64_t b2_handle_t;
+
+/* ---- library / device ------------------------------------------------------------- */
+int b2_version(void);
+const char* b2_last_error(void);
+int b2_device_count(void);
+/* Select the device used by subsequent calls from this host thread (default 0).
+ * Reference: the device index popped from GPU_LOCK (plonk/prover.rs:56-74). */
+int b2_set_device(int device);
+int b2_get_device(void);
+int b2_synchronize(void);
+/* number of kernels this library launched on the current device since the last reset */
+uint64_t b2_launch_count(int reset);
+
+/* ---- SRS (bases resident in HBM) -------------------------------------------------- */
+/* Upload n affine points once; they stay resident until b2_srs_free.  Replaces the
+ * per-call re-upload of `bases` in gpu_multiexp_single_gpu_with_bound
+ * (arithmetic.rs:349-360) for Params::g / Params::g_lagrange (poly/commitment.rs:23-29). */
+int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_t* out);
+/* Synthetic bases for benchmarks / property tests: bases[i] = [h(seed, first+i)] G with
+ * h = 64-bit splitmix64 hash, generated on the device. */
+int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t* out);
+int b2_srs_len(b2_handle_t srs, size_t* n);
+int b2_srs_read(b2_handle_t srs, size_t offset, size_t count, void* out_affine64);
+int b2_srs_free(b2_handle_t srs);
+
+/* ---- MSM -------------------------------------------------------------------------- */
+/* sum_i scalars[i] * srs[offset + i], i < n.  max_bits bounds every scalar
+ * (scalar < 2^max_bits); pass 254 (Fr::NUM_BITS) when unknown.  n == 0 or max_bits == 0
+ * gives the identity.
+ * Replaces gpu_multiexp_single_gpu_with_bound (arithmetic.rs:334-367) and, through
+ * Params::commit / commit_lagrange / commit_lagrange_with_bound
+ * (poly/commitment.rs:129-142,199-222), best_multiexp_gpu_cond (arithmetic.rs:442-458).
+ * Zero scalars contribute nothing, so the CPU-side zero filtering of
+ * commit_lagrange_with_bound (commitment.rs:204-212) is not needed. */
+int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96);
+/* Same with `scalars` and `out_jac96` in device memory, asynchronous on `stream`
+ * (a cudaStream_t, NULL = the library's per-device stream). */
+int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, uint32_t max_bits,
+               void* d_out_jac96, void* stream);
+/* best_multiexp (arithmetic.rs:465-492) with both slices on the host: uploads the bases
+ * for this call only.  Prefer b2_srs_register + b2_msm. */
+int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_jac96);
+/* Sum of `count` Jacobian points (96 B each): the combine of per-GPU partials that
+ * gpu_multiexp_bound does on the host (arithmetic.rs:428-435). */
+int b2_g1_sum(const void* jac96, size_t count, void* out_jac96);
+
+/* ---- NTT -------------------------------------------------------------------------- */
+typedef struct b2_ntt_desc {
+    uint32_t log_n;        /* transform length 2^log_n, 1 <= log_n <= 28 (Fr::S) */
+    uint32_t location;     /* 0: in/out are host pointers; 1: device pointers */
+    const void* omega;     /* 32 B, primitive 2^log_n-th root of unity */
+    const void* divisor;   /* NULL, or 32 B multiplied into every output (iNTT 2^-k) */
+    const void* coset_in;  /* NULL, or 64 B {z1, z2}: x[i] *= z_(i%3) for i%3 != 0 before the transform */
+    const void* coset_out; /* NULL, or 64 B {z1, z2}: X[o] *= z_(o%3) for o%3 != 0 after it */
+    uint64_t n_in;         /* elements present per input column (<= 2^log_n); the rest is zero */
+    uint64_t n_out;        /* outputs kept per column (<= 2^log_n) */
+    uint64_t columns;      /* independent transforms in this batch */
+    const void* in;
+    uint64_t in_stride;    /* elements between input columns */
+    void* out;             /* may equal `in` */
+    uint64_t out_stride;
+    void* stream;          /* location 1 only: cudaStream_t or NULL */
+} b2_ntt_desc;
+/* General entry point; the functions below are thin wrappers over it. */
+int b2_ntt_exec(const b2_ntt_desc* desc);
+
+/* best_fft / gpu_fft (arithmetic.rs:495-512, 546-554): in-place natural-order NTT */
+int b2_best_fft(void* a, const void* omega, uint32_t log_n);
+/* gpu_ifft (arithmetic.rs:515-534) = EvaluationDomain::ifft (poly/domain.rs:400-414):
+ * NTT with omega_inv, then every element times `divisor`.  lagrange_to_coeff[_st]
+ * (poly/domain.rs:233-266) is this with (omega_inv, ifft_divisor, k). */
+int b2_gpu_ifft(void* a, const void* omega_inv, uint32_t log_n, const void* divisor);
+/* EvaluationDomain::coeff_to_extended (poly/domain.rs:270-287) for `columns` polynomials
+ * of 2^k coefficients each (contiguous): coset scaling by {1, zeta, zeta^2}[i%3],
+ * zero-extension to 2^ext_k, forward NTT with extended_omega.  `out` receives
+ * columns * 2^ext_k elements. */
+int b2_coeff_to_extended(const void* a, void* out, uint64_t columns, uint32_t k, uint32_t ext_k,
+                         const void* zeta, const void* zeta_sq, const void* ext_omega);
+/* EvaluationDomain::extended_to_coeff (poly/domain.rs:328-350): iNTT of size 2^ext_k,
+ * scaling by {1, zeta^2, zeta}[i%3], truncation to n_out = n * (j - 1) elements. */
+int b2_extended_to_coeff(const void* a, void* out, uint64_t n_out, uint32_t ext_k, const void* zeta,
+                         const void* zeta_sq, const void* ext_omega_inv, const void* ext_divisor);
+/* EvaluationDomain::divide_by_vanishing_poly (poly/domain.rs:354-373):
+ * a[i] *= t_evaluations[i % t_len], t_len a power of two, in place (host pointers). */
+int b2_divide_by_vanishing_poly(void* a, uint32_t ext_k, const void* t_evaluations, uint32_t t_len);
+
+/* ---- fused commit + iNTT ---------------------------------------------------------- */
+/* gpu_multiexp_bound_and_fft (arithmetic.rs:375-410) = Params::commit_lagrange_and_ifft
+ * (poly/commitment.rs:144-170): one upload of the 2^log_n Lagrange values, MSM against
+ * srs[0 .. 2^log_n) and in-place iNTT (omega = omega_inv, divisor = 2^-k) of the same
+ * device-resident vector.  `coeffs` is overwritten with the coefficient form. */
+int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void* omega_inv,
+                    const void* divisor, uint32_t log_n, void* out_jac96);
+/* The prover's per-column batching (plonk/prover.rs:293-299, 470-501, 561-593): `columns`
+ * contiguous columns of n scalars each, one commitment per column against the same SRS
+ * (out: columns * 96 B); with do_ifft != 0 each column is also replaced by its iNTT. */
+int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits,
+                    int do_ifft, const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96);
+
+/* ---- memory helpers --------------------------------------------------------------- */
+int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
+int b2_host_free(void* p);
+int b2_dev_alloc(size_t bytes, void** out);
+int b2_dev_free(void* p);
+int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
+int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+
+/* ---- diagnostics used by tests / bench -------------------------------------------- */
+/* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a). */
+int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out);
+/* Measures the device's sustained 32x32->64 multiply-accumulate rate with the kernels'
+ * own instruction mix (carry-chained IMAD.WIDE Montgomery products); returns wide MACs/s
+ * counted as 136 per product (64 product + 64 reduction + 8 for m = t*inv). */
+int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s);
+/* Timing of the last b2_msm / b2_ntt_exec / b2_commit_batch on this device, CUDA events
+ * on the launching stream: kernel-only ms and (host variants) total ms incl. copies. */
+int b2_last_timing(double* kernel_ms, double* total_ms);
+/* Per-phase kernel times of the last MSM (ms): digits, scan, scatter, accumulate, fixup,
+ * reduce, final.  `phases` must hold 8 doubles. */
+int b2_last_msm_phases(double* phases);
+/* Window configuration the MSM would use for (n, max_bits): c, number of windows. */
+int b2_msm_config(size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PCS_H */

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    import __graft_entry__ as g
+    g.build()
+    yield
+
+
+@pytest.fixture(scope="session")
+def gpu():
+    from halo2_gpu_specific_b200 import _lib
+    _lib.require_gpu()
+    _lib.set_device(0)
+    return _lib

@@ -1,0 +1,222 @@
+"""GPU parity: MSM / Params commits vs the oracle, bit-exact on the (normalised) point, through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+import halo2_gpu_specific_b200 as h2
+from halo2_gpu_specific_b200.arithmetic import Srs
+from oracle import bn254 as o
+from oracle import cref
+
+pytestmark = pytest.mark.gpu
+FIX = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fixtures.npz"))
+Q_ONE = np.array(o.fq_encode_one(1), dtype=np.uint64)
+
+
+def _affine(jac):
+    """engine output is normalised: Z = 1 (Montgomery) or the identity (0, 1, 0)"""
+    jac = np.asarray(jac).reshape(12)
+    if not jac[8:].any():
+        return None
+    assert np.array_equal(jac[8:], Q_ONE), "result must be normalised to Z = 1"
+    return o.g1_affine_decode(jac[:8].reshape(1, 8))[0]
+
+
+def _bases(n, seed):
+    ks = np.array([o._to_limbs(x) for x in o.random_fr(n, seed)], dtype=np.uint64) if n <= 4096 else None
+    if ks is None:
+        ks = cref.from_mont(0, cref.random_fr_mont(n, seed))
+    return cref.g1_mul_gen(ks)
+
+
+def _want(scalars, bases):
+    return o.g1_jacobian_decode(cref.best_multiexp(scalars, bases, 8))
+
+
+def test_golden_fixture(gpu):
+    got = h2.best_multiexp(FIX["msm_n512_scalars"], FIX["msm_n512_bases"])
+    assert _affine(got) == o.g1_jacobian_decode(FIX["msm_n512_out"])
+
+
+def test_kat_30G(gpu):
+    bases = o.g1_affine_encode([o.g1_mul(o.G1_GEN, i) for i in range(1, 5)])
+    got = h2.best_multiexp(o.fr_encode([1, 2, 3, 4]), bases)
+    assert _affine(got) == (0x036083bfa420b15a4c11f66a3cffd55318b019feb45f833a876e93848625f5ae,
+                            0x2630c348c019c3edb74fe62a7e921361aae9621988223514d56ca8b36adc9e36)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 31, 32, 33, 255, 1000, 4097, (1 << 14) + 1, (1 << 16), (1 << 17) - 1])
+def test_msm_matches_oracle_random(gpu, n):
+    """n = 2^14 + 1 is the reference's GPU threshold (arithmetic.rs:446); 2^k - 1 is kate_division's length"""
+    scalars = cref.random_fr_mont(n, 0xB2000003 + n)
+    bases = _bases(n, 0x51 + n)
+    assert _affine(h2.best_multiexp(scalars, bases)) == _want(scalars, bases)
+
+
+def test_msm_resident_srs_slices(gpu):
+    n = 5000
+    scalars = cref.random_fr_mont(n, 3)
+    bases = _bases(n, 4)
+    srs = Srs.register(bases)
+    assert np.array_equal(srs.read(10, 5), bases[10:15])
+    assert _affine(h2.best_multiexp(scalars, srs)) == _want(scalars, bases)
+    assert _affine(h2.best_multiexp(scalars[:1234], srs[0:1234])) == _want(scalars[:1234], bases[:1234])
+    assert _affine(h2.best_multiexp(scalars[:1000], srs[77:1077])) == _want(scalars[:1000], bases[77:1077])
+    with pytest.raises(gpu.B2Error):
+        h2.best_multiexp(scalars, srs[0:10])
+    srs.free()
+
+
+def test_msm_adversarial_complete_addition(gpu):
+    """all-equal bases, (P, -P) with equal digits, zero scalars, r-1, top window all ones, identity base"""
+    G = o.G1_GEN
+    P = o.g1_mul(G, 12345)
+    # 1. everything cancels
+    bases = [P] * 300 + [o.g1_neg(P)] * 300
+    sc = [7] * 600
+    assert _affine(h2.best_multiexp(o.fr_encode(sc), o.g1_affine_encode(bases))) is None
+    # 2. all-equal bases, assorted scalars -> [sum] P  (forces P + P inside buckets)
+    sc2 = [0, 1, 2, o.R_MOD - 1, (1 << 253) + 5, 0, (1 << 254) - 1 - (1 << 254) % 1] + [3] * 500 + [0xFFFF] * 100
+    sc2 = [s % o.R_MOD for s in sc2]
+    bases2 = [P] * len(sc2)
+    assert _affine(h2.best_multiexp(o.fr_encode(sc2), o.g1_affine_encode(bases2))) == o.g1_mul(P, sum(sc2) % o.R_MOD)
+    # 3. identity bases are skipped; zero scalars contribute nothing
+    bases3 = [None, G, None, P] * 50
+    sc3 = [5, 0, 9, 11] * 50
+    assert _affine(h2.best_multiexp(o.fr_encode(sc3), o.g1_affine_encode(bases3))) == o.g1_mul(P, 11 * 50)
+    # 4. all-zero scalars
+    assert _affine(h2.best_multiexp(o.fr_encode([0] * 100), o.g1_affine_encode([P] * 100))) is None
+    # 5. scalars whose every window is 2^c - 1 (carry ripples through all signed windows)
+    sc5 = [o.R_MOD - 1, (1 << 253) - 1, (1 << 240) - 1, (1 << 16) - 1, (1 << 15), (1 << 15) - 1] * 20
+    pts5 = _bases(len(sc5), 99)
+    assert _affine(h2.best_multiexp(o.fr_encode(sc5), pts5)) == _want(o.fr_encode(sc5), pts5)
+
+
+@pytest.mark.parametrize("bits", [1, 8, 15, 16, 17, 32, 64])
+def test_msm_with_bound(gpu, bits):
+    """gpu_multiexp_single_gpu_with_bound (arithmetic.rs:334-367): max_bits is a contract"""
+    n = 3000
+    scalars = cref.random_fr_small_mont(n, 0x77 + bits, bits)
+    scalars[::3] = 0  # advice columns are mostly small / zero (commitment.rs:204-212 filters zeros)
+    bases = _bases(n, 0x78)
+    srs = Srs.register(bases)
+    want = _want(scalars, bases)
+    assert _affine(h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, bits)) == want
+    assert _affine(h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, 254)) == want
+    srs.free()
+
+
+def test_msm_bound_violation_is_an_error(gpu):
+    n = 100
+    scalars = cref.random_fr_mont(n, 5)
+    srs = Srs.register(_bases(n, 6))
+    with pytest.raises(gpu.B2Error) as e:
+        h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, 16)
+    assert e.value.code == gpu.B2_ERR_BOUND
+    srs.free()
+
+
+def test_skewed_distribution_one_hot_bucket(gpu):
+    """every scalar equal: one bucket per window holds all points (chunks cut it many times)"""
+    n = 1 << 15
+    scalars = np.tile(o.fr_encode([0x0123456789ABCDEF0123456789ABCDEF0123456789ABCDEF])[0], (n, 1))
+    bases = _bases(n, 0x99)
+    assert _affine(h2.best_multiexp(scalars, bases)) == _want(scalars, bases)
+
+
+def test_params_commit_identity_and_variants(gpu):
+    """poly/commitment.rs:480-495 test_commit_lagrange on the GPU path, plus the commit variants"""
+    K = 6
+    params = h2.Params(K, FIX["params_k6_g"], FIX["params_k6_g_lagrange"])
+    dom = h2.EvaluationDomain(1, K)
+    a = o.fr_encode(list(range(1 << K)))
+    c_lag = params.commit_lagrange(a)
+    assert _affine(c_lag) == o.g1_jacobian_decode(FIX["params_k6_commit_lagrange"])
+    b = dom.lagrange_to_coeff(a.copy())
+    assert np.array_equal(params.commit(b), c_lag)
+    assert np.array_equal(params.commit_lagrange_with_bound(a, 6), c_lag)
+    coeffs, c2 = params.commit_lagrange_and_ifft(a.copy(), dom.omega_inv, dom.ifft_divisor)
+    assert np.array_equal(coeffs, b) and np.array_equal(c2, c_lag)
+    # shorter polynomial than n (kate_division output has n - 1 coefficients)
+    assert _affine(params.commit(b[:-1])) == _want(b[:-1], FIX["params_k6_g"][:-1])
+    params.free()
+
+
+def test_commit_batch(gpu):
+    k, cols = 11, 5
+    n = 1 << k
+    bases = _bases(n, 0x31)
+    params = h2.Params(k, bases, bases)
+    dom = h2.EvaluationDomain(5, k)
+    x = cref.random_fr_mont(cols * n, 0x32).reshape(cols, n, 4)
+    want_pts = [_want(x[c], bases) for c in range(cols)]
+    out = params.commit_lagrange_batch(x.copy())
+    assert [_affine(p) for p in out] == want_pts
+    y = x.copy()
+    out2 = params.commit_lagrange_batch(y, ifft=(dom.omega_inv, dom.ifft_divisor))
+    assert [_affine(p) for p in out2] == want_pts
+    for c in range(cols):
+        assert np.array_equal(y[c], cref.ifft(x[c], dom.omega_inv, dom.ifft_divisor, k, 8))
+    params.free()
+
+
+def test_g1_sum(gpu):
+    pts = [o.g1_mul(o.G1_GEN, s) for s in (5, 7, o.R_MOD - 12, 0)]
+    enc = np.stack([o.g1_jacobian_encode(p) for p in pts])
+    assert _affine(h2.arithmetic.g1_sum(enc)) is None
+    assert _affine(h2.arithmetic.g1_sum(enc[:2])) == o.g1_mul(o.G1_GEN, 12)
+    assert _affine(h2.arithmetic.g1_sum(np.stack([enc[0], enc[0]]))) == o.g1_mul(o.G1_GEN, 10)
+
+
+def _splitmix(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15))
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def synthetic_multipliers(n, first, seed):
+    """h_i of b2_srs_synthetic: bases[i] = [h_i] G"""
+    with np.errstate(over="ignore"):
+        idx = np.arange(first, first + n, dtype=np.uint64)
+        h = _splitmix(np.uint64(seed) ^ _splitmix(idx))
+    h[h == 0] = 1
+    return h
+
+
+def test_synthetic_srs_points(gpu):
+    srs = Srs.synthetic(64, first_index=1000, seed=0xB2000003)
+    h = synthetic_multipliers(64, 1000, 0xB2000003)
+    got = o.g1_affine_decode(srs.read())
+    for i in (0, 1, 63):
+        assert got[i] == o.g1_mul(o.G1_GEN, int(h[i]))
+    srs.free()
+
+
+@pytest.mark.parametrize("logn,bits", [(20, 254), (22, 254), (22, 16)])
+def test_full_size_property(gpu, logn, bits):
+    """BASELINE sizes: MSM(s, [h_i]G) must equal [sum s_i h_i mod r] G (linearity; O(n) host check)"""
+    n = 1 << logn
+    seed = 0xB2000003
+    srs = Srs.synthetic(n, 0, seed)
+    if bits == 254:
+        scalars = cref.random_fr_mont(n, seed)
+    else:
+        scalars = cref.random_fr_small_mont(n, seed, bits)
+        scalars[::2] = 0  # 50 % zeros column
+    got = _affine(h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, bits))
+    h = synthetic_multipliers(n, 0, seed)
+    s_can = cref.from_mont(0, scalars)
+    # sum s_i * h_i mod r, limb-wise with Python ints on column sums
+    total = 0
+    hh = h.astype(object)
+    for limb in range(4):
+        col = s_can[:, limb]
+        # split to 32-bit halves so that products fit comfortably in Python ints via object dot
+        lo = (col & np.uint64(0xFFFFFFFF)).astype(object)
+        hi = (col >> np.uint64(32)).astype(object)
+        total += (int(np.dot(lo, hh)) + (int(np.dot(hi, hh)) << 32)) << (64 * limb)
+    want = o.g1_mul(o.G1_GEN, total % o.R_MOD)
+    assert got == want
+    srs.free()
