@@ -185,6 +185,21 @@ def synthetic_multipliers(n, first, seed):
     return h
 
 
+def dot_mod_r(s_can, h):
+    """sum_i s_i * h_i as a Python int: 16-bit pieces so every partial dot fits in uint64 (n <= 2^26)"""
+    total = 0
+    h16 = [((h >> np.uint64(16 * b)) & np.uint64(0xFFFF)) for b in range(4)]
+    for limb in range(4):
+        col = s_can[:, limb]
+        for a in range(4):
+            piece = (col >> np.uint64(16 * a)) & np.uint64(0xFFFF)
+            if not piece.any():
+                continue
+            for b in range(4):
+                total += int(np.dot(piece, h16[b])) << (64 * limb + 16 * a + 16 * b)
+    return total
+
+
 def test_synthetic_srs_points(gpu):
     srs = Srs.synthetic(64, first_index=1000, seed=0xB2000003)
     h = synthetic_multipliers(64, 1000, 0xB2000003)
@@ -207,16 +222,7 @@ def test_full_size_property(gpu, logn, bits):
         scalars[::2] = 0  # 50 % zeros column
     got = _affine(h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, bits))
     h = synthetic_multipliers(n, 0, seed)
-    s_can = cref.from_mont(0, scalars)
-    # sum s_i * h_i mod r, limb-wise with Python ints on column sums
-    total = 0
-    hh = h.astype(object)
-    for limb in range(4):
-        col = s_can[:, limb]
-        # split to 32-bit halves so that products fit comfortably in Python ints via object dot
-        lo = (col & np.uint64(0xFFFFFFFF)).astype(object)
-        hi = (col >> np.uint64(32)).astype(object)
-        total += (int(np.dot(lo, hh)) + (int(np.dot(hi, hh)) << 32)) << (64 * limb)
+    total = dot_mod_r(cref.from_mont(0, scalars), h)
     want = o.g1_mul(o.G1_GEN, total % o.R_MOD)
     assert got == want
     srs.free()
