@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- BN254 MSM Mpts/s (+ Fr NTT Melem/s) at 2^22 on 1..8 B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--logn 22]
+
+A "step" is one pass of the commitment hot path over one synthetic column per GPU: one MSM of
+2^22 uniformly random Fr scalars against that rank's resident point-range shard of the SRS
+(north_star: "MSM point ranges per GPU with one partial G1 point combined per rank"), the NCCL
+all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GPU work is fixed
+("weak" scaling): at N ranks the job is one MSM of N * 2^22 points.
+
+  value   whole-job points/s with the scalars already resident in HBM; device time (CUDA events
+          on the launching stream, max over ranks)
+  e2e     same metric through the public host API (arithmetic.best_multiexp on a pinned host
+          column against the resident Srs): H2D of the scalars and D2H of the point are inside
+          the timed region
+  roofline  dominant kernel (msm_accumulate): integer-pipe roofline, measured with CUDA events
+          inside this run; peak = this run's own carry-chained IMAD.WIDE probe
+  ntt     N == 1 only: 64 columns of a k=22 forward NTT, device resident: Melem/s, HBM GB/s vs
+          the measured copy peak, and the same integer roofline
+  cpu_baseline / --impl reference: the C restatement of the reference's rayon path
+          (oracle/cpu_ref.c = arithmetic.rs:20-108, 465-492) on the box's host cores
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "BN254 G1 MSM throughput at 2^22 points per GPU"
+UNIT = "Mpts/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region"""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w_max": max(pw), "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def random_montgomery_scalars(n: int, seed: int, pinned=None) -> np.ndarray:
+    """uniform 252-bit values used directly as Montgomery residues (< r, so every one is a valid
+    encoding of a uniformly distributed field element).  No oracle involved."""
+    rng = np.random.default_rng(seed)
+    out = pinned if pinned is not None else np.empty((n, 4), dtype=np.uint64)
+    out[:] = rng.integers(0, 2**64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] &= np.uint64((1 << 60) - 1)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """--impl reference: the reference's CPU path (C restatement; the Rust crate cannot be built
+    offline) on all host cores, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cref
+    cores = os.cpu_count() or 1
+    n_full = 1 << args.logn
+    # calibrate on 2^16, then pick the largest power-of-two sample that keeps the run bounded
+    cal = 1 << 16
+    ks = np.zeros((n_full, 4), dtype=np.uint64)
+    ks[:, 0] = np.arange(1, n_full + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    t0 = time.time()
+    bases_cal = cref.g1_mul_gen(ks[:cal], cores)
+    gen_rate = cal / (time.time() - t0)
+    sc = cref.random_fr_mont(cal, 0xB2000003)
+    t0 = time.time()
+    cref.best_multiexp(sc, bases_cal, cores)
+    rate = cal / (time.time() - t0)
+    budget_s = 150.0
+    total_steps = args.steps + args.warmup
+    sample = n_full
+    while sample > cal and (sample / gen_rate + total_steps * sample / rate) > budget_s:
+        sample >>= 1
+    # bases [k_i] G with 64-bit k_i (cheap to generate; MSM cost does not depend on the point values)
+    bases = cref.g1_mul_gen(ks[:sample], cores)
+    scalars = cref.random_fr_mont(sample, 0xB2000003)
+    for _ in range(args.warmup):
+        cref.best_multiexp(scalars, bases, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cref.best_multiexp(scalars, bases, cores)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt / 1e6
+    sample_desc = f"MSM of 2^{sample.bit_length() - 1} of the 2^{args.logn} points per step ({cores} threads, chunk = n/T)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+        "config": {"workload": f"BN254 G1 MSM, 2^{args.logn} uniformly random Fr scalars (best_multiexp, arithmetic.rs:465-492)",
+                   "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "C restatement of halo2_proofs/src/arithmetic.rs (oracle/cpu_ref.c), not the Rust binary: no rustc/cargo "
+                "in the image and the reference's arithmetic crate is an un-vendored git dependency",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_engine(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    import halo2_gpu_specific_b200 as h2
+    from halo2_gpu_specific_b200 import _lib
+    from halo2_gpu_specific_b200.arithmetic import Srs
+    from halo2_gpu_specific_b200 import parallel
+
+    _lib.require_gpu()  # no CPU fallback: fail loudly
+    torch.cuda.set_device(local)
+    _lib.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    n = 1 << args.logn
+    seed = 0xB2000003
+
+    # --- inputs: this rank's point range of the SRS (resident) and its slice of the scalar vector
+    srs = Srs.synthetic(n, first_index=rank * n, seed=seed)
+    h_scalars = _lib.pinned_empty((n, 4))
+    random_montgomery_scalars(n, seed + rank, pinned=h_scalars)
+    d_scalars = torch.from_numpy(h_scalars.view(np.int64)).to(dev)
+    d_partial = torch.zeros(12, dtype=torch.int64, device=dev)
+    d_gather = torch.zeros(12 * world, dtype=torch.int64, device=dev)
+    d_result = torch.zeros(12, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    def step_resident():
+        _lib.check(L.b2_msm_dev(srs.handle, 0, ctypes.c_void_p(d_scalars.data_ptr()), n, 254,
+                                ctypes.c_void_p(d_partial.data_ptr()), sp))
+        if world > 1:
+            dist.all_gather_into_tensor(d_gather, d_partial)
+            _lib.check(L.b2_g1_sum_dev(ctypes.c_void_p(d_gather.data_ptr()), world,
+                                       ctypes.c_void_p(d_result.data_ptr()), sp))
+
+    def step_e2e():
+        return parallel.sharded_msm(h_scalars, srs, 254)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- IMAD peak probe (integer roofline denominator), before the timed region
+    macs, muls = ctypes.c_double(), ctypes.c_double()
+    _lib.check(L.b2_imad_probe(ctypes.byref(macs), ctypes.byref(muls)))
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.b2_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    acc_ms = []
+    phase_sum = {}
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record(stream)
+    barrier()
+    launches = int(L.b2_launch_count(0))
+    dev_ms = ev0.elapsed_time(ev1)
+    # per-phase times of the last step (CUDA events recorded by the library on the same stream)
+    ph = _lib.last_msm_phases()
+    c_w = (ctypes.c_uint32(), ctypes.c_uint32())
+    L.b2_msm_config(n, 254, ctypes.byref(c_w[0]), ctypes.byref(c_w[1]))
+    c_bits, windows = c_w[0].value, c_w[1].value
+    # accumulate-kernel duration: measure it over several steps through the phase events
+    for _ in range(min(args.steps, 5)):
+        step_resident()
+        torch.cuda.synchronize()
+        p = _lib.last_msm_phases()
+        acc_ms.append(p["accumulate"])
+        for k_, v_ in p.items():
+            phase_sum[k_] = phase_sum.get(k_, 0.0) + v_
+    nph = max(len(acc_ms), 1)
+    phases_avg = {k_: v_ / nph for k_, v_ in phase_sum.items()}
+
+    # --- e2e through the public host API
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res_e2e = step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # consistency: the host-API result equals the device-resident result (same inputs)
+    step_resident()
+    torch.cuda.synchronize()
+    res_dev = (d_result if world > 1 else d_partial).cpu().numpy().view(np.uint64)
+    assert np.array_equal(res_dev, res_e2e), "device-resident and host-API results differ"
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    ntt = None
+    if world == 1 and not args.no_ntt:
+        ntt = bench_ntt(args, torch, dev, _lib, h2, float(muls.value))
+
+    if rank == 0:
+        hbm_peak, peak_src = _peaks()
+        total_pts = n * world * args.steps
+        value = total_pts / (dev_ms * 1e-3) / 1e6
+        acc = statistics.mean(acc_ms)
+        mac_per_launch = 128.0 * 10.0 * n * windows          # 10 mul-equivalents per mixed add
+        achieved = mac_per_launch / (acc * 1e-3) / 1e12
+        peak = float(macs.value) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32x8 (256-bit Montgomery integers)", "data": "synthetic",
+            "config": {
+                "workload": f"BN254 G1 MSM, 2^{args.logn} uniformly random Fr scalars per GPU against a resident "
+                            f"point-range shard of the SRS (gpu_multiexp_bound, arithmetic.rs:413-440); "
+                            f"one 96-byte partial per rank all-gathered over NCCL and summed",
+                "points_per_gpu": n, "window_bits": c_bits, "windows": windows, "parallelism": f"range-shard x{world}",
+                "cache": "inputs larger than L2: scalars 128 MiB + bases 256 MiB + sort buffers 512 MiB per step",
+                "timing": "CUDA events on the launching stream, max over ranks",
+            },
+            "e2e": {"value": total_pts / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
+                    "api": "halo2_gpu_specific_b200.parallel.sharded_msm (pinned host column -> b2_msm -> 96 B)"},
+            "gpu_launches": launches,
+            "roofline": {
+                "kernel": "msm_accumulate_kernel", "bound": "int", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
+                "frac": achieved / peak, "traffic": None,
+                "model": f"128 MACs x 10 mul-equivalents x n x W = {mac_per_launch:.3e} 32x32->64 MACs per launch "
+                         f"(SURVEY 8d), duration {acc:.3f} ms (CUDA events, mean of {len(acc_ms)})",
+                "peak_source": "b2_imad_probe in this run: carry-chained IMAD.WIDE Montgomery products, "
+                               f"{muls.value / 1e9:.1f} G modmul/s x 128",
+                "share_of_step": acc / phases_avg.get("total", acc),
+            },
+            "msm_phases_ms": phases_avg,
+            "clocks": clocks,
+            "hbm_peak": {"gbs": hbm_peak, "source": peak_src},
+        }
+        if ntt:
+            line["ntt"] = ntt
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
+    """64 columns, k = logn forward NTT, device resident (config 2 of BASELINE.json)"""
+    from halo2_gpu_specific_b200._lib import NttDesc
+    L = _lib.lib()
+    k = args.logn
+    n = 1 << k
+    cols = args.ntt_cols
+    dom = h2.EvaluationDomain(5, k)
+    g = torch.Generator(device=dev)
+    g.manual_seed(0xB2000002)
+    # 252-bit Montgomery residues generated on the device
+    x = torch.randint(-2**63, 2**63 - 1, (cols, n, 4), dtype=torch.int64, device=dev, generator=g)
+    x[:, :, 3] &= (1 << 60) - 1
+    stream = torch.cuda.current_stream()
+    d = NttDesc()
+    d.log_n, d.location = k, 1
+    d.omega = dom.omega.ctypes.data
+    d.n_in = d.n_out = d.in_stride = d.out_stride = n
+    d.columns = cols
+    d.in_ = d.out = x.data_ptr()
+    d.stream = stream.cuda_stream
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        _lib.check(L.b2_ntt_exec(ctypes.byref(d)))
+    torch.cuda.synchronize()
+    L.b2_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        _lib.check(L.b2_ntt_exec(ctypes.byref(d)))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    launches = int(L.b2_launch_count(0)) // steps
+    elems = cols * n
+    hbm_peak, peak_src = _peaks()
+    passes = launches
+    gbs = 64.0 * elems / (ms * 1e-3) / 1e9
+    macs = 64.0 * k * elems
+    # e2e: host pinned column batch through lagrange_to_coeff_batch (H2D + iNTT + D2H), 8 columns
+    ecols = 8
+    hx = _lib.pinned_empty((ecols, n, 4))
+    random_montgomery_scalars(ecols * n, 7, pinned=hx.reshape(-1, 4))
+    dom.lagrange_to_coeff_batch(hx)
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        dom.lagrange_to_coeff_batch(hx)
+    e2e_ms = (time.perf_counter() - t0) / reps * 1e3
+    _lib.pinned_free(hx)
+    return {
+        "metric": f"Fr NTT throughput at 2^{k}, {cols} columns, device resident", "value": elems / (ms * 1e-3) / 1e6,
+        "unit": "Melem/s", "ms_per_batch": ms, "passes": passes,
+        "roofline_hbm": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                         "model": "64 B per element per transform (one read + one write)", "peak_source": peak_src},
+        "roofline_int": {"bound": "int", "achieved": macs / (ms * 1e-3) / 1e12, "peak": modmuls_per_s * 128 / 1e12,
+                         "unit": "TMAC/s", "frac": (macs / (ms * 1e-3)) / (modmuls_per_s * 128),
+                         "model": "64 * log2(n) MACs per element (SURVEY 8d)"},
+        "e2e": {"value": ecols * n / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "columns": ecols,
+                "h2d_bytes": ecols * n * 32, "d2h_bytes": ecols * n * 32,
+                "api": "EvaluationDomain.lagrange_to_coeff_batch (pinned host columns, iNTT)"},
+    }
+
+
+def cpu_baseline(args):
+    """Bounded sample of the same workload on the host cores (C restatement of the rayon path)."""
+    from oracle import cref
+    cores = os.cpu_count() or 1
+    sample = 1 << min(args.logn, 18)
+    ks = np.zeros((sample, 4), dtype=np.uint64)
+    ks[:, 0] = np.arange(1, sample + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    bases = cref.g1_mul_gen(ks, cores)
+    scalars = cref.random_fr_mont(sample, 0xB2000003)
+    cref.best_multiexp(scalars[:4096], bases[:4096], cores)
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or (time.perf_counter() - t0 < 8.0 and reps < 20):
+        cref.best_multiexp(scalars, bases, cores)
+        reps += 1
+    dt = (time.perf_counter() - t0) / reps
+    k = min(args.logn, 20)
+    x = cref.random_fr_mont(1 << k, 0xB2000002)
+    from halo2_gpu_specific_b200 import _fr
+    om = _fr.to_mont(pow(_fr.ROOT_OF_UNITY, 1 << (28 - k), _fr.R_MOD))
+    t1 = time.perf_counter()
+    cref.best_fft(x, om, k, cores)
+    fft_dt = time.perf_counter() - t1
+    return {"value": sample / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"best_multiexp on 2^{sample.bit_length() - 1} of the 2^{args.logn} points, {reps} repetitions, "
+                      f"{cores} threads (oracle/cpu_ref.c, restatement of arithmetic.rs:20-108,465-492)",
+            "ntt": {"value": (1 << k) / fft_dt / 1e6, "unit": "Melem/s", "sample": f"best_fft_cpu k={k}, one column"}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--logn", type=int, default=22)
+    ap.add_argument("--ntt-cols", type=int, default=64)
+    ap.add_argument("--no-ntt", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "engine":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_engine(args)
+
+
+if __name__ == "__main__":
+    main()

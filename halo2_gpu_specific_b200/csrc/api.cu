@@ -649,6 +649,17 @@ int b2_g1_sum(const void* jac96, size_t count, void* out_jac96) {
     return B2_OK;
 }
 
+int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream) {
+    if (!d_out_jac96 || (count && !d_jac96)) return fail(B2_ERR_ARG, "g1_sum_dev: null pointer");
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    LAUNCH(*ctx, g1_sum_kernel, 1, 32, 0, st, (const char*)d_jac96, (uint32_t)count, (char*)d_out_jac96);
+    return B2_OK;
+}
+
 // ---- NTT
 int b2_ntt_exec(const b2_ntt_desc* d) {
     if (!d || !d->omega || !d->in || !d->out) return fail(B2_ERR_ARG, "ntt: null pointer");
@@ -973,7 +984,7 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
         if (rate > best) best = rate;
     }
     if (modmuls_per_s) *modmuls_per_s = best;
-    if (wide_macs_per_s) *wide_macs_per_s = best * 136.0;
+    if (wide_macs_per_s) *wide_macs_per_s = best * 128.0;
     return B2_OK;
 }
 

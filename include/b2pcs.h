@@ -90,6 +90,9 @@ int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_
 /* Sum of `count` Jacobian points (96 B each): the combine of per-GPU partials that
  * gpu_multiexp_bound does on the host (arithmetic.rs:428-435). */
 int b2_g1_sum(const void* jac96, size_t count, void* out_jac96);
+/* Same with device pointers, asynchronous on `stream` (NULL = the library stream): used after
+ * the NCCL all-gather of one partial per rank. */
+int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream);
 
 /* ---- NTT -------------------------------------------------------------------------- */
 typedef struct b2_ntt_desc {
@@ -156,8 +159,9 @@ int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 /* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a). */
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out);
 /* Measures the device's sustained 32x32->64 multiply-accumulate rate with the kernels'
- * own instruction mix (carry-chained IMAD.WIDE Montgomery products); returns wide MACs/s
- * counted as 136 per product (64 product + 64 reduction + 8 for m = t*inv). */
+ * own instruction mix (carry-chained IMAD.WIDE Montgomery products); returns modular
+ * multiplications per second and wide MACs/s counted as 128 per product (64 product + 64
+ * reduction terms, the accounting of SURVEY.md section 8d). */
 int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s);
 /* Timing of the last b2_msm / b2_ntt_exec / b2_commit_batch on this device, CUDA events
  * on the launching stream: kernel-only ms and (host variants) total ms incl. copies. */
