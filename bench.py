@@ -193,14 +193,19 @@ def run_engine(args):
 
     # --- inputs: this rank's point range of the SRS (resident) and its slice of the scalar vector
     srs = Srs.synthetic(n, first_index=rank * n, seed=seed)
+    if not args.no_precompute:
+        srs.precompute()   # window table of this rank's shard (one-off, like the SRS upload itself)
     h_scalars = _lib.pinned_empty((n, 4))
     random_montgomery_scalars(n, seed + rank, pinned=h_scalars)
     d_scalars = torch.from_numpy(h_scalars.view(np.int64)).to(dev)
     d_partial = torch.zeros(12, dtype=torch.int64, device=dev)
     d_gather = torch.zeros(12 * world, dtype=torch.int64, device=dev)
     d_result = torch.zeros(12, dtype=torch.int64, device=dev)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: the library launches on it, torch's events and NCCL order on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sp = ctypes.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
 
     def step_resident():
         _lib.check(L.b2_msm_dev(srs.handle, 0, ctypes.c_void_p(d_scalars.data_ptr()), n, 254,
@@ -243,9 +248,9 @@ def run_engine(args):
     dev_ms = ev0.elapsed_time(ev1)
     # per-phase times of the last step (CUDA events recorded by the library on the same stream)
     ph = _lib.last_msm_phases()
-    c_w = (ctypes.c_uint32(), ctypes.c_uint32())
-    L.b2_msm_config(n, 254, ctypes.byref(c_w[0]), ctypes.byref(c_w[1]))
-    c_bits, windows = c_w[0].value, c_w[1].value
+    c_w = (ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32())
+    L.b2_msm_config(srs.handle, n, 254, ctypes.byref(c_w[0]), ctypes.byref(c_w[1]), ctypes.byref(c_w[2]))
+    c_bits, windows, bucket_sets = c_w[0].value, c_w[1].value, c_w[2].value
     # accumulate-kernel duration: measure it over several steps through the phase events
     for _ in range(min(args.steps, 5)):
         step_resident()
@@ -271,7 +276,8 @@ def run_engine(args):
     # consistency: the host-API result equals the device-resident result (same inputs)
     step_resident()
     torch.cuda.synchronize()
-    res_dev = (d_result if world > 1 else d_partial).cpu().numpy().view(np.uint64)
+    res_dev = np.ascontiguousarray((d_result if world > 1 else d_partial).cpu().numpy().view(np.uint64))
+    _lib.check(L.b2_g1_normalize(_lib.ptr(res_dev), 1))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-API results differ"
 
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -299,7 +305,8 @@ def run_engine(args):
                 "workload": f"BN254 G1 MSM, 2^{args.logn} uniformly random Fr scalars per GPU against a resident "
                             f"point-range shard of the SRS (gpu_multiexp_bound, arithmetic.rs:413-440); "
                             f"one 96-byte partial per rank all-gathered over NCCL and summed",
-                "points_per_gpu": n, "window_bits": c_bits, "windows": windows, "parallelism": f"range-shard x{world}",
+                "points_per_gpu": n, "window_bits": c_bits, "windows": windows, "bucket_sets": bucket_sets,
+                "srs_window_table": not args.no_precompute, "parallelism": f"range-shard x{world}",
                 "cache": "inputs larger than L2: scalars 128 MiB + bases 256 MiB + sort buffers 512 MiB per step",
                 "timing": "CUDA events on the launching stream, max over ranks",
             },
@@ -344,6 +351,8 @@ def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
     x = torch.randint(-2**63, 2**63 - 1, (cols, n, 4), dtype=torch.int64, device=dev, generator=g)
     x[:, :, 3] &= (1 << 60) - 1
     stream = torch.cuda.current_stream()
+    assert stream.cuda_stream != 0
+    torch.cuda.synchronize()
     d = NttDesc()
     d.log_n, d.location = k, 1
     d.omega = dom.omega.ctypes.data
@@ -433,6 +442,7 @@ def main():
     ap.add_argument("--ntt-cols", type=int, default=64)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-precompute", action="store_true", help="plain bases: one bucket set per window + Horner")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":
         args.warmup = 3

@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2pcs.so")
+LIB_PATH = os.environ.get("B2PCS_LIB") or os.path.join(_HERE, "libb2pcs.so")  # env: kernel-variant experiments
 
 B2_OK, B2_ERR_ARG, B2_ERR_CUDA, B2_ERR_OOM, B2_ERR_BOUND, B2_ERR_HANDLE = 0, -1, -2, -3, -4, -5
 
@@ -42,8 +42,8 @@ class NttDesc(ctypes.Structure):
 # every symbol include/b2pcs.h declares (checked by tests/test_abi.py without a GPU)
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_get_device", "b2_synchronize",
-    "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_len", "b2_srs_read", "b2_srs_free",
-    "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
+    "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
+    "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
@@ -65,6 +65,8 @@ def lib() -> ctypes.CDLL:
         vp, sz, u32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64
         L.b2_srs_register.argtypes = [vp, sz, sz, ctypes.POINTER(u64)]
         L.b2_srs_synthetic.argtypes = [sz, u64, u64, ctypes.POINTER(u64)]
+        L.b2_srs_precompute.argtypes = [u64, u32]
+        L.b2_g1_normalize.argtypes = [vp, sz]
         L.b2_srs_len.argtypes = [u64, ctypes.POINTER(sz)]
         L.b2_srs_read.argtypes = [u64, sz, sz, vp]
         L.b2_srs_free.argtypes = [u64]
@@ -91,7 +93,7 @@ def lib() -> ctypes.CDLL:
         L.b2_imad_probe.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.b2_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.b2_last_msm_phases.argtypes = [ctypes.POINTER(ctypes.c_double)]
-        L.b2_msm_config.argtypes = [sz, u32, ctypes.POINTER(u32), ctypes.POINTER(u32)]
+        L.b2_msm_config.argtypes = [u64, sz, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]
         _lib = L
     return _lib
 

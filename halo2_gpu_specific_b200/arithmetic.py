@@ -39,6 +39,11 @@ class Srs:
         check(lib().b2_srs_synthetic(n, first_index, seed, ctypes.byref(h)))
         return cls(h.value, n)
 
+    def precompute(self, window_bits: int = 0) -> "Srs":
+        """build the window table (b2_srs_precompute): one shared bucket set, wider windows"""
+        check(lib().b2_srs_precompute(self.handle, int(window_bits)))
+        return self
+
     def __len__(self) -> int:
         return self.n
 

@@ -73,8 +73,10 @@ struct Buf {
 
 struct Srs {
     int device;
-    char* d;
+    char* d;            // n affine points
     size_t n;
+    char* table;        // optional window table: table[w * n + i] = 2^(c*w) * P_i, or nullptr
+    uint32_t tc, tW;    // its window width and number of windows
 };
 
 struct NttPlan {
@@ -101,7 +103,7 @@ struct DeviceCtx {
     uint64_t launches = 0;
     // MSM workspace
     Buf scalars, codes, sorted, counts, offsets, cursor, buckets, part_pt, part_bucket, block_out, window_sums,
-        out96, errflag, tmp_bases, partials;
+        out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids;
     // NTT workspace
     Buf ntt_in, ntt_work, ntt_out;
     std::map<std::string, NttPlan*> plans;
@@ -152,6 +154,86 @@ int ctx_get(DeviceCtx** out) {
                         cudaGetErrorString(le_));                                                          \
     } while (0)
 
+// ---- host-side Fq (4 x 64-bit limbs): only used to normalise the single result point
+typedef unsigned __int128 u128_t;
+const uint64_t HQ_P[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+const uint64_t HQ_INV = 0x87d20782e4866389ULL;
+const uint64_t HQ_ONE[4] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL};
+
+void hq_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+    uint64_t t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        u128_t c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128_t)a[j] * b[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * HQ_INV;
+        c = (u128_t)m * HQ_P[0] + t[0];
+        c >>= 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128_t)m * HQ_P[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    bool ge = t[4] != 0;
+    if (!ge) {
+        ge = true;
+        for (int i = 3; i >= 0; i--) {
+            if (t[i] > HQ_P[i]) break;
+            if (t[i] < HQ_P[i]) { ge = false; break; }
+        }
+    }
+    if (ge) {
+        u128_t br = 0;
+        for (int i = 0; i < 4; i++) {
+            u128_t d = (u128_t)t[i] - HQ_P[i] - (uint64_t)br;
+            t[i] = (uint64_t)d;
+            br = (d >> 64) & 1;
+        }
+    }
+    memcpy(r, t, 32);
+}
+void hq_inv(uint64_t r[4], const uint64_t a[4]) {
+    uint64_t e[4] = {HQ_P[0] - 2, HQ_P[1], HQ_P[2], HQ_P[3]};
+    uint64_t acc[4];
+    memcpy(acc, HQ_ONE, 32);
+    for (int i = 255; i >= 0; i--) {
+        hq_mul(acc, acc, acc);
+        if ((e[i / 64] >> (i % 64)) & 1) hq_mul(acc, acc, a);
+    }
+    memcpy(r, acc, 32);
+}
+// Jacobian (X, Y, Z) -> (x, y, 1) or the identity (0, 1, 0), in place (12 x u64, Montgomery)
+void jac_normalise_host(void* p) {
+    uint64_t v[12];
+    memcpy(v, p, 96);
+    uint64_t* X = v;
+    uint64_t* Y = v + 4;
+    uint64_t* Z = v + 8;
+    if ((Z[0] | Z[1] | Z[2] | Z[3]) == 0) {
+        memset(v, 0, 96);
+        memcpy(v + 4, HQ_ONE, 32);
+    } else {
+        uint64_t zi[4], zi2[4], zi3[4];
+        hq_inv(zi, Z);
+        hq_mul(zi2, zi, zi);
+        hq_mul(zi3, zi2, zi);
+        hq_mul(X, X, zi2);
+        hq_mul(Y, Y, zi3);
+        memcpy(Z, HQ_ONE, 32);
+    }
+    memcpy(p, v, 96);
+}
+
 Fr fr_from_bytes(const void* p) {
     Fr r;
     memcpy(r.v, p, 32);
@@ -179,17 +261,37 @@ void msm_pick_config(size_t n, uint32_t max_bits, uint32_t* c_out, uint32_t* W_o
     *W_out = W;
 }
 
-// device-pointer MSM on ctx.stream-compatible stream `st`; writes 96 B (normalised) to d_out
-int msm_run(DeviceCtx& ctx, const char* d_bases, const void* d_scalars, size_t n, uint32_t max_bits,
+struct MsmBases {
+    const char* d;        // plain affine bases (already offset), used when table == nullptr
+    const char* table;    // window table of the whole SRS, or nullptr
+    uint32_t tc, tW;
+    size_t n_srs, offset; // table geometry: point (w, i) lives at table[w * n_srs + offset + i]
+};
+
+// device-pointer MSM on stream `st`; writes a 96 B Jacobian (not normalised) to d_out
+int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint32_t max_bits,
             void* d_out, cudaStream_t st, bool record_phases, bool reset_flag = true) {
     if (max_bits > 254) max_bits = 254;
     MsmGeom g;
-    msm_pick_config(n, max_bits, &g.c, &g.W);
+    const bool pre = mb.table != nullptr;
+    if (pre) {
+        g.c = mb.tc;
+        g.W = max_bits / g.c + 1;
+        if (g.W > mb.tW) g.W = mb.tW;
+    } else {
+        msm_pick_config(n, max_bits, &g.c, &g.W);
+    }
     g.B = 1u << (g.c - 1);
     g.n = (uint32_t)n;
-    const size_t nb = (size_t)g.W * g.B;
+    g.bucket_stride = pre ? 0u : g.B;
+    g.point_stride = pre ? (uint32_t)mb.n_srs : 0u;
+    g.point_offset = pre ? (uint32_t)mb.offset : 0u;
+    const uint32_t nsets = pre ? 1u : g.W;
+    const size_t nb = (size_t)nsets * g.B;
+    const char* d_points = pre ? mb.table : mb.d;
     const uint32_t T = (uint32_t)ctx.sms * (uint32_t)ctx.acc_blocks_per_sm * 128u;
     const uint32_t bpw = (g.B + MSM_RT * MSM_RM - 1) / (MSM_RT * MSM_RM);
+    const uint32_t ntiles = (uint32_t)((nb + SCAN_TILE - 1) / SCAN_TILE);
 
     int rc;
     if ((rc = ctx.codes.reserve((size_t)g.W * n * 4))) return rc;
@@ -197,10 +299,16 @@ int msm_run(DeviceCtx& ctx, const char* d_bases, const void* d_scalars, size_t n
     if ((rc = ctx.counts.reserve(nb * 4))) return rc;
     if ((rc = ctx.offsets.reserve((nb + 1) * 4))) return rc;
     if ((rc = ctx.cursor.reserve(nb * 4))) return rc;
+    if ((rc = ctx.tile_sums.reserve((size_t)ntiles * 4 + 16))) return rc;
     if ((rc = ctx.buckets.reserve(nb * 128))) return rc;
     if ((rc = ctx.part_pt.reserve((size_t)2 * T * 128))) return rc;
     if ((rc = ctx.part_bucket.reserve((size_t)2 * T * 4))) return rc;
-    if ((rc = ctx.block_out.reserve((size_t)g.W * bpw * 128))) return rc;
+    if ((rc = ctx.part_ids.reserve((size_t)2 * T * 4))) return rc;
+    if ((rc = ctx.part_pt2.reserve((size_t)2 * (2 * T / PR_L + 2) * 128))) return rc;
+    if ((rc = ctx.part_bucket2.reserve((size_t)2 * (2 * T / PR_L + 2) * 4))) return rc;
+    if ((rc = ctx.part_pt3.reserve((size_t)2 * (2 * T / PR_L + 2) * 128))) return rc;
+    if ((rc = ctx.part_bucket3.reserve((size_t)2 * (2 * T / PR_L + 2) * 4))) return rc;
+    if ((rc = ctx.block_out.reserve((size_t)nsets * bpw * 128))) return rc;
     if ((rc = ctx.window_sums.reserve(32 * 128))) return rc;
     if ((rc = ctx.errflag.reserve(16))) return rc;
 
@@ -211,33 +319,65 @@ int msm_run(DeviceCtx& ctx, const char* d_bases, const void* d_scalars, size_t n
     LAUNCH(ctx, msm_digits_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4*)d_scalars,
            ctx.codes.as<uint32_t>(), ctx.counts.as<uint32_t>(), g, max_bits, ctx.errflag.as<int>());
     if (record_phases) CK(cudaEventRecord(ev[1], st));
-    LAUNCH(ctx, msm_scan_kernel, 1, 1024, 0, st, ctx.counts.as<uint32_t>(), ctx.offsets.as<uint32_t>(),
-           ctx.cursor.as<uint32_t>(), (uint32_t)nb);
+    LAUNCH(ctx, msm_scan_tile_kernel, ntiles, SCAN_THREADS, 0, st, ctx.counts.as<uint32_t>(),
+           ctx.offsets.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
+    LAUNCH(ctx, msm_scan_top_kernel, 1, SCAN_THREADS, 0, st, ctx.tile_sums.as<uint32_t>(), ntiles,
+           ctx.offsets.as<uint32_t>() + nb);
+    LAUNCH(ctx, msm_scan_add_kernel, ntiles, SCAN_THREADS, 0, st, ctx.offsets.as<uint32_t>(),
+           ctx.cursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
     if (record_phases) CK(cudaEventRecord(ev[2], st));
     LAUNCH(ctx, msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), g.W), 256, 0, st,
            ctx.codes.as<uint32_t>(), ctx.cursor.as<uint32_t>(), ctx.sorted.as<uint32_t>(), g);
     if (record_phases) CK(cudaEventRecord(ev[3], st));
-    // chunk is sized from the upper bound n*W; threads past the real entry count exit
-    uint64_t emax = (uint64_t)n * g.W;
-    uint32_t chunk = (uint32_t)((emax + T - 1) / T);
-    if (chunk < 16) chunk = 16;
-    LAUNCH(ctx, msm_accumulate_kernel, T / 128, 128, 0, st, d_bases, 64u, ctx.sorted.as<uint32_t>(),
-           ctx.offsets.as<uint32_t>(), (uint32_t)nb, chunk, T, ctx.buckets.as<char>(), ctx.part_pt.as<char>(),
+    // every thread takes ceil(E / T) entries of the bucket-sorted list (E is read on the device)
+    LAUNCH(ctx, msm_accumulate_kernel, T / 128, 128, 0, st, d_points, 64u, ctx.sorted.as<uint32_t>(),
+           ctx.offsets.as<uint32_t>(), (uint32_t)nb, 16u, T, ctx.buckets.as<char>(), ctx.part_pt.as<char>(),
            ctx.part_bucket.as<uint32_t>());
     if (record_phases) CK(cudaEventRecord(ev[4], st));
-    LAUNCH(ctx, msm_fixup_kernel, (2 * T + 127) / 128, 128, 0, st, ctx.part_pt.as<char>(),
-           ctx.part_bucket.as<uint32_t>(), 2 * T, ctx.buckets.as<char>());
+    {
+        // fast path (runs of <= FIX_G records), then levels for long runs only:
+        // 2T records -> 2 * ceil(2T / PR_L) -> ... -> one thread; level kernels exit at once
+        // unless the fast path raised the flag (second int of errflag)
+        uint32_t nrec = 2 * T;
+        int* need = ctx.errflag.as<int>() + 1;
+        CK(cudaMemsetAsync(need, 0, 4, st));
+        LAUNCH(ctx, msm_fixup_small_kernel, (nrec + 127) / 128, 128, 0, st, ctx.part_pt.as<char>(),
+               ctx.part_bucket.as<uint32_t>(), nrec, ctx.part_ids.as<uint32_t>(), need, ctx.buckets.as<char>());
+        char* in_pt = ctx.part_pt.as<char>();
+        uint32_t* in_b = ctx.part_ids.as<uint32_t>();
+        char* out_pt = ctx.part_pt2.as<char>();
+        uint32_t* out_b = ctx.part_bucket2.as<uint32_t>();
+        for (int level = 0;; level++) {
+            const uint32_t nth = (nrec + PR_L - 1) / PR_L;
+            LAUNCH(ctx, msm_partial_reduce_kernel, (nth + 127) / 128, 128, 0, st, in_pt, in_b, nrec, out_pt, out_b,
+                   nth, need, ctx.buckets.as<char>());
+            if (nth == 1) break;
+            nrec = 2 * nth;
+            if (level == 0) {   // ping-pong between the two small buffers after the first level
+                in_pt = out_pt;
+                in_b = out_b;
+                out_pt = ctx.part_pt3.as<char>();
+                out_b = ctx.part_bucket3.as<uint32_t>();
+            } else {
+                std::swap(in_pt, out_pt);
+                std::swap(in_b, out_b);
+            }
+        }
+    }
     if (record_phases) CK(cudaEventRecord(ev[5], st));
-    LAUNCH(ctx, msm_reduce_kernel, g.W * bpw, MSM_RT, MSM_RT * 128, st, ctx.buckets.as<char>(),
-           ctx.offsets.as<uint32_t>(), g, bpw, ctx.block_out.as<char>());
+    MsmGeom gr = g;
+    gr.W = nsets;
+    LAUNCH(ctx, msm_reduce_kernel, nsets * bpw, MSM_RT, MSM_RT * 128, st, ctx.buckets.as<char>(),
+           ctx.offsets.as<uint32_t>(), gr, bpw, ctx.block_out.as<char>());
     if (record_phases) CK(cudaEventRecord(ev[6], st));
-    LAUNCH(ctx, msm_final_kernel, 1, 32, 0, st, ctx.block_out.as<char>(), g, bpw, ctx.window_sums.as<char>(),
-           (char*)d_out, 1);
+    LAUNCH(ctx, msm_final_kernel, 1, MSM_FT, 0, st, ctx.block_out.as<char>(), g.c, nsets, bpw,
+           ctx.window_sums.as<char>(), (char*)d_out);
     if (record_phases) CK(cudaEventRecord(ev[7], st));
     return B2_OK;
 }
 
 int msm_collect_phases(DeviceCtx& ctx) {
+    CK(cudaEventSynchronize(ctx.ev[7]));
     for (int i = 0; i < 7; i++) {
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx.ev[i], ctx.ev[i + 1]));
@@ -273,17 +413,19 @@ int srs_lookup(b2_handle_t h, Srs* out) {
 
 constexpr size_t MSM_MAX_N = (size_t)1 << 26;  // per launch (entry offsets are 32-bit)
 
-// host wrapper pieces: MSM over possibly > MSM_MAX_N points by splitting; all on ctx.stream
-int msm_run_split(DeviceCtx& ctx, const char* d_bases, const char* d_scalars, size_t n, uint32_t max_bits,
+// MSM over possibly > MSM_MAX_N points by splitting; all on stream `st`
+int msm_run_split(DeviceCtx& ctx, const Srs& s, size_t offset, const char* d_scalars, size_t n, uint32_t max_bits,
                   void* d_out, cudaStream_t st, bool record, bool reset_flag = true) {
-    if (n <= MSM_MAX_N) return msm_run(ctx, d_bases, d_scalars, n, max_bits, d_out, st, record, reset_flag);
+    MsmBases mb{s.d + offset * 64, s.table, s.tc, s.tW, s.n, offset};
+    if (n <= MSM_MAX_N) return msm_run(ctx, mb, d_scalars, n, max_bits, d_out, st, record, reset_flag);
     size_t parts = (n + MSM_MAX_N - 1) / MSM_MAX_N;
     int rc;
     if ((rc = ctx.partials.reserve(parts * 96))) return rc;
     for (size_t p = 0; p < parts; p++) {
         size_t lo = p * MSM_MAX_N, cnt = std::min(MSM_MAX_N, n - lo);
-        if ((rc = msm_run(ctx, d_bases + lo * 64, d_scalars + lo * 32, cnt, max_bits,
-                          ctx.partials.as<char>() + p * 96, st, record && p == 0, reset_flag && p == 0)))
+        MsmBases pb{s.d + (offset + lo) * 64, s.table, s.tc, s.tW, s.n, offset + lo};
+        if ((rc = msm_run(ctx, pb, d_scalars + lo * 32, cnt, max_bits, ctx.partials.as<char>() + p * 96, st,
+                          record && p == 0, reset_flag && p == 0)))
             return rc;
     }
     LAUNCH(ctx, g1_sum_kernel, 1, 32, 0, st, ctx.partials.as<char>(), (uint32_t)parts, (char*)d_out);
@@ -513,7 +655,7 @@ int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_
     }
     std::lock_guard<std::mutex> lk2(g_srs_mu);
     b2_handle_t h = g_next_handle++;
-    g_srs[h] = Srs{ctx->dev, d, n};
+    g_srs[h] = Srs{ctx->dev, d, n, nullptr, 0, 0};
     *out = h;
     return B2_OK;
 }
@@ -530,8 +672,55 @@ int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t*
     CK(cudaStreamSynchronize(ctx->stream));
     std::lock_guard<std::mutex> lk2(g_srs_mu);
     b2_handle_t h = g_next_handle++;
-    g_srs[h] = Srs{ctx->dev, d, n};
+    g_srs[h] = Srs{ctx->dev, d, n, nullptr, 0, 0};
     *out = h;
+    return B2_OK;
+}
+int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits) {
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (s.table) return B2_OK;
+    uint32_t c = window_bits;
+    if (c == 0) {
+        uint32_t lg = 0;
+        while ((2ull << lg) <= s.n) lg++;
+        int cc = (int)lg - 2;
+        if (cc < 10) cc = 10;
+        if (cc > 20) cc = (lg >= 25) ? 22 : 20;
+        c = (uint32_t)cc;
+    }
+    if (c < 8 || c > 24) return fail(B2_ERR_ARG, "srs_precompute: window_bits %u out of [8, 24]", c);
+    const uint32_t W = 254 / c + 1;
+    if ((unsigned long long)W * s.n >= (1ull << 31))
+        return fail(B2_ERR_ARG, "srs_precompute: %u windows x %zu points exceed the 31-bit point index", W, s.n);
+    int save = g_dev;
+    g_dev = s.device;
+    DeviceCtx* ctx;
+    rc = ctx_get(&ctx);
+    g_dev = save;
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    char* t = nullptr;
+    cudaError_t e = cudaMalloc(&t, (size_t)W * s.n * 64);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2_ERR_OOM, "srs_precompute: cudaMalloc(%zu): %s", (size_t)W * s.n * 64, cudaGetErrorString(e));
+    }
+    CK(cudaMemcpyAsync(t, s.d, s.n * 64, cudaMemcpyDeviceToDevice, ctx->stream));
+    const unsigned blocks = (unsigned)((s.n + 128ull * PRE_K - 1) / (128ull * PRE_K));
+    for (uint32_t w = 1; w < W; w++)
+        LAUNCH(*ctx, srs_precompute_kernel, blocks, 128, 0, ctx->stream, t, (unsigned long long)s.n, w, c);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::lock_guard<std::mutex> lk2(g_srs_mu);
+    auto it = g_srs.find(srs);
+    if (it == g_srs.end()) {
+        cudaFree(t);
+        return fail(B2_ERR_HANDLE, "SRS freed during precompute");
+    }
+    it->second.table = t;
+    it->second.tc = c;
+    it->second.tW = W;
     return B2_OK;
 }
 int b2_srs_len(b2_handle_t srs, size_t* n) {
@@ -556,13 +745,23 @@ int b2_srs_free(b2_handle_t srs) {
     if (it == g_srs.end()) return fail(B2_ERR_HANDLE, "unknown SRS handle");
     cudaSetDevice(it->second.device);
     cudaFree(it->second.d);
+    if (it->second.table) cudaFree(it->second.table);
     g_srs.erase(it);
     return B2_OK;
 }
 
 // ---- MSM
-int b2_msm_config(size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows) {
+int b2_msm_config(b2_handle_t srs, size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows, uint32_t* bucket_sets) {
+    if (max_bits > 254) max_bits = 254;
+    Srs s;
+    if (srs && srs_lookup(srs, &s) == B2_OK && s.table) {
+        *c = s.tc;
+        *windows = std::min(max_bits / s.tc + 1, s.tW);
+        if (bucket_sets) *bucket_sets = 1;
+        return B2_OK;
+    }
     msm_pick_config(n, max_bits, c, windows);
+    if (bucket_sets) *bucket_sets = *windows;
     return B2_OK;
 }
 
@@ -578,7 +777,7 @@ int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, 
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     if (n == 0 || max_bits == 0) return write_identity(*ctx, d_out_jac96, st);
-    return msm_run_split(*ctx, s.d + offset * 64, (const char*)d_scalars, n, max_bits, d_out_jac96, st, true);
+    return msm_run_split(*ctx, s, offset, (const char*)d_scalars, n, max_bits, d_out_jac96, st, true);
 }
 
 int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96) {
@@ -601,12 +800,12 @@ int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32
     if ((rc = ctx->scalars.reserve(n * 32))) return rc;
     CK(cudaEventRecord(ctx->ev[8], st));
     CK(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
-    if ((rc = msm_run_split(*ctx, s.d + offset * 64, ctx->scalars.as<char>(), n, max_bits, ctx->out96.p, st, true)))
+    if ((rc = msm_run_split(*ctx, s, offset, ctx->scalars.as<char>(), n, max_bits, ctx->out96.p, st, true)))
         return rc;
     CK(cudaMemcpyAsync(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost, st));
     CK(cudaEventRecord(ctx->ev[9], st));
     if ((rc = check_bound_flag(*ctx, st))) return rc;
-    if ((rc = msm_collect_phases(*ctx))) return rc;
+    jac_normalise_host(out_jac96);
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
@@ -646,6 +845,13 @@ int b2_g1_sum(const void* jac96, size_t count, void* out_jac96) {
            ctx->out96.as<char>());
     CK(cudaMemcpyAsync(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    jac_normalise_host(out_jac96);
+    return B2_OK;
+}
+
+int b2_g1_normalize(void* jac96, size_t count) {
+    if (!jac96 && count) return fail(B2_ERR_ARG, "g1_normalize: null pointer");
+    for (size_t i = 0; i < count; i++) jac_normalise_host((char*)jac96 + i * 96);
     return B2_OK;
 }
 
@@ -861,7 +1067,7 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
                 continue;
             }
             // the bound flag is sticky across the whole batch (reset once, read once)
-            if ((rc = msm_run_split(*ctx, s.d, ctx->ntt_in.as<char>() + c * col_bytes, n, max_bits, dout, st, false,
+            if ((rc = msm_run_split(*ctx, s, 0, ctx->ntt_in.as<char>() + c * col_bytes, n, max_bits, dout, st, false,
                                     c0 == 0 && c == 0)))
                 return rc;
         }
@@ -885,6 +1091,7 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
     ctx->last_kernel_ms = kms;
+    for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
     return B2_OK;
 }
@@ -1000,6 +1207,10 @@ int b2_last_msm_phases(double* phases) {
     DeviceCtx* ctx;
     int rc = ctx_get(&ctx);
     if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if ((rc = msm_collect_phases(*ctx))) return rc;
+    }
     for (int i = 0; i < 8; i++) phases[i] = ctx->phases[i];
     return B2_OK;
 }

@@ -17,7 +17,7 @@
 //                          16-bit advice values, all-equal scalars); mixed XYZZ adds;
 //                          buckets wholly inside a chunk are written directly, the <= 2
 //                          buckets cut by a chunk boundary become partial records
-//   5. msm_fixup_kernel    sums the partial records of each cut bucket
+//   5. msm_partial_reduce_kernel  sums the partial records of each cut bucket, level by level
 //   6. msm_reduce_kernel   per window: sum_j (j+1) * B_j with per-thread running sums,
 //                          a block-level suffix scan (no scalar multiplications) and one
 //                          small multiply per block
@@ -29,10 +29,14 @@
 namespace b2 {
 
 struct MsmGeom {
-    uint32_t c;          // window bits
-    uint32_t W;          // number of windows
-    uint32_t B;          // buckets per window = 2^(c-1)
-    uint32_t n;          // number of scalars / points
+    uint32_t c;              // window bits
+    uint32_t W;              // number of windows
+    uint32_t B;              // buckets per window = 2^(c-1)
+    uint32_t n;              // number of scalars / points
+    uint32_t bucket_stride;  // bucket id = w * bucket_stride + |d| - 1:  B (one bucket set per window)
+                             // or 0 (precomputed 2^(c*w) multiples: all windows share one set)
+    uint32_t point_stride;   // point index = w * point_stride + point_offset + i  (0 for plain bases)
+    uint32_t point_offset;
 };
 
 // ---------------------------------------------------------------- 1. digits + histogram
@@ -94,39 +98,89 @@ __global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* _
         if (d != 0) {
             const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
             code = (mag << 1) | (d < 0 ? 1u : 0u);
-            atomicAdd(&counts[(size_t)w * g.B + (mag - 1)], 1u);
+            atomicAdd(&counts[(size_t)w * g.bucket_stride + (mag - 1)], 1u);
         }
         codes[(size_t)w * g.n + i] = code;
     }
 }
 
 // ---------------------------------------------------------------- 2. exclusive scan
-// Single block; offsets[0..total] with offsets[total] = number of entries.  Also copies the
-// exclusive offsets into `cursor` for the scatter pass.
-__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                uint32_t* __restrict__ cursor, uint32_t total) {
-    __shared__ uint32_t sums[1024];
-    const uint32_t t = threadIdx.x, T = blockDim.x;
-    const uint32_t per = (total + T - 1) / T;
-    const uint32_t lo = t * per, hi = min(lo + per, total);
-    uint32_t s = 0;
-    for (uint32_t j = lo; j < hi; j++) s += counts[j];
-    sums[t] = s;
+// Three small kernels: per-tile scan (SCAN_TILE counts per block), scan of the tile totals,
+// and the add-back that writes offsets[] (+ offsets[total] = number of entries) and the
+// scatter cursors.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_PER_THREAD = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_PER_THREAD;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* sm, uint32_t* total) {
+    // sm: SCAN_THREADS entries.  Hillis-Steele; returns the exclusive prefix of v.
+    const uint32_t t = threadIdx.x;
+    sm[t] = v;
     __syncthreads();
-    // Hillis-Steele inclusive scan over T partial sums
-    for (uint32_t d = 1; d < T; d <<= 1) {
-        uint32_t v = (t >= d) ? sums[t - d] : 0;
+    for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+        uint32_t o = (t >= d) ? sm[t - d] : 0;
         __syncthreads();
-        sums[t] += v;
+        sm[t] += o;
         __syncthreads();
     }
-    uint32_t run = (t == 0) ? 0 : sums[t - 1];
+    const uint32_t incl = sm[t];
+    *total = sm[blockDim.x - 1];
+    __syncthreads();
+    return incl - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+msm_scan_tile_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                     uint32_t* __restrict__ tile_sums, uint32_t total) {
+    __shared__ uint32_t sm[SCAN_THREADS];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+    uint32_t v[SCAN_PER_THREAD], s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        v[i] = (base + i < total) ? counts[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t run = block_exclusive_scan(s, sm, &tot);
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        if (base + i < total) offsets[base + i] = run;
+        run += v[i];
+    }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of ntiles tile totals (ntiles <= SCAN_THREADS * 64)
+__global__ void __launch_bounds__(SCAN_THREADS)
+msm_scan_top_kernel(uint32_t* __restrict__ tile_sums, uint32_t ntiles, uint32_t* __restrict__ grand_total) {
+    __shared__ uint32_t sm[SCAN_THREADS];
+    const uint32_t per = (ntiles + blockDim.x - 1) / blockDim.x;
+    const uint32_t lo = threadIdx.x * per, hi = min(lo + per, ntiles);
+    uint32_t s = 0;
+    for (uint32_t j = lo; j < hi; j++) s += tile_sums[j];
+    uint32_t tot;
+    uint32_t run = block_exclusive_scan(s, sm, &tot);
     for (uint32_t j = lo; j < hi; j++) {
-        offsets[j] = run;
-        cursor[j] = run;
-        run += counts[j];
+        const uint32_t v = tile_sums[j];
+        tile_sums[j] = run;
+        run += v;
     }
-    if (t == T - 1) offsets[total] = sums[T - 1];
+    if (threadIdx.x == 0) *grand_total = tot;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+msm_scan_add_kernel(uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor,
+                    const uint32_t* __restrict__ tile_sums, uint32_t total) {
+    const uint32_t add = tile_sums[blockIdx.x];
+    const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_PER_THREAD;
+#pragma unroll
+    for (int i = 0; i < SCAN_PER_THREAD; i++) {
+        if (base + i < total) {
+            const uint32_t v = offsets[base + i] + add;
+            offsets[base + i] = v;
+            cursor[base + i] = v;
+        }
+    }
 }
 
 // ---------------------------------------------------------------- 3. scatter
@@ -138,8 +192,8 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint32_t*
     const uint32_t code = codes[(size_t)w * g.n + i];
     if (code == 0) return;
     const uint32_t mag = code >> 1;
-    const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.B + (mag - 1)], 1u);
-    sorted[pos] = i | ((code & 1u) << 31);
+    const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.bucket_stride + (mag - 1)], 1u);
+    sorted[pos] = (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31);
 }
 
 // ---------------------------------------------------------------- 4. accumulate
@@ -150,9 +204,44 @@ __device__ __forceinline__ Affine msm_load_point(const char* __restrict__ bases,
     return p;
 }
 
-// Thread t owns entries [t*L, min((t+1)*L, E)).  offsets[] has nb+1 entries.
+// Thread t owns entries [t*L, min((t+1)*L, E)) of the bucket-sorted list; offsets[] has nb+1
+// entries.  The loop is FLAT over entries: every lane of a warp executes the expensive mixed
+// add in lock step for exactly L iterations, and bucket boundaries are handled by a short
+// divergent flush in between (a per-bucket inner loop would leave lanes idle until the
+// largest bucket of the warp is done).
 // part_pt[2t], part_pt[2t+1]: head / tail partial sums; part_bucket = bucket id or 0xffffffff.
-__global__ void __launch_bounds__(128)
+#ifndef MSM_ACC_MIN_BLOCKS
+#define MSM_ACC_MIN_BLOCKS 4
+#endif
+__device__ __forceinline__ void msm_prefetch_point(const char* __restrict__ bases, uint32_t stride, uint32_t ent) {
+    const char* p = bases + (size_t)(ent & 0x7fffffffu) * stride;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+}
+
+// Partial-record convention (shared with msm_partial_reduce_kernel): every producer thread owns
+// two record slots.  slot 0 = sum of a bucket that BEGAN before the thread's range ("head cut"),
+// slot 1 = sum of a bucket that CONTINUES after it ("tail cut"); a bucket covering the whole
+// range writes its sum to slot 0 and an identity point with the same id to slot 1, so the
+// records of one bucket are always adjacent in (thread, slot) order.  Unused slots carry the id
+// 0xffffffff.
+__device__ __forceinline__ void msm_flush_bucket(const XYZZ& acc, uint32_t b, bool head_cut, bool tail_cut,
+                                                 uint32_t t, char* __restrict__ buckets,
+                                                 char* __restrict__ part_pt, uint32_t* __restrict__ part_bucket) {
+    if (!head_cut && !tail_cut) {
+        xyzz_store(buckets + (size_t)b * 128, acc);
+        return;
+    }
+    const uint32_t s0 = head_cut ? 0u : 1u;
+    xyzz_store(part_pt + (size_t)(2 * t + s0) * 128, acc);
+    part_bucket[2 * t + s0] = b;
+    if (head_cut && tail_cut) {
+        xyzz_store(part_pt + (size_t)(2 * t + 1) * 128, XYZZ::identity());
+        part_bucket[2 * t + 1] = b;
+    }
+}
+
+__global__ void __launch_bounds__(128, MSM_ACC_MIN_BLOCKS)
 msm_accumulate_kernel(const char* __restrict__ bases, uint32_t base_stride, const uint32_t* __restrict__ sorted,
                       const uint32_t* __restrict__ offsets, uint32_t nb, uint32_t chunk,
                       uint32_t nthreads_total, char* __restrict__ buckets, char* __restrict__ part_pt,
@@ -160,71 +249,117 @@ msm_accumulate_kernel(const char* __restrict__ bases, uint32_t base_stride, cons
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nthreads_total) return;
     const uint32_t E = offsets[nb];
+    // equal shares of the REAL entry count (zero digits produce no entries), at least `chunk`
+    chunk = max(chunk, (uint32_t)(((uint64_t)E + nthreads_total - 1) / nthreads_total));
     const uint64_t lo64 = (uint64_t)t * chunk;
-    uint32_t slot = 0;
     part_bucket[2 * t] = 0xffffffffu;
     part_bucket[2 * t + 1] = 0xffffffffu;
     if (lo64 >= E) return;
     const uint32_t lo = (uint32_t)lo64;
     const uint32_t hi = (uint32_t)min((uint64_t)E, lo64 + chunk);
 
-    // bucket containing entry lo: largest b with offsets[b] <= lo  (then skip empties)
-    uint32_t bl = 0, bh = nb;  // invariant: offsets[bl] <= lo < offsets[bh]
+    // bucket containing entry lo: offsets[b] <= lo < offsets[b + 1]
+    uint32_t bl = 0, bh = nb;
     while (bh - bl > 1) {
         const uint32_t mid = (bl + bh) >> 1;
         if (offsets[mid] <= lo) bl = mid; else bh = mid;
     }
     uint32_t b = bl;
-    uint32_t e = lo;
-    while (e < hi) {
-        const uint32_t b_begin = offsets[b];
-        const uint32_t b_end = offsets[b + 1];
-        if (b_end <= e) { b++; continue; }       // empty bucket (or already consumed)
-        const uint32_t stop = min(b_end, hi);
-        XYZZ acc = XYZZ::identity();
-        Affine p = msm_load_point(bases, base_stride, sorted[e]);
-        for (; e < stop; e++) {
-            Affine cur = p;
-            if (e + 1 < stop) p = msm_load_point(bases, base_stride, sorted[e + 1]);  // prefetch
-            xyzz_madd(acc, cur);
+    uint32_t b_begin = offsets[b], b_end = offsets[b + 1];
+    XYZZ acc = XYZZ::identity();
+    uint32_t ent = sorted[lo];
+    uint32_t ent_next = (lo + 1 < hi) ? sorted[lo + 1] : ent;
+    msm_prefetch_point(bases, base_stride, ent_next);
+#pragma unroll 1
+    for (uint32_t e = lo; e < hi; e++) {
+        if (e == b_end) {   // bucket b is complete: flush it and move to the next non-empty one
+            msm_flush_bucket(acc, b, b_begin < lo, false, t, buckets, part_pt, part_bucket);
+            acc = XYZZ::identity();
+            do {
+                b++;
+                b_begin = b_end;
+                b_end = offsets[b + 1];
+            } while (b_end <= e);
         }
-        if (b_begin >= lo && b_end <= hi) {
-            xyzz_store(buckets + (size_t)b * 128, acc);
-        } else {
-            // cut bucket: at most one at the head and one at the tail of a chunk
-            xyzz_store(part_pt + (size_t)(2 * t + slot) * 128, acc);
-            part_bucket[2 * t + slot] = b;
-            slot++;
+        Affine p = msm_load_point(bases, base_stride, ent);
+        ent = ent_next;
+        if (e + 2 < hi) {
+            ent_next = sorted[e + 2];
+            msm_prefetch_point(bases, base_stride, ent_next);
         }
-        b++;
+        xyzz_madd(acc, p);
     }
+    msm_flush_bucket(acc, b, b_begin < lo, b_end > hi, t, buckets, part_pt, part_bucket);
 }
 
 // ---------------------------------------------------------------- 5. fix-up of cut buckets
-// Partial records are ordered by (thread, slot) and their bucket ids are non-decreasing, so
-// the records of one bucket are contiguous (unused slots, id 0xffffffff, may be interleaved).
-__global__ void msm_fixup_kernel(const char* __restrict__ part_pt, const uint32_t* __restrict__ part_bucket,
-                                 uint32_t nrec, char* __restrict__ buckets) {
+// The partial records form a list sorted by bucket id in which equal ids are adjacent.  Each
+// thread sums runs of equal ids over PR_L consecutive records; complete runs go to buckets[],
+// runs cut by the thread's range become the next level's records (same convention).  The host
+// launches this with shrinking record counts until one thread sees everything, so a bucket cut
+// into thousands of pieces (all-equal scalars, the 1-bit top window) costs O(log) launches,
+// not one serial chain.
+// Fast path first: one thread per record; a run of <= FIX_G records (the normal case is 2: the
+// tail of one chunk and the head of the next) is summed by its first record's thread.  Longer
+// runs keep their ids in ids_out and raise *need_levels for the level kernels.
+constexpr int FIX_G = 4;
+__global__ void __launch_bounds__(128)
+msm_fixup_small_kernel(const char* __restrict__ part_pt, const uint32_t* __restrict__ part_bucket, uint32_t nrec,
+                       uint32_t* __restrict__ ids_out, int* __restrict__ need_levels, char* __restrict__ buckets) {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= nrec) return;
     const uint32_t b = part_bucket[r];
-    if (b == 0xffffffffu) return;
-    // leader = first record of this bucket
-    for (int64_t q = (int64_t)r - 1; q >= 0; q--) {
-        const uint32_t pb = part_bucket[q];
-        if (pb == 0xffffffffu) continue;
-        if (pb == b) return;  // not the leader
-        break;
+    if (b == 0xffffffffu) { ids_out[r] = b; return; }
+    // run boundaries within a +-FIX_G window
+    uint32_t start = r, end = r + 1;
+    while (start > 0 && r - start < FIX_G && part_bucket[start - 1] == b) start--;
+    while (end < nrec && end - r < FIX_G && part_bucket[end] == b) end++;
+    const bool open_left = start > 0 && part_bucket[start - 1] == b;
+    const bool open_right = end < nrec && part_bucket[end] == b;
+    if (open_left || open_right || end - start > FIX_G) {
+        ids_out[r] = b;              // long run: leave it to the level kernels
+        if (r == start || open_left) atomicExch(need_levels, 1);
+        return;
     }
+    ids_out[r] = 0xffffffffu;
+    if (r != start) return;
     XYZZ acc = xyzz_load(part_pt + (size_t)r * 128);
-    for (uint32_t q = r + 1; q < nrec; q++) {
-        const uint32_t nb_ = part_bucket[q];
-        if (nb_ == 0xffffffffu) continue;
-        if (nb_ != b) break;
+    for (uint32_t q = r + 1; q < end; q++) {
         XYZZ o = xyzz_load(part_pt + (size_t)q * 128);
         xyzz_add_ni(acc, o);
     }
     xyzz_store(buckets + (size_t)b * 128, acc);
+}
+
+constexpr int PR_L = 32;
+__global__ void __launch_bounds__(128)
+msm_partial_reduce_kernel(const char* __restrict__ in_pt, const uint32_t* __restrict__ in_bucket, uint32_t nrec,
+                          char* __restrict__ out_pt, uint32_t* __restrict__ out_bucket, uint32_t nthreads,
+                          const int* __restrict__ need_levels, char* __restrict__ buckets) {
+    if (*need_levels == 0) return;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nthreads) return;
+    out_bucket[2 * t] = 0xffffffffu;
+    out_bucket[2 * t + 1] = 0xffffffffu;
+    const uint32_t lo = t * PR_L;
+    if (lo >= nrec) return;
+    const uint32_t hi = min(nrec, lo + PR_L);
+    uint32_t r = lo;
+    while (r < hi) {
+        const uint32_t b = in_bucket[r];
+        if (b == 0xffffffffu) { r++; continue; }
+        const uint32_t start = r;
+        XYZZ acc = xyzz_load(in_pt + (size_t)r * 128);
+        r++;
+        while (r < hi && in_bucket[r] == b) {
+            XYZZ o = xyzz_load(in_pt + (size_t)r * 128);
+            xyzz_add_ni(acc, o);
+            r++;
+        }
+        const bool head_cut = (start == lo) && lo > 0 && in_bucket[lo - 1] == b;
+        const bool tail_cut = (r == hi) && hi < nrec && in_bucket[hi] == b;
+        msm_flush_bucket(acc, b, head_cut, tail_cut, t, buckets, out_pt, out_bucket);
+    }
 }
 
 // ---------------------------------------------------------------- 6. bucket reduction
@@ -301,46 +436,60 @@ msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__
 }
 
 // ---------------------------------------------------------------- 7. window combine
-// One block of 32 threads: lane w sums the block results of window w, then lane 0 runs
-// Horner over windows and normalises.  out: 96 B Jacobian with Z = 1 (or the identity
-// (0, 1, 0)).  If `accumulate` != 0 the previous value of `out` is added first
-// (used when an MSM is split into several launches).
-__global__ void msm_final_kernel(const char* __restrict__ block_out, MsmGeom g, uint32_t blocks_per_window,
-                                 char* __restrict__ window_sums, char* __restrict__ out, int normalise) {
-    const uint32_t w = threadIdx.x;
-    if (w < g.W) {
-        XYZZ acc = XYZZ::identity();
-        for (uint32_t b = 0; b < blocks_per_window; b++) {
-            XYZZ o = xyzz_load(block_out + ((size_t)w * blocks_per_window + b) * 128);
-            xyzz_add_ni(acc, o);
-        }
-        xyzz_store(window_sums + (size_t)w * 128, acc);
-    }
-    __syncthreads();
-    if (threadIdx.x != 0) return;
-    XYZZ acc = XYZZ::identity();
-    for (int w2 = (int)g.W - 1; w2 >= 0; w2--) {
-        for (uint32_t i = 0; i < g.c; i++) xyzz_dbl_ni(acc);
-        XYZZ o = xyzz_load(window_sums + (size_t)w2 * 128);
-        xyzz_add_ni(acc, o);
-    }
-    if (normalise) {
-        Affine a = xyzz_to_affine(acc);
-        if (acc.is_identity()) {
-            fp_store<FqParams>(out, Fq::zero());
-            fp_store<FqParams>(out + 32, Fq::one());
-            fp_store<FqParams>(out + 64, Fq::zero());
-        } else {
-            fp_store<FqParams>(out, a.x);
-            fp_store<FqParams>(out + 32, a.y);
-            fp_store<FqParams>(out + 64, Fq::one());
-        }
+// One block.  For every window: tree-sum of its block results; then (only when there is more
+// than one bucket set) Horner over windows with c doublings each.  Output: 96 B Jacobian
+// (X*ZZ, Y*ZZZ, ZZ) -- NOT normalised; the host entry points normalise after the 96-byte
+// read-back (one field inversion is ~100x cheaper on a CPU core than on one GPU thread).
+constexpr int MSM_FT = 128;
+
+__device__ __forceinline__ void xyzz_store_jacobian(char* out, const XYZZ& p) {
+    if (p.is_identity()) {
+        fp_store<FqParams>(out, Fq::zero());
+        fp_store<FqParams>(out + 32, Fq::one());
+        fp_store<FqParams>(out + 64, Fq::zero());
     } else {
-        xyzz_store(out, acc);
+        fp_store<FqParams>(out, FQ_MUL(p.x, p.zz));
+        fp_store<FqParams>(out + 32, FQ_MUL(p.y, p.zzz));
+        fp_store<FqParams>(out + 64, p.zz);
     }
 }
 
-// Sum of `count` Jacobian points (96 B each) -> normalised Jacobian.  Single thread.
+__global__ void __launch_bounds__(MSM_FT)
+msm_final_kernel(const char* __restrict__ block_out, uint32_t c, uint32_t nsets, uint32_t blocks_per_window,
+                 char* __restrict__ window_sums, char* __restrict__ out) {
+    __shared__ uint4 fin_smem[MSM_FT * 8];
+    char* sm = reinterpret_cast<char*>(fin_smem);
+    const uint32_t t = threadIdx.x;
+    for (uint32_t w = 0; w < nsets; w++) {
+        XYZZ acc = XYZZ::identity();
+        for (uint32_t b = t; b < blocks_per_window; b += MSM_FT) {
+            XYZZ o = xyzz_load(block_out + ((size_t)w * blocks_per_window + b) * 128);
+            xyzz_add_ni(acc, o);
+        }
+        xyzz_store(sm + (size_t)t * 128, acc);
+        __syncthreads();
+        for (uint32_t d = MSM_FT / 2; d >= 1; d >>= 1) {
+            if (t < d) {
+                XYZZ o = xyzz_load(sm + (size_t)(t + d) * 128);
+                xyzz_add_ni(acc, o);
+                xyzz_store(sm + (size_t)t * 128, acc);
+            }
+            __syncthreads();
+        }
+        if (t == 0) xyzz_store(window_sums + (size_t)w * 128, acc);
+        __syncthreads();
+    }
+    if (t != 0) return;
+    XYZZ acc = xyzz_load(window_sums + (size_t)(nsets - 1) * 128);
+    for (int w2 = (int)nsets - 2; w2 >= 0; w2--) {
+        for (uint32_t i = 0; i < c; i++) xyzz_dbl_ni(acc);
+        XYZZ o = xyzz_load(window_sums + (size_t)w2 * 128);
+        xyzz_add_ni(acc, o);
+    }
+    xyzz_store_jacobian(out, acc);
+}
+
+// Sum of `count` Jacobian points (96 B each) -> Jacobian (un-normalised).  Single thread.
 // (combine of per-GPU / per-chunk partials: arithmetic.rs:428-435 does this on the host)
 __global__ void g1_sum_kernel(const char* __restrict__ pts, uint32_t count, char* __restrict__ out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -350,15 +499,47 @@ __global__ void g1_sum_kernel(const char* __restrict__ pts, uint32_t count, char
         XYZZ o = xyzz_from_jacobian(fp_load<FqParams>(p), fp_load<FqParams>(p + 32), fp_load<FqParams>(p + 64));
         xyzz_add_ni(acc, o);
     }
-    Affine a = xyzz_to_affine(acc);
-    if (acc.is_identity()) {
-        fp_store<FqParams>(out, Fq::zero());
-        fp_store<FqParams>(out + 32, Fq::one());
-        fp_store<FqParams>(out + 64, Fq::zero());
-    } else {
-        fp_store<FqParams>(out, a.x);
-        fp_store<FqParams>(out + 32, a.y);
-        fp_store<FqParams>(out + 64, Fq::one());
+    xyzz_store_jacobian(out, acc);
+}
+
+// ---------------------------------------------------------------- SRS window tables
+// table[w * n + i] = 2^(c*w) * P_i (affine).  One launch per window: c doublings in XYZZ, then
+// one shared field inversion per thread for its PRE_K points (Montgomery's trick).
+constexpr int PRE_K = 8;
+__global__ void __launch_bounds__(128)
+srs_precompute_kernel(char* __restrict__ table, unsigned long long n, uint32_t w, uint32_t c) {
+    const unsigned long long i0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * PRE_K;
+    if (i0 >= n) return;
+    XYZZ pts[PRE_K];
+    Fq prefix[PRE_K];
+    Fq run = Fq::one();
+    const char* src = table + (size_t)(w - 1) * n * 64;
+    char* dst = table + (size_t)w * n * 64;
+    for (int j = 0; j < PRE_K; j++) {
+        const unsigned long long i = i0 + j;
+        pts[j] = XYZZ::identity();
+        prefix[j] = run;
+        if (i >= n) continue;
+        Affine a = affine_load(src + i * 64);
+        if (a.is_identity()) continue;
+        XYZZ p = xyzz_dbl_affine(a);
+        for (uint32_t d = 1; d < c; d++) xyzz_dbl_ni(p);
+        pts[j] = p;
+        run = FQ_MUL(run, FQ_MUL(p.zz, p.zzz));
+    }
+    Fq inv = fp_inv<FqParams>(run);
+    for (int j = PRE_K - 1; j >= 0; j--) {
+        const unsigned long long i = i0 + j;
+        if (i >= n) continue;
+        if (pts[j].is_identity()) {
+            fp_store<FqParams>(dst + i * 64, Fq::zero());
+            fp_store<FqParams>(dst + i * 64 + 32, Fq::zero());
+            continue;
+        }
+        Fq den_inv = FQ_MUL(inv, prefix[j]);                      // 1 / (zz * zzz)
+        inv = FQ_MUL(inv, FQ_MUL(pts[j].zz, pts[j].zzz));
+        fp_store<FqParams>(dst + i * 64, FQ_MUL(pts[j].x, FQ_MUL(den_inv, pts[j].zzz)));
+        fp_store<FqParams>(dst + i * 64 + 32, FQ_MUL(pts[j].y, FQ_MUL(den_inv, pts[j].zz)));
     }
 }
 

@@ -66,6 +66,12 @@ int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_
 /* Synthetic bases for benchmarks / property tests: bases[i] = [h(seed, first+i)] G with
  * h = 64-bit splitmix64 hash, generated on the device. */
 int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t* out);
+/* Build the window table of a resident SRS: table[w][i] = 2^(window_bits * w) * P_i for every
+ * window w (affine, in HBM: 254/window_bits + 1 copies of the SRS).  MSMs against this SRS then
+ * drop every scalar digit into ONE shared bucket set: no per-window bucket reduction and no
+ * doublings at the end, and the window can be wider (fewer point additions).  window_bits = 0
+ * picks it from the SRS length (20 for 2^21..2^24 points).  Optional; results are identical. */
+int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits);
 int b2_srs_len(b2_handle_t srs, size_t* n);
 int b2_srs_read(b2_handle_t srs, size_t offset, size_t count, void* out_affine64);
 int b2_srs_free(b2_handle_t srs);
@@ -81,7 +87,9 @@ int b2_srs_free(b2_handle_t srs);
  * commit_lagrange_with_bound (commitment.rs:204-212) is not needed. */
 int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96);
 /* Same with `scalars` and `out_jac96` in device memory, asynchronous on `stream`
- * (a cudaStream_t, NULL = the library's per-device stream). */
+ * (a cudaStream_t, NULL = the library's per-device stream).  The device result is a valid
+ * Jacobian point but NOT normalised (the host entry points normalise after the read-back;
+ * use b2_g1_normalize on the 96 bytes once they are on the host). */
 int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, uint32_t max_bits,
                void* d_out_jac96, void* stream);
 /* best_multiexp (arithmetic.rs:465-492) with both slices on the host: uploads the bases
@@ -90,8 +98,10 @@ int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_
 /* Sum of `count` Jacobian points (96 B each): the combine of per-GPU partials that
  * gpu_multiexp_bound does on the host (arithmetic.rs:428-435). */
 int b2_g1_sum(const void* jac96, size_t count, void* out_jac96);
-/* Same with device pointers, asynchronous on `stream` (NULL = the library stream): used after
- * the NCCL all-gather of one partial per rank. */
+/* Normalise `count` Jacobian points in host memory in place: Z = 1, or (0, 1, 0). */
+int b2_g1_normalize(void* jac96, size_t count);
+/* Same as b2_g1_sum with device pointers, asynchronous on `stream` (NULL = the library stream),
+ * result not normalised: used after the NCCL all-gather of one partial per rank. */
 int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream);
 
 /* ---- NTT -------------------------------------------------------------------------- */
@@ -169,8 +179,10 @@ int b2_last_timing(double* kernel_ms, double* total_ms);
 /* Per-phase kernel times of the last MSM (ms): digits, scan, scatter, accumulate, fixup,
  * reduce, final.  `phases` must hold 8 doubles. */
 int b2_last_msm_phases(double* phases);
-/* Window configuration the MSM would use for (n, max_bits): c, number of windows. */
-int b2_msm_config(size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows);
+/* Window configuration an MSM of n scalars against `srs` (0 = plain bases) would use:
+ * window bits c, number of windows, number of bucket sets (1 with a window table). */
+int b2_msm_config(b2_handle_t srs, size_t n, uint32_t max_bits, uint32_t* c, uint32_t* windows,
+                  uint32_t* bucket_sets);
 
 #ifdef __cplusplus
 }

@@ -54,6 +54,32 @@ def test_msm_matches_oracle_random(gpu, n):
     assert _affine(h2.best_multiexp(scalars, bases)) == _want(scalars, bases)
 
 
+@pytest.mark.parametrize("n,c", [(1, 0), (33, 8), (1000, 0), (5000, 13), ((1 << 14) + 1, 0), (1 << 16, 0), (1 << 16, 20)])
+def test_msm_window_table_matches_oracle(gpu, n, c):
+    """b2_srs_precompute: table of 2^(c*w) multiples, one shared bucket set -- same point"""
+    scalars = cref.random_fr_mont(n, 0xB2000003 + n)
+    bases = _bases(n, 0x51 + n)
+    srs = Srs.register(bases).precompute(c)
+    assert _affine(h2.best_multiexp(scalars, srs)) == _want(scalars, bases)
+    if n >= 1000:
+        assert _affine(h2.best_multiexp(scalars[:777], srs[100:877])) == _want(scalars[:777], bases[100:877])
+        small = cref.random_fr_small_mont(n, 9, 16)
+        small[::3] = 0
+        assert _affine(h2.gpu_multiexp_single_gpu_with_bound(small, srs, 16)) == _want(small, bases)
+    srs.free()
+
+
+def test_msm_window_table_adversarial(gpu):
+    G = o.G1_GEN
+    P = o.g1_mul(G, 12345)
+    bases = [P] * 300 + [o.g1_neg(P)] * 300 + [None, G]
+    srs = Srs.register(o.g1_affine_encode(bases)).precompute(9)
+    assert _affine(h2.best_multiexp(o.fr_encode([7] * 600 + [5, 0]), srs)) is None
+    sc = [o.R_MOD - 1, (1 << 253) - 1, 1, 2] * 150 + [3, 9]
+    assert _affine(h2.best_multiexp(o.fr_encode(sc), srs)) == o.msm_naive(sc, bases)
+    srs.free()
+
+
 def test_msm_resident_srs_slices(gpu):
     n = 5000
     scalars = cref.random_fr_mont(n, 3)
@@ -215,6 +241,8 @@ def test_full_size_property(gpu, logn, bits):
     n = 1 << logn
     seed = 0xB2000003
     srs = Srs.synthetic(n, 0, seed)
+    if logn == 22:
+        srs.precompute()
     if bits == 254:
         scalars = cref.random_fr_mont(n, seed)
     else:
