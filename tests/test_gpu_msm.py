@@ -254,3 +254,14 @@ def test_full_size_property(gpu, logn, bits):
     want = o.g1_mul(o.G1_GEN, total % o.R_MOD)
     assert got == want
     srs.free()
+
+
+def test_cpp_host_mirror_selftest(gpu):
+    """host/halo2_b200.hpp (C++ mirror of the Rust interface): the reference's test_commit_lagrange,
+    commit variants, iFFT consistency and the coset round trip, compiled by build()"""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "halo2_gpu_specific_b200", "host",
+                       "host_selftest")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "host_selftest ok" in out.stdout
