@@ -290,7 +290,10 @@ int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n,
     const size_t nb = (size_t)nsets * g.B;
     const char* d_points = pre ? mb.table : mb.d;
     const uint32_t T = (uint32_t)ctx.sms * (uint32_t)ctx.acc_blocks_per_sm * 128u;
-    const uint32_t bpw = (g.B + MSM_RT * MSM_RM - 1) / (MSM_RT * MSM_RM);
+    // buckets per reduce thread: enough blocks to fill the chip, fewer adds per bucket when there are many
+    uint32_t rm = g.B >> 15;
+    rm = rm < 2 ? 2 : (rm > 16 ? 16 : rm);
+    const uint32_t bpw = (g.B + MSM_RT * rm - 1) / (MSM_RT * rm);
     const uint32_t ntiles = (uint32_t)((nb + SCAN_TILE - 1) / SCAN_TILE);
 
     int rc;
@@ -348,11 +351,11 @@ int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n,
         char* out_pt = ctx.part_pt2.as<char>();
         uint32_t* out_b = ctx.part_bucket2.as<uint32_t>();
         for (int level = 0;; level++) {
-            const uint32_t nth = (nrec + PR_L - 1) / PR_L;
-            LAUNCH(ctx, msm_partial_reduce_kernel, (nth + 127) / 128, 128, 0, st, in_pt, in_b, nrec, out_pt, out_b,
-                   nth, need, ctx.buckets.as<char>());
-            if (nth == 1) break;
-            nrec = 2 * nth;
+            const uint32_t nw = (nrec + PR_L - 1) / PR_L;   // one warp per PR_L records
+            LAUNCH(ctx, msm_partial_reduce_kernel, (nw * 32 + 127) / 128, 128, 0, st, in_pt, in_b, nrec, out_pt, out_b,
+                   nw, need, ctx.buckets.as<char>());
+            if (nw == 1) break;
+            nrec = 2 * nw;
             if (level == 0) {   // ping-pong between the two small buffers after the first level
                 in_pt = out_pt;
                 in_b = out_b;
@@ -368,7 +371,7 @@ int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n,
     MsmGeom gr = g;
     gr.W = nsets;
     LAUNCH(ctx, msm_reduce_kernel, nsets * bpw, MSM_RT, MSM_RT * 128, st, ctx.buckets.as<char>(),
-           ctx.offsets.as<uint32_t>(), gr, bpw, ctx.block_out.as<char>());
+           ctx.offsets.as<uint32_t>(), gr, bpw, rm, ctx.block_out.as<char>());
     if (record_phases) CK(cudaEventRecord(ev[6], st));
     LAUNCH(ctx, msm_final_kernel, 1, MSM_FT, 0, st, ctx.block_out.as<char>(), g.c, nsets, bpw,
            ctx.window_sums.as<char>(), (char*)d_out);
@@ -1192,6 +1195,31 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
     }
     if (modmuls_per_s) *modmuls_per_s = best;
     if (wide_macs_per_s) *wide_macs_per_s = best * 128.0;
+    return B2_OK;
+}
+
+int b2_dfma_probe(double* dfma_per_s) {
+    DeviceCtx* ctx;
+    int rc = ctx_get(&ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    cudaStream_t st = ctx->stream;
+    const int iters = 20000, ILP = 8;
+    const int blocks = ctx->sms * 8, threads = 256;
+    LAUNCH(*ctx, dfma_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<double>(), 100);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, dfma_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<double>(), iters);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        double rate = (double)blocks * threads * (double)iters * ILP / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    *dfma_per_s = best;
     return B2_OK;
 }
 

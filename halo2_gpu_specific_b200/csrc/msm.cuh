@@ -299,10 +299,10 @@ msm_accumulate_kernel(const char* __restrict__ bases, uint32_t base_stride, cons
 // launches this with shrinking record counts until one thread sees everything, so a bucket cut
 // into thousands of pieces (all-equal scalars, the 1-bit top window) costs O(log) launches,
 // not one serial chain.
-// Fast path first: one thread per record; a run of <= FIX_G records (the normal case is 2: the
-// tail of one chunk and the head of the next) is summed by its first record's thread.  Longer
+// Fast path first: one thread per record; a run of <= FIX_G records (the normal case is 2-4: the
+// tail of one chunk and the head of the next, or a bucket spanning a few short chunks) is summed by its first record's thread.  Longer
 // runs keep their ids in ids_out and raise *need_levels for the level kernels.
-constexpr int FIX_G = 4;
+constexpr int FIX_G = 16;
 __global__ void __launch_bounds__(128)
 msm_fixup_small_kernel(const char* __restrict__ part_pt, const uint32_t* __restrict__ part_bucket, uint32_t nrec,
                        uint32_t* __restrict__ ids_out, int* __restrict__ need_levels, char* __restrict__ buckets) {
@@ -331,54 +331,70 @@ msm_fixup_small_kernel(const char* __restrict__ part_pt, const uint32_t* __restr
     xyzz_store(buckets + (size_t)b * 128, acc);
 }
 
+// Level kernel: one WARP per 32 consecutive records; a segmented shuffle reduction (5 rounds, every
+// lane adding in parallel) sums each run of equal ids, so a level costs ~5 point additions of
+// latency and shrinks the list 16x.  Run leaders flush with the same head/tail convention.
 constexpr int PR_L = 32;
+__device__ __forceinline__ Fq shfl_down_fq(const Fq& a, int d) {
+    Fq r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_down_sync(0xffffffffu, a.v[i], d);
+    return r;
+}
 __global__ void __launch_bounds__(128)
 msm_partial_reduce_kernel(const char* __restrict__ in_pt, const uint32_t* __restrict__ in_bucket, uint32_t nrec,
-                          char* __restrict__ out_pt, uint32_t* __restrict__ out_bucket, uint32_t nthreads,
+                          char* __restrict__ out_pt, uint32_t* __restrict__ out_bucket, uint32_t nwarps,
                           const int* __restrict__ need_levels, char* __restrict__ buckets) {
     if (*need_levels == 0) return;
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nthreads) return;
-    out_bucket[2 * t] = 0xffffffffu;
-    out_bucket[2 * t + 1] = 0xffffffffu;
-    const uint32_t lo = t * PR_L;
-    if (lo >= nrec) return;
-    const uint32_t hi = min(nrec, lo + PR_L);
-    uint32_t r = lo;
-    while (r < hi) {
-        const uint32_t b = in_bucket[r];
-        if (b == 0xffffffffu) { r++; continue; }
-        const uint32_t start = r;
-        XYZZ acc = xyzz_load(in_pt + (size_t)r * 128);
-        r++;
-        while (r < hi && in_bucket[r] == b) {
-            XYZZ o = xyzz_load(in_pt + (size_t)r * 128);
-            xyzz_add_ni(acc, o);
-            r++;
-        }
-        const bool head_cut = (start == lo) && lo > 0 && in_bucket[lo - 1] == b;
-        const bool tail_cut = (r == hi) && hi < nrec && in_bucket[hi] == b;
-        msm_flush_bucket(acc, b, head_cut, tail_cut, t, buckets, out_pt, out_bucket);
+    const uint32_t wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one output pair per warp
+    const uint32_t lane = threadIdx.x & 31;
+    if (wid >= nwarps) return;
+    if (lane < 2) out_bucket[2 * wid + lane] = 0xffffffffu;
+    const uint32_t r = wid * PR_L + lane;
+    uint32_t id = (r < nrec) ? in_bucket[r] : 0xffffffffu;
+    XYZZ acc = XYZZ::identity();
+    if (id != 0xffffffffu) acc = xyzz_load(in_pt + (size_t)r * 128);
+    // neighbours outside the warp decide whether the first / last run is cut
+    const uint32_t lo = wid * PR_L, hi = min(nrec, lo + PR_L);
+    const uint32_t prev_out = (lo > 0) ? in_bucket[lo - 1] : 0xffffffffu;
+    const uint32_t next_out = (hi < nrec) ? in_bucket[hi] : 0xffffffffu;
+    const uint32_t id_prev = __shfl_up_sync(0xffffffffu, id, 1);
+    const bool leader = (id != 0xffffffffu) && (lane == 0 || id_prev != id);
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) {
+        XYZZ o;
+        o.x = shfl_down_fq(acc.x, d);
+        o.y = shfl_down_fq(acc.y, d);
+        o.zz = shfl_down_fq(acc.zz, d);
+        o.zzz = shfl_down_fq(acc.zzz, d);
+        const uint32_t oid = __shfl_down_sync(0xffffffffu, id, d);
+        if (lane + d < 32 && oid == id && id != 0xffffffffu) xyzz_add(acc, o);
+    }
+    // run extent: the run of a leader ends at the last lane with the same id
+    const uint32_t same_as_last = __shfl_sync(0xffffffffu, id, 31);
+    if (leader) {
+        const bool head_cut = (lane == 0) && prev_out == id;
+        const bool tail_cut = (same_as_last == id) && (hi - lo == 32) && next_out == id;
+        msm_flush_bucket(acc, id, head_cut, tail_cut, wid, buckets, out_pt, out_bucket);
     }
 }
 
 // ---------------------------------------------------------------- 6. bucket reduction
 // Block of RT threads handles RT*RM consecutive buckets of one window; bucket j (0-based
 // inside the window) has weight j+1.  Output per block: sum_j (j+1) B_j over its range.
-constexpr int MSM_RT = 128;  // threads per reduce block
-constexpr int MSM_RM = 4;    // buckets per thread
+constexpr int MSM_RT = 128;      // threads per reduce block; each thread takes `rm` buckets (power of two)
 
 __global__ void __launch_bounds__(MSM_RT)
 msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__ offsets, MsmGeom g,
-                  uint32_t blocks_per_window, char* __restrict__ block_out) {
+                  uint32_t blocks_per_window, uint32_t rm, char* __restrict__ block_out) {
     extern __shared__ uint4 red_smem[];   // MSM_RT XYZZ points (128 B each)
     char* sm = reinterpret_cast<char*>(red_smem);
     const uint32_t w = blockIdx.x / blocks_per_window;
     const uint32_t blk = blockIdx.x % blocks_per_window;
     const uint32_t t = threadIdx.x;
-    const uint32_t j0 = (blk * MSM_RT + t) * MSM_RM;   // first bucket of this thread (in-window)
+    const uint32_t j0 = (blk * MSM_RT + t) * rm;   // first bucket of this thread (in-window)
     XYZZ run = XYZZ::identity(), sum = XYZZ::identity();
-    for (int i = MSM_RM - 1; i >= 0; i--) {
+    for (int i = (int)rm - 1; i >= 0; i--) {
         const uint32_t j = j0 + (uint32_t)i;
         if (j < g.B) {
             const size_t gb = (size_t)w * g.B + j;
@@ -390,7 +406,7 @@ msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__
         xyzz_add_ni(sum, run);
     }
     // thread value: sum_i (i+1) B_{j0+i} = sum;  run = sum_i B_{j0+i}
-    // block total = sum_t [ sum_t + (t*RM) * run_t ]  (+ blk offset handled below)
+    // block total = sum_t [ sum_t + (t*rm) * run_t ]  (+ blk offset handled below)
     // S_t = suffix sum of run over threads >= t  ->  sum_t t*run_t = sum_{t>=1} S_t
     xyzz_store(sm + (size_t)t * 128, run);
     __syncthreads();
@@ -413,7 +429,7 @@ msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__
     if (t >= 1) {
         XYZZ s = run;
 #pragma unroll 1
-        for (int i = 1; i < MSM_RM; i <<= 1) xyzz_dbl_ni(s);
+        for (uint32_t i = 1; i < rm; i <<= 1) xyzz_dbl_ni(s);
         xyzz_add_ni(v, s);
     }
     xyzz_store(sm + (size_t)t * 128, v);
@@ -429,7 +445,7 @@ msm_reduce_kernel(const char* __restrict__ buckets, const uint32_t* __restrict__
     if (t == 0) {
         // + (blk * RT * RM) * total_run
         XYZZ off = total_run;
-        xyzz_mul_small(off, blk * MSM_RT * MSM_RM);
+        xyzz_mul_small(off, blk * MSM_RT * rm);
         xyzz_add_ni(v, off);
         xyzz_store(block_out + (size_t)blockIdx.x * 128, v);
     }
@@ -607,6 +623,23 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint4* sink, int iters)
 #pragma unroll
     for (int j = 1; j < ILP; j++) acc = fp_add<FqParams>(acc, x[j]);
     if (acc.v[0] == 0x12345678u && acc.v[7] == 0x9abcdef0u) fp_store<FqParams>(sink, acc);
+}
+
+// FP64 FMA throughput probe (is the fp64 pipe a usable second multiplier on this part?)
+template <int ILP>
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* sink, int iters) {
+    double x[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) x[j] = 1.0 + 1e-9 * (threadIdx.x + j);
+    const double a = 1.0000001, b = 1e-7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = fma(x[j], a, b);
+    }
+    double acc = 0;
+#pragma unroll
+    for (int j = 0; j < ILP; j++) acc += x[j];
+    if (acc == 123.456) *sink = acc;
 }
 
 }  // namespace b2

@@ -84,27 +84,36 @@ class EvaluationDomain:
         check(lib().b2_ntt_exec(ctypes.byref(d)))
         return cols
 
-    def coeff_to_extended(self, a: np.ndarray) -> np.ndarray:
-        """:270-287; accepts (n,4) or a batch (columns, n, 4); returns (.., 2^extended_k, 4)"""
+    def coeff_to_extended(self, a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """:270-287; accepts (n,4) or a batch (columns, n, 4); returns (.., 2^extended_k, 4).
+        `out` may be a preallocated (e.g. pinned) buffer of that shape."""
         arr = as_fr(a) if a.ndim <= 2 else np.ascontiguousarray(a)
         batch = arr.ndim == 3
         cols = arr.shape[0] if batch else 1
         if (arr.shape[1] if batch else arr.shape[0]) != self.n:
             raise B2Error(B2_ERR_ARG, "assert_eq!(a.values.len(), 1 << self.k)")
         require_gpu()
-        out = np.empty((cols, self.extended_len(), 4), dtype=np.uint64)
+        if out is None:
+            out = np.empty((cols, self.extended_len(), 4), dtype=np.uint64)
+        elif out.size != cols * self.extended_len() * 4 or not out.flags.c_contiguous:
+            raise B2Error(B2_ERR_ARG, "out has the wrong size")
+        out = out.reshape(cols, self.extended_len(), 4)
         check(lib().b2_coeff_to_extended(ptr(arr), ptr(out), cols, self.k, self.extended_k, ptr(self.g_coset),
                                          ptr(self.g_coset_inv), ptr(self.extended_omega)))
         return out if batch else out[0]
 
-    def extended_to_coeff(self, a: np.ndarray) -> np.ndarray:
-        """:328-350; returns n * quotient_poly_degree coefficients"""
+    def extended_to_coeff(self, a: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """:328-350; returns n * quotient_poly_degree coefficients (`out`: optional preallocated buffer)"""
         arr = as_fr(a)
         if arr.shape[0] != self.extended_len():
             raise B2Error(B2_ERR_ARG, "assert_eq!(a.values.len(), self.extended_len())")
         require_gpu()
         n_out = self.n * self.quotient_poly_degree
-        out = np.empty((n_out, 4), dtype=np.uint64)
+        if out is None:
+            out = np.empty((n_out, 4), dtype=np.uint64)
+        elif out.size != n_out * 4 or not out.flags.c_contiguous:
+            raise B2Error(B2_ERR_ARG, "out has the wrong size")
+        out = out.reshape(n_out, 4)
         check(lib().b2_extended_to_coeff(ptr(arr), ptr(out), n_out, self.extended_k, ptr(self.g_coset),
                                          ptr(self.g_coset_inv), ptr(self.extended_omega_inv),
                                          ptr(self.extended_ifft_divisor)))

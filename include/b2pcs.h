@@ -173,6 +173,9 @@ int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void
  * multiplications per second and wide MACs/s counted as 128 per product (64 product + 64
  * reduction terms, the accounting of SURVEY.md section 8d). */
 int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s);
+/* FP64 FMA rate of the device (diagnostic: documents why the fp64 pipe is / is not a usable
+ * second multiplier for the bignum kernels on this part). */
+int b2_dfma_probe(double* dfma_per_s);
 /* Timing of the last b2_msm / b2_ntt_exec / b2_commit_batch on this device, CUDA events
  * on the launching stream: kernel-only ms and (host variants) total ms incl. copies. */
 int b2_last_timing(double* kernel_ms, double* total_ms);
