@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -93,24 +95,45 @@ struct NttPlan {
     std::vector<void*> owned;
 };
 
-struct DeviceCtx {
-    int dev = -1;
-    bool ready = false;
-    std::mutex mu;
+struct DeviceCtx;
+
+// One execution lane = a stream + its own grow-only workspace + events.  Concurrent host threads
+// (the reference calls this path from rayon workers, plonk/prover.rs:293,470,535,561,643) each
+// take a free lane, so the H2D copy of one call overlaps the kernels and the D2H of others
+// instead of being serialised behind a single per-device lock.
+struct Lane {
+    DeviceCtx* dev = nullptr;
+    int index = 0;
     cudaStream_t stream = nullptr;
     int sms = 0;
     int acc_blocks_per_sm = 1;
-    uint64_t launches = 0;
+    std::atomic<uint64_t>* launch_counter = nullptr;
     // MSM workspace
     Buf scalars, codes, sorted, counts, offsets, cursor, buckets, part_pt, part_bucket, block_out, window_sums,
         out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids;
     // NTT workspace
     Buf ntt_in, ntt_work, ntt_out;
-    std::map<std::string, NttPlan*> plans;
     // timing
     cudaEvent_t ev[16];
+    cudaEvent_t busy;            // last work enqueued on a caller-provided stream (async _dev calls)
+    bool busy_valid = false;
     double last_kernel_ms = 0, last_total_ms = 0;
     double phases[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+constexpr int MAX_LANES = 8;
+
+struct DeviceCtx {
+    int dev = -1;
+    bool ready = false;
+    std::mutex mu;                  // lane pool + lazy init
+    std::condition_variable cv;
+    int nlanes = 0;
+    Lane lanes[MAX_LANES];
+    bool lane_free[MAX_LANES];
+    std::mutex plan_mu;             // NTT plan cache
+    std::map<std::string, NttPlan*> plans;
+    std::atomic<uint64_t> launches{0};
 };
 
 constexpr int MAX_DEV = 16;
@@ -119,35 +142,101 @@ std::mutex g_srs_mu;
 std::map<b2_handle_t, Srs> g_srs;
 b2_handle_t g_next_handle = 1;
 
-int ctx_get(DeviceCtx** out) {
+struct LastCall {
+    double kernel_ms = 0, total_ms = 0;
+    Lane* lane = nullptr;
+};
+thread_local LastCall g_last;
+
+int dev_get(DeviceCtx** out) {
     int dev = g_dev;
     if (dev < 0 || dev >= MAX_DEV) return fail(B2_ERR_ARG, "bad device %d", dev);
     DeviceCtx& c = g_ctx[dev];
     CK(cudaSetDevice(dev));
+    std::lock_guard<std::mutex> lk(c.mu);
     if (!c.ready) {
-        std::lock_guard<std::mutex> lk(c.mu);
-        if (!c.ready) {
-            c.dev = dev;
-            CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-            cudaDeviceProp prop;
-            CK(cudaGetDeviceProperties(&prop, dev));
-            c.sms = prop.multiProcessorCount;
-            CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
-            c.acc_blocks_per_sm = nb > 0 ? nb : 1;
-            for (auto& e : c.ev) CK(cudaEventCreate(&e));
-            c.ready = true;
+        c.dev = dev;
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
+        int nl = 3;
+        if (const char* e = getenv("B2_LANES")) {
+            int v = atoi(e);
+            if (v >= 1 && v <= MAX_LANES) nl = v;
         }
+        for (int i = 0; i < nl; i++) {
+            Lane& l = c.lanes[i];
+            l.dev = &c;
+            l.index = i;
+            l.sms = prop.multiProcessorCount;
+            l.acc_blocks_per_sm = nb > 0 ? nb : 1;
+            l.launch_counter = &c.launches;
+            CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            for (auto& e : l.ev) CK(cudaEventCreate(&e));
+            CK(cudaEventCreateWithFlags(&l.busy, cudaEventDisableTiming));
+            c.lane_free[i] = true;
+        }
+        c.nlanes = nl;
+        c.ready = true;
     }
     *out = &c;
     return B2_OK;
 }
 
+// RAII: take a free lane of the current device (blocks while all are busy)
+struct LaneLock {
+    Lane* lane = nullptr;
+    int acquire() {
+        DeviceCtx* c;
+        int rc = dev_get(&c);
+        if (rc) return rc;
+        std::unique_lock<std::mutex> lk(c->mu);
+        for (;;) {
+            for (int i = 0; i < c->nlanes; i++)
+                if (c->lane_free[i]) {
+                    c->lane_free[i] = false;
+                    lane = &c->lanes[i];
+                    break;
+                }
+            if (lane) break;
+            c->cv.wait(lk);
+        }
+        lk.unlock();
+        if (lane->busy_valid) {  // async work of a previous _dev call may still use this workspace
+            cudaError_t e = cudaStreamWaitEvent(lane->stream, lane->busy, 0);
+            if (e != cudaSuccess) return fail(B2_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+        }
+        g_last.lane = lane;
+        return B2_OK;
+    }
+    // work was enqueued on a caller stream: the next user of the lane must order after it
+    int order_after_busy(cudaStream_t user) {
+        if (user != lane->stream && lane->busy_valid) CK(cudaStreamWaitEvent(user, lane->busy, 0));
+        return B2_OK;
+    }
+    int mark_busy(cudaStream_t user) {
+        if (user == lane->stream) return B2_OK;
+        CK(cudaEventRecord(lane->busy, user));
+        lane->busy_valid = true;
+        return B2_OK;
+    }
+    ~LaneLock() {
+        if (!lane) return;
+        DeviceCtx* c = lane->dev;
+        {
+            std::lock_guard<std::mutex> lk(c->mu);
+            c->lane_free[lane->index] = true;
+        }
+        c->cv.notify_one();
+    }
+};
+
 #define LAUNCH(ctx, kernel, grid, block, smem, st, ...)                                                    \
     do {                                                                                                   \
         kernel<<<(grid), (block), (smem), (st)>>>(__VA_ARGS__);                                            \
-        (ctx).launches++;                                                                                  \
+        (*(ctx).launch_counter)++;                                                                               \
         cudaError_t le_ = cudaGetLastError();                                                              \
         if (le_ != cudaSuccess)                                                                            \
             return fail(B2_ERR_CUDA, "%s:%d launch %s: %s", __FILE__, __LINE__, #kernel,                   \
@@ -269,7 +358,7 @@ struct MsmBases {
 };
 
 // device-pointer MSM on stream `st`; writes a 96 B Jacobian (not normalised) to d_out
-int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint32_t max_bits,
+int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint32_t max_bits,
             void* d_out, cudaStream_t st, bool record_phases, bool reset_flag = true) {
     if (max_bits > 254) max_bits = 254;
     MsmGeom g;
@@ -379,7 +468,7 @@ int msm_run(DeviceCtx& ctx, const MsmBases& mb, const void* d_scalars, size_t n,
     return B2_OK;
 }
 
-int msm_collect_phases(DeviceCtx& ctx) {
+int msm_collect_phases(Lane& ctx) {
     CK(cudaEventSynchronize(ctx.ev[7]));
     for (int i = 0; i < 7; i++) {
         float ms = 0;
@@ -390,10 +479,11 @@ int msm_collect_phases(DeviceCtx& ctx) {
     CK(cudaEventElapsedTime(&ms, ctx.ev[0], ctx.ev[7]));
     ctx.phases[7] = ms;
     ctx.last_kernel_ms = ms;
+    g_last.kernel_ms = ms;
     return B2_OK;
 }
 
-int write_identity(DeviceCtx& ctx, void* d_out, cudaStream_t st) {
+int write_identity(Lane& ctx, void* d_out, cudaStream_t st) {
     // (0, 1, 0) in Montgomery form
     uint32_t h[24];
     memset(h, 0, sizeof h);
@@ -417,7 +507,7 @@ int srs_lookup(b2_handle_t h, Srs* out) {
 constexpr size_t MSM_MAX_N = (size_t)1 << 26;  // per launch (entry offsets are 32-bit)
 
 // MSM over possibly > MSM_MAX_N points by splitting; all on stream `st`
-int msm_run_split(DeviceCtx& ctx, const Srs& s, size_t offset, const char* d_scalars, size_t n, uint32_t max_bits,
+int msm_run_split(Lane& ctx, const Srs& s, size_t offset, const char* d_scalars, size_t n, uint32_t max_bits,
                   void* d_out, cudaStream_t st, bool record, bool reset_flag = true) {
     MsmBases mb{s.d + offset * 64, s.table, s.tc, s.tW, s.n, offset};
     if (n <= MSM_MAX_N) return msm_run(ctx, mb, d_scalars, n, max_bits, d_out, st, record, reset_flag);
@@ -435,7 +525,7 @@ int msm_run_split(DeviceCtx& ctx, const Srs& s, size_t offset, const char* d_sca
     return B2_OK;
 }
 
-int check_bound_flag(DeviceCtx& ctx, cudaStream_t st) {
+int check_bound_flag(Lane& ctx, cudaStream_t st) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, ctx.errflag.p, 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -444,7 +534,7 @@ int check_bound_flag(DeviceCtx& ctx, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------- NTT
-int ntt_table(DeviceCtx& ctx, NttPlan* pl, Fr** out, const Fr& base, unsigned long long mult, uint32_t count,
+int ntt_table(Lane& ctx, NttPlan* pl, Fr** out, const Fr& base, unsigned long long mult, uint32_t count,
               bool scaled, const Fr& scale) {
     void* p = nullptr;
     CK(cudaMalloc(&p, (size_t)count * 32));
@@ -455,7 +545,7 @@ int ntt_table(DeviceCtx& ctx, NttPlan* pl, Fr** out, const Fr& base, unsigned lo
     return B2_OK;
 }
 
-int ntt_get_plan(DeviceCtx& ctx, const void* omega, const void* divisor, uint32_t log_n, NttPlan** out) {
+int ntt_get_plan(Lane& ctx, const void* omega, const void* divisor, uint32_t log_n, NttPlan** out) {
     std::string key((const char*)omega, 32);
     key.append((const char*)&log_n, 4);
     if (divisor) {
@@ -464,8 +554,9 @@ int ntt_get_plan(DeviceCtx& ctx, const void* omega, const void* divisor, uint32_
     } else {
         key.push_back(0);
     }
-    auto it = ctx.plans.find(key);
-    if (it != ctx.plans.end()) {
+    std::lock_guard<std::mutex> plk(ctx.dev->plan_mu);
+    auto it = ctx.dev->plans.find(key);
+    if (it != ctx.dev->plans.end()) {
         *out = it->second;
         return B2_OK;
     }
@@ -516,14 +607,14 @@ int ntt_get_plan(DeviceCtx& ctx, const void* omega, const void* divisor, uint32_
         }
     }
     CK(cudaStreamSynchronize(ctx.stream));
-    ctx.plans[key] = pl;
+    ctx.dev->plans[key] = pl;
     *out = pl;
     return B2_OK;
 }
 
 // all-device NTT of `cols` columns.  in -> (work) -> out.  `work` must hold cols * 2^log_n
 // elements when npass > 1.  out may alias in.
-int ntt_run_dev(DeviceCtx& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, uint64_t n_in, void* d_out,
+int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, uint64_t n_in, void* d_out,
                 uint64_t out_stride, uint64_t n_out, void* d_work, uint64_t cols, const Fr* coset_in,
                 const Fr* coset_out, cudaStream_t st) {
     const uint32_t k = pl->log_n;
@@ -623,28 +714,27 @@ int b2_set_device(int device) {
 }
 int b2_get_device(void) { return g_dev; }
 int b2_synchronize(void) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(ctx->stream));
     CK(cudaDeviceSynchronize());
     return B2_OK;
 }
 uint64_t b2_launch_count(int reset) {
-    DeviceCtx* ctx;
-    if (ctx_get(&ctx)) return 0;
-    uint64_t v = ctx->launches;
-    if (reset) ctx->launches = 0;
+    DeviceCtx* dev;
+    if (dev_get(&dev)) return 0;
+    uint64_t v = dev->launches.load();
+    if (reset) dev->launches.store(0);
     return v;
 }
 
 // ---- SRS
 int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_t* out) {
     if (!bases || !out || n == 0 || stride_bytes < 64) return fail(B2_ERR_ARG, "srs_register: bad arguments");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     char* d = nullptr;
     CK(cudaMalloc(&d, n * 64));
     cudaError_t e;
@@ -658,16 +748,16 @@ int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_
     }
     std::lock_guard<std::mutex> lk2(g_srs_mu);
     b2_handle_t h = g_next_handle++;
-    g_srs[h] = Srs{ctx->dev, d, n, nullptr, 0, 0};
+    g_srs[h] = Srs{ctx->dev->dev, d, n, nullptr, 0, 0};
     *out = h;
     return B2_OK;
 }
 int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t* out) {
     if (!out || n == 0) return fail(B2_ERR_ARG, "srs_synthetic: bad arguments");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     char* d = nullptr;
     CK(cudaMalloc(&d, n * 64));
     LAUNCH(*ctx, srs_synth_kernel, (unsigned)((n + 127) / 128), 128, 0, ctx->stream, d, (unsigned long long)n,
@@ -675,7 +765,7 @@ int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t*
     CK(cudaStreamSynchronize(ctx->stream));
     std::lock_guard<std::mutex> lk2(g_srs_mu);
     b2_handle_t h = g_next_handle++;
-    g_srs[h] = Srs{ctx->dev, d, n, nullptr, 0, 0};
+    g_srs[h] = Srs{ctx->dev->dev, d, n, nullptr, 0, 0};
     *out = h;
     return B2_OK;
 }
@@ -699,11 +789,11 @@ int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits) {
         return fail(B2_ERR_ARG, "srs_precompute: %u windows x %zu points exceed the 31-bit point index", W, s.n);
     int save = g_dev;
     g_dev = s.device;
-    DeviceCtx* ctx;
-    rc = ctx_get(&ctx);
+    LaneLock ll;
+    rc = ll.acquire();
     g_dev = save;
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     char* t = nullptr;
     cudaError_t e = cudaMalloc(&t, (size_t)W * s.n * 64);
     if (e != cudaSuccess) {
@@ -774,13 +864,17 @@ int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, 
     int rc = srs_lookup(srs, &s);
     if (rc) return rc;
     if (offset + n > s.n) return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
-    DeviceCtx* ctx;
-    if ((rc = ctx_get(&ctx))) return rc;
-    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    LaneLock ll;
+    if ((rc = ll.acquire())) return rc;
+    Lane* ctx = ll.lane;
+    if (s.device != ctx->dev->dev)
+        return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if ((rc = ll.order_after_busy(st))) return rc;
     if (n == 0 || max_bits == 0) return write_identity(*ctx, d_out_jac96, st);
-    return msm_run_split(*ctx, s, offset, (const char*)d_scalars, n, max_bits, d_out_jac96, st, true);
+    rc = msm_run_split(*ctx, s, offset, (const char*)d_scalars, n, max_bits, d_out_jac96, st, true);
+    if (rc) return rc;
+    return ll.mark_busy(st);
 }
 
 int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96) {
@@ -789,10 +883,11 @@ int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32
     int rc = srs_lookup(srs, &s);
     if (rc) return rc;
     if (offset + n > s.n) return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
-    DeviceCtx* ctx;
-    if ((rc = ctx_get(&ctx))) return rc;
-    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    LaneLock ll;
+    if ((rc = ll.acquire())) return rc;
+    Lane* ctx = ll.lane;
+    if (s.device != ctx->dev->dev)
+        return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
     cudaStream_t st = ctx->stream;
     if ((rc = ctx->out96.reserve(96))) return rc;
     if (n == 0 || max_bits == 0) {
@@ -812,6 +907,7 @@ int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
+    g_last.total_ms = ms;
     return B2_OK;
 }
 
@@ -819,10 +915,10 @@ int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_
     if (!out_jac96 || (n && (!coeffs || !bases))) return fail(B2_ERR_ARG, "best_multiexp: null pointer");
     b2_handle_t h = 0;
     if (n == 0) {
-        DeviceCtx* ctx;
-        int rc = ctx_get(&ctx);
+        LaneLock ll;
+        int rc = ll.acquire();
         if (rc) return rc;
-        std::lock_guard<std::mutex> lk(ctx->mu);
+        Lane* ctx = ll.lane;
         if ((rc = ctx->out96.reserve(96))) return rc;
         if ((rc = write_identity(*ctx, ctx->out96.p, ctx->stream))) return rc;
         CK(cudaMemcpy(out_jac96, ctx->out96.p, 96, cudaMemcpyDeviceToHost));
@@ -837,10 +933,10 @@ int b2_best_multiexp(const void* coeffs, const void* bases, size_t n, void* out_
 
 int b2_g1_sum(const void* jac96, size_t count, void* out_jac96) {
     if (!out_jac96 || (count && !jac96)) return fail(B2_ERR_ARG, "g1_sum: null pointer");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     if ((rc = ctx->partials.reserve(std::max<size_t>(count, 1) * 96))) return rc;
     if ((rc = ctx->out96.reserve(96))) return rc;
     if (count) CK(cudaMemcpyAsync(ctx->partials.p, jac96, count * 96, cudaMemcpyHostToDevice, ctx->stream));
@@ -860,13 +956,13 @@ int b2_g1_normalize(void* jac96, size_t count) {
 
 int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream) {
     if (!d_out_jac96 || (count && !d_jac96)) return fail(B2_ERR_ARG, "g1_sum_dev: null pointer");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
     LAUNCH(*ctx, g1_sum_kernel, 1, 32, 0, st, (const char*)d_jac96, (uint32_t)count, (char*)d_out_jac96);
-    return B2_OK;
+    return B2_OK;   // uses no lane workspace
 }
 
 // ---- NTT
@@ -878,10 +974,10 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
         return fail(B2_ERR_ARG, "ntt: n_in/n_out must be in [1, 2^log_n]");
     if (d->columns == 0) return B2_OK;
     if (d->in_stride < d->n_in || d->out_stride < d->n_out) return fail(B2_ERR_ARG, "ntt: stride shorter than column");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     NttPlan* pl;
     if ((rc = ntt_get_plan(*ctx, d->omega, d->divisor, d->log_n, &pl))) return rc;
     Fr cin[2], cout[2];
@@ -890,49 +986,57 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
     const Fr* pcin = d->coset_in ? cin : nullptr;
     const Fr* pcout = d->coset_out ? cout : nullptr;
 
+    // location: 0 host -> host, 1 device -> device, 2 host -> device, 3 device -> host
+    if (d->location > 3) return fail(B2_ERR_ARG, "ntt: location must be 0..3");
+    const bool in_host = (d->location == 0 || d->location == 2);
+    const bool out_host = (d->location == 0 || d->location == 3);
+    const bool async = !in_host && !out_host && d->stream;
     // sub-batch so that the scratch stays bounded
     const size_t col_bytes = (size_t)N * 32;
     const size_t limit = ntt_scratch_limit();
-    uint64_t sub = std::max<uint64_t>(1, limit / (col_bytes * (d->location == 0 ? 2 : 1)));
+    uint64_t sub = std::max<uint64_t>(1, limit / (col_bytes * 2));
     sub = std::min<uint64_t>(sub, d->columns);
-    cudaStream_t st = (d->location == 1 && d->stream) ? (cudaStream_t)d->stream : ctx->stream;
+    cudaStream_t st = async ? (cudaStream_t)d->stream : ctx->stream;
+    if ((rc = ll.order_after_busy(st))) return rc;
     float k_ms_total = 0;
     CK(cudaEventRecord(ctx->ev[8], st));
     for (uint64_t c0 = 0; c0 < d->columns; c0 += sub) {
         const uint64_t cc = std::min<uint64_t>(sub, d->columns - c0);
-        if (d->location == 1) {
-            if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
-            const char* in = (const char*)d->in + c0 * d->in_stride * 32;
-            char* out = (char*)d->out + c0 * d->out_stride * 32;
-            CK(cudaEventRecord(ctx->ev[10], st));
-            if ((rc = ntt_run_dev(*ctx, pl, in, d->in_stride, d->n_in, out, d->out_stride, d->n_out, ctx->ntt_work.p,
-                                  cc, pcin, pcout, st)))
-                return rc;
-            CK(cudaEventRecord(ctx->ev[11], st));
-        } else {
-            // host: stage in (compact), transform, stage out
-            if ((rc = ctx->ntt_in.reserve(cc * col_bytes))) return rc;  // sized N so it can hold the output too
-            if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
-            const char* hin = (const char*)d->in + c0 * d->in_stride * 32;
-            char* hout = (char*)d->out + c0 * d->out_stride * 32;
-            if ((rc = copy2d(ctx->ntt_in.p, d->n_in, hin, d->in_stride, d->n_in, cc, cudaMemcpyHostToDevice, st))) return rc;
-            CK(cudaEventRecord(ctx->ev[10], st));
-            void* dout = ctx->ntt_in.p;
-            uint64_t dout_stride = N;
-            if (pl->npass == 1 && d->n_in < N) {
-                // single pass reads and writes in one kernel: a compact input cannot share the buffer
+        const char* uin = (const char*)d->in + c0 * d->in_stride * 32;
+        char* uout = (char*)d->out + c0 * d->out_stride * 32;
+        if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
+        // input on the device
+        const void* din = uin;
+        uint64_t din_stride = d->in_stride;
+        if (in_host) {
+            // sized for N per column so that it can also receive the output of a multi-pass transform
+            if ((rc = ctx->ntt_in.reserve(cc * (out_host ? col_bytes : (size_t)d->n_in * 32)))) return rc;
+            if ((rc = copy2d(ctx->ntt_in.p, d->n_in, uin, d->in_stride, d->n_in, cc, cudaMemcpyHostToDevice, st))) return rc;
+            din = ctx->ntt_in.p;
+            din_stride = d->n_in;
+        }
+        // output on the device
+        void* dout = uout;
+        uint64_t dout_stride = d->out_stride;
+        if (out_host) {
+            dout_stride = N;
+            const bool reuse_in = in_host && (pl->npass > 1 || d->n_in == N);  // input is consumed by pass 0
+            if (reuse_in) {
+                dout = ctx->ntt_in.p;
+            } else {
                 if ((rc = ctx->ntt_out.reserve(cc * col_bytes))) return rc;
                 dout = ctx->ntt_out.p;
-            } else if (pl->npass == 1) {
-                dout_stride = N;
             }
-            if ((rc = ntt_run_dev(*ctx, pl, ctx->ntt_in.p, d->n_in, d->n_in, dout, dout_stride, d->n_out,
-                                  ctx->ntt_work.p, cc, pcin, pcout, st)))
-                return rc;
-            CK(cudaEventRecord(ctx->ev[11], st));
-            if ((rc = copy2d(hout, d->out_stride, dout, dout_stride, d->n_out, cc, cudaMemcpyDeviceToHost, st))) return rc;
         }
-        if (d->location == 0 || !d->stream) {
+        CK(cudaEventRecord(ctx->ev[10], st));
+        if ((rc = ntt_run_dev(*ctx, pl, din, din_stride, d->n_in, dout, dout_stride, d->n_out, ctx->ntt_work.p, cc, pcin,
+                              pcout, st)))
+            return rc;
+        CK(cudaEventRecord(ctx->ev[11], st));
+        if (out_host &&
+            (rc = copy2d(uout, d->out_stride, dout, dout_stride, d->n_out, cc, cudaMemcpyDeviceToHost, st)))
+            return rc;
+        if (!async) {
             CK(cudaStreamSynchronize(st));
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
@@ -940,12 +1044,16 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
         }
     }
     CK(cudaEventRecord(ctx->ev[9], st));
-    if (d->location == 0 || !d->stream) {
+    if (!async) {
         CK(cudaStreamSynchronize(st));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
         ctx->last_total_ms = ms;
         ctx->last_kernel_ms = k_ms_total;
+        g_last.total_ms = ms;
+        g_last.kernel_ms = k_ms_total;
+    } else {
+        if ((rc = ll.mark_busy(st))) return rc;   // asynchronous on the caller's stream
     }
     return B2_OK;
 }
@@ -1013,10 +1121,10 @@ int b2_extended_to_coeff(const void* a, void* out, uint64_t n_out, uint32_t ext_
 }
 int b2_divide_by_vanishing_poly(void* a, uint32_t ext_k, const void* t_evaluations, uint32_t t_len) {
     if (!a || !t_evaluations || t_len == 0 || (t_len & (t_len - 1))) return fail(B2_ERR_ARG, "divide: bad arguments");
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     const uint64_t N = 1ull << ext_k;
     if ((rc = ctx->ntt_in.reserve(N * 32))) return rc;
     if ((rc = ctx->ntt_out.reserve((size_t)t_len * 32))) return rc;
@@ -1041,10 +1149,11 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
     int rc = srs_lookup(srs, &s);
     if (rc) return rc;
     if (n > s.n) return fail(B2_ERR_ARG, "commit_batch: column length %zu exceeds SRS length %zu", n, s.n);
-    DeviceCtx* ctx;
-    if ((rc = ctx_get(&ctx))) return rc;
-    if (s.device != ctx->dev) return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev);
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    LaneLock ll;
+    if ((rc = ll.acquire())) return rc;
+    Lane* ctx = ll.lane;
+    if (s.device != ctx->dev->dev)
+        return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
     cudaStream_t st = ctx->stream;
     NttPlan* pl = nullptr;
     if (do_ifft && (rc = ntt_get_plan(*ctx, omega_inv, divisor, log_n, &pl))) return rc;
@@ -1094,6 +1203,8 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
     ctx->last_kernel_ms = kms;
+    g_last.total_ms = ms;
+    g_last.kernel_ms = kms;
     for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
     return B2_OK;
@@ -1106,8 +1217,8 @@ int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void
 
 // ---- memory helpers
 int b2_host_alloc(size_t bytes, void** out) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
     if (rc) return rc;
     cudaError_t e = cudaMallocHost(out, bytes);
     if (e != cudaSuccess) {
@@ -1121,8 +1232,8 @@ int b2_host_free(void* p) {
     return B2_OK;
 }
 int b2_dev_alloc(size_t bytes, void** out) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
     if (rc) return rc;
     CK(cudaMalloc(out, bytes));
     return B2_OK;
@@ -1132,15 +1243,15 @@ int b2_dev_free(void* p) {
     return B2_OK;
 }
 int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
     if (rc) return rc;
     CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
     return B2_OK;
 }
 int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
     if (rc) return rc;
     CK(cudaMemcpy(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost));
     return B2_OK;
@@ -1150,10 +1261,10 @@ int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out) {
     if (!a || !b || !out || op < 0 || op > 3 || field < 0 || field > 1) return fail(B2_ERR_ARG, "field_vec: bad arguments");
     if (n == 0) return B2_OK;
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     if ((rc = ctx->ntt_in.reserve(n * 32))) return rc;
     if ((rc = ctx->ntt_work.reserve(n * 32))) return rc;
     if ((rc = ctx->ntt_out.reserve(n * 32))) return rc;
@@ -1172,10 +1283,10 @@ int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void
 }
 
 int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     if ((rc = ctx->out96.reserve(96))) return rc;
     cudaStream_t st = ctx->stream;
     const int iters = 2000, ILP = 4;
@@ -1199,10 +1310,10 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
 }
 
 int b2_dfma_probe(double* dfma_per_s) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    LaneLock ll;
+    int rc = ll.acquire();
     if (rc) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
+    Lane* ctx = ll.lane;
     if ((rc = ctx->out96.reserve(96))) return rc;
     cudaStream_t st = ctx->stream;
     const int iters = 20000, ILP = 8;
@@ -1224,22 +1335,18 @@ int b2_dfma_probe(double* dfma_per_s) {
 }
 
 int b2_last_timing(double* kernel_ms, double* total_ms) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
-    if (rc) return rc;
-    if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
-    if (total_ms) *total_ms = ctx->last_total_ms;
+    // of the last host-pointer call made by THIS thread
+    if (kernel_ms) *kernel_ms = g_last.kernel_ms;
+    if (total_ms) *total_ms = g_last.total_ms;
     return B2_OK;
 }
 int b2_last_msm_phases(double* phases) {
-    DeviceCtx* ctx;
-    int rc = ctx_get(&ctx);
+    // CUDA-event times of the last MSM this thread ran (valid until another call reuses its lane)
+    Lane* ln = g_last.lane;
+    if (!ln) return fail(B2_ERR_ARG, "no MSM has run on this thread");
+    int rc = msm_collect_phases(*ln);
     if (rc) return rc;
-    {
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        if ((rc = msm_collect_phases(*ctx))) return rc;
-    }
-    for (int i = 0; i < 8; i++) phases[i] = ctx->phases[i];
+    for (int i = 0; i < 8; i++) phases[i] = ln->phases[i];
     return B2_OK;
 }
 

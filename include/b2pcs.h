@@ -107,7 +107,7 @@ int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* st
 /* ---- NTT -------------------------------------------------------------------------- */
 typedef struct b2_ntt_desc {
     uint32_t log_n;        /* transform length 2^log_n, 1 <= log_n <= 28 (Fr::S) */
-    uint32_t location;     /* 0: in/out are host pointers; 1: device pointers */
+    uint32_t location;     /* 0: host -> host; 1: device -> device; 2: host in, device out; 3: device in, host out */
     const void* omega;     /* 32 B, primitive 2^log_n-th root of unity */
     const void* divisor;   /* NULL, or 32 B multiplied into every output (iNTT 2^-k) */
     const void* coset_in;  /* NULL, or 64 B {z1, z2}: x[i] *= z_(i%3) for i%3 != 0 before the transform */
@@ -119,7 +119,7 @@ typedef struct b2_ntt_desc {
     uint64_t in_stride;    /* elements between input columns */
     void* out;             /* may equal `in` */
     uint64_t out_stride;
-    void* stream;          /* location 1 only: cudaStream_t or NULL */
+    void* stream;          /* location 1 only: cudaStream_t (call is asynchronous on it) or NULL */
 } b2_ntt_desc;
 /* General entry point; the functions below are thin wrappers over it. */
 int b2_ntt_exec(const b2_ntt_desc* desc);

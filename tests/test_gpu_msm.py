@@ -265,3 +265,31 @@ def test_cpp_host_mirror_selftest(gpu):
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "host_selftest ok" in out.stdout
+
+
+def test_concurrent_callers_share_the_device(gpu):
+    """the reference calls this path from rayon workers (plonk/prover.rs:293,470,535,561,643): several host
+    threads commit / transform at once; every call takes its own lane (stream + workspace)"""
+    from concurrent.futures import ThreadPoolExecutor
+    k = 12
+    n = 1 << k
+    bases = _bases(n, 0x41)
+    srs = Srs.register(bases).precompute()
+    dom = h2.EvaluationDomain(5, k)
+    cols = [cref.random_fr_mont(n, 0x500 + i) for i in range(12)]
+    want_pts = [_want(c, bases) for c in cols]
+    want_ntt = [cref.ifft(c, dom.omega_inv, dom.ifft_divisor, k, 8) for c in cols]
+
+    def work(i):
+        gpu.set_device(0)
+        p = h2.best_multiexp(cols[i], srs)
+        a = cols[i].copy()
+        dom.lagrange_to_coeff(a)
+        return _affine(p), a
+
+    with ThreadPoolExecutor(6) as ex:
+        res = list(ex.map(work, range(len(cols)))) + list(ex.map(work, range(len(cols))))
+    for i, (p, a) in enumerate(res):
+        assert p == want_pts[i % len(cols)]
+        assert np.array_equal(a, want_ntt[i % len(cols)])
+    srs.free()

@@ -161,3 +161,40 @@ def test_three_pass_sizes(gpu):
     assert got == want
     h2.gpu_ifft(s, enc(omi), k, enc(div))
     assert np.array_equal(s, orig)
+
+
+def test_mixed_host_device_locations(gpu):
+    """b2_ntt_exec locations 2 (host in, device out) and 3 (device in, host out)"""
+    import ctypes
+    from halo2_gpu_specific_b200._lib import NttDesc
+    L = gpu.lib()
+    k = 13
+    n = 1 << k
+    dom = h2.EvaluationDomain(5, k)
+    x = cref.random_fr_mont(n, 0x77)
+    want = cref.coeff_to_extended(x, k, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega, 8)
+    d_ext = ctypes.c_void_p()
+    gpu.check(L.b2_dev_alloc(dom.extended_len() * 32, ctypes.byref(d_ext)))
+    z = np.concatenate([dom.g_coset, dom.g_coset_inv])
+    e = NttDesc()
+    e.log_n, e.location, e.omega = dom.extended_k, 2, dom.extended_omega.ctypes.data
+    e.coset_in = z.ctypes.data
+    e.n_in, e.in_stride = n, n
+    e.n_out = e.out_stride = dom.extended_len()
+    e.columns, e.in_, e.out = 1, x.ctypes.data, d_ext.value
+    gpu.check(L.b2_ntt_exec(ctypes.byref(e)))
+    got = np.empty_like(want)
+    gpu.check(L.b2_memcpy_d2h(gpu.ptr(got), d_ext, got.nbytes))
+    assert np.array_equal(got, want)
+    # device in -> host out: extended_to_coeff of the resident extended column
+    zi = np.concatenate([dom.g_coset_inv, dom.g_coset])
+    f = NttDesc()
+    f.log_n, f.location, f.omega = dom.extended_k, 3, dom.extended_omega_inv.ctypes.data
+    f.divisor, f.coset_out = dom.extended_ifft_divisor.ctypes.data, zi.ctypes.data
+    f.n_in = f.in_stride = dom.extended_len()
+    f.n_out = f.out_stride = n * dom.quotient_poly_degree
+    back = np.empty((n * dom.quotient_poly_degree, 4), dtype=np.uint64)
+    f.columns, f.in_, f.out = 1, d_ext.value, back.ctypes.data
+    gpu.check(L.b2_ntt_exec(ctypes.byref(f)))
+    assert np.array_equal(back[:n], x) and not back[n:].any()
+    L.b2_dev_free(d_ext)
