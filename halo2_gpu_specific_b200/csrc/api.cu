@@ -90,6 +90,7 @@ struct NttPlan {
     Fr* tw_lo = nullptr;
     Fr* tw_hi = nullptr;         // unscaled
     Fr* tw_hi_scaled = nullptr;  // times divisor (pass 0 of an iNTT); == tw_hi when no divisor
+    Fr* tw_full = nullptr;       // w^e (times divisor), e < N/2: pass-0 twiddles with one product per element
     bool has_div = false;
     Fr div;
     std::vector<void*> owned;
@@ -606,6 +607,14 @@ int ntt_get_plan(Lane& ctx, const void* omega, const void* divisor, uint32_t log
                 return rc;
         }
     }
+    // full (half-length) pass-0 twiddle table while it stays small next to 180 GB of HBM
+    size_t full_limit = (size_t)512 << 20;
+    if (const char* e = getenv("B2_NTT_FULL_TW_MB")) full_limit = (size_t)atoll(e) << 20;
+    if (P > 1 && (((size_t)16) << log_n) <= full_limit) {
+        if ((rc = ntt_table(ctx, pl, &pl->tw_full, w, 1ull, 1u << (log_n - 1), divisor != nullptr,
+                            divisor ? pl->div : none)))
+            return rc;
+    }
     CK(cudaStreamSynchronize(ctx.stream));
     ctx.dev->plans[key] = pl;
     *out = pl;
@@ -641,6 +650,8 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         a.tw_sub = pl->tw_sub[p];
         a.tw_lo = pl->tw_lo;
         a.tw_hi = first ? pl->tw_hi_scaled : pl->tw_hi;
+        a.tw_full = first ? pl->tw_full : nullptr;
+        if (first && !last && pl->tw_full && pl->has_div) a.scale_out = 1;  // table entry 0 is the divisor, not 1
         if (first && coset_in) {
             a.coset_in = 1;
             a.zin1 = coset_in[0];

@@ -41,6 +41,8 @@ struct NttPassArgs {
     const Fr* tw_sub;                   // w_{2^m}^j, j < 2^(m-1)
     const Fr* tw_lo;                    // w_N^j, j < 2^tw_h
     const Fr* tw_hi;                    // w_N^(j * 2^tw_h) (times the divisor for pass 0 of an iNTT)
+    const Fr* tw_full;                  // optional: w_N^e for e < N/2 (times the divisor), used by pass 0;
+                                        // w^(e + N/2) = -w^e.  One product per element instead of two.
     int coset_in;                       // first pass: multiply x[i] by zin[i % 3 - 1]
     int coset_out;                      // last pass : multiply X[o] by zout[o % 3 - 1]
     int scale_out;                      // last pass : multiply everything by `scale` (P == 1 iNTT)
@@ -189,11 +191,19 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
         const uint64_t i_next = L >> (a.s_lo - m_next);
         const uint32_t shift = a.s_lo - m_next;
         const uint64_t lo_mask = (1ull << a.tw_h) - 1ull;
+        const bool full = first && a.tw_full != nullptr;
+        const uint64_t half_mask = (1ull << (a.log_n - 1)) - 1ull;
         for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
             Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(j, hs));
             const uint64_t opart = ntt_digit_reverse((H << m) | j, a.mm, (int)a.pass + 1);
             const uint64_t e = (i_next * opart) << shift;
-            if (e != 0) {
+            if (full) {
+                // entry 0 carries the iNTT divisor (or 1): skip the product only when it is 1
+                if (e != 0 || a.scale_out) {
+                    x = fp_mul<FrParams>(x, fp_load_nc<FrParams>(a.tw_full + (e & half_mask)));
+                    if (e >> (a.log_n - 1)) x = fp_neg<FrParams>(x);
+                }
+            } else if (e != 0) {
                 Fr t = fp_mul<FrParams>(fp_load_nc<FrParams>(a.tw_lo + (e & lo_mask)),
                                         fp_load_nc<FrParams>(a.tw_hi + (e >> a.tw_h)));
                 x = fp_mul<FrParams>(x, t);
