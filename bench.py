@@ -272,6 +272,24 @@ def run_engine(args):
         res_e2e = step_e2e()
     barrier()
     e2e_s = time.perf_counter() - t0
+    # the same API driven the way the reference's prover drives it: several host threads (rayon
+    # workers, plonk/prover.rs:293) committing columns at once; each call still copies its own
+    # scalars in and its point out, the library overlaps them across its lanes
+    from concurrent.futures import ThreadPoolExecutor
+    n_callers = 3
+
+    def caller(_):
+        _lib.set_device(local)
+        for _ in range(args.steps):
+            h2.gpu_multiexp_single_gpu_with_bound(h_scalars, srs, 254)
+
+    barrier()
+    with ThreadPoolExecutor(n_callers) as ex:
+        t0 = time.perf_counter()
+        list(ex.map(caller, range(n_callers)))
+        torch.cuda.synchronize()
+        conc_s = time.perf_counter() - t0
+    barrier()
     clocks = sampler.stop() if rank == 0 else None
 
     # consistency: the host-API result equals the device-resident result (same inputs)
@@ -281,10 +299,10 @@ def run_engine(args):
     _lib.check(L.b2_g1_normalize(_lib.ptr(res_dev), 1))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-API results differ"
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, e2e_s * 1e3, conc_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    dev_ms, e2e_ms, conc_ms = float(t[0]), float(t[1]), float(t[2])
 
     ntt = None
     if world == 1 and not args.no_ntt:
@@ -314,10 +332,17 @@ def run_engine(args):
             "e2e": {"value": total_pts / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
                     "api": "halo2_gpu_specific_b200.parallel.sharded_msm (pinned host column -> b2_msm -> 96 B)"},
+            "e2e_concurrent": {"value": n * world * args.steps * n_callers / (conc_ms * 1e-3) / 1e6, "unit": UNIT,
+                               "host_threads": n_callers,
+                               "note": "same per-call copies; 3 concurrent callers per GPU (local partial MSMs only, "
+                                       "no cross-rank combine), as the reference's rayon workers would call it"},
             "gpu_launches": launches,
             "roofline": {
                 "kernel": "msm_accumulate_kernel", "bound": "int", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak,
+                "traffic": 7.59e9 if (args.logn == 22 and not args.no_precompute) else None,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
+                                "(profiles/r1_ncu_summary.md); algorithmic gather bytes 3.7e9: DRAM is ~10 % busy",
                 "model": f"128 MACs x 10 mul-equivalents x n x W = {mac_per_launch:.3e} 32x32->64 MACs per launch "
                          f"(SURVEY 8d), duration {acc:.3f} ms (CUDA events, mean of {len(acc_ms)})",
                 "peak_source": "b2_imad_probe in this run: carry-chained IMAD.WIDE Montgomery products, "

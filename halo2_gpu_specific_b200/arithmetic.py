@@ -119,6 +119,12 @@ def best_multiexp(coeffs, bases: Bases) -> np.ndarray:
     return gpu_multiexp_bound(coeffs, bases, _fr.NUM_BITS)
 
 
+def small_multiexp(coeffs, bases: Bases) -> np.ndarray:
+    """arithmetic.rs:112-132.  The reference keeps this double-and-add loop on the CPU for a handful of
+    points; the same point comes out of the engine's MSM, so the mirror routes it there."""
+    return gpu_multiexp_bound(coeffs, bases, _fr.NUM_BITS)
+
+
 def best_multiexp_gpu_cond(coeffs, bases: Bases) -> np.ndarray:
     """arithmetic.rs:442-458: empty -> identity; otherwise the GPU path.  (The reference
     keeps n <= 2^14 on the CPU; this engine has no CPU path, the result is the same point.)"""

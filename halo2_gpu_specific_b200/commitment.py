@@ -80,3 +80,23 @@ class Params:
     def free(self) -> None:
         self.g.free()
         self.g_lagrange.free()
+
+
+class ParamsVerifier:
+    """poly/commitment.rs:33-40, 384-389: only the piece on the hot path, the small MSM over the public
+    inputs (`commit_lagrange` against the first public_inputs_size Lagrange bases)."""
+
+    def __init__(self, k: int, g_lagrange):
+        self.k = k
+        self.n = 1 << k
+        self.g_lagrange = g_lagrange if isinstance(g_lagrange, Srs) else Srs.register(g_lagrange)
+
+    def commit_lagrange(self, scalars) -> np.ndarray:
+        """:384-389"""
+        p = as_fr(scalars)
+        if p.shape[0] > len(self.g_lagrange):
+            raise B2Error(B2_ERR_ARG, "more scalars than Lagrange bases")
+        return best_multiexp_gpu_cond(p, self.g_lagrange[0:p.shape[0]])
+
+    def free(self) -> None:
+        self.g_lagrange.free()

@@ -212,6 +212,20 @@ struct LaneLock {
         g_last.lane = lane;
         return B2_OK;
     }
+    // non-blocking: returns false when every lane is taken
+    bool try_acquire(DeviceCtx* c) {
+        std::unique_lock<std::mutex> lk(c->mu);
+        for (int i = 0; i < c->nlanes; i++)
+            if (c->lane_free[i]) {
+                c->lane_free[i] = false;
+                lane = &c->lanes[i];
+                break;
+            }
+        lk.unlock();
+        if (!lane) return false;
+        if (lane->busy_valid) cudaStreamWaitEvent(lane->stream, lane->busy, 0);
+        return true;
+    }
     // work was enqueued on a caller stream: the next user of the lane must order after it
     int order_after_busy(cudaStream_t user) {
         if (user != lane->stream && lane->busy_valid) CK(cudaStreamWaitEvent(user, lane->busy, 0));
@@ -323,6 +337,26 @@ void jac_normalise_host(void* p) {
     }
     memcpy(p, v, 96);
 }
+
+// A batch call pipelines its columns over every lane that is free right now: while one lane's
+// kernels run, the next lane's H2D copy and the previous lane's D2H copy are in flight.
+struct LaneSet {
+    LaneLock primary;
+    LaneLock extra[MAX_LANES];
+    std::vector<Lane*> lanes;
+    int acquire(int want) {
+        int rc = primary.acquire();
+        if (rc) return rc;
+        lanes.push_back(primary.lane);
+        for (int i = 0; i + 1 < want && i < MAX_LANES; i++)
+            if (extra[i].try_acquire(primary.lane->dev)) lanes.push_back(extra[i].lane);
+        return B2_OK;
+    }
+    int sync_all() {
+        for (Lane* l : lanes) CK(cudaStreamSynchronize(l->stream));
+        return B2_OK;
+    }
+};
 
 Fr fr_from_bytes(const void* p) {
     Fr r;
@@ -505,7 +539,19 @@ int srs_lookup(b2_handle_t h, Srs* out) {
     return B2_OK;
 }
 
-constexpr size_t MSM_MAX_N = (size_t)1 << 26;  // per launch (entry offsets are 32-bit)
+// per launch (entry offsets are 32-bit); B2_MSM_MAX_N lowers it so that tests can exercise the split path
+size_t msm_max_n() {
+    static size_t v = 0;
+    if (!v) {
+        v = (size_t)1 << 26;
+        if (const char* e = getenv("B2_MSM_MAX_N")) {
+            long long x = atoll(e);
+            if (x >= 64 && x <= (1ll << 26)) v = (size_t)x;
+        }
+    }
+    return v;
+}
+#define MSM_MAX_N (msm_max_n())
 
 // MSM over possibly > MSM_MAX_N points by splitting; all on stream `st`
 int msm_run_split(Lane& ctx, const Srs& s, size_t offset, const char* d_scalars, size_t n, uint32_t max_bits,
@@ -985,10 +1031,12 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
         return fail(B2_ERR_ARG, "ntt: n_in/n_out must be in [1, 2^log_n]");
     if (d->columns == 0) return B2_OK;
     if (d->in_stride < d->n_in || d->out_stride < d->n_out) return fail(B2_ERR_ARG, "ntt: stride shorter than column");
-    LaneLock ll;
-    int rc = ll.acquire();
+    if (d->location > 3) return fail(B2_ERR_ARG, "ntt: location must be 0..3");
+    const bool wants_pipeline = d->location != 1 && d->columns > 1;
+    LaneSet set;
+    int rc = set.acquire(wants_pipeline ? MAX_LANES : 1);
     if (rc) return rc;
-    Lane* ctx = ll.lane;
+    Lane* ctx = set.primary.lane;
     NttPlan* pl;
     if ((rc = ntt_get_plan(*ctx, d->omega, d->divisor, d->log_n, &pl))) return rc;
     Fr cin[2], cout[2];
@@ -998,32 +1046,41 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
     const Fr* pcout = d->coset_out ? cout : nullptr;
 
     // location: 0 host -> host, 1 device -> device, 2 host -> device, 3 device -> host
-    if (d->location > 3) return fail(B2_ERR_ARG, "ntt: location must be 0..3");
     const bool in_host = (d->location == 0 || d->location == 2);
     const bool out_host = (d->location == 0 || d->location == 3);
     const bool async = !in_host && !out_host && d->stream;
-    // sub-batch so that the scratch stays bounded
     const size_t col_bytes = (size_t)N * 32;
-    const size_t limit = ntt_scratch_limit();
-    uint64_t sub = std::max<uint64_t>(1, limit / (col_bytes * 2));
+    // sub-batch so that the scratch stays bounded; host batches are cut finer so that the lanes
+    // can overlap copy-in, transform and copy-out of neighbouring chunks
+    uint64_t sub = std::max<uint64_t>(1, ntt_scratch_limit() / (col_bytes * 2));
     sub = std::min<uint64_t>(sub, d->columns);
-    cudaStream_t st = async ? (cudaStream_t)d->stream : ctx->stream;
-    if ((rc = ll.order_after_busy(st))) return rc;
+    const size_t nl = set.lanes.size();
+    if ((in_host || out_host) && nl > 1 && d->columns > 1) {
+        uint64_t fine = std::max<uint64_t>(1, d->columns / (2 * nl));
+        // keep chunks big enough to amortise launches: at least ~8 MiB of data
+        const uint64_t min_cols = std::max<uint64_t>(1, ((size_t)8 << 20) / col_bytes);
+        sub = std::min(sub, std::max(fine, min_cols));
+    }
+    cudaStream_t st0 = async ? (cudaStream_t)d->stream : ctx->stream;
+    if ((rc = set.primary.order_after_busy(st0))) return rc;
+    CK(cudaEventRecord(ctx->ev[8], st0));
     float k_ms_total = 0;
-    CK(cudaEventRecord(ctx->ev[8], st));
-    for (uint64_t c0 = 0; c0 < d->columns; c0 += sub) {
+    uint64_t chunk_index = 0;
+    for (uint64_t c0 = 0; c0 < d->columns; c0 += sub, chunk_index++) {
         const uint64_t cc = std::min<uint64_t>(sub, d->columns - c0);
+        Lane* ln = async ? ctx : set.lanes[chunk_index % nl];
+        cudaStream_t st = async ? st0 : ln->stream;
         const char* uin = (const char*)d->in + c0 * d->in_stride * 32;
         char* uout = (char*)d->out + c0 * d->out_stride * 32;
-        if (pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
+        if (pl->npass > 1 && (rc = ln->ntt_work.reserve(cc * col_bytes))) return rc;
         // input on the device
         const void* din = uin;
         uint64_t din_stride = d->in_stride;
         if (in_host) {
             // sized for N per column so that it can also receive the output of a multi-pass transform
-            if ((rc = ctx->ntt_in.reserve(cc * (out_host ? col_bytes : (size_t)d->n_in * 32)))) return rc;
-            if ((rc = copy2d(ctx->ntt_in.p, d->n_in, uin, d->in_stride, d->n_in, cc, cudaMemcpyHostToDevice, st))) return rc;
-            din = ctx->ntt_in.p;
+            if ((rc = ln->ntt_in.reserve(cc * (out_host ? col_bytes : (size_t)d->n_in * 32)))) return rc;
+            if ((rc = copy2d(ln->ntt_in.p, d->n_in, uin, d->in_stride, d->n_in, cc, cudaMemcpyHostToDevice, st))) return rc;
+            din = ln->ntt_in.p;
             din_stride = d->n_in;
         }
         // output on the device
@@ -1033,30 +1090,32 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
             dout_stride = N;
             const bool reuse_in = in_host && (pl->npass > 1 || d->n_in == N);  // input is consumed by pass 0
             if (reuse_in) {
-                dout = ctx->ntt_in.p;
+                dout = ln->ntt_in.p;
             } else {
-                if ((rc = ctx->ntt_out.reserve(cc * col_bytes))) return rc;
-                dout = ctx->ntt_out.p;
+                if ((rc = ln->ntt_out.reserve(cc * col_bytes))) return rc;
+                dout = ln->ntt_out.p;
             }
         }
-        CK(cudaEventRecord(ctx->ev[10], st));
-        if ((rc = ntt_run_dev(*ctx, pl, din, din_stride, d->n_in, dout, dout_stride, d->n_out, ctx->ntt_work.p, cc, pcin,
+        const bool timed = (nl == 1 || !(in_host || out_host)) && !async;
+        if (timed) CK(cudaEventRecord(ln->ev[10], st));
+        if ((rc = ntt_run_dev(*ln, pl, din, din_stride, d->n_in, dout, dout_stride, d->n_out, ln->ntt_work.p, cc, pcin,
                               pcout, st)))
             return rc;
-        CK(cudaEventRecord(ctx->ev[11], st));
+        if (timed) CK(cudaEventRecord(ln->ev[11], st));
         if (out_host &&
             (rc = copy2d(uout, d->out_stride, dout, dout_stride, d->n_out, cc, cudaMemcpyDeviceToHost, st)))
             return rc;
-        if (!async) {
+        if (timed) {
             CK(cudaStreamSynchronize(st));
             float ms = 0;
-            CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
+            CK(cudaEventElapsedTime(&ms, ln->ev[10], ln->ev[11]));
             k_ms_total += ms;
         }
     }
-    CK(cudaEventRecord(ctx->ev[9], st));
     if (!async) {
-        CK(cudaStreamSynchronize(st));
+        if ((rc = set.sync_all())) return rc;
+        CK(cudaEventRecord(ctx->ev[9], st0));
+        CK(cudaStreamSynchronize(st0));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
         ctx->last_total_ms = ms;
@@ -1064,7 +1123,7 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
         g_last.total_ms = ms;
         g_last.kernel_ms = k_ms_total;
     } else {
-        if ((rc = ll.mark_busy(st))) return rc;   // asynchronous on the caller's stream
+        if ((rc = set.primary.mark_busy(st0))) return rc;   // asynchronous on the caller's stream
     }
     return B2_OK;
 }
@@ -1160,62 +1219,59 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
     int rc = srs_lookup(srs, &s);
     if (rc) return rc;
     if (n > s.n) return fail(B2_ERR_ARG, "commit_batch: column length %zu exceeds SRS length %zu", n, s.n);
-    LaneLock ll;
-    if ((rc = ll.acquire())) return rc;
-    Lane* ctx = ll.lane;
+    LaneSet set;
+    if ((rc = set.acquire(columns > 1 ? MAX_LANES : 1))) return rc;
+    Lane* ctx = set.primary.lane;
     if (s.device != ctx->dev->dev)
         return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
-    cudaStream_t st = ctx->stream;
     NttPlan* pl = nullptr;
     if (do_ifft && (rc = ntt_get_plan(*ctx, omega_inv, divisor, log_n, &pl))) return rc;
     const size_t col_bytes = n * 32;
-    uint64_t sub = std::max<uint64_t>(1, ntt_scratch_limit() / (2 * col_bytes));
-    sub = std::min<uint64_t>(sub, columns);
-    if ((rc = ctx->partials.reserve(columns * 96))) return rc;
     if (max_bits > 254) max_bits = 254;
-    float kms = 0;
-    int bound_flag_any = 0;
-    CK(cudaEventRecord(ctx->ev[8], st));
-    for (uint64_t c0 = 0; c0 < columns; c0 += sub) {
-        const uint64_t cc = std::min<uint64_t>(sub, columns - c0);
-        if ((rc = ctx->ntt_in.reserve(cc * col_bytes))) return rc;
-        if (do_ifft && pl->npass > 1 && (rc = ctx->ntt_work.reserve(cc * col_bytes))) return rc;
-        char* h = (char*)columns_data + c0 * col_bytes;
-        CK(cudaMemcpyAsync(ctx->ntt_in.p, h, cc * col_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaEventRecord(ctx->ev[10], st));
-        for (uint64_t c = 0; c < cc; c++) {
-            char* dout = ctx->partials.as<char>() + (c0 + c) * 96;
-            if (max_bits == 0) {
-                if ((rc = write_identity(*ctx, dout, st))) return rc;
-                continue;
-            }
-            // the bound flag is sticky across the whole batch (reset once, read once)
-            if ((rc = msm_run_split(*ctx, s, 0, ctx->ntt_in.as<char>() + c * col_bytes, n, max_bits, dout, st, false,
-                                    c0 == 0 && c == 0)))
+    const size_t nl = set.lanes.size();
+    CK(cudaEventRecord(ctx->ev[8], ctx->stream));
+    // one column per step, lanes round-robin: copy-in of column i+1 and copy-out of column i-1 overlap
+    // the MSM (+ iNTT) of column i
+    for (uint64_t c = 0; c < columns; c++) {
+        Lane* ln = set.lanes[c % nl];
+        cudaStream_t st = ln->stream;
+        char* h = (char*)columns_data + c * col_bytes;
+        if ((rc = ln->ntt_in.reserve(col_bytes))) return rc;
+        if ((rc = ln->out96.reserve(96))) return rc;
+        if (do_ifft && pl->npass > 1 && (rc = ln->ntt_work.reserve(col_bytes))) return rc;
+        CK(cudaMemcpyAsync(ln->ntt_in.p, h, col_bytes, cudaMemcpyHostToDevice, st));
+        if (max_bits == 0) {
+            if ((rc = write_identity(*ln, ln->out96.p, st))) return rc;
+        } else {
+            // the bound flag is sticky per lane for the whole batch (reset once, read once)
+            if ((rc = msm_run_split(*ln, s, 0, ln->ntt_in.as<char>(), n, max_bits, ln->out96.p, st, false, c < nl)))
                 return rc;
         }
+        CK(cudaMemcpyAsync((char*)out_jac96 + c * 96, ln->out96.p, 96, cudaMemcpyDeviceToHost, st));
         if (do_ifft) {
-            if ((rc = ntt_run_dev(*ctx, pl, ctx->ntt_in.p, n, n, ctx->ntt_in.p, n, n, ctx->ntt_work.p, cc, nullptr,
-                                  nullptr, st)))
+            if ((rc = ntt_run_dev(*ln, pl, ln->ntt_in.p, n, n, ln->ntt_in.p, n, n, ln->ntt_work.p, 1, nullptr, nullptr, st)))
                 return rc;
+            CK(cudaMemcpyAsync(h, ln->ntt_in.p, col_bytes, cudaMemcpyDeviceToHost, st));
         }
-        CK(cudaEventRecord(ctx->ev[11], st));
-        if (do_ifft) CK(cudaMemcpyAsync(h, ctx->ntt_in.p, cc * col_bytes, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        float ms = 0;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[10], ctx->ev[11]));
-        kms += ms;
     }
-    CK(cudaMemcpyAsync(out_jac96, ctx->partials.p, columns * 96, cudaMemcpyDeviceToHost, st));
-    if (max_bits != 0) CK(cudaMemcpyAsync(&bound_flag_any, ctx->errflag.p, 4, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(ctx->ev[9], st));
-    CK(cudaStreamSynchronize(st));
+    int bound_flag_any = 0;
+    if (max_bits != 0) {
+        for (size_t l = 0; l < nl && l < columns; l++) {
+            int flag = 0;
+            CK(cudaMemcpyAsync(&flag, set.lanes[l]->errflag.p, 4, cudaMemcpyDeviceToHost, set.lanes[l]->stream));
+            CK(cudaStreamSynchronize(set.lanes[l]->stream));
+            bound_flag_any |= flag;
+        }
+    }
+    if ((rc = set.sync_all())) return rc;
+    CK(cudaEventRecord(ctx->ev[9], ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
     float ms = 0;
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
-    ctx->last_kernel_ms = kms;
+    ctx->last_kernel_ms = 0;
     g_last.total_ms = ms;
-    g_last.kernel_ms = kms;
+    g_last.kernel_ms = 0;
     for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
     return B2_OK;

@@ -293,3 +293,36 @@ def test_concurrent_callers_share_the_device(gpu):
         assert p == want_pts[i % len(cols)]
         assert np.array_equal(a, want_ntt[i % len(cols)])
     srs.free()
+
+
+def test_split_path_for_huge_msm(gpu):
+    """MSMs beyond the per-launch limit are split by point range and summed on the device
+    (same shape as gpu_multiexp_bound, arithmetic.rs:413-440); B2_MSM_MAX_N shrinks the limit"""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np; sys.path.insert(0, %r);"
+        "import halo2_gpu_specific_b200 as h2; from halo2_gpu_specific_b200.arithmetic import Srs;"
+        "from oracle import cref;"
+        "n = 5000; sc = cref.random_fr_mont(n, 3); ks = cref.from_mont(0, cref.random_fr_mont(n, 4));"
+        "b = cref.g1_mul_gen(ks); want = cref.jac_to_affine(cref.best_multiexp(sc, b, 4))[0];"
+        "ok = [np.array_equal(h2.best_multiexp(sc, s)[:8], want) for s in (Srs.register(b), Srs.register(b).precompute())];"
+        "print('SPLIT', ok)"
+    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2_MSM_MAX_N="1024")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "SPLIT [True, True]" in out.stdout, out.stdout + out.stderr
+
+
+def test_small_multiexp_and_params_verifier(gpu):
+    """arithmetic.rs:112-132 (benches/arithmetic.rs shape: a few points) and ParamsVerifier::commit_lagrange
+    (poly/commitment.rs:384-389)"""
+    n = 16
+    bases = _bases(n, 0x61)
+    sc = cref.random_fr_mont(n, 0x62)
+    want = o.small_multiexp(o.fr_decode(sc), o.g1_affine_decode(bases))
+    assert _affine(h2.small_multiexp(sc, bases)) == want
+    pv = h2.ParamsVerifier(6, FIX["params_k6_g_lagrange"])
+    pub = o.fr_encode([5, 0, 7])
+    assert _affine(pv.commit_lagrange(pub)) == _want(pub, FIX["params_k6_g_lagrange"][:3])
+    pv.free()
