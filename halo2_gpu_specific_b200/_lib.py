@@ -45,7 +45,7 @@ SYMBOLS = [
     "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
-    "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
+    "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
 ]
 
@@ -85,6 +85,8 @@ def lib() -> ctypes.CDLL:
         L.b2_commit_batch.argtypes = [u64, vp, u64, sz, u32, ctypes.c_int, vp, vp, u32, vp]
         L.b2_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
         L.b2_host_free.argtypes = [vp]
+        L.b2_host_register.argtypes = [vp, sz]
+        L.b2_host_unregister.argtypes = [vp]
         L.b2_dev_alloc.argtypes = [sz, ctypes.POINTER(vp)]
         L.b2_dev_free.argtypes = [vp]
         L.b2_memcpy_h2d.argtypes = [vp, vp, sz]

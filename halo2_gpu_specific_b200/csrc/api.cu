@@ -111,7 +111,7 @@ struct Lane {
     std::atomic<uint64_t>* launch_counter = nullptr;
     // MSM workspace
     Buf scalars, codes, sorted, counts, offsets, cursor, buckets, part_pt, part_bucket, block_out, window_sums,
-        out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids;
+        out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids, pcounts, poffs, pcursor, ptmp;
     // NTT workspace
     Buf ntt_in, ntt_work, ntt_out;
     // timing
@@ -414,14 +414,17 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
     const size_t nb = (size_t)nsets * g.B;
     const char* d_points = pre ? mb.table : mb.d;
     const uint32_t T = (uint32_t)ctx.sms * (uint32_t)ctx.acc_blocks_per_sm * 128u;
+    // buckets that can be populated: with a single window (bounded scalars, e.g. 16-bit advice values)
+    // digits stay below 2^max_bits, so the reduction only has to visit that prefix of the bucket set
+    uint32_t b_used = g.B;
+    if (g.W == 1 && max_bits < g.c - 1) b_used = 1u << max_bits;
     // buckets per reduce thread: enough blocks to fill the chip, fewer adds per bucket when there are many
-    uint32_t rm = g.B >> 15;
+    uint32_t rm = b_used >> 15;
     rm = rm < 2 ? 2 : (rm > 16 ? 16 : rm);
-    const uint32_t bpw = (g.B + MSM_RT * rm - 1) / (MSM_RT * rm);
+    const uint32_t bpw = (b_used + MSM_RT * rm - 1) / (MSM_RT * rm);
     const uint32_t ntiles = (uint32_t)((nb + SCAN_TILE - 1) / SCAN_TILE);
 
     int rc;
-    if ((rc = ctx.codes.reserve((size_t)g.W * n * 4))) return rc;
     if ((rc = ctx.sorted.reserve((size_t)g.W * n * 4))) return rc;
     if ((rc = ctx.counts.reserve(nb * 4))) return rc;
     if ((rc = ctx.offsets.reserve((nb + 1) * 4))) return rc;
@@ -441,21 +444,57 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
 
     cudaEvent_t* ev = ctx.ev;
     if (record_phases) CK(cudaEventRecord(ev[0], st));
-    CK(cudaMemsetAsync(ctx.counts.p, 0, nb * 4, st));
     if (reset_flag) CK(cudaMemsetAsync(ctx.errflag.p, 0, 4, st));
-    LAUNCH(ctx, msm_digits_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4*)d_scalars,
-           ctx.codes.as<uint32_t>(), ctx.counts.as<uint32_t>(), g, max_bits, ctx.errflag.as<int>());
-    if (record_phases) CK(cudaEventRecord(ev[1], st));
-    LAUNCH(ctx, msm_scan_tile_kernel, ntiles, SCAN_THREADS, 0, st, ctx.counts.as<uint32_t>(),
-           ctx.offsets.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
-    LAUNCH(ctx, msm_scan_top_kernel, 1, SCAN_THREADS, 0, st, ctx.tile_sums.as<uint32_t>(), ntiles,
-           ctx.offsets.as<uint32_t>() + nb);
-    LAUNCH(ctx, msm_scan_add_kernel, ntiles, SCAN_THREADS, 0, st, ctx.offsets.as<uint32_t>(),
-           ctx.cursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
-    if (record_phases) CK(cudaEventRecord(ev[2], st));
-    LAUNCH(ctx, msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), g.W), 256, 0, st,
-           ctx.codes.as<uint32_t>(), ctx.cursor.as<uint32_t>(), ctx.sorted.as<uint32_t>(), g);
-    if (record_phases) CK(cudaEventRecord(ev[3], st));
+    // sort the (bucket, point) entries by bucket
+    // Two-level partitioned sort: measured SLOWER than the global-atomic counting sort on B200 (2^22: 2.3 ms
+    // vs 1.1 ms; its level-1 writes are still one partial sector per entry), so it is opt-in
+    // (B2_MSM_PARTSORT=1) until level 1 stages its runs through shared memory.
+    static const bool part_enabled = getenv("B2_MSM_PARTSORT") && atoi(getenv("B2_MSM_PARTSORT")) == 1;
+    const uint32_t npart = (uint32_t)((nb + PART_BUCKETS - 1) / PART_BUCKETS);
+    const bool use_part = part_enabled && nb >= (1u << 16) && n >= ((size_t)1 << 18) && npart <= PART_MAX;
+    if (use_part) {
+        // two-level partitioned counting sort (local scatters, no global atomics, no global bucket scan)
+        uint32_t tile = (uint32_t)std::max<size_t>(2048, (n + 4095) / 4096);
+        const uint32_t ncta = (uint32_t)((n + tile - 1) / tile);
+        const size_t ncnt = (size_t)npart * ncta;
+        const uint32_t ptiles = (uint32_t)((ncnt + SCAN_TILE - 1) / SCAN_TILE);
+        if ((rc = ctx.pcounts.reserve(ncnt * 4))) return rc;
+        if ((rc = ctx.poffs.reserve((ncnt + 1) * 4))) return rc;
+        if ((rc = ctx.pcursor.reserve(ncnt * 4))) return rc;
+        if ((rc = ctx.tile_sums.reserve((size_t)ptiles * 4 + 16))) return rc;
+        if ((rc = ctx.ptmp.reserve((size_t)g.W * n * 8))) return rc;
+        LAUNCH(ctx, msm_part_count_kernel, ncta, PART_THREADS, npart * 4, st, (const uint4*)d_scalars,
+               ctx.pcounts.as<uint32_t>(), npart, ncta, tile, g, max_bits, ctx.errflag.as<int>());
+        if (record_phases) CK(cudaEventRecord(ev[1], st));
+        LAUNCH(ctx, msm_scan_tile_kernel, ptiles, SCAN_THREADS, 0, st, ctx.pcounts.as<uint32_t>(),
+               ctx.poffs.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)ncnt);
+        LAUNCH(ctx, msm_scan_top_kernel, 1, SCAN_THREADS, 0, st, ctx.tile_sums.as<uint32_t>(), ptiles,
+               ctx.poffs.as<uint32_t>() + ncnt);
+        LAUNCH(ctx, msm_scan_add_kernel, ptiles, SCAN_THREADS, 0, st, ctx.poffs.as<uint32_t>(),
+               ctx.pcursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)ncnt);
+        if (record_phases) CK(cudaEventRecord(ev[2], st));
+        LAUNCH(ctx, msm_part_scatter_kernel, ncta, PART_THREADS, npart * 4, st, (const uint4*)d_scalars,
+               ctx.poffs.as<uint32_t>(), npart, ncta, tile, g, ctx.ptmp.as<uint2>());
+        LAUNCH(ctx, msm_part_sort_kernel, npart, 1024, 0, st, ctx.ptmp.as<uint2>(), ctx.poffs.as<uint32_t>(), npart,
+               ncta, (uint32_t)nb, ctx.offsets.as<uint32_t>(), ctx.sorted.as<uint32_t>());
+        if (record_phases) CK(cudaEventRecord(ev[3], st));
+    } else {
+        if ((rc = ctx.codes.reserve((size_t)g.W * n * 4))) return rc;
+        CK(cudaMemsetAsync(ctx.counts.p, 0, nb * 4, st));
+        LAUNCH(ctx, msm_digits_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4*)d_scalars,
+               ctx.codes.as<uint32_t>(), ctx.counts.as<uint32_t>(), g, max_bits, ctx.errflag.as<int>());
+        if (record_phases) CK(cudaEventRecord(ev[1], st));
+        LAUNCH(ctx, msm_scan_tile_kernel, ntiles, SCAN_THREADS, 0, st, ctx.counts.as<uint32_t>(),
+               ctx.offsets.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
+        LAUNCH(ctx, msm_scan_top_kernel, 1, SCAN_THREADS, 0, st, ctx.tile_sums.as<uint32_t>(), ntiles,
+               ctx.offsets.as<uint32_t>() + nb);
+        LAUNCH(ctx, msm_scan_add_kernel, ntiles, SCAN_THREADS, 0, st, ctx.offsets.as<uint32_t>(),
+               ctx.cursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)nb);
+        if (record_phases) CK(cudaEventRecord(ev[2], st));
+        LAUNCH(ctx, msm_scatter_kernel, dim3((unsigned)((n + 255) / 256), g.W), 256, 0, st,
+               ctx.codes.as<uint32_t>(), ctx.cursor.as<uint32_t>(), ctx.sorted.as<uint32_t>(), g);
+        if (record_phases) CK(cudaEventRecord(ev[3], st));
+    }
     // every thread takes ceil(E / T) entries of the bucket-sorted list (E is read on the device)
     LAUNCH(ctx, msm_accumulate_kernel, T / 128, 128, 0, st, d_points, 64u, ctx.sorted.as<uint32_t>(),
            ctx.offsets.as<uint32_t>(), (uint32_t)nb, 16u, T, ctx.buckets.as<char>(), ctx.part_pt.as<char>(),
@@ -1292,6 +1331,21 @@ int b2_host_alloc(size_t bytes, void** out) {
         cudaGetLastError();
         return fail(B2_ERR_OOM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e));
     }
+    return B2_OK;
+}
+int b2_host_register(void* p, size_t bytes) {
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
+    if (rc) return rc;
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(B2_ERR_CUDA, "cudaHostRegister(%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return B2_OK;
+}
+int b2_host_unregister(void* p) {
+    CK(cudaHostUnregister(p));
     return B2_OK;
 }
 int b2_host_free(void* p) {

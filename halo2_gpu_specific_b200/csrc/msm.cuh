@@ -44,14 +44,12 @@ struct MsmGeom {
 // Signed digits: add K = sum_{w < W-1} 2^(c*w + c - 1) once, then digit_w = window_w - 2^(c-1)
 // for w < W-1 and the top window is taken unsigned (it has at most c-1 significant bits
 // because W = floor(max_bits / c) + 1).
-__global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ codes,
-                                  uint32_t* __restrict__ counts, MsmGeom g, uint32_t max_bits,
-                                  int* __restrict__ err_flag) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= g.n) return;
+// canonical scalar + signed-digit bias K; returns the biased 256-bit value in s
+__device__ __forceinline__ Fr msm_biased_scalar(const uint4* __restrict__ scalars, uint32_t i, const MsmGeom& g,
+                                                uint32_t max_bits, int* __restrict__ err_flag) {
     Fr s = fp_from_mont<FrParams>(fp_load_nc<FrParams>(scalars + 2ull * i));
     // contract check: scalar < 2^max_bits
-    if (max_bits < 256) {
+    if (err_flag != nullptr && max_bits < 256) {
         uint32_t over = 0;
 #pragma unroll
         for (int l = 0; l < 8; l++) {
@@ -61,45 +59,54 @@ __global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* _
         }
         if (over) atomicExch(err_flag, 1);
     }
-    // s += K
-    {
-        uint32_t k[8];
+    uint32_t k[8];
 #pragma unroll
-        for (int l = 0; l < 8; l++) k[l] = 0;
-        for (uint32_t w = 0; w + 1 < g.W; w++) {
-            const uint32_t bit = g.c * w + g.c - 1;
-            if (bit < 256) k[bit >> 5] |= 1u << (bit & 31);
-        }
-        asm("add.cc.u32 %0, %0, %8;\n\t"
-            "addc.cc.u32 %1, %1, %9;\n\t"
-            "addc.cc.u32 %2, %2, %10;\n\t"
-            "addc.cc.u32 %3, %3, %11;\n\t"
-            "addc.cc.u32 %4, %4, %12;\n\t"
-            "addc.cc.u32 %5, %5, %13;\n\t"
-            "addc.cc.u32 %6, %6, %14;\n\t"
-            "addc.u32 %7, %7, %15;"
-            : "+r"(s.v[0]), "+r"(s.v[1]), "+r"(s.v[2]), "+r"(s.v[3]), "+r"(s.v[4]), "+r"(s.v[5]), "+r"(s.v[6]),
-              "+r"(s.v[7])
-            : "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
+    for (int l = 0; l < 8; l++) k[l] = 0;
+    for (uint32_t w = 0; w + 1 < g.W; w++) {
+        const uint32_t bit = g.c * w + g.c - 1;
+        if (bit < 256) k[bit >> 5] |= 1u << (bit & 31);
     }
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(s.v[0]), "+r"(s.v[1]), "+r"(s.v[2]), "+r"(s.v[3]), "+r"(s.v[4]), "+r"(s.v[5]), "+r"(s.v[6]),
+          "+r"(s.v[7])
+        : "r"(k[0]), "r"(k[1]), "r"(k[2]), "r"(k[3]), "r"(k[4]), "r"(k[5]), "r"(k[6]), "r"(k[7]));
+    return s;
+}
+
+// digit of window w: code = (|d| << 1) | (d < 0), 0 when the digit is zero
+__device__ __forceinline__ uint32_t msm_digit_code(const Fr& s, uint32_t w, const MsmGeom& g) {
     const uint32_t half = 1u << (g.c - 1);
-    const uint32_t mask = (g.c == 32) ? 0xffffffffu : ((1u << g.c) - 1u);
+    const uint32_t mask = (1u << g.c) - 1u;
+    const uint32_t bit = g.c * w;
+    uint32_t raw = 0;
+    if (bit < 256) {
+        const uint32_t limb = bit >> 5, off = bit & 31;
+        uint64_t two = s.v[limb];
+        if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
+        raw = (uint32_t)(two >> off) & mask;
+    }
+    const int32_t d = (w + 1 < g.W) ? (int32_t)raw - (int32_t)half : (int32_t)raw;
+    if (d == 0) return 0;
+    const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    return (mag << 1) | (d < 0 ? 1u : 0u);
+}
+
+__global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ codes,
+                                  uint32_t* __restrict__ counts, MsmGeom g, uint32_t max_bits,
+                                  int* __restrict__ err_flag) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= g.n) return;
+    const Fr s = msm_biased_scalar(scalars, i, g, max_bits, err_flag);
     for (uint32_t w = 0; w < g.W; w++) {
-        const uint32_t bit = g.c * w;
-        uint32_t raw = 0;
-        if (bit < 256) {
-            const uint32_t limb = bit >> 5, off = bit & 31;
-            uint64_t two = s.v[limb];
-            if (limb + 1 < 8) two |= (uint64_t)s.v[limb + 1] << 32;
-            raw = (uint32_t)(two >> off) & mask;
-        }
-        int32_t d = (w + 1 < g.W) ? (int32_t)raw - (int32_t)half : (int32_t)raw;
-        uint32_t code = 0;
-        if (d != 0) {
-            const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
-            code = (mag << 1) | (d < 0 ? 1u : 0u);
-            atomicAdd(&counts[(size_t)w * g.bucket_stride + (mag - 1)], 1u);
-        }
+        const uint32_t code = msm_digit_code(s, w, g);
+        if (code) atomicAdd(&counts[(size_t)w * g.bucket_stride + ((code >> 1) - 1)], 1u);
         codes[(size_t)w * g.n + i] = code;
     }
 }
@@ -194,6 +201,116 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint32_t*
     const uint32_t mag = code >> 1;
     const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.bucket_stride + (mag - 1)], 1u);
     sorted[pos] = (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31);
+}
+
+// ---------------------------------------------------------------- 3b. partitioned counting sort
+// Large MSMs: instead of one global atomic and one random 4-byte store per entry, sort in two
+// levels that keep every scatter local.  Level 1 splits the entries by the high bits of the
+// bucket id into partitions of PART_BUCKETS buckets (per-CTA shared-memory histograms, a scan,
+// then CTA-contiguous runs per partition); level 2 counting-sorts each partition inside one CTA
+// (its ~1-2 MB slice of the entry list stays in L2) and emits the bucket offsets on the way, so
+// the global bucket scan disappears too.
+constexpr int PART_LOG = 11;
+constexpr int PART_BUCKETS = 1 << PART_LOG;
+constexpr int PART_THREADS = 256;
+constexpr int PART_MAX = 4096;        // partitions (shared-memory histogram size)
+
+__global__ void __launch_bounds__(PART_THREADS)
+msm_part_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ pcounts, uint32_t npart,
+                      uint32_t ncta, uint32_t tile, MsmGeom g, uint32_t max_bits, int* __restrict__ err_flag) {
+    extern __shared__ uint32_t part_hist[];
+    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) part_hist[p] = 0;
+    __syncthreads();
+    const uint32_t base = blockIdx.x * tile;
+    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+        const uint32_t i = base + k;
+        if (i >= g.n) break;
+        const Fr s = msm_biased_scalar(scalars, i, g, max_bits, err_flag);
+        for (uint32_t w = 0; w < g.W; w++) {
+            const uint32_t code = msm_digit_code(s, w, g);
+            if (code) atomicAdd(&part_hist[(w * g.bucket_stride + ((code >> 1) - 1)) >> PART_LOG], 1u);
+        }
+    }
+    __syncthreads();
+    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) pcounts[(size_t)p * ncta + blockIdx.x] = part_hist[p];
+}
+
+__global__ void __launch_bounds__(PART_THREADS)
+msm_part_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ poffs, uint32_t npart,
+                        uint32_t ncta, uint32_t tile, MsmGeom g, uint2* __restrict__ tmp) {
+    extern __shared__ uint32_t part_cur[];
+    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) part_cur[p] = poffs[(size_t)p * ncta + blockIdx.x];
+    __syncthreads();
+    const uint32_t base = blockIdx.x * tile;
+    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
+        const uint32_t i = base + k;
+        if (i >= g.n) break;
+        const Fr s = msm_biased_scalar(scalars, i, g, 256, nullptr);
+        for (uint32_t w = 0; w < g.W; w++) {
+            const uint32_t code = msm_digit_code(s, w, g);
+            if (!code) continue;
+            const uint32_t bucket = w * g.bucket_stride + ((code >> 1) - 1);
+            const uint32_t pos = atomicAdd(&part_cur[bucket >> PART_LOG], 1u);
+            tmp[pos] = make_uint2(bucket & (PART_BUCKETS - 1),
+                                  (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31));
+        }
+    }
+}
+
+// one CTA per partition
+__global__ void __launch_bounds__(1024)
+msm_part_sort_kernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ poffs, uint32_t npart, uint32_t ncta,
+                     uint32_t nb, uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
+    __shared__ uint32_t hist[PART_BUCKETS];
+    __shared__ uint32_t wsum[32];
+    const uint32_t p = blockIdx.x;
+    const uint32_t total = poffs[(size_t)npart * ncta];          // E (one past the last count)
+    const uint32_t pstart = poffs[(size_t)p * ncta];
+    const uint32_t pend = (p + 1 < npart) ? poffs[(size_t)(p + 1) * ncta] : total;
+    for (uint32_t j = threadIdx.x; j < PART_BUCKETS; j += blockDim.x) hist[j] = 0;
+    __syncthreads();
+    for (uint32_t e = pstart + threadIdx.x; e < pend; e += blockDim.x) atomicAdd(&hist[tmp[e].x], 1u);
+    __syncthreads();
+    // exclusive scan of 2048 counters with 1024 threads: two per thread
+    const uint32_t t = threadIdx.x;
+    const uint32_t a0 = hist[2 * t], a1 = hist[2 * t + 1];
+    uint32_t v = a0 + a1;
+    // warp scan
+    const uint32_t lane = t & 31, wid = t >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= (uint32_t)d) incl += o;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        uint32_t x = wsum[lane];
+        uint32_t xi = x;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
+            if (lane >= (uint32_t)d) xi += o;
+        }
+        wsum[lane] = xi - x;   // exclusive warp offsets
+    }
+    __syncthreads();
+    const uint32_t excl = wsum[wid] + incl - v;
+    // bucket offsets (global) and scatter cursors (shared)
+    const uint32_t b0 = p * PART_BUCKETS + 2 * t;
+    if (b0 < nb) offsets[b0] = pstart + excl;
+    if (b0 + 1 < nb) offsets[b0 + 1] = pstart + excl + a0;
+    __syncthreads();
+    hist[2 * t] = pstart + excl;
+    hist[2 * t + 1] = pstart + excl + a0;
+    if (p + 1 == npart && t == 0) offsets[nb] = total;
+    __syncthreads();
+    for (uint32_t e = pstart + threadIdx.x; e < pend; e += blockDim.x) {
+        const uint2 ent = tmp[e];
+        const uint32_t pos = atomicAdd(&hist[ent.x], 1u);
+        sorted[pos] = ent.y;
+    }
 }
 
 // ---------------------------------------------------------------- 4. accumulate

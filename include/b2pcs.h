@@ -160,6 +160,10 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
 /* ---- memory helpers --------------------------------------------------------------- */
 int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
 int b2_host_free(void* p);
+/* Page-lock an existing host allocation in place (e.g. the Vec<Fr> of a long-lived advice column)
+ * so that its copies run at full PCIe rate and overlap with kernels; undo with b2_host_unregister. */
+int b2_host_register(void* p, size_t bytes);
+int b2_host_unregister(void* p);
 int b2_dev_alloc(size_t bytes, void** out);
 int b2_dev_free(void* p);
 int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
