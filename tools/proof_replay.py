@@ -53,6 +53,9 @@ def main():
     ap.add_argument("--k", type=int, default=0)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--fuse-advice", action="store_true",
+                    help="phase 2 commits AND inverse-transforms each advice column in one upload "
+                         "(commit_lagrange_and_ifft, poly/commitment.rs:144-170), so phase 8's advice iNTTs disappear")
     ap.add_argument("--threads", type=int, default=3, help="concurrent host callers (rayon workers in the reference)")
     a = ap.parse_args()
     sh = dict(SHAPES[a.shape])
@@ -85,9 +88,16 @@ def main():
     big[:] = rng.integers(0, 2**64, size=(pool, n, 4), dtype=np.uint64)
     big[:, :, 3] &= np.uint64((1 << 60) - 1)
     small_tbl = np.stack([_fr.to_mont(v) for v in range(1 << 16)])
-    small = _lib.pinned_empty((pool, n, 4))
-    small[:] = small_tbl[rng.integers(0, 1 << 16, size=(pool, n))]
+    # the fused variant overwrites each advice column with its coefficient form, so it needs one
+    # distinct small-valued column per advice column of this rank
+    pool_small = max(pool, my_share(sh["A"], rank, world)) if a.fuse_advice else pool
+    small = _lib.pinned_empty((pool_small, n, 4))
+    for i in range(pool_small):
+        small[i] = small_tbl[rng.integers(0, 1 << 16, size=n)]
     small[:, ::3] = 0
+    small0 = np.array(small)   # pristine copy: the fused variant transforms the pool in place
+    small_lk = _lib.pinned_empty((pool, n, 4))   # lookup multiplicity columns (never transformed)
+    small_lk[:] = small0[:pool]
     ext_n = dom.extended_len()
     ext_host = _lib.pinned_empty((ext_n, 4))          # h(X) evaluations / quotient coefficients
     ext_host[:] = np.resize(big[0], (ext_n, 4))
@@ -125,7 +135,8 @@ def main():
 
     def cols_of(src, count):
         """a (count, n, 4) pinned batch built from the pool (count may exceed the pool)"""
-        return [src[i % pool: i % pool + 1] for i in range(count)]
+        m = src.shape[0]
+        return [src[i % m: i % m + 1] for i in range(count)]
 
     def commit_each(src, count, bits, ifft=False, basis="lagrange"):
         def one(c):
@@ -137,8 +148,8 @@ def main():
         cols = cols_of(src, count)
         if ifft:   # in-place transforms: one distinct pool column per concurrent caller
             out = []
-            for i in range(0, len(cols), pool):
-                out += par(one, cols[i:i + pool])
+            for i in range(0, len(cols), src.shape[0]):
+                out += par(one, cols[i:i + src.shape[0]])
             return out
         return par(one, cols)
 
@@ -162,11 +173,11 @@ def main():
             for i in range(0, len(cols), pool):
                 par(lambda c: dom.lagrange_to_coeff(c[0]), cols[i:i + pool])
         ph["1_instance"], _ = phase(lambda: (commit_each(big, I, 254), ifft_cols(I)))
-        ph["2_advice_commit"], _ = phase(lambda: commit_each(small, A, 16))
-        ph["3_lookup_m_commit"], _ = phase(lambda: commit_each(small, Lk, 16))
+        ph["2_advice_commit"], _ = phase(lambda: commit_each(small, A, 16, ifft=a.fuse_advice))
+        ph["3_lookup_m_commit"], _ = phase(lambda: commit_each(small_lk, Lk, 16))
         ph["6_z_commit_and_ifft"], _ = phase(lambda: commit_each(big, P + S + H, 254, ifft=True))
         ph["7_vanishing_commit"], _ = phase(lambda: commit_each(big, 1 if rank == 0 else 0, 254, basis="g"))
-        ph["8_advice_ifft"], _ = phase(lambda: ifft_cols(A))
+        ph["8_advice_ifft"], _ = phase(lambda: None if a.fuse_advice else ifft_cols(A))
         n_ext = A + I + P + S + Lk + H
         ph["8_coeff_to_extended"], _ = phase(lambda: par(lambda c: extend_on_device(c[0]), cols_of(big, n_ext)))
         if rank == 0:
@@ -187,7 +198,7 @@ def main():
                "excluded": "phase 9 evaluate_h (quotient evaluation) and all CPU-side protocol logic "
                            "(witness synthesis, grand products, transcript) are not on the replayed path",
                "transfers": "host-resident pinned columns; every call copies its column in and its result out",
-               "host_threads": a.threads}
+               "host_threads": a.threads, "fuse_advice_commit_and_ifft": bool(a.fuse_advice)}
         print(json.dumps(doc), flush=True)
         if a.out:
             json.dump(doc, open(a.out, "w"), indent=1)
