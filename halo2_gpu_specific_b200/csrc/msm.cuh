@@ -95,6 +95,9 @@ __device__ __forceinline__ uint32_t msm_digit_code(const Fr& s, uint32_t w, cons
     const int32_t d = (w + 1 < g.W) ? (int32_t)raw - (int32_t)half : (int32_t)raw;
     if (d == 0) return 0;
     const uint32_t mag = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+    // the unsigned top window only exceeds the bucket range when the scalar breaks the max_bits
+    // contract; that call fails with B2_ERR_BOUND, but it must not write out of bounds first
+    if (mag > half) return 0;
     return (mag << 1) | (d < 0 ? 1u : 0u);
 }
 

@@ -140,6 +140,14 @@ def test_msm_bound_violation_is_an_error(gpu):
     with pytest.raises(gpu.B2Error) as e:
         h2.gpu_multiexp_single_gpu_with_bound(scalars, srs, 16)
     assert e.value.code == gpu.B2_ERR_BOUND
+    # the failed call must leave the engine usable (no out-of-bounds writes): same for a window table
+    pre = Srs.register(_bases(n, 6)).precompute(10)
+    for bits in (1, 9, 16, 20, 100):
+        with pytest.raises(gpu.B2Error):
+            h2.gpu_multiexp_single_gpu_with_bound(scalars, pre, bits)
+    ok = cref.random_fr_small_mont(n, 8, 16)
+    assert _affine(h2.gpu_multiexp_single_gpu_with_bound(ok, pre, 16)) == _want(ok, _bases(n, 6))
+    pre.free()
     srs.free()
 
 

@@ -168,6 +168,8 @@ def main():
     results = []
     for rep in range(a.reps + 1):
         ph = {}
+        if a.fuse_advice:
+            small[:] = small0      # untimed: fresh small-valued advice columns for this repetition
         def ifft_cols(count):
             cols = cols_of(big, count)
             for i in range(0, len(cols), pool):
