@@ -160,6 +160,8 @@ int dev_get(DeviceCtx** out) {
         cudaDeviceProp prop;
         CK(cudaGetDeviceProperties(&prop, dev));
         CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CK(cudaFuncSetAttribute(ntt_pass_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(ntt_pass_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
         int nl = 3;
@@ -648,13 +650,23 @@ int ntt_get_plan(Lane& ctx, const void* omega, const void* divisor, uint32_t log
     }
     NttPlan* pl = new NttPlan();
     pl->log_n = log_n;
-    uint32_t maxm = 11;
+    // digit sizes: up to 2^11 points per CTA (64 KB of shared memory, 2-3 CTAs per SM); digits of
+    // 12 / 13 bits are owned by a cluster of 2 / 4 CTAs (distributed shared memory)
+    uint32_t maxm = 11, maxc = 13;
     if (const char* e = getenv("B2_NTT_MAXM")) {
         int v = atoi(e);
         if (v >= 3 && v <= 12) maxm = (uint32_t)v;
     }
+    if (const char* e = getenv("B2_NTT_MAXC")) {
+        int v = atoi(e);
+        if (v >= 11 && v <= 13) maxc = (uint32_t)v;
+    }
+    if (getenv("B2_NTT_CLUSTER") && atoi(getenv("B2_NTT_CLUSTER")) == 0 && maxc > 12) maxc = 12;  // 128 KB single CTA
     int P = (int)((log_n + maxm - 1) / maxm);
-    if (maxm == 11 && (log_n == 12 || log_n == 23 || log_n == 24)) P = (int)((log_n + 11) / 12);
+    if (maxm == 11) {
+        const int Pc = (int)((log_n + maxc - 1) / maxc);   // passes when wide digits are allowed
+        if (Pc < P) P = Pc;
+    }
     if (P > NTT_MAX_PASSES) {
         delete pl;
         return fail(B2_ERR_ARG, "log_n %u needs more than %d passes", log_n, NTT_MAX_PASSES);
@@ -751,15 +763,38 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
             a.scale_out = 1;
             a.scale = pl->div;
         }
-        const uint32_t threads = std::max(32u, 1u << (a.m >= 3 ? a.m - 3 : 0));
-        const size_t smem = ((size_t)32 << a.m);
+        static const bool use_clusters = !(getenv("B2_NTT_CLUSTER") && atoi(getenv("B2_NTT_CLUSTER")) == 0);
+        a.cl_log = (use_clusters && a.m >= 12) ? a.m - 11 : 0;
+        const uint32_t mloc = a.m - a.cl_log;
+        const uint32_t threads = std::max(32u, 1u << (mloc >= 3 ? mloc - 3 : 0));
+        const size_t smem = ((size_t)32 << mloc);
         const uint64_t lines = N >> a.m;
         for (uint64_t c0 = 0; c0 < cols; c0 += 65535) {
             const uint64_t cc = std::min<uint64_t>(65535, cols - c0);
             NttPassArgs b = a;
             b.in = a.in + 2ull * c0 * a.in_col_stride;
             b.out = a.out + 2ull * c0 * a.out_col_stride;
-            LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+            if (a.cl_log == 0) {
+                LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+            } else {
+                cudaLaunchConfig_t cfg;
+                memset(&cfg, 0, sizeof cfg);
+                cfg.gridDim = dim3((unsigned)(lines << a.cl_log), (unsigned)cc);
+                cfg.blockDim = dim3(threads);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 1u << a.cl_log;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                cudaError_t le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
+                                                 : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);
+                (*ctx.launch_counter)++;
+                if (le != cudaSuccess) return fail(B2_ERR_CUDA, "cluster NTT launch: %s", cudaGetErrorString(le));
+            }
         }
     }
     return B2_OK;

@@ -19,6 +19,8 @@
 //   last pass  : the inverse period-3 scaling and truncation of extended_to_coeff
 //                (domain.rs:341-347)
 #pragma once
+#include <cooperative_groups.h>
+
 #include "fp.cuh"
 
 namespace b2 {
@@ -46,6 +48,7 @@ struct NttPassArgs {
     int coset_in;                       // first pass: multiply x[i] by zin[i % 3 - 1]
     int coset_out;                      // last pass : multiply X[o] by zout[o % 3 - 1]
     int scale_out;                      // last pass : multiply everything by `scale` (P == 1 iNTT)
+    uint32_t cl_log;                    // log2 of the cluster size that owns one tile (0 = single CTA)
     Fr zin1, zin2, zout1, zout2, scale;
 };
 
@@ -79,9 +82,10 @@ __device__ __forceinline__ void ntt_bfly1(Fr& a, Fr& b) {  // twiddle == 1
 // One group of R consecutive DIT stages (s0+1 .. s0+R) on the shared-memory tile.
 template <int R, bool FIRST>
 __device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* __restrict__ tw, uint32_t m,
-                                         uint32_t s0, uint32_t hs) {
+                                         uint32_t mloc, uint32_t s0, uint32_t hs) {
+    // m: log size of the whole sub-NTT (twiddle stride); mloc: log size of the part in this CTA
     constexpr int E = 1 << R;
-    const uint32_t items = 1u << (m - R);
+    const uint32_t items = 1u << (mloc - R);
     for (uint32_t w = threadIdx.x; w < items; w += blockDim.x) {
         const uint32_t low = w & ((1u << s0) - 1u);
         const uint32_t base = ((w >> s0) << (s0 + R)) | low;
@@ -130,14 +134,23 @@ __device__ __forceinline__ uint64_t ntt_digit_reverse(uint64_t v, const uint32_t
     return r;
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
+// CL_LOG = 0: one CTA owns the whole 2^m tile.  CL_LOG = 1, 2: a thread-block cluster of 2 / 4 CTAs
+// owns it, 2^(m - CL_LOG) elements (64 KB) per CTA: the first m - CL_LOG DIT stages are local to each
+// CTA, the last CL_LOG stages exchange through distributed shared memory.  This keeps 2-3 CTAs
+// resident per SM for 2^12 / 2^13-point digits (a single CTA with a 128 KB tile runs alone on its
+// SM and exposes its load / store latency), and lets k = 25, 26 run in two passes.
+template <int CL_LOG>
+__device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
+    namespace cg = cooperative_groups;
     extern __shared__ uint4 ntt_smem[];
-    const uint32_t m = a.m, N = 1u << m;
+    const uint32_t m = a.m, mloc = m - CL_LOG, Nloc = 1u << mloc;
     uint4* s_lo4 = ntt_smem;
-    uint4* s_hi4 = ntt_smem + N;
-    const uint32_t hs = (m >= 9) ? (m - 3) : 31u;
+    uint4* s_hi4 = ntt_smem + Nloc;
+    const uint32_t hs = (mloc >= 9) ? (mloc - 3) : 31u;
+    uint32_t rank = 0;
+    if (CL_LOG > 0) rank = cg::this_cluster().block_rank();
 
-    const uint64_t line = blockIdx.x;
+    const uint64_t line = blockIdx.x >> CL_LOG;
     const uint64_t col = blockIdx.y;
     const uint64_t L = line & ((1ull << a.s_lo) - 1ull);
     const uint64_t H = line >> a.s_lo;
@@ -146,8 +159,11 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
     uint4* out = a.out + 2ull * col * a.out_col_stride;
     const bool first = (a.pass == 0), last = (a.pass + 1 == a.npass);
 
-    // ---- load (bit-reversed into the tile) ----
-    for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
+    // ---- load (bit-reversed into the tile): tile position p = bitrev_m(j); this CTA holds the
+    // positions whose top CL_LOG bits equal its rank, i.e. the j with low bits bitrev(rank) ----
+    const uint32_t jr = CL_LOG ? (__brev(rank) >> (32 - CL_LOG)) : 0u;
+    for (uint32_t jl = threadIdx.x; jl < Nloc; jl += blockDim.x) {
+        const uint32_t j = (jl << CL_LOG) | jr;
         const uint64_t pos = base_pos + ((uint64_t)j << a.s_lo);
         Fr x;
         if (!first || pos < a.n_in) {
@@ -160,31 +176,66 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
         } else {
             x = Fr::zero();
         }
-        const uint32_t jr = __brev(j) >> (32 - m);
-        sm_st(s_lo4, s_hi4, ntt_swz(jr, hs), x);
+        const uint32_t pl = mloc ? (__brev(jl) >> (32 - mloc)) : 0u;
+        sm_st(s_lo4, s_hi4, ntt_swz(pl, hs), x);
     }
     __syncthreads();
 
-    // ---- DIT stages, three per shared-memory round trip ----
+    // ---- local DIT stages, three per shared-memory round trip ----
     uint32_t s0 = 0;
     {
-        const uint32_t r = m < 3 ? m : 3;
-        if (r == 3) ntt_step<3, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
-        else if (r == 2) ntt_step<2, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
-        else ntt_step<1, true>(s_lo4, s_hi4, a.tw_sub, m, 0, hs);
+        const uint32_t r = mloc < 3 ? mloc : 3;
+        if (r == 3) ntt_step<3, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        else if (r == 2) ntt_step<2, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        else if (r == 1) ntt_step<1, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
         s0 = r;
         __syncthreads();
     }
-    while (s0 < m) {
-        const uint32_t r = (m - s0) < 3 ? (m - s0) : 3;
-        if (r == 3) ntt_step<3, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
-        else if (r == 2) ntt_step<2, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
-        else ntt_step<1, false>(s_lo4, s_hi4, a.tw_sub, m, s0, hs);
+    while (s0 < mloc) {
+        const uint32_t r = (mloc - s0) < 3 ? (mloc - s0) : 3;
+        if (r == 3) ntt_step<3, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        else if (r == 2) ntt_step<2, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        else ntt_step<1, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
         s0 += r;
         __syncthreads();
     }
 
-    // ---- store ----
+    // ---- cross-CTA stages through distributed shared memory ----
+    if (CL_LOG > 0) {
+        cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+        for (int q = 0; q < CL_LOG; q++) {
+            cluster.sync();   // partner's previous stage is complete and visible
+            // stage s = mloc + q + 1: position p pairs with p + 2^(mloc + q): rank bit q selects a / b
+            const uint32_t partner = rank ^ (1u << q);
+            const bool is_b = (rank >> q) & 1u;
+            const uint32_t ra = is_b ? partner : rank;           // rank holding the "a" element
+            uint4* r_lo4 = cluster.map_shared_rank(s_lo4, partner);
+            uint4* r_hi4 = cluster.map_shared_rank(s_hi4, partner);
+            uint4* a_lo = is_b ? r_lo4 : s_lo4;
+            uint4* a_hi = is_b ? r_hi4 : s_hi4;
+            uint4* b_lo = is_b ? s_lo4 : r_lo4;
+            uint4* b_hi = is_b ? s_hi4 : r_hi4;
+            // each CTA of the pair takes half of the butterflies
+            const uint32_t half = Nloc >> 1;
+            const uint32_t i0 = is_b ? half : 0u;
+            const uint32_t jj_hi = (ra & ((1u << q) - 1u)) << mloc;   // p_a mod 2^(mloc+q), high part
+            const uint32_t sh = m - (mloc + q + 1);
+            for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
+                const uint32_t i = i0 + t;
+                const uint32_t sw = ntt_swz(i, hs);
+                Fr xa = sm_ld(a_lo, a_hi, sw);
+                Fr xb = sm_ld(b_lo, b_hi, sw);
+                Fr tw = fp_load_nc<FrParams>(a.tw_sub + ((size_t)(jj_hi | i) << sh));
+                ntt_bfly(xa, xb, tw);
+                sm_st(a_lo, a_hi, sw, xa);
+                sm_st(b_lo, b_hi, sw, xb);
+            }
+        }
+        cluster.sync();
+    }
+
+    // ---- store: this CTA holds tile positions j = rank * Nloc + il (natural order) ----
     if (!last) {
         // twiddle exponent = i_next * digit_reverse(H, j) * 2^(k - (m_1+..+m_{p+1}))
         const uint32_t m_next = a.mm[a.pass + 1];
@@ -193,8 +244,9 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
         const uint64_t lo_mask = (1ull << a.tw_h) - 1ull;
         const bool full = first && a.tw_full != nullptr;
         const uint64_t half_mask = (1ull << (a.log_n - 1)) - 1ull;
-        for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
-            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(j, hs));
+        for (uint32_t il = threadIdx.x; il < Nloc; il += blockDim.x) {
+            const uint32_t j = (rank << mloc) | il;
+            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(il, hs));
             const uint64_t opart = ntt_digit_reverse((H << m) | j, a.mm, (int)a.pass + 1);
             const uint64_t e = (i_next * opart) << shift;
             if (full) {
@@ -214,8 +266,9 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
             fp_store<FrParams>(out + 2ull * pos, x);
         }
     } else {
-        for (uint32_t j = threadIdx.x; j < N; j += blockDim.x) {
-            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(j, hs));
+        for (uint32_t il = threadIdx.x; il < Nloc; il += blockDim.x) {
+            const uint32_t j = (rank << mloc) | il;
+            Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(il, hs));
             const uint64_t o = ntt_digit_reverse((H << m) | j, a.mm, (int)a.npass);
             if (o >= a.n_out) continue;
             if (a.scale_out) x = fp_mul<FrParams>(x, a.scale);
@@ -228,6 +281,10 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) {
         }
     }
 }
+
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) { ntt_pass_impl<0>(a); }
+__global__ void __launch_bounds__(256) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1>(a); }
+__global__ void __launch_bounds__(256) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2>(a); }
 
 // out[j] = base^(j * mult) * (scale if has_scale), j < count
 __global__ void ntt_pow_table_kernel(Fr* out, const Fr base, unsigned long long mult, uint32_t count,
