@@ -764,7 +764,9 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
             a.scale = pl->div;
         }
         static const bool use_clusters = !(getenv("B2_NTT_CLUSTER") && atoi(getenv("B2_NTT_CLUSTER")) == 0);
-        a.cl_log = (use_clusters && a.m >= 12) ? a.m - 11 : 0;
+        // measured on B200: 11- and 12-bit digits run best on a cluster of 2 (2^10 / 2^11 points per CTA),
+        // 13-bit digits on a cluster of 4 (profiles/r1_ncu_summary.md)
+        a.cl_log = !use_clusters ? 0 : (a.m >= 13 ? 2 : (a.m >= 11 ? 1 : 0));
         const uint32_t mloc = a.m - a.cl_log;
         const uint32_t threads = std::max(32u, 1u << (mloc >= 3 ? mloc - 3 : 0));
         const size_t smem = ((size_t)32 << mloc);
