@@ -102,11 +102,65 @@ def gpu_multiexp_single_gpu(coeffs, bases: Bases) -> np.ndarray:
     return gpu_multiexp_single_gpu_with_bound(coeffs, bases, 254)
 
 
-def gpu_multiexp_bound(coeffs, bases: Bases, max_bits: int) -> np.ndarray:
-    """arithmetic.rs:413-440.  The reference splits by point range over N_GPU devices of one
-    process; this engine runs one process per GPU, so inside a process this is the
-    single-GPU call and the cross-rank split lives in parallel.sharded_msm."""
-    return gpu_multiexp_single_gpu_with_bound(coeffs, bases, max_bits)
+class MultiGpuSrs:
+    """The reference's in-process multi-GPU model (N_GPU devices behind one pool, plonk/prover.rs:56-74):
+    the bases are split by point range, part_len = ceil(n / n_gpu) (arithmetic.rs:426), and shard g lives
+    on device g.  `devices` defaults to every visible device."""
+
+    def __init__(self, bases: np.ndarray, devices=None, precompute: bool = True):
+        require_gpu()
+        b = np.ascontiguousarray(np.asarray(bases, dtype=np.uint64))
+        self.devices = list(range(lib().b2_device_count())) if devices is None else list(devices)
+        self.n = b.shape[0]
+        ng = len(self.devices)
+        self.part_len = (self.n + ng - 1) // ng if self.n else 0
+        self.shards = []
+        prev = lib().b2_get_device()
+        try:
+            for g, dev in enumerate(self.devices):
+                lo = min(g * self.part_len, self.n)
+                hi = min(lo + self.part_len, self.n)
+                if hi == lo:
+                    break
+                check(lib().b2_set_device(dev))
+                srs = Srs.register(b[lo:hi])
+                if precompute:
+                    srs.precompute()
+                self.shards.append((dev, lo, hi, srs))
+        finally:
+            lib().b2_set_device(prev)
+
+    def __len__(self) -> int:
+        return self.n
+
+    def free(self) -> None:
+        for _, _, _, srs in self.shards:
+            srs.free()
+        self.shards = []
+
+
+def gpu_multiexp_bound(coeffs, bases, max_bits: int) -> np.ndarray:
+    """arithmetic.rs:413-440: split by point range over the GPUs, one partial per device, sum of the
+    partials.  With a MultiGpuSrs the split runs inside this process (one host thread per device, as the
+    reference's par_chunks does); with a single-device Srs / array it is the single-GPU call, and the
+    one-process-per-GPU variant lives in parallel.sharded_msm."""
+    if not isinstance(bases, MultiGpuSrs):
+        return gpu_multiexp_single_gpu_with_bound(coeffs, bases, max_bits)
+    c = as_fr(coeffs)
+    if c.shape[0] != len(bases):
+        raise B2Error(B2_ERR_ARG, f"coeffs ({c.shape[0]}) and bases ({len(bases)}) differ in length")
+    if max_bits == 0 or c.shape[0] == 0:
+        return _identity()
+    from concurrent.futures import ThreadPoolExecutor
+
+    def part(shard):
+        dev, lo, hi, srs = shard
+        check(lib().b2_set_device(dev))       # per-thread device selection
+        return gpu_multiexp_single_gpu_with_bound(c[lo:hi], srs, max_bits)
+
+    with ThreadPoolExecutor(len(bases.shards)) as ex:
+        partials = list(ex.map(part, bases.shards))
+    return g1_sum(np.stack(partials))
 
 
 def gpu_multiexp(coeffs, bases: Bases) -> np.ndarray:

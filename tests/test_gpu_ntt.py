@@ -198,3 +198,24 @@ def test_mixed_host_device_locations(gpu):
     gpu.check(L.b2_ntt_exec(ctypes.byref(f)))
     assert np.array_equal(back[:n], x) and not back[n:].any()
     L.b2_dev_free(d_ext)
+
+
+@pytest.mark.parametrize("maxm,k", [(7, 20), (5, 18), (8, 17)])
+def test_three_and_four_pass_plans(gpu, maxm, k):
+    """k >= 27 needs three passes on the device; force small digits (B2_NTT_MAXM) so that the 3- and 4-pass
+    index arithmetic (digit reversal, two-level twiddles on later boundaries) is exercised at test sizes"""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r);"
+        "import halo2_gpu_specific_b200 as h2; from oracle import cref, bn254 as o;"
+        "k = %d; dom = h2.EvaluationDomain(5, k); x = cref.random_fr_mont(1 << k, 11);"
+        "a = x.copy(); h2.best_fft(a, dom.omega, k); ok1 = np.array_equal(a, cref.best_fft(x, dom.omega, k, 8));"
+        "b = x.copy(); dom.lagrange_to_coeff(b); ok2 = np.array_equal(b, cref.ifft(x, dom.omega_inv, dom.ifft_divisor, k, 8));"
+        "c = dom.coeff_to_extended(x[: 1 << (k - 2)]) if False else None;"
+        "print('PASSES', ok1, ok2)"
+    ) % (root, k)
+    env = dict(os.environ, B2_NTT_MAXM=str(maxm), B2_NTT_MAXC="11")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "PASSES True True" in out.stdout, out.stdout + out.stderr
