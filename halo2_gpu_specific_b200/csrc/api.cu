@@ -162,6 +162,7 @@ int dev_get(DeviceCtx** out) {
         CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(msm_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
         int nl = 3;
@@ -475,8 +476,11 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
         LAUNCH(ctx, msm_scan_add_kernel, ptiles, SCAN_THREADS, 0, st, ctx.poffs.as<uint32_t>(),
                ctx.pcursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)ncnt);
         if (record_phases) CK(cudaEventRecord(ev[2], st));
-        LAUNCH(ctx, msm_part_scatter_kernel, ncta, PART_THREADS, npart * 4, st, (const uint4*)d_scalars,
-               ctx.poffs.as<uint32_t>(), npart, ncta, tile, g, ctx.ptmp.as<uint2>());
+        // sub-tile staged in shared memory: <= 2 scalars per thread and <= 56 KB of entries
+        uint32_t sub = std::min<uint32_t>(2 * PART_THREADS, (56u << 10) / (10u * g.W));
+        const size_t smem_sc = (size_t)(3 * npart + 3) * 4 + (size_t)sub * g.W * 10;
+        LAUNCH(ctx, msm_part_scatter_kernel, ncta, PART_THREADS, smem_sc, st, (const uint4*)d_scalars,
+               ctx.poffs.as<uint32_t>(), npart, ncta, tile, sub, g, ctx.ptmp.as<uint2>());
         LAUNCH(ctx, msm_part_sort_kernel, npart, 1024, 0, st, ctx.ptmp.as<uint2>(), ctx.poffs.as<uint32_t>(), npart,
                ncta, (uint32_t)nb, ctx.offsets.as<uint32_t>(), ctx.sorted.as<uint32_t>());
         if (record_phases) CK(cudaEventRecord(ev[3], st));
@@ -909,11 +913,15 @@ int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits) {
     if (s.table) return B2_OK;
     uint32_t c = window_bits;
     if (c == 0) {
+        // measured on B200 (tools/window_variants.sh): 2^16 -> 16, 2^18 -> 17, 2^20..2^24 -> 20, 2^26 -> 22
         uint32_t lg = 0;
         while ((2ull << lg) <= s.n) lg++;
-        int cc = (int)lg - 2;
-        if (cc < 10) cc = 10;
-        if (cc > 20) cc = (lg >= 25) ? 22 : 20;
+        int cc;
+        if (lg >= 25) cc = 22;
+        else if (lg >= 20) cc = 20;
+        else if (lg >= 18) cc = 17;
+        else if (lg >= 16) cc = 16;
+        else cc = std::max(10, (int)lg - 2);
         c = (uint32_t)cc;
     }
     if (c < 8 || c > 24) return fail(B2_ERR_ARG, "srs_precompute: window_bits %u out of [8, 24]", c);

@@ -107,10 +107,21 @@ __global__ void msm_digits_kernel(const uint4* __restrict__ scalars, uint32_t* _
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= g.n) return;
     const Fr s = msm_biased_scalar(scalars, i, g, max_bits, err_flag);
-    for (uint32_t w = 0; w < g.W; w++) {
+    for (uint32_t w = 0; w + 1 < g.W; w++) {
         const uint32_t code = msm_digit_code(s, w, g);
         if (code) atomicAdd(&counts[(size_t)w * g.bucket_stride + ((code >> 1) - 1)], 1u);
         codes[(size_t)w * g.n + i] = code;
+    }
+    // The top window often has only a few significant bits (254 mod c, or the carry of a bounded
+    // scalar), i.e. a handful of buckets that every scalar hits: aggregate equal buckets inside the
+    // warp so that those hot counters see one atomic per warp instead of 32.
+    {
+        const uint32_t w = g.W - 1;
+        const uint32_t code = msm_digit_code(s, w, g);
+        codes[(size_t)w * g.n + i] = code;
+        const uint32_t key = code ? (w * g.bucket_stride + ((code >> 1) - 1)) : 0xffffffffu;
+        const uint32_t peers = __match_any_sync(__activemask(), key);
+        if (code && (threadIdx.x & 31u) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
     }
 }
 
@@ -200,10 +211,23 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint32_t*
     const uint32_t w = blockIdx.y;
     if (i >= g.n) return;
     const uint32_t code = codes[(size_t)w * g.n + i];
+    const uint32_t entry = (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31);
+    if (w + 1 < g.W) {
+        if (code == 0) return;
+        const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.bucket_stride + ((code >> 1) - 1)], 1u);
+        sorted[pos] = entry;
+        return;
+    }
+    // top window: warp-aggregated (see msm_digits_kernel)
+    const uint32_t key = code ? (w * g.bucket_stride + ((code >> 1) - 1)) : 0xffffffffu;
+    const uint32_t peers = __match_any_sync(__activemask(), key);
     if (code == 0) return;
-    const uint32_t mag = code >> 1;
-    const uint32_t pos = atomicAdd(&cursor[(size_t)w * g.bucket_stride + (mag - 1)], 1u);
-    sorted[pos] = (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31);
+    const uint32_t lane = threadIdx.x & 31u;
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (lane == (uint32_t)leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    sorted[base + __popc(peers & ((1u << lane) - 1u))] = entry;
 }
 
 // ---------------------------------------------------------------- 3b. partitioned counting sort
@@ -238,25 +262,88 @@ msm_part_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ 
     for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) pcounts[(size_t)p * ncta + blockIdx.x] = part_hist[p];
 }
 
+// Level 1 scatter, staged: the CTA walks its tile in sub-tiles of `sub` scalars; the entries of a
+// sub-tile are first grouped by partition in shared memory (local histogram, scan, placement), then
+// written out so that consecutive threads store consecutive entries of one partition: full sectors
+// instead of one partial sector per entry.
+// shared memory: hist[npart] | loc_off[npart + 1] | gcur[npart] | stage[sub * W] (uint2) | stage_p[sub * W] (u16)
 __global__ void __launch_bounds__(PART_THREADS)
 msm_part_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ poffs, uint32_t npart,
-                        uint32_t ncta, uint32_t tile, MsmGeom g, uint2* __restrict__ tmp) {
-    extern __shared__ uint32_t part_cur[];
-    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) part_cur[p] = poffs[(size_t)p * ncta + blockIdx.x];
-    __syncthreads();
-    const uint32_t base = blockIdx.x * tile;
-    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-        const uint32_t i = base + k;
-        if (i >= g.n) break;
-        const Fr s = msm_biased_scalar(scalars, i, g, 256, nullptr);
-        for (uint32_t w = 0; w < g.W; w++) {
-            const uint32_t code = msm_digit_code(s, w, g);
-            if (!code) continue;
-            const uint32_t bucket = w * g.bucket_stride + ((code >> 1) - 1);
-            const uint32_t pos = atomicAdd(&part_cur[bucket >> PART_LOG], 1u);
-            tmp[pos] = make_uint2(bucket & (PART_BUCKETS - 1),
-                                  (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31));
+                        uint32_t ncta, uint32_t tile, uint32_t sub, MsmGeom g, uint2* __restrict__ tmp) {
+    extern __shared__ uint32_t part_smem[];
+    uint32_t* hist = part_smem;
+    uint32_t* loc_off = hist + npart;
+    uint32_t* gcur = loc_off + npart + 1;
+    uint2* stage = reinterpret_cast<uint2*>(gcur + npart + ((npart & 1u) ? 0 : 1));   // 8-byte aligned
+    uint16_t* stage_p = reinterpret_cast<uint16_t*>(stage + (size_t)sub * g.W);
+    const uint32_t t = threadIdx.x;
+    for (uint32_t p = t; p < npart; p += blockDim.x) gcur[p] = poffs[(size_t)p * ncta + blockIdx.x];
+    const uint32_t tile_base = blockIdx.x * tile;
+    for (uint32_t s0 = 0; s0 < tile; s0 += sub) {
+        if (tile_base + s0 >= g.n) break;
+        __syncthreads();
+        for (uint32_t p = t; p < npart; p += blockDim.x) hist[p] = 0;
+        __syncthreads();
+        // pass 1: local histogram (scalars stay in registers for pass 2: sub <= 2 * blockDim)
+        Fr sc[2];
+        bool have[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const uint32_t k = t + u * blockDim.x;
+            const uint32_t i = tile_base + s0 + k;
+            have[u] = (k < sub) && (s0 + k < tile) && (i < g.n);
+            if (!have[u]) continue;
+            sc[u] = msm_biased_scalar(scalars, i, g, 256, nullptr);
+            for (uint32_t w = 0; w < g.W; w++) {
+                const uint32_t code = msm_digit_code(sc[u], w, g);
+                if (code) atomicAdd(&hist[(w * g.bucket_stride + ((code >> 1) - 1)) >> PART_LOG], 1u);
+            }
         }
+        __syncthreads();
+        // exclusive scan of hist -> loc_off (npart <= 4096; one warp, serial over chunks)
+        if (t < 32) {
+            uint32_t carry = 0;
+            for (uint32_t base = 0; base < npart; base += 32) {
+                const uint32_t v = (base + t < npart) ? hist[base + t] : 0;
+                uint32_t incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (t >= (uint32_t)d) incl += o;
+                }
+                if (base + t < npart) loc_off[base + t] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (t == 0) loc_off[npart] = carry;
+        }
+        __syncthreads();
+        for (uint32_t p = t; p < npart; p += blockDim.x) hist[p] = loc_off[p];   // placement cursors
+        __syncthreads();
+        // pass 2: place the entries, grouped by partition
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (!have[u]) continue;
+            const uint32_t i = tile_base + s0 + t + u * blockDim.x;
+            for (uint32_t w = 0; w < g.W; w++) {
+                const uint32_t code = msm_digit_code(sc[u], w, g);
+                if (!code) continue;
+                const uint32_t bucket = w * g.bucket_stride + ((code >> 1) - 1);
+                const uint32_t p = bucket >> PART_LOG;
+                const uint32_t pos = atomicAdd(&hist[p], 1u);
+                stage[pos] = make_uint2(bucket & (PART_BUCKETS - 1),
+                                        (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31));
+                stage_p[pos] = (uint16_t)p;
+            }
+        }
+        __syncthreads();
+        // write out: consecutive threads -> consecutive entries of the same partition
+        const uint32_t total = loc_off[npart];
+        for (uint32_t e = t; e < total; e += blockDim.x) {
+            const uint32_t p = stage_p[e];
+            tmp[gcur[p] + (e - loc_off[p])] = stage[e];
+        }
+        __syncthreads();
+        for (uint32_t p = t; p < npart; p += blockDim.x) gcur[p] += loc_off[p + 1] - loc_off[p];
     }
 }
 

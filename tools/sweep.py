@@ -91,11 +91,14 @@ def ntt_sweep(L, ks, cols, reps, out):
         out["ntt"].append(res)
 
 
+WINDOW_BITS = 0
+
+
 def msm_sweep(L, logns, reps, out):
     for lg in logns:
         n = 1 << lg
         t0 = time.time()
-        srs = Srs.synthetic(n, 0, 0xB2000003).precompute()
+        srs = Srs.synthetic(n, 0, 0xB2000003).precompute(WINDOW_BITS)
         setup_s = time.time() - t0
         res = {"logn": lg, "srs_setup_s": setup_s}
         cfg = (ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32())
@@ -132,7 +135,10 @@ def main():
     ap.add_argument("--cols", type=int, default=64)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--out", default="gpurun_out/sweep.json")
+    ap.add_argument("--window-bits", type=int, default=0, help="force the SRS window-table width (0 = library default)")
     a = ap.parse_args()
+    global WINDOW_BITS
+    WINDOW_BITS = a.window_bits
     _lib.require_gpu()
     L = _lib.lib()
     out = {"ntt": [], "msm": []}
