@@ -47,6 +47,7 @@ SYMBOLS = [
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
+    "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
 ]
 
 _lib = None
@@ -97,6 +98,11 @@ def lib() -> ctypes.CDLL:
         L.b2_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.b2_last_msm_phases.argtypes = [ctypes.POINTER(ctypes.c_double)]
         L.b2_msm_config.argtypes = [u64, sz, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]
+        L.b2_quotient_program_create.argtypes = [vp, ctypes.POINTER(u64)]
+        L.b2_quotient_program_free.argtypes = [u64]
+        L.b2_quotient_program_info.argtypes = [u64] + [ctypes.POINTER(u32)] * 4
+        L.b2_quotient_eval.argtypes = [u64, vp]
+        L.b2_quotient_program_dump.argtypes = [u64, vp, sz, ctypes.POINTER(u32), vp, sz, ctypes.POINTER(u32)]
         _lib = L
     return _lib
 

@@ -22,6 +22,7 @@
 #include "../../include/b2pcs.h"
 #include "msm.cuh"
 #include "ntt.cuh"
+#include "quotient.cuh"
 
 using namespace b2;
 
@@ -114,6 +115,8 @@ struct Lane {
         out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids, pcounts, poffs, pcursor, ptmp;
     // NTT workspace
     Buf ntt_in, ntt_work, ntt_out;
+    // quotient evaluation: per-call tables, spilled slots
+    Buf qtab, qspill;
     // timing
     cudaEvent_t ev[16];
     cudaEvent_t busy;            // last work enqueued on a caller-provided stream (async _dev calls)
@@ -267,7 +270,8 @@ const uint64_t HQ_P[4] = {0x3c208c16d87cfd47ULL, 0x97816a916871ca8dULL, 0xb85045
 const uint64_t HQ_INV = 0x87d20782e4866389ULL;
 const uint64_t HQ_ONE[4] = {0xd35d438dc58f0d9dULL, 0x0a78eb28f5c70b3dULL, 0x666ea36f7879462cULL, 0x0e0a77c19a07df2fULL};
 
-void hq_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
+// generic 4-limb Montgomery product r = a * b * 2^-256 mod P (host; scalar bookkeeping only)
+void hm_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4], const uint64_t P[4], uint64_t INV) {
     uint64_t t[6] = {0, 0, 0, 0, 0, 0};
     for (int i = 0; i < 4; i++) {
         u128_t c = 0;
@@ -279,11 +283,11 @@ void hq_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
         c += t[4];
         t[4] = (uint64_t)c;
         t[5] = (uint64_t)(c >> 64);
-        uint64_t m = t[0] * HQ_INV;
-        c = (u128_t)m * HQ_P[0] + t[0];
+        uint64_t m = t[0] * INV;
+        c = (u128_t)m * P[0] + t[0];
         c >>= 64;
         for (int j = 1; j < 4; j++) {
-            c += (u128_t)m * HQ_P[j] + t[j];
+            c += (u128_t)m * P[j] + t[j];
             t[j - 1] = (uint64_t)c;
             c >>= 64;
         }
@@ -295,19 +299,36 @@ void hq_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) {
     if (!ge) {
         ge = true;
         for (int i = 3; i >= 0; i--) {
-            if (t[i] > HQ_P[i]) break;
-            if (t[i] < HQ_P[i]) { ge = false; break; }
+            if (t[i] > P[i]) break;
+            if (t[i] < P[i]) { ge = false; break; }
         }
     }
     if (ge) {
         u128_t br = 0;
         for (int i = 0; i < 4; i++) {
-            u128_t d = (u128_t)t[i] - HQ_P[i] - (uint64_t)br;
+            u128_t d = (u128_t)t[i] - P[i] - (uint64_t)br;
             t[i] = (uint64_t)d;
             br = (d >> 64) & 1;
         }
     }
     memcpy(r, t, 32);
+}
+void hq_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) { hm_mul(r, a, b, HQ_P, HQ_INV); }
+// host Fr (challenge powers of the quotient programs)
+const uint64_t HR_P[4] = {0x43e1f593f0000001ULL, 0x2833e84879b97091ULL, 0xb85045b68181585dULL, 0x30644e72e131a029ULL};
+const uint64_t HR_INV = 0xc2e1f593efffffffULL;
+const uint64_t HR_ONE[4] = {0xac96341c4ffffffbULL, 0x36fc76959f60cd29ULL, 0x666ea36f7879462eULL, 0x0e0a77c19a07df2fULL};
+void hr_mul(uint64_t r[4], const uint64_t a[4], const uint64_t b[4]) { hm_mul(r, a, b, HR_P, HR_INV); }
+void hr_pow(uint64_t r[4], const uint64_t a[4], uint64_t e) {
+    uint64_t acc[4], base[4];
+    memcpy(acc, HR_ONE, 32);
+    memcpy(base, a, 32);
+    while (e) {
+        if (e & 1) hr_mul(acc, acc, base);
+        hr_mul(base, base, base);
+        e >>= 1;
+    }
+    memcpy(r, acc, 32);
 }
 void hq_inv(uint64_t r[4], const uint64_t a[4]) {
     uint64_t e[4] = {HQ_P[0] - 2, HQ_P[1], HQ_P[2], HQ_P[3]};
@@ -1517,3 +1538,5 @@ int b2_last_msm_phases(double* phases) {
 }
 
 }  // extern "C"
+
+#include "api_quotient.inl"

@@ -157,6 +157,87 @@ int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void
 int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits,
                     int do_ifft, const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96);
 
+/* ---- quotient evaluation (evaluate_h) ---------------------------------------------- */
+/* Evaluator::evaluate_h (plonk/evaluation.rs:778-1226) computes, for every row of the extended
+ * domain, the y-fold of all gate polynomials and of the permutation / lookup / shuffle terms.
+ * The circuit-specific part is the reference's own data: `rotations`, `constants` and the list
+ * of `Calculation`s over `ValueSource`s (evaluation.rs:46-112, built by Evaluator::new,
+ * :309-620).  A program is that list in flat form; the engine lowers it once (dead-code
+ * elimination, Store inlining, slot allocation from live ranges) and then evaluates it with ONE
+ * kernel launch per call, every row a thread, columns device-resident. */
+#define B2_Q_CONSTANT 0      /* ValueSource::Constant(index)                       (evaluation.rs:48) */
+#define B2_Q_INTERMEDIATE 1  /* ValueSource::Intermediate(index): result of calcs[index]        (:50) */
+#define B2_Q_FIXED 2         /* ValueSource::Fixed(index, rotation)                            (:52) */
+#define B2_Q_ADVICE 3        /* ValueSource::Advice(index, rotation)                           (:54) */
+#define B2_Q_INSTANCE 4      /* ValueSource::Instance(index, rotation)                         (:56) */
+#define B2_Q_AUX 5           /* engine-side columns: z / sigma / m cosets, l0, l_last, l_active_row */
+#define B2_Q_CHALLENGE 6     /* challenges[index] (beta, gamma, theta, y, beta*zeta*delta^j, ...) */
+#define B2_Q_COSET_X 7       /* x0 * x_step^row: `beta_term` of evaluation.rs:1018-1019 */
+
+#define B2_QOP_ADD 0            /* Calculation::Add(a, b)                                      (:97) */
+#define B2_QOP_SUB 1            /* Calculation::Sub(a, b)                                      (:99) */
+#define B2_QOP_MUL 2            /* Calculation::Mul(a, b)                                     (:101) */
+#define B2_QOP_NEGATE 3         /* Calculation::Negate(a)                                     (:103) */
+#define B2_QOP_LC_CHALLENGE 4   /* Calculation::LcChallenge(a, b, ch, p) = (a + ch^p) * b, ch^1 when p <= 1 (:105,208-211) */
+#define B2_QOP_MUL_CH_ADD 5     /* a * ch + b: Calculation::LcTheta (ch = theta, :107) and the fold value * y + part (:897) */
+#define B2_QOP_ADD_CHALLENGE 6  /* Calculation::AddChallenge(a, ch)                           (:109) */
+#define B2_QOP_STORE 7          /* Calculation::Store(a)                                      (:111) */
+
+typedef struct b2_qsrc {
+    uint32_t kind;      /* B2_Q_* */
+    uint32_t index;
+    uint32_t rotation;  /* column kinds: index into `rotations` */
+} b2_qsrc;
+typedef struct b2_qcalc {
+    uint32_t op;        /* B2_QOP_* */
+    b2_qsrc a, b;
+    uint32_t challenge; /* LC_CHALLENGE / MUL_CH_ADD / ADD_CHALLENGE: index into challenges */
+    uint32_t power;     /* LC_CHALLENGE */
+} b2_qcalc;
+typedef struct b2_quotient_program_desc {
+    const int32_t* rotations;   /* Evaluator::rotations (:274) */
+    uint32_t n_rotations;
+    const void* constants;      /* Evaluator::constants (:272), n_constants * 32 B, Montgomery */
+    uint32_t n_constants;
+    const b2_qcalc* calcs;      /* Evaluator::calculations (:276) followed by whatever the caller appends */
+    uint32_t n_calcs;
+    b2_qsrc result;             /* the value stored per row */
+    uint32_t n_fixed, n_advice, n_instance, n_aux, n_challenges;   /* table sizes (validated) */
+} b2_quotient_program_desc;
+/* Lowers and validates on the host (works without a GPU); device upload happens on first use. */
+int b2_quotient_program_create(const b2_quotient_program_desc* desc, b2_handle_t* out);
+int b2_quotient_program_free(b2_handle_t program);
+/* lowered instruction count, shared-memory slots per row, field multiplications / additions per row */
+int b2_quotient_program_info(b2_handle_t program, uint32_t* n_instr, uint32_t* n_slots, uint32_t* n_mul,
+                             uint32_t* n_addsub);
+
+/* Diagnostic: the lowered program (4 words per instruction: op | dst_slot << 8, operand a, operand b, 0;
+ * operand word = kind << 28 | rotation << 20 | index with kind 0 constant, 1 slot, 2 column (fixed, advice,
+ * instance, aux concatenated), 3 challenge (derived powers appended after the caller's), 4 coset x; ops
+ * 0 add, 1 sub, 2 mul, 3 neg, 4 copy) and the (challenge, power) pairs of the derived challenge entries.
+ * Lets the host-side lowering be checked without a GPU. */
+int b2_quotient_program_dump(b2_handle_t program, uint32_t* instr_words, size_t instr_capacity, uint32_t* result_word,
+                             uint32_t* derived_pairs, size_t derived_capacity, uint32_t* n_derived);
+
+typedef struct b2_quotient_args {
+    uint32_t log_rows;            /* rows = 2^log_rows: extended_k (evaluation.rs:792), or k for one coset */
+    uint32_t rot_scale;           /* 2^(extended_k - k) (:793), or 1 */
+    const void* const* fixed;     /* host arrays of DEVICE pointers, one per column, 2^log_rows Fr each */
+    const void* const* advice;
+    const void* const* instance;
+    const void* const* aux;
+    const void* challenges;       /* host, n_challenges * 32 B */
+    const void* x0;               /* host 32 B each; NULL when the program has no B2_Q_COSET_X operand */
+    const void* x_step;
+    const void* scale;            /* host, NULL or scale_len * 32 B: result *= scale[row % scale_len] */
+    uint32_t scale_len;           /*   (divide_by_vanishing_poly's t_evaluations, poly/domain.rs:354-373) */
+    void* out;                    /* device: result of row i is stored at out[out_offset + i * out_stride] */
+    uint64_t out_stride;
+    uint64_t out_offset;
+    void* stream;                 /* cudaStream_t or NULL; the call returns after the launch is enqueued */
+} b2_quotient_args;
+int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args);
+
 /* ---- memory helpers --------------------------------------------------------------- */
 int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
 int b2_host_free(void* p);

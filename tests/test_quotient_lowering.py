@@ -1,0 +1,156 @@
+"""CPU-only: the host logic of the quotient engine -- the Python mirror's program builder
+(halo2_gpu_specific_b200/evaluation.py) and the C++ lowering behind b2_quotient_program_create
+(Store inlining, dead-code elimination, slot allocation, derived challenge powers) -- checked by
+interpreting the DUMPED lowered program with big ints and comparing every extended-domain row with the
+oracle's evaluate_h (oracle/plonk.py, restatement of plonk/evaluation.rs:778-1226)."""
+import pytest
+
+import plonk_fixture as fxm
+from oracle import bn254 as o
+from oracle import plonk as P
+
+import halo2_gpu_specific_b200 as h2
+from halo2_gpu_specific_b200 import evaluation as E
+from halo2_gpu_specific_b200._lib import B2Error
+
+R = o.R_MOD
+
+
+def make_evaluator(fx):
+    ev, cs = fx["ev"], fx["cs"]
+    return h2.Evaluator(ev.rotations, ev.constants, ev.calculations, ev.value_parts, ev.lookup_results,
+                        ev.shuffle_results, cs.num_fixed, cs.num_advice, cs.num_instance, cs.permutation_columns,
+                        cs.degree(), cs.blinding_factors())
+
+
+def interpret(prog, rotations, constants, columns, challenges, rows, rot_scale, x0, x_step):
+    """reference semantics of the lowered form (include/b2pcs.h, b2_quotient_program_dump)"""
+    instr, result, derived = prog.dump()
+    ch = list(challenges) + [pow(challenges[c], p, R) for c, p in derived]
+    n_slots = prog.info()["n_slots"]
+    out = []
+    x = x0
+    for row in range(rows):
+        slots = [None] * n_slots
+
+        def fetch(w):
+            kind, rot, idx = w >> 28, (w >> 20) & 0xff, w & 0xfffff
+            if kind == 0:
+                return constants[idx]
+            if kind == 1:
+                assert slots[idx] is not None, "read of an unwritten slot"
+                return slots[idx]
+            if kind == 2:
+                return columns[idx][(row + rotations[rot] * rot_scale) % rows]
+            if kind == 3:
+                return ch[idx]
+            return x
+
+        for op, dst, a, b in instr:
+            va = fetch(a)
+            if op == 3:
+                r = (-va) % R
+            elif op == 4:
+                r = va
+            else:
+                vb = fetch(b)
+                r = (va * vb) % R if op == 2 else ((va + vb) % R if op == 0 else (va - vb) % R)
+            slots[dst] = r
+        out.append(fetch(result))
+        x = x * x_step % R
+    return out
+
+
+@pytest.fixture(scope="module")
+def fx():
+    return fxm.build(k=5, seed=11)
+
+
+def test_lowered_program_matches_oracle(fx):
+    Ev = make_evaluator(fx)
+    cz = fxm.cosets(fx)
+    want = fxm.oracle_h(fx, cz)
+    prog = Ev.program(len(fx["perm_z"]), [len(l["z"]) for l in fx["lookups_lagrange"]], len(fx["shuffle_z"]))
+    info = prog.info()
+    assert info["n_slots"] < info["n_instr"] and info["n_mul"] > 0
+    d = fx["domain"]
+    aux = [cz["l0"], cz["l_last"], cz["l_active_row"]] + cz["sigma"] + cz["perm_z"]
+    for lk in cz["lookups"]:
+        aux += lk["z_cosets"] + [lk["m_coset"]]
+    aux += cz["shuffles"]
+    columns = cz["fixed"] + cz["advice"] + cz["instance"] + aux
+    challenges = [fx["beta"], fx["gamma"], fx["theta"], fx["y"]]
+    dlt = fx["beta"] * d.g_coset % R
+    for _ in fx["cs"].permutation_columns:
+        challenges.append(dlt)
+        dlt = dlt * P.FR_DELTA % R
+    # rotations / constants as the builder extended them: re-derive through a second build
+    rotations = list(fx["ev"].rotations)
+    for r in (0, 1, -(fx["cs"].blinding_factors() + 1)):
+        if r not in rotations:
+            rotations.append(r)
+    constants = list(fx["ev"].constants)
+    if 1 not in constants:
+        constants.append(1)
+    got = interpret(prog, rotations, constants, columns, challenges, d.extended_len(),
+                    1 << (d.extended_k - d.k), 1, d.extended_omega)
+    assert got == want
+
+
+def test_gates_only_program(fx):
+    """no permutation / lookups / shuffles: only the value_parts fold"""
+    ev, cs = fx["ev"], fx["cs"]
+    Ev = h2.Evaluator(ev.rotations, ev.constants, ev.calculations, ev.value_parts, [], [], cs.num_fixed,
+                      cs.num_advice, cs.num_instance, [], cs.degree(), cs.blinding_factors())
+    prog = Ev.program(0, [], 0)
+    cz = fxm.cosets(fx)
+    d = fx["domain"]
+    cs2 = P.ConstraintSystem(cs.num_fixed, cs.num_advice, cs.num_instance, cs.degree(), cs.blinding_factors())
+    cs2.gates = cs.gates
+    ev2 = P.Evaluator.new(cs2)
+    want = P.evaluate_h(ev2, cs2, d, cz["fixed"], cz["advice"], cz["instance"], cz["l0"], cz["l_last"],
+                        cz["l_active_row"], [], fx["y"], fx["beta"], fx["gamma"], fx["theta"], [], [], [])
+    rotations = list(ev.rotations)
+    for r in (0, 1, -(cs.blinding_factors() + 1)):
+        if r not in rotations:
+            rotations.append(r)
+    columns = cz["fixed"] + cz["advice"] + cz["instance"] + [cz["l0"], cz["l_last"], cz["l_active_row"]]
+    got = interpret(prog, rotations, list(ev.constants), columns, [fx["beta"], fx["gamma"], fx["theta"], fx["y"]],
+                    d.extended_len(), 1 << (d.extended_k - d.k), 1, d.extended_omega)
+    assert got == want
+    # the lookups' calculations are dead code here and must have been eliminated
+    full = make_evaluator(fx).program(len(fx["perm_z"]), [len(l["z"]) for l in fx["lookups_lagrange"]], 1).info()
+    assert prog.info()["n_instr"] < full["n_instr"] // 2
+
+
+def test_lowering_rejects_bad_programs():
+    mk = lambda calcs, result, **kw: E.QuotientProgram([0], [0, 1], calcs, result, kw.get("nf", 1), 1, 0, 0, 4)  # noqa: E731
+    with pytest.raises(B2Error):   # forward reference
+        mk([("Add", ("Intermediate", 1), ("Constant", 0)), ("Store", ("Constant", 1))], ("Intermediate", 0))
+    with pytest.raises(B2Error):   # column out of range
+        mk([("Store", ("Fixed", 3, 0))], ("Intermediate", 0))
+    with pytest.raises(B2Error):   # rotation index out of range
+        mk([("Store", ("Advice", 0, 2))], ("Intermediate", 0))
+    with pytest.raises(B2Error):   # constant out of range
+        mk([("Store", ("Constant", 9))], ("Intermediate", 0))
+    p = mk([("Store", ("Fixed", 0, 0))], ("Intermediate", 0))   # a pure column read needs no instruction
+    assert p.info()["n_instr"] == 0
+    p.free()
+
+
+def test_lc_challenge_powers_are_derived():
+    calcs = [("Store", ("Advice", 0, 0)),
+             ("LcChallenge", ("Intermediate", 0), ("Intermediate", 0), "Beta", 3),
+             ("LcChallenge", ("Intermediate", 1), ("Intermediate", 0), "Beta", 3),
+             ("LcChallenge", ("Intermediate", 2), ("Intermediate", 0), "Gamma", 1)]
+    p = E.QuotientProgram([0], [0, 1], calcs, ("Intermediate", 3), 0, 1, 0, 0, 4)
+    instr, result, derived = p.dump()
+    assert derived == [(0, 3)]            # beta^3 once; gamma^1 is gamma itself (evaluation.rs:208-211)
+    a0 = [5, 7, 11, 13]
+    got = interpret(p, [0], [0, 1], [a0], [2, 3, 0, 0], 4, 1, 1, 1)
+    want = []
+    for v in a0:
+        t = (v + 8) * v % R
+        t = (t + 8) * v % R
+        want.append((t + 3) * v % R)
+    assert got == want

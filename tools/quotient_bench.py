@@ -1,0 +1,136 @@
+"""Times the fused quotient-evaluation kernel (b2_quotient_eval) on a synthetic zkWasm-scale shape
+(A = 64 advice, F = 32 fixed, I = 1, 8 lookups with 12 input sets, 4 shuffles,
+8 permutation sets over 24 columns, degree 5), columns resident in HBM.
+
+    python tools/quotient_bench.py --k 20 [--gates 96] [--reps 5] [--json out.json]
+
+Reports rows/s, field multiplications/s against the measured integer peak (b2_imad_probe) and the
+column bytes read per second against the HBM peak."""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import random
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import halo2_gpu_specific_b200 as h2  # noqa: E402
+from halo2_gpu_specific_b200 import _fr, _lib  # noqa: E402
+from halo2_gpu_specific_b200 import evaluation as E  # noqa: E402
+
+
+def synthetic_evaluator(A=64, F=32, I=1, gates=96, lookups=(2, 2, 2, 2, 1, 1, 1, 1), shuffles=4, perm_cols=24,
+                        degree=5, seed=1):
+    """Calculation lists in the reference's form (what Evaluator::new would hand over), no CSE needed."""
+    rng = random.Random(seed)
+    rotations = [0, 1, -1, 2]
+    constants = [0, 1, 2, 7]
+    calcs = []
+
+    def emit(c):
+        calcs.append(c)
+        return ("Intermediate", len(calcs) - 1)
+
+    def col(kind, n):
+        return emit(("Store", (kind, rng.randrange(n), rng.randrange(len(rotations)))))
+
+    value_parts = []
+    for g in range(gates):   # q * (a*b - c) and q * (a*b*c + 7*d - e): degree 3 / 4
+        q = col("Fixed", F)
+        a, b, c = col("Advice", A), col("Advice", A), col("Advice", A)
+        if g % 2 == 0:
+            t = emit(("Sub", emit(("Mul", a, b)), c))
+        else:
+            d, e = col("Advice", A), col("Advice", A)
+            t = emit(("Mul", emit(("Mul", a, b)), c))
+            t = emit(("Sub", emit(("Add", t, emit(("Mul", d, ("Constant", 3))))), e))
+        value_parts.append(emit(("Mul", q, t)))
+    lookup_results = []
+    for sets in lookups:
+        def compressed(width):
+            lc = col("Advice", A)
+            for _ in range(width - 1):
+                lc = emit(("LcTheta", lc, col("Advice", A)))
+            return lc
+        table = ("AddChallenge", emit(("LcTheta", col("Fixed", F), col("Fixed", F))), "Beta")
+        prods, sums = [], []
+        for _ in range(sets):
+            ins = [emit(("AddChallenge", compressed(2), "Beta")) for _ in range(2)]
+            prods.append(("Store", emit(("Mul", ins[0], ins[1]))))
+            sums.append(("Store", emit(("Add", ins[1], ins[0]))))
+        lookup_results.append((table, prods, sums))
+    shuffle_results = []
+    for _ in range(shuffles):
+        a, b = col("Advice", A), col("Advice", A)
+        shuffle_results.append((("AddChallenge", a, "Beta"), ("AddChallenge", b, "Beta")))
+    perm = [("Advice", i) for i in range(perm_cols)]
+    ev = h2.Evaluator(rotations, constants, calcs, value_parts, lookup_results, shuffle_results, F, A, I, perm, degree, 5)
+    return ev, list(lookups), shuffles, (perm_cols + degree - 3) // (degree - 2)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--k", type=int, default=20)
+    ap.add_argument("--gates", type=int, default=96)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    _lib.require_gpu()
+    _lib.set_device(0)
+    ev, lookups, shuffles, n_sets = synthetic_evaluator(gates=args.gates)
+    prog = ev.program(n_sets, lookups, shuffles)
+    info = prog.info()
+    ext_k = args.k + 2
+    rows = 1 << ext_k
+    ncols = prog.n_fixed + prog.n_advice + prog.n_instance + prog.n_aux
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    # synthetic resident columns: 8 distinct random columns, the rest device copies of them
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 1 << 62, size=(8, rows, 4), dtype=np.uint64)   # < 2^254: valid field elements (< r)
+    base[:, :, 3] &= np.uint64((1 << 60) - 1)
+    buf = E.DeviceBuffer(ncols * rows)
+    t0 = time.time()
+    for c in range(ncols):
+        buf.upload(base[c % 8], c * rows)
+    upload_s = time.time() - t0
+    out = E.DeviceBuffer(rows)
+    ptrs = [buf.ptr + c * rows * 32 for c in range(ncols)]
+    nf, na, ni = prog.n_fixed, prog.n_advice, prog.n_instance
+    challenges = [(i + 2) * 0x123456789ABCDEF % _fr.R_MOD for i in range(prog.n_challenges)]
+    dom = h2.EvaluationDomain(5, args.k)
+    times = []
+    for _ in range(args.reps + 2):
+        prog.eval(ext_k, 4, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+                  out.ptr, x0=1, x_step=dom._ext_omega, scale=dom.t_evaluations)
+        times.append(_lib.last_timing()[0])
+    times = times[2:]
+    ms = float(np.median(times))
+    wide, modmul = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib().b2_imad_probe(ctypes.byref(wide), ctypes.byref(modmul)))
+    instr, _, _ = prog.dump()
+    col_reads = sum(1 for op, dst, a, b in instr for w in ((a, b) if op < 3 else (a,)) if (w >> 28) == 2)
+    muls = info["n_mul"] + 2   # + coset point + vanishing scale
+    res = {
+        "k": args.k, "extended_k": ext_k, "rows": rows, "columns_resident": ncols,
+        "resident_GiB": ncols * rows * 32 / 2**30, "program": info, "column_reads_per_row": col_reads,
+        "kernel_ms": ms, "rows_per_s": rows / (ms * 1e-3),
+        "modmul_per_s": muls * rows / (ms * 1e-3), "modmul_peak_per_s": modmul.value,
+        "int_frac": muls * rows / (ms * 1e-3) / modmul.value,
+        "column_GBps": col_reads * 32 * rows / (ms * 1e-3) / 1e9,
+        "upload_s": upload_s,
+    }
+    print(json.dumps(res))
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump(res, f, indent=1)
+    buf.free()
+    out.free()
+
+
+if __name__ == "__main__":
+    main()
