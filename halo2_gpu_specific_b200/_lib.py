@@ -48,6 +48,7 @@ SYMBOLS = [
     "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
+    "b2_batch_invert", "b2_batch_invert_dev", "b2_prefix_scan", "b2_prefix_scan_dev", "b2_fr_vec_dev",
 ]
 
 _lib = None
@@ -102,6 +103,11 @@ def lib() -> ctypes.CDLL:
         L.b2_quotient_program_free.argtypes = [u64]
         L.b2_quotient_program_info.argtypes = [u64] + [ctypes.POINTER(u32)] * 4
         L.b2_quotient_eval.argtypes = [u64, vp]
+        L.b2_batch_invert.argtypes = [vp, sz]
+        L.b2_batch_invert_dev.argtypes = [vp, sz, vp]
+        L.b2_prefix_scan.argtypes = [ctypes.c_int, vp, sz, vp, vp, sz]
+        L.b2_prefix_scan_dev.argtypes = [ctypes.c_int, vp, sz, vp, vp, vp, sz, vp]
+        L.b2_fr_vec_dev.argtypes = [ctypes.c_int, vp, vp, sz, vp, vp]
         L.b2_quotient_program_dump.argtypes = [u64, vp, sz, ctypes.POINTER(u32), vp, sz, ctypes.POINTER(u32)]
         _lib = L
     return _lib

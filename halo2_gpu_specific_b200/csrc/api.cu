@@ -23,6 +23,7 @@
 #include "msm.cuh"
 #include "ntt.cuh"
 #include "quotient.cuh"
+#include "scan.cuh"
 
 using namespace b2;
 
@@ -117,6 +118,8 @@ struct Lane {
     Buf ntt_in, ntt_work, ntt_out;
     // quotient evaluation: per-call tables, spilled slots
     Buf qtab, qspill;
+    // batch inversion / prefix scans
+    Buf scan_tmp, scan_tot;
     // timing
     cudaEvent_t ev[16];
     cudaEvent_t busy;            // last work enqueued on a caller-provided stream (async _dev calls)
@@ -1540,3 +1543,4 @@ int b2_last_msm_phases(double* phases) {
 }  // extern "C"
 
 #include "api_quotient.inl"
+#include "api_scan.inl"

@@ -238,6 +238,25 @@ typedef struct b2_quotient_args {
 } b2_quotient_args;
 int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args);
 
+/* ---- grand products / grand sums ----------------------------------------------------- */
+/* The vector steps between the expression kernel and commit_lagrange_and_ifft when the prover builds
+ * the permutation, logup and shuffle z columns (plonk/permutation/prover.rs:72-165,
+ * plonk/logup/prover.rs:263-336, plonk/shuffle/prover.rs:107-141).  *_dev variants take device pointers
+ * and are asynchronous on `stream` when it is not NULL. */
+/* batch_invert (arithmetic.rs:840-844; ff::BatchInvert semantics: zeros are left as zero), in place */
+int b2_batch_invert(void* a, size_t n);
+int b2_batch_invert_dev(void* d_a, size_t n, void* stream);
+/* out[0] = init, out[i + 1] = init (op) in[0] (op) ... (op) in[i] for i + 1 < n_out <= n_in + 1.
+ * op 0: product (mul_acc, arithmetic.rs:806-836; permutation/prover.rs:149-152; shuffle/prover.rs:137-141),
+ * op 1: sum (logup/prover.rs:318-336).  init: 32 B on the host, NULL = the operator's identity; d_init (device,
+ * 32 B) overrides it -- the last_z hand-over between column sets (permutation/prover.rs:146,160) without a
+ * host round trip.  out must not alias in. */
+int b2_prefix_scan(int op, const void* in, size_t n_in, const void* init, void* out, size_t n_out);
+int b2_prefix_scan_dev(int op, const void* d_in, size_t n_in, const void* init, const void* d_init, void* d_out,
+                       size_t n_out, void* stream);
+/* d_out[i] = d_a[i] op d_b[i] over Fr on device pointers; op: 0 mul, 1 add, 2 sub.  d_out may alias an input. */
+int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+
 /* ---- memory helpers --------------------------------------------------------------- */
 int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
 int b2_host_free(void* p);
