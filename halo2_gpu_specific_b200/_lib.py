@@ -36,6 +36,7 @@ class NttDesc(ctypes.Structure):
         ("out", ctypes.c_void_p),
         ("out_stride", ctypes.c_uint64),
         ("stream", ctypes.c_void_p),
+        ("coset_gen", ctypes.c_void_p),
     ]
 
 

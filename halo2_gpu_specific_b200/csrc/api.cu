@@ -140,6 +140,7 @@ struct DeviceCtx {
     bool lane_free[MAX_LANES];
     std::mutex plan_mu;             // NTT plan cache
     std::map<std::string, NttPlan*> plans;
+    std::map<std::string, Fr*> pow_tables;   // g^j tables of coset transforms, keyed by (g, length)
     std::atomic<uint64_t> launches{0};
 };
 
@@ -750,7 +751,7 @@ int ntt_get_plan(Lane& ctx, const void* omega, const void* divisor, uint32_t log
 // elements when npass > 1.  out may alias in.
 int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, uint64_t n_in, void* d_out,
                 uint64_t out_stride, uint64_t n_out, void* d_work, uint64_t cols, const Fr* coset_in,
-                const Fr* coset_out, cudaStream_t st) {
+                const Fr* coset_out, cudaStream_t st, const Fr* in_scale = nullptr) {
     const uint32_t k = pl->log_n;
     const uint64_t N = 1ull << k;
     uint32_t s_lo = k;
@@ -777,6 +778,7 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         a.tw_hi = first ? pl->tw_hi_scaled : pl->tw_hi;
         a.tw_full = first ? pl->tw_full : nullptr;
         if (first && !last && pl->tw_full && pl->has_div) a.scale_out = 1;  // table entry 0 is the divisor, not 1
+        if (first) a.in_scale = in_scale;
         if (first && coset_in) {
             a.coset_in = 1;
             a.zin1 = coset_in[0];
@@ -827,6 +829,27 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
             }
         }
     }
+    return B2_OK;
+}
+
+// g^j, j < count, resident and cached per device (one table per coset generator of a domain)
+int ntt_pow_table(Lane& ctx, const void* gen, uint64_t count, const Fr** out) {
+    std::string key((const char*)gen, 32);
+    key.append((const char*)&count, 8);
+    std::lock_guard<std::mutex> plk(ctx.dev->plan_mu);
+    auto it = ctx.dev->pow_tables.find(key);
+    if (it != ctx.dev->pow_tables.end()) {
+        *out = it->second;
+        return B2_OK;
+    }
+    void* p = nullptr;
+    CK(cudaMalloc(&p, (size_t)count * 32));
+    const unsigned long long threads = (count + POW_SEQ - 1) / POW_SEQ;
+    LAUNCH(ctx, ntt_pow_seq_kernel, (unsigned)((threads + 127) / 128), 128, 0, ctx.stream, (Fr*)p, fr_from_bytes(gen),
+           (unsigned long long)count);
+    CK(cudaStreamSynchronize(ctx.stream));
+    ctx.dev->pow_tables[key] = (Fr*)p;
+    *out = (Fr*)p;
     return B2_OK;
 }
 
@@ -1152,6 +1175,8 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
     if (d->coset_out) { cout[0] = fr_from_bytes(d->coset_out); cout[1] = fr_from_bytes((const char*)d->coset_out + 32); }
     const Fr* pcin = d->coset_in ? cin : nullptr;
     const Fr* pcout = d->coset_out ? cout : nullptr;
+    const Fr* in_scale = nullptr;
+    if (d->coset_gen && (rc = ntt_pow_table(*ctx, d->coset_gen, d->n_in, &in_scale))) return rc;
 
     // location: 0 host -> host, 1 device -> device, 2 host -> device, 3 device -> host
     const bool in_host = (d->location == 0 || d->location == 2);
@@ -1207,7 +1232,7 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
         const bool timed = (nl == 1 || !(in_host || out_host)) && !async;
         if (timed) CK(cudaEventRecord(ln->ev[10], st));
         if ((rc = ntt_run_dev(*ln, pl, din, din_stride, d->n_in, dout, dout_stride, d->n_out, ln->ntt_work.p, cc, pcin,
-                              pcout, st)))
+                              pcout, st, in_scale)))
             return rc;
         if (timed) CK(cudaEventRecord(ln->ev[11], st));
         if (out_host &&

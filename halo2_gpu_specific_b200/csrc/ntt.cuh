@@ -49,6 +49,7 @@ struct NttPassArgs {
     int coset_out;                      // last pass : multiply X[o] by zout[o % 3 - 1]
     int scale_out;                      // last pass : multiply everything by `scale` (P == 1 iNTT)
     uint32_t cl_log;                    // log2 of the cluster size that owns one tile (0 = single CTA)
+    const Fr* in_scale;                 // first pass: optional table, x[i] *= in_scale[i] (g^i: evaluation on the coset g*H)
     Fr zin1, zin2, zout1, zout2, scale;
 };
 
@@ -173,6 +174,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
                 if (r3 == 1) x = fp_mul<FrParams>(x, a.zin1);
                 else if (r3 == 2) x = fp_mul<FrParams>(x, a.zin2);
             }
+            if (first && a.in_scale != nullptr) x = fp_mul<FrParams>(x, fp_load_nc<FrParams>(a.in_scale + pos));
         } else {
             x = Fr::zero();
         }
@@ -301,6 +303,22 @@ __global__ void ntt_pow_table_kernel(Fr* out, const Fr base, unsigned long long 
     }
     if (has_scale) acc = fp_mul<FrParams>(acc, scale);
     fp_store<FrParams>(out + j, acc);
+}
+
+// out[j] = base^j, j < count: every thread raises base to its first index, then multiplies along
+constexpr int POW_SEQ = 64;
+__global__ void __launch_bounds__(128) ntt_pow_seq_kernel(Fr* out, const Fr base, unsigned long long count) {
+    const unsigned long long j0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) * POW_SEQ;
+    if (j0 >= count) return;
+    Fr acc = Fr::one(), b = base;
+    for (unsigned long long e = j0; e; e >>= 1) {
+        if (e & 1ull) acc = fp_mul<FrParams>(acc, b);
+        b = fp_sqr<FrParams>(b);
+    }
+    for (int i = 0; i < POW_SEQ && j0 + i < count; i++) {
+        fp_store<FrParams>(out + j0 + i, acc);
+        acc = fp_mul<FrParams>(acc, base);
+    }
 }
 
 // a[i] *= t[i % period]  (divide_by_vanishing_poly, poly/domain.rs:354-373)

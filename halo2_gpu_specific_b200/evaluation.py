@@ -361,7 +361,8 @@ class Evaluator:
     # ---- evaluate_h -----------------------------------------------------------------------
     def evaluate_h(self, domain, fixed_polys, advice_polys, instance_polys, l0, l_last, l_active_row, sigma_polys,
                    y: int, beta: int, gamma: int, theta: int, lookups, shuffles, permutations,
-                   to_coeff: bool = False, zeta: Optional[int] = None) -> np.ndarray:
+                   to_coeff: bool = False, zeta: Optional[int] = None, mode: str = "cosets",
+                   cosets: Optional[Sequence[int]] = None) -> np.ndarray:
         """evaluation.rs:778-1226 for one proof.
 
         *_polys, sigma_polys, permutations (z per set), lookups ([{"z": [...], "m": poly}]), shuffles ([poly]):
@@ -369,9 +370,17 @@ class Evaluator:
         (:1229-1241); l0 / l_last / l_active_row: extended-domain evaluations as ProvingKey holds them.
         Everything is extended on the device and stays there.  Returns the extended evaluations, or with
         to_coeff=True the coefficients of h(X) = numerator / (X^n - 1) (divide_by_vanishing_poly folded into
-        the kernel's store, then extended_to_coeff on the device): vanishing/prover.rs:64-96."""
+        the kernel's store, then extended_to_coeff on the device): vanishing/prover.rs:64-96.
+
+        mode "extended": every polynomial is coset-extended to 2^extended_k rows first (the reference's
+        layout).  mode "cosets" (default): the extended domain is walked as its 2^(extended_k - k)
+        interleaved cosets zeta * extended_omega^c * <omega> -- extended row 2^(extended_k-k) * i + c is row i
+        of coset c, and a rotation never leaves its coset -- so each pass needs only size-2^k transforms
+        (no zero padding) and 2^-(extended_k-k) of the memory; `cosets` restricts the pass to some of them
+        (the multi-GPU split: one coset per rank, rows of the others left untouched)."""
         require_gpu()
         ext_len = domain.extended_len()
+        n = domain.n
         n_sets = len(permutations)
         set_counts = [len(lk["z"]) for lk in lookups]
         prog = self.program(n_sets, set_counts, len(shuffles))
@@ -380,38 +389,87 @@ class Evaluator:
             aux_polys += list(lk["z"]) + [lk["m"]]
         aux_polys += list(shuffles)
         groups = [list(fixed_polys), list(advice_polys), list(instance_polys), aux_polys]
-        total_cols = sum(len(g) for g in groups) + 3
-        buf = DeviceBuffer(total_cols * ext_len)
+        zeta_v = domain._zeta if zeta is None else zeta
+        R = _fr.R_MOD
+        challenges = [beta % R, gamma % R, theta % R, y % R]
+        d = beta * zeta_v % R                                     # delta_start, evaluation.rs:1011
+        for _ in self.permutation_columns:
+            challenges.append(d)
+            d = d * DELTA % R
+        lag_host = [np.asarray(v, dtype=np.uint64).reshape(ext_len, 4) for v in (l0, l_last, l_active_row)]
+        n_polys = sum(len(g) for g in groups)
+        if mode == "extended":
+            if cosets is not None:
+                raise B2Error(B2_ERR_ARG, "`cosets` needs mode='cosets'")
+            buf = DeviceBuffer((n_polys + 3) * ext_len)
+            out = DeviceBuffer(ext_len)
+            try:
+                ptrs, col = [], 0
+                for g in groups:
+                    if g:
+                        coeff_to_extended_dev(domain, np.stack([np.asarray(p, dtype=np.uint64).reshape(-1, 4) for p in g]),
+                                              buf, col)
+                    ptrs.append([buf.ptr + (col + i) * ext_len * 32 for i in range(len(g))])
+                    col += len(g)
+                lag = []
+                for v in lag_host:
+                    buf.upload(v, col * ext_len)
+                    lag.append(buf.ptr + col * ext_len * 32)
+                    col += 1
+                scale = domain.t_evaluations if to_coeff else None
+                prog.eval(domain.extended_k, 1 << (domain.extended_k - domain.k), ptrs[0], ptrs[1], ptrs[2],
+                          lag + ptrs[3], challenges, out.ptr, x0=1, x_step=domain._ext_omega, scale=scale)
+                return extended_to_coeff_dev(domain, out) if to_coeff else out.download()
+            finally:
+                buf.free()
+                out.free()
+        if mode != "cosets":
+            raise B2Error(B2_ERR_ARG, f"unknown mode {mode!r}")
+        n_cosets = 1 << (domain.extended_k - domain.k)
+        which = list(range(n_cosets)) if cosets is None else list(cosets)
+        if to_coeff and len(which) != n_cosets:
+            raise B2Error(B2_ERR_ARG, "to_coeff needs every coset")
+        coef = DeviceBuffer(max(1, n_polys) * n)           # coefficient forms, uploaded once
+        cos = DeviceBuffer((n_polys + 3) * n)               # one coset of every polynomial + l0 / l_last / l_active_row
         out = DeviceBuffer(ext_len)
         try:
+            allp = [np.asarray(p, dtype=np.uint64).reshape(n, 4) for g in groups for p in g]
+            if allp:
+                coef.upload(np.stack(allp))
             ptrs, col = [], 0
             for g in groups:
-                if g:
-                    coeff_to_extended_dev(domain, np.stack([np.asarray(p, dtype=np.uint64).reshape(-1, 4) for p in g]),
-                                          buf, col)
-                ptrs.append([buf.ptr + (col + i) * ext_len * 32 for i in range(len(g))])
+                ptrs.append([cos.ptr + (col + i) * n * 32 for i in range(len(g))])
                 col += len(g)
-            lag = []
-            for v in (l0, l_last, l_active_row):
-                buf.upload(np.asarray(v, dtype=np.uint64).reshape(ext_len, 4), col * ext_len)
-                lag.append(buf.ptr + col * ext_len * 32)
-                col += 1
-            zeta_v = domain._zeta if zeta is None else zeta
-            R = _fr.R_MOD
-            challenges = [beta % R, gamma % R, theta % R, y % R]
-            d = beta * zeta_v % R                                     # delta_start, evaluation.rs:1011
-            for _ in self.permutation_columns:
-                challenges.append(d)
-                d = d * DELTA % R
-            scale = domain.t_evaluations if to_coeff else None
-            prog.eval(domain.extended_k, 1 << (domain.extended_k - domain.k), ptrs[0], ptrs[1], ptrs[2],
-                      lag + ptrs[3], challenges, out.ptr, x0=1, x_step=domain._ext_omega, scale=scale)
-            if not to_coeff:
-                return out.download()
-            return extended_to_coeff_dev(domain, out)
+            lag = [cos.ptr + (n_polys + i) * n * 32 for i in range(3)]
+            for c in which:
+                g_c = zeta_v * pow(domain._ext_omega, c, R) % R
+                if n_polys:
+                    coeff_to_coset_dev(domain, coef.ptr, n_polys, g_c, cos.ptr)
+                for i, v in enumerate(lag_host):
+                    cos.upload(np.ascontiguousarray(v[c::n_cosets]), (n_polys + i) * n)
+                scale = domain.t_evaluations[c:c + 1] if to_coeff else None
+                prog.eval(domain.k, 1, ptrs[0], ptrs[1], ptrs[2], lag + ptrs[3], challenges, out.ptr,
+                          x0=pow(domain._ext_omega, c, R), x_step=domain._omega, scale=scale,
+                          out_stride=n_cosets, out_offset=c)
+            return extended_to_coeff_dev(domain, out) if to_coeff else out.download()
         finally:
-            buf.free()
+            coef.free()
+            cos.free()
             out.free()
+
+
+def coeff_to_coset_dev(domain, d_coeffs: int, columns: int, gen: int, d_out: int) -> None:
+    """Evaluations of `columns` device-resident polynomials (2^k coefficients each) on the coset gen * <omega>:
+    one size-2^k transform per column with x[i] *= gen^i fused into its first pass (b2_ntt_desc.coset_gen)."""
+    g = _fr.to_mont(gen)
+    d = NttDesc()
+    d.log_n, d.location = domain.k, 1
+    d.omega = domain.omega.ctypes.data
+    d.coset_gen = g.ctypes.data
+    d.n_in = d.in_stride = d.n_out = d.out_stride = domain.n
+    d.columns = columns
+    d.in_, d.out = d_coeffs, d_out
+    check(lib().b2_ntt_exec(ctypes.byref(d)))
 
 
 def extended_to_coeff_dev(domain, ext: DeviceBuffer) -> np.ndarray:

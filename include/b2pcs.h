@@ -120,6 +120,10 @@ typedef struct b2_ntt_desc {
     void* out;             /* may equal `in` */
     uint64_t out_stride;
     void* stream;          /* location 1 only: cudaStream_t (call is asynchronous on it) or NULL */
+    const void* coset_gen; /* NULL, or 32 B g: x[i] *= g^i before the transform, i.e. the outputs are the evaluations
+                            * of the input polynomial on the coset g * <omega>.  With g = zeta * extended_omega^c and
+                            * omega of order 2^k this is the c-th of the 2^(extended_k - k) interleaved cosets that make
+                            * up coeff_to_extended's output (row 2^(extended_k-k) * i + c), computed without zero padding */
 } b2_ntt_desc;
 /* General entry point; the functions below are thin wrappers over it. */
 int b2_ntt_exec(const b2_ntt_desc* desc);

@@ -22,23 +22,58 @@ def enc(v):
     return o.fr_encode(v)
 
 
-def run_gpu(fx, Ev, dom, to_coeff=False):
+def run_gpu(fx, Ev, dom, to_coeff=False, **kw):
     c = fx["coeff"]
     l0, l_last, l_active = P.lagrange_basis_cosets(fx["cs"], fx["domain"])
     lookups = [{"z": [enc(z) for z in zs], "m": enc(m)} for zs, m in zip(c["lookup_z"], c["lookup_m"])]
     return Ev.evaluate_h(dom, [enc(p) for p in c["fixed"]], [enc(p) for p in c["advice"]],
                          [enc(p) for p in c["instance"]], enc(l0), enc(l_last), enc(l_active),
                          [enc(p) for p in c["sigma"]], fx["y"], fx["beta"], fx["gamma"], fx["theta"], lookups,
-                         [enc(p) for p in c["shuffle_z"]], [enc(p) for p in c["perm_z"]], to_coeff=to_coeff)
+                         [enc(p) for p in c["shuffle_z"]], [enc(p) for p in c["perm_z"]], to_coeff=to_coeff, **kw)
 
 
+@pytest.mark.parametrize("mode", ["extended", "cosets"])
 @pytest.mark.parametrize("k,j", [(5, None), (5, 9), (6, None)])
-def test_evaluate_h_matches_oracle(gpu, k, j):
+def test_evaluate_h_matches_oracle(gpu, k, j, mode):
     fx = fxm.build(k=k, seed=3 + k, domain_j=j)
     dom = h2.EvaluationDomain(j or fx["cs"].degree(), k)
-    got = run_gpu(fx, make_evaluator(fx), dom)
+    got = run_gpu(fx, make_evaluator(fx), dom, mode=mode)
     want = fxm.oracle_h(fx)
     assert np.array_equal(got, enc(want))
+
+
+def test_coset_subset_leaves_other_rows(gpu):
+    """the multi-GPU split: a rank evaluates only its cosets; together they tile the extended domain"""
+    fx = fxm.build(k=5, seed=31)
+    dom = h2.EvaluationDomain(fx["cs"].degree(), 5)
+    want = enc(fxm.oracle_h(fx))
+    Ev = make_evaluator(fx)
+    nc = 1 << (dom.extended_k - dom.k)
+    merged = np.zeros_like(want)
+    for rank in range(2):
+        mine = list(range(rank, nc, 2))
+        part = run_gpu(fx, Ev, dom, cosets=mine)
+        for c in mine:
+            merged[c::nc] = part[c::nc]
+    assert np.array_equal(merged, want)
+
+
+def test_coset_transform_matches_extended(gpu):
+    """b2_ntt_desc.coset_gen: coset c of coeff_to_extended's output without zero padding"""
+    from oracle import cref
+    k = 10
+    dom = h2.EvaluationDomain(5, k)
+    a = cref.random_fr_mont(3 << k, 0xB2000055).reshape(3, 1 << k, 4)
+    ext = dom.coeff_to_extended(a)
+    nc = 1 << (dom.extended_k - k)
+    src = E.DeviceBuffer(3 << k).upload(a)
+    dst = E.DeviceBuffer(3 << k)
+    for c in range(nc):
+        g = dom._zeta * pow(dom._ext_omega, c, R) % R
+        E.coeff_to_coset_dev(dom, src.ptr, 3, g, dst.ptr)
+        got = dst.download().reshape(3, 1 << k, 4)
+        assert np.array_equal(got, ext[:, c::nc])
+    src.free(); dst.free()
 
 
 def test_h_coefficients_match_oracle(gpu):
@@ -46,9 +81,10 @@ def test_h_coefficients_match_oracle(gpu):
     fx = fxm.build(k=5, seed=21)
     d = fx["domain"]
     dom = h2.EvaluationDomain(fx["cs"].degree(), 5)
-    got = run_gpu(fx, make_evaluator(fx), dom, to_coeff=True)
-    want = d.extended_to_coeff(d.divide_by_vanishing_poly(fxm.oracle_h(fx)))
-    assert np.array_equal(got, enc(want))
+    want = enc(d.extended_to_coeff(d.divide_by_vanishing_poly(fxm.oracle_h(fx))))
+    for mode in ("extended", "cosets"):
+        got = run_gpu(fx, make_evaluator(fx), dom, to_coeff=True, mode=mode)
+        assert np.array_equal(got, want), mode
 
 
 def test_spilled_slots_match(gpu, monkeypatch):
