@@ -18,6 +18,9 @@ all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GP
           inside this run; peak = this run's own carry-chained IMAD.WIDE probe
   ntt     N == 1 only: 64 columns of a k=22 forward NTT, device resident: Melem/s, HBM GB/s vs
           the measured copy peak, and the same integer roofline
+  quotient  N == 1 only: evaluate_h + h(X) of a synthetic zkWasm-scale constraint system at k = logn from
+          HBM-resident coefficient forms (coset mode), wall seconds, kernel times and the fused kernel's
+          integer roofline; its own cpu_baseline (C restatement of the reference's row loop)
   cpu_baseline / --impl reference: the C restatement of the reference's rayon path
           (oracle/cpu_ref.c = arithmetic.rs:20-108, 465-492) on the box's host cores
 
@@ -307,6 +310,9 @@ def run_engine(args):
     ntt = None
     if world == 1 and not args.no_ntt:
         ntt = bench_ntt(args, torch, dev, _lib, h2, float(muls.value))
+    quotient = None
+    if world == 1 and not args.no_quotient:
+        quotient = bench_quotient(args, _lib, h2, float(muls.value))
 
     if rank == 0:
         hbm_peak, peak_src = _peaks()
@@ -355,6 +361,8 @@ def run_engine(args):
         }
         if ntt:
             line["ntt"] = ntt
+        if quotient:
+            line["quotient"] = quotient
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -429,6 +437,92 @@ def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
     }
 
 
+def bench_quotient(args, _lib, h2, modmuls_per_s):
+    """evaluate_h + h(X) for a synthetic zkWasm-scale constraint system at k = logn (the
+    "k = 22 create_proof" phase that follows the commitments): coefficient forms resident in HBM, the extended
+    domain walked coset by coset (one batched size-2^k transform of all polynomials + ONE fused kernel per coset),
+    then divide_by_vanishing_poly (folded into the kernel's store) and extended_to_coeff back to the host."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import quotient_bench as qb
+    from halo2_gpu_specific_b200 import _fr
+    from halo2_gpu_specific_b200 import evaluation as E
+    k = args.logn
+    n = 1 << k
+    ev, lookups, shuffles, n_sets = qb.synthetic_evaluator()
+    prog = ev.program(n_sets, lookups, shuffles)
+    info = prog.info()
+    ncols = prog.n_fixed + prog.n_advice + prog.n_instance + prog.n_aux
+    dom = h2.EvaluationDomain(5, k)
+    nc = 1 << (dom.extended_k - k)
+    R = _fr.R_MOD
+    base = np.empty((4, n, 4), dtype=np.uint64)
+    random_montgomery_scalars(4 * n, 11, pinned=base.reshape(-1, 4))
+    coef = E.DeviceBuffer(ncols * n)
+    for c in range(ncols):
+        coef.upload(base[c % 4], c * n)
+    cos = E.DeviceBuffer(ncols * n)
+    out = E.DeviceBuffer(dom.extended_len())
+    ptrs = [cos.ptr + c * n * 32 for c in range(ncols)]
+    nf, na, ni = prog.n_fixed, prog.n_advice, prog.n_instance
+    challenges = [(i + 2) * 0x123456789ABCDEF % R for i in range(prog.n_challenges)]
+    L = _lib.lib()
+    runs = []
+    for rep in range(3):
+        L.b2_synchronize()
+        L.b2_launch_count(1)
+        t0 = time.perf_counter()
+        ntt_ms = eval_ms = 0.0
+        for c in range(nc):
+            g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
+            E.coeff_to_coset_dev(dom, coef.ptr, ncols, g_c, cos.ptr)
+            ntt_ms += _lib.last_timing()[0]
+            prog.eval(k, 1, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+                      out.ptr, x0=pow(dom._ext_omega, c, R), x_step=dom._omega, scale=dom.t_evaluations[c:c + 1],
+                      out_stride=nc, out_offset=c)
+            eval_ms += _lib.last_timing()[0]
+        h = E.extended_to_coeff_dev(dom, out)
+        runs.append((time.perf_counter() - t0, ntt_ms, eval_ms, int(L.b2_launch_count(0))))
+    wall, ntt_ms, eval_ms, launches = min(runs[1:])
+    coef.free(); cos.free(); out.free()
+    rows = n * nc
+    muls = info["n_mul"] + 2                       # + the coset point and the vanishing scale
+    res = {
+        "metric": f"evaluate_h + h(X) coefficients at k={k} (extended_k={dom.extended_k}), synthetic zkWasm-scale "
+                  f"constraint system: {ncols} polynomials, {info['n_instr']} field instructions per row",
+        "value": wall, "unit": "s", "higher_is_better": False, "rows": rows, "gpu_launches": launches,
+        "ntt_kernel_ms": ntt_ms, "eval_kernel_ms": eval_ms, "d2h_bytes": int(h.nbytes),
+        "resident_GiB": (2 * ncols * n + rows) * 32 / 2**30, "program": info,
+        "eval_rows_per_s": rows / (eval_ms * 1e-3),
+        "roofline_int": {"kernel": "quotient_eval_kernel", "bound": "int", "unit": "TMAC/s",
+                         "achieved": muls * 128.0 * rows / (eval_ms * 1e-3) / 1e12, "peak": modmuls_per_s * 128 / 1e12,
+                         "frac": muls * rows / (eval_ms * 1e-3) / modmuls_per_s,
+                         "model": f"{muls} field multiplications per row x 128 MACs (SURVEY 8d accounting); "
+                                  f"additions and operand decode are not counted"},
+    }
+    if not args.no_cpu:
+        # CPU: the C restatement of the reference's row loop (Calculation::evaluate, plonk/evaluation.rs:846-1001) on a
+        # bounded sample of rows of the SAME program, all host cores
+        from oracle import cref
+        f = ev.flat_h_program(n_sets, lookups, shuffles)
+        cores = os.cpu_count() or 1
+        lr = 12
+        crow = 1 << lr
+        cols_h = [np.ascontiguousarray(base[c % 4][:crow]) for c in range(ncols)]
+        enc = lambda v: np.stack([_fr.to_mont(x) for x in v])  # noqa: E731
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 2 or (time.perf_counter() - t0 < 5.0 and reps < 50):
+            cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"], cols_h[:nf],
+                               cols_h[nf:nf + na], cols_h[nf + na:nf + na + ni], cols_h[nf + na + ni:], enc(challenges),
+                               lr, 1, x0=_fr.to_mont(1), step=dom.omega, threads=cores)
+            reps += 1
+        dt = (time.perf_counter() - t0) / reps
+        res["cpu_baseline"] = {"value": crow / dt, "unit": "rows/s", "cores": cores, "kind": "port",
+                               "sample": f"2^{lr} rows of the same program per repetition, {reps} repetitions "
+                                         f"(oracle/cpu_ref.c ref_quotient_eval; expression kernel only, no transforms)"}
+    return res
+
+
 def cpu_baseline(args):
     """Bounded sample of the same workload on the host cores (C restatement of the rayon path)."""
     from oracle import cref
@@ -468,6 +562,7 @@ def main():
     ap.add_argument("--ntt-cols", type=int, default=64)
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-quotient", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="plain bases: one bucket set per window + Horner")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

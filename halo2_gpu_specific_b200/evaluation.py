@@ -238,6 +238,11 @@ class Evaluator:
 
     # ---- program construction -----------------------------------------------------------
     def build_h_program(self, n_perm_sets: int, lookup_set_counts: Sequence[int], n_shuffles: int):
+        f = self.flat_h_program(n_perm_sets, lookup_set_counts, n_shuffles)
+        return QuotientProgram(f["rotations"], f["constants"], f["calcs"], f["result"], self.num_fixed, self.num_advice,
+                               self.num_instance, f["n_aux"], f["n_challenges"])
+
+    def flat_h_program(self, n_perm_sets: int, lookup_set_counts: Sequence[int], n_shuffles: int) -> dict:
         """Flat Calculation list for the whole of evaluate_h.  Aux columns, in order:
         l0, l_last, l_active_row, sigma cosets (one per permutation column), permutation z cosets (one per
         set), then per lookup its z cosets and its m coset, then the shuffle product cosets.
@@ -348,9 +353,8 @@ class Evaluator:
             fold(emit(("Mul", t, l_active)))
 
         result = acc[0] if acc[0] is not None else const(0)
-        n_challenges = CH_FIRST_DELTA + n_sigma
-        return QuotientProgram(rotations, constants, calcs, result, self.num_fixed, self.num_advice,
-                               self.num_instance, aux_next, n_challenges)
+        return {"rotations": rotations, "constants": constants, "calcs": calcs, "result": result, "n_aux": aux_next,
+                "n_challenges": CH_FIRST_DELTA + n_sigma}
 
     def program(self, n_perm_sets: int, lookup_set_counts: Sequence[int], n_shuffles: int) -> QuotientProgram:
         key = (n_perm_sets, tuple(lookup_set_counts), n_shuffles)

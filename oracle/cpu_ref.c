@@ -565,4 +565,128 @@ int ref_jac_sum(const u64 *in_jac, size_t n, u64 *out_jac) {
     memcpy(out_jac, &acc, sizeof acc);
     return 0;
 }
+/* ------------------------------------------------------------------------------------------------
+ * evaluate_h row loop: Calculation::evaluate / ValueSource::get over all rows
+ * (plonk/evaluation.rs:60-268 and the "expressions" loop :846-1001): for every row, every Calculation
+ * in order into `intermediates`, then the designated result.  Rows are split into one contiguous
+ * chunk per thread (:849-851).  The calculation records have the layout of b2_qcalc (include/b2pcs.h),
+ * i.e. the reference's enums flattened: kinds 0 Constant, 1 Intermediate, 2 Fixed, 3 Advice, 4 Instance,
+ * 5 Aux (z / sigma / l0 ... cosets, which the reference reads in its hand-written permutation / lookup /
+ * shuffle loops, :1005-1220), 6 Challenge, 7 coset point x0 * step^row (beta_term, :1018-1019);
+ * ops 0 Add, 1 Sub, 2 Mul, 3 Negate, 4 LcChallenge, 5 a * ch + b (LcTheta / the y fold), 6 AddChallenge, 7 Store. */
+typedef struct { uint32_t kind, index, rot; } qsrc_t;
+typedef struct { uint32_t op; qsrc_t a, b; uint32_t challenge, power; } qcalc_t;
+typedef struct {
+    const int32_t *rotations; uint32_t n_rot;
+    const fe *constants;
+    const qcalc_t *calcs; uint32_t n_calcs;
+    qsrc_t result;
+    const fe *const *cols[4];          /* fixed, advice, instance, aux */
+    const fe *challenges;
+    fe x0, step;
+    uint32_t log_rows, rot_scale;
+    fe *out;
+    size_t lo, hi;
+} qjob;
+
+static inline void q_get(const qjob *j, const qsrc_t *s, const size_t *rot_idx, const fe *inter, const fe *x, fe *r) {
+    switch (s->kind) {
+    case 0: *r = j->constants[s->index]; break;
+    case 1: *r = inter[s->index]; break;
+    case 2: case 3: case 4: case 5: *r = j->cols[s->kind - 2][s->index][rot_idx[s->rot]]; break;
+    case 6: *r = j->challenges[s->index]; break;
+    default: *r = *x; break;
+    }
+}
+
+static void *q_worker(void *arg) {
+    qjob *j = (qjob *)arg;
+    const size_t size = (size_t)1 << j->log_rows;
+    fe *inter = (fe *)malloc(sizeof(fe) * (j->n_calcs ? j->n_calcs : 1));
+    fe *chp = (fe *)malloc(sizeof(fe) * (j->n_calcs ? j->n_calcs : 1));   /* challenge powers of the LcChallenge calcs */
+    for (uint32_t c = 0; c < j->n_calcs; c++) {
+        if (j->calcs[c].op != 4) continue;
+        chp[c] = j->challenges[j->calcs[c].challenge];
+        if (j->calcs[c].power > 1) {
+            u64 e[4] = {j->calcs[c].power, 0, 0, 0};
+            fe_pow(&FR, &chp[c], &j->challenges[j->calcs[c].challenge], e);
+        }
+    }
+    size_t *rot_idx = (size_t *)malloc(sizeof(size_t) * (j->n_rot ? j->n_rot : 1));
+    fe x;
+    {   /* x0 * step^lo */
+        u64 e[4] = {j->lo, 0, 0, 0};
+        fe p;
+        fe_pow(&FR, &p, &j->step, e);
+        fe_mul(&FR, &x, &j->x0, &p);
+    }
+    for (size_t idx = j->lo; idx < j->hi; idx++) {
+        for (uint32_t r = 0; r < j->n_rot; r++) {   /* get_rotation_idx, :40-42 */
+            long long v = ((long long)idx + (long long)j->rotations[r] * (long long)j->rot_scale) % (long long)size;
+            if (v < 0) v += (long long)size;
+            rot_idx[r] = (size_t)v;
+        }
+        for (uint32_t c = 0; c < j->n_calcs; c++) {
+            const qcalc_t *q = &j->calcs[c];
+            fe a, b, t;
+            q_get(j, &q->a, rot_idx, inter, &x, &a);
+            switch (q->op) {
+            case 0: q_get(j, &q->b, rot_idx, inter, &x, &b); fe_add(&FR, &inter[c], &a, &b); break;
+            case 1: q_get(j, &q->b, rot_idx, inter, &x, &b); fe_sub(&FR, &inter[c], &a, &b); break;
+            case 2: q_get(j, &q->b, rot_idx, inter, &x, &b); fe_mul(&FR, &inter[c], &a, &b); break;
+            case 3: fe_neg(&FR, &inter[c], &a); break;
+            case 4: {   /* (a + ch^p) * b, ch^1 when p <= 1 (:205-211) */
+                q_get(j, &q->b, rot_idx, inter, &x, &b);
+                fe_add(&FR, &t, &a, &chp[c]);
+                fe_mul(&FR, &inter[c], &t, &b);
+                break;
+            }
+            case 5: q_get(j, &q->b, rot_idx, inter, &x, &b); fe_mul(&FR, &t, &a, &j->challenges[q->challenge]);
+                    fe_add(&FR, &inter[c], &t, &b); break;
+            case 6: fe_add(&FR, &inter[c], &a, &j->challenges[q->challenge]); break;
+            default: inter[c] = a; break;
+            }
+        }
+        q_get(j, &j->result, rot_idx, inter, &x, &j->out[idx]);
+        fe_mul(&FR, &x, &x, &j->step);
+    }
+    free(inter);
+    free(chp);
+    free(rot_idx);
+    return NULL;
+}
+
+int ref_quotient_eval(const int32_t *rotations, uint32_t n_rot, const u64 *constants, const void *calcs, uint32_t n_calcs,
+                      const uint32_t result[3], const u64 *const *fixed, const u64 *const *advice,
+                      const u64 *const *instance, const u64 *const *aux, const u64 *challenges, const u64 *x0,
+                      const u64 *step, uint32_t log_rows, uint32_t rot_scale, u64 *out, int T) {
+    const size_t size = (size_t)1 << log_rows;
+    if (T < 1) T = 1;
+    if ((size_t)T > size) T = (int)size;
+    qjob *jobs = (qjob *)calloc((size_t)T, sizeof(qjob));
+    pthread_t *th = (pthread_t *)calloc((size_t)T, sizeof(pthread_t));
+    const size_t chunk = (size + (size_t)T - 1) / (size_t)T;
+    for (int t = 0; t < T; t++) {
+        qjob *j = &jobs[t];
+        j->rotations = rotations; j->n_rot = n_rot;
+        j->constants = (const fe *)constants;
+        j->calcs = (const qcalc_t *)calcs; j->n_calcs = n_calcs;
+        j->result.kind = result[0]; j->result.index = result[1]; j->result.rot = result[2];
+        j->cols[0] = (const fe *const *)fixed; j->cols[1] = (const fe *const *)advice;
+        j->cols[2] = (const fe *const *)instance; j->cols[3] = (const fe *const *)aux;
+        j->challenges = (const fe *)challenges;
+        if (x0) memcpy(&j->x0, x0, 32); else j->x0 = FR.one;
+        if (step) memcpy(&j->step, step, 32); else j->step = FR.one;
+        j->log_rows = log_rows; j->rot_scale = rot_scale;
+        j->out = (fe *)out;
+        j->lo = (size_t)t * chunk; j->hi = j->lo + chunk > size ? size : j->lo + chunk;
+        if (j->lo > size) j->lo = size;
+        pthread_create(&th[t], NULL, q_worker, j);
+    }
+    for (int t = 0; t < T; t++) pthread_join(th[t], NULL);
+    free(jobs);
+    free(th);
+    return 0;
+}
+
 int ref_version(void) { return 1; }

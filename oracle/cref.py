@@ -177,3 +177,65 @@ def random_fr_small_mont(n: int, seed: int, bits: int) -> np.ndarray:
     raw = np.zeros((n, 4), dtype=np.uint64)
     raw[:, 0] = z >> np.uint64(64 - bits) if bits < 64 else z
     return to_mont(0, raw)
+
+
+# ---- evaluate_h row loop (plonk/evaluation.rs:846-1001 generalised to one flat Calculation list) ----
+_QKIND = {"Constant": 0, "Intermediate": 1, "Fixed": 2, "Advice": 3, "Instance": 4, "Aux": 5, "Challenge": 6, "CosetX": 7}
+_QCH = {"Beta": 0, "Gamma": 1, "Theta": 2, "Y": 3}
+
+
+def _qsrc(s):
+    return (_QKIND[s[0]], s[1] if len(s) > 1 else 0, s[2] if len(s) > 2 else 0)
+
+
+def _qcalc_words(c):
+    """(op, a.kind, a.index, a.rot, b.kind, b.index, b.rot, challenge, power): the layout of b2_qcalc"""
+    t, z = c[0], (0, 0, 0)
+    if t in ("Add", "Sub", "Mul"):
+        return ({"Add": 0, "Sub": 1, "Mul": 2}[t],) + _qsrc(c[1]) + _qsrc(c[2]) + (0, 0)
+    if t == "Negate":
+        return (3,) + _qsrc(c[1]) + z + (0, 0)
+    if t == "LcChallenge":
+        return (4,) + _qsrc(c[1]) + _qsrc(c[2]) + (_QCH[c[3]], c[4])
+    if t == "LcTheta":
+        return (5,) + _qsrc(c[1]) + _qsrc(c[2]) + (2, 0)
+    if t == "MulChAdd":
+        return (5,) + _qsrc(c[1]) + _qsrc(c[2]) + (c[3], 0)
+    if t == "AddChallenge":
+        return (6,) + _qsrc(c[1]) + z + (_QCH[c[2]], 0)
+    if t == "Store":
+        return (7,) + _qsrc(c[1]) + z + (0, 0)
+    raise ValueError(c)
+
+
+def quotient_eval(rotations, constants, calcs, result, fixed, advice, instance, aux, challenges, log_rows: int,
+                  rot_scale: int, x0=None, step=None, threads: int = 8) -> np.ndarray:
+    """Every Calculation for every row, then `result` (reference enums as tuples, see oracle/plonk.py).
+    constants / challenges / x0 / step: Montgomery (.., 4) arrays; columns: lists of (rows, 4) arrays."""
+    rows = 1 << log_rows
+    rot = np.asarray(list(rotations), dtype=np.int32)
+    cst = _c(constants, 4) if len(constants) else np.zeros((1, 4), np.uint64)
+    words = np.asarray([_qcalc_words(c) for c in calcs], dtype=np.uint32).reshape(-1, 9) if len(calcs) \
+        else np.zeros((1, 9), np.uint32)
+    res = np.asarray(_qsrc(result), dtype=np.uint32)
+    keep = []
+
+    def table(cols):
+        arrs = [_c(a, 4) for a in cols]
+        for a in arrs:
+            assert a.shape[0] == rows
+        keep.append(arrs)
+        t = (ctypes.c_void_p * max(1, len(arrs)))(*[a.ctypes.data for a in arrs])
+        keep.append(t)
+        return t
+
+    ch = _c(challenges, 4) if len(challenges) else np.zeros((1, 4), np.uint64)
+    out = np.zeros((rows, 4), dtype=np.uint64)
+    x0a = _c(x0).reshape(4) if x0 is not None else None
+    sta = _c(step).reshape(4) if step is not None else None
+    rc = lib().ref_quotient_eval(_p(rot), ctypes.c_uint32(len(rot)), _p(cst), _p(words), ctypes.c_uint32(len(calcs)),
+                                 _p(res), table(fixed), table(advice), table(instance), table(aux), _p(ch),
+                                 _p(x0a) if x0a is not None else None, _p(sta) if sta is not None else None,
+                                 ctypes.c_uint32(log_rows), ctypes.c_uint32(rot_scale), _p(out), int(threads))
+    assert rc == 0
+    return out

@@ -173,3 +173,43 @@ def test_large_random_program_spot_rows(gpu):
             slots[dst] = r
         assert o.fr_decode(got[row][None])[0] == fetch(result), f"row {row}"
     prog.free()
+
+
+def test_zkwasm_shape_program_full_compare(gpu):
+    """the benchmark's synthetic zkWasm-scale program (tools/quotient_bench.py: 1200+ instructions, 156 columns)
+    at 2^13 rows with rot_scale 4: every row against the C restatement of Calculation::evaluate."""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import quotient_bench as qb
+    from oracle import cref
+    ev, lookups, shuffles, n_sets = qb.synthetic_evaluator(gates=40)
+    f = ev.flat_h_program(n_sets, lookups, shuffles)
+    prog = ev.program(n_sets, lookups, shuffles)
+    log_rows = 13
+    rows = 1 << log_rows
+    ncols = prog.n_fixed + prog.n_advice + prog.n_instance + prog.n_aux
+    cols = cref.random_fr_mont(rows * ncols, 0xB2000088).reshape(ncols, rows, 4)
+    rng = random.Random(5)
+    challenges = [rng.randrange(R) for _ in range(prog.n_challenges)]
+    x0, step = rng.randrange(R), rng.randrange(R)
+    scale = cref.random_fr_mont(4, 0xB2000089)
+    buf = E.DeviceBuffer(rows * ncols).upload(cols)
+    out = E.DeviceBuffer(rows)
+    ptrs = [buf.ptr + c * rows * 32 for c in range(ncols)]
+    nf, na, ni = prog.n_fixed, prog.n_advice, prog.n_instance
+    prog.eval(log_rows, 4, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+              out.ptr, x0=x0, x_step=step)
+    got = out.download()
+    want = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"], list(cols[:nf]),
+                              list(cols[nf:nf + na]), list(cols[nf + na:nf + na + ni]), list(cols[nf + na + ni:]),
+                              enc(challenges), log_rows, 4, x0=enc([x0])[0], step=enc([step])[0], threads=4)
+    assert np.array_equal(got, want)
+    # the same with the vanishing scale folded into the store
+    prog.eval(log_rows, 4, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+              out.ptr, x0=x0, x_step=step, scale=scale)
+    got = out.download()
+    sc = o.fr_decode(scale)
+    wd = o.fr_decode(want[:64])
+    gd = o.fr_decode(got[:64])
+    assert gd == [w * sc[i % 4] % R for i, w in enumerate(wd)]
+    buf.free(); out.free()

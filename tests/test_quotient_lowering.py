@@ -154,3 +154,32 @@ def test_lc_challenge_powers_are_derived():
         t = (t + 8) * v % R
         want.append((t + 3) * v % R)
     assert got == want
+
+
+def test_c_restatement_matches_python_oracle(fx):
+    """oracle/cpu_ref.c ref_quotient_eval (Calculation::evaluate over all rows) on the flat evaluate_h program
+    == oracle/plonk.py evaluate_h: two restatements of plonk/evaluation.rs agree."""
+    import numpy as np
+    from oracle import cref
+    Ev = make_evaluator(fx)
+    cz = fxm.cosets(fx)
+    want = fxm.oracle_h(fx, cz)
+    f = Ev.flat_h_program(len(fx["perm_z"]), [len(l["z"]) for l in fx["lookups_lagrange"]], len(fx["shuffle_z"]))
+    d = fx["domain"]
+    enc = o.fr_encode
+    aux = [cz["l0"], cz["l_last"], cz["l_active_row"]] + cz["sigma"] + cz["perm_z"]
+    for lk in cz["lookups"]:
+        aux += lk["z_cosets"] + [lk["m_coset"]]
+    aux += cz["shuffles"]
+    assert len(aux) == f["n_aux"]
+    challenges = [fx["beta"], fx["gamma"], fx["theta"], fx["y"]]
+    dlt = fx["beta"] * d.g_coset % R
+    for _ in fx["cs"].permutation_columns:
+        challenges.append(dlt)
+        dlt = dlt * P.FR_DELTA % R
+    got = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"],
+                             [enc(c) for c in cz["fixed"]], [enc(c) for c in cz["advice"]],
+                             [enc(c) for c in cz["instance"]], [enc(c) for c in aux], enc(challenges),
+                             d.extended_k, 1 << (d.extended_k - d.k), x0=enc([1])[0], step=enc([d.extended_omega])[0],
+                             threads=3)
+    assert np.array_equal(got, enc(want))
