@@ -46,7 +46,7 @@ SYMBOLS = [
     "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
-    "b2_commit_batch", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
+    "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
     "b2_batch_invert", "b2_batch_invert_dev", "b2_prefix_scan", "b2_prefix_scan_dev", "b2_fr_vec_dev",
@@ -86,6 +86,7 @@ def lib() -> ctypes.CDLL:
         L.b2_divide_by_vanishing_poly.argtypes = [vp, u32, vp, u32]
         L.b2_msm_and_ifft.argtypes = [u64, vp, u32, vp, vp, u32, vp]
         L.b2_commit_batch.argtypes = [u64, vp, u64, sz, u32, ctypes.c_int, vp, vp, u32, vp]
+        L.b2_commit_batch_resident.argtypes = [u64, vp, ctypes.c_int, vp, u64, sz, u32, ctypes.c_int, vp, vp, u32, vp]
         L.b2_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
         L.b2_host_free.argtypes = [vp]
         L.b2_host_register.argtypes = [vp, sz]

@@ -1342,8 +1342,9 @@ int b2_divide_by_vanishing_poly(void* a, uint32_t ext_k, const void* t_evaluatio
 }
 
 // ---- fused commit + iNTT
-int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits, int do_ifft,
-                    const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96) {
+static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits, int do_ifft,
+                             const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96, void* d_keep,
+                             int columns_on_device) {
     if (!columns_data || !out_jac96 || n == 0) return fail(B2_ERR_ARG, "commit_batch: bad arguments");
     if (do_ifft && (!omega_inv || !divisor || n != ((size_t)1 << log_n)))
         return fail(B2_ERR_ARG, "commit_batch: ifft needs n == 2^log_n, omega_inv and divisor");
@@ -1369,22 +1370,31 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
         Lane* ln = set.lanes[c % nl];
         cudaStream_t st = ln->stream;
         char* h = (char*)columns_data + c * col_bytes;
-        if ((rc = ln->ntt_in.reserve(col_bytes))) return rc;
+        // where the column lives on the device: a lane staging buffer, or the caller's resident buffer
+        char* dcol;
+        if (columns_on_device) {
+            dcol = h;
+        } else if (d_keep) {
+            dcol = (char*)d_keep + c * col_bytes;
+        } else {
+            if ((rc = ln->ntt_in.reserve(col_bytes))) return rc;
+            dcol = ln->ntt_in.as<char>();
+        }
         if ((rc = ln->out96.reserve(96))) return rc;
         if (do_ifft && pl->npass > 1 && (rc = ln->ntt_work.reserve(col_bytes))) return rc;
-        CK(cudaMemcpyAsync(ln->ntt_in.p, h, col_bytes, cudaMemcpyHostToDevice, st));
+        if (!columns_on_device) CK(cudaMemcpyAsync(dcol, h, col_bytes, cudaMemcpyHostToDevice, st));
         if (max_bits == 0) {
             if ((rc = write_identity(*ln, ln->out96.p, st))) return rc;
         } else {
             // the bound flag is sticky per lane for the whole batch (reset once, read once)
-            if ((rc = msm_run_split(*ln, s, 0, ln->ntt_in.as<char>(), n, max_bits, ln->out96.p, st, false, c < nl)))
+            if ((rc = msm_run_split(*ln, s, 0, dcol, n, max_bits, ln->out96.p, st, false, c < nl)))
                 return rc;
         }
         CK(cudaMemcpyAsync((char*)out_jac96 + c * 96, ln->out96.p, 96, cudaMemcpyDeviceToHost, st));
         if (do_ifft) {
-            if ((rc = ntt_run_dev(*ln, pl, ln->ntt_in.p, n, n, ln->ntt_in.p, n, n, ln->ntt_work.p, 1, nullptr, nullptr, st)))
+            if ((rc = ntt_run_dev(*ln, pl, dcol, n, n, dcol, n, n, ln->ntt_work.p, 1, nullptr, nullptr, st)))
                 return rc;
-            CK(cudaMemcpyAsync(h, ln->ntt_in.p, col_bytes, cudaMemcpyDeviceToHost, st));
+            if (!d_keep && !columns_on_device) CK(cudaMemcpyAsync(h, dcol, col_bytes, cudaMemcpyDeviceToHost, st));
         }
     }
     int bound_flag_any = 0;
@@ -1408,6 +1418,24 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
     for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
     return B2_OK;
+}
+
+int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits, int do_ifft,
+                    const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96) {
+    return commit_batch_impl(srs, columns_data, columns, n, max_bits, do_ifft, omega_inv, divisor, log_n, out_jac96, nullptr, 0);
+}
+
+int b2_commit_batch_resident(b2_handle_t srs, const void* columns_data, int columns_on_device, void* d_columns,
+                             uint64_t columns, size_t n, uint32_t max_bits, int do_ifft, const void* omega_inv,
+                             const void* divisor, uint32_t log_n, void* out_jac96) {
+    if (columns_on_device) {
+        if (!d_columns) return fail(B2_ERR_ARG, "commit_batch_resident: d_columns is NULL");
+        return commit_batch_impl(srs, d_columns, columns, n, max_bits, do_ifft, omega_inv, divisor, log_n, out_jac96,
+                                 nullptr, 1);
+    }
+    if (!d_columns) return fail(B2_ERR_ARG, "commit_batch_resident: d_columns is NULL");
+    return commit_batch_impl(srs, const_cast<void*>(columns_data), columns, n, max_bits, do_ifft, omega_inv, divisor, log_n,
+                             out_jac96, d_columns, 0);
 }
 
 int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void* omega_inv, const void* divisor,

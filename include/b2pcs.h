@@ -161,6 +161,15 @@ int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void
 int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_t n, uint32_t max_bits,
                     int do_ifft, const void* omega_inv, const void* divisor, uint32_t log_n, void* out_jac96);
 
+/* Same commitments, but the columns stay (or already are) in HBM: with columns_on_device == 0 each host column is
+ * copied straight into d_columns[c * n] (pipelined over the lanes), committed there and, with do_ifft, transformed
+ * in place there -- nothing is copied back; with columns_on_device != 0 the columns are read from d_columns and
+ * columns_data is ignored.  This is what lets the advice / z columns be uploaded once per proof: their coefficient
+ * forms are then consumed on the device by the coset transforms of evaluate_h (plonk/prover.rs:639-661). */
+int b2_commit_batch_resident(b2_handle_t srs, const void* columns_data, int columns_on_device, void* d_columns,
+                             uint64_t columns, size_t n, uint32_t max_bits, int do_ifft, const void* omega_inv,
+                             const void* divisor, uint32_t log_n, void* out_jac96);
+
 /* ---- quotient evaluation (evaluate_h) ---------------------------------------------- */
 /* Evaluator::evaluate_h (plonk/evaluation.rs:778-1226) computes, for every row of the extended
  * domain, the y-fold of all gate polynomials and of the permutation / lookup / shuffle terms.

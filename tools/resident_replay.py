@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""Device-resident schedule replay of create_proof at zkWasm scale, one B200.
+
+tools/proof_replay.py replays the commitment / NTT calls the way the reference issues them: every call
+copies its column in and its result out, so the schedule is PCIe-bound, and it stops short of evaluate_h.
+This tool replays the SAME schedule (halo2_proofs/src/plonk/prover.rs:206-850) the way the engine is meant
+to be driven once the callers on both sides of the commitment path are on the device too:
+
+  * every witness column crosses PCIe ONCE (pinned host -> its slot in one resident coefficient buffer),
+    is committed there (b2_commit_batch_resident) and inverse-transformed in place;
+  * the z columns are built on the device (expression kernel + batch inversion + prefix scan, 8f rank 3),
+    committed and inverse-transformed there, never visiting the host;
+  * evaluate_h (8f rank 1) walks the extended domain coset by coset from the resident coefficient forms
+    (fixed and sigma polynomials are resident since keygen), h(X) stays on the device and its D pieces are
+    committed from there (b2_msm_dev);
+  * what the CPU side of the reference still needs afterwards (coefficient forms for the multiopen
+    evaluations, the h pieces) is copied back ONCE and reported as its own line.
+
+Phases are serialised as in the prover (the transcript squeezes a challenge between them).  Synthetic data:
+16-bit advice values, uniform field elements elsewhere; the gate program is tools/quotient_bench.py's.
+
+    python tools/resident_replay.py [--k 22] [--reps 2] [--out file.json]
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import halo2_gpu_specific_b200 as h2  # noqa: E402
+from halo2_gpu_specific_b200 import _fr, _lib  # noqa: E402
+from halo2_gpu_specific_b200 import evaluation as E  # noqa: E402
+from halo2_gpu_specific_b200._lib import NttDesc  # noqa: E402
+from halo2_gpu_specific_b200.arithmetic import Srs  # noqa: E402
+import quotient_bench as qb  # noqa: E402
+
+R = _fr.R_MOD
+vp = ctypes.c_void_p
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--k", type=int, default=22)
+    ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--no-fixed-cosets", action="store_true",
+                    help="re-transform the fixed and sigma polynomials in every proof instead of keeping their cosets "
+                         "resident since keygen (pk.fixed_cosets / permutation cosets, plonk/keygen.rs, are what the "
+                         "reference's CPU path keeps too)")
+    a = ap.parse_args()
+    _lib.require_gpu()
+    _lib.set_device(0)
+    L = _lib.lib()
+    k = a.k
+    n = 1 << k
+    dom = h2.EvaluationDomain(5, k)
+    nc = 1 << (dom.extended_k - k)
+    sh = dict(A=64, I=1, F=32, L=8, S=12, H=4, P=8, D=4, R=3, perm_cols=24)
+    lookups = (2, 2, 2, 2, 1, 1, 1, 1)
+    assert sum(lookups) == sh["S"] and len(lookups) == sh["L"]
+
+    t0 = time.time()
+    g = Srs.synthetic(n, 0, 0xB2000003)
+    gl = Srs.synthetic(n, n, 0xB2000003)
+    params = h2.Params(k, g, gl)
+    ev, lk, shf, n_sets = qb.synthetic_evaluator(A=sh["A"], F=sh["F"], I=sh["I"], lookups=lookups, shuffles=sh["H"],
+                                                 perm_cols=sh["perm_cols"])
+    prog = ev.program(n_sets, lk, shf)
+    assert n_sets == sh["P"]
+
+    # ---- one resident coefficient buffer; slot layout (columns of n elements)
+    slots = {}
+    cur = 0
+    for name, cnt in (("fixed", sh["F"]), ("sigma", sh["perm_cols"]), ("advice", sh["A"]), ("instance", sh["I"]),
+                      ("perm_z", sh["P"]), ("lookup_z", sh["S"]), ("shuffle_z", sh["H"]), ("lookup_m", sh["L"])):
+        slots[name] = (cur, cnt)
+        cur += cnt
+    n_polys = cur
+    n_key = sh["F"] + sh["perm_cols"]                  # proving-key polynomials: first in the buffer
+    keep_key_cosets = not a.no_fixed_cosets
+    coef = E.DeviceBuffer(n_polys * n)
+    cos = E.DeviceBuffer((n_polys + 3) * n)
+    key_cos = E.DeviceBuffer(((n_key + 3) * nc if keep_key_cosets else 1) * n)   # per coset: key polys, l0, l_last, l_active
+    sigma_lagrange = E.DeviceBuffer(sh["perm_cols"] * n)       # pkey.permutations (keygen), used by the z construction
+    work = E.DeviceBuffer(max(sh["P"], 1) * n)
+    hext = E.DeviceBuffer(dom.extended_len())
+    hcoef = E.DeviceBuffer(n * dom.quotient_poly_degree)
+    d96 = E.DeviceBuffer(8)
+
+    def slot_ptr(name, i=0):
+        return coef.ptr + (slots[name][0] + i) * n * 32
+
+    rng = np.random.default_rng(3)
+    pool = 6
+    big = _lib.pinned_empty((pool, n, 4))
+    big[:] = rng.integers(0, 2**64, size=(pool, n, 4), dtype=np.uint64)
+    big[:, :, 3] &= np.uint64((1 << 60) - 1)
+    small_tbl = np.stack([_fr.to_mont(v) for v in range(1 << 16)])
+    small = _lib.pinned_empty((pool, n, 4))
+    for i in range(pool):
+        small[i] = small_tbl[rng.integers(0, 1 << 16, size=n)]
+    small[:, ::3] = 0
+    back = _lib.pinned_empty((pool, n, 4))                      # landing zone of the final copy-back
+    lag = [big[i % pool] for i in range(3)]   # (pinned) l0 / l_last / l_active_row values of one coset
+
+    # keygen-time residency (untimed): fixed + sigma coefficient forms, sigma in Lagrange form
+    for i in range(sh["F"]):
+        coef.upload(big[i % pool], slots["fixed"][0] * n + i * n)
+    for i in range(sh["perm_cols"]):
+        coef.upload(big[(i + 1) % pool], slots["sigma"][0] * n + i * n)
+        sigma_lagrange.upload(big[(i + 2) % pool], i * n)
+    if keep_key_cosets:
+        for c in range(nc):
+            g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
+            E.coeff_to_coset_dev(dom, coef.ptr, n_key, g_c, key_cos.ptr + c * (n_key + 3) * n * 32)
+            for i in range(3):
+                key_cos.upload(lag[i], (c * (n_key + 3) + n_key + i) * n)
+    setup_s = time.time() - t0
+
+    def batch_of(src, count):
+        return [src[i % pool: i % pool + 1] for i in range(count)]
+
+    def commit_resident(src, count, name, bits, ifft):
+        """host columns -> resident slots, committed (and inverse-transformed) there"""
+        out = np.zeros((count, 12), dtype=np.uint64)
+        done = 0
+        # the pinned pool holds `pool` distinct columns: consecutive pool entries are contiguous, so send
+        # them in contiguous runs
+        while done < count:
+            run = min(pool - (done % pool), count - done)
+            cols = src[done % pool: done % pool + run]
+            _lib.check(L.b2_commit_batch_resident(params.g_lagrange.handle, vp(cols.ctypes.data), 0, vp(slot_ptr(name, done)),
+                                                  run, n, bits, 1 if ifft else 0, vp(dom.omega_inv.ctypes.data),
+                                                  vp(dom.ifft_divisor.ctypes.data), k, vp(out[done:].ctypes.data)))
+            done += run
+        return out
+
+    def commit_on_device(name, count, bits, ifft):
+        out = np.zeros((count, 12), dtype=np.uint64)
+        _lib.check(L.b2_commit_batch_resident(params.g_lagrange.handle, None, 1, vp(slot_ptr(name)), count, n, bits,
+                                              1 if ifft else 0, vp(dom.omega_inv.ctypes.data),
+                                              vp(dom.ifft_divisor.ctypes.data), k, vp(out.ctypes.data)))
+        return out
+
+    def intt_on_device(name, count):
+        d = NttDesc()
+        d.log_n, d.location = k, 1
+        d.omega, d.divisor = dom.omega_inv.ctypes.data, dom.ifft_divisor.ctypes.data
+        d.n_in = d.n_out = d.in_stride = d.out_stride = n
+        d.columns = count
+        d.in_ = d.out = slot_ptr(name)
+        _lib.check(L.b2_ntt_exec(ctypes.byref(d)))
+
+    # z construction (permutation shape, permutation/prover.rs:72-165): per z column two expression passes over three
+    # resident Lagrange columns + three sigma columns, one batch inversion for all, one scan each
+    from halo2_gpu_specific_b200.grand_product import ExprCompiler
+    ch = [5, 7, 0] + [11 + j for j in range(3)]
+
+    def z_programs():
+        c1 = ExprCompiler()
+        acc = None
+        for j in range(3):
+            t = c1.emit(("Mul", ("Challenge", 0), ("Aux", j, 0)))
+            t = c1.emit(("AddChallenge", c1.emit(("Add", t, ("Advice", j, 0))), "Gamma"))
+            acc = t if acc is None else c1.emit(("Mul", acc, t))
+        p1 = E.QuotientProgram(c1.rotations, c1.constants, c1.calcs, acc, 0, 3, 0, 3, len(ch))
+        c2 = ExprCompiler()
+        acc = ("Aux", 0, 0)
+        for j in range(3):
+            t = c2.emit(("Mul", ("CosetX",), ("Challenge", 3 + j)))
+            t = c2.emit(("AddChallenge", c2.emit(("Add", t, ("Advice", j, 0))), "Gamma"))
+            acc = c2.emit(("Mul", acc, t))
+        p2 = E.QuotientProgram(c2.rotations, c2.constants, c2.calcs, acc, 0, 3, 0, 1, len(ch))
+        return p1, p2
+
+    zp1, zp2 = z_programs()
+
+    def build_z(name, count):
+        adv0 = slots["advice"][0]
+        for s in range(count):
+            cols = [coef.ptr + (adv0 + (3 * s + j) % sh["A"]) * n * 32 for j in range(3)]   # still Lagrange form here
+            sig = [sigma_lagrange.ptr + ((3 * s + j) % sh["perm_cols"]) * n * 32 for j in range(3)]
+            zp1.eval(k, 1, [], cols, [], sig, ch, work.ptr + (s % sh["P"]) * n * 32)
+            if s % sh["P"] == sh["P"] - 1 or s == count - 1:
+                first = s - (s % sh["P"])
+                _lib.check(L.b2_batch_invert_dev(vp(work.ptr), (s - first + 1) * n, None))
+                for t in range(first, s + 1):
+                    cols = [coef.ptr + (adv0 + (3 * t + j) % sh["A"]) * n * 32 for j in range(3)]
+                    w = work.ptr + (t % sh["P"]) * n * 32
+                    zp2.eval(k, 1, [], cols, [], [w], ch, w, x0=1, x_step=dom._omega)
+                    dst = slot_ptr(name, t)
+                    if t == 0:
+                        _lib.check(L.b2_prefix_scan_dev(0, vp(w), n, None, None, vp(dst), n, None))
+                    else:
+                        _lib.check(L.b2_prefix_scan_dev(0, vp(w), n, None, vp(slot_ptr(name, t - 1) + (n - 6) * 32), vp(dst), n, None))
+
+    # evaluate_h pointer tables
+    def col_ptrs(base_ptr, c):
+        key_base = key_cos.ptr + c * (n_key + 3) * n * 32
+
+        def p(name, i):
+            if keep_key_cosets and name in ("fixed", "sigma"):
+                return key_base + (slots[name][0] + i) * n * 32
+            return base_ptr + (slots[name][0] + i) * n * 32
+        fixed = [p("fixed", i) for i in range(sh["F"])]
+        advice = [p("advice", i) for i in range(sh["A"])]
+        inst = [p("instance", i) for i in range(sh["I"])]
+        if keep_key_cosets:
+            aux = [key_base + (n_key + i) * n * 32 for i in range(3)]
+        else:
+            aux = [base_ptr + (n_polys + i) * n * 32 for i in range(3)]
+        aux += [p("sigma", i) for i in range(sh["perm_cols"])] + [p("perm_z", i) for i in range(sh["P"])]
+        zi = 0
+        for li, sets in enumerate(lookups):
+            aux += [p("lookup_z", zi + i) for i in range(sets)] + [p("lookup_m", li)]
+            zi += sets
+        aux += [p("shuffle_z", i) for i in range(sh["H"])]
+        return fixed, advice, inst, aux
+
+    tables = [col_ptrs(cos.ptr, c) for c in range(nc)]
+    challenges = [(i + 2) * 0x123456789ABCDEF % R for i in range(prog.n_challenges)]
+
+    def evaluate_h():
+        for c in range(nc):
+            g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
+            if keep_key_cosets:     # only the witness-dependent polynomials are transformed per proof
+                E.coeff_to_coset_dev(dom, coef.ptr + n_key * n * 32, n_polys - n_key, g_c, cos.ptr + n_key * n * 32)
+            else:
+                E.coeff_to_coset_dev(dom, coef.ptr, n_polys, g_c, cos.ptr)
+                for i in range(3):
+                    cos.upload(lag[i], (n_polys + i) * n)
+            fx, adv, ins, aux = tables[c]
+            prog.eval(k, 1, fx, adv, ins, aux, challenges, hext.ptr, x0=pow(dom._ext_omega, c, R), x_step=dom._omega,
+                      scale=dom.t_evaluations[c:c + 1], out_stride=nc, out_offset=c)
+
+    def h_to_coeff():
+        z = np.concatenate([dom.g_coset_inv, dom.g_coset])
+        d = NttDesc()
+        d.log_n, d.location = dom.extended_k, 1
+        d.omega, d.divisor = dom.extended_omega_inv.ctypes.data, dom.extended_ifft_divisor.ctypes.data
+        d.coset_out = z.ctypes.data
+        d.n_in = d.in_stride = dom.extended_len()
+        d.n_out = d.out_stride = n * dom.quotient_poly_degree
+        d.columns, d.in_, d.out = 1, hext.ptr, hcoef.ptr
+        _lib.check(L.b2_ntt_exec(ctypes.byref(d)))
+
+    def commit_h_pieces():
+        out = np.zeros((sh["D"], 12), dtype=np.uint64)
+        for i in range(sh["D"]):
+            _lib.check(L.b2_msm_dev(params.g.handle, 0, vp(hcoef.ptr + i * n * 32), n, 254, vp(d96.ptr), None))
+            L.b2_synchronize()
+            _lib.check(L.b2_memcpy_d2h(vp(out[i:].ctypes.data), vp(d96.ptr), 96))
+        _lib.check(L.b2_g1_normalize(vp(out.ctypes.data), sh["D"]))
+        return out
+
+    def copy_back():
+        """coefficient forms the CPU side uses for the multiopen evaluations + the h pieces"""
+        cnt = 0
+        for name in ("advice", "instance", "perm_z", "lookup_z", "shuffle_z", "lookup_m"):
+            for i in range(slots[name][1]):
+                _lib.check(L.b2_memcpy_d2h(vp(back[cnt % pool].ctypes.data), vp(slot_ptr(name, i)), n * 32))
+                cnt += 1
+        for i in range(sh["D"]):
+            _lib.check(L.b2_memcpy_d2h(vp(back[cnt % pool].ctypes.data), vp(hcoef.ptr + i * n * 32), n * 32))
+            cnt += 1
+        return cnt
+
+    def phase(fn):
+        L.b2_synchronize()
+        t = time.perf_counter()
+        out = fn()
+        L.b2_synchronize()
+        return time.perf_counter() - t, out
+
+    results = []
+    for rep in range(a.reps + 1):
+        ph = {}
+        ph["1_instance_commit_ifft"], _ = phase(lambda: commit_resident(big, sh["I"], "instance", 254, True))
+        ph["2_advice_commit"], _ = phase(lambda: commit_resident(small, sh["A"], "advice", 16, False))
+        ph["3_lookup_m_commit"], _ = phase(lambda: commit_resident(small, sh["L"], "lookup_m", 16, False))
+        ph["5_z_construct_on_device"], _ = phase(lambda: (build_z("perm_z", sh["P"]), build_z("lookup_z", sh["S"]),
+                                                          build_z("shuffle_z", sh["H"])))
+        ph["6_z_commit_and_ifft"], _ = phase(lambda: (commit_on_device("perm_z", sh["P"], 254, True),
+                                                      commit_on_device("lookup_z", sh["S"], 254, True),
+                                                      commit_on_device("shuffle_z", sh["H"], 254, True)))
+        ph["7_vanishing_commit"], _ = phase(lambda: params.commit(big[0]))
+        ph["8_advice_m_ifft_on_device"], _ = phase(lambda: (intt_on_device("advice", sh["A"]),
+                                                             intt_on_device("lookup_m", sh["L"])))
+        ph["9_evaluate_h"], _ = phase(evaluate_h)
+        ph["10_h_to_coeff"], _ = phase(h_to_coeff)
+        ph["10_h_commits"], _ = phase(commit_h_pieces)
+        ph["11_copy_back_for_multiopen"], ncopy = phase(copy_back)
+        ph["12_multiopen_commits"], _ = phase(lambda: [params.commit(c[0]) for c in batch_of(big, sh["R"])])
+        ph["total"] = sum(ph.values())
+        results.append(ph)
+    best = min(results[1:], key=lambda p: p["total"])
+    doc = {"workload": "create_proof schedule replay, zkWasm-scale shape, device-resident", "k": k, "shape": sh,
+           "n_gpus": 1, "phases_s": best, "wall_s": best["total"], "setup_s": setup_s,
+           "key_cosets_resident": keep_key_cosets,
+           "resident_GiB": (2 * n_polys + 3 + sh["perm_cols"] + sh["P"] + 8 + ((n_key + 3) * nc if keep_key_cosets else 0))
+                           * n * 32 / 2**30,
+           "h2d_GiB": (sh["I"] + sh["A"] + sh["L"] + 1 + sh["R"] + (0 if keep_key_cosets else 3 * nc)) * n * 32 / 2**30,
+           "d2h_GiB": ncopy * n * 32 / 2**30,
+           "program": prog.info(),
+           "excluded": "CPU-side protocol logic (witness synthesis, the logup multiplicities, transcript hashing, "
+                       "the multiopen polynomial bookkeeping)",
+           "note": "z construction uses the permutation-shaped expression programs for all P + S + H columns"}
+    print(json.dumps(doc), flush=True)
+    if a.out:
+        json.dump(doc, open(a.out, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
