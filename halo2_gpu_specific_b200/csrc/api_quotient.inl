@@ -367,6 +367,9 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
         return fail(B2_ERR_ARG, "quotient_eval: scale_len must be a power of two");
     if (args->rot_scale == 0 || args->out_stride == 0) return fail(B2_ERR_ARG, "quotient_eval: rot_scale / out_stride must be >= 1");
     const unsigned long long rows = 1ull << args->log_rows;
+    const unsigned long long row_begin = args->row_count ? args->row_begin : 0;
+    const unsigned long long row_count = args->row_count ? args->row_count : rows;
+    if (row_begin >= rows || row_count > rows - row_begin) return fail(B2_ERR_ARG, "quotient_eval: row range outside the domain");
 
     LaneLock ll;
     if ((rc = ll.acquire())) return rc;
@@ -467,8 +470,10 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
     a.out = reinterpret_cast<uint4*>(args->out);
     a.out_stride = args->out_stride;
     a.out_offset = args->out_offset;
+    a.row_begin = row_begin;
+    a.row_count = row_count;
     const size_t smem = (size_t)p->n_slots * Q_THREADS * 32;
-    const unsigned long long blocks_all = (rows + Q_THREADS - 1) / Q_THREADS;
+    const unsigned long long blocks_all = (row_count + Q_THREADS - 1) / Q_THREADS;
     const char* force_spill = getenv("B2_Q_FORCE_SPILL");   // tests: exercise the global-slot variant
     CK(cudaEventRecord(ctx->ev[12], st));
     if (smem <= Q_SMEM_LIMIT && !(force_spill && atoi(force_spill) == 1)) {

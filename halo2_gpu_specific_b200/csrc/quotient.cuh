@@ -60,6 +60,8 @@ struct QArgs {
     unsigned long long out_stride;   // result of row i goes to out[out_offset + i * out_stride]
     unsigned long long out_offset;
     uint4* slot_spill;            // global slots when they do not fit in shared memory
+    unsigned long long row_begin; // rows [row_begin, row_begin + row_count) are evaluated (a rank's share);
+    unsigned long long row_count; // result of row i still goes to out[out_offset + (i - row_begin) * out_stride]
 };
 
 template <bool SMEM>
@@ -108,8 +110,9 @@ __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a)
         slots.lo = base + threadIdx.x;
         slots.hi = base + (size_t)a.n_slots * Q_THREADS + threadIdx.x;
     }
-    for (unsigned long long row = (unsigned long long)blockIdx.x * Q_THREADS + threadIdx.x; row < a.rows;
-         row += (unsigned long long)gridDim.x * Q_THREADS) {
+    for (unsigned long long rel = (unsigned long long)blockIdx.x * Q_THREADS + threadIdx.x; rel < a.row_count;
+         rel += (unsigned long long)gridDim.x * Q_THREADS) {
+        const unsigned long long row = a.row_begin + rel;
         // coset point of this row (beta_term of evaluation.rs:1018-1019): two-level table, one product
         Fr x_here = Fr::zero();
         if (a.x_lo != nullptr)
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a)
         }
         Fr res = q_fetch<SMEM>(a.result, a, slots, row, x_here);
         if (a.scale != nullptr) res = fp_mul<FrParams>(res, fp_load_nc<FrParams>(a.scale + (row & a.scale_mask)));
-        fp_store<FrParams>(a.out + 2ull * (a.out_offset + row * a.out_stride), res);
+        fp_store<FrParams>(a.out + 2ull * (a.out_offset + rel * a.out_stride), res);
     }
 }
 

@@ -56,7 +56,7 @@ class QArgs(ctypes.Structure):
                 ("x0", ctypes.c_void_p), ("x_step", ctypes.c_void_p),
                 ("scale", ctypes.c_void_p), ("scale_len", ctypes.c_uint32),
                 ("out", ctypes.c_void_p), ("out_stride", ctypes.c_uint64), ("out_offset", ctypes.c_uint64),
-                ("stream", ctypes.c_void_p)]
+                ("stream", ctypes.c_void_p), ("row_begin", ctypes.c_uint64), ("row_count", ctypes.c_uint64)]
 
 
 _KIND = {"Constant": Q_CONSTANT, "Intermediate": Q_INTERMEDIATE, "Fixed": Q_FIXED, "Advice": Q_ADVICE,
@@ -142,7 +142,7 @@ class QuotientProgram:
 
     def eval(self, log_rows: int, rot_scale: int, fixed, advice, instance, aux, challenges: Sequence[int], out_ptr: int,
              x0: Optional[int] = None, x_step: Optional[int] = None, scale: Optional[np.ndarray] = None,
-             out_stride: int = 1, out_offset: int = 0, stream: int = 0) -> None:
+             out_stride: int = 1, out_offset: int = 0, stream: int = 0, row_begin: int = 0, row_count: int = 0) -> None:
         """fixed / advice / instance / aux: sequences of DEVICE pointers (ints)."""
         require_gpu()
 
@@ -170,6 +170,7 @@ class QuotientProgram:
             scale = np.ascontiguousarray(scale, dtype=np.uint64).reshape(-1, 4)
             a.scale, a.scale_len = scale.ctypes.data, scale.shape[0]
         a.out, a.out_stride, a.out_offset, a.stream = out_ptr, out_stride, out_offset, stream
+        a.row_begin, a.row_count = row_begin, row_count
         check(lib().b2_quotient_eval(ctypes.c_uint64(self.handle), ctypes.byref(a)))
 
 
@@ -433,33 +434,95 @@ class Evaluator:
         which = list(range(n_cosets)) if cosets is None else list(cosets)
         if to_coeff and len(which) != n_cosets:
             raise B2Error(B2_ERR_ARG, "to_coeff needs every coset")
-        coef = DeviceBuffer(max(1, n_polys) * n)           # coefficient forms, uploaded once
-        cos = DeviceBuffer((n_polys + 3) * n)               # one coset of every polynomial + l0 / l_last / l_active_row
         out = DeviceBuffer(ext_len)
         try:
-            allp = [np.asarray(p, dtype=np.uint64).reshape(n, 4) for g in groups for p in g]
-            if allp:
-                coef.upload(np.stack(allp))
-            ptrs, col = [], 0
-            for g in groups:
-                ptrs.append([cos.ptr + (col + i) * n * 32 for i in range(len(g))])
-                col += len(g)
-            lag = [cos.ptr + (n_polys + i) * n * 32 for i in range(3)]
-            for c in which:
-                g_c = zeta_v * pow(domain._ext_omega, c, R) % R
-                if n_polys:
-                    coeff_to_coset_dev(domain, coef.ptr, n_polys, g_c, cos.ptr)
-                for i, v in enumerate(lag_host):
-                    cos.upload(np.ascontiguousarray(v[c::n_cosets]), (n_polys + i) * n)
-                scale = domain.t_evaluations[c:c + 1] if to_coeff else None
-                prog.eval(domain.k, 1, ptrs[0], ptrs[1], ptrs[2], lag + ptrs[3], challenges, out.ptr,
-                          x0=pow(domain._ext_omega, c, R), x_step=domain._omega, scale=scale,
-                          out_stride=n_cosets, out_offset=c)
+            self.evaluate_h_tasks(domain, groups, lag_host, challenges, prog, [(c, 0, n) for c in which], out.ptr,
+                                  compact=False, scaled=to_coeff, zeta=zeta_v)
             return extended_to_coeff_dev(domain, out) if to_coeff else out.download()
         finally:
-            coef.free()
-            cos.free()
             out.free()
+
+    def evaluate_h_tasks(self, domain, groups, lag_host, challenges, prog, tasks, out_ptr: int, compact: bool,
+                         scaled: bool, zeta: int, resident: "Optional[ResidentPolys]" = None) -> None:
+        """Coset-mode core.  tasks: (coset, row_begin, row_count) triples, coset-major; the rows of a task go to
+        out[4 * row + coset] (compact=False, the extended layout) or are appended to `out` in task order
+        (compact=True: what a rank contributes to the all-gather, parallel.sharded_evaluate_h).  scaled: fold
+        divide_by_vanishing_poly into the store.  resident: polynomials already in HBM (ResidentPolys);
+        otherwise they are uploaded for this call."""
+        n = domain.n
+        R = _fr.R_MOD
+        n_cosets = 1 << (domain.extended_k - domain.k)
+        res = resident if resident is not None else ResidentPolys(domain, groups, lag_host)
+        try:
+            loaded, written = None, 0
+            for c, begin, count in tasks:
+                if c != loaded:
+                    g_c = zeta * pow(domain._ext_omega, c, R) % R
+                    if res.n_polys:
+                        coeff_to_coset_dev(domain, res.coef.ptr, res.n_polys, g_c, res.cos.ptr)
+                    loaded = c
+                scale = domain.t_evaluations[c:c + 1] if scaled else None
+                if compact:
+                    stride, offset = 1, written
+                else:
+                    stride, offset = n_cosets, c + begin * n_cosets
+                p = res.ptrs
+                prog.eval(domain.k, 1, p[0], p[1], p[2], res.lag_ptrs(c) + p[3], challenges, out_ptr,
+                          x0=pow(domain._ext_omega, c, R), x_step=domain._omega, scale=scale,
+                          out_stride=stride, out_offset=offset, row_begin=begin, row_count=count)
+                written += count
+        finally:
+            if resident is None:
+                res.free()
+
+
+class ResidentPolys:
+    """Everything evaluate_h reads, resident in HBM: the coefficient forms of all polynomials (one buffer,
+    fixed | advice | instance | aux order), one coset's worth of scratch for their evaluations, and
+    l0 / l_last / l_active_row split into the 2^(extended_k - k) cosets (they are proving-key data)."""
+
+    def __init__(self, domain, groups, lag_host):
+        n = domain.n
+        nc = 1 << (domain.extended_k - domain.k)
+        self.n_polys = sum(len(g) for g in groups)
+        self.coef = DeviceBuffer(max(1, self.n_polys) * n)
+        self.cos = DeviceBuffer(max(1, self.n_polys) * n)
+        self.lag = DeviceBuffer(3 * nc * n)
+        col = 0
+        for g in groups:                       # column by column: no host-side concatenation of the whole set
+            for p in g:
+                self.coef.upload(np.asarray(p, dtype=np.uint64).reshape(n, 4), col * n)
+                col += 1
+        for c in range(nc):
+            for i, v in enumerate(lag_host):
+                v = np.asarray(v, dtype=np.uint64).reshape(-1, 4)
+                self.lag.upload(np.ascontiguousarray(v[c::nc]), (c * 3 + i) * n)
+        self.ptrs, col = [], 0
+        for g in groups:
+            self.ptrs.append([self.cos.ptr + (col + i) * n * 32 for i in range(len(g))])
+            col += len(g)
+        self._n = n
+
+    def lag_ptrs(self, c: int):
+        return [self.lag.ptr + (c * 3 + i) * self._n * 32 for i in range(3)]
+
+    def free(self):
+        self.coef.free()
+        self.cos.free()
+        self.lag.free()
+
+
+def interleave_cosets_dev(domain, d_compact: int, d_ext: int) -> None:
+    """coset-major h (coset c at d_compact[c * n ...]) -> extended layout d_ext[4 * i + c]: a zero-instruction
+    program whose result is its one aux column, stored with the coset stride"""
+    n_cosets = 1 << (domain.extended_k - domain.k)
+    prog = QuotientProgram([0], [0], [], ("Aux", 0, 0), 0, 0, 0, 1, 0)
+    try:
+        for c in range(n_cosets):
+            prog.eval(domain.k, 1, [], [], [], [d_compact + c * domain.n * 32], [], d_ext, out_stride=n_cosets,
+                      out_offset=c)
+    finally:
+        prog.free()
 
 
 def coeff_to_coset_dev(domain, d_coeffs: int, columns: int, gen: int, d_out: int) -> None:

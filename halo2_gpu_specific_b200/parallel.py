@@ -69,3 +69,79 @@ def sharded_msm(scalars_shard: np.ndarray, srs_shard, max_bits: int = 254, *,
     if ws == 1:
         return np.asarray(partial, dtype=np.uint64).reshape(12)
     return combine(all_gather_partials(partial))
+
+
+# ---- evaluate_h over several GPUs -------------------------------------------------------------------
+def quotient_tasks(n_cosets: int, n: int, world_size: int, rank: int):
+    """The extended domain in coset-major order (coset 0 rows 0..n-1, coset 1, ...) is cut into world_size equal
+    contiguous ranges; returns this rank's range as (coset, row_begin, row_count) triples.  With world_size <=
+    n_cosets a rank owns whole cosets; beyond that the ranks sharing a coset each transform it and evaluate
+    their rows.  Cosets never exchange data (a rotation stays inside its coset)."""
+    total = n_cosets * n
+    lo, hi = shard_range(total, world_size, rank)
+    tasks = []
+    while lo < hi:
+        c, begin = divmod(lo, n)
+        count = min(n - begin, hi - lo)
+        tasks.append((c, begin, count))
+        lo += count
+    return tasks
+
+
+def all_gather_rows(local: "np.ndarray | object", rows_total: int):
+    """every rank's compact slice of h (equal row counts) -> the full coset-major array, on every rank"""
+    d = _dist()
+    if d is None:
+        return local
+    import torch
+    t = local if isinstance(local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(local).view(np.int64))
+    out = torch.empty((rows_total, 4), dtype=torch.int64, device=t.device)
+    d.all_gather_into_tensor(out.view(-1), t.reshape(-1))
+    return out if isinstance(local, torch.Tensor) else out.numpy().view(np.uint64)
+
+
+def sharded_evaluate_h(ev, domain, fixed_polys, advice_polys, instance_polys, l0, l_last, l_active_row, sigma_polys,
+                       y: int, beta: int, gamma: int, theta: int, lookups, shuffles, permutations, zeta=None,
+                       resident=None) -> np.ndarray:
+    """Evaluator::evaluate_h + h(X) with the rows of the extended domain split over the ranks of the default
+    process group (one process per GPU): every rank holds the coefficient forms, evaluates its rows
+    (quotient_tasks), the slices of h are all-gathered over NCCL (32 B per row, the only exchange), and each
+    rank finishes with divide_by_vanishing_poly (folded into the kernel) + extended_to_coeff.
+    Returns the coefficients of h(X), identical on every rank.  resident: an evaluation.ResidentPolys built from
+    the same polynomials (then the *_polys arguments only give the counts): nothing is uploaded in the call."""
+    import torch
+    from . import _fr
+    from .evaluation import DELTA, DeviceBuffer, extended_to_coeff_dev, interleave_cosets_dev
+    rank, ws = world()
+    n, ext_len = domain.n, domain.extended_len()
+    nc = ext_len // n
+    if (nc * n) % ws:
+        raise ValueError("world size must divide the extended domain")
+    prog = ev.program(len(permutations), [len(lk["z"]) for lk in lookups], len(shuffles))
+    aux_polys = list(sigma_polys) + list(permutations)
+    for lk in lookups:
+        aux_polys += list(lk["z"]) + [lk["m"]]
+    aux_polys += list(shuffles)
+    groups = [list(fixed_polys), list(advice_polys), list(instance_polys), aux_polys]
+    R = _fr.R_MOD
+    zeta_v = domain._zeta if zeta is None else zeta
+    challenges = [beta % R, gamma % R, theta % R, y % R]
+    dlt = beta * zeta_v % R
+    for _ in ev.permutation_columns:
+        challenges.append(dlt)
+        dlt = dlt * DELTA % R
+    lag_host = [np.asarray(v, dtype=np.uint64).reshape(ext_len, 4) for v in (l0, l_last, l_active_row)]
+    tasks = quotient_tasks(nc, n, ws, rank)
+    mine = sum(t[2] for t in tasks)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    local = torch.empty((mine, 4), dtype=torch.int64, device=dev)
+    ev.evaluate_h_tasks(domain, groups, lag_host, challenges, prog, tasks, local.data_ptr(), compact=True, scaled=True,
+                        zeta=zeta_v, resident=resident)
+    full = all_gather_rows(local, nc * n)
+    torch.cuda.synchronize()
+    ext = DeviceBuffer(ext_len)
+    try:
+        interleave_cosets_dev(domain, full.data_ptr(), ext.ptr)
+        return extended_to_coeff_dev(domain, ext)
+    finally:
+        ext.free()

@@ -248,6 +248,8 @@ typedef struct b2_quotient_args {
     uint64_t out_stride;
     uint64_t out_offset;
     void* stream;                 /* cudaStream_t or NULL; the call returns after the launch is enqueued */
+    uint64_t row_begin;           /* row_count != 0: only rows [row_begin, row_begin + row_count) are evaluated and   */
+    uint64_t row_count;           /*   row i is stored at out[out_offset + (i - row_begin) * out_stride] (a rank's share) */
 } b2_quotient_args;
 int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args);
 

@@ -213,3 +213,58 @@ def test_zkwasm_shape_program_full_compare(gpu):
     gd = o.fr_decode(got[:64])
     assert gd == [w * sc[i % 4] % R for i, w in enumerate(wd)]
     buf.free(); out.free()
+
+
+def test_sharded_path_single_rank(gpu):
+    """parallel.sharded_evaluate_h with one rank: compact task output, interleave, extended_to_coeff"""
+    from halo2_gpu_specific_b200 import parallel
+    fx = fxm.build(k=5, seed=41)
+    d = fx["domain"]
+    dom = h2.EvaluationDomain(fx["cs"].degree(), 5)
+    c = fx["coeff"]
+    l0, l_last, l_active = P.lagrange_basis_cosets(fx["cs"], d)
+    lookups = [{"z": [enc(z) for z in zs], "m": enc(m)} for zs, m in zip(c["lookup_z"], c["lookup_m"])]
+    got = parallel.sharded_evaluate_h(make_evaluator(fx), dom, [enc(p) for p in c["fixed"]], [enc(p) for p in c["advice"]],
+                                      [enc(p) for p in c["instance"]], enc(l0), enc(l_last), enc(l_active),
+                                      [enc(p) for p in c["sigma"]], fx["y"], fx["beta"], fx["gamma"], fx["theta"], lookups,
+                                      [enc(p) for p in c["shuffle_z"]], [enc(p) for p in c["perm_z"]])
+    want = enc(d.extended_to_coeff(d.divide_by_vanishing_poly(fxm.oracle_h(fx))))
+    assert np.array_equal(got, want)
+
+
+def test_row_ranges_of_one_coset(gpu):
+    """two ranks sharing a coset: each evaluates half of its rows"""
+    fx = fxm.build(k=5, seed=43)
+    dom = h2.EvaluationDomain(fx["cs"].degree(), 5)
+    want = enc(fxm.oracle_h(fx))
+    Ev = make_evaluator(fx)
+    c = fx["coeff"]
+    l0, l_last, l_active = P.lagrange_basis_cosets(fx["cs"], fx["domain"])
+    lookups = [{"z": [enc(z) for z in zs], "m": enc(m)} for zs, m in zip(c["lookup_z"], c["lookup_m"])]
+    prog = Ev.program(len(c["perm_z"]), [len(l["z"]) for l in lookups], len(c["shuffle_z"]))
+    aux = [enc(p) for p in c["sigma"]] + [enc(p) for p in c["perm_z"]]
+    for lk in lookups:
+        aux += lk["z"] + [lk["m"]]
+    aux += [enc(p) for p in c["shuffle_z"]]
+    groups = [[enc(p) for p in c["fixed"]], [enc(p) for p in c["advice"]], [enc(p) for p in c["instance"]], aux]
+    lag = [enc(v) for v in (l0, l_last, l_active)]
+    ch = [fx["beta"], fx["gamma"], fx["theta"], fx["y"]]
+    dlt = fx["beta"] * dom._zeta % R
+    for _ in fx["cs"].permutation_columns:
+        ch.append(dlt)
+        dlt = dlt * P.FR_DELTA % R
+    n, nc = dom.n, 4
+    from halo2_gpu_specific_b200 import parallel
+    out = E.DeviceBuffer(nc * n)
+    for rank in range(8):
+        tasks = parallel.quotient_tasks(nc, n, 8, rank)
+        part = E.DeviceBuffer(sum(t[2] for t in tasks))
+        Ev.evaluate_h_tasks(dom, groups, lag, ch, prog, tasks, part.ptr, compact=True, scaled=False, zeta=dom._zeta)
+        got = part.download()
+        pos = 0
+        for cst, begin, count in tasks:
+            rows = [nc * (begin + i) + cst for i in range(count)]
+            assert np.array_equal(got[pos:pos + count], want[rows]), (rank, cst, begin)
+            pos += count
+        part.free()
+    out.free()

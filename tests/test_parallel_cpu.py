@@ -65,3 +65,45 @@ def test_shard_ranges_cover_and_match_reference_rule():
             part_len = (n + w - 1) // w   # arithmetic.rs:426
             assert all(hi - lo <= part_len for lo, hi in parts)
     assert parallel.column_range(64, 8, 3) == (24, 32)
+
+
+def test_quotient_tasks_tile_the_extended_domain():
+    from halo2_gpu_specific_b200 import parallel
+    for nc, n in ((4, 1 << 10), (8, 1 << 6), (2, 1 << 5)):
+        for w in (1, 2, 4, 8, 16):
+            seen = []
+            for r in range(w):
+                tasks = parallel.quotient_tasks(nc, n, w, r)
+                assert sum(t[2] for t in tasks) == nc * n // w
+                for c, begin, count in tasks:
+                    assert 0 <= c < nc and count > 0 and begin + count <= n
+                    seen += [c * n + begin + i for i in (0, count - 1)]
+                    seen.append((c * n + begin, c * n + begin + count))
+            ranges = sorted(x for x in seen if isinstance(x, tuple))
+            assert ranges[0][0] == 0 and ranges[-1][1] == nc * n
+            for a, b in zip(ranges, ranges[1:]):
+                assert a[1] == b[0]          # contiguous, disjoint, coset-major
+    assert parallel.quotient_tasks(4, 16, 2, 1) == [(2, 0, 16), (3, 0, 16)]
+    assert parallel.quotient_tasks(4, 16, 8, 3) == [(1, 8, 8)]
+
+
+def _gather_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from halo2_gpu_specific_b200 import parallel
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    nc, n = 4, 32
+    full = (np.arange(nc * n * 4, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(nc * n, 4)
+    mine = np.concatenate([full[c * n + b: c * n + b + cnt] for c, b, cnt in parallel.quotient_tasks(nc, n, world, rank)])
+    got = parallel.all_gather_rows(mine, nc * n)
+    np.save(os.path.join(outdir, f"g{rank}.npy"), got)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_rows_world2_gloo(tmp_path):
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    full = (np.arange(4 * 32 * 4, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(128, 4)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"g{r}.npy"), full)
