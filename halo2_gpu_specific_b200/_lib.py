@@ -49,6 +49,8 @@ SYMBOLS = [
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
+    "b2_g1_decompress", "b2_g1_compress", "b2_srs_register_compressed", "b2_srs_read_compressed",
+    "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev",
     "b2_batch_invert", "b2_batch_invert_dev", "b2_prefix_scan", "b2_prefix_scan_dev", "b2_fr_vec_dev",
 ]
 
@@ -105,6 +107,14 @@ def lib() -> ctypes.CDLL:
         L.b2_quotient_program_free.argtypes = [u64]
         L.b2_quotient_program_info.argtypes = [u64] + [ctypes.POINTER(u32)] * 4
         L.b2_quotient_eval.argtypes = [u64, vp]
+        L.b2_g1_decompress.argtypes = [vp, sz, u32, vp]
+        L.b2_g1_compress.argtypes = [vp, sz, u32, vp]
+        L.b2_srs_register_compressed.argtypes = [vp, sz, u32, ctypes.POINTER(u64)]
+        L.b2_srs_read_compressed.argtypes = [u64, sz, sz, u32, vp]
+        L.b2_eval_polynomial.argtypes = [vp, u64, vp, vp]
+        L.b2_eval_polynomial_dev.argtypes = [vp, u64, u64, u64, vp, vp]
+        L.b2_kate_division.argtypes = [vp, u64, vp, vp]
+        L.b2_kate_division_dev.argtypes = [vp, u64, vp, vp, vp]
         L.b2_batch_invert.argtypes = [vp, sz]
         L.b2_batch_invert_dev.argtypes = [vp, sz, vp]
         L.b2_prefix_scan.argtypes = [ctypes.c_int, vp, sz, vp, vp, sz]

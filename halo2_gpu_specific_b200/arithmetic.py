@@ -33,6 +33,21 @@ class Srs:
         return cls(h.value, b.shape[0])
 
     @classmethod
+    def register_compressed(cls, data: bytes, n: int, sign_bit: int = 7) -> "Srs":
+        """n 32-byte compressed points as they sit in a params file (poly/commitment.rs:262-273): decompressed on
+        the device straight into the resident SRS"""
+        require_gpu()
+        buf = np.frombuffer(data, dtype=np.uint8, count=32 * n)
+        h = ctypes.c_uint64()
+        check(lib().b2_srs_register_compressed(ctypes.c_void_p(buf.ctypes.data), n, sign_bit, ctypes.byref(h)))
+        return cls(h.value, n)
+
+    def read_compressed(self, sign_bit: int = 7) -> bytes:
+        out = np.empty(32 * self.n, dtype=np.uint8)
+        check(lib().b2_srs_read_compressed(self.handle, self.offset, self.n, sign_bit, ctypes.c_void_p(out.ctypes.data)))
+        return out.tobytes()
+
+    @classmethod
     def synthetic(cls, n: int, first_index: int = 0, seed: int = 0xB2000003) -> "Srs":
         require_gpu()
         h = ctypes.c_uint64()
@@ -241,4 +256,25 @@ def g1_sum(points) -> np.ndarray:
     require_gpu()
     out = np.zeros(12, dtype=np.uint64)
     check(lib().b2_g1_sum(ptr(p), p.shape[0], ptr(out)))
+    return out
+
+
+def eval_polynomial(poly: np.ndarray, point) -> np.ndarray:
+    """arithmetic.rs:714-735: poly (n, 4) coefficients, point (4,) -> (4,) Montgomery"""
+    require_gpu()
+    p = as_fr(poly)
+    pt = as_fr1(point)
+    out = np.empty(4, dtype=np.uint64)
+    check(lib().b2_eval_polynomial(ptr(p), p.shape[0], ptr(pt), ptr(out)))
+    return out
+
+
+def kate_division(a: np.ndarray, b) -> np.ndarray:
+    """arithmetic.rs:752-773: (a(X) - a(b)) / (X - b), n - 1 coefficients"""
+    require_gpu()
+    p = as_fr(a)
+    if p.shape[0] < 2:
+        raise B2Error(B2_ERR_ARG, "kate_division needs at least two coefficients")
+    out = np.empty((p.shape[0] - 1, 4), dtype=np.uint64)
+    check(lib().b2_kate_division(ptr(p), p.shape[0], ptr(as_fr1(b)), ptr(out)))
     return out

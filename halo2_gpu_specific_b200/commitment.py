@@ -16,7 +16,8 @@ class Params:
     g / g_lagrange: (n,8) uint64 affine arrays (as Params::read would produce), or Srs
     objects that are already resident."""
 
-    def __init__(self, k: int, g, g_lagrange, precompute: bool = True):
+    def __init__(self, k: int, g, g_lagrange, precompute: bool = True, additional_data: bytes = b""):
+        self.additional_data = bytes(additional_data)
         self.k = k
         self.n = 1 << k
         self.g = g if isinstance(g, Srs) else Srs.register(g)
@@ -76,6 +77,47 @@ class Params:
             check(lib().b2_commit_batch(self.g_lagrange.handle, ptr(cols), cols.shape[0], cols.shape[1],
                                         int(max_bits), 1, ptr(om), ptr(dv), self.k, ptr(out)))
         return out
+
+    def write(self, writer, sign_bit: int = 7) -> None:
+        """:241-253: k || g || g_lagrange (32-byte compressed points) || len || additional_data.  The points are
+        compressed on the device from the resident SRS."""
+        writer.write(int(self.k).to_bytes(4, "little"))
+        writer.write(self.g.read_compressed(sign_bit))
+        writer.write(self.g_lagrange.read_compressed(sign_bit))
+        writer.write(len(self.additional_data).to_bytes(4, "little"))
+        writer.write(self.additional_data)
+
+    @classmethod
+    def read(cls, reader, sign_bit: int = 7, precompute: bool = True) -> "Params":
+        """:256-294.  The compressed points go to the device as read; the Fq square roots the reference computes
+        with `parallelize` on the CPU (:262-273) run there.  Raises B2Error(B2_ERR_ARG) on an invalid point."""
+        head = reader.read(4)
+        if len(head) != 4:
+            raise B2Error(B2_ERR_ARG, "params: truncated header")
+        k = int.from_bytes(head, "little")
+        if k > _fr.S:
+            raise B2Error(B2_ERR_ARG, f"params: k = {k} exceeds Fr::S")
+        n = 1 << k
+        parts = []
+        for _ in range(2):
+            b = reader.read(32 * n)
+            if len(b) != 32 * n:
+                raise B2Error(B2_ERR_ARG, "params: truncated point section")
+            parts.append(b)
+        ln = reader.read(4)
+        if len(ln) != 4:
+            raise B2Error(B2_ERR_ARG, "params: truncated additional-data length")
+        ln = int.from_bytes(ln, "little")
+        extra = reader.read(ln)
+        if len(extra) != ln:
+            raise B2Error(B2_ERR_ARG, "params: truncated additional data")
+        g = Srs.register_compressed(parts[0], n, sign_bit)
+        try:
+            gl = Srs.register_compressed(parts[1], n, sign_bit)
+        except B2Error:
+            g.free()
+            raise
+        return cls(k, g, gl, precompute=precompute, additional_data=extra)
 
     def free(self) -> None:
         self.g.free()

@@ -24,6 +24,7 @@
 #include "ntt.cuh"
 #include "quotient.cuh"
 #include "scan.cuh"
+#include "encoding.cuh"
 
 using namespace b2;
 
@@ -1597,3 +1598,4 @@ int b2_last_msm_phases(double* phases) {
 
 #include "api_quotient.inl"
 #include "api_scan.inl"
+#include "api_encoding.inl"

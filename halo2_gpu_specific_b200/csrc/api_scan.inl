@@ -140,3 +140,119 @@ int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_ou
 }
 
 }  // extern "C"
+
+// ---- eval_polynomial / kate_division on device-resident coefficient forms ----------------------------
+namespace {
+
+int hr_inv(uint64_t r[4], const uint64_t a[4]) {   // a^(r - 2)
+    uint64_t acc[4], base[4];
+    memcpy(acc, HR_ONE, 32);
+    memcpy(base, a, 32);
+    uint64_t e[4] = {HR_P[0] - 2, HR_P[1], HR_P[2], HR_P[3]};
+    for (int i = 0; i < 256; i++) {
+        if ((e[i / 64] >> (i % 64)) & 1) hr_mul(acc, acc, base);
+        hr_mul(base, base, base);
+    }
+    memcpy(r, acc, 32);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t stride, uint64_t n, const void* point,
+                           void* out_host) {
+    if (!d_polys || !point || !out_host || n == 0 || stride < n) return fail(B2_ERR_ARG, "eval_polynomial: bad arguments");
+    if (columns == 0) return B2_OK;
+    if (columns > 65535) return fail(B2_ERR_ARG, "eval_polynomial: at most 65535 polynomials per call");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = ctx->stream;
+    const uint64_t threads = (n + EVAL_C - 1) / EVAL_C;
+    const uint32_t bpc = (uint32_t)((threads + EVAL_T - 1) / EVAL_T);
+    const size_t lo_n = (size_t)1 << EVAL_LO, hi_n = (size_t)(threads >> EVAL_LO) + 1;
+    if ((rc = ctx->scan_tmp.reserve((lo_n + hi_n) * 32 + (size_t)columns * bpc * 32 + (size_t)columns * 32))) return rc;
+    Fr* lo = ctx->scan_tmp.as<Fr>();
+    Fr* hi = lo + lo_n;
+    uint4* partials = reinterpret_cast<uint4*>(hi + hi_n);
+    uint4* d_out = partials + 2ull * columns * bpc;
+    const Fr x = fr_from_bytes(point);
+    Fr one;
+    memcpy(one.v, HR_ONE, 32);
+    LAUNCH(*ctx, ntt_pow_table_kernel, (unsigned)((lo_n + 127) / 128), 128, 0, st, lo, x, (unsigned long long)EVAL_C,
+           (uint32_t)lo_n, 0, one);
+    LAUNCH(*ctx, ntt_pow_table_kernel, (unsigned)((hi_n + 127) / 128), 128, 0, st, hi, x,
+           (unsigned long long)EVAL_C << EVAL_LO, (uint32_t)hi_n, 0, one);
+    LAUNCH(*ctx, eval_poly_partial_kernel, dim3(bpc, (unsigned)columns), EVAL_T, 0, st, (const uint4*)d_polys,
+           (unsigned long long)stride, (unsigned long long)n, x, lo, hi, partials, bpc);
+    LAUNCH(*ctx, eval_poly_final_kernel, (unsigned)columns, EVAL_T, 0, st, partials, bpc, d_out);
+    CK(cudaMemcpyAsync(out_host, d_out, (size_t)columns * 32, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* out) {
+    if (!poly || !point || !out || n == 0) return fail(B2_ERR_ARG, "eval_polynomial: bad arguments");
+    void* d = nullptr;
+    CK(cudaMalloc(&d, n * 32));
+    cudaError_t e = cudaMemcpy(d, poly, n * 32, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? b2_eval_polynomial_dev(d, 1, n, n, point, out) : fail(B2_ERR_CUDA, "eval_polynomial: upload failed");
+    cudaFree(d);
+    return rc;
+}
+
+int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, void* stream) {
+    if (!d_a || !b || !d_q || n < 2) return fail(B2_ERR_ARG, "kate_division: bad arguments");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if ((rc = ll.order_after_busy(st))) return rc;
+    uint64_t bb[4];
+    memcpy(bb, b, 32);
+    if ((bb[0] | bb[1] | bb[2] | bb[3]) == 0) {
+        // b = 0: q[j] = a[j + 1]
+        CK(cudaMemcpyAsync(d_q, (const char*)d_a + 32, (n - 1) * 32, cudaMemcpyDeviceToDevice, st));
+    } else {
+        uint64_t binv[4];
+        hr_inv(binv, bb);
+        if ((rc = ctx->ntt_work.reserve((size_t)n * 32 * 3 + 64))) return rc;   // b^i | b^-i | t, then P in ntt_out
+        if ((rc = ctx->ntt_out.reserve((size_t)(n + 1) * 32))) return rc;
+        Fr* bpow = ctx->ntt_work.as<Fr>();
+        Fr* binvpow = bpow + n;
+        uint4* t = reinterpret_cast<uint4*>(binvpow + n);
+        const unsigned long long threads = (n + POW_SEQ - 1) / POW_SEQ;
+        LAUNCH(*ctx, ntt_pow_seq_kernel, (unsigned)((threads + 127) / 128), 128, 0, st, bpow, fr_from_bytes(bb),
+               (unsigned long long)n);
+        LAUNCH(*ctx, ntt_pow_seq_kernel, (unsigned)((threads + 127) / 128), 128, 0, st, binvpow, fr_from_bytes(binv),
+               (unsigned long long)n);
+        const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sms * 16);
+        LAUNCH(*ctx, kate_scale_kernel, grid, 256, 0, st, (const uint4*)d_a, bpow, t, (unsigned long long)n);
+        Fr zero;
+        memset(zero.v, 0, 32);
+        if ((rc = scan_run(*ctx, 1, t, n, zero, nullptr, ctx->ntt_out.p, n + 1, st))) return rc;
+        LAUNCH(*ctx, kate_finish_kernel, grid, 256, 0, st, ctx->ntt_out.as<uint4>(), binvpow, (uint4*)d_q,
+               (unsigned long long)n);
+    }
+    if (stream) return ll.mark_busy(st);
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_kate_division(const void* a, uint64_t n, const void* b, void* q) {
+    if (!a || !b || !q || n < 2) return fail(B2_ERR_ARG, "kate_division: bad arguments");
+    void* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)(2 * n) * 32));
+    cudaError_t e = cudaMemcpy(d, a, n * 32, cudaMemcpyHostToDevice);
+    int rc = e == cudaSuccess ? b2_kate_division_dev(d, n, b, (char*)d + n * 32, nullptr) : fail(B2_ERR_CUDA, "kate_division: upload failed");
+    if (rc == B2_OK && cudaMemcpy(q, (char*)d + n * 32, (n - 1) * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(B2_ERR_CUDA, "kate_division: download failed");
+    cudaFree(d);
+    return rc;
+}
+
+}  // extern "C"

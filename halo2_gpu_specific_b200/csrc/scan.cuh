@@ -156,3 +156,85 @@ __global__ void fr_vec_dev_kernel(const uint4* __restrict__ a, const uint4* __re
 }
 
 }  // namespace b2
+
+namespace b2 {
+
+// ---- eval_polynomial (halo2_proofs/src/arithmetic.rs:707-735) ----------------------------------------
+// sum_i a[i] * x^i for `columns` polynomials at one point.  Thread t of a column runs Horner over EVAL_C
+// consecutive coefficients and scales by x^(t * EVAL_C) (two-level table built by the caller: lo[j] = x^(j * EVAL_C)
+// for j < 2^EVAL_LO, hi[j] = x^(j * EVAL_C << EVAL_LO)); a block sums its threads and adds into out[column]
+// with one carry-safe atomic-free step: per-block partials are written and a second launch folds them.
+constexpr int EVAL_C = 32;
+constexpr int EVAL_T = 128;
+constexpr int EVAL_LO = 10;
+
+__global__ void __launch_bounds__(EVAL_T) eval_poly_partial_kernel(const uint4* __restrict__ polys, unsigned long long stride,
+                                                                  unsigned long long n, const Fr x, const Fr* __restrict__ lo,
+                                                                  const Fr* __restrict__ hi, uint4* __restrict__ partials,
+                                                                  uint32_t blocks_per_col) {
+    __shared__ uint4 sm[2 * EVAL_T];
+    const uint32_t col = blockIdx.y;
+    const unsigned long long t = (unsigned long long)blockIdx.x * EVAL_T + threadIdx.x;
+    const unsigned long long i0 = t * EVAL_C;
+    const uint4* a = polys + 2ull * col * stride;
+    Fr acc = Fr::zero();
+    if (i0 < n) {
+        const unsigned long long i1 = min(n, i0 + EVAL_C);
+        for (unsigned long long i = i1; i-- > i0;) acc = fp_add<FrParams>(fp_mul<FrParams>(acc, x), fp_load<FrParams>(a + 2ull * i));
+        const Fr p = fp_mul<FrParams>(fp_load_nc<FrParams>(lo + (t & ((1u << EVAL_LO) - 1u))),
+                                      fp_load_nc<FrParams>(hi + (t >> EVAL_LO)));
+        acc = fp_mul<FrParams>(acc, p);
+    }
+    fp_store<FrParams>(sm + 2 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = EVAL_T / 2; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) {
+            acc = fp_add<FrParams>(acc, fp_load<FrParams>(sm + 2 * (threadIdx.x + d)));
+            fp_store<FrParams>(sm + 2 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp_store<FrParams>(partials + 2ull * ((unsigned long long)col * blocks_per_col + blockIdx.x), acc);
+}
+
+__global__ void __launch_bounds__(EVAL_T) eval_poly_final_kernel(const uint4* __restrict__ partials, uint32_t blocks_per_col,
+                                                                uint4* __restrict__ out) {
+    __shared__ uint4 sm[2 * EVAL_T];
+    const uint32_t col = blockIdx.x;
+    Fr acc = Fr::zero();
+    for (uint32_t b = threadIdx.x; b < blocks_per_col; b += EVAL_T)
+        acc = fp_add<FrParams>(acc, fp_load<FrParams>(partials + 2ull * ((unsigned long long)col * blocks_per_col + b)));
+    fp_store<FrParams>(sm + 2 * threadIdx.x, acc);
+    __syncthreads();
+    for (uint32_t d = EVAL_T / 2; d >= 1; d >>= 1) {
+        if (threadIdx.x < d) {
+            acc = fp_add<FrParams>(acc, fp_load<FrParams>(sm + 2 * (threadIdx.x + d)));
+            fp_store<FrParams>(sm + 2 * threadIdx.x, acc);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) fp_store<FrParams>(out + 2ull * col, acc);
+}
+
+// ---- kate_division (arithmetic.rs:752-773): q = (a(X) - a(b)) / (X - b), q[j] = sum_{i > j} a[i] b^(i-j-1) ------
+// With P = prefix sums of a[i] * b^i (P[j+1] = sum_{i <= j}):  q[j] = (P[n] - P[j + 1]) * b^-(j + 1).
+// step 1: t[i] = a[i] * bpow[i];   (scan)   step 3 below.
+__global__ void kate_scale_kernel(const uint4* __restrict__ a, const Fr* __restrict__ bpow, uint4* __restrict__ t,
+                                  unsigned long long n) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+        fp_store<FrParams>(t + 2ull * i, fp_mul<FrParams>(fp_load<FrParams>(a + 2ull * i), fp_load_nc<FrParams>(bpow + i)));
+}
+__global__ void kate_finish_kernel(const uint4* __restrict__ P, const Fr* __restrict__ binvpow, uint4* __restrict__ q,
+                                   unsigned long long n) {
+    unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    const Fr total = fp_load<FrParams>(P + 2ull * n);
+    for (; j + 1 < n; j += stride) {
+        const Fr s = fp_sub<FrParams>(total, fp_load<FrParams>(P + 2ull * (j + 1)));
+        fp_store<FrParams>(q + 2ull * j, fp_mul<FrParams>(s, fp_load_nc<FrParams>(binvpow + j + 1)));
+    }
+}
+
+}  // namespace b2

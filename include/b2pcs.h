@@ -76,6 +76,19 @@ int b2_srs_len(b2_handle_t srs, size_t* n);
 int b2_srs_read(b2_handle_t srs, size_t offset, size_t count, void* out_affine64);
 int b2_srs_free(b2_handle_t srs);
 
+/* ---- Params::read / Params::write (poly/commitment.rs:241-294) ---------------------- */
+/* The params file holds g and g_lagrange as 32-byte compressed points (C::to_bytes / C::from_bytes of the pinned
+ * pairing crate: x as 32 little-endian bytes of the canonical integer, the parity of the canonical y in bit
+ * `sign_bit` of byte 31 -- 7 in the pasta / pairing_bn256 convention -- and the identity as 32 zero bytes).  The
+ * reference decompresses on the CPU (:262-273: one Fq square root per point); these take the file bytes as they are.
+ * An invalid encoding (x >= q, or x^3 + 3 not a square) fails with B2_ERR_ARG naming the point, where the reference
+ * panics on `Option::from(C::from_bytes(..)).unwrap()` (:270). */
+int b2_g1_decompress(const void* bytes32, size_t n, uint32_t sign_bit, void* out_affine64);
+int b2_g1_compress(const void* affine64, size_t n, uint32_t sign_bit, void* out_bytes32);
+/* file bytes -> resident SRS (the affine form never exists on the host) and back */
+int b2_srs_register_compressed(const void* bytes32, size_t n, uint32_t sign_bit, b2_handle_t* out);
+int b2_srs_read_compressed(b2_handle_t srs, size_t offset, size_t count, uint32_t sign_bit, void* out_bytes32);
+
 /* ---- MSM -------------------------------------------------------------------------- */
 /* sum_i scalars[i] * srs[offset + i], i < n.  max_bits bounds every scalar
  * (scalar < 2^max_bits); pass 254 (Fr::NUM_BITS) when unknown.  n == 0 or max_bits == 0
@@ -271,6 +284,19 @@ int b2_prefix_scan_dev(int op, const void* d_in, size_t n_in, const void* init, 
                        size_t n_out, void* stream);
 /* d_out[i] = d_a[i] op d_b[i] over Fr on device pointers; op: 0 mul, 1 add, 2 sub.  d_out may alias an input. */
 int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+
+/* ---- polynomial evaluation / division on resident coefficient forms --------------------- */
+/* eval_polynomial (arithmetic.rs:707-735): out[c] = sum_i poly_c[i] * point^i for `columns` polynomials of n
+ * coefficients (device, `stride` elements apart) at one point; the evaluations land on the host (columns * 32 B).
+ * This is what lets the coefficient forms stay in HBM after evaluate_h: the prover's evaluation phase
+ * (plonk/prover.rs:693-760) needs numbers, not polynomials. */
+int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t stride, uint64_t n, const void* point,
+                           void* out_host);
+int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* out);
+/* kate_division (arithmetic.rs:752-773): q = (a(X) - a(b)) / (X - b), n - 1 coefficients; q must not alias a.
+ * Used by the multiopen provers (poly/multiopen/gwc/prover.rs:158, shplonk/prover.rs:23). */
+int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, void* stream);
+int b2_kate_division(const void* a, uint64_t n, const void* b, void* q);
 
 /* ---- memory helpers --------------------------------------------------------------- */
 int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */

@@ -471,6 +471,18 @@ def eval_polynomial(poly: Sequence[int], point: int) -> int:
     return acc
 
 
+def kate_division(a: Sequence[int], b: int) -> List[int]:
+    """arithmetic.rs:752-773: a(X) divided by (X - b), remainder dropped."""
+    b = (-b) % R_MOD  # :758
+    q = [0] * (len(a) - 1)
+    tmp = 0
+    for j in range(len(q) - 1, -1, -1):  # :764-770 (q and a walked from the high end)
+        lead = (a[j + 1] - tmp) % R_MOD
+        q[j] = lead
+        tmp = lead * b % R_MOD
+    return q
+
+
 def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[int]:
     """arithmetic.rs:848-906 restated as plain Lagrange interpolation."""
     n = len(points)
@@ -496,8 +508,66 @@ def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[in
 # --------------------------------------------------------------------------
 # Params: restatement of poly/commitment.rs
 # --------------------------------------------------------------------------
+def fq_sqrt(a: int) -> Optional[int]:
+    """q = 3 mod 4: a^((q+1)/4) when a is a square"""
+    y = pow(a, (Q_MOD + 1) // 4, Q_MOD)
+    return y if y * y % Q_MOD == a % Q_MOD else None
+
+
+def g1_to_bytes(p: Point, sign_bit: int = 7) -> bytes:
+    """GroupEncoding::to_bytes of the pinned pairing crate.  [EXT] (SURVEY 8c): restated from the pasta /
+    pairing_bn256 convention -- x little-endian canonical, parity of canonical y in the top bit of byte 31,
+    identity = 32 zero bytes.  Byte-level parity with the reference's params files is unpinned."""
+    if p is None:
+        return bytes(32)
+    x, y = p
+    b = bytearray(x.to_bytes(32, "little"))
+    b[31] |= (y & 1) << sign_bit
+    return bytes(b)
+
+
+def g1_from_bytes(b: bytes, sign_bit: int = 7) -> Point:
+    """GroupEncoding::from_bytes (same convention); raises ValueError where the reference's
+    `Option::from(C::from_bytes(..)).unwrap()` panics (poly/commitment.rs:270)."""
+    assert len(b) == 32
+    t = bytearray(b)
+    sign = (t[31] >> sign_bit) & 1
+    t[31] &= ~(1 << sign_bit) & 0xFF
+    x = int.from_bytes(bytes(t), "little")
+    if x == 0 and sign == 0:
+        return None
+    if x >= Q_MOD:
+        raise ValueError("x is not canonical")
+    y = fq_sqrt((x * x * x + CURVE_B) % Q_MOD)
+    if y is None:
+        raise ValueError("not on the curve")
+    if (y & 1) != sign:
+        y = Q_MOD - y
+    return (x, y)
+
+
 class Params:
-    """poly/commitment.rs:23-29, unsafe_setup :56-124, commit* :129-222."""
+    """poly/commitment.rs:23-29, unsafe_setup :56-124, commit* :129-222, write / read :241-294."""
+
+    def write(self, additional_data: bytes = b"", sign_bit: int = 7) -> bytes:
+        """:241-253"""
+        out = bytearray(self.k.to_bytes(4, "little"))
+        for p in self.g:
+            out += g1_to_bytes(p, sign_bit)
+        for p in self.g_lagrange:
+            out += g1_to_bytes(p, sign_bit)
+        out += len(additional_data).to_bytes(4, "little") + additional_data
+        return bytes(out)
+
+    @classmethod
+    def read(cls, data: bytes, sign_bit: int = 7):
+        """:256-294 -> (k, g, g_lagrange, additional_data)"""
+        k = int.from_bytes(data[:4], "little")
+        n = 1 << k
+        pts = [g1_from_bytes(data[4 + 32 * i: 36 + 32 * i], sign_bit) for i in range(2 * n)]
+        off = 4 + 64 * n
+        ln = int.from_bytes(data[off:off + 4], "little")
+        return k, pts[:n], pts[n:], data[off + 4: off + 4 + ln]
 
     def __init__(self, k: int, s: int):
         assert k <= FR_S  # :60

@@ -211,3 +211,19 @@ def test_frozen_fixtures_match_both_oracles():
     assert o.g1_jacobian_decode(cref.best_multiexp(FIX["msm_n512_scalars"], FIX["msm_n512_bases"], 8)) == want
     assert o.g1_jacobian_decode(cref.best_multiexp(o.fr_encode(list(range(64))), FIX["params_k6_g_lagrange"], 8)) == \
         o.g1_jacobian_decode(FIX["params_k6_commit_lagrange"])
+
+
+def test_point_encoding_roundtrip_and_params_file():
+    """oracle restatement of GroupEncoding / Params::write / Params::read (poly/commitment.rs:241-294; [EXT] convention)"""
+    import random
+    from oracle import bn254 as o
+    rng = random.Random(3)
+    pts = [None, o.G1_GEN, o.g1_neg(o.G1_GEN)] + [o.g1_mul(o.G1_GEN, rng.randrange(1, o.R_MOD)) for _ in range(20)]
+    for sb in (7, 6):
+        for p in pts:
+            assert o.g1_from_bytes(o.g1_to_bytes(p, sb), sb) == p
+    assert o.g1_to_bytes(o.G1_GEN) == (1).to_bytes(32, "little")                 # y = 2 is even: no flag
+    assert o.g1_to_bytes(o.g1_neg(o.G1_GEN))[31] == 0x80 and o.g1_to_bytes(None) == bytes(32)
+    ref = o.Params(3, 77)
+    k, g, gl, extra = o.Params.read(ref.write(b"xyz"))
+    assert (k, g, gl, extra) == (3, ref.g, ref.g_lagrange, b"xyz")
