@@ -90,6 +90,7 @@ struct NttPlan {
     uint32_t mm[NTT_MAX_PASSES] = {0, 0, 0, 0};
     uint32_t tw_h = 0;
     Fr* tw_sub[NTT_MAX_PASSES] = {nullptr, nullptr, nullptr, nullptr};
+    Fr* tw_sub_shoup[NTT_MAX_PASSES] = {nullptr, nullptr, nullptr, nullptr};   // (w, floor(w 2^256 / r)) pairs
     Fr* tw_lo = nullptr;
     Fr* tw_hi = nullptr;         // unscaled
     Fr* tw_hi_scaled = nullptr;  // times divisor (pass 0 of an iNTT); == tw_hi when no divisor
@@ -170,6 +171,9 @@ int dev_get(DeviceCtx** out) {
         CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(ntt_pass_mont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        CK(cudaFuncSetAttribute(ntt_pass_mont_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        CK(cudaFuncSetAttribute(ntt_pass_mont_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(msm_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
@@ -712,12 +716,21 @@ int ntt_get_plan(Lane& ctx, const void* omega, const void* divisor, uint32_t log
         for (int j = 0; j < i; j++)
             if (pl->mm[j] == pl->mm[i]) {
                 pl->tw_sub[i] = pl->tw_sub[j];
+                pl->tw_sub_shoup[i] = pl->tw_sub_shoup[j];
                 found = true;
                 break;
             }
         if (found) continue;
         uint32_t cnt = pl->mm[i] >= 1 ? (1u << (pl->mm[i] - 1)) : 1u;
         if ((rc = ntt_table(ctx, pl, &pl->tw_sub[i], w, 1ull << (log_n - pl->mm[i]), cnt, false, none))) return rc;
+        {
+            void* p = nullptr;
+            CK(cudaMalloc(&p, (size_t)64 << pl->mm[i]));      // four 16-byte planes of 2^m entries
+            pl->owned.push_back(p);
+            pl->tw_sub_shoup[i] = (Fr*)p;
+            LAUNCH(ctx, ntt_shoup_table_kernel, ((1u << pl->mm[i]) + 127) / 128, 128, 0, ctx.stream,
+                   (const Fr*)pl->tw_sub[i], (uint4*)p, pl->mm[i]);
+        }
     }
     if (P > 1) {
         if ((rc = ntt_table(ctx, pl, &pl->tw_lo, w, 1ull, 1u << pl->tw_h, false, none))) return rc;
@@ -774,7 +787,8 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         a.npass = (uint32_t)pl->npass;
         for (int i = 0; i < NTT_MAX_PASSES; i++) a.mm[i] = pl->mm[i];
         a.tw_h = pl->tw_h;
-        a.tw_sub = pl->tw_sub[p];
+        static const bool use_shoup = !(getenv("B2_NTT_SHOUP") && atoi(getenv("B2_NTT_SHOUP")) == 0);
+        a.tw_sub = use_shoup ? pl->tw_sub_shoup[p] : pl->tw_sub[p];
         a.tw_lo = pl->tw_lo;
         a.tw_hi = first ? pl->tw_hi_scaled : pl->tw_hi;
         a.tw_full = first ? pl->tw_full : nullptr;
@@ -808,7 +822,8 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
             b.in = a.in + 2ull * c0 * a.in_col_stride;
             b.out = a.out + 2ull * c0 * a.out_col_stride;
             if (a.cl_log == 0) {
-                LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+                if (use_shoup) LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+                else LAUNCH(ctx, ntt_pass_mont_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
             } else {
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof cfg);
@@ -823,8 +838,13 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
                 attr[0].val.clusterDim.z = 1;
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
-                cudaError_t le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
-                                                 : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);
+                cudaError_t le;
+                if (use_shoup)
+                    le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
+                                         : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);
+                else
+                    le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_mont_cluster2_kernel, b)
+                                         : cudaLaunchKernelEx(&cfg, ntt_pass_mont_cluster4_kernel, b);
                 (*ctx.launch_counter)++;
                 if (le != cudaSuccess) return fail(B2_ERR_CUDA, "cluster NTT launch: %s", cudaGetErrorString(le));
             }
@@ -1503,7 +1523,8 @@ int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
 
 // ---- diagnostics
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out) {
-    if (!a || !b || !out || op < 0 || op > 3 || field < 0 || field > 1) return fail(B2_ERR_ARG, "field_vec: bad arguments");
+    if (!a || !b || !out || op < 0 || op > 4 || field < 0 || field > 1 || (op == 4 && field != 0))
+        return fail(B2_ERR_ARG, "field_vec: bad arguments");
     if (n == 0) return B2_OK;
     LaneLock ll;
     int rc = ll.acquire();
@@ -1550,6 +1571,31 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
     }
     if (modmuls_per_s) *modmuls_per_s = best;
     if (wide_macs_per_s) *wide_macs_per_s = best * 128.0;
+    return B2_OK;
+}
+
+int b2_shoup_probe(double* muls_per_s) {
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    cudaStream_t st = ctx->stream;
+    const int iters = 2000, ILP = 4;
+    const int blocks = ctx->sms * 8, threads = 256;
+    LAUNCH(*ctx, shoup_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<uint4>(), 50);  // warm-up
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, shoup_probe_kernel<ILP>, blocks, threads, 0, st, ctx->out96.as<uint4>(), iters);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        const double rate = (double)blocks * threads * (double)iters * ILP / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    if (muls_per_s) *muls_per_s = best;
     return B2_OK;
 }
 

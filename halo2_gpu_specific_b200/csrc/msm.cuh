@@ -25,6 +25,7 @@
 //                          (c doublings each), normalises to Z = 1
 #pragma once
 #include "curve.cuh"
+#include "fp_shoup.cuh"
 
 namespace b2 {
 
@@ -796,7 +797,13 @@ srs_synth_kernel(char* __restrict__ bases, unsigned long long n, unsigned long l
 }
 
 // ---------------------------------------------------------------- element-wise test kernels
-// op: 0 mul, 1 add, 2 sub, 3 sqr
+// op: 0 mul, 1 add, 2 sub, 3 sqr, 4 Shoup constant multiplication (Fr)
+template <class P>
+__device__ __forceinline__ Fp<P> field_vec_shoup(const Fp<P>& x, const Fp<P>& y) { return fp_mul<P>(x, y); }
+template <>
+__device__ __forceinline__ Fr field_vec_shoup<FrParams>(const Fr& x, const Fr& y) {
+    return fr_mul_shoup(x, fp_from_mont<FrParams>(y), fr_shoup_companion(y));
+}
 template <class P>
 __global__ void field_vec_kernel(const uint4* a, const uint4* b, uint4* o, unsigned long long n, int op) {
     const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -806,7 +813,10 @@ __global__ void field_vec_kernel(const uint4* a, const uint4* b, uint4* o, unsig
     case 0: r = fp_mul<P>(x, y); break;
     case 1: r = fp_add<P>(x, y); break;
     case 2: r = fp_sub<P>(x, y); break;
-    default: r = fp_sqr<P>(x); break;
+    case 3: r = fp_sqr<P>(x); break;
+    default:   // 4 (Fr only): x * y through the Shoup path, y treated as a Montgomery-form constant
+        r = field_vec_shoup(x, y);
+        break;
     }
     fp_store<P>(o + 2 * i, r);
 }
@@ -830,6 +840,27 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint4* sink, int iters)
 #pragma unroll
     for (int j = 1; j < ILP; j++) acc = fp_add<FqParams>(acc, x[j]);
     if (acc.v[0] == 0x12345678u && acc.v[7] == 0x9abcdef0u) fp_store<FqParams>(sink, acc);
+}
+
+// Same probe for the Shoup constant multiplication (NTT butterflies).
+template <int ILP>
+__global__ void __launch_bounds__(256) shoup_probe_kernel(uint4* sink, int iters) {
+    Fr x[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+        x[j] = Fr::one();
+        x[j].v[0] ^= threadIdx.x + j;
+    }
+    const Fr ym = Fr::r2();
+    const Fr y = fp_from_mont<FrParams>(ym), yp = fr_shoup_companion(ym);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) x[j] = fr_mul_shoup(x[j], y, yp);
+    }
+    Fr acc = x[0];
+#pragma unroll
+    for (int j = 1; j < ILP; j++) acc = fp_add<FrParams>(acc, x[j]);
+    if (acc.v[0] == 0x12345678u && acc.v[7] == 0x9abcdef0u) fp_store<FrParams>(sink, acc);
 }
 
 // FP64 FMA throughput probe (is the fp64 pipe a usable second multiplier on this part?)

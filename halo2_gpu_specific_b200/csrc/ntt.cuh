@@ -22,6 +22,7 @@
 #include <cooperative_groups.h>
 
 #include "fp.cuh"
+#include "fp_shoup.cuh"
 
 namespace b2 {
 
@@ -40,7 +41,8 @@ struct NttPassArgs {
     uint32_t pass, npass;
     uint32_t mm[NTT_MAX_PASSES];        // digit sizes m_1..m_P
     uint32_t tw_h;                      // split of the two-level table: e = hi * 2^tw_h + lo
-    const Fr* tw_sub;                   // w_{2^m}^j, j < 2^(m-1)
+    const Fr* tw_sub;                   // w_{2^m}^j, j < 2^(m-1) in Montgomery form, or the stage-major four-plane
+                                        // (w, floor(w 2^256 / r)) table of ntt_shoup_table_kernel (Shoup kernels)
     const Fr* tw_lo;                    // w_N^j, j < 2^tw_h
     const Fr* tw_hi;                    // w_N^(j * 2^tw_h) (times the divisor for pass 0 of an iNTT)
     const Fr* tw_full;                  // optional: w_N^e for e < N/2 (times the divisor), used by pass 0;
@@ -69,8 +71,51 @@ __device__ __forceinline__ void sm_st(uint4* lo, uint4* hi, uint32_t idx, const 
     hi[idx] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
 }
 
+// Shoup twiddle table of one digit size m, built from the Montgomery-form table tw_mont[j] = w_{2^m}^j:
+// stage-major (stage s = 1..m owns the 2^(s-1) entries w_{2^s}^jj at positions 2^(s-1) - 1 + jj) so that the
+// lanes of a warp, which hold consecutive jj, read consecutive entries; and split into four 16-byte planes
+// (w low / high half, floor(w 2^256 / r) low / high half), each 2^m entries long, so that every LDG.128 of a
+// warp is one contiguous 512-byte run.  (The stride-2^(m-s) gathers from a single table were the NTT's second
+// bottleneck: 5.8x the shared-memory wavefronts on the L1 data pipe.)
+__global__ void ntt_shoup_table_kernel(const Fr* __restrict__ tw_mont, uint4* __restrict__ planes, uint32_t m) {
+    const uint32_t pos = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t total = (1u << m) - 1u;
+    if (pos >= total) return;
+    const uint32_t s = 32u - __clz(pos + 1u);              // stage: 2^(s-1) <= pos + 1 < 2^s
+    const uint32_t jj = pos + 1u - (1u << (s - 1));
+    const Fr wm = fp_load<FrParams>(tw_mont + ((size_t)jj << (m - s)));
+    const Fr w = fp_from_mont<FrParams>(wm), wp = fr_shoup_companion(wm);
+    const size_t plane = (size_t)1 << m;
+    planes[pos] = make_uint4(w.v[0], w.v[1], w.v[2], w.v[3]);
+    planes[plane + pos] = make_uint4(w.v[4], w.v[5], w.v[6], w.v[7]);
+    planes[2 * plane + pos] = make_uint4(wp.v[0], wp.v[1], wp.v[2], wp.v[3]);
+    planes[3 * plane + pos] = make_uint4(wp.v[4], wp.v[5], wp.v[6], wp.v[7]);
+}
+
 __device__ __forceinline__ void ntt_bfly(Fr& a, Fr& b, const Fr& tw) {
     Fr t = fp_mul<FrParams>(b, tw);
+    b = fp_sub<FrParams>(a, t);
+    a = fp_add<FrParams>(a, t);
+}
+// Butterfly of stage s (1-based) of a 2^m-point sub-NTT with twiddle w_{2^s}^jj.
+// SHOUP = true: tw is the stage-major four-plane table of ntt_shoup_table_kernel and the product is the 92-MAC
+// constant multiplication of fp_shoup.cuh; false: tw[j] = w_{2^m}^j in Montgomery form, generic product.
+template <bool SHOUP>
+__device__ __forceinline__ void ntt_bfly_tab(Fr& a, Fr& b, const Fr* __restrict__ tw, uint32_t m, uint32_t s, uint32_t jj) {
+    Fr t;
+    if (SHOUP) {
+        const uint4* pl = reinterpret_cast<const uint4*>(tw) + ((1u << (s - 1)) - 1u + jj);
+        const size_t plane = (size_t)1 << m;
+        const uint4 w0 = __ldg(pl), w1 = __ldg(pl + plane), p0 = __ldg(pl + 2 * plane), p1 = __ldg(pl + 3 * plane);
+        Fr w, wp;
+        w.v[0] = w0.x; w.v[1] = w0.y; w.v[2] = w0.z; w.v[3] = w0.w;
+        w.v[4] = w1.x; w.v[5] = w1.y; w.v[6] = w1.z; w.v[7] = w1.w;
+        wp.v[0] = p0.x; wp.v[1] = p0.y; wp.v[2] = p0.z; wp.v[3] = p0.w;
+        wp.v[4] = p1.x; wp.v[5] = p1.y; wp.v[6] = p1.z; wp.v[7] = p1.w;
+        t = fr_mul_shoup(b, w, wp);
+    } else {
+        t = fp_mul<FrParams>(b, fp_load_nc<FrParams>(tw + ((size_t)jj << (m - s))));
+    }
     b = fp_sub<FrParams>(a, t);
     a = fp_add<FrParams>(a, t);
 }
@@ -81,7 +126,7 @@ __device__ __forceinline__ void ntt_bfly1(Fr& a, Fr& b) {  // twiddle == 1
 }
 
 // One group of R consecutive DIT stages (s0+1 .. s0+R) on the shared-memory tile.
-template <int R, bool FIRST>
+template <int R, bool FIRST, bool SHOUP>
 __device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* __restrict__ tw, uint32_t m,
                                          uint32_t mloc, uint32_t s0, uint32_t hs) {
     // m: log size of the whole sub-NTT (twiddle stride); mloc: log size of the part in this CTA
@@ -97,7 +142,6 @@ __device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* _
         for (int st = 0; st < R; st++) {
             // stage s = s0 + st + 1: partner differs in bit `st` of q; twiddle exponent
             // jj = low + (q & (2^st - 1)) * 2^s0, table index jj << (m - s)
-            const uint32_t sh = m - (s0 + st + 1);
 #pragma unroll
             for (int q = 0; q < E; q++) {
                 if (q & (1 << st)) continue;
@@ -106,8 +150,7 @@ __device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* _
                     ntt_bfly1(x[q], x[q | (1 << st)]);
                 } else {
                     const uint32_t jj = low + ((uint32_t)lowq << s0);
-                    Fr t = fp_load_nc<FrParams>(tw + ((size_t)jj << sh));
-                    ntt_bfly(x[q], x[q | (1 << st)], t);
+                    ntt_bfly_tab<SHOUP>(x[q], x[q | (1 << st)], tw, m, s0 + st + 1, jj);
                 }
             }
         }
@@ -140,7 +183,7 @@ __device__ __forceinline__ uint64_t ntt_digit_reverse(uint64_t v, const uint32_t
 // CTA, the last CL_LOG stages exchange through distributed shared memory.  This keeps 2-3 CTAs
 // resident per SM for 2^12 / 2^13-point digits (a single CTA with a 128 KB tile runs alone on its
 // SM and exposes its load / store latency), and lets k = 25, 26 run in two passes.
-template <int CL_LOG>
+template <int CL_LOG, bool SHOUP>
 __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     namespace cg = cooperative_groups;
     extern __shared__ uint4 ntt_smem[];
@@ -187,17 +230,17 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     uint32_t s0 = 0;
     {
         const uint32_t r = mloc < 3 ? mloc : 3;
-        if (r == 3) ntt_step<3, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
-        else if (r == 2) ntt_step<2, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
-        else if (r == 1) ntt_step<1, true>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        if (r == 3) ntt_step<3, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        else if (r == 2) ntt_step<2, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        else if (r == 1) ntt_step<1, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
         s0 = r;
         __syncthreads();
     }
     while (s0 < mloc) {
         const uint32_t r = (mloc - s0) < 3 ? (mloc - s0) : 3;
-        if (r == 3) ntt_step<3, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
-        else if (r == 2) ntt_step<2, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
-        else ntt_step<1, false>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        if (r == 3) ntt_step<3, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        else if (r == 2) ntt_step<2, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        else ntt_step<1, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
         s0 += r;
         __syncthreads();
     }
@@ -222,14 +265,12 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
             const uint32_t half = Nloc >> 1;
             const uint32_t i0 = is_b ? half : 0u;
             const uint32_t jj_hi = (ra & ((1u << q) - 1u)) << mloc;   // p_a mod 2^(mloc+q), high part
-            const uint32_t sh = m - (mloc + q + 1);
             for (uint32_t t = threadIdx.x; t < half; t += blockDim.x) {
                 const uint32_t i = i0 + t;
                 const uint32_t sw = ntt_swz(i, hs);
                 Fr xa = sm_ld(a_lo, a_hi, sw);
                 Fr xb = sm_ld(b_lo, b_hi, sw);
-                Fr tw = fp_load_nc<FrParams>(a.tw_sub + ((size_t)(jj_hi | i) << sh));
-                ntt_bfly(xa, xb, tw);
+                ntt_bfly_tab<SHOUP>(xa, xb, a.tw_sub, m, mloc + q + 1, jj_hi | i);
                 sm_st(a_lo, a_hi, sw, xa);
                 sm_st(b_lo, b_hi, sw, xb);
             }
@@ -284,9 +325,13 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     }
 }
 
-__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) { ntt_pass_impl<0>(a); }
-__global__ void __launch_bounds__(256) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1>(a); }
-__global__ void __launch_bounds__(256) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2>(a); }
+__global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) { ntt_pass_impl<0, true>(a); }
+__global__ void __launch_bounds__(256, 2) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, true>(a); }
+__global__ void __launch_bounds__(256, 2) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
+// Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
+__global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
+__global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }
+__global__ void __launch_bounds__(256) ntt_pass_mont_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, false>(a); }
 
 // out[j] = base^(j * mult) * (scale if has_scale), j < count
 __global__ void ntt_pow_table_kernel(Fr* out, const Fr base, unsigned long long mult, uint32_t count,

@@ -311,13 +311,17 @@ int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
 int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 
 /* ---- diagnostics used by tests / bench -------------------------------------------- */
-/* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a). */
+/* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a),
+ * 4 (Fr only) the same product as op 0 computed through the NTT's Shoup constant-multiplication path. */
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out);
 /* Measures the device's sustained 32x32->64 multiply-accumulate rate with the kernels'
  * own instruction mix (carry-chained IMAD.WIDE Montgomery products); returns modular
  * multiplications per second and wide MACs/s counted as 128 per product (64 product + 64
  * reduction terms, the accounting of SURVEY.md section 8d). */
 int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s);
+/* Same probe for the constant multiplication the NTT butterflies use (Shoup: 92 wide MACs + 23 narrow
+ * products per multiplication by a precomputed twiddle instead of 128 + 8). */
+int b2_shoup_probe(double* muls_per_s);
 /* FP64 FMA rate of the device (diagnostic: documents why the fp64 pipe is / is not a usable
  * second multiplier for the bignum kernels on this part). */
 int b2_dfma_probe(double* dfma_per_s);

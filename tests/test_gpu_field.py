@@ -40,6 +40,28 @@ def test_field_ops_edge_values(gpu, field):
         assert np.array_equal(_vec(gpu, field, op, a, b), cref.field_vec(field, op, a, b)), op
 
 
+def test_shoup_constant_multiplication_equals_montgomery_product(gpu):
+    """op 4 = the NTT butterflies' constant multiplication (fp_shoup.cuh): derive (w, floor(w 2^256 / r)) from the
+    Montgomery-form operand on the device, multiply, reduce: must be the same residue as the generic product."""
+    n = 1 << 16
+    a = cref.random_fr_mont(n, 0xC0)
+    b = cref.random_fr_mont(n, 0xC1)
+    assert np.array_equal(_vec(gpu, 0, 4, a, b), cref.field_vec(0, 0, a, b))
+    p = o.R_MOD
+    vals = [0, 1, 2, p - 1, p - 2, (1 << 253), p - 3, 0xFFFFFFFF, 0xFFFFFFFFFFFFFFFF, (1 << 128) - 1, (1 << 224) - 1,
+            p >> 1, (p >> 1) + 1, int("ffffffff00000000" * 4, 16) % p, int("00000000ffffffff" * 4, 16) % p]
+    pairs = [(x, y) for x in vals for y in vals]
+    a = np.array([o._to_limbs(x) for x, _ in pairs], dtype=np.uint64)
+    b = np.array([o._to_limbs(y) for _, y in pairs], dtype=np.uint64)
+    assert np.array_equal(_vec(gpu, 0, 4, a, b), cref.field_vec(0, 0, a, b))
+
+
+def test_shoup_probe_reports_a_rate(gpu):
+    muls = ctypes.c_double()
+    gpu.check(gpu.lib().b2_shoup_probe(ctypes.byref(muls)))
+    assert muls.value > 1e9
+
+
 def test_imad_probe_reports_a_rate(gpu):
     macs, muls = ctypes.c_double(), ctypes.c_double()
     gpu.check(gpu.lib().b2_imad_probe(ctypes.byref(macs), ctypes.byref(muls)))
