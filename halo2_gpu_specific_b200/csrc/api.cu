@@ -813,7 +813,7 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         // 13-bit digits on a cluster of 4 (profiles/r1_ncu_summary.md)
         a.cl_log = !use_clusters ? 0 : (a.m >= 13 ? 2 : (a.m >= 11 ? 1 : 0));
         const uint32_t mloc = a.m - a.cl_log;
-        const uint32_t threads = std::max(32u, 1u << (mloc >= 3 ? mloc - 3 : 0));
+        const uint32_t threads = std::max(32u, 1u << (mloc >= NTT_RMAX ? mloc - NTT_RMAX : 0));
         const size_t smem = ((size_t)32 << mloc);
         const uint64_t lines = N >> a.m;
         for (uint64_t c0 = 0; c0 < cols; c0 += 65535) {

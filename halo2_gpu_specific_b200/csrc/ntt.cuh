@@ -27,6 +27,12 @@
 namespace b2 {
 
 constexpr int NTT_MAX_PASSES = 4;
+#ifndef NTT_RMAX
+#define NTT_RMAX 3      // DIT stages per shared-memory round trip (2^NTT_RMAX elements per thread)
+#endif
+#ifndef NTT_CL_MINB
+#define NTT_CL_MINB 2      // resident cluster-kernel CTAs per SM the register allocation must allow
+#endif
 
 struct NttPassArgs {
     const uint4* in;
@@ -229,7 +235,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     // ---- local DIT stages, three per shared-memory round trip ----
     uint32_t s0 = 0;
     {
-        const uint32_t r = mloc < 3 ? mloc : 3;
+        const uint32_t r = mloc < NTT_RMAX ? mloc : NTT_RMAX;
         if (r == 3) ntt_step<3, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
         else if (r == 2) ntt_step<2, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
         else if (r == 1) ntt_step<1, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
@@ -237,7 +243,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
         __syncthreads();
     }
     while (s0 < mloc) {
-        const uint32_t r = (mloc - s0) < 3 ? (mloc - s0) : 3;
+        const uint32_t r = (mloc - s0) < NTT_RMAX ? (mloc - s0) : NTT_RMAX;
         if (r == 3) ntt_step<3, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
         else if (r == 2) ntt_step<2, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
         else ntt_step<1, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
@@ -326,8 +332,8 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
 }
 
 __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) { ntt_pass_impl<0, true>(a); }
-__global__ void __launch_bounds__(256, 2) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, true>(a); }
-__global__ void __launch_bounds__(256, 2) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, true>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
 // Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
 __global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
 __global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }

@@ -14,7 +14,7 @@ res = {"shoup": os.environ.get("B2_NTT_SHOUP", "1")}
 mm, sm = ctypes.c_double(), ctypes.c_double()
 L.b2_imad_probe(None, ctypes.byref(mm)); L.b2_shoup_probe(ctypes.byref(sm))
 res["montgomery_mul_per_s"] = mm.value; res["shoup_mul_per_s"] = sm.value
-for k, cols in ((18, 64), (20, 64), (22, 64), (24, 16)):
+for k, cols in [(int(a), 64 if int(a) < 24 else 16) for a in os.environ.get("KS", "18,20,22,24").split(",")]:
     n = 1 << k
     dom = h2.EvaluationDomain(5, k)
     buf = E.DeviceBuffer(cols * n)
