@@ -1523,7 +1523,7 @@ int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {
 
 // ---- diagnostics
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out) {
-    if (!a || !b || !out || op < 0 || op > 4 || field < 0 || field > 1 || (op == 4 && field != 0))
+    if (!a || !b || !out || op < 0 || op > 6 || field < 0 || field > 1 || (op == 4 && field != 0))
         return fail(B2_ERR_ARG, "field_vec: bad arguments");
     if (n == 0) return B2_OK;
     LaneLock ll;

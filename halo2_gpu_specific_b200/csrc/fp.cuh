@@ -284,6 +284,59 @@ __device__ __forceinline__ Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
     return r;
 }
 
+// Second product of a fused pair: adds c[even]*d to E and c[odd]*d to O in place (same alignment as after
+// mm_row0 / mm_row: E at positions 0..7, O at positions 1..8); E's carry-out goes to O[7].
+__device__ __forceinline__ void mm_row_acc(uint32_t (&E)[8], uint32_t (&O)[8], const uint32_t (&c)[8], uint32_t d) {
+    asm("mad.lo.cc.u32 %8, %17, %24, %8;\n\t madc.hi.cc.u32 %9, %17, %24, %9;\n\t"
+        "madc.lo.cc.u32 %10, %19, %24, %10;\n\t madc.hi.cc.u32 %11, %19, %24, %11;\n\t"
+        "madc.lo.cc.u32 %12, %21, %24, %12;\n\t madc.hi.cc.u32 %13, %21, %24, %13;\n\t"
+        "madc.lo.cc.u32 %14, %23, %24, %14;\n\t madc.hi.u32 %15, %23, %24, %15;\n\t"
+        "mad.lo.cc.u32 %0, %16, %24, %0;\n\t madc.hi.cc.u32 %1, %16, %24, %1;\n\t"
+        "madc.lo.cc.u32 %2, %18, %24, %2;\n\t madc.hi.cc.u32 %3, %18, %24, %3;\n\t"
+        "madc.lo.cc.u32 %4, %20, %24, %4;\n\t madc.hi.cc.u32 %5, %20, %24, %5;\n\t"
+        "madc.lo.cc.u32 %6, %22, %24, %6;\n\t madc.hi.cc.u32 %7, %22, %24, %7;\n\t"
+        "addc.u32 %15, %15, 0;"
+        : "+r"(E[0]), "+r"(E[1]), "+r"(E[2]), "+r"(E[3]), "+r"(E[4]), "+r"(E[5]), "+r"(E[6]), "+r"(E[7]),
+          "+r"(O[0]), "+r"(O[1]), "+r"(O[2]), "+r"(O[3]), "+r"(O[4]), "+r"(O[5]), "+r"(O[6]), "+r"(O[7])
+        : "r"(c[0]), "r"(c[1]), "r"(c[2]), "r"(c[3]), "r"(c[4]), "r"(c[5]), "r"(c[6]), "r"(c[7]), "r"(d));
+}
+
+// r = (a*b + c*d) * 2^-256 mod p with ONE Montgomery reduction (one m*p row per 32 bits for both products):
+// 192 + 8 multiply-accumulates instead of 256 + 16.  Inputs < p; the accumulators stay below 3p*2^32 and the
+// result below p*(1 + 2p/2^256) < 1.38p, so one conditional subtraction finishes it.
+template <class P>
+__device__ __forceinline__ Fp<P> fp_mul2_add(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    uint32_t A[8], B[8];
+    mm_row0(A, B, a.v, b.v[0]); mm_row_acc(A, B, c.v, d.v[0]); mm_redc<P>(A, B);
+    mm_row(B, A, a.v, b.v[1]);  mm_row_acc(B, A, c.v, d.v[1]); mm_redc<P>(B, A);
+    mm_row(A, B, a.v, b.v[2]);  mm_row_acc(A, B, c.v, d.v[2]); mm_redc<P>(A, B);
+    mm_row(B, A, a.v, b.v[3]);  mm_row_acc(B, A, c.v, d.v[3]); mm_redc<P>(B, A);
+    mm_row(A, B, a.v, b.v[4]);  mm_row_acc(A, B, c.v, d.v[4]); mm_redc<P>(A, B);
+    mm_row(B, A, a.v, b.v[5]);  mm_row_acc(B, A, c.v, d.v[5]); mm_redc<P>(B, A);
+    mm_row(A, B, a.v, b.v[6]);  mm_row_acc(A, B, c.v, d.v[6]); mm_redc<P>(A, B);
+    mm_row(B, A, a.v, b.v[7]);  mm_row_acc(B, A, c.v, d.v[7]); mm_redc<P>(B, A);
+    Fp<P> r;
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, 0;"
+        : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]),
+          "=r"(r.v[7])
+        : "r"(A[0]), "r"(A[1]), "r"(A[2]), "r"(A[3]), "r"(A[4]), "r"(A[5]), "r"(A[6]), "r"(A[7]),
+          "r"(B[1]), "r"(B[2]), "r"(B[3]), "r"(B[4]), "r"(B[5]), "r"(B[6]), "r"(B[7]));
+    fp_reduce_once<P>(r.v);
+    return r;
+}
+// r = a*b - c*d (same cost: c is negated first)
+template <class P>
+__device__ __forceinline__ Fp<P> fp_mul2_sub(const Fp<P>& a, const Fp<P>& b, const Fp<P>& c, const Fp<P>& d) {
+    return fp_mul2_add<P>(a, b, fp_neg<P>(c), d);
+}
+
 template <class P>
 __device__ __forceinline__ Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
 

@@ -797,7 +797,7 @@ srs_synth_kernel(char* __restrict__ bases, unsigned long long n, unsigned long l
 }
 
 // ---------------------------------------------------------------- element-wise test kernels
-// op: 0 mul, 1 add, 2 sub, 3 sqr, 4 Shoup constant multiplication (Fr)
+// op: 0 mul, 1 add, 2 sub, 3 sqr, 4 Shoup constant multiplication (Fr), 5 / 6 fused x*y +- y*y
 template <class P>
 __device__ __forceinline__ Fp<P> field_vec_shoup(const Fp<P>& x, const Fp<P>& y) { return fp_mul<P>(x, y); }
 template <>
@@ -814,9 +814,11 @@ __global__ void field_vec_kernel(const uint4* a, const uint4* b, uint4* o, unsig
     case 1: r = fp_add<P>(x, y); break;
     case 2: r = fp_sub<P>(x, y); break;
     case 3: r = fp_sqr<P>(x); break;
-    default:   // 4 (Fr only): x * y through the Shoup path, y treated as a Montgomery-form constant
+    case 4:   // (Fr only): x * y through the Shoup path, y treated as a Montgomery-form constant
         r = field_vec_shoup(x, y);
         break;
+    case 5: r = fp_mul2_add<P>(x, y, y, y); break;   // x*y + y*y with one reduction
+    default: r = fp_mul2_sub<P>(x, y, y, y); break;  // 6: x*y - y*y
     }
     fp_store<P>(o + 2 * i, r);
 }

@@ -312,7 +312,8 @@ int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 
 /* ---- diagnostics used by tests / bench -------------------------------------------- */
 /* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a),
- * 4 (Fr only) the same product as op 0 computed through the NTT's Shoup constant-multiplication path. */
+ * 4 (Fr only) the same product as op 0 computed through the NTT's Shoup constant-multiplication path,
+ * 5 a*b + b*b and 6 a*b - b*b through the fused two-product reduction the MSM point additions use. */
 int b2_field_vec(int field, int op, const void* a, const void* b, size_t n, void* out);
 /* Measures the device's sustained 32x32->64 multiply-accumulate rate with the kernels'
  * own instruction mix (carry-chained IMAD.WIDE Montgomery products); returns modular

@@ -56,6 +56,19 @@ def test_shoup_constant_multiplication_equals_montgomery_product(gpu):
     assert np.array_equal(_vec(gpu, 0, 4, a, b), cref.field_vec(0, 0, a, b))
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_fused_two_product_reduction(gpu, field):
+    """ops 5 / 6: a*b +- b*b with one Montgomery reduction (fp_mul2_add / fp_mul2_sub, the Y3 of the point additions)."""
+    p = o.Q_MOD if field else o.R_MOD
+    vals = [0, 1, 2, p - 1, p - 2, (1 << 253), p - 3, 0xFFFFFFFF, (1 << 128) - 1, p >> 1, (p >> 1) + 1]
+    pairs = [(x, y) for x in vals for y in vals]
+    a = np.concatenate([np.array([o._to_limbs(x) for x, _ in pairs], dtype=np.uint64), cref.random_fr_mont(1 << 14, 0xD0 + field)])
+    b = np.concatenate([np.array([o._to_limbs(y) for _, y in pairs], dtype=np.uint64), cref.random_fr_mont(1 << 14, 0xD2 + field)])
+    ab, bb = cref.field_vec(field, 0, a, b), cref.field_vec(field, 3, b, b)
+    assert np.array_equal(_vec(gpu, field, 5, a, b), cref.field_vec(field, 1, ab, bb))
+    assert np.array_equal(_vec(gpu, field, 6, a, b), cref.field_vec(field, 2, ab, bb))
+
+
 def test_shoup_probe_reports_a_rate(gpu):
     muls = ctypes.c_double()
     gpu.check(gpu.lib().b2_shoup_probe(ctypes.byref(muls)))
