@@ -350,7 +350,9 @@ def run_engine(args):
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
                                 "(profiles/r1_ncu_summary.md); algorithmic gather bytes 3.7e9: DRAM is ~10 % busy",
                 "model": f"128 MACs x 10 mul-equivalents x n x W = {mac_per_launch:.3e} 32x32->64 MACs per launch "
-                         f"(SURVEY 8d), duration {acc:.3f} ms (CUDA events, mean of {len(acc_ms)})",
+                         f"(SURVEY 8d), duration {acc:.3f} ms (CUDA events, mean of {len(acc_ms)}); the kernel issues "
+                         "9.44 product-equivalents per mixed add (the two products of Y3 share one reduction), so "
+                         "the multiplier pipe itself is busy 0.944x this fraction",
                 "peak_source": "b2_imad_probe in this run: carry-chained IMAD.WIDE Montgomery products, "
                                f"{muls.value / 1e9:.1f} G modmul/s x 128",
                 "share_of_step": acc / phases_avg.get("total", acc),
@@ -430,7 +432,9 @@ def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
                          "model": "64 B per element per transform (one read + one write)", "peak_source": peak_src},
         "roofline_int": {"bound": "int", "achieved": macs / (ms * 1e-3) / 1e12, "peak": modmuls_per_s * 128 / 1e12,
                          "unit": "TMAC/s", "frac": (macs / (ms * 1e-3)) / (modmuls_per_s * 128),
-                         "model": "64 * log2(n) MACs per element (SURVEY 8d)"},
+                         "model": "64 * log2(n) MACs per element (SURVEY 8d); the butterflies multiply by precomputed "
+                                  "twiddles with Shoup's method (92 wide MACs + 23 narrow products instead of 128 + "
+                                  "8 per product), so the multiplier pipe does ~0.81x the work this model charges"},
         "e2e": {"value": ecols * n / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "columns": ecols,
                 "h2d_bytes": ecols * n * 32, "d2h_bytes": ecols * n * 32,
                 "api": "EvaluationDomain.lagrange_to_coeff_batch (pinned host columns, iNTT)"},

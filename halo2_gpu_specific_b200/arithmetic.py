@@ -278,3 +278,17 @@ def kate_division(a: np.ndarray, b) -> np.ndarray:
     out = np.empty((p.shape[0] - 1, 4), dtype=np.uint64)
     check(lib().b2_kate_division(ptr(p), p.shape[0], ptr(as_fr1(b)), ptr(out)))
     return out
+
+
+def poly_combine(polys, v) -> np.ndarray:
+    """poly/multiopen/gwc/prover.rs:47-56: fold `batch = batch * v + poly` over the polynomials opened at one point.
+    polys: sequence of (n, 4) coefficient arrays (same n); v: (4,) Montgomery -> (n, 4)"""
+    require_gpu()
+    cols = [as_fr(p) for p in polys]
+    if not cols or any(c.shape != cols[0].shape for c in cols):
+        raise B2Error(B2_ERR_ARG, "poly_combine needs at least one polynomial and equal lengths")
+    import ctypes
+    arr = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+    out = np.empty_like(cols[0])
+    check(lib().b2_poly_combine(arr, len(cols), cols[0].shape[0], ptr(as_fr1(v)), ptr(out)))
+    return out

@@ -243,6 +243,69 @@ int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, 
     return B2_OK;
 }
 
+// (plain v, floor(v 2^256 / r)) of a Montgomery-form scalar, on the host (see fr_shoup_companion)
+static void hr_shoup_pair(const void* v_mont, Fr* plain, Fr* comp) {
+    uint64_t vm[4], one[4] = {1, 0, 0, 0}, pl[4];
+    memcpy(vm, v_mont, 32);
+    hr_mul(pl, vm, one);
+    memcpy(plain->v, pl, 32);
+    static const uint64_t NINV[4] = {0xc2e1f593efffffffULL, 0x6586864b4c6911b3ULL, 0xe39a982899062391ULL,
+                                     0x73f82f1d0d8341b2ULL};   // -r^-1 mod 2^256
+    uint64_t o[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        unsigned __int128 carry = 0;
+        for (int j = 0; i + j < 4; j++) {
+            unsigned __int128 t = (unsigned __int128)vm[i] * NINV[j] + o[i + j] + carry;
+            o[i + j] = (uint64_t)t;
+            carry = t >> 64;
+        }
+    }
+    memcpy(comp->v, o, 32);
+}
+
+int b2_poly_combine_dev(const void* const* d_polys, uint32_t m, uint64_t n, const void* v, void* d_out, void* stream) {
+    if (!d_polys || !v || !d_out || m == 0 || n == 0) return fail(B2_ERR_ARG, "poly_combine: bad arguments");
+    for (uint32_t j = 0; j < m; j++)
+        if (!d_polys[j]) return fail(B2_ERR_ARG, "poly_combine: null polynomial %u", j);
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    if ((rc = ll.order_after_busy(st))) return rc;
+    if ((rc = ctx->qtab.reserve((size_t)m * sizeof(void*)))) return rc;
+    // the pointer table is read by the kernel after this call may have returned (stream != NULL): stage it in
+    // pageable memory the runtime copies synchronously
+    CK(cudaMemcpyAsync(ctx->qtab.p, d_polys, (size_t)m * sizeof(void*), cudaMemcpyHostToDevice, st));
+    Fr vp, vc;
+    hr_shoup_pair(v, &vp, &vc);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->sms * 16);
+    LAUNCH(*ctx, poly_combine_kernel, grid, 256, 0, st, (const uint4* const*)ctx->qtab.p, m, (unsigned long long)n, vp, vc,
+           (uint4*)d_out);
+    if (stream) return ll.mark_busy(st);
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
+int b2_poly_combine(const void* const* polys, uint32_t m, uint64_t n, const void* v, void* out) {
+    if (!polys || !v || !out || m == 0 || n == 0) return fail(B2_ERR_ARG, "poly_combine: bad arguments");
+    void* d = nullptr;
+    CK(cudaMalloc(&d, (size_t)(m + 1) * n * 32));
+    std::vector<const void*> ptrs(m);
+    int rc = B2_OK;
+    for (uint32_t j = 0; j < m && rc == B2_OK; j++) {
+        ptrs[j] = (char*)d + (size_t)j * n * 32;
+        if (!polys[j] || cudaMemcpy((void*)ptrs[j], polys[j], n * 32, cudaMemcpyHostToDevice) != cudaSuccess)
+            rc = fail(B2_ERR_CUDA, "poly_combine: upload of polynomial %u failed", j);
+    }
+    char* d_out = (char*)d + (size_t)m * n * 32;
+    if (rc == B2_OK) rc = b2_poly_combine_dev(ptrs.data(), m, n, v, d_out, nullptr);
+    if (rc == B2_OK && cudaMemcpy(out, d_out, n * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(B2_ERR_CUDA, "poly_combine: download failed");
+    cudaFree(d);
+    return rc;
+}
+
 int b2_kate_division(const void* a, uint64_t n, const void* b, void* q) {
     if (!a || !b || !q || n < 2) return fail(B2_ERR_ARG, "kate_division: bad arguments");
     void* d = nullptr;

@@ -7,6 +7,7 @@
 // the z columns never visit the host between the expression kernel and the commitment.
 #pragma once
 #include "fp.cuh"
+#include "fp_shoup.cuh"
 
 namespace b2 {
 
@@ -234,6 +235,26 @@ __global__ void kate_finish_kernel(const uint4* __restrict__ P, const Fr* __rest
     for (; j + 1 < n; j += stride) {
         const Fr s = fp_sub<FrParams>(total, fp_load<FrParams>(P + 2ull * (j + 1)));
         fp_store<FrParams>(q + 2ull * j, fp_mul<FrParams>(s, fp_load_nc<FrParams>(binvpow + j + 1)));
+    }
+}
+
+// ---- multiopen batching (poly/multiopen/gwc/prover.rs:47-56; shplonk/prover.rs does the same fold) -----------------
+// out[i] = sum_j v^(m-1-j) * polys[j][i]: the Horner fold `poly_batch = poly_batch * v + poly` over the m polynomials
+// opened at one point, element by element.  v is the same for every element, so the product is the Shoup constant
+// multiplication (w = v as a plain integer, wp = floor(v 2^256 / r)); one pass over the m polynomials, nothing
+// written but the result.
+__global__ void __launch_bounds__(256)
+poly_combine_kernel(const uint4* const* __restrict__ polys, uint32_t m, unsigned long long n, const Fr v_plain,
+                    const Fr v_comp, uint4* __restrict__ out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        Fr acc = fp_load_nc<FrParams>(polys[0] + 2ull * i);
+        for (uint32_t j = 1; j < m; j++) {
+            const Fr pj = fp_load_nc<FrParams>(polys[j] + 2ull * i);
+            acc = fp_add<FrParams>(fr_mul_shoup(acc, v_plain, v_comp), pj);
+        }
+        fp_store<FrParams>(out + 2ull * i, acc);
     }
 }
 

@@ -298,6 +298,14 @@ int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* ou
 int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, void* stream);
 int b2_kate_division(const void* a, uint64_t n, const void* b, void* q);
 
+/* Multiopen batching (poly/multiopen/gwc/prover.rs:47-56 and its cuda variant :58-140, which runs the same fold on
+ * the GPU through the Bn256_Fr_eval_mul_c / _eval_sum kernels; shplonk/prover.rs folds the same way):
+ * out[i] = sum_j v^(m-1-j) * polys[j][i], i.e. poly_batch = poly_batch * v + poly over the m polynomials opened at
+ * one point.  `polys` is a HOST array of m pointers (device pointers for _dev, host pointers otherwise), n
+ * coefficients each; v: 32 B Montgomery on the host.  d_out may alias polys[0] only. */
+int b2_poly_combine_dev(const void* const* d_polys, uint32_t m, uint64_t n, const void* v, void* d_out, void* stream);
+int b2_poly_combine(const void* const* polys, uint32_t m, uint64_t n, const void* v, void* out);
+
 /* ---- memory helpers --------------------------------------------------------------- */
 int b2_host_alloc(size_t bytes, void** out);   /* page-locked host memory */
 int b2_host_free(void* p);

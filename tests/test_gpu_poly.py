@@ -56,3 +56,41 @@ def test_kate_division_large_identity(gpu):
     q = arithmetic.kate_division(a, enc([b])[0])
     ev = lambda p, x: o.fr_decode(arithmetic.eval_polynomial(p, enc([x])[0])[None])[0]  # noqa: E731
     assert (ev(q, r) * (r - b) + ev(a, b)) % R == ev(a, r)
+
+
+@pytest.mark.parametrize("m,n", [(1, 5), (2, 1), (3, 257), (17, 4096)])
+def test_poly_combine_matches_the_horner_fold(gpu, m, n):
+    """gwc/prover.rs:47-56: poly_batch = poly_batch * v + poly, element by element"""
+    rng = random.Random(m * 1000 + n)
+    polys = [[rng.randrange(R) for _ in range(n)] for _ in range(m)]
+    for v in (0, 1, R - 1, rng.randrange(R)):
+        want = [0] * n
+        for p in polys:
+            want = [(w * v + c) % R for w, c in zip(want, p)]
+        got = arithmetic.poly_combine([enc(p) for p in polys], enc([v])[0])
+        assert np.array_equal(got, enc(want))
+
+
+def test_poly_combine_resident_then_open(gpu):
+    """One opening of the multiopen argument on resident polynomials: fold, evaluate, divide; the witness polynomial
+    satisfies w(r) * (r - z) + batch(z) == batch(r)."""
+    n, m = 1 << 16, 12
+    polys = cref.random_fr_mont(n * m, 0xB20000A3).reshape(m, n, 4)
+    buf = DeviceBuffer(n * (m + 2)).upload(polys)
+    rng = random.Random(11)
+    v, z, r = rng.randrange(R), rng.randrange(R), rng.randrange(R)
+    L = _lib.lib()
+    ptrs = (ctypes.c_void_p * m)(*[buf.ptr + j * n * 32 for j in range(m)])
+    d_batch, d_w = buf.ptr + m * n * 32, buf.ptr + (m + 1) * n * 32
+    _lib.check(L.b2_poly_combine_dev(ptrs, m, n, _lib.ptr(enc([v])[0]), ctypes.c_void_p(d_batch), None))
+    _lib.check(L.b2_kate_division_dev(ctypes.c_void_p(d_batch), n, _lib.ptr(enc([z])[0]), ctypes.c_void_p(d_w), None))
+    batch = buf.download(n, m * n)
+    assert np.array_equal(batch, arithmetic.poly_combine(list(polys), enc([v])[0]))
+    want0 = 0
+    for j in range(m):
+        want0 = (want0 * v + o.fr_decode(polys[j][:1])[0]) % R
+    assert o.fr_decode(batch[:1])[0] == want0
+    w = buf.download(n - 1, (m + 1) * n)
+    ev = lambda p, x: o.fr_decode(arithmetic.eval_polynomial(p, enc([x])[0])[None])[0]  # noqa: E731
+    assert (ev(w, r) * (r - z) + ev(batch, z)) % R == ev(batch, r)
+    buf.free()

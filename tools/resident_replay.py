@@ -13,8 +13,11 @@ to be driven once the callers on both sides of the commitment path are on the de
   * evaluate_h (8f rank 1) walks the extended domain coset by coset from the resident coefficient forms
     (fixed and sigma polynomials are resident since keygen), h(X) stays on the device and its D pieces are
     committed from there (b2_msm_dev);
-  * what the CPU side of the reference still needs afterwards (coefficient forms for the multiopen
-    evaluations, the h pieces) is copied back ONCE and reported as its own line.
+  * the evaluation phase and the multiopen argument (eval_polynomial of every query, the per-point fold
+    poly_batch = poly_batch * v + poly, kate_division and the witness commitments) run on the resident coefficient
+    forms too (b2_eval_polynomial_dev, b2_poly_combine_dev, b2_kate_division_dev, b2_msm_dev): only evaluations
+    (32 B) and commitments (96 B) go back.  --host-multiopen restores the earlier behaviour (copy the coefficient
+    forms back once for a CPU-side phase) for comparison.
 
 Phases are serialised as in the prover (the transcript squeezes a challenge between them).  Synthetic data:
 16-bit advice values, uniform field elements elsewhere; the gate program is tools/quotient_bench.py's.
@@ -54,6 +57,9 @@ def main():
                     help="re-transform the fixed and sigma polynomials in every proof instead of keeping their cosets "
                          "resident since keygen (pk.fixed_cosets / permutation cosets, plonk/keygen.rs, are what the "
                          "reference's CPU path keeps too)")
+    ap.add_argument("--host-multiopen", action="store_true",
+                    help="round-1 behaviour: copy the coefficient forms back for a CPU-side evaluation / multiopen phase "
+                         "instead of evaluating, folding and dividing them on the device")
     a = ap.parse_args()
     _lib.require_gpu()
     _lib.set_device(0)
@@ -103,8 +109,13 @@ def main():
     big[:] = rng.integers(0, 2**64, size=(pool, n, 4), dtype=np.uint64)
     big[:, :, 3] &= np.uint64((1 << 60) - 1)
     small_tbl = np.stack([_fr.to_mont(v) for v in range(1 << 16)])
-    small = _lib.pinned_empty((pool, n, 4))
-    for i in range(pool):
+    spool = 32          # advice-like columns: a longer contiguous pinned run keeps the copy / MSM pipeline of one
+                        # b2_commit_batch_resident call full (the reference's advice Vec<Polynomial> is one such run)
+    small = _lib.pinned_empty((spool, n, 4))
+    for i in range(spool):
+        if i >= pool:
+            small[i] = small[i % pool]
+            continue
         small[i] = small_tbl[rng.integers(0, 1 << 16, size=n)]
     small[:, ::3] = 0
     back = _lib.pinned_empty((pool, n, 4))                      # landing zone of the final copy-back
@@ -133,9 +144,10 @@ def main():
         done = 0
         # the pinned pool holds `pool` distinct columns: consecutive pool entries are contiguous, so send
         # them in contiguous runs
+        plen = src.shape[0]
         while done < count:
-            run = min(pool - (done % pool), count - done)
-            cols = src[done % pool: done % pool + run]
+            run = min(plen - (done % plen), count - done)
+            cols = src[done % plen: done % plen + run]
             _lib.check(L.b2_commit_batch_resident(params.g_lagrange.handle, vp(cols.ctypes.data), 0, vp(slot_ptr(name, done)),
                                                   run, n, bits, 1 if ifft else 0, vp(dom.omega_inv.ctypes.data),
                                                   vp(dom.ifft_divisor.ctypes.data), k, vp(out[done:].ctypes.data)))
@@ -260,6 +272,53 @@ def main():
         _lib.check(L.b2_g1_normalize(vp(out.ctypes.data), sh["D"]))
         return out
 
+    # ---- evaluation phase + multiopen on the resident coefficient forms (plonk/prover.rs:693-850,
+    # poly/multiopen/gwc/prover.rs:27-177): the CPU side needs numbers and points only
+    x_pt = _fr.to_mont(0x1F2E3D4C5B6A79881F2E3D4C5B6A7988 % R)
+    x_next = _fr.to_mont(0x1F2E3D4C5B6A79881F2E3D4C5B6A7988 * dom._omega % R)
+    x_last = _fr.to_mont(0x1F2E3D4C5B6A79881F2E3D4C5B6A7988 * pow(dom._omega, n - 6, R) % R)
+    v_ch = _fr.to_mont(0x0123456789ABCDEF0FEDCBA987654321 % R)
+    n_adv_next = sh["A"] // 4                          # advice columns also queried at the next row
+    groups_x = ["advice", "instance", "fixed", "sigma", "perm_z", "lookup_z", "lookup_m", "shuffle_z"]
+
+    def open_sets():
+        at_x = [slot_ptr(g, i) for g in groups_x for i in range(slots[g][1])] + \
+               [hcoef.ptr + i * n * 32 for i in range(sh["D"])]
+        at_next = [slot_ptr("advice", i) for i in range(n_adv_next)] + \
+                  [slot_ptr(g, i) for g in ("perm_z", "lookup_z", "shuffle_z") for i in range(slots[g][1])]
+        at_last = [slot_ptr("perm_z", i) for i in range(sh["P"] - 1)]
+        return [(x_pt, at_x), (x_next, at_next), (x_last, at_last)]
+
+    def evaluate_all():
+        """eval_polynomial of every query (plonk/prover.rs:703-790): contiguous slot groups, one call per group and point"""
+        cnt = 0
+        for pt, names in ((x_pt, groups_x), (x_next, ("perm_z", "lookup_z", "shuffle_z"))):
+            for g in names:
+                c = slots[g][1]
+                out = np.empty((c, 4), dtype=np.uint64)
+                _lib.check(L.b2_eval_polynomial_dev(vp(slot_ptr(g)), c, n, n, vp(pt.ctypes.data), vp(out.ctypes.data)))
+                cnt += c
+        out = np.empty((max(n_adv_next, sh["D"], sh["P"]), 4), dtype=np.uint64)
+        _lib.check(L.b2_eval_polynomial_dev(vp(slot_ptr("advice")), n_adv_next, n, n, vp(x_next.ctypes.data), vp(out.ctypes.data)))
+        _lib.check(L.b2_eval_polynomial_dev(vp(slot_ptr("perm_z")), sh["P"] - 1, n, n, vp(x_last.ctypes.data), vp(out.ctypes.data)))
+        _lib.check(L.b2_eval_polynomial_dev(vp(hcoef.ptr), sh["D"], n, n, vp(x_pt.ctypes.data), vp(out.ctypes.data)))
+        return cnt + n_adv_next + sh["P"] - 1 + sh["D"]
+
+    def multiopen():
+        """gwc: per point, poly_batch = fold by v; witness = kate_division(poly_batch, point); commit"""
+        sets = open_sets()
+        out = np.zeros((len(sets), 12), dtype=np.uint64)
+        batch, wit = cos.ptr, cos.ptr + n * 32
+        for i, (pt, ptrs) in enumerate(sets):
+            arr = (vp * len(ptrs))(*ptrs)
+            _lib.check(L.b2_poly_combine_dev(arr, len(ptrs), n, vp(v_ch.ctypes.data), vp(batch), None))
+            _lib.check(L.b2_kate_division_dev(vp(batch), n, vp(pt.ctypes.data), vp(wit), None))
+            _lib.check(L.b2_msm_dev(params.g.handle, 0, vp(wit), n - 1, 254, vp(d96.ptr), None))
+            L.b2_synchronize()
+            _lib.check(L.b2_memcpy_d2h(vp(out[i:].ctypes.data), vp(d96.ptr), 96))
+        _lib.check(L.b2_g1_normalize(vp(out.ctypes.data), len(sets)))
+        return sum(len(p) for _, p in sets)
+
     def copy_back():
         """coefficient forms the CPU side uses for the multiopen evaluations + the h pieces"""
         cnt = 0
@@ -280,6 +339,7 @@ def main():
         return time.perf_counter() - t, out
 
     results = []
+    n_evals = n_opened = ncopy = 0
     for rep in range(a.reps + 1):
         ph = {}
         ph["1_instance_commit_ifft"], _ = phase(lambda: commit_resident(big, sh["I"], "instance", 254, True))
@@ -296,8 +356,13 @@ def main():
         ph["9_evaluate_h"], _ = phase(evaluate_h)
         ph["10_h_to_coeff"], _ = phase(h_to_coeff)
         ph["10_h_commits"], _ = phase(commit_h_pieces)
-        ph["11_copy_back_for_multiopen"], ncopy = phase(copy_back)
-        ph["12_multiopen_commits"], _ = phase(lambda: [params.commit(c[0]) for c in batch_of(big, sh["R"])])
+        if a.host_multiopen:
+            ph["11_copy_back_for_multiopen"], ncopy = phase(copy_back)
+            ph["12_multiopen_commits"], _ = phase(lambda: [params.commit(c[0]) for c in batch_of(big, sh["R"])])
+        else:
+            ncopy = 0
+            ph["11_evaluations_on_device"], n_evals = phase(evaluate_all)
+            ph["12_multiopen_on_device"], n_opened = phase(multiopen)
         ph["total"] = sum(ph.values())
         results.append(ph)
     best = min(results[1:], key=lambda p: p["total"])
@@ -306,7 +371,10 @@ def main():
            "key_cosets_resident": keep_key_cosets,
            "resident_GiB": (2 * n_polys + 3 + sh["perm_cols"] + sh["P"] + 8 + ((n_key + 3) * nc if keep_key_cosets else 0))
                            * n * 32 / 2**30,
-           "h2d_GiB": (sh["I"] + sh["A"] + sh["L"] + 1 + sh["R"] + (0 if keep_key_cosets else 3 * nc)) * n * 32 / 2**30,
+           "h2d_GiB": (sh["I"] + sh["A"] + sh["L"] + 1 + (sh["R"] if a.host_multiopen else 0)
+                       + (0 if keep_key_cosets else 3 * nc)) * n * 32 / 2**30,
+           "multiopen": "host (coefficient forms copied back)" if a.host_multiopen else
+                        {"where": "device", "evaluations": n_evals, "polynomials_folded": n_opened, "points": sh["R"]},
            "d2h_GiB": ncopy * n * 32 / 2**30,
            "program": prog.info(),
            "excluded": "CPU-side protocol logic (witness synthesis, the logup multiplicities, transcript hashing, "
