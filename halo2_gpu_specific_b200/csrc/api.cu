@@ -76,6 +76,29 @@ struct Buf {
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
 
+// page-locked host staging (grow-only): small results are copied here asynchronously and handed to the caller
+// after the stream sync.  A cudaMemcpyAsync into PAGEABLE caller memory blocks the host until the producing
+// kernels finish, which serialises every lane pipeline behind it.
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return B2_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes < 4096 ? 4096 : bytes + (bytes >> 2);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(B2_ERR_OOM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+        }
+        cap = want;
+        return B2_OK;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
 struct Srs {
     int device;
     char* d;            // n affine points
@@ -122,6 +145,8 @@ struct Lane {
     Buf qtab, qspill;
     // batch inversion / prefix scans
     Buf scan_tmp, scan_tot;
+    // pinned landing zone of small device-to-host results (commitments of a batch)
+    PinnedBuf h_stage;
     // timing
     cudaEvent_t ev[16];
     cudaEvent_t busy;            // last work enqueued on a caller-provided stream (async _dev calls)
@@ -1384,6 +1409,8 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     const size_t col_bytes = n * 32;
     if (max_bits > 254) max_bits = 254;
     const size_t nl = set.lanes.size();
+    if ((rc = ctx->h_stage.reserve((size_t)columns * 96))) return rc;
+    char* h_pts = ctx->h_stage.as<char>();
     CK(cudaEventRecord(ctx->ev[8], ctx->stream));
     // one column per step, lanes round-robin: copy-in of column i+1 and copy-out of column i-1 overlap
     // the MSM (+ iNTT) of column i
@@ -1411,7 +1438,7 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
             if ((rc = msm_run_split(*ln, s, 0, dcol, n, max_bits, ln->out96.p, st, false, c < nl)))
                 return rc;
         }
-        CK(cudaMemcpyAsync((char*)out_jac96 + c * 96, ln->out96.p, 96, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(h_pts + c * 96, ln->out96.p, 96, cudaMemcpyDeviceToHost, st));
         if (do_ifft) {
             if ((rc = ntt_run_dev(*ln, pl, dcol, n, n, dcol, n, n, ln->ntt_work.p, 1, nullptr, nullptr, st)))
                 return rc;
@@ -1436,6 +1463,7 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     ctx->last_kernel_ms = 0;
     g_last.total_ms = ms;
     g_last.kernel_ms = 0;
+    memcpy(out_jac96, h_pts, (size_t)columns * 96);
     for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");
     return B2_OK;
