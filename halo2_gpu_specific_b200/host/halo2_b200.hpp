@@ -175,6 +175,33 @@ inline void gpu_ifft(std::vector<Fr>& a, const Fr& omega, uint32_t log_n, const 
     check(b2_gpu_ifft(a.data(), &omega, log_n, &divisor), "b2_gpu_ifft");
 }
 
+// arithmetic.rs:707-735
+inline Fr eval_polynomial(const std::vector<Fr>& poly, const Fr& point) {
+    if (poly.empty()) return Fr{{0, 0, 0, 0}};
+    Fr out;
+    check(b2_eval_polynomial(poly.data(), poly.size(), &point, &out), "b2_eval_polynomial");
+    return out;
+}
+// arithmetic.rs:752-773: (a(X) - a(b)) / (X - b)
+inline std::vector<Fr> kate_division(const std::vector<Fr>& a, const Fr& b) {
+    if (a.size() < 2) throw std::runtime_error("kate_division needs at least two coefficients");
+    std::vector<Fr> q(a.size() - 1);
+    check(b2_kate_division(a.data(), a.size(), &b, q.data()), "b2_kate_division");
+    return q;
+}
+// poly/multiopen/gwc/prover.rs:47-56: poly_batch = poly_batch * v + poly over the polynomials opened at one point
+inline std::vector<Fr> poly_combine(const std::vector<const std::vector<Fr>*>& polys, const Fr& v) {
+    if (polys.empty()) throw std::runtime_error("poly_combine needs at least one polynomial");
+    std::vector<const void*> ptrs;
+    for (const auto* p : polys) {
+        if (p->size() != polys[0]->size()) throw std::runtime_error("poly_combine: lengths differ");
+        ptrs.push_back(p->data());
+    }
+    std::vector<Fr> out(polys[0]->size());
+    check(b2_poly_combine(ptrs.data(), (uint32_t)ptrs.size(), out.size(), &v, out.data()), "b2_poly_combine");
+    return out;
+}
+
 // ---------------------------------------------------------------------------------------------
 // poly/domain.rs:24-149
 class EvaluationDomain {

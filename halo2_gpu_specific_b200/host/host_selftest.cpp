@@ -8,7 +8,7 @@
 
 using namespace halo2_b200;
 
-static Fr eval_polynomial(const std::vector<Fr>& poly, const Fr& x) {  // arithmetic.rs:707-711
+static Fr host_eval(const std::vector<Fr>& poly, const Fr& x) {  // arithmetic.rs:707-711, on the CPU
     Fr acc = {{0, 0, 0, 0}};
     for (size_t i = poly.size(); i-- > 0;) {
         acc = fr::mul(acc, x);
@@ -66,7 +66,22 @@ int main() {
     // coefficient form evaluates back to the Lagrange values: b(omega^i) == a[i]
     for (uint64_t i = 0; i < n; i += 7) {
         Fr x = fr::pow_vartime(domain.omega, i);
-        if (!fr::eq(eval_polynomial(b, x), a[i])) { std::printf("FAIL iFFT consistency at %llu\n", (unsigned long long)i); return 1; }
+        if (!fr::eq(host_eval(b, x), a[i])) { std::printf("FAIL iFFT consistency at %llu\n", (unsigned long long)i); return 1; }
+    }
+    // one opening of the multiopen argument (gwc/prover.rs:47-160): fold a and b by v, divide by (X - z):
+    // w(r) * (r - z) + batch(z) == batch(r)
+    {
+        const Fr v = fr::from_u64(0x1234567), z = fr::from_u64(0x89abcdef), r = fr::from_u64(0x31415926);
+        std::vector<Fr> batch = poly_combine({&a, &b}, v);
+        for (uint64_t i = 0; i < n; i += 5) {   // batch[i] = a[i] * v + b[i]
+            std::vector<Fr> two = {b[i], a[i]};
+            if (!fr::eq(host_eval(two, v), batch[i])) { std::printf("FAIL poly_combine at %llu\n", (unsigned long long)i); return 1; }
+        }
+        std::vector<Fr> w = kate_division(batch, z);
+        const Fr lhs = fr::mul(halo2_b200::eval_polynomial(w, r), fr::sub(r, z));
+        const Fr rhs = fr::sub(halo2_b200::eval_polynomial(batch, r), halo2_b200::eval_polynomial(batch, z));
+        if (!fr::eq(lhs, rhs)) { std::printf("FAIL kate_division identity\n"); return 1; }
+        if (!fr::eq(halo2_b200::eval_polynomial(batch, r), host_eval(batch, r))) { std::printf("FAIL eval_polynomial\n"); return 1; }
     }
     // coset round trip with j = 5
     EvaluationDomain d5(5, K);

@@ -227,3 +227,21 @@ def test_point_encoding_roundtrip_and_params_file():
     ref = o.Params(3, 77)
     k, g, gl, extra = o.Params.read(ref.write(b"xyz"))
     assert (k, g, gl, extra) == (3, ref.g, ref.g_lagrange, b"xyz")
+
+
+def test_shoup_generator_emulation_and_committed_header():
+    """tools/gen_shoup.py: the carry chains of the Shoup constant multiplication, executed limb by limb with PTX
+    add.cc / madc semantics, reproduce a*w - q*r with q at most 2 below floor(a*w/r) (no carry lost), and the committed
+    csrc/fp_shoup.cuh is exactly what the generator prints."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_shoup", os.path.join(root, "tools", "gen_shoup.py"))
+    gs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gs)
+    g = gs.build()
+    c = gs.count(g)
+    assert c["mad.lo"] == 92 + 16 and c["mad.hi"] + c["mul.hi"] == 92 + 7
+    assert gs.selftest(g, n_random=2000) >= 2000
+    with open(os.path.join(root, "halo2_gpu_specific_b200", "csrc", "fp_shoup.cuh")) as f:
+        assert f.read() == gs.render(g)

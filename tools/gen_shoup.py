@@ -271,13 +271,13 @@ __device__ __forceinline__ Fr fr_shoup_companion(const Fr& wm) {{
     return hdr
 
 
-def selftest(g):
+def selftest(g, n_random=20000):
     r = R_MOD
     pp = BETA - r
     random.seed(5)
     edge = [0, 1, 2, r - 1, r - 2, (1 << 224) - 1, (1 << 253), M32, (1 << 64) - 1, r >> 1,
             int('ffffffff00000000' * 4, 16) % r, int('00000000ffffffff' * 4, 16) % r]
-    cases = [(a, w) for a in edge for w in edge] + [(random.randrange(r), random.randrange(r)) for _ in range(20000)]
+    cases = [(a, w) for a in edge for w in edge] + [(random.randrange(r), random.randrange(r)) for _ in range(n_random)]
     for a, w in cases:
         wp = (w << 256) // r
         env = {}
