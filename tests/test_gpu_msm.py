@@ -243,13 +243,13 @@ def test_synthetic_srs_points(gpu):
     srs.free()
 
 
-@pytest.mark.parametrize("logn,bits", [(20, 254), (22, 254), (22, 16)])
+@pytest.mark.parametrize("logn,bits", [(20, 254), (22, 254), (22, 16), (24, 254)])
 def test_full_size_property(gpu, logn, bits):
     """BASELINE sizes: MSM(s, [h_i]G) must equal [sum s_i h_i mod r] G (linearity; O(n) host check)"""
     n = 1 << logn
     seed = 0xB2000003
     srs = Srs.synthetic(n, 0, seed)
-    if logn == 22:
+    if logn >= 22:
         srs.precompute()
     if bits == 254:
         scalars = cref.random_fr_mont(n, seed)
