@@ -12,8 +12,9 @@ per GPU.  What is sharded and what is exchanged:
               (the 32-byte hand-over of z[last] between permutation sets is not modelled across ranks)  no collective
   phase  8    every rank inverse-transforms its own advice / m columns                                no collective
   exchange B  all-gather of the coefficient forms of every witness-dependent polynomial              NCCL, 97 * 2^k * 32 B
-  phase  9    evaluate_h: rows of the extended domain split coset-major (parallel.quotient_tasks); all-gather of the
-              h slices; extended_to_coeff on every rank                                              NCCL, 2^(k+2) * 32 B
+  phase  9    evaluate_h: rows of the extended domain split coset-major (parallel.quotient_tasks); ranks that share a
+              coset split its transforms and swap the halves point-to-point; all-gather of the h slices;
+              extended_to_coeff on every rank                                  NCCL, 2^(k+2) * 32 B (+ P2P 97/2 * 2^k * 32 B)
   phase 10    the D pieces of h are committed on D different ranks                                    no collective
   phase 11    evaluations: every rank evaluates its block of each polynomial group                    no collective
   phase 12    multiopen: the fold poly_batch = poly_batch * v + poly is split by COEFFICIENT range (it is element-wise),
@@ -73,6 +74,10 @@ def main():
     ap.add_argument("--k", type=int, default=22)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--out", default="")
+    ap.add_argument("--j", type=int, default=5, help="EvaluationDomain degree parameter (5: four cosets; 3: two cosets, "
+                                                     "which lets 4 ranks exercise the shared-coset path)")
+    ap.add_argument("--no-split-transforms", action="store_true",
+                    help="ranks that share a coset each transform all of its polynomials (no point-to-point exchange)")
     a = ap.parse_args()
     rank, world, local = (int(os.environ.get(v, d)) for v, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
     torch.cuda.set_device(local)
@@ -83,9 +88,9 @@ def main():
     L = _lib.lib()
     k = a.k
     n = 1 << k
-    dom = h2.EvaluationDomain(5, k)
+    dom = h2.EvaluationDomain(a.j, k)
     nc = 1 << (dom.extended_k - k)
-    sh = dict(A=64, I=1, F=32, L=8, S=12, H=4, P=8, D=4, R=3, perm_cols=24)
+    sh = dict(A=64, I=1, F=32, L=8, S=12, H=4, P=8, D=dom.quotient_poly_degree, R=3, perm_cols=24)
     lookups = (2, 2, 2, 2, 1, 1, 1, 1)
     n_z = sh["P"] + sh["S"] + sh["H"]
     for cnt in (sh["A"], sh["L"], n_z, n, nc * n):
@@ -269,12 +274,37 @@ def main():
     challenges = [(i + 2) * 0x123456789ABCDEF % R for i in range(prog.n_challenges)]
     tasks = parallel.quotient_tasks(nc, n, world, rank)
 
+    # ranks sharing a coset (world > number of cosets): each transforms a share of the witness polynomials and the
+    # group swaps the shares over NVLink (point-to-point), instead of every rank transforming all of them
+    share = max(1, world // nc)
+    grp_first = (rank // share) * share
+    n_wit = n_polys - n_key
+
+    def coset_transform(c):
+        g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
+        if share == 1 or a.no_split_transforms:
+            E.coeff_to_coset_dev(dom, coef.ptr + n_key * n * 32, n_wit, g_c, cos.ptr + n_key * n * 32)
+            return
+        bounds = [parallel.shard_range(n_wit, share, j) for j in range(share)]
+        lo, hi = bounds[rank - grp_first]
+        E.coeff_to_coset_dev(dom, coef.ptr + (n_key + lo) * n * 32, hi - lo, g_c, cos.ptr + (n_key + lo) * n * 32)
+        L.b2_synchronize()
+        ops = []
+        for j, (plo, phi) in enumerate(bounds):
+            peer = grp_first + j
+            if peer == rank:
+                continue
+            ops.append(dist.P2POp(dist.isend, cos.rows((n_key + lo) * n, (hi - lo) * n), peer))
+            ops.append(dist.P2POp(dist.irecv, cos.rows((n_key + plo) * n, (phi - plo) * n), peer))
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        torch.cuda.synchronize()
+
     def evaluate_h():
         loaded, written = None, 0
         for c, begin, count in tasks:
             if c != loaded:
-                g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
-                E.coeff_to_coset_dev(dom, coef.ptr + n_key * n * 32, n_polys - n_key, g_c, cos.ptr + n_key * n * 32)
+                coset_transform(c)
                 loaded = c
             fx, adv, ins, aux = tables[c]
             prog.eval(k, 1, fx, adv, ins, aux, challenges, hloc.ptr, x0=pow(dom._ext_omega, c, R), x_step=dom._omega,
