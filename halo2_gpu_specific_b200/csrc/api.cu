@@ -920,6 +920,30 @@ int copy2d(void* dst, uint64_t dst_stride, const void* src, uint64_t src_stride,
     return B2_OK;
 }
 
+// instruction-rate probes: best of three timed launches of a dependent-product kernel
+template <class K>
+int run_probe(Lane* ctx, K kernel, double* out) {
+    cudaStream_t st = ctx->stream;
+    const int iters = 2000, ILP = 4;
+    const int blocks = ctx->sms * 8, threads = 256;
+    kernel<<<blocks, threads, 0, st>>>(ctx->out96.as<uint4>(), 50);   // warm-up
+    (*ctx->launch_counter)++;
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        kernel<<<blocks, threads, 0, st>>>(ctx->out96.as<uint4>(), iters);
+        (*ctx->launch_counter)++;
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        const double rate = (double)blocks * threads * (double)iters * ILP / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    *out = best;
+    return B2_OK;
+}
+
 }  // namespace
 
 // ============================================================================ C ABI
@@ -1600,6 +1624,27 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s) {
     if (modmuls_per_s) *modmuls_per_s = best;
     if (wide_macs_per_s) *wide_macs_per_s = best * 128.0;
     return B2_OK;
+}
+
+int b2_mul_probe(int kind, double* per_s) {
+    if (!per_s || kind < 0 || kind > 4) return fail(B2_ERR_ARG, "mul_probe: kind 0..4");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    switch (kind) {
+    case 0: return run_probe(ctx, imad_probe_kernel<4>, per_s);
+    case 1: return run_probe(ctx, shoup_probe_kernel<4>, per_s);
+#ifdef B2_FP_GEN
+    case 2: return run_probe(ctx, mul_probe_kernel<4, 2>, per_s);
+    case 3: return run_probe(ctx, mul_probe_kernel<4, 3>, per_s);
+#else
+    case 2:
+    case 3: return fail(B2_ERR_ARG, "mul_probe: kinds 2 and 3 need a build with -DB2_FP_GEN (tools/gen_fp.py variants)");
+#endif
+    default: return run_probe(ctx, mul_probe_kernel<4, 4>, per_s);
+    }
 }
 
 int b2_shoup_probe(double* muls_per_s) {

@@ -254,9 +254,9 @@ __device__ __forceinline__ void mm_redc(uint32_t (&E)[8], uint32_t (&O)[8]) {
           "n"(P::p7));
 }
 
-// r = a*b*2^-256 mod p, fully reduced.  Inputs < p.
+// r = a*b*2^-256 mod p, fully reduced.  Inputs < p.  (Interleaved product / reduction rows: 128 + 8 MACs.)
 template <class P>
-__device__ __forceinline__ Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+__device__ __forceinline__ Fp<P> fp_mul_cios(const Fp<P>& a, const Fp<P>& b) {
     uint32_t A[8], B[8];
     mm_row0(A, B, a.v, b.v[0]); mm_redc<P>(A, B);
     mm_row(B, A, a.v, b.v[1]);  mm_redc<P>(B, A);
@@ -337,8 +337,34 @@ __device__ __forceinline__ Fp<P> fp_mul2_sub(const Fp<P>& a, const Fp<P>& b, con
     return fp_mul2_add<P>(a, b, fp_neg<P>(c), d);
 }
 
+// Which product the kernels use: the interleaved one above.  tools/gen_fp.py also generates a Montgomery squaring
+// (100 MACs) and a Karatsuba product (112 MACs) in separated-operand-scanning form (fp_gen.cuh, compiled with
+// -DB2_FP_GEN, selected with -DB2_FP_MUL_KARA / -DB2_FP_SQR_SOS).  Measured on B200 (b2_mul_probe): 62.3 and 67.2
+// G products/s against 68.1 for this one, and msm_accumulate 10.2 ms instead of 8.75: the saved multiplier slots are
+// eaten by ptxas turning the carry-sink additions into IMAD.X on the same pipe and by the longer dependent addition
+// chains (295 / 284 instructions per product instead of 182), so they stay out of the default build.
+#ifdef B2_FP_GEN
+}  // namespace b2
+#include "fp_gen.cuh"
+namespace b2 {
+#endif
+
 template <class P>
-__device__ __forceinline__ Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
+__device__ __forceinline__ Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
+#if defined(B2_FP_GEN) && defined(B2_FP_MUL_KARA)
+    return fp_mul_kara<P>(a, b);
+#else
+    return fp_mul_cios<P>(a, b);
+#endif
+}
+template <class P>
+__device__ __forceinline__ Fp<P> fp_sqr(const Fp<P>& a) {
+#if defined(B2_FP_GEN) && defined(B2_FP_SQR_SOS)
+    return fp_sqr_sos<P>(a);
+#else
+    return fp_mul<P>(a, a);
+#endif
+}
 
 // Montgomery form -> canonical integer (multiply by 1)
 template <class P>

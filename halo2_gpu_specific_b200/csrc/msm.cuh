@@ -836,7 +836,34 @@ __global__ void __launch_bounds__(256) imad_probe_kernel(uint4* sink, int iters)
     Fq y = Fq::r2();
     for (int i = 0; i < iters; i++) {
 #pragma unroll
-        for (int j = 0; j < ILP; j++) x[j] = fp_mul<FqParams>(x[j], y);
+        for (int j = 0; j < ILP; j++) x[j] = fp_mul_cios<FqParams>(x[j], y);   // the schoolbook mix: the roofline's denominator
+    }
+    Fq acc = x[0];
+#pragma unroll
+    for (int j = 1; j < ILP; j++) acc = fp_add<FqParams>(acc, x[j]);
+    if (acc.v[0] == 0x12345678u && acc.v[7] == 0x9abcdef0u) fp_store<FqParams>(sink, acc);
+}
+
+// Same probe for the generated variants: KIND 2 = fp_mul_kara, 3 = fp_sqr_sos, 4 = fp_mul2_add (two products, one reduction)
+template <int ILP, int KIND>
+__global__ void __launch_bounds__(256) mul_probe_kernel(uint4* sink, int iters) {
+    Fq x[ILP];
+#pragma unroll
+    for (int j = 0; j < ILP; j++) {
+        x[j] = Fq::one();
+        x[j].v[0] ^= threadIdx.x + j;
+    }
+    Fq y = Fq::r2();
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < ILP; j++) {
+#ifdef B2_FP_GEN
+            if (KIND == 2) x[j] = fp_mul_kara<FqParams>(x[j], y);
+            else if (KIND == 3) x[j] = fp_sqr_sos<FqParams>(x[j]);
+            else
+#endif
+                x[j] = fp_mul2_add<FqParams>(x[j], y, y, x[j]);
+        }
     }
     Fq acc = x[0];
 #pragma unroll

@@ -331,6 +331,11 @@ int b2_imad_probe(double* wide_macs_per_s, double* modmuls_per_s);
 /* Same probe for the constant multiplication the NTT butterflies use (Shoup: 92 wide MACs + 23 narrow
  * products per multiplication by a precomputed twiddle instead of 128 + 8). */
 int b2_shoup_probe(double* muls_per_s);
+/* Rates of the other field products, same harness: kind 0 = interleaved Montgomery product (= b2_imad_probe),
+ * 1 = Shoup constant product, 4 = two products under one reduction (fp_mul2_add, 192 MACs; counted as ONE call);
+ * 2 = Karatsuba Montgomery product (112 MACs) and 3 = Montgomery squaring (100 MACs) exist only in builds with
+ * -DB2_FP_GEN (generated variants that measured slower, see csrc/fp.cuh) and return B2_ERR_ARG otherwise. */
+int b2_mul_probe(int kind, double* per_s);
 /* FP64 FMA rate of the device (diagnostic: documents why the fp64 pipe is / is not a usable
  * second multiplier for the bignum kernels on this part). */
 int b2_dfma_probe(double* dfma_per_s);
