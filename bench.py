@@ -376,6 +376,18 @@ def run_engine(args):
         dist.destroy_process_group()
 
 
+def _ntt_multiplier_occupancy(L, elems_per_s, k, passes, montgomery_per_s):
+    """time the multiplier pipe would need at the probed product rates / measured time: k/2 Shoup products per element
+    (butterflies) + (passes - 1) Montgomery products per element (inter-pass twiddles)"""
+    shoup = ctypes.c_double()
+    if L.b2_shoup_probe(ctypes.byref(shoup)) != 0 or shoup.value <= 0:
+        return None
+    need_s_per_elem = (k / 2.0) / shoup.value + (passes - 1) / montgomery_per_s
+    return {"frac": need_s_per_elem * elems_per_s, "shoup_products_per_s": shoup.value,
+            "model": "(k/2 butterfly products at the Shoup probe rate + (passes-1) twiddle products at the Montgomery probe "
+                     "rate) per element / measured time per element"}
+
+
 def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
     """64 columns, k = logn forward NTT, device resident (config 2 of BASELINE.json)"""
     from halo2_gpu_specific_b200._lib import NttDesc
@@ -438,6 +450,7 @@ def bench_ntt(args, torch, dev, _lib, h2, modmuls_per_s):
                          "model": "64 * log2(n) MACs per element (SURVEY 8d); the butterflies multiply by precomputed "
                                   "twiddles with Shoup's method (92 wide MACs + 23 narrow products instead of 128 + "
                                   "8 per product), so the multiplier pipe does ~0.81x the work this model charges"},
+        "multiplier_occupancy": _ntt_multiplier_occupancy(L, elems / (ms * 1e-3), k, passes, modmuls_per_s),
         "e2e": {"value": ecols * n / (e2e_ms * 1e-3) / 1e6, "unit": "Melem/s", "columns": ecols,
                 "h2d_bytes": ecols * n * 32, "d2h_bytes": ecols * n * 32,
                 "api": "EvaluationDomain.lagrange_to_coeff_batch (pinned host columns, iNTT)"},

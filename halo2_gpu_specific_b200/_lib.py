@@ -50,7 +50,7 @@ SYMBOLS = [
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
     "b2_g1_decompress", "b2_g1_compress", "b2_srs_register_compressed", "b2_srs_read_compressed",
-    "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev", "b2_poly_combine", "b2_poly_combine_dev",
+    "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev", "b2_poly_combine", "b2_poly_combine_dev", "b2_witness_file_columns", "b2_commit_witness_file",
     "b2_batch_invert", "b2_batch_invert_dev", "b2_prefix_scan", "b2_prefix_scan_dev", "b2_fr_vec_dev",
 ]
 
@@ -119,6 +119,8 @@ def lib() -> ctypes.CDLL:
         L.b2_kate_division_dev.argtypes = [vp, u64, vp, vp, vp]
         L.b2_poly_combine_dev.argtypes = [ctypes.POINTER(vp), ctypes.c_uint32, u64, vp, vp, vp]
         L.b2_poly_combine.argtypes = [ctypes.POINTER(vp), ctypes.c_uint32, u64, vp, vp]
+        L.b2_witness_file_columns.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32)]
+        L.b2_commit_witness_file.argtypes = [ctypes.c_uint64, ctypes.c_char_p, ctypes.c_uint32, u64, u64, ctypes.c_uint32, vp, vp]
         L.b2_batch_invert.argtypes = [vp, sz]
         L.b2_batch_invert_dev.argtypes = [vp, sz, vp]
         L.b2_prefix_scan.argtypes = [ctypes.c_int, vp, sz, vp, vp, sz]

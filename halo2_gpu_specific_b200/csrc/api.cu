@@ -18,6 +18,10 @@
 #include <mutex>
 #include <string>
 #include <vector>
+#include <thread>
+
+#include <fcntl.h>
+#include <unistd.h>
 
 #include "../../include/b2pcs.h"
 #include "msm.cuh"
@@ -1509,6 +1513,78 @@ int b2_commit_batch_resident(b2_handle_t srs, const void* columns_data, int colu
     if (!d_columns) return fail(B2_ERR_ARG, "commit_batch_resident: d_columns is NULL");
     return commit_batch_impl(srs, const_cast<void*>(columns_data), columns, n, max_bits, do_ifft, omega_inv, divisor, log_n,
                              out_jac96, d_columns, 0);
+}
+
+// ---- witness file (halo2_proofs/src/helpers.rs:919-1015): u32 LE column count, then column i at byte offset
+// 4 + i * 2^(k+5): 2^k field elements exactly as they sit in memory (Montgomery, 32 B).
+static int witness_pread_all(int fd, char* dst, size_t bytes, uint64_t off) {
+    while (bytes) {
+        ssize_t got = pread(fd, dst, bytes, (off_t)off);
+        if (got <= 0) return -1;
+        dst += got;
+        off += (uint64_t)got;
+        bytes -= (size_t)got;
+    }
+    return 0;
+}
+
+int b2_witness_file_columns(const char* path, uint32_t* n_columns) {
+    if (!path || !n_columns) return fail(B2_ERR_ARG, "witness_file_columns: bad arguments");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(B2_ERR_ARG, "witness file %s: cannot open", path);
+    uint32_t len = 0;
+    const int bad = witness_pread_all(fd, (char*)&len, 4, 0);
+    close(fd);
+    if (bad) return fail(B2_ERR_ARG, "witness file %s: no header", path);
+    *n_columns = len;
+    return B2_OK;
+}
+
+int b2_commit_witness_file(b2_handle_t srs, const char* path, uint32_t k, uint64_t first, uint64_t count, uint32_t max_bits,
+                           void* d_keep, void* out_jac96) {
+    if (!path || !out_jac96 || k > 26) return fail(B2_ERR_ARG, "commit_witness_file: bad arguments");
+    if (count == 0) return B2_OK;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(B2_ERR_ARG, "witness file %s: cannot open", path);
+    uint32_t len = 0;
+    if (witness_pread_all(fd, (char*)&len, 4, 0) || first + count > len) {
+        close(fd);
+        return fail(B2_ERR_ARG, "witness file %s holds %u columns, asked for [%llu, %llu)", path, len,
+                    (unsigned long long)first, (unsigned long long)(first + count));
+    }
+    const size_t n = (size_t)1 << k, col_bytes = n * 32;
+    // two pinned staging buffers of `per` columns: the next group is read from the file (page cache / disk) while the
+    // current one goes through the commit pipeline (H2D + MSM across the lanes)
+    const uint64_t per = std::max<uint64_t>(1, std::min<uint64_t>(count, ((size_t)256 << 20) / col_bytes));
+    char* stage[2] = {nullptr, nullptr};
+    int rc = B2_OK;
+    for (int i = 0; i < 2 && rc == B2_OK; i++)
+        if (cudaMallocHost((void**)&stage[i], per * col_bytes) != cudaSuccess) {
+            cudaGetLastError();
+            rc = fail(B2_ERR_OOM, "commit_witness_file: cannot pin %zu bytes", (size_t)(per * col_bytes));
+        }
+    auto read_group = [&](uint64_t g0, char* dst) -> int {
+        const uint64_t cnt = std::min<uint64_t>(per, count - g0);
+        for (uint64_t c = 0; c < cnt; c++)
+            if (witness_pread_all(fd, dst + c * col_bytes, col_bytes, 4ull + ((first + g0 + c) << (k + 5)))) return -1;
+        return 0;
+    };
+    if (rc == B2_OK && read_group(0, stage[0])) rc = fail(B2_ERR_ARG, "witness file %s: short read", path);
+    int cur = 0;
+    for (uint64_t g0 = 0; g0 < count && rc == B2_OK; g0 += per, cur ^= 1) {
+        const uint64_t cnt = std::min<uint64_t>(per, count - g0);
+        int next_bad = 0;
+        std::thread reader;
+        if (g0 + per < count) reader = std::thread([&, g0] { next_bad = read_group(g0 + per, stage[cur ^ 1]); });
+        rc = commit_batch_impl(srs, stage[cur], cnt, n, max_bits, 0, nullptr, nullptr, k, (char*)out_jac96 + g0 * 96,
+                               d_keep ? (char*)d_keep + g0 * col_bytes : nullptr, 0);
+        if (reader.joinable()) reader.join();
+        if (rc == B2_OK && next_bad) rc = fail(B2_ERR_ARG, "witness file %s: short read", path);
+    }
+    for (int i = 0; i < 2; i++)
+        if (stage[i]) cudaFreeHost(stage[i]);
+    close(fd);
+    return rc;
 }
 
 int b2_msm_and_ifft(b2_handle_t srs, void* coeffs, uint32_t max_bits, const void* omega_inv, const void* divisor,

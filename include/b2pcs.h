@@ -298,6 +298,17 @@ int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* ou
 int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, void* stream);
 int b2_kate_division(const void* a, uint64_t n, const void* b, void* q);
 
+/* ---- witness file ------------------------------------------------------------------------ */
+/* The on-disk witness of halo2_proofs/src/helpers.rs:919-1015 (store_witness / fetch_witness): a u32 LE column count,
+ * then advice column i at byte offset 4 + i * 2^(k+5), 2^k elements as they sit in memory.  b2_commit_witness_file
+ * replaces fetch_witness + the per-column commit_lagrange_with_bound loop (plonk/prover.rs:293-299) for columns
+ * [first, first + count): the file is read through two pinned staging buffers while the previous group is being
+ * copied and committed; with d_keep != NULL the columns also stay resident there (count * 2^k * 32 B, Lagrange form).
+ * out_jac96: count points, normalised. */
+int b2_witness_file_columns(const char* path, uint32_t* n_columns);
+int b2_commit_witness_file(b2_handle_t srs, const char* path, uint32_t k, uint64_t first, uint64_t count, uint32_t max_bits,
+                           void* d_keep, void* out_jac96);
+
 /* Multiopen batching (poly/multiopen/gwc/prover.rs:47-56 and its cuda variant :58-140, which runs the same fold on
  * the GPU through the Bn256_Fr_eval_mul_c / _eval_sum kernels; shplonk/prover.rs folds the same way):
  * out[i] = sum_j v^(m-1-j) * polys[j][i], i.e. poly_batch = poly_batch * v + poly over the m polynomials opened at

@@ -107,3 +107,22 @@ def test_all_gather_rows_world2_gloo(tmp_path):
     full = (np.arange(4 * 32 * 4, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)).reshape(128, 4)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / f"g{r}.npy"), full)
+
+
+def test_witness_file_layout_round_trip(tmp_path):
+    """helpers.rs:919-1015: u32 count, column i at 4 + i * 2^(k+5), raw in-memory field elements (host I/O only)"""
+    import numpy as np
+    from halo2_gpu_specific_b200 import helpers
+    k, cols = 6, 5
+    n = 1 << k
+    rng = np.random.default_rng(5)
+    advice = [rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64) for _ in range(cols)]
+    path = str(tmp_path / "w.bin")
+    helpers.store_witness(path, advice, k)
+    raw = open(path, "rb").read()
+    assert len(raw) == 4 + cols * (1 << (k + 5))
+    assert int.from_bytes(raw[:4], "little") == cols
+    off = 4 + 3 * (1 << (k + 5))
+    assert raw[off:off + 32] == advice[3][0].tobytes()
+    back = helpers.fetch_witness(path, k)
+    assert len(back) == cols and all(np.array_equal(a, b) for a, b in zip(advice, back))
