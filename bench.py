@@ -187,6 +187,7 @@ def run_engine(args):
     torch.cuda.set_device(local)
     _lib.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cpus = _lib.bind_host_to_gpu(local) if world > 1 else None   # pinned buffers on the GPU's NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
@@ -346,6 +347,8 @@ def run_engine(args):
                                "note": "same per-call copies; 3 concurrent callers per GPU (local partial MSMs only, "
                                        "no cross-rank combine), as the reference's rayon workers would call it"},
             "gpu_launches": launches,
+            "host_binding": ({"cpus_rank0": len(numa_cpus), "note": "each rank bound to the CPUs NVML reports local to its GPU "
+                              "before allocating pinned buffers (B2_NUMA_BIND=0 disables)"} if numa_cpus else None),
             "roofline": {
                 "kernel": "msm_accumulate_kernel", "bound": "int", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
                 "frac": achieved / peak,

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+from typing import Optional
 
 import numpy as np
 
@@ -160,6 +161,36 @@ def as_fr(a, copy: bool = False) -> np.ndarray:
 def as_fr1(a) -> np.ndarray:
     arr = np.ascontiguousarray(np.asarray(a, dtype=np.uint64).reshape(4))
     return arr
+
+
+def bind_host_to_gpu(device_index: int) -> Optional[list]:
+    """Restrict this process to the CPUs NVML reports as local to the GPU, so that page-locked buffers allocated
+    afterwards land on the GPU's NUMA node (first-touch) and its host copies do not cross the socket interconnect.
+    Meant for one-process-per-GPU runs with N > 1, where N ranks otherwise pull their columns out of whichever
+    node the scheduler happened to place them on.  Returns the CPU list, or None when NVML / the cpuset does not
+    allow it (nothing is changed then).  B2_NUMA_BIND=0 disables it."""
+    if os.environ.get("B2_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = device_index
+        if visible:
+            ids = [v for v in visible.split(",") if v.strip() != ""]
+            if device_index < len(ids) and ids[device_index].strip().isdigit():
+                phys = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
 
 
 def pinned_empty(shape, dtype=np.uint64) -> np.ndarray:

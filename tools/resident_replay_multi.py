@@ -83,6 +83,7 @@ def main():
     torch.cuda.set_device(local)
     _lib.require_gpu()
     _lib.set_device(local)
+    numa_cpus = _lib.bind_host_to_gpu(local) if world > 1 else None      # pinned columns on the GPU's NUMA node
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     L = _lib.lib()
@@ -441,7 +442,7 @@ def main():
                                  "h": nc * n * 32 / 2**30 if world > 1 else 0,
                                  "multiopen_folds": sh["R"] * n * 32 / 2**30 if world > 1 else 0},
                "h2d_GiB_per_rank": ((a_hi - a_lo) + (l_hi - l_lo) + sh["I"] + 1) * n * 32 / 2**30,
-               "digest_h_and_folds": digest,
+               "digest_h_and_folds": digest, "host_cpus_rank0": (len(numa_cpus) if numa_cpus else None),
                "evaluations_rank0": n_evals, "polynomials_folded": n_opened, "tasks_rank0": tasks,
                "timing": "per phase: barrier + synchronize on both sides, wall clock on rank 0 (= max over ranks)",
                "program": prog.info(),
