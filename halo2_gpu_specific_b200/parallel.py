@@ -88,6 +88,16 @@ def quotient_tasks(n_cosets: int, n: int, world_size: int, rank: int):
     return tasks
 
 
+def coset_transform_shares(n_cosets: int, world_size: int, rank: int, n_polys: int):
+    """Ranks that evaluate rows of the same coset (world_size > n_cosets, see quotient_tasks) need the coset
+    evaluations of ALL n_polys polynomials, but need not all compute them: the group splits the polynomials and swaps
+    the shares point-to-point.  Returns (group_first_rank, [(rank, poly_lo, poly_hi), ...]) for this rank's group; a
+    group of one (world_size <= n_cosets) transforms everything itself."""
+    share = max(1, world_size // n_cosets)
+    first = (rank // share) * share
+    return first, [(first + j,) + shard_range(n_polys, share, j) for j in range(share)]
+
+
 def all_gather_rows(local: "np.ndarray | object", rows_total: int):
     """every rank's compact slice of h (equal row counts) -> the full coset-major array, on every rank"""
     d = _dist()

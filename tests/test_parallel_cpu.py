@@ -126,3 +126,23 @@ def test_witness_file_layout_round_trip(tmp_path):
     assert raw[off:off + 32] == advice[3][0].tobytes()
     back = helpers.fetch_witness(path, k)
     assert len(back) == cols and all(np.array_equal(a, b) for a, b in zip(advice, back))
+
+
+def test_coset_transform_shares_cover_every_polynomial_once():
+    """ranks sharing a coset split its transforms (tools/resident_replay_multi.py): the shares of a group are disjoint,
+    cover all polynomials, and groups line up with quotient_tasks (same coset for every rank of a group)"""
+    from halo2_gpu_specific_b200 import parallel
+    n, nc, n_polys = 1 << 10, 4, 97
+    for world in (1, 2, 4, 8, 16):
+        for rank in range(world):
+            first, shares = parallel.coset_transform_shares(nc, world, rank, n_polys)
+            assert [s[0] for s in shares] == list(range(first, first + len(shares))) and first <= rank < first + len(shares)
+            covered = []
+            for _, lo, hi in shares:
+                covered += list(range(lo, hi))
+            assert covered == list(range(n_polys))
+            cosets = {parallel.quotient_tasks(nc, n, world, r)[0][0] for r, _, _ in shares}
+            if world > nc:
+                assert len(cosets) == 1 and all(len(parallel.quotient_tasks(nc, n, world, r)) == 1 for r, _, _ in shares)
+            else:
+                assert len(shares) == 1

@@ -277,16 +277,16 @@ def main():
 
     # ranks sharing a coset (world > number of cosets): each transforms a share of the witness polynomials and the
     # group swaps the shares over NVLink (point-to-point), instead of every rank transforming all of them
-    share = max(1, world // nc)
-    grp_first = (rank // share) * share
     n_wit = n_polys - n_key
+    grp_first, shares = parallel.coset_transform_shares(nc, world, rank, n_wit)
+    share = len(shares)
 
     def coset_transform(c):
         g_c = dom._zeta * pow(dom._ext_omega, c, R) % R
         if share == 1 or a.no_split_transforms:
             E.coeff_to_coset_dev(dom, coef.ptr + n_key * n * 32, n_wit, g_c, cos.ptr + n_key * n * 32)
             return
-        bounds = [parallel.shard_range(n_wit, share, j) for j in range(share)]
+        bounds = [(plo, phi) for _, plo, phi in shares]
         lo, hi = bounds[rank - grp_first]
         E.coeff_to_coset_dev(dom, coef.ptr + (n_key + lo) * n * 32, hi - lo, g_c, cos.ptr + (n_key + lo) * n * 32)
         L.b2_synchronize()
