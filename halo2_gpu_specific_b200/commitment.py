@@ -78,6 +78,19 @@ class Params:
                                         int(max_bits), 1, ptr(om), ptr(dv), self.k, ptr(out)))
         return out
 
+    def commit_batch(self, cols: np.ndarray) -> np.ndarray:
+        """`commit` (:129-133) for several coefficient-form polynomials of one length (the h(X) pieces,
+        vanishing/prover.rs:86-96, and the multiopen witness polynomials, gwc/prover.rs:162): (columns, m, 4),
+        m <= n, against g[0..m] -> (columns, 12) normalised."""
+        if cols.ndim != 3 or cols.shape[2] != 4 or cols.shape[1] > self.n or cols.shape[1] == 0:
+            raise B2Error(B2_ERR_ARG, "expected (columns, m <= n, 4)")
+        cols = np.ascontiguousarray(cols, dtype=np.uint64)
+        require_gpu()
+        out = np.zeros((cols.shape[0], 12), dtype=np.uint64)
+        check(lib().b2_commit_batch(self.g.handle, ptr(cols), cols.shape[0], cols.shape[1], _fr.NUM_BITS, 0, None, None,
+                                    self.k, ptr(out)))
+        return out
+
     def write(self, writer, sign_bit: int = 7) -> None:
         """:241-253: k || g || g_lagrange (32-byte compressed points) || len || additional_data.  The points are
         compressed on the device from the resident SRS."""

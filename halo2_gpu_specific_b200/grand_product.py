@@ -262,6 +262,24 @@ def shuffle_commit_product(domain, group, blinding_factors: int, advice, fixed, 
         cols.free(); work.free(); zbuf.free()
 
 
+def compress_expressions(domain, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
+    """evaluate_with_theta (plonk/evaluation.rs:2330-2398) for several expression lists over the same Lagrange
+    columns: what logup's `compress` computes before the multiplicities are counted (logup/prover.rs:83-112).
+    Returns (len(expression_lists), n, 4)."""
+    require_gpu()
+    n, k = domain.n, domain.k
+    m = len(expression_lists)
+    cols = _Columns(fixed, advice, instance, n)
+    out = DeviceBuffer(max(1, m) * n)
+    try:
+        for i, exprs in enumerate(expression_lists):
+            c = ExprCompiler()
+            _run(c, c.emit(("Store", c.compress(exprs))), cols, [], [0, 0, theta % R], out.ptr + i * n * 32, k)
+        return out.download(m * n).reshape(m, n, 4) if m else np.zeros((0, n, 4), np.uint64)
+    finally:
+        cols.free(); out.free()
+
+
 def batch_invert(a: np.ndarray) -> np.ndarray:
     """arithmetic.rs:840-844, in place on a host array"""
     require_gpu()

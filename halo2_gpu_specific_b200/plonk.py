@@ -1,0 +1,765 @@
+"""Host mirror of the prover that drives the engine: plonk::keygen (the parts the prover reads) and
+plonk::create_proof / create_proof_from_witness of the reference, with every MSM, NTT, z column, quotient
+evaluation, polynomial evaluation and multiopen fold issued as a batched call into the C ABI (SURVEY.md 8f
+rank 2: "replace per-column par_iter calls with batched FFI calls; thread the caller's rng through").
+
+  ConstraintSystem, queries        plonk/circuit.rs (the fields the prover reads; query_*_index / get_any_query_index)
+  GraphBuilder -> Evaluator        plonk/evaluation.rs:307-448, 623-776 (Evaluator::new, add_expression)
+  keygen                           plonk/keygen.rs:213-431, plonk/permutation/keygen.rs:196-262
+  create_proof                     plonk/prover.rs:85-173 (instances), :916-1500 = :206-850 (the proof),
+                                   plonk/vanishing/prover.rs:41-153, plonk/permutation/prover.rs:181-304,
+                                   plonk/logup/prover.rs:70-256, 420-491, plonk/shuffle/prover.rs:200-240,
+                                   poly/multiopen/gwc.rs:38-62, poly/multiopen/gwc/prover.rs:19-173
+All paths relative to /root/reference/halo2_proofs/src.  Out of scope, as in DESIGN.md section 7: the circuit
+front-end (layouter, selector compression, witness synthesis -- the advice columns arrive as fetch_witness would
+deliver them) and the verifier.
+
+Numbers are (.., 4) uint64 Montgomery arrays (the reference's in-memory Fr); challenges and evaluation points are
+Python ints (canonical).  The numeric work goes through an `Engine` object; the only implementation in this package
+is the device one (it raises without a CUDA device -- there is no CPU fallback).  The parameter exists so that the
+host logic (transcript order, RNG order, query grouping, multiplicities) can be tested on CPU against a test double
+that lives in tests/.
+
+Three inputs cannot be read from the reference tree and are parameters (see oracle/prover.py for the same list):
+the verifying key's transcript scalar (`transcript_repr`), the point compression bit (`sign_bit`) and the source of
+randomness (`rng`; draw order documented at create_proof).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _fr
+from ._lib import B2_ERR_ARG, B2Error
+from .transcript import Blake2bWrite, Point
+
+R = _fr.R_MOD
+DELTA = pow(_fr.GENERATOR, 1 << _fr.S, R)          # Fr::DELTA
+
+
+# --------------------------------------------------------------------------
+# ConstraintSystem (the part the prover reads)
+# --------------------------------------------------------------------------
+class ConstraintSystem:
+    """Expressions are the reference's enum as tuples (see grand_product.ExprCompiler).  gates: list of
+    polynomial lists (gate.polynomials()); lookups: [{"table_expressions", "input_expressions_sets"}]
+    (logup::Argument); shuffles: groups of {"input_expressions", "shuffle_expressions"}; permutation_columns:
+    [("Advice"|"Fixed"|"Instance", index)].  degree / blinding_factors are what cs.degree() /
+    cs.blinding_factors() return (circuit.rs:1838-1944): computing them needs the front-end's query bookkeeping."""
+
+    def __init__(self, num_fixed: int, num_advice: int, num_instance: int, degree: int, blinding_factors: int = 5,
+                 gates=(), lookups=(), shuffles=(), permutation_columns=(), advice_queries=None, fixed_queries=None,
+                 instance_queries=None):
+        self.num_fixed, self.num_advice, self.num_instance = num_fixed, num_advice, num_instance
+        self.gates = [list(g) for g in gates]
+        self.lookups = list(lookups)
+        self.shuffles = [list(g) for g in shuffles]
+        self.permutation_columns = [tuple(c) for c in permutation_columns]
+        self._degree, self._blinding_factors = degree, blinding_factors
+        self.advice_queries, self.fixed_queries, self.instance_queries = advice_queries, fixed_queries, instance_queries
+
+    @classmethod
+    def like(cls, other) -> "ConstraintSystem":
+        """copy of any object with the same attributes (e.g. a front-end's description)"""
+        return cls(other.num_fixed, other.num_advice, other.num_instance, other.degree(), other.blinding_factors(),
+                   other.gates, other.lookups, other.shuffles, other.permutation_columns,
+                   getattr(other, "advice_queries", None), getattr(other, "fixed_queries", None),
+                   getattr(other, "instance_queries", None))
+
+    def degree(self) -> int:
+        return self._degree
+
+    def blinding_factors(self) -> int:
+        return self._blinding_factors
+
+    def queries(self) -> Dict[str, List[Tuple[int, int]]]:
+        """(column, rotation) lists per column kind.  Their order is the order of the circuit's meta.query_* calls
+        in the reference; without a front-end the rule is: permutation columns at Rotation::cur (enable_equality),
+        then gates, lookups (input sets, table), shuffles, in order of first appearance -- unless the lists were
+        given explicitly."""
+        if self.advice_queries is None:
+            q: Dict[str, List[Tuple[int, int]]] = {"Advice": [], "Fixed": [], "Instance": []}
+
+            def walk(e):
+                t = e[0]
+                if t in q:
+                    if (e[1], e[2]) not in q[t]:
+                        q[t].append((e[1], e[2]))
+                elif t in ("Negated", "Scaled"):
+                    walk(e[1])
+                elif t in ("Sum", "Product"):
+                    walk(e[1])
+                    walk(e[2])
+                elif t != "Constant":
+                    raise B2Error(B2_ERR_ARG, f"unknown Expression {e!r}")
+
+            for kind, col in self.permutation_columns:
+                walk((kind, col, 0))
+            for gate in self.gates:
+                for poly in gate:
+                    walk(poly)
+            for lk in self.lookups:
+                for s in lk["input_expressions_sets"]:
+                    for inp in s:
+                        for e in inp:
+                            walk(e)
+                for e in lk["table_expressions"]:
+                    walk(e)
+            for group in self.shuffles:
+                for a in group:
+                    for e in list(a["input_expressions"]) + list(a["shuffle_expressions"]):
+                        walk(e)
+            self.advice_queries, self.fixed_queries, self.instance_queries = q["Advice"], q["Fixed"], q["Instance"]
+        return {"Advice": self.advice_queries, "Fixed": self.fixed_queries, "Instance": self.instance_queries}
+
+
+# --------------------------------------------------------------------------
+# Evaluator::new (evaluation.rs:307-448): expression DAG with common-subexpression sharing
+# --------------------------------------------------------------------------
+_RANK = {"Constant": 0, "Intermediate": 1, "Fixed": 2, "Advice": 3, "Instance": 4}
+ZERO, ONE = ("Constant", 0), ("Constant", 1)
+
+
+class GraphBuilder:
+    """The interning tables of Evaluator: constants, rotations and calculations are appended on first use and
+    referred to by index afterwards (evaluation.rs:623-668), so equal sub-expressions share one slot."""
+
+    def __init__(self):
+        self.constants: List[int] = []
+        self.rotations: List[int] = []
+        self.calculations: List[tuple] = []
+        self._c: Dict[int, int] = {}
+        self._r: Dict[int, int] = {}
+        self._k: Dict[tuple, int] = {}
+
+    def constant(self, v: int):
+        v %= R
+        if v not in self._c:
+            self._c[v] = len(self.constants)
+            self.constants.append(v)
+        return ("Constant", self._c[v])
+
+    def rotation(self, r: int) -> int:
+        if r not in self._r:
+            self._r[r] = len(self.rotations)
+            self.rotations.append(r)
+        return self._r[r]
+
+    def calc(self, c: tuple):
+        if c not in self._k:
+            self._k[c] = len(self.calculations)
+            self.calculations.append(c)
+        return ("Intermediate", self._k[c])
+
+    @staticmethod
+    def _ordered(a, b):
+        """commutative operands in derive(PartialOrd) order of ValueSource (evaluation.rs:45-58, 742, 758)"""
+        return (a, b) if (_RANK[a[0]],) + tuple(a[1:]) <= (_RANK[b[0]],) + tuple(b[1:]) else (b, a)
+
+    def expression(self, e):
+        """add_expression, evaluation.rs:671-776 (including :727-728, which returns b for `0 - b`)"""
+        t = e[0]
+        if t == "Constant":
+            return self.constant(e[1])
+        if t in ("Fixed", "Advice", "Instance"):
+            return self.calc(("Store", (t, e[1], self.rotation(e[2]))))
+        if t == "Negated":
+            if e[1][0] == "Constant":
+                return self.constant(-e[1][1])
+            a = self.expression(e[1])
+            return a if a == ZERO else self.calc(("Negate", a))
+        if t == "Sum":
+            if e[2][0] == "Negated":
+                a, b = self.expression(e[1]), self.expression(e[2][1])
+                if a == ZERO:
+                    return b
+                return a if b == ZERO else self.calc(("Sub", a, b))
+            a, b = self.expression(e[1]), self.expression(e[2])
+            if a == ZERO:
+                return b
+            if b == ZERO:
+                return a
+            return self.calc(("Add",) + self._ordered(a, b))
+        if t == "Product":
+            a, b = self.expression(e[1]), self.expression(e[2])
+            if a == ZERO or b == ZERO:
+                return ZERO
+            if a == ONE:
+                return b
+            if b == ONE:
+                return a
+            return self.calc(("Mul",) + self._ordered(a, b))
+        if t == "Scaled":
+            if e[2] % R == 0:
+                return ZERO
+            if e[2] % R == 1:
+                return self.expression(e[1])
+            c = self.constant(e[2])
+            return self.calc(("Mul", self.expression(e[1]), c))
+        raise B2Error(B2_ERR_ARG, f"unknown Expression {e!r}")
+
+    def theta_fold(self, expressions):
+        """evaluate_lc, evaluation.rs:350-360"""
+        parts = [self.expression(x) for x in expressions]
+        acc = parts[0]
+        for p in parts[1:]:
+            acc = self.calc(("LcTheta", acc, p))
+        return acc
+
+
+def evaluator_parts(cs) -> dict:
+    """Evaluator::new (evaluation.rs:309-448, CPU structures; :539-578 for the shuffles) as plain data"""
+    g = GraphBuilder()
+    assert g.constant(0) == ZERO and g.constant(1) == ONE
+    value_parts = [g.expression(poly) for gate in cs.gates for poly in gate]
+    lookup_results = []
+    for lk in cs.lookups:
+        table = ("AddChallenge", g.theta_fold(lk["table_expressions"]), "Beta")
+        sets = [[g.calc(("AddChallenge", g.theta_fold(inp), "Beta")) for inp in s] for s in lk["input_expressions_sets"]]
+        products, sums = [], []
+        for s in sets:
+            acc = s[0]
+            for v in s[1:]:
+                acc = g.calc(("Mul", acc, v))
+            products.append(("Store", acc))
+        for s in sets:
+            if len(s) == 1:
+                sums.append(("Store", ONE))
+                continue
+            terms = []
+            for i in range(len(s)):
+                rest = s[:i] + s[i + 1:]
+                acc = rest[0]
+                for v in rest[1:]:
+                    acc = g.calc(("Mul", acc, v))
+                terms.append(acc)
+            acc = terms[0]
+            for v in terms[1:]:
+                acc = g.calc(("Add", acc, v))
+            sums.append(("Store", acc))
+        lookup_results.append((table, products, sums))
+    shuffle_results = []
+    for group in cs.shuffles:
+        lcs = [(g.theta_fold(a["input_expressions"]), g.theta_fold(a["shuffle_expressions"])) for a in group]
+        pair = []
+        for which in (0, 1):
+            folded = [lc[which] for lc in lcs]
+            acc = ("AddChallenge", folded[0], "Beta")
+            for i, part in enumerate(folded[1:], start=1):
+                acc = ("LcChallenge", part, g.calc(acc), "Beta", i + 1)
+            pair.append(acc)
+        shuffle_results.append(tuple(pair))
+    return {"rotations": g.rotations, "constants": g.constants, "calculations": g.calculations,
+            "value_parts": value_parts, "lookup_results": lookup_results, "shuffle_results": shuffle_results}
+
+
+def build_evaluator(cs):
+    from .evaluation import Evaluator
+    p = evaluator_parts(cs)
+    return Evaluator(p["rotations"], p["constants"], p["calculations"], p["value_parts"], p["lookup_results"],
+                     p["shuffle_results"], cs.num_fixed, cs.num_advice, cs.num_instance, cs.permutation_columns,
+                     cs.degree(), cs.blinding_factors())
+
+
+# --------------------------------------------------------------------------
+# randomness
+# --------------------------------------------------------------------------
+class SeededRng:
+    """Reproducible source for the prover's random values (tests, benchmarks, the fixed-RNG parity the
+    north star asks for).  fr_vec returns Montgomery limbs of 253-bit values (every 253-bit integer is below r)."""
+
+    def __init__(self, seed: int):
+        self._g = np.random.Generator(np.random.PCG64(seed))
+
+    def u64_vec(self, n: int) -> np.ndarray:
+        return self._g.integers(0, 1 << 64, size=n, dtype=np.uint64)
+
+    def u16_vec(self, n: int) -> np.ndarray:
+        return self._g.integers(0, 1 << 16, size=n, dtype=np.uint64)
+
+    def fr_vec(self, n: int) -> np.ndarray:
+        a = self._g.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 61) - 1)
+        return a
+
+
+class OsRng:
+    """rand_core::OsRng for the same interface"""
+
+    def u64_vec(self, n: int) -> np.ndarray:
+        return np.frombuffer(os.urandom(8 * n), dtype=np.uint64).copy()
+
+    def u16_vec(self, n: int) -> np.ndarray:
+        return np.frombuffer(os.urandom(2 * n), dtype=np.uint16).astype(np.uint64)
+
+    def fr_vec(self, n: int) -> np.ndarray:
+        a = np.frombuffer(os.urandom(32 * n), dtype=np.uint64).reshape(n, 4).copy()
+        a[:, 3] &= np.uint64((1 << 61) - 1)
+        return a
+
+
+# --------------------------------------------------------------------------
+# the device engine
+# --------------------------------------------------------------------------
+def _mont_vec(vals: Sequence[int]) -> np.ndarray:
+    return np.stack([_fr.to_mont(int(v)) for v in vals]) if len(vals) else np.zeros((0, 4), np.uint64)
+
+
+class Engine:
+    """Every numeric step of keygen / create_proof as one call into the C ABI (through the mirrors of this
+    package).  Points come back as canonical affine (x, y) tuples, None for the identity."""
+
+    def __init__(self, params, domain):
+        from ._lib import require_gpu
+        require_gpu()
+        self.params, self.domain = params, domain
+
+    # -- commitments
+    @staticmethod
+    def _points(jac: np.ndarray) -> List[Point]:
+        from .transcript import point_from_engine
+        return [point_from_engine(p) for p in jac]
+
+    def commit_lagrange(self, cols: np.ndarray, max_bits: int = _fr.NUM_BITS) -> List[Point]:
+        """Params::commit_lagrange[_with_bound] per column (plonk/prover.rs:124-127, 293-299)"""
+        return self._points(self.params.commit_lagrange_batch(np.ascontiguousarray(cols), max_bits))
+
+    def commit_lagrange_and_ifft(self, cols: np.ndarray) -> List[Point]:
+        """Params::commit_lagrange_and_ifft per column (plonk/prover.rs:470-501, 535-553, 561-593); cols become
+        coefficient forms in place"""
+        d = self.domain
+        return self._points(self.params.commit_lagrange_batch(cols, ifft=(d.omega_inv, d.ifft_divisor)))
+
+    def commit(self, cols: np.ndarray) -> List[Point]:
+        """Params::commit per polynomial (vanishing/prover.rs:64, 86-96; gwc/prover.rs:162)"""
+        return self._points(self.params.commit_batch(cols))
+
+    # -- transforms
+    def lagrange_to_coeff(self, cols: np.ndarray) -> np.ndarray:
+        return self.domain.lagrange_to_coeff_batch(cols)
+
+    def coeff_to_extended(self, cols: np.ndarray) -> np.ndarray:
+        return self.domain.coeff_to_extended(cols)
+
+    def fft(self, a: np.ndarray) -> np.ndarray:
+        """best_fft over the size-n domain, in place"""
+        from .arithmetic import best_fft
+        best_fft(a, self.domain.omega, self.domain.k)
+        return a
+
+    # -- element-wise field work
+    def fr_vec(self, op: str, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        from ._lib import check, lib, ptr
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+        if a.shape != b.shape:
+            raise B2Error(B2_ERR_ARG, "fr_vec: shapes differ")
+        out = np.empty_like(a)
+        if a.shape[0]:
+            check(lib().b2_field_vec(0, {"mul": 0, "add": 1, "sub": 2}[op], ptr(a), ptr(b), a.shape[0], ptr(out)))
+        return out
+
+    def to_mont(self, canonical: np.ndarray) -> np.ndarray:
+        """canonical limbs -> Montgomery: the Montgomery product with R^2"""
+        r2 = np.array([(pow(2, 512, R) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+        c = np.ascontiguousarray(canonical, dtype=np.uint64).reshape(-1, 4)
+        return self.fr_vec("mul", c, np.broadcast_to(r2, c.shape))
+
+    def from_mont(self, a: np.ndarray) -> np.ndarray:
+        """Montgomery -> canonical limbs: the Montgomery product with 1"""
+        one = np.array([1, 0, 0, 0], dtype=np.uint64)
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+        return self.fr_vec("mul", a, np.broadcast_to(one, a.shape))
+
+    # -- z columns and the quotient
+    def compress(self, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
+        from .grand_product import compress_expressions
+        return compress_expressions(self.domain, expression_lists, advice, fixed, instance, theta)
+
+    def permutation_commit(self, cs, sigmas, advice, fixed, instance, beta, gamma, blinds):
+        from .grand_product import permutation_commit
+        return permutation_commit(self.domain, cs.permutation_columns, cs.degree(), cs.blinding_factors(), sigmas, advice,
+                                  fixed, instance, beta, gamma, blinds)
+
+    def logup_commit_z(self, cs, lookup, advice, fixed, instance, m, theta, beta):
+        from .grand_product import logup_commit_z
+        return logup_commit_z(self.domain, lookup, cs.blinding_factors(), advice, fixed, instance, m, theta, beta)
+
+    def shuffle_commit_product(self, cs, group, advice, fixed, instance, theta, beta):
+        from .grand_product import shuffle_commit_product
+        return shuffle_commit_product(self.domain, group, cs.blinding_factors(), advice, fixed, instance, theta, beta)
+
+    def evaluate_h(self, pk, advice_polys, instance_polys, y, beta, gamma, theta, lookups, shuffles, permutations):
+        """Evaluator::evaluate_h + divide_by_vanishing_poly + extended_to_coeff (plonk/prover.rs:663-690,
+        vanishing/prover.rs:72-76) -> the n * (degree - 1) coefficients of h(X)"""
+        return pk.ev.evaluate_h(self.domain, pk.fixed_polys, advice_polys, instance_polys, pk.l0, pk.l_last,
+                                pk.l_active_row, pk.sigma_polys, y, beta, gamma, theta, lookups, shuffles, permutations,
+                                to_coeff=True)
+
+    # -- evaluation and opening
+    def eval_polynomial(self, poly: np.ndarray, point: int) -> int:
+        from .arithmetic import eval_polynomial
+        return _fr.from_mont(eval_polynomial(poly, _fr.to_mont(point)))
+
+    def poly_combine(self, polys, v: int) -> np.ndarray:
+        from .arithmetic import poly_combine
+        return poly_combine(polys, _fr.to_mont(v))
+
+    def kate_division(self, poly: np.ndarray, z: int) -> np.ndarray:
+        from .arithmetic import kate_division
+        return kate_division(poly, _fr.to_mont(z))
+
+
+# --------------------------------------------------------------------------
+# keygen
+# --------------------------------------------------------------------------
+class VerifyingKey:
+    def __init__(self, cs, domain, fixed_commitments, permutation_commitments, transcript_repr: Optional[int]):
+        self.cs, self.domain = cs, domain
+        self.fixed_commitments, self.permutation_commitments = fixed_commitments, permutation_commitments
+        if transcript_repr is None:
+            # plonk.rs:91-109 hashes Rust's Debug text of the pinned key; that text cannot be produced here, so the
+            # default is the same construction over this package's own description of the key
+            s = repr((domain.k, domain.extended_k, hex(domain._omega), fixed_commitments, permutation_commitments,
+                      cs.num_fixed, cs.num_advice, cs.num_instance, cs.gates, cs.lookups, cs.shuffles,
+                      cs.permutation_columns, cs.queries(), cs.degree(), cs.blinding_factors())).encode()
+            h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
+            h.update(len(s).to_bytes(8, "little"))
+            h.update(s)
+            transcript_repr = int.from_bytes(h.digest(), "little")
+        self.transcript_repr = transcript_repr % R
+
+
+class ProvingKey:
+    """plonk::ProvingKey: vk, l0 / l_last / l_active_row (extended), fixed_values / fixed_polys, the permutation
+    proving key (sigma values and polynomials) and the Evaluator"""
+
+
+def identity_mapping(m: int, n: int) -> np.ndarray:
+    """permutation::keygen::Assembly::new: mapping[i][j] = (i, j), as an (m, n, 2) array"""
+    out = np.empty((m, n, 2), dtype=np.int64)
+    out[..., 0] = np.arange(m)[:, None]
+    out[..., 1] = np.arange(n)[None, :]
+    return out
+
+
+def keygen(params, cs, fixed: np.ndarray, mapping, engine: Optional[Engine] = None, zeta: Optional[int] = None,
+           transcript_repr: Optional[int] = None) -> ProvingKey:
+    """keygen_vk + keygen_pk for a laid-out circuit.  fixed: (num_fixed, n, 4) Lagrange columns; mapping: the
+    permutation as (m, n, 2) integers (column position in cs.permutation_columns, row), Assembly.mapping."""
+    from .domain import EvaluationDomain
+    domain = EvaluationDomain(cs.degree(), params.k) if zeta is None else EvaluationDomain(cs.degree(), params.k, zeta)
+    E = engine or Engine(params, domain)
+    n = domain.n
+    fixed = np.ascontiguousarray(fixed, dtype=np.uint64).reshape(cs.num_fixed, n, 4)
+    m = len(cs.permutation_columns)
+    mapping = np.asarray(mapping, dtype=np.int64).reshape(m, n, 2)
+    # sigma_i[j] = delta^i' * omega^j' with (i', j') = mapping[i][j] (permutation/keygen.rs:196-233); the columns
+    # delta^i * omega^j are the size-n transform of the polynomial delta^i * X
+    ident = np.zeros((max(1, m), n, 4), dtype=np.uint64)
+    d = 1
+    for i in range(m):
+        ident[i, 1] = _fr.to_mont(d)
+        E.fft(ident[i])
+        d = d * DELTA % R
+    sigmas = np.ascontiguousarray(ident[mapping[..., 0], mapping[..., 1]]) if m else np.zeros((0, n, 4), np.uint64)
+    pk = ProvingKey()
+    fixed_commitments = E.commit_lagrange(fixed) if cs.num_fixed else []         # keygen.rs:288-291
+    permutation_commitments = E.commit_lagrange(sigmas) if m else []             # permutation/keygen.rs:244-251
+    pk.vk = VerifyingKey(cs, domain, fixed_commitments, permutation_commitments, transcript_repr)
+    pk.fixed_values = fixed
+    pk.fixed_polys = E.lagrange_to_coeff(fixed.copy()) if cs.num_fixed else fixed
+    pk.sigmas = sigmas
+    pk.sigma_polys = E.lagrange_to_coeff(sigmas.copy()) if m else sigmas
+    # l0, l_blind, l_last over the extended domain (keygen.rs:398-431)
+    bf = cs.blinding_factors()
+    one = _fr.to_mont(1)
+    lag = np.zeros((3, n, 4), dtype=np.uint64)
+    lag[0, 0] = one
+    lag[1, n - bf:] = one
+    lag[2, n - bf - 1] = one
+    ext = E.coeff_to_extended(E.lagrange_to_coeff(lag))
+    pk.l0, l_blind, pk.l_last = ext[0], ext[1], ext[2]
+    ones = np.broadcast_to(one, pk.l0.shape)
+    pk.l_active_row = E.fr_vec("sub", ones, E.fr_vec("add", pk.l_last, l_blind))
+    pk.ev = build_evaluator(cs)
+    return pk
+
+
+# --------------------------------------------------------------------------
+# logup multiplicities (host: sort + binary search, as in the reference)
+# --------------------------------------------------------------------------
+def _sort_keys(canonical: np.ndarray) -> np.ndarray:
+    """canonical (n, 4) little-endian limbs -> fixed-width big-endian byte strings, whose order is the integer order"""
+    be = np.ascontiguousarray(canonical[:, ::-1]).astype(">u8")
+    return np.frombuffer(be.tobytes(), dtype="S32")
+
+
+def logup_multiplicity(inputs_canonical: Sequence[np.ndarray], table_canonical: np.ndarray, usable: int, n: int
+                       ) -> np.ndarray:
+    """logup/prover.rs:115-184 -> m as integer counts per row.  The table's usable rows are stably sorted by value
+    and every input value is looked up with <[T]>::binary_search_by_key; when the table repeats a value the row that
+    search returns gets the count, so the probe sequence of the pinned toolchain's implementation
+    (mid = left + size / 2, first Equal probe wins) is reproduced on the run [lo, hi) of equal keys."""
+    keys = _sort_keys(np.ascontiguousarray(table_canonical[:usable]))
+    order = np.argsort(keys, kind="stable")
+    skeys = keys[order]
+    m = np.zeros(n, dtype=np.int64)
+    for inp in inputs_canonical:
+        vals = _sort_keys(np.ascontiguousarray(inp[:usable]))
+        lo = np.searchsorted(skeys, vals, side="left")
+        hi = np.searchsorted(skeys, vals, side="right")
+        if np.any(hi <= lo):
+            raise B2Error(B2_ERR_ARG, "logup binary_search_by_key should hit")
+        ulo, inverse = np.unique(lo, return_inverse=True)
+        uhi = np.zeros_like(ulo)
+        uhi[inverse] = hi
+        found = np.full(ulo.shape, -1, dtype=np.int64)
+        left = np.zeros_like(ulo)
+        right = np.full_like(ulo, usable)
+        size = right - left
+        while np.any(found < 0):
+            live = found < 0
+            mid = left + size // 2
+            less = live & (mid < ulo)
+            greater = live & (mid >= uhi)
+            hit = live & ~less & ~greater
+            found[hit] = mid[hit]
+            left = np.where(less, mid + 1, left)
+            right = np.where(greater, mid, right)
+            size = right - left
+        m += np.bincount(order[found[inverse]], minlength=n)
+    return m
+
+
+# --------------------------------------------------------------------------
+# create_proof
+# --------------------------------------------------------------------------
+def _max_bits(counts: np.ndarray) -> int:
+    """expression_max_bits, logup/prover.rs:493-517"""
+    return max(16, int(counts.max()).bit_length() if counts.size else 0)
+
+
+def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence[Sequence[int]], rng,
+                 sign_bit: int = 7, engine: Optional[Engine] = None, advice_max_bits: int = _fr.NUM_BITS,
+                 timings: Optional[dict] = None) -> bytes:
+    """plonk::create_proof (GWC multiopen) for one circuit instance, advice given (create_proof_from_witness).
+
+    advice: (num_advice, n, 4) Lagrange columns; consumed (blinding rows are written into it and it ends up in
+    coefficient form).  instances: per instance column the public values (canonical ints), zero padded internally.
+    advice_max_bits: the bound handed to commit_lagrange_with_bound (the reference scans each column for its
+    largest scalar, plonk/prover.rs:945-962, 296; a caller that knows its witness range passes it).
+
+    Random values come from `rng` in this order (vector draws):
+      1. u16_vec(num_advice * (bf + 1)): advice column i takes [i*(bf+1), (i+1)*(bf+1)) for its last bf+1 rows
+      2. per lookup: u16_vec(bf + 1), the last rows of m
+      3. per permutation set: fr_vec(bf);  4. per lookup, per z: fr_vec(bf);  5. per shuffle group: fr_vec(bf)
+      6. vanishing random polynomial: fr_vec(k), fr_vec(n), u64_vec(n), fr_vec(n), u64_vec(n)
+         (coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]), vanishing/prover.rs:48-63)
+    """
+    import time
+    vk = pk.vk
+    cs, domain = vk.cs, vk.domain
+    E = engine or Engine(params, domain)
+    n, k = domain.n, domain.k
+    bf = cs.blinding_factors()
+    usable = n - (bf + 1)
+    queries = cs.queries()
+    tr = Blake2bWrite(sign_bit)
+    t_last = [time.perf_counter()]
+
+    def lap(name: str) -> None:
+        if timings is not None:
+            now = time.perf_counter()
+            timings[name] = timings.get(name, 0.0) + now - t_last[0]
+            t_last[0] = now
+
+    # ---- create_single_instances (plonk/prover.rs:85-173)
+    if len(instances) != cs.num_instance:
+        raise B2Error(B2_ERR_ARG, "InvalidInstances")
+    tr.common_scalar(vk.transcript_repr)
+    instance_values = np.zeros((cs.num_instance, n, 4), dtype=np.uint64)
+    for i, values in enumerate(instances):
+        if len(values) > usable:
+            raise B2Error(B2_ERR_ARG, "InstanceTooLarge")
+        if len(values):
+            instance_values[i, :len(values)] = _mont_vec(values)
+    if cs.num_instance:
+        for c in E.commit_lagrange(instance_values):
+            tr.common_point(c)
+    instance_polys = E.lagrange_to_coeff(instance_values.copy()) if cs.num_instance else instance_values
+    lap("instance")
+
+    # ---- advice (:964-1010)
+    if advice.shape != (cs.num_advice, n, 4) or advice.dtype != np.uint64 or not advice.flags.c_contiguous:
+        raise B2Error(B2_ERR_ARG, f"advice must be a C-contiguous uint64 array of shape ({cs.num_advice}, {n}, 4)")
+    blind = rng.u16_vec(cs.num_advice * (bf + 1))
+    advice[:, usable:] = _mont_vec(blind).reshape(cs.num_advice, bf + 1, 4)
+    for c in E.commit_lagrange(advice, advice_max_bits):
+        tr.write_point(c)
+    theta = tr.squeeze_challenge()
+    lap("advice")
+
+    # ---- lookups: compress, multiplicities, m commitments (:334-366, logup/prover.rs:70-256)
+    fixed_values = pk.fixed_values
+    ms = np.zeros((len(cs.lookups), n, 4), dtype=np.uint64)
+    m_bits = 16
+    for li, lk in enumerate(cs.lookups):
+        lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
+        comp = E.from_mont(E.compress(lists, advice, fixed_values, instance_values, theta)).reshape(len(lists), n, 4)
+        counts = logup_multiplicity(list(comp[:-1]), comp[-1], usable, n)
+        m_bits = max(m_bits, _max_bits(counts[:usable]))
+        canon = np.zeros((n, 4), dtype=np.uint64)
+        canon[:, 0] = counts.astype(np.uint64)
+        canon[usable:, 0] = rng.u16_vec(bf + 1)
+        ms[li] = E.to_mont(canon)
+    if len(cs.lookups):
+        for c in E.commit_lagrange(ms, m_bits):
+            tr.write_point(c)
+    beta = tr.squeeze_challenge()
+    gamma = tr.squeeze_challenge()
+    lap("lookup_m")
+
+    # ---- z columns (:411-633): permutation, lookups, shuffles -- built on the device, blinded, committed and
+    # brought to coefficient form as ONE batch
+    zs: List[np.ndarray] = []
+    if cs.permutation_columns:
+        chunk_len = cs.degree() - 2
+        n_sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
+        blinds = [rng.fr_vec(bf) for _ in range(n_sets)]
+        zs += E.permutation_commit(cs, pk.sigmas, advice, fixed_values, instance_values, beta, gamma, blinds)
+    n_perm = len(zs)
+    lookup_z_counts = []
+    for li, lk in enumerate(cs.lookups):
+        raw = E.logup_commit_z(cs, lk, advice, fixed_values, instance_values, ms[li], theta, beta)
+        lookup_z_counts.append(len(raw))
+        for z in raw:
+            zs.append(np.concatenate([z, rng.fr_vec(bf)]))
+    for group in cs.shuffles:
+        z = E.shuffle_commit_product(cs, group, advice, fixed_values, instance_values, theta, beta)
+        zs.append(np.concatenate([z, rng.fr_vec(bf)]))
+    z_polys = np.ascontiguousarray(np.stack(zs)) if zs else np.zeros((0, n, 4), np.uint64)
+    if len(zs):
+        for c in E.commit_lagrange_and_ifft(z_polys):
+            tr.write_point(c)
+    perm_polys = [z_polys[i] for i in range(n_perm)]
+    lookups, pos = [], n_perm
+    if len(cs.lookups):
+        ms = E.lagrange_to_coeff(ms)                                     # lagrange_to_coeff_st(l.0), :497
+    for li, cnt in enumerate(lookup_z_counts):
+        lookups.append({"z": [z_polys[pos + i] for i in range(cnt)], "m": ms[li]})
+        pos += cnt
+    shuffle_polys = [z_polys[pos + i] for i in range(len(cs.shuffles))]
+    lap("z_columns")
+
+    # ---- vanishing commit, y (:635-639, vanishing/prover.rs:41-70)
+    random = rng.fr_vec(k)
+    a, u = rng.fr_vec(n), rng.u64_vec(n)
+    b, v = rng.fr_vec(n), rng.u64_vec(n)
+    kk = np.uint64(k)
+    random_poly = E.fr_vec("mul", E.fr_vec("add", a, random[(u % kk).astype(np.int64)]),
+                           E.fr_vec("add", b, random[(v % kk).astype(np.int64)]))
+    tr.write_point(E.commit(random_poly.reshape(1, n, 4))[0])
+    y = tr.squeeze_challenge()
+    lap("vanishing_commit")
+
+    # ---- h(X) (:640-690, vanishing/prover.rs:64-110)
+    advice_polys = E.lagrange_to_coeff(advice)                           # lagrange_to_coeff_st per column, :643-646
+    h_coeffs = E.evaluate_h(pk, advice_polys, instance_polys, y, beta, gamma, theta, lookups, shuffle_polys, perm_polys)
+    n_pieces = h_coeffs.shape[0] // n                                     # par_chunks_exact(n)
+    h_pieces = np.ascontiguousarray(h_coeffs[:n_pieces * n]).reshape(n_pieces, n, 4)
+    for c in E.commit(h_pieces):
+        tr.write_point(c)
+    x = tr.squeeze_challenge()
+    xn = pow(x, n, R)
+    lap("h_poly")
+
+    # ---- evaluations (:694-790)
+    rot = lambda at: x * pow(domain._omega if at >= 0 else domain._omega_inv, abs(at), R) % R      # noqa: E731
+    ev = E.eval_polynomial
+    for col, at in queries["Instance"]:
+        tr.write_scalar(ev(instance_polys[col], rot(at)))
+    for col, at in queries["Advice"]:
+        tr.write_scalar(ev(advice_polys[col], rot(at)))
+    for col, at in queries["Fixed"]:
+        tr.write_scalar(ev(pk.fixed_polys[col], rot(at)))
+    h_poly = E.poly_combine([h_pieces[i] for i in reversed(range(n_pieces))], xn)   # fold acc * xn + piece, rev
+    tr.write_scalar(ev(random_poly, x))
+    for poly in pk.sigma_polys:
+        tr.write_scalar(ev(poly, x))
+    last = -(bf + 1)
+    x_next, x_last = rot(1), rot(last)
+
+    def eval_z_set(polys):
+        for i, z in enumerate(polys):
+            tr.write_scalar(ev(z, x))
+            tr.write_scalar(ev(z, x_next))
+            if i + 1 < len(polys):
+                tr.write_scalar(ev(z, x_last))
+
+    eval_z_set(perm_polys)
+    for lk in lookups:
+        tr.write_scalar(ev(lk["m"], x))
+        eval_z_set(lk["z"])
+    for z in shuffle_polys:
+        tr.write_scalar(ev(z, x))
+        tr.write_scalar(ev(z, x_next))
+    lap("evaluations")
+
+    # ---- multiopen queries (:792-838) as (rotation, point, polynomial)
+    qs: List[Tuple[int, int, np.ndarray]] = []
+
+    def open_z_set(polys):
+        for z in polys:
+            qs.append((0, x, z))
+            qs.append((1, x_next, z))
+        for z in list(reversed(polys))[1:]:
+            qs.append((last, x_last, z))
+
+    for col, at in queries["Instance"]:
+        qs.append((at, rot(at), instance_polys[col]))
+    for col, at in queries["Advice"]:
+        qs.append((at, rot(at), advice_polys[col]))
+    open_z_set(perm_polys)
+    for lk in lookups:
+        qs.append((0, x, lk["m"]))
+        open_z_set(lk["z"])
+    for z in shuffle_polys:
+        qs.append((0, x, z))
+        qs.append((1, x_next, z))
+    for col, at in queries["Fixed"]:
+        qs.append((at, rot(at), pk.fixed_polys[col]))
+    for poly in pk.sigma_polys:
+        qs.append((0, x, poly))
+    qs.append((0, x, h_poly))
+    qs.append((0, x, random_poly))
+
+    gwc_create_proof(E, tr, qs, n)
+    lap("multiopen")
+    return tr.finalize()
+
+
+def gwc_create_proof(E: Engine, tr: Blake2bWrite, queries, n: int) -> None:
+    """poly/multiopen/gwc/prover.rs:19-173.  construct_intermediate_sets (gwc.rs:38-62) groups the queries by
+    ROTATION (BTreeMap<Rotation, _>, ascending), point = the first query's; per group the polynomials are folded with
+    v on the device (the reference's cuda build does the same for groups of more than four), the folded polynomial
+    is evaluated and divided by (X - z) there, and all witness polynomials are committed as one batch."""
+    v = tr.squeeze_challenge()
+    groups: Dict[int, list] = {}
+    for q in queries:
+        groups.setdefault(q[0], []).append(q)
+    witnesses = []
+    for r in sorted(groups):
+        group = groups[r]
+        z = group[0][1]
+        if any(q[1] != z for q in group):
+            raise B2Error(B2_ERR_ARG, "assert_eq!(query.get_point(), z)")
+        poly_batch = E.poly_combine([q[2] for q in group], v)
+        eval_batch = E.eval_polynomial(poly_batch, z)
+        poly_batch[0] = _fr.to_mont((_fr.from_mont(poly_batch[0]) - eval_batch) % R)
+        witnesses.append(E.kate_division(poly_batch, z))
+    for c in E.commit(np.ascontiguousarray(np.stack(witnesses))):
+        tr.write_point(c)

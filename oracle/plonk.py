@@ -251,8 +251,9 @@ class Evaluator:
             ev.lookup_results.append((table, products, sums))
 
         for group in cs.shuffles:                                      # :539-578
-            inputs = [evaluate_lc(a["input_expressions"]) for a in group]
-            shuffles = [evaluate_lc(a["shuffle_expressions"]) for a in group]
+            pairs = [(evaluate_lc(a["input_expressions"]), evaluate_lc(a["shuffle_expressions"])) for a in group]  # :536-548
+            inputs = [p[0] for p in pairs]
+            shuffles = [p[1] for p in pairs]
             product_inputs = ("AddChallenge", inputs[0], "Beta")
             for i, part in list(enumerate(inputs))[1:]:
                 product_inputs = ("LcChallenge", part, ev.add_calculation(product_inputs), "Beta", i + 1)

@@ -1,0 +1,821 @@
+"""CPU oracle for the whole proof: keygen, create_proof (GWC and SHPLONK-free GWC default) and verify_proof.
+
+TEST INFRASTRUCTURE ONLY (same rules as oracle/bn254.py and oracle/plonk.py): only tests/,
+__graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
+
+Restates, with Python big ints (MSMs go through the C restatement, oracle/cpu_ref.c):
+  * transcript::{Blake2bWrite, Blake2bRead, Challenge255}        transcript.rs:14-293
+  * VerifyingKey::hash_into                                     plonk.rs:91-109   (see `vk_transcript_repr`)
+  * keygen_vk / keygen_pk (fixed + permutation parts)           plonk/keygen.rs:213-431, plonk/permutation/keygen.rs:196-262
+  * create_single_instances / create_proof_from_witness         plonk/prover.rs:85-173, 916-1500 (same body as :206-850)
+  * vanishing::Argument::{commit, construct, evaluate, open}    plonk/vanishing/prover.rs:41-153
+  * permutation / logup / shuffle evaluate + open               plonk/permutation/prover.rs:181-304, plonk/logup/prover.rs:420-491,
+                                                                plonk/shuffle/prover.rs:200-240
+  * multiopen::gwc::{create_proof, verify_proof}                poly/multiopen/gwc.rs:38-62, gwc/prover.rs:19-173, gwc/verifier.rs:16-91
+  * verify_proof                                                plonk/verifier.rs:127-507 and the argument verifiers
+                                                                (vanishing/verifier.rs, permutation/verifier.rs,
+                                                                logup/verifier.rs, shuffle/verifier.rs)
+  * Decider::verify                                             poly/multiopen.rs:31-57
+All paths relative to /root/reference/halo2_proofs/src.
+
+PARITY STATUS: byte-level parity with the Rust binary is unpinned (the reference cannot be built here and holds
+no golden proofs).  What pins this file is the reference's own acceptance test strategy (examples / tests:
+create_proof -> verify_proof must accept, a tampered proof / instance must not): tests/test_oracle_prover.py.
+Three inputs are parameters because they cannot be read from the reference tree:
+  * the verifying key's transcript scalar (Rust `{:?}` of PinnedVerificationKey, plonk.rs:100) -- `vk_transcript_repr`
+    hashes a description of its own under the same personalisation and feeds it through the same common_scalar call;
+  * the point compression rule ([EXT], oracle/bn254.py g1_to_bytes) -- `sign_bit`;
+  * randomness: the reference draws from OsRng / thread_rng at four sites (plonk/prover.rs:283, 352, 427;
+    vanishing/prover.rs:57); here every draw comes from the caller's `rng` in the order `create_proof` documents
+    ("thread the caller's rng through").
+The pairing check e(left, [s]G2) * e(right, -G2) == 1 is restated in two equivalent forms: `Decider.verify_trapdoor`
+checks [s]*left == right in G1 with the toxic waste of the synthetic SRS (Params::unsafe_setup keeps no s, the
+test SRS does), and `Decider.verify` runs the optimal-ate pairing (oracle/pairing.py) on [s]G2 alone.
+"""
+from __future__ import annotations
+
+import hashlib
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import bn254 as o
+from . import cref
+from . import plonk as P
+
+R = o.R_MOD
+Q = o.Q_MOD
+Point = Optional[Tuple[int, int]]
+
+
+# --------------------------------------------------------------------------
+# transcript.rs
+# --------------------------------------------------------------------------
+PREFIX_CHALLENGE, PREFIX_POINT, PREFIX_SCALAR = b"\x00", b"\x01", b"\x02"     # transcript.rs:14-20
+
+
+class TranscriptError(Exception):
+    pass
+
+
+class _Blake2b:
+    def __init__(self):
+        self.state = hashlib.blake2b(digest_size=64, person=b"Halo2-Transcript")     # :83-86, :161-164
+
+    def squeeze_challenge(self) -> int:
+        """:121-126, Challenge255::new :266-276 (from_bytes_wide of the 64-byte digest)"""
+        self.state.update(PREFIX_CHALLENGE)
+        return int.from_bytes(self.state.copy().digest(), "little") % R
+
+    def common_point(self, p: Point) -> None:
+        """:128-140"""
+        if p is None:
+            raise TranscriptError("cannot write points at infinity to the transcript")
+        self.state.update(PREFIX_POINT)
+        self.state.update(p[0].to_bytes(32, "little"))
+        self.state.update(p[1].to_bytes(32, "little"))
+
+    def common_scalar(self, s: int) -> None:
+        """:142-147"""
+        self.state.update(PREFIX_SCALAR)
+        self.state.update((s % R).to_bytes(32, "little"))
+
+
+class Blake2bWrite(_Blake2b):
+    def __init__(self, sign_bit: int = 7):
+        super().__init__()
+        self.sign_bit = sign_bit
+        self.proof = bytearray()
+
+    def write_point(self, p: Point) -> None:
+        """:180-184"""
+        self.common_point(p)
+        self.proof += o.g1_to_bytes(p, self.sign_bit)
+
+    def write_scalar(self, s: int) -> None:
+        """:185-189"""
+        self.common_scalar(s)
+        self.proof += (s % R).to_bytes(32, "little")
+
+    def finalize(self) -> bytes:
+        return bytes(self.proof)
+
+
+class Blake2bRead(_Blake2b):
+    def __init__(self, proof: bytes, sign_bit: int = 7):
+        super().__init__()
+        self.sign_bit = sign_bit
+        self.data = bytes(proof)
+        self.pos = 0
+
+    def _take(self) -> bytes:
+        if self.pos + 32 > len(self.data):
+            raise TranscriptError("proof too short")
+        b = self.data[self.pos:self.pos + 32]
+        self.pos += 32
+        return b
+
+    def read_point(self) -> Point:
+        """:93-102"""
+        try:
+            p = o.g1_from_bytes(self._take(), self.sign_bit)
+        except ValueError as e:
+            raise TranscriptError(f"invalid point encoding in proof: {e}")
+        self.common_point(p)
+        return p
+
+    def read_scalar(self) -> int:
+        """:104-116"""
+        s = int.from_bytes(self._take(), "little")
+        if s >= R:
+            raise TranscriptError("invalid field element encoding in proof")
+        self.common_scalar(s)
+        return s
+
+
+# --------------------------------------------------------------------------
+# ConstraintSystem queries (plonk/circuit.rs query_*_index / get_any_query_index)
+# --------------------------------------------------------------------------
+def walk_expression(e, visit) -> None:
+    t = e[0]
+    if t in ("Fixed", "Advice", "Instance"):
+        visit(t, e[1], e[2])
+    elif t in ("Negated", "Scaled"):
+        walk_expression(e[1], visit)
+    elif t in ("Sum", "Product"):
+        walk_expression(e[1], visit)
+        walk_expression(e[2], visit)
+
+
+def collect_queries(cs) -> Dict[str, List[Tuple[int, int]]]:
+    """The (column, rotation) lists ConstraintSystem keeps per column kind.  In the reference their order is the
+    order of the circuit's meta.query_* calls (a front-end matter); the rule here: permutation columns at
+    Rotation::cur first (enable_equality, circuit.rs query_any_index), then gates, lookups (input sets, table),
+    shuffles, each in order of first appearance.  A cs that carries explicit *_queries lists keeps them."""
+    if getattr(cs, "advice_queries", None) is not None:
+        return {"Advice": cs.advice_queries, "Fixed": cs.fixed_queries, "Instance": cs.instance_queries}
+    q: Dict[str, List[Tuple[int, int]]] = {"Advice": [], "Fixed": [], "Instance": []}
+
+    def visit(kind, col, rot):
+        if (col, rot) not in q[kind]:
+            q[kind].append((col, rot))
+
+    for kind, col in cs.permutation_columns:
+        visit(kind, col, 0)
+    for gate in cs.gates:
+        for poly in gate:
+            walk_expression(poly, visit)
+    for lk in cs.lookups:
+        for s in lk["input_expressions_sets"]:
+            for inp in s:
+                for e in inp:
+                    walk_expression(e, visit)
+        for e in lk["table_expressions"]:
+            walk_expression(e, visit)
+    for group in cs.shuffles:
+        for a in group:
+            for e in a["input_expressions"] + a["shuffle_expressions"]:
+                walk_expression(e, visit)
+    cs.advice_queries, cs.fixed_queries, cs.instance_queries = q["Advice"], q["Fixed"], q["Instance"]
+    return q
+
+
+def eval_expression_at_queries(e, queries, fixed_evals, advice_evals, instance_evals) -> int:
+    """Expression::evaluate with the verifier's closures (plonk/verifier.rs:318-331): a column query reads the
+    evaluation at its query index."""
+    t = e[0]
+    if t == "Constant":
+        return e[1]
+    if t in ("Fixed", "Advice", "Instance"):
+        evals = {"Fixed": fixed_evals, "Advice": advice_evals, "Instance": instance_evals}[t]
+        return evals[queries[t].index((e[1], e[2]))]
+    rec = lambda x: eval_expression_at_queries(x, queries, fixed_evals, advice_evals, instance_evals)  # noqa: E731
+    if t == "Negated":
+        return (-rec(e[1])) % R
+    if t == "Sum":
+        return (rec(e[1]) + rec(e[2])) % R
+    if t == "Product":
+        return rec(e[1]) * rec(e[2]) % R
+    if t == "Scaled":
+        return rec(e[1]) * e[2] % R
+    raise ValueError(t)
+
+
+# --------------------------------------------------------------------------
+# Params (synthetic SRS through the C restatement) and commitments
+# --------------------------------------------------------------------------
+def _canonical_limbs(vals: Sequence[int]) -> np.ndarray:
+    out = np.empty((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        out[i] = o._to_limbs(v % R)
+    return out
+
+
+def msm(scalars: Sequence[int], bases: np.ndarray) -> Point:
+    """best_multiexp (arithmetic.rs:465-492, C restatement) -> affine point"""
+    if len(scalars) == 0:
+        return None
+    j = cref.best_multiexp(o.fr_encode(scalars), bases[:len(scalars)])
+    return o.g1_affine_decode(cref.jac_to_affine(j))[0]
+
+
+class Params:
+    """poly/commitment.rs:56-124 (unsafe_setup) with a caller-chosen s; bases as (n, 8) Montgomery affine arrays
+    (the layout the engine registers), commit / commit_lagrange :129-142."""
+
+    def __init__(self, k: int, s: int):
+        self.k, self.n, self.s = k, 1 << k, s % R
+        n = self.n
+        pw, cur = [], 1
+        for _ in range(n):
+            pw.append(cur)
+            cur = cur * s % R
+        self.g = cref.g1_mul_gen(_canonical_limbs(pw))                                # :63-83
+        root = o.FR_ROOT_OF_UNITY
+        for _ in range(k, o.FR_S):
+            root = root * root % R
+        mult = (pow(s, n, R) - 1) * o.fr_inv(n % R) % R
+        lag, rp = [], 1
+        for _ in range(n):
+            lag.append(mult * rp % R * o.fr_inv((s - rp) % R) % R)                    # :85-112
+            rp = rp * root % R
+        self.g_lagrange = cref.g1_mul_gen(_canonical_limbs(lag))
+        self.g1 = o.G1_GEN                                                            # ParamsVerifier.g1
+
+    def commit(self, poly: Sequence[int]) -> Point:
+        assert len(poly) <= self.n
+        return msm(poly, self.g)
+
+    def commit_lagrange(self, poly: Sequence[int]) -> Point:
+        assert len(poly) <= self.n
+        return msm(poly, self.g_lagrange)
+
+
+# --------------------------------------------------------------------------
+# keygen
+# --------------------------------------------------------------------------
+def vk_transcript_repr(cs, domain, fixed_commitments, permutation_commitments) -> int:
+    """plonk.rs:91-109 hashes Rust's `{:?}` of the pinned verifying key (Blake2b, personal "Halo2-Verify-Key",
+    u64 length prefix) and absorbs from_bytes_wide(digest) with common_scalar.  The Debug text is not
+    reproducible without the crate, so the string hashed here is this file's own description of the same
+    contents; callers that hold the reference's scalar pass it to create_proof / verify_proof instead."""
+    q = collect_queries(cs)
+    s = repr({
+        "base_modulus": hex(Q), "scalar_modulus": hex(R),
+        "domain": {"k": domain.k, "extended_k": domain.extended_k, "omega": hex(domain.omega)},
+        "fixed_commitments": fixed_commitments, "permutation": permutation_commitments,
+        "cs": {"num_fixed": cs.num_fixed, "num_advice": cs.num_advice, "num_instance": cs.num_instance,
+               "gates": cs.gates, "lookups": cs.lookups, "shuffles": cs.shuffles,
+               "permutation_columns": cs.permutation_columns, "queries": q,
+               "degree": cs.degree(), "blinding_factors": cs.blinding_factors()},
+    }).encode()
+    h = hashlib.blake2b(digest_size=64, person=b"Halo2-Verify-Key")
+    h.update(len(s).to_bytes(8, "little"))
+    h.update(s)
+    return int.from_bytes(h.digest(), "little") % R
+
+
+class VerifyingKey:
+    def __init__(self, cs, domain, fixed_commitments, permutation_commitments, transcript_repr=None):
+        self.cs, self.domain = cs, domain
+        self.fixed_commitments = fixed_commitments
+        self.permutation_commitments = permutation_commitments
+        self.queries = collect_queries(cs)
+        self.transcript_repr = (vk_transcript_repr(cs, domain, fixed_commitments, permutation_commitments)
+                                if transcript_repr is None else transcript_repr % R)
+
+
+class ProvingKey:
+    pass
+
+
+def keygen(params: Params, cs, fixed: Sequence[Sequence[int]], mapping, zeta: Optional[int] = None,
+           transcript_repr: Optional[int] = None) -> ProvingKey:
+    """keygen_vk + keygen_pk (plonk/keygen.rs:213-431) for an already laid out circuit: `fixed` are the fixed
+    columns (selectors included, already compressed or not -- a front-end matter), `mapping` the permutation
+    (oracle/plonk.py identity_mapping / mapping_copy)."""
+    domain = o.EvaluationDomain(cs.degree(), params.k) if zeta is None else o.EvaluationDomain(cs.degree(), params.k, zeta)
+    assert len(fixed) == cs.num_fixed and all(len(c) == params.n for c in fixed)
+    sigmas = P.permutation_sigmas(cs, domain, mapping)
+    fixed_commitments = [params.commit_lagrange(c) for c in fixed]               # keygen.rs:288-291
+    permutation_commitments = [params.commit_lagrange(s) for s in sigmas]        # permutation/keygen.rs:244-251
+    pk = ProvingKey()
+    pk.vk = VerifyingKey(cs, domain, fixed_commitments, permutation_commitments, transcript_repr)
+    pk.fixed_values = [list(c) for c in fixed]
+    pk.fixed_polys = [domain.lagrange_to_coeff(c) for c in fixed]               # keygen.rs:381-385
+    pk.sigmas = sigmas
+    pk.sigma_polys = [domain.lagrange_to_coeff(s) for s in sigmas]              # permutation/keygen.rs:254-262
+    pk.l0, pk.l_last, pk.l_active_row = P.lagrange_basis_cosets(cs, domain)     # keygen.rs:398-431
+    pk.ev = P.Evaluator.new(cs)                                                  # keygen.rs:433
+    return pk
+
+
+# --------------------------------------------------------------------------
+# randomness: adapter from the caller's vector RNG to the scalar draws of oracle/plonk.py
+# --------------------------------------------------------------------------
+class _RngAdapter:
+    """oracle/plonk.py draws blinding values one at a time with rng.randrange(modulus); the proof-level RNG
+    contract is in blocks (create_proof docstring).  A block is fetched when the first value of it is asked for."""
+
+    def __init__(self, rng, fr_block: int, u16_block: int):
+        self.rng, self.fr_block, self.u16_block = rng, fr_block, u16_block
+        self.fr_q: List[int] = []
+        self.u16_q: List[int] = []
+
+    def randrange(self, m: int) -> int:
+        if m == R:
+            if not self.fr_q:
+                self.fr_q = o.fr_decode(self.rng.fr_vec(self.fr_block))
+            return self.fr_q.pop(0)
+        if m == 1 << 16:
+            if not self.u16_q:
+                self.u16_q = [int(v) for v in self.rng.u16_vec(self.u16_block)]
+            return self.u16_q.pop(0)
+        raise ValueError(m)
+
+
+# --------------------------------------------------------------------------
+# create_proof
+# --------------------------------------------------------------------------
+def vanishing_random_poly(domain, rng) -> List[int]:
+    """vanishing/prover.rs:48-63 with the caller's rng (the reference mixes `rng` with thread_rng):
+    random = k field elements; coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]), the four streams
+    drawn as a = fr_vec(n), u = u64_vec(n), b = fr_vec(n), v = u64_vec(n)."""
+    k, n = domain.k, domain.n
+    random = o.fr_decode(rng.fr_vec(k))
+    a = o.fr_decode(rng.fr_vec(n))
+    u = [int(x) for x in rng.u64_vec(n)]
+    b = o.fr_decode(rng.fr_vec(n))
+    v = [int(x) for x in rng.u64_vec(n)]
+    return [(a[i] + random[u[i] % k]) * (b[i] + random[v[i] % k]) % R for i in range(n)]
+
+
+def scalar_bits(v: int) -> int:
+    return v.bit_length()
+
+
+def binary_search_index(sorted_pairs, value: int) -> int:
+    """<[T]>::binary_search_by_key as implemented by the pinned toolchain (nightly-2023-06-01, core::slice):
+    probes mid = left + size / 2 and returns the first probe that compares Equal -- which decides the row that
+    gets the multiplicity when the table repeats a value (logup/prover.rs:115-117, 146-150)."""
+    size = len(sorted_pairs)
+    left, right = 0, size
+    while left < right:
+        mid = left + size // 2
+        t = sorted_pairs[mid][0]
+        if t < value:
+            left = mid + 1
+        elif t > value:
+            right = mid
+        else:
+            return sorted_pairs[mid][1]
+        size = right - left
+    raise KeyError("logup binary_search_by_key should hit")
+
+
+def logup_multiplicity(input_sets, table, usable: int, n: int) -> List[int]:
+    """logup/prover.rs:115-184: stable sort of (value, row) by value (canonical integer order, Ord for Fr is
+    [EXT]), binary search per input value, counts credited to the row the search returns."""
+    pairs = sorted(((table[i], i) for i in range(usable)), key=lambda p: p[0])
+    m = [0] * n
+    cache: Dict[int, int] = {}
+    for s in input_sets:
+        for inp in s:
+            for v in inp[:usable]:
+                if v not in cache:
+                    cache[v] = binary_search_index(pairs, v)
+                m[cache[v]] += 1
+    return m
+
+
+def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]], instances: Sequence[Sequence[int]],
+                 rng, sign_bit: int = 7) -> bytes:
+    """plonk/prover.rs:916-1500 (create_proof_from_witness: the advice columns are given, as read by fetch_witness)
+    with the GWC multiopen (`create_proof`, :1759-1781: use_gwc = true), one circuit instance per proof.
+
+    `rng` supplies every random value, in this order (vector draws; fr_vec returns Montgomery limbs):
+      1. u16_vec(num_advice * (bf + 1)): blinding rows of advice column i are [i*(bf+1), (i+1)*(bf+1))   (:973-977)
+      2. per lookup: u16_vec(bf + 1) for the blinding rows of m                                         (logup/prover.rs:232-236)
+      3. per permutation set: fr_vec(bf)                                                                (permutation/prover.rs:156-158)
+      4. per lookup, per z: fr_vec(bf)                                                                  (plonk/prover.rs:445-449)
+      5. per shuffle group: fr_vec(bf)                                                                  (plonk/prover.rs:518-521)
+      6. vanishing_random_poly                                                                          (vanishing/prover.rs:48-63)
+    """
+    vk = pk.vk
+    cs, domain = vk.cs, vk.domain
+    n, k = params.n, params.k
+    bf = cs.blinding_factors()
+    usable = n - (bf + 1)
+    queries = vk.queries
+    tr = Blake2bWrite(sign_bit)
+    lag2coeff = domain.lagrange_to_coeff
+
+    # ---- create_single_instances :85-173
+    if len(instances) != cs.num_instance:
+        raise ValueError("InvalidInstances")
+    tr.common_scalar(vk.transcript_repr)                                       # vk.hash_into
+    instance_values = []
+    for values in instances:
+        if len(values) > usable:
+            raise ValueError("InstanceTooLarge")
+        instance_values.append([v % R for v in values] + [0] * (n - len(values)))
+    for poly in instance_values:
+        tr.common_point(params.commit_lagrange(poly))                          # :124-137
+    instance_polys = [lag2coeff(p) for p in instance_values]
+
+    # ---- advice :964-1010
+    assert len(advice) == cs.num_advice
+    blind = [int(v) for v in rng.u16_vec(cs.num_advice * (bf + 1))]
+    advice_values = []
+    for i, col in enumerate(advice):
+        col = [v % R for v in col[:usable]] + blind[i * (bf + 1):(i + 1) * (bf + 1)]
+        assert len(col) == n
+        advice_values.append(col)
+    for col in advice_values:
+        tr.write_point(params.commit_lagrange(col))                            # commit_lagrange_with_bound: same point
+    theta = tr.squeeze_challenge()
+
+    # ---- lookups: compress, m commitments (:334-366)
+    adapter = _RngAdapter(rng, bf, bf + 1)
+    lookups = []
+    for lk in cs.lookups:
+        comp = lambda ex: P.evaluate_with_theta(ex, n, 1, pk.fixed_values, advice_values, instance_values, theta)  # noqa: E731
+        input_sets = [[comp(inp) for inp in s] for s in lk["input_expressions_sets"]]
+        table = comp(lk["table_expressions"])
+        m = logup_multiplicity(input_sets, table, usable, n)
+        for i in range(usable, n):
+            m[i] = adapter.randrange(1 << 16)
+        lookups.append({"input_sets": input_sets, "table": table, "m": m})
+    for lk in lookups:
+        tr.write_point(params.commit_lagrange(lk["m"]))
+    beta = tr.squeeze_challenge()
+    gamma = tr.squeeze_challenge()
+
+    # ---- z columns (:411-633); transcript order: permutation, lookups, shuffles
+    perm_z = P.permutation_commit(cs, domain, pk.sigmas, advice_values, pk.fixed_values, instance_values, beta, gamma,
+                                  adapter) if cs.permutation_columns else []
+    for lk in lookups:
+        zs = P.logup_commit_z(cs, domain, lk["input_sets"], lk["table"], lk["m"], beta)
+        lk["z"] = [P.blind_to_n(z, n, adapter) for z in zs]
+    shuffle_z = [P.blind_to_n(P.shuffle_commit_product(cs, domain, g, theta, beta, advice_values, pk.fixed_values,
+                                                       instance_values), n, adapter) for g in cs.shuffles]
+    for z in perm_z:
+        tr.write_point(params.commit_lagrange(z))
+    for lk in lookups:
+        for z in lk["z"]:
+            tr.write_point(params.commit_lagrange(z))
+    for z in shuffle_z:
+        tr.write_point(params.commit_lagrange(z))
+    perm_polys = [lag2coeff(z) for z in perm_z]
+    for lk in lookups:
+        lk["z_polys"] = [lag2coeff(z) for z in lk["z"]]
+        lk["m_poly"] = lag2coeff(lk["m"])
+    shuffle_polys = [lag2coeff(z) for z in shuffle_z]
+
+    # ---- vanishing commit, y (:635-639)
+    random_poly = vanishing_random_poly(domain, rng)
+    tr.write_point(params.commit(random_poly))
+    y = tr.squeeze_challenge()
+
+    # ---- h(X) (:640-690, vanishing/prover.rs:64-110)
+    advice_polys = [lag2coeff(c) for c in advice_values]
+    ext = domain.coeff_to_extended
+    h = P.evaluate_h(pk.ev, cs, domain, [ext(p) for p in pk.fixed_polys], [ext(p) for p in advice_polys],
+                     [ext(p) for p in instance_polys], pk.l0, pk.l_last, pk.l_active_row,
+                     [ext(p) for p in pk.sigma_polys], y, beta, gamma, theta,
+                     [{"z_cosets": [ext(z) for z in lk["z_polys"]], "m_coset": ext(lk["m_poly"])} for lk in lookups],
+                     [ext(p) for p in shuffle_polys], [ext(p) for p in perm_polys])
+    h_coeffs = domain.extended_to_coeff(domain.divide_by_vanishing_poly(h))
+    h_pieces = [h_coeffs[i:i + n] for i in range(0, len(h_coeffs) - n + 1, n)]  # par_chunks_exact(n)
+    for piece in h_pieces:
+        tr.write_point(params.commit(piece))
+    x = tr.squeeze_challenge()
+    xn = pow(x, n, R)
+
+    # ---- evaluations (:694-790)
+    rot = domain.rotate_omega
+    ev = o.eval_polynomial
+    for col, at in queries["Instance"]:
+        tr.write_scalar(ev(instance_polys[col], rot(x, at)))
+    for col, at in queries["Advice"]:
+        tr.write_scalar(ev(advice_polys[col], rot(x, at)))
+    for col, at in queries["Fixed"]:
+        tr.write_scalar(ev(pk.fixed_polys[col], rot(x, at)))
+    h_poly = [0] * n                                                          # vanishing/prover.rs:119-123
+    for piece in reversed(h_pieces):
+        h_poly = [(a * xn + b) % R for a, b in zip(h_poly, piece)]
+    tr.write_scalar(ev(random_poly, x))
+    for poly in pk.sigma_polys:                                               # permutation/prover.rs:194-205
+        tr.write_scalar(ev(poly, x))
+    x_next, x_last = rot(x, 1), rot(x, -(bf + 1))
+    for i, z in enumerate(perm_polys):                                        # permutation/prover.rs:208-252
+        tr.write_scalar(ev(z, x))
+        tr.write_scalar(ev(z, x_next))
+        if i + 1 < len(perm_polys):
+            tr.write_scalar(ev(z, x_last))
+    for lk in lookups:                                                        # logup/prover.rs:421-447
+        tr.write_scalar(ev(lk["m_poly"], x))
+        for i, z in enumerate(lk["z_polys"]):
+            tr.write_scalar(ev(z, x))
+            tr.write_scalar(ev(z, x_next))
+            if i + 1 < len(lk["z_polys"]):
+                tr.write_scalar(ev(z, x_last))
+    for z in shuffle_polys:                                                   # shuffle/prover.rs:201-215
+        tr.write_scalar(ev(z, x))
+        tr.write_scalar(ev(z, x_next))
+
+    # ---- queries for the multiopen argument (:792-838): (rotation, point, polynomial)
+    qs: List[Tuple[int, int, List[int]]] = []
+    for col, at in queries["Instance"]:
+        qs.append((at, rot(x, at), instance_polys[col]))
+    for col, at in queries["Advice"]:
+        qs.append((at, rot(x, at), advice_polys[col]))
+    for z in perm_polys:                                                      # permutation/prover.rs:257-303
+        qs.append((0, x, z))
+        qs.append((1, x_next, z))
+    for z in list(reversed(perm_polys))[1:]:
+        qs.append((-(bf + 1), x_last, z))
+    for lk in lookups:                                                        # logup/prover.rs:451-491
+        qs.append((0, x, lk["m_poly"]))
+        for z in lk["z_polys"]:
+            qs.append((0, x, z))
+            qs.append((1, x_next, z))
+        for z in list(reversed(lk["z_polys"]))[1:]:
+            qs.append((-(bf + 1), x_last, z))
+    for z in shuffle_polys:                                                   # shuffle/prover.rs:219-239
+        qs.append((0, x, z))
+        qs.append((1, x_next, z))
+    for col, at in queries["Fixed"]:
+        qs.append((at, rot(x, at), pk.fixed_polys[col]))
+    for poly in pk.sigma_polys:                                               # permutation/prover.rs:182-192
+        qs.append((0, x, poly))
+    qs.append((0, x, h_poly))                                                 # vanishing/prover.rs:135-152
+    qs.append((0, x, random_poly))
+
+    gwc_create_proof(params, tr, qs)
+    return tr.finalize()
+
+
+def construct_intermediate_sets(queries):
+    """poly/multiopen/gwc.rs:38-62: BTreeMap<Rotation, Vec<Q>> -- queries grouped by ROTATION (this fork; upstream
+    groups by point), groups in ascending rotation order, queries in arrival order, point = first query's."""
+    groups: Dict[int, list] = {}
+    for q in queries:
+        groups.setdefault(q[0], []).append(q)
+    return [(groups[r][0][1], groups[r]) for r in sorted(groups)]
+
+
+def gwc_create_proof(params: Params, tr: Blake2bWrite, queries) -> None:
+    """poly/multiopen/gwc/prover.rs:19-173 (the sort by batch size only schedules work; W's are written in set order)"""
+    v = tr.squeeze_challenge()
+    for z, group in construct_intermediate_sets(queries):
+        poly_batch = [0] * params.n
+        for q in group:
+            assert q[1] == z
+            poly_batch = [(a * v + b) % R for a, b in zip(poly_batch, q[2])]
+        eval_batch = o.eval_polynomial(poly_batch, z)
+        poly_batch[0] = (poly_batch[0] - eval_batch) % R
+        witness = o.kate_division(poly_batch, z)
+        tr.write_point(params.commit(witness))
+
+
+# --------------------------------------------------------------------------
+# verify_proof
+# --------------------------------------------------------------------------
+class VerifyError(Exception):
+    pass
+
+
+def _g1_lincomb(terms: Sequence[Tuple[int, Point]]) -> Point:
+    """evaluate an MSM<C> (poly/msm.rs): sum of scalar * point"""
+    terms = [(s % R, p) for s, p in terms if p is not None and s % R]
+    if not terms:
+        return None
+    return msm([s for s, _ in terms], o.g1_affine_encode([p for _, p in terms]))
+
+
+def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[int]], proof: bytes,
+                 sign_bit: int = 7, pairing: bool = False) -> bool:
+    """plonk/verifier.rs:127-507 with SingleVerifier and the GWC multiopen; False = the final check failed,
+    VerifyError / TranscriptError = the proof is malformed.  `pairing=True` decides with the optimal-ate pairing
+    on [s]G2 (Decider::verify); the default decides with the equivalent G1 equation [s]*left == right."""
+    cs, domain = vk.cs, vk.domain
+    n = params.n
+    bf = cs.blinding_factors()
+    queries = vk.queries
+    if len(instances) != cs.num_instance:
+        raise VerifyError("InvalidInstances")
+    instance_commitments = []
+    for inst in instances:                                                    # :148-162
+        if len(inst) > n - (bf + 1):
+            raise VerifyError("InstanceTooLarge")
+        instance_commitments.append(params.commit_lagrange([v % R for v in inst]))
+    tr = Blake2bRead(proof, sign_bit)
+    tr.common_scalar(vk.transcript_repr)                                      # :167
+    for c in instance_commitments:
+        tr.common_point(c)
+    advice_commitments = [tr.read_point() for _ in range(cs.num_advice)]
+    theta = tr.squeeze_challenge()
+    m_commitments = [tr.read_point() for _ in cs.lookups]
+    beta = tr.squeeze_challenge()
+    gamma = tr.squeeze_challenge()
+    chunk_len = cs.degree() - 2
+    n_sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
+    perm_commitments = [tr.read_point() for _ in range(n_sets)]
+    lookup_z_commitments = [[tr.read_point() for _ in lk["input_expressions_sets"]] for lk in cs.lookups]
+    shuffle_commitments = [tr.read_point() for _ in cs.shuffles]
+    random_poly_commitment = tr.read_point()
+    y = tr.squeeze_challenge()
+    h_commitments = [tr.read_point() for _ in range(domain.quotient_poly_degree)]
+    x = tr.squeeze_challenge()
+    instance_evals = [tr.read_scalar() for _ in queries["Instance"]]
+    advice_evals = [tr.read_scalar() for _ in queries["Advice"]]
+    fixed_evals = [tr.read_scalar() for _ in queries["Fixed"]]
+    random_eval = tr.read_scalar()
+    permutation_evals = [tr.read_scalar() for _ in vk.permutation_commitments]
+    perm_sets = []
+    for i, c in enumerate(perm_commitments):                                  # permutation/verifier.rs:74-101
+        e, ne = tr.read_scalar(), tr.read_scalar()
+        le = tr.read_scalar() if i + 1 < len(perm_commitments) else None
+        perm_sets.append({"c": c, "eval": e, "next": ne, "last": le})
+    lookups = []
+    for mc, zcs in zip(m_commitments, lookup_z_commitments):                  # logup/verifier.rs:70-101
+        m_eval = tr.read_scalar()
+        zsets = []
+        for i, c in enumerate(zcs):
+            e, ne = tr.read_scalar(), tr.read_scalar()
+            le = tr.read_scalar() if i + 1 < len(zcs) else None
+            zsets.append({"c": c, "eval": e, "next": ne, "last": le})
+        lookups.append({"m_c": mc, "m_eval": m_eval, "z": zsets})
+    shuffles = [{"c": c, "eval": tr.read_scalar(), "next": tr.read_scalar()} for c in shuffle_commitments]
+
+    # ---- expected h(x) (:280-399)
+    xn = pow(x, n, R)
+    l_evals = domain.l_i_range(x, xn, range(-(bf + 1), 1))
+    assert len(l_evals) == 2 + bf
+    l_last = l_evals[0]
+    l_blind = sum(l_evals[1:1 + bf]) % R
+    l_0 = l_evals[1 + bf]
+    active = (1 - (l_last + l_blind)) % R
+    ee = lambda e: eval_expression_at_queries(e, queries, fixed_evals, advice_evals, instance_evals)  # noqa: E731
+    comp = lambda exprs: _fold([ee(e) for e in exprs], theta)                 # noqa: E731
+
+    def col_eval(column):
+        kind, idx = column
+        evals = {"Fixed": fixed_evals, "Advice": advice_evals, "Instance": instance_evals}[kind]
+        return evals[queries[kind].index((idx, 0))]                          # get_any_query_index(column, cur)
+
+    exprs: List[int] = []
+    for gate in cs.gates:
+        for poly in gate:
+            exprs.append(ee(poly))
+    # permutation/verifier.rs:105-203
+    if perm_sets:
+        exprs.append(l_0 * (1 - perm_sets[0]["eval"]) % R)
+        last = perm_sets[-1]["eval"]
+        exprs.append((last * last - last) * l_last % R)
+        for i in range(1, len(perm_sets)):
+            exprs.append((perm_sets[i]["eval"] - perm_sets[i - 1]["last"]) * l_0 % R)
+        for ci, st in enumerate(perm_sets):
+            columns = cs.permutation_columns[ci * chunk_len:(ci + 1) * chunk_len]
+            pevals = permutation_evals[ci * chunk_len:(ci + 1) * chunk_len]
+            left = st["next"]
+            for column, pe in zip(columns, pevals):
+                left = left * ((col_eval(column) + beta * pe + gamma) % R) % R
+            right = st["eval"]
+            cur_delta = beta * x % R * pow(P.FR_DELTA, ci * chunk_len, R) % R
+            for column in columns:
+                right = right * ((col_eval(column) + cur_delta + gamma) % R) % R
+                cur_delta = cur_delta * P.FR_DELTA % R
+            exprs.append((left - right) * active % R)
+    # logup/verifier.rs:104-218
+    for lk, arg in zip(lookups, cs.lookups):
+        zs = lk["z"]
+        exprs.append(l_0 * zs[0]["eval"] % R)
+        exprs.append(l_last * zs[-1]["eval"] % R)
+        phi = [(comp(inp) + beta) % R for inp in arg["input_expressions_sets"][0]]
+        tau = (comp(arg["table_expressions"]) + beta) % R
+        product_fi = _prod(phi)
+        sum_inv = sum(o.fr_inv(p) if p else 0 for p in phi) % R
+        left = (tau * (zs[0]["next"] - zs[0]["eval"]) + lk["m_eval"]) % R * product_fi % R
+        right = tau * product_fi % R * sum_inv % R
+        exprs.append((left - right) * active % R)
+        for i in range(1, len(zs)):
+            exprs.append(l_0 * (zs[i]["eval"] - zs[i - 1]["last"]) % R)
+        for zset, iset in list(zip(zs, arg["input_expressions_sets"]))[1:]:
+            phi = [(comp(inp) + beta) % R for inp in iset]
+            product_fi = _prod(phi)
+            sum_inv = sum(o.fr_inv(p) if p else 0 for p in phi) % R
+            exprs.append((zset["next"] - zset["eval"] - sum_inv) * product_fi % R * active % R)
+    # shuffle/verifier.rs:58-121
+    for sh, group in zip(shuffles, cs.shuffles):
+        exprs.append(l_0 * (1 - sh["eval"]) % R)
+        exprs.append(l_last * (sh["eval"] * sh["eval"] - sh["eval"]) % R)
+        ps, pi = 1, 1
+        for i, a in enumerate(group):
+            ch = pow(beta, 1 + i, R)
+            ps = ps * ((comp(a["shuffle_expressions"]) + ch) % R) % R
+            pi = pi * ((comp(a["input_expressions"]) + ch) % R) % R
+        exprs.append((sh["next"] * ps - sh["eval"] * pi) * active % R)
+    expected_h_eval = _fold(exprs, y) * o.fr_inv((xn - 1) % R) % R          # vanishing/verifier.rs:88-96
+
+    # h_commitment MSM: sum xn^i * h_i (vanishing/verifier.rs:98-106)
+    h_terms, pw = [], 1
+    for c in h_commitments:
+        h_terms.append((pw, c))
+        pw = pw * xn % R
+
+    # ---- verifier queries (:401-488): (rotation, point, commitment terms, eval)
+    rot = domain.rotate_omega
+    x_next, x_last = rot(x, 1), rot(x, -(bf + 1))
+    qs = []
+    one = lambda c: [(1, c)]                                                   # noqa: E731
+    for (col, at), e in zip(queries["Instance"], instance_evals):
+        qs.append((at, rot(x, at), one(instance_commitments[col]), e))
+    for (col, at), e in zip(queries["Advice"], advice_evals):
+        qs.append((at, rot(x, at), one(advice_commitments[col]), e))
+    for st in perm_sets:
+        qs.append((0, x, one(st["c"]), st["eval"]))
+        qs.append((1, x_next, one(st["c"]), st["next"]))
+    for st in list(reversed(perm_sets))[1:]:
+        qs.append((-(bf + 1), x_last, one(st["c"]), st["last"]))
+    for lk in lookups:
+        qs.append((0, x, one(lk["m_c"]), lk["m_eval"]))
+        for st in lk["z"]:
+            qs.append((0, x, one(st["c"]), st["eval"]))
+            qs.append((1, x_next, one(st["c"]), st["next"]))
+        for st in list(reversed(lk["z"]))[1:]:
+            qs.append((-(bf + 1), x_last, one(st["c"]), st["last"]))
+    for sh in shuffles:
+        qs.append((0, x, one(sh["c"]), sh["eval"]))
+        qs.append((1, x_next, one(sh["c"]), sh["next"]))
+    for (col, at), e in zip(queries["Fixed"], fixed_evals):
+        qs.append((at, rot(x, at), one(vk.fixed_commitments[col]), e))
+    for c, e in zip(vk.permutation_commitments, permutation_evals):
+        qs.append((0, x, one(c), e))
+    qs.append((0, x, h_terms, expected_h_eval))
+    qs.append((0, x, one(random_poly_commitment), random_eval))
+
+    left, right = gwc_verify_proof(params, tr, qs)
+    if pairing:
+        return Decider.verify(params, left, right)
+    return Decider.verify_trapdoor(params, left, right)
+
+
+def _fold(vals: Sequence[int], c: int) -> int:
+    acc = 0
+    for v in vals:
+        acc = (acc * c + v) % R
+    return acc
+
+
+def _prod(vals: Sequence[int]) -> int:
+    acc = 1
+    for v in vals:
+        acc = acc * v % R
+    return acc
+
+
+def gwc_verify_proof(params: Params, tr: Blake2bRead, queries) -> Tuple[Point, Point]:
+    """poly/multiopen/gwc/verifier.rs:16-91 -> (left, right) of the PairMSM, evaluated"""
+    v = tr.squeeze_challenge()
+    u = tr.squeeze_challenge()
+    commitment_multi: List[Tuple[int, Point]] = []
+    eval_multi = 0
+    witness: List[Tuple[int, Point]] = []
+    witness_with_aux: List[Tuple[int, Point]] = []
+    scale = lambda terms, c: [(s * c % R, p) for s, p in terms]               # noqa: E731
+    for z, group in construct_intermediate_sets(queries):
+        try:
+            wi = tr.read_point()
+        except TranscriptError:
+            raise VerifyError("SamplingError")
+        witness_with_aux = scale(witness_with_aux, u) + [(z, wi)]
+        witness = scale(witness, u) + [(1, wi)]
+        commitment_multi = scale(commitment_multi, u)
+        eval_multi = eval_multi * u % R
+        commitment_batch: List[Tuple[int, Point]] = []
+        eval_batch = 0
+        for q in group:
+            assert q[1] == z
+            commitment_batch = scale(commitment_batch, v) + list(q[2])
+            eval_batch = (eval_batch * v + q[3]) % R
+        commitment_multi += commitment_batch
+        eval_multi = (eval_multi + eval_batch) % R
+    left = _g1_lincomb(witness)
+    right = _g1_lincomb(witness_with_aux + commitment_multi + [(eval_multi, o.g1_neg(params.g1))])
+    return left, right
+
+
+class Decider:
+    """poly/multiopen.rs:31-57: e(left, [s]G2) * e(right, -G2) == 1"""
+
+    @staticmethod
+    def verify_trapdoor(params: Params, left: Point, right: Point) -> bool:
+        return o.g1_mul(left, params.s) == right
+
+    @staticmethod
+    def verify(params: Params, left: Point, right: Point) -> bool:
+        from . import pairing as pr
+        s_g2 = pr.g2_mul(pr.G2_GEN, params.s)                                # ParamsVerifier.s_g2 (commitment.rs:114-118)
+        return pr.pairing_check([(left, s_g2), (right, pr.g2_neg(pr.G2_GEN))])

@@ -1,0 +1,231 @@
+"""CPU tests of the prover mirror's HOST logic (halo2_gpu_specific_b200/plonk.py, transcript.py): the same
+create_proof / keygen code that drives the device engine is run here over a test double that answers every numeric
+call with the CPU oracle (tests/oracle_engine.py), and must produce the oracle prover's bytes (oracle/prover.py,
+written independently from the reference) -- transcript order, RNG order, query grouping, multiplicities and the
+Evaluator graph are all host decisions.  The device engine itself is covered by tests/test_gpu_prover.py."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+import plonk_fixture as fxm
+from oracle import bn254 as o
+from oracle import plonk as P
+from oracle import prover as PR
+from oracle_engine import OracleEngine
+
+from halo2_gpu_specific_b200 import plonk as HP
+from halo2_gpu_specific_b200 import transcript as HT
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import plonk_bench_circuit as bench_circuit  # noqa: E402
+
+R = o.R_MOD
+enc, dec = o.fr_encode, o.fr_decode
+S_TOXIC = 0x2B200B200B200B200B200B200B200B2001
+
+
+class HostParams:
+    """what keygen / create_proof read from Params when the engine is injected"""
+
+    def __init__(self, k):
+        self.k, self.n = k, 1 << k
+
+
+def both_sides(k, seed):
+    fx = fxm.build(k=k, seed=seed)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, S_TOXIC)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+    eng = OracleEngine(oparams, opk.vk.domain, ocs)
+    pk = HP.keygen(HostParams(k), cs, np.stack([enc(c) for c in fx["fixed"]]), np.array(fx["mapping"], dtype=np.int64),
+                   engine=eng, transcript_repr=opk.vk.transcript_repr)
+    return fx, oparams, opk, cs, eng, pk
+
+
+def test_evaluator_graph_matches_reference_construction():
+    """Evaluator::new: same constants, rotations, calculations (order and sharing), value parts, lookup and
+    shuffle results as the oracle's restatement of evaluation.rs:307-448"""
+    for seed in (3, 11):
+        fx = fxm.build(k=5, seed=seed)
+        parts = HP.evaluator_parts(HP.ConstraintSystem.like(fx["cs"]))
+        ev = P.Evaluator.new(fx["cs"])
+        assert parts["rotations"] == ev.rotations and parts["constants"] == ev.constants
+        assert parts["calculations"] == ev.calculations
+        assert parts["value_parts"] == ev.value_parts
+        assert parts["lookup_results"] == ev.lookup_results
+        assert parts["shuffle_results"] == ev.shuffle_results
+
+
+def test_evaluator_graph_simplifications():
+    cs = HP.ConstraintSystem(1, 2, 0, degree=3)
+    a, b = ("Advice", 0, 0), ("Advice", 1, 0)
+    cs.gates.append([("Product", a, b), ("Product", b, a), ("Sum", ("Product", a, b), ("Constant", 0)),
+                     ("Scaled", a, 1), ("Scaled", b, 0), ("Negated", ("Constant", 1)),
+                     ("Sum", ("Constant", 0), ("Negated", b))])
+    p = HP.evaluator_parts(cs)
+    assert p["constants"][:2] == [0, 1] and p["constants"][2] == R - 1
+    assert sum(1 for c in p["calculations"] if c[0] == "Mul") == 1          # a*b and b*a share one slot
+    vp = p["value_parts"]
+    assert vp[0] == vp[1] == vp[2]
+    assert vp[4] == ("Constant", 0) and vp[5] == ("Constant", 2)
+    assert vp[6] == vp[3 + 0] or p["calculations"][vp[6][1]] == ("Store", ("Advice", 1, 0))   # (sic) 0 - b -> b
+
+
+def test_queries_follow_the_documented_rule():
+    fx = fxm.build(k=5, seed=3)
+    cs = HP.ConstraintSystem.like(fx["cs"])
+    q = cs.queries()
+    assert q == PR.collect_queries(fx["cs"])
+    assert q["Advice"][:3] == [(0, 0), (1, 0), (2, 0)] and (0, 1) in q["Advice"] and (2, -1) in q["Advice"]
+    assert q["Fixed"][0] == (5, 0) and q["Instance"] == [(0, 0)]
+    explicit = HP.ConstraintSystem(**bench_circuit.constraint_system_args())
+    assert explicit.queries()["Fixed"] == [(1, 0), (2, 0), (3, 0), (0, 0)]
+
+
+def test_keygen_matches_oracle():
+    fx, oparams, opk, cs, eng, pk = both_sides(5, 11)
+    assert pk.vk.fixed_commitments == opk.vk.fixed_commitments
+    assert pk.vk.permutation_commitments == opk.vk.permutation_commitments
+    for got, want in ((pk.sigmas, opk.sigmas), (pk.sigma_polys, opk.sigma_polys), (pk.fixed_polys, opk.fixed_polys)):
+        assert len(got) == len(want)
+        for a, b in zip(got, want):
+            assert np.array_equal(a, enc(b))
+    assert np.array_equal(pk.l0, enc(opk.l0))
+    assert np.array_equal(pk.l_last, enc(opk.l_last))
+    assert np.array_equal(pk.l_active_row, enc(opk.l_active_row))
+    # without an explicit scalar the key hashes its own description, deterministically
+    a = HP.VerifyingKey(cs, pk.vk.domain, pk.vk.fixed_commitments, pk.vk.permutation_commitments, None)
+    b = HP.VerifyingKey(cs, pk.vk.domain, pk.vk.fixed_commitments, pk.vk.permutation_commitments, None)
+    assert a.transcript_repr == b.transcript_repr != 0
+
+
+@pytest.mark.parametrize("k,seed,rng_seed", [(5, 11, 1), (5, 3, 7), (6, 17, 2)])
+def test_create_proof_bytes_match_oracle_and_verify(k, seed, rng_seed):
+    fx, oparams, opk, cs, eng, pk = both_sides(k, seed)
+    inst = [fx["instance"][0][:4]]
+    want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(rng_seed))
+    adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+    timings = {}
+    got = HP.create_proof(HostParams(k), pk, adv, inst, HP.SeededRng(rng_seed), engine=eng, timings=timings)
+    assert got == want
+    assert PR.verify_proof(oparams, opk.vk, inst, got)
+    assert set(timings) == {"instance", "advice", "lookup_m", "z_columns", "vanishing_commit", "h_poly", "evaluations",
+                            "multiopen"}
+
+
+def test_create_proof_argument_checks():
+    fx, oparams, opk, cs, eng, pk = both_sides(5, 11)
+    adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+    with pytest.raises(HP.B2Error):
+        HP.create_proof(HostParams(5), pk, adv, [], HP.SeededRng(1), engine=eng)                  # InvalidInstances
+    with pytest.raises(HP.B2Error):
+        HP.create_proof(HostParams(5), pk, adv, [[1] * 27], HP.SeededRng(1), engine=eng)          # InstanceTooLarge
+    with pytest.raises(HP.B2Error):
+        HP.create_proof(HostParams(5), pk, adv[:-1], [[1]], HP.SeededRng(1), engine=eng)
+    bad = adv.copy()
+    bad[7, 3] = enc([1])[0]                                                                      # not in the table
+    with pytest.raises(HP.B2Error):
+        HP.create_proof(HostParams(5), pk, bad, [fx["instance"][0][:4]], HP.SeededRng(1), engine=eng)
+
+
+def test_benches_plonk_circuit_proves_and_verifies():
+    """BASELINE config 4's circuit (benches/plonk.rs) at k = 6: no lookups, shuffles or instances; explicit query
+    order as the reference's configure() produces it"""
+    k = 6
+    cs = HP.ConstraintSystem(**bench_circuit.constraint_system_args())
+    fixed, advice, mapping = bench_circuit.build(k)
+    ocs = P.ConstraintSystem(4, 3, 0, degree=5, blinding_factors=5)
+    ocs.gates, ocs.permutation_columns = cs.gates, cs.permutation_columns
+    ocs.advice_queries, ocs.fixed_queries, ocs.instance_queries = cs.advice_queries, cs.fixed_queries, cs.instance_queries
+    oparams = PR.Params(k, S_TOXIC)
+    omap = [[(int(c), int(r)) for c, r in col] for col in mapping]
+    opk = PR.keygen(oparams, ocs, [dec(c) for c in fixed], omap)
+    eng = OracleEngine(oparams, opk.vk.domain, ocs)
+    pk = HP.keygen(HostParams(k), cs, fixed, mapping, engine=eng, transcript_repr=opk.vk.transcript_repr)
+    want = PR.create_proof(oparams, opk, [dec(c) for c in advice], [], HP.SeededRng(5))
+    got = HP.create_proof(HostParams(k), pk, advice.copy(), [], HP.SeededRng(5), engine=eng, advice_max_bits=254)
+    assert got == want
+    assert PR.verify_proof(oparams, opk.vk, [], got)
+    # 3 advice + 1 z... : A=3, P=1 sets (3 columns, chunk 3), vanishing 1 + 4 h pieces; evals 3+4+1+3+2; W for rot 0, 1
+    assert len(got) == 32 * ((3 + 1 + 1 + 4) + (3 + 4 + 1 + 3 + 2) + 2)
+    # an unsatisfied witness must not verify
+    broken = advice.copy()
+    broken[2, 4] = enc([5])[0]
+    bad = HP.create_proof(HostParams(k), pk, broken, [], HP.SeededRng(5), engine=eng)
+    assert not PR.verify_proof(oparams, opk.vk, [], bad)
+
+
+def test_logup_multiplicity_matches_scalar_restatement():
+    """numpy sort / searchsorted / probe simulation vs the scalar restatement of binary_search_by_key, on tables
+    with long runs of repeated values"""
+    rng = random.Random(5)
+    for trial in range(20):
+        n = 64
+        usable = n - 6
+        distinct = [rng.randrange(R) for _ in range(rng.randrange(1, 12))] + [0, 1, R - 1]
+        table = [rng.choice(distinct) for _ in range(n)]
+        inputs = [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(3)]
+        want = PR.logup_multiplicity([inputs[:2], inputs[2:]], table, usable, n)
+        canon = lambda col: np.array([o._to_limbs(v) for v in col], dtype=np.uint64)      # noqa: E731
+        got = HP.logup_multiplicity([canon(c) for c in inputs], canon(table), usable, n)
+        assert got.tolist() == want
+    with pytest.raises(HP.B2Error):
+        HP.logup_multiplicity([canon([2] * n)], canon([3] * n), usable, n)
+
+
+def test_transcript_matches_oracle_transcript():
+    rng = random.Random(9)
+    a, b = HT.Blake2bWrite(), PR.Blake2bWrite()
+    pts = [o.g1_mul(o.G1_GEN, rng.randrange(R)) for _ in range(4)]
+    for step in range(40):
+        op = rng.randrange(5)
+        if op == 0:
+            assert a.squeeze_challenge() == b.squeeze_challenge()
+        elif op == 1:
+            p = rng.choice(pts)
+            a.write_point(o.g1_jacobian_encode(p))           # as the engine returns it: Jacobian, Z = 1
+            b.write_point(p)
+        elif op == 2:
+            p = rng.choice(pts)
+            a.common_point(o.g1_affine_encode([p])[0])
+            b.common_point(p)
+        elif op == 3:
+            s = rng.randrange(R)
+            a.write_scalar(enc([s])[0])                       # Montgomery limbs
+            b.write_scalar(s)
+        else:
+            s = rng.randrange(R)
+            a.common_scalar(s)
+            b.common_scalar(s)
+    assert a.finalize() == b.finalize() and a.squeeze_challenge() == b.squeeze_challenge()
+    with pytest.raises(HT.B2Error):
+        a.write_point(np.zeros(12, dtype=np.uint64))           # identity: "cannot write points at infinity"
+    assert HT.point_from_engine(np.zeros(8, dtype=np.uint64)) is None
+    assert HT.g1_to_bytes(None) == bytes(32)
+    assert HT.g1_to_bytes((1, 2)) == o.g1_to_bytes((1, 2)) and HT.g1_to_bytes((5, 3), 6) == o.g1_to_bytes((5, 3), 6)
+
+
+def test_seeded_rng_is_reproducible_and_in_range():
+    a, b = HP.SeededRng(4), HP.SeededRng(4)
+    assert np.array_equal(a.fr_vec(100), b.fr_vec(100)) and np.array_equal(a.u16_vec(9), b.u16_vec(9))
+    assert all(o._limbs_to_int(r) < R for r in a.fr_vec(200))
+    assert int(a.u16_vec(1000).max()) < 1 << 16
+    x = HP.OsRng()
+    assert x.fr_vec(3).shape == (3, 4) and x.u16_vec(5).shape == (5,) and x.u64_vec(2).dtype == np.uint64
+
+
+def test_device_engine_refuses_to_run_without_a_gpu():
+    """no CPU fallback: constructing the device engine (what create_proof does by default) needs CUDA"""
+    from halo2_gpu_specific_b200 import _lib
+    if _lib.lib().b2_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(HP.B2Error):
+        HP.Engine(HostParams(5), None)
+    fx, oparams, opk, cs, eng, pk = both_sides(5, 11)
+    adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+    with pytest.raises(HP.B2Error):
+        HP.create_proof(HostParams(5), pk, adv, [fx["instance"][0][:4]], HP.SeededRng(1))
