@@ -21,6 +21,8 @@ all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GP
   quotient  N == 1 only: evaluate_h + h(X) of a synthetic zkWasm-scale constraint system at k = logn from
           HBM-resident coefficient forms (coset mode), wall seconds, kernel times and the fused kernel's
           integer roofline; its own cpu_baseline (C restatement of the reference's row loop)
+  create_proof  N == 1 only: BASELINE config 4, the benches/plonk.rs circuit at k = 18, whole create_proof through
+          the prover mirror (plonk.create_proof), wall seconds and per-phase split
   cpu_baseline / --impl reference: the C restatement of the reference's rayon path
           (oracle/cpu_ref.c = arithmetic.rs:20-108, 465-492) on the box's host cores
 
@@ -318,6 +320,10 @@ def run_engine(args):
     if world == 1 and not args.no_quotient:
         quotient = bench_quotient(args, _lib, h2, float(muls.value))
 
+    proof = None
+    if world == 1 and not args.no_proof:
+        proof = bench_create_proof(args, _lib, h2)
+
     if rank == 0:
         hbm_peak, peak_src = _peaks()
         total_pts = n * world * args.steps
@@ -371,6 +377,8 @@ def run_engine(args):
             line["ntt"] = ntt
         if quotient:
             line["quotient"] = quotient
+        if proof:
+            line["create_proof"] = proof
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -546,6 +554,54 @@ def bench_quotient(args, _lib, h2, modmuls_per_s):
     return res
 
 
+def bench_create_proof(args, _lib, h2):
+    """BASELINE config 4: the benches/plonk.rs circuit, full create_proof (GWC) through the prover mirror
+    (halo2_gpu_specific_b200.plonk) at k = --proof-k.  Wall clock around the whole call: host transcript, RNG and
+    bookkeeping included, advice columns in pageable host memory.  The bases are synthetic and unstructured (timing
+    does not depend on their values); the same code path with a structured SRS is checked against the oracle's
+    verifier, pairing included, in tests/test_gpu_prover.py (k = 8, 14, 18).  Never fatal for the main line."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import plonk_bench_circuit as bc
+        from halo2_gpu_specific_b200 import plonk as HP
+        from halo2_gpu_specific_b200.arithmetic import Srs
+        k = args.proof_k
+        n = 1 << k
+        cs = HP.ConstraintSystem(**bc.constraint_system_args())
+        fixed, advice, mapping = bc.build(k)
+        params = h2.Params(k, Srs.synthetic(n, 0, 0xB2000091), Srs.synthetic(n, n, 0xB2000091))
+        try:
+            pk = HP.keygen(params, cs, fixed, mapping)
+            L = _lib.lib()
+            times, phases, launches, nbytes = [], {}, 0, 0
+            for it in range(1 + args.proof_reps):
+                adv = advice.copy()
+                tm = {}
+                l0 = L.b2_launch_count(0)
+                t0 = time.perf_counter()
+                proof = HP.create_proof(params, pk, adv, [], HP.SeededRng(it), timings=tm)
+                dt = time.perf_counter() - t0
+                if it:                                    # first call warms plans, tables and workspaces
+                    times.append(dt)
+                    launches = L.b2_launch_count(0) - l0
+                    nbytes = len(proof)
+                    for name, v in tm.items():
+                        phases.setdefault(name, []).append(v)
+            return {
+                "metric": f"create_proof wall time, benches/plonk.rs circuit at k={k} (3 advice, 4 fixed, 1 permutation "
+                          f"set, degree 5), GWC multiopen",
+                "value": statistics.median(times), "unit": "s", "higher_is_better": False, "reps": len(times),
+                "all_s": times, "phases_s": {a: statistics.median(b) for a, b in phases.items()},
+                "gpu_launches": launches, "proof_bytes": nbytes,
+                "h2d_bytes": int(advice.nbytes), "srs": "synthetic unstructured bases (timing only)",
+                "api": "halo2_gpu_specific_b200.plonk.create_proof (host advice columns -> proof bytes)",
+            }
+        finally:
+            params.free()
+    except Exception as e:                                # noqa: BLE001 -- reported, never fatal for the MSM line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_baseline(args):
     """Bounded sample of the same workload on the host cores (C restatement of the rayon path)."""
     from oracle import cref
@@ -586,6 +642,9 @@ def main():
     ap.add_argument("--no-ntt", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-quotient", action="store_true")
+    ap.add_argument("--no-proof", action="store_true")
+    ap.add_argument("--proof-k", type=int, default=18)
+    ap.add_argument("--proof-reps", type=int, default=3)
     ap.add_argument("--no-precompute", action="store_true", help="plain bases: one bucket set per window + Horner")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

@@ -1,0 +1,129 @@
+"""GPU parity of the whole prover through the engine (halo2_gpu_specific_b200.plonk.create_proof over the C ABI):
+proof bytes identical to the CPU oracle's (oracle/prover.py) under the same RNG, and acceptance by the oracle's
+verify_proof (incl. the real pairing check) -- the reference's own prove -> verify test strategy -- up to the
+benches/plonk.rs circuit at k = 18 (BASELINE config 4)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import plonk_fixture as fxm
+from oracle import bn254 as o
+from oracle import plonk as P
+from oracle import prover as PR
+
+import halo2_gpu_specific_b200 as h2
+from halo2_gpu_specific_b200 import grand_product as gp
+from halo2_gpu_specific_b200 import plonk as HP
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import plonk_bench_circuit as bench_circuit  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+R = o.R_MOD
+enc, dec = o.fr_encode, o.fr_decode
+S_TOXIC = 0x2B200B200B200B200B200B200B200B2001
+
+
+def engine_side(k, oparams, cs, fixed, mapping, transcript_repr):
+    params = h2.Params(k, oparams.g, oparams.g_lagrange)
+    pk = HP.keygen(params, cs, fixed, mapping, transcript_repr=transcript_repr)
+    return params, pk
+
+
+@pytest.mark.parametrize("k,seed,rng_seed", [(5, 11, 1), (6, 17, 2)])
+def test_proof_bytes_match_oracle(gpu, k, seed, rng_seed):
+    fx = fxm.build(k=k, seed=seed)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, S_TOXIC)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+    params, pk = engine_side(k, oparams, cs, np.stack([enc(c) for c in fx["fixed"]]),
+                             np.array(fx["mapping"], dtype=np.int64), opk.vk.transcript_repr)
+    try:
+        # keygen on the device == keygen in the oracle
+        assert pk.vk.fixed_commitments == opk.vk.fixed_commitments
+        assert pk.vk.permutation_commitments == opk.vk.permutation_commitments
+        for got, want in ((pk.sigmas, opk.sigmas), (pk.sigma_polys, opk.sigma_polys), (pk.fixed_polys, opk.fixed_polys)):
+            for a, b in zip(got, want):
+                assert np.array_equal(a, enc(b))
+        assert np.array_equal(pk.l0, enc(opk.l0)) and np.array_equal(pk.l_last, enc(opk.l_last))
+        assert np.array_equal(pk.l_active_row, enc(opk.l_active_row))
+        inst = [fx["instance"][0][:4]]
+        want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(rng_seed))
+        adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+        launches0 = gpu.lib().b2_launch_count(0)
+        got = HP.create_proof(params, pk, adv, inst, HP.SeededRng(rng_seed))
+        assert gpu.lib().b2_launch_count(0) > launches0
+        assert got == want
+        assert PR.verify_proof(oparams, opk.vk, inst, got, pairing=(k == 5))
+    finally:
+        params.free()
+
+
+def test_compress_expressions(gpu):
+    fx = fxm.build(k=6, seed=17)
+    cs, n = fx["cs"], fx["n"]
+    dom = h2.EvaluationDomain(cs.degree(), fx["k"])
+    adv, fixed, inst = [enc(c) for c in fx["advice"]], [enc(c) for c in fx["fixed"]], [enc(c) for c in fx["instance"]]
+    lists = [[P.Advice(5)], [P.Fixed(4), P.Fixed(5)], [P.Const(3)], [P.Sum(P.Advice(1, 1), P.Const(2)), P.Instance(0, -1)]]
+    got = gp.compress_expressions(dom, lists, adv, fixed, inst, fx["theta"])
+    for g, ex in zip(got, lists):
+        want = P.evaluate_with_theta(ex, n, 1, fx["fixed"], fx["advice"], fx["instance"], fx["theta"])
+        assert np.array_equal(g, enc(want))
+
+
+def test_commit_batch_against_g(gpu):
+    """Params::commit for several polynomials shorter than n (the multiopen witnesses have n - 1 coefficients)"""
+    k = 7
+    oparams = PR.Params(k, S_TOXIC)
+    params = h2.Params(k, oparams.g, oparams.g_lagrange)
+    try:
+        from oracle import cref
+        x = cref.random_fr_mont(3 * 127, 0xB2000081).reshape(3, 127, 4)
+        got = [HP.Engine._points(params.commit_batch(x))[i] for i in range(3)]
+        assert got == [oparams.commit(dec(x[i])) for i in range(3)]
+    finally:
+        params.free()
+
+
+def _bench_circuit(k):
+    cs = HP.ConstraintSystem(**bench_circuit.constraint_system_args())
+    fixed, advice, mapping = bench_circuit.build(k)
+    ocs = P.ConstraintSystem(4, 3, 0, degree=5, blinding_factors=5)
+    ocs.gates, ocs.permutation_columns = cs.gates, cs.permutation_columns
+    ocs.advice_queries, ocs.fixed_queries, ocs.instance_queries = cs.advice_queries, cs.fixed_queries, cs.instance_queries
+    return cs, ocs, fixed, advice, mapping
+
+
+@pytest.mark.parametrize("k,pairing", [(8, True), (14, False), (18, True)])
+def test_benches_plonk_circuit_proof_verifies(gpu, k, pairing):
+    """BASELINE config 4: the benches/plonk.rs circuit, full create_proof on the engine, accepted by the oracle
+    verifier.  The verifying key the oracle reads is the one the ENGINE's keygen produced (commitments computed on
+    the device); the oracle side only needs the SRS trapdoor / [s]G2 and the constraint system."""
+    cs, ocs, fixed, advice, mapping = _bench_circuit(k)
+    oparams = PR.Params(k, S_TOXIC)
+    params = h2.Params(k, oparams.g, oparams.g_lagrange)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        timings = {}
+        proof = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(k), timings=timings)
+        assert len(proof) == 32 * ((3 + 1 + 1 + 4) + (3 + 4 + 1 + 3 + 2) + 2)
+        ovk = PR.VerifyingKey(ocs, o.EvaluationDomain(cs.degree(), k), pk.vk.fixed_commitments,
+                              pk.vk.permutation_commitments, pk.vk.transcript_repr)
+        assert PR.verify_proof(oparams, ovk, [], proof, pairing=pairing)
+        if k <= 8:
+            # same bytes as the oracle prover, which also did its own keygen
+            opk = PR.keygen(oparams, ocs, [dec(c) for c in fixed], [[(int(c), int(r)) for c, r in col] for col in mapping],
+                            transcript_repr=pk.vk.transcript_repr)
+            assert opk.vk.fixed_commitments == pk.vk.fixed_commitments
+            assert PR.create_proof(oparams, opk, [dec(c) for c in advice], [], HP.SeededRng(k)) == proof
+        # a broken witness (one product row off by one) must not verify
+        bad = advice.copy()
+        bad[2, 4] = enc([5])[0]
+        proof_bad = HP.create_proof(params, pk, bad, [], HP.SeededRng(k))
+        assert not PR.verify_proof(oparams, ovk, [], proof_bad)
+        print(f"k={k} create_proof phases (s): " + ", ".join(f"{a} {b:.4f}" for a, b in timings.items()))
+    finally:
+        params.free()
