@@ -54,6 +54,14 @@ class Srs:
         check(lib().b2_srs_synthetic(n, first_index, seed, ctypes.byref(h)))
         return cls(h.value, n)
 
+    @classmethod
+    def from_scalars_dev(cls, d_scalars: int, n: int) -> "Srs":
+        """bases[i] = [k_i] G for n Montgomery-form scalars at device pointer d_scalars (b2_srs_from_scalars_dev)"""
+        require_gpu()
+        h = ctypes.c_uint64()
+        check(lib().b2_srs_from_scalars_dev(ctypes.c_void_p(d_scalars), n, ctypes.byref(h)))
+        return cls(h.value, n)
+
     def precompute(self, window_bits: int = 0) -> "Srs":
         """build the window table (b2_srs_precompute): one shared bucket set, wider windows"""
         check(lib().b2_srs_precompute(self.handle, int(window_bits)))

@@ -30,6 +30,51 @@ class Params:
             self.g.precompute()
             self.g_lagrange.precompute()
 
+    @classmethod
+    def unsafe_setup(cls, k: int, s: int, precompute: bool = True) -> "Params":
+        """Params::unsafe_setup (:56-124) on the device, for a caller-chosen s (the reference draws it from OsRng,
+        :61, and forgets it): g[i] = [s^i] G (:63-83), g_lagrange[i] = [(s^n - 1)/n * w^i / (s - w^i)] G (:85-112).
+        The scalar side is a prefix product, a batch inversion and three element-wise passes on resident vectors;
+        the point side one fixed-base multiplication per point.  2 * 2^k points without touching the host --
+        SURVEY 8d config 3's "synthetic SRS built on the GPU by the engine itself"."""
+        import ctypes
+        from .evaluation import DeviceBuffer
+        if k > _fr.S:
+            raise B2Error(B2_ERR_ARG, "assert!(k <= Fr::S)")                  # :60
+        require_gpu()
+        R = _fr.R_MOD
+        n = 1 << k
+        s %= R
+        L = lib()
+        vp = ctypes.c_void_p
+        one = _fr.to_mont(1)
+        const, pw, den = DeviceBuffer(n), DeviceBuffer(n), DeviceBuffer(n)
+        try:
+            def fill(value: int) -> None:
+                const.upload(np.tile(_fr.to_mont(value), (n, 1)))
+
+            def powers(base: int, out: DeviceBuffer) -> None:               # out[i] = base^i
+                fill(base)
+                check(L.b2_prefix_scan_dev(0, vp(const.ptr), n, ptr(one), None, vp(out.ptr), n, None))
+
+            powers(s, pw)
+            g = Srs.from_scalars_dev(pw.ptr, n)
+            root = _fr.ROOT_OF_UNITY
+            for _ in range(k, _fr.S):
+                root = root * root % R
+            powers(root, pw)                                                 # w^i
+            fill(s)
+            check(L.b2_fr_vec_dev(2, vp(const.ptr), vp(pw.ptr), n, vp(den.ptr), None))       # s - w^i
+            check(L.b2_batch_invert_dev(vp(den.ptr), n, None))
+            check(L.b2_fr_vec_dev(0, vp(pw.ptr), vp(den.ptr), n, vp(den.ptr), None))         # w^i / (s - w^i)
+            fill((pow(s, n, R) - 1) * _fr.inv(n % R) % R)
+            check(L.b2_fr_vec_dev(0, vp(den.ptr), vp(const.ptr), n, vp(den.ptr), None))      # * (s^n - 1) / n
+            check(L.b2_synchronize())
+            g_lagrange = Srs.from_scalars_dev(den.ptr, n)
+        finally:
+            const.free(); pw.free(); den.free()
+        return cls(k, g, g_lagrange, precompute=precompute)
+
     def commit(self, poly) -> np.ndarray:
         """:129-133"""
         p = as_fr(poly)

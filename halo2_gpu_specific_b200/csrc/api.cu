@@ -1027,6 +1027,30 @@ int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t*
     *out = h;
     return B2_OK;
 }
+int b2_srs_from_scalars_dev(const void* d_scalars, size_t n, b2_handle_t* out) {
+    if (!out || !d_scalars || n == 0) return fail(B2_ERR_ARG, "srs_from_scalars: bad arguments");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    char* d = nullptr;
+    CK(cudaMalloc(&d, n * 64));
+    LAUNCH(*ctx, srs_from_scalars_kernel, (unsigned)((n + 127) / 128), 128, 0, ctx->stream, d, (const uint4*)d_scalars,
+           (unsigned long long)n);
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::lock_guard<std::mutex> lk2(g_srs_mu);
+    b2_handle_t h = g_next_handle++;
+    g_srs[h] = Srs{ctx->dev->dev, d, n, nullptr, 0, 0};
+    *out = h;
+    return B2_OK;
+}
+int b2_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes) {
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
+    if (rc) return rc;
+    CK(cudaMemcpy(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice));
+    return B2_OK;
+}
 int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits) {
     Srs s;
     int rc = srs_lookup(srs, &s);

@@ -796,6 +796,27 @@ srs_synth_kernel(char* __restrict__ bases, unsigned long long n, unsigned long l
     fp_store<FqParams>(bases + i * 64 + 32, a.y);
 }
 
+// bases[i] = [k_i] G for Montgomery-form Fr scalars resident on the device: the point side of
+// Params::unsafe_setup (poly/commitment.rs:63-112: g[i] = [s^i] G, g_lagrange[i] = [l_i(s)] G), one thread per
+// point, plain double-and-add from the top bit (setup-time work, 254 doublings + ~127 mixed adds per point)
+__global__ void __launch_bounds__(128)
+srs_from_scalars_kernel(char* __restrict__ bases, const uint4* __restrict__ scalars, unsigned long long n) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Fr k = fp_from_mont<FrParams>(fp_load<FrParams>(scalars + 2 * i));
+    Affine gen;
+    gen.x = Fq::one();
+    gen.y = fp_dbl<FqParams>(Fq::one());
+    XYZZ acc = XYZZ::identity();
+    for (int b = 253; b >= 0; b--) {
+        xyzz_dbl_ni(acc);
+        if ((k.v[b >> 5] >> (b & 31)) & 1u) xyzz_madd(acc, gen);
+    }
+    Affine a = xyzz_to_affine(acc);
+    fp_store<FqParams>(bases + i * 64, a.x);
+    fp_store<FqParams>(bases + i * 64 + 32, a.y);
+}
+
 // ---------------------------------------------------------------- element-wise test kernels
 // op: 0 mul, 1 add, 2 sub, 3 sqr, 4 Shoup constant multiplication (Fr), 5 / 6 fused x*y +- y*y
 template <class P>

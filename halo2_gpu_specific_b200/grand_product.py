@@ -103,11 +103,22 @@ class _Columns:
         nf, na, _ = self.counts
         self.fixed, self.advice, self.instance = p[:nf], p[nf:nf + na], p[nf + na:]
 
+    @classmethod
+    def resident(cls, fixed_ptrs, advice_ptrs, instance_ptrs, n: int) -> "_Columns":
+        """columns that already live on the device (device pointers); nothing is owned"""
+        self = cls.__new__(cls)
+        self.n = n
+        self.fixed, self.advice, self.instance = list(fixed_ptrs), list(advice_ptrs), list(instance_ptrs)
+        self.counts = (len(self.fixed), len(self.advice), len(self.instance))
+        self.buf = None
+        return self
+
     def of(self, kind: str):
         return {"Fixed": self.fixed, "Advice": self.advice, "Instance": self.instance}[kind]
 
     def free(self):
-        self.buf.free()
+        if self.buf is not None:
+            self.buf.free()
 
 
 def _run(comp: ExprCompiler, result, cols: _Columns, aux: Sequence[int], challenges: Sequence[int], out_ptr: int,
@@ -120,26 +131,23 @@ def _run(comp: ExprCompiler, result, cols: _Columns, aux: Sequence[int], challen
         prog.free()
 
 
-def permutation_commit(domain, permutation_columns, degree: int, blinding_factors: int, sigmas, advice, fixed, instance,
-                       beta: int, gamma: int, blinds: Sequence[np.ndarray]) -> List[np.ndarray]:
-    """permutation/prover.rs:47-165.  sigmas: the permutation polynomials in Lagrange form
-    (pkey.permutations); blinds[s]: (blinding_factors, 4) values for the last rows of set s.
-    Returns the z columns (Lagrange basis, (n, 4) Montgomery), one per column chunk."""
-    require_gpu()
+def _h2d(dst_ptr: int, a: np.ndarray) -> None:
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    check(lib().b2_memcpy_h2d(ctypes.c_void_p(dst_ptr), ctypes.c_void_p(a.ctypes.data), a.nbytes))
+
+
+def permutation_commit_dev(domain, permutation_columns, degree: int, blinding_factors: int, sig_ptrs: Sequence[int],
+                           cols: _Columns, beta: int, gamma: int, blinds: Sequence[np.ndarray], z_ptrs: Sequence[int]) -> None:
+    """permutation/prover.rs:47-165 on resident columns: sig_ptrs are the permutation polynomials in Lagrange form
+    (pkey.permutations), z_ptrs[s] receives the finished z column of set s (n rows, blinding rows included)."""
     n, k = domain.n, domain.k
     chunk_len = degree - 2                                            # :66
     m = len(permutation_columns)
     n_sets = (m + chunk_len - 1) // chunk_len
-    if len(blinds) != n_sets:
-        raise B2Error(B2_ERR_ARG, f"expected blinding rows for {n_sets} sets")
-    cols = _Columns(fixed, advice, instance, n)
-    sig = DeviceBuffer(max(1, m) * n)
+    if len(blinds) != n_sets or len(z_ptrs) != n_sets or len(sig_ptrs) != m:
+        raise B2Error(B2_ERR_ARG, f"expected {n_sets} sets of blinding rows / outputs and {m} sigma columns")
     work = DeviceBuffer(max(1, n_sets) * n)     # denominators, then the fractions
-    zbuf = DeviceBuffer(max(1, n_sets) * n)
     try:
-        if m:
-            sig.upload(np.stack([np.asarray(s, dtype=np.uint64).reshape(n, 4) for s in sigmas]))
-        sig_ptrs = [sig.ptr + j * n * 32 for j in range(m)]
         # challenges: beta, gamma, theta (unused), then beta * DELTA^j per column (delta_omega * beta, :108-121)
         ch = [beta % R, gamma % R, 0]
         d = beta % R
@@ -155,7 +163,7 @@ def permutation_commit(domain, permutation_columns, degree: int, blinding_factor
                 t = c.emit(("Mul", ("Challenge", CH_BETA), ("Aux", j, 0)))
                 t = c.emit(("AddChallenge", c.emit(("Add", t, (kind, idx, 0))), "Gamma"))
                 acc = t if acc is None else c.emit(("Mul", acc, t))
-            _run(c, acc, cols, sig_ptrs, ch, work.ptr + s * n * 32, k)
+            _run(c, acc, cols, list(sig_ptrs), ch, work.ptr + s * n * 32, k)
         _invert(work.ptr, n_sets * n)                                  # :104 (all sets in one launch)
         for s in range(n_sets):
             chunk = list(enumerate(permutation_columns))[s * chunk_len:(s + 1) * chunk_len]
@@ -169,34 +177,55 @@ def permutation_commit(domain, permutation_columns, degree: int, blinding_factor
             frac = work.ptr + s * n * 32
             _run(c, acc, cols, [frac], ch, frac, k, x0=1, x_step=domain._omega)
             # z[0] = last_z, z[i + 1] = z[i] * fraction[i]   :135-152
-            zs = zbuf.ptr + s * n * 32
             if s == 0:
-                _scan(0, frac, n, zs, n, init=1)
+                _scan(0, frac, n, z_ptrs[s], n, init=1)
             else:
-                last = zbuf.ptr + ((s - 1) * n + n - (blinding_factors + 1)) * 32     # :160
-                _scan(0, frac, n, zs, n, d_init=last)
-            zbuf.upload(np.asarray(blinds[s], dtype=np.uint64).reshape(blinding_factors, 4),
-                        s * n + n - blinding_factors)                  # :156-158
+                last = z_ptrs[s - 1] + (n - (blinding_factors + 1)) * 32                   # :160
+                _scan(0, frac, n, z_ptrs[s], n, d_init=last)
+            _h2d(z_ptrs[s] + (n - blinding_factors) * 32,
+                 np.asarray(blinds[s], dtype=np.uint64).reshape(blinding_factors, 4))       # :156-158
+    finally:
+        work.free()
+
+
+def permutation_commit(domain, permutation_columns, degree: int, blinding_factors: int, sigmas, advice, fixed, instance,
+                       beta: int, gamma: int, blinds: Sequence[np.ndarray]) -> List[np.ndarray]:
+    """permutation/prover.rs:47-165.  sigmas: the permutation polynomials in Lagrange form
+    (pkey.permutations); blinds[s]: (blinding_factors, 4) values for the last rows of set s.
+    Returns the z columns (Lagrange basis, (n, 4) Montgomery), one per column chunk."""
+    require_gpu()
+    n = domain.n
+    chunk_len = degree - 2
+    m = len(permutation_columns)
+    n_sets = (m + chunk_len - 1) // chunk_len
+    if len(blinds) != n_sets:
+        raise B2Error(B2_ERR_ARG, f"expected blinding rows for {n_sets} sets")
+    cols = _Columns(fixed, advice, instance, n)
+    sig = DeviceBuffer(max(1, m) * n)
+    zbuf = DeviceBuffer(max(1, n_sets) * n)
+    try:
+        if m:
+            sig.upload(np.stack([np.asarray(s, dtype=np.uint64).reshape(n, 4) for s in sigmas]))
+        permutation_commit_dev(domain, permutation_columns, degree, blinding_factors,
+                               [sig.ptr + j * n * 32 for j in range(m)], cols, beta, gamma, blinds,
+                               [zbuf.ptr + s * n * 32 for s in range(n_sets)])
         out = zbuf.download(n_sets * n).reshape(n_sets, n, 4) if n_sets else np.zeros((0, n, 4), np.uint64)
         return [out[s] for s in range(n_sets)]
     finally:
-        cols.free(); sig.free(); work.free(); zbuf.free()
+        cols.free(); sig.free(); zbuf.free()
 
 
-def logup_commit_z(domain, lookup, blinding_factors: int, advice, fixed, instance, multiplicity, theta: int, beta: int
-                   ) -> List[np.ndarray]:
-    """logup/prover.rs:263-336 with the compression of :83-112 fused in.  lookup: {"table_expressions",
-    "input_expressions_sets"} (Expression tuples); multiplicity: m(X) values (n, 4).
-    Returns the raw z vectors (n - blinding_factors rows each), one per input set."""
-    require_gpu()
+def logup_commit_z_dev(domain, lookup, blinding_factors: int, cols: _Columns, m_ptr: int, theta: int, beta: int,
+                       z_ptrs: Sequence[int]) -> None:
+    """logup/prover.rs:263-336 (with the compression of :83-112 fused in) on resident columns; m_ptr: m(X) values;
+    z_ptrs[i] receives the first n - blinding_factors rows of the z column of input set i."""
     n, k = domain.n, domain.k
     sets = lookup["input_expressions_sets"]
+    if len(z_ptrs) != len(sets):
+        raise B2Error(B2_ERR_ARG, f"expected {len(sets)} output columns")
     n_inputs = sum(len(s) for s in sets)
-    cols = _Columns(fixed, advice, instance, n)
     inv = DeviceBuffer((n_inputs + 1) * n)       # beta + compressed input, per input; then beta + table
     grand = DeviceBuffer(len(sets) * n)
-    zbuf = DeviceBuffer(len(sets) * n)
-    mbuf = DeviceBuffer(n).upload(np.asarray(multiplicity, dtype=np.uint64).reshape(n, 4))
     ch = [beta % R, 0, theta % R]
     try:
         slot = 0
@@ -220,30 +249,44 @@ def logup_commit_z(domain, lookup, blinding_factors: int, advice, fixed, instanc
                 slot += 1
             if si == 0:                                                # :297-305: sum - table_inv * m
                 acc = c.emit(("Sub", acc, c.emit(("Mul", ("Aux", n_inputs, 0), ("Aux", n_inputs + 1, 0)))))
-            _run(c, acc, cols, inv_ptrs + [mbuf.ptr], ch, grand.ptr + si * n * 32, k)
+            _run(c, acc, cols, inv_ptrs + [m_ptr], ch, grand.ptr + si * n * 32, k)
         u = n - (blinding_factors + 1)
         n_out = n - blinding_factors
         for si in range(len(sets)):                                    # :318-336
-            zs = zbuf.ptr + si * n * 32
             if si == 0:
-                _scan(1, grand.ptr, n, zs, n_out, init=0)
+                _scan(1, grand.ptr, n, z_ptrs[si], n_out, init=0)
             else:
-                _scan(1, grand.ptr + si * n * 32, n, zs, n_out, d_init=zbuf.ptr + ((si - 1) * n + u) * 32)
+                _scan(1, grand.ptr + si * n * 32, n, z_ptrs[si], n_out, d_init=z_ptrs[si - 1] + u * 32)
+    finally:
+        inv.free(); grand.free()
+
+
+def logup_commit_z(domain, lookup, blinding_factors: int, advice, fixed, instance, multiplicity, theta: int, beta: int
+                   ) -> List[np.ndarray]:
+    """logup/prover.rs:263-336 with the compression of :83-112 fused in.  lookup: {"table_expressions",
+    "input_expressions_sets"} (Expression tuples); multiplicity: m(X) values (n, 4).
+    Returns the raw z vectors (n - blinding_factors rows each), one per input set."""
+    require_gpu()
+    n = domain.n
+    sets = lookup["input_expressions_sets"]
+    cols = _Columns(fixed, advice, instance, n)
+    zbuf = DeviceBuffer(len(sets) * n)
+    mbuf = DeviceBuffer(n).upload(np.asarray(multiplicity, dtype=np.uint64).reshape(n, 4))
+    try:
+        logup_commit_z_dev(domain, lookup, blinding_factors, cols, mbuf.ptr, theta, beta,
+                           [zbuf.ptr + i * n * 32 for i in range(len(sets))])
+        n_out = n - blinding_factors
         out = zbuf.download(len(sets) * n).reshape(len(sets), n, 4)
         return [out[i, :n_out].copy() for i in range(len(sets))]
     finally:
-        cols.free(); inv.free(); grand.free(); zbuf.free(); mbuf.free()
+        cols.free(); zbuf.free(); mbuf.free()
 
 
-def shuffle_commit_product(domain, group, blinding_factors: int, advice, fixed, instance, theta: int, beta: int
-                           ) -> np.ndarray:
-    """shuffle/prover.rs:60-141.  group: [{"input_expressions", "shuffle_expressions"}].
-    Returns z (n - blinding_factors rows)."""
-    require_gpu()
+def shuffle_commit_product_dev(domain, group, blinding_factors: int, cols: _Columns, theta: int, beta: int, z_ptr: int
+                               ) -> None:
+    """shuffle/prover.rs:60-141 on resident columns; z_ptr receives the first n - blinding_factors rows of z."""
     n, k = domain.n, domain.k
-    cols = _Columns(fixed, advice, instance, n)
     work = DeviceBuffer(n)
-    zbuf = DeviceBuffer(n)
     ch = [beta % R, 0, theta % R]
     try:
         def product(which: str, c: ExprCompiler, acc):
@@ -255,11 +298,33 @@ def shuffle_commit_product(domain, group, blinding_factors: int, advice, fixed, 
         _invert(work.ptr, n)                                                                  # :132
         c = ExprCompiler()
         _run(c, product("input_expressions", c, ("Aux", 0, 0)), cols, [work.ptr], ch, work.ptr, k)   # :134
-        n_out = n - blinding_factors
-        _scan(0, work.ptr, n, zbuf.ptr, n_out, init=1)                                        # :137-146
-        return zbuf.download(n_out)
+        _scan(0, work.ptr, n, z_ptr, n - blinding_factors, init=1)                            # :137-146
     finally:
-        cols.free(); work.free(); zbuf.free()
+        work.free()
+
+
+def shuffle_commit_product(domain, group, blinding_factors: int, advice, fixed, instance, theta: int, beta: int
+                           ) -> np.ndarray:
+    """shuffle/prover.rs:60-141.  group: [{"input_expressions", "shuffle_expressions"}].
+    Returns z (n - blinding_factors rows)."""
+    require_gpu()
+    n = domain.n
+    cols = _Columns(fixed, advice, instance, n)
+    zbuf = DeviceBuffer(n)
+    try:
+        shuffle_commit_product_dev(domain, group, blinding_factors, cols, theta, beta, zbuf.ptr)
+        return zbuf.download(n - blinding_factors)
+    finally:
+        cols.free(); zbuf.free()
+
+
+def compress_expressions_dev(domain, expression_lists, cols: _Columns, theta: int, out_ptr: int) -> None:
+    """evaluate_with_theta (plonk/evaluation.rs:2330-2398) per expression list on resident columns; list i goes to
+    out_ptr + i * n * 32"""
+    n, k = domain.n, domain.k
+    for i, exprs in enumerate(expression_lists):
+        c = ExprCompiler()
+        _run(c, c.emit(("Store", c.compress(exprs))), cols, [], [0, 0, theta % R], out_ptr + i * n * 32, k)
 
 
 def compress_expressions(domain, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
@@ -267,14 +332,12 @@ def compress_expressions(domain, expression_lists, advice, fixed, instance, thet
     columns: what logup's `compress` computes before the multiplicities are counted (logup/prover.rs:83-112).
     Returns (len(expression_lists), n, 4)."""
     require_gpu()
-    n, k = domain.n, domain.k
+    n = domain.n
     m = len(expression_lists)
     cols = _Columns(fixed, advice, instance, n)
     out = DeviceBuffer(max(1, m) * n)
     try:
-        for i, exprs in enumerate(expression_lists):
-            c = ExprCompiler()
-            _run(c, c.emit(("Store", c.compress(exprs))), cols, [], [0, 0, theta % R], out.ptr + i * n * 32, k)
+        compress_expressions_dev(domain, expression_lists, cols, theta, out.ptr)
         return out.download(m * n).reshape(m, n, 4) if m else np.zeros((0, n, 4), np.uint64)
     finally:
         cols.free(); out.free()

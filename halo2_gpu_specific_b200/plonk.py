@@ -302,40 +302,138 @@ class OsRng:
 
 
 # --------------------------------------------------------------------------
-# the device engine
+# engines
 # --------------------------------------------------------------------------
+# create_proof talks to its engine in terms of BLOCKS (a run of columns of n field elements that the engine
+# owns) and COLUMNS (one column of a block).  What a block is belongs to the engine: the resident engine keeps
+# device buffers, the host-API engine plain numpy arrays.  The operations:
+#   put / alloc / cols / write_rows                      data movement
+#   put_and_commit_lagrange, commit_lagrange, commit_lagrange_and_ifft, commit, lagrange_to_coeff
+#   compress_canonical, put_canonical                    logup: compressed expressions out, multiplicities in
+#   permutation_z, logup_z, shuffle_z                    z columns written into columns of a block
+#   random_poly, evaluate_h_blocks                       vanishing argument
+#   eval_polynomial, poly_combine, sub_constant, kate_division_padded   evaluation phase and multiopen
+#   key_blocks, release
 def _mont_vec(vals: Sequence[int]) -> np.ndarray:
     return np.stack([_fr.to_mont(int(v)) for v in vals]) if len(vals) else np.zeros((0, 4), np.uint64)
 
 
-class Engine:
-    """Every numeric step of keygen / create_proof as one call into the C ABI (through the mirrors of this
-    package).  Points come back as canonical affine (x, y) tuples, None for the identity."""
+def _points(jac: np.ndarray) -> List[Point]:
+    from .transcript import point_from_engine
+    return [point_from_engine(p) for p in jac]
+
+
+class ArrayBlocks:
+    """Block protocol for engines whose blocks are numpy arrays (columns, n, 4): the host-API engine below, and the
+    test double in tests/.  Everything here is expressed through the array primitives those engines provide
+    (commit_lagrange, compress, permutation_commit, evaluate_h, kate_division, ...)."""
+
+    def put(self, host: np.ndarray) -> np.ndarray:
+        return np.ascontiguousarray(host, dtype=np.uint64)
+
+    def alloc(self, count: int) -> np.ndarray:
+        return np.zeros((count, self.domain.n, 4), dtype=np.uint64)
+
+    @staticmethod
+    def cols(block: np.ndarray) -> list:
+        return [block[i] for i in range(block.shape[0])]
+
+    @staticmethod
+    def write_rows(col: np.ndarray, row: int, values: np.ndarray) -> None:
+        col[row:row + len(values)] = values
+
+    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: int):
+        return host, self.commit_lagrange(host, max_bits)
+
+    def compress_canonical(self, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
+        comp = self.compress(expression_lists, advice, fixed, instance, theta)
+        return self.from_mont(comp).reshape(len(expression_lists), self.domain.n, 4)
+
+    def put_canonical(self, canonical: np.ndarray) -> np.ndarray:
+        return self.to_mont(canonical).reshape(canonical.shape)
+
+    def permutation_z(self, cs, pk, advice, instance, beta, gamma, blinds, out_cols) -> None:
+        zs = self.permutation_commit(cs, pk.sigmas, advice, pk.fixed_values, instance, beta, gamma, blinds)
+        for o, z in zip(out_cols, zs):
+            o[:] = z
+
+    def logup_z(self, cs, lookup, pk, advice, instance, m_col, theta, beta, out_cols) -> None:
+        raw = self.logup_commit_z(cs, lookup, advice, pk.fixed_values, instance, m_col, theta, beta)
+        for o, z in zip(out_cols, raw):
+            o[:len(z)] = z
+
+    def shuffle_z(self, cs, group, pk, advice, instance, theta, beta, out_col) -> None:
+        z = self.shuffle_commit_product(cs, group, advice, pk.fixed_values, instance, theta, beta)
+        out_col[:len(z)] = z
+
+    def random_poly(self, random, a, u, b, v) -> np.ndarray:
+        kk = np.uint64(random.shape[0])
+        p = self.fr_vec("mul", self.fr_vec("add", a, random[(u % kk).astype(np.int64)]),
+                        self.fr_vec("add", b, random[(v % kk).astype(np.int64)]))
+        return p.reshape(1, -1, 4)
+
+    def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta) -> np.ndarray:
+        n = self.domain.n
+        lookups, pos = [], n_perm
+        for li, cnt in enumerate(lookup_z_counts):
+            lookups.append({"z": [z_block[pos + i] for i in range(cnt)], "m": m_block[li]})
+            pos += cnt
+        h = self.evaluate_h(pk, advice, instance, y, beta, gamma, theta, lookups,
+                            [z_block[pos + i] for i in range(n_shuffles)], [z_block[i] for i in range(n_perm)])
+        pieces = h.shape[0] // n                                          # par_chunks_exact(n)
+        return np.ascontiguousarray(h[:pieces * n]).reshape(pieces, n, 4)
+
+    @staticmethod
+    def sub_constant(col: np.ndarray, value: int) -> None:
+        col[0] = _fr.to_mont((_fr.from_mont(col[0]) - value) % R)
+
+    def kate_division_padded(self, col: np.ndarray, z: int) -> np.ndarray:
+        q = self.kate_division(col, z)
+        return np.concatenate([q, np.zeros((1, 4), dtype=np.uint64)])
+
+    @staticmethod
+    def stack(cols) -> np.ndarray:
+        return np.ascontiguousarray(np.stack(cols))
+
+    @staticmethod
+    def key_blocks(pk) -> dict:
+        return {"fixed_values": pk.fixed_values, "fixed_polys": pk.fixed_polys, "sigmas": pk.sigmas,
+                "sigma_polys": pk.sigma_polys}
+
+    def release(self) -> None:
+        pass
+
+    def free(self) -> None:
+        pass
+
+
+class Engine(ArrayBlocks):
+    """Host-API engine: every numeric step is one call into the C ABI with HOST arrays (each call copies its
+    operands in and its result out), the way the reference's `cuda` build drives its GPU.  Used by keygen and
+    available to create_proof (`engine=Engine(params, domain)`); create_proof's default is ResidentEngine."""
 
     def __init__(self, params, domain):
         from ._lib import require_gpu
         require_gpu()
         self.params, self.domain = params, domain
 
-    # -- commitments
-    @staticmethod
-    def _points(jac: np.ndarray) -> List[Point]:
-        from .transcript import point_from_engine
-        return [point_from_engine(p) for p in jac]
+    _points = staticmethod(_points)
 
+    # -- commitments
     def commit_lagrange(self, cols: np.ndarray, max_bits: int = _fr.NUM_BITS) -> List[Point]:
         """Params::commit_lagrange[_with_bound] per column (plonk/prover.rs:124-127, 293-299)"""
-        return self._points(self.params.commit_lagrange_batch(np.ascontiguousarray(cols), max_bits))
+        return _points(self.params.commit_lagrange_batch(np.ascontiguousarray(cols), max_bits))
 
     def commit_lagrange_and_ifft(self, cols: np.ndarray) -> List[Point]:
         """Params::commit_lagrange_and_ifft per column (plonk/prover.rs:470-501, 535-553, 561-593); cols become
         coefficient forms in place"""
         d = self.domain
-        return self._points(self.params.commit_lagrange_batch(cols, ifft=(d.omega_inv, d.ifft_divisor)))
+        return _points(self.params.commit_lagrange_batch(cols, ifft=(d.omega_inv, d.ifft_divisor)))
 
     def commit(self, cols: np.ndarray) -> List[Point]:
         """Params::commit per polynomial (vanishing/prover.rs:64, 86-96; gwc/prover.rs:162)"""
-        return self._points(self.params.commit_batch(cols))
+        return _points(self.params.commit_batch(cols))
 
     # -- transforms
     def lagrange_to_coeff(self, cols: np.ndarray) -> np.ndarray:
@@ -364,15 +462,13 @@ class Engine:
 
     def to_mont(self, canonical: np.ndarray) -> np.ndarray:
         """canonical limbs -> Montgomery: the Montgomery product with R^2"""
-        r2 = np.array([(pow(2, 512, R) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
         c = np.ascontiguousarray(canonical, dtype=np.uint64).reshape(-1, 4)
-        return self.fr_vec("mul", c, np.broadcast_to(r2, c.shape))
+        return self.fr_vec("mul", c, np.broadcast_to(_RAW_R2, c.shape))
 
     def from_mont(self, a: np.ndarray) -> np.ndarray:
         """Montgomery -> canonical limbs: the Montgomery product with 1"""
-        one = np.array([1, 0, 0, 0], dtype=np.uint64)
         a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
-        return self.fr_vec("mul", a, np.broadcast_to(one, a.shape))
+        return self.fr_vec("mul", a, np.broadcast_to(_RAW_ONE, a.shape))
 
     # -- z columns and the quotient
     def compress(self, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
@@ -413,6 +509,336 @@ class Engine:
         return kate_division(poly, _fr.to_mont(z))
 
 
+_RAW_ONE = np.array([1, 0, 0, 0], dtype=np.uint64)                                     # canonical 1 (not Montgomery)
+_RAW_R2 = np.array([(pow(2, 512, R) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+
+
+class DevBlock:
+    """`count` columns of n field elements in one device allocation (ResidentEngine); a block of one column is
+    also what the engine hands out as a column"""
+    __slots__ = ("ptr", "count", "n")
+
+    def __init__(self, ptr: int, count: int, n: int):
+        self.ptr, self.count, self.n = ptr, count, n
+
+    def col(self, i: int) -> "DevBlock":
+        return DevBlock(self.ptr + i * self.n * 32, 1, self.n)
+
+
+class ResidentEngine:
+    """Device-resident engine: every witness column crosses PCIe once (pipelined with its commitment), every other
+    polynomial is born in HBM and stays there -- z columns, multiplicities, the random polynomial, h(X), the folded
+    multiopen polynomials and their quotients; only commitments (96 B), evaluations (32 B) and, for logup, the
+    compressed input / table values (the multiplicities are counted on the host, as in the reference) go back.
+    The proving key's polynomials, and their evaluations on every coset of the extended domain, are made resident
+    on first use and kept for later proofs (pk.fixed_cosets / permutation cosets are what the reference's CPU
+    prover keeps too, plonk/keygen.rs)."""
+
+    def __init__(self, params, domain):
+        from ._lib import require_gpu
+        require_gpu()
+        self.params, self.domain = params, domain
+        self._live: list = []          # per-proof device buffers, freed by release()
+        self._kept: list = []          # proving-key data and constants, freed by free()
+        self._keys: dict = {}          # id(pk) -> resident proving-key data (kept across proofs)
+        self._consts: dict = {}
+
+    # -- memory
+    def _buffer(self, elems: int, keep: bool = False):
+        from .evaluation import DeviceBuffer
+        b = DeviceBuffer(elems)
+        (self._kept if keep else self._live).append(b)
+        return b
+
+    def alloc(self, count: int) -> DevBlock:
+        n = self.domain.n
+        return DevBlock(self._buffer(max(1, count) * n).ptr, count, n)
+
+    def put(self, host: np.ndarray, keep: bool = False) -> DevBlock:
+        host = np.ascontiguousarray(host, dtype=np.uint64)
+        count, n = host.shape[0], host.shape[1]
+        b = self._buffer(max(1, count) * n, keep)
+        if count:
+            b.upload(host)
+        return DevBlock(b.ptr, count, n)
+
+    @staticmethod
+    def cols(block: DevBlock) -> list:
+        return [block.col(i) for i in range(block.count)]
+
+    @staticmethod
+    def write_rows(col: DevBlock, row: int, values: np.ndarray) -> None:
+        from .grand_product import _h2d
+        _h2d(col.ptr + row * 32, values)
+
+    def get(self, block: DevBlock) -> np.ndarray:
+        import ctypes
+        from ._lib import check, lib
+        out = np.empty((block.count, block.n, 4), dtype=np.uint64)
+        check(lib().b2_memcpy_d2h(ctypes.c_void_p(out.ctypes.data), ctypes.c_void_p(block.ptr), out.nbytes))
+        return out
+
+    def stack(self, cols) -> DevBlock:
+        """columns -> one contiguous block (device-to-device copies)"""
+        import ctypes
+        from ._lib import check, lib
+        n = self.domain.n
+        out = self.alloc(len(cols))
+        for i, c in enumerate(cols):
+            check(lib().b2_memcpy_d2d(ctypes.c_void_p(out.ptr + i * n * 32), ctypes.c_void_p(c.ptr), n * 32))
+        return out
+
+    def _const_column(self, name: str, limbs: np.ndarray) -> int:
+        """a resident column filled with one value (operand of the element-wise kernel)"""
+        if name not in self._consts:
+            n = self.domain.n
+            self._consts[name] = self.put(np.broadcast_to(limbs, (1, n, 4)), keep=True)
+        return self._consts[name].ptr
+
+    def release(self) -> None:
+        """free what the last proof allocated; the proving key stays resident"""
+        for b in self._live:
+            b.free()
+        self._live = []
+
+    def free(self) -> None:
+        """release() + the resident proving keys and constants"""
+        self.release()
+        for b in self._kept:
+            b.free()
+        self._kept = []
+        self._keys, self._consts = {}, {}
+
+    # -- commitments
+    def _commit(self, srs, host_ptr, block: DevBlock, max_bits: int, ifft: bool) -> List[Point]:
+        import ctypes
+        from ._lib import check, lib, ptr
+        d = self.domain
+        out = np.zeros((block.count, 12), dtype=np.uint64)
+        if block.count:
+            vp = ctypes.c_void_p
+            check(lib().b2_commit_batch_resident(srs.handle, vp(host_ptr) if host_ptr else None, 0 if host_ptr else 1,
+                                                 vp(block.ptr), block.count, block.n, int(max_bits), 1 if ifft else 0,
+                                                 ptr(d.omega_inv), ptr(d.ifft_divisor), d.k, ptr(out)))
+        return _points(out)
+
+    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: int):
+        """host columns -> resident block, committed on the way in (copy of column i + 1 overlaps the MSM of column i)"""
+        if not (host.flags.c_contiguous and host.dtype == np.uint64 and host.ndim == 3):
+            raise B2Error(B2_ERR_ARG, "expected a C-contiguous uint64 (columns, n, 4) array")
+        block = self.alloc(host.shape[0])
+        return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, max_bits, False)
+
+    def commit_lagrange(self, block: DevBlock, max_bits: int = _fr.NUM_BITS) -> List[Point]:
+        return self._commit(self.params.g_lagrange, 0, block, max_bits, False)
+
+    def commit_lagrange_and_ifft(self, block: DevBlock) -> List[Point]:
+        return self._commit(self.params.g_lagrange, 0, block, _fr.NUM_BITS, True)
+
+    def commit(self, block: DevBlock) -> List[Point]:
+        return self._commit(self.params.g, 0, block, _fr.NUM_BITS, False)
+
+    # -- transforms
+    def lagrange_to_coeff(self, block: DevBlock) -> DevBlock:
+        import ctypes
+        from ._lib import NttDesc, check, lib
+        if block.count:
+            dm = self.domain
+            d = NttDesc()
+            d.log_n, d.location = dm.k, 1
+            d.omega, d.divisor = dm.omega_inv.ctypes.data, dm.ifft_divisor.ctypes.data
+            d.n_in = d.n_out = d.in_stride = d.out_stride = dm.n
+            d.columns = block.count
+            d.in_ = d.out = block.ptr
+            check(lib().b2_ntt_exec(ctypes.byref(d)))
+        return block
+
+    # -- element-wise
+    def _fr_vec(self, op: int, a_ptr: int, b_ptr: int, count: int, out_ptr: int) -> None:
+        import ctypes
+        from ._lib import check, lib
+        vp = ctypes.c_void_p
+        check(lib().b2_fr_vec_dev(op, vp(a_ptr), vp(b_ptr), count, vp(out_ptr), None))
+
+    # -- logup
+    def _columns(self, pk, advice: DevBlock, instance: DevBlock):
+        from .grand_product import _Columns
+        key = self.key_blocks(pk)
+        ptrs = lambda b: [b.ptr + i * b.n * 32 for i in range(b.count)]      # noqa: E731
+        return _Columns.resident(ptrs(key["fixed_values"]), ptrs(advice), ptrs(instance), self.domain.n)
+
+    def compress_canonical(self, expression_lists, advice, fixed, instance, theta: int, pk=None) -> np.ndarray:
+        from .grand_product import _Columns, compress_expressions_dev
+        n = self.domain.n
+        ptrs = lambda b: [b.ptr + i * b.n * 32 for i in range(b.count)]      # noqa: E731
+        cols = _Columns.resident(ptrs(fixed), ptrs(advice), ptrs(instance), n)
+        out = self.alloc(len(expression_lists))
+        compress_expressions_dev(self.domain, expression_lists, cols, theta, out.ptr)
+        one = self._const_column("raw_one", _RAW_ONE)
+        for i in range(out.count):                                            # Montgomery -> canonical
+            self._fr_vec(0, out.ptr + i * n * 32, one, n, out.ptr + i * n * 32)
+        return self.get(out)
+
+    def put_canonical(self, canonical: np.ndarray) -> DevBlock:
+        n = self.domain.n
+        block = self.put(canonical)
+        r2 = self._const_column("raw_r2", _RAW_R2)
+        for i in range(block.count):                                          # canonical -> Montgomery
+            self._fr_vec(0, block.ptr + i * n * 32, r2, n, block.ptr + i * n * 32)
+        return block
+
+    # -- z columns
+    def permutation_z(self, cs, pk, advice, instance, beta, gamma, blinds, out_cols) -> None:
+        from .grand_product import permutation_commit_dev
+        sig = self.key_blocks(pk)["sigmas"]
+        permutation_commit_dev(self.domain, cs.permutation_columns, cs.degree(), cs.blinding_factors(),
+                               [sig.ptr + j * sig.n * 32 for j in range(sig.count)], self._columns(pk, advice, instance),
+                               beta, gamma, blinds, [c.ptr for c in out_cols])
+
+    def logup_z(self, cs, lookup, pk, advice, instance, m_col, theta, beta, out_cols) -> None:
+        from .grand_product import logup_commit_z_dev
+        logup_commit_z_dev(self.domain, lookup, cs.blinding_factors(), self._columns(pk, advice, instance), m_col.ptr,
+                           theta, beta, [c.ptr for c in out_cols])
+
+    def shuffle_z(self, cs, group, pk, advice, instance, theta, beta, out_col) -> None:
+        from .grand_product import shuffle_commit_product_dev
+        shuffle_commit_product_dev(self.domain, group, cs.blinding_factors(), self._columns(pk, advice, instance), theta,
+                                   beta, out_col.ptr)
+
+    # -- vanishing argument
+    def random_poly(self, random, a, u, b, v) -> DevBlock:
+        n = self.domain.n
+        kk = np.uint64(random.shape[0])
+        blk = self.put(np.stack([a, random[(u % kk).astype(np.int64)], b, random[(v % kk).astype(np.int64)]]))
+        p = [blk.ptr + i * n * 32 for i in range(4)]
+        self._fr_vec(1, p[0], p[1], n, p[0])
+        self._fr_vec(1, p[2], p[3], n, p[2])
+        self._fr_vec(0, p[0], p[2], n, p[0])
+        return DevBlock(blk.ptr, 1, n)
+
+    def key_blocks(self, pk) -> dict:
+        """the proving key's columns, resident (made so on first use)"""
+        key = self._keys.get(id(pk))
+        if key is None:
+            key = {name: self.put(getattr(pk, name), keep=True)
+                   for name in ("fixed_values", "fixed_polys", "sigmas", "sigma_polys")}
+            self._keys[id(pk)] = key
+        return key
+
+    def _key_cosets(self, pk) -> list:
+        """per coset c of the extended domain: one block holding the evaluations of the fixed and sigma polynomials
+        on it, followed by the rows of l0 / l_last / l_active_row that belong to it"""
+        from .evaluation import coeff_to_coset_dev
+        key = self.key_blocks(pk)
+        if "cosets" not in key:
+            dm = self.domain
+            n = dm.n
+            nc = 1 << (dm.extended_k - dm.k)
+            F, S = key["fixed_polys"].count, key["sigma_polys"].count
+            out = []
+            for c in range(nc):
+                g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
+                blk = DevBlock(self._buffer((F + S + 3) * n, keep=True).ptr, F + S + 3, n)
+                if F:
+                    coeff_to_coset_dev(dm, key["fixed_polys"].ptr, F, g_c, blk.ptr)
+                if S:
+                    coeff_to_coset_dev(dm, key["sigma_polys"].ptr, S, g_c, blk.ptr + F * n * 32)
+                for i, v in enumerate((pk.l0, pk.l_last, pk.l_active_row)):
+                    rows = np.ascontiguousarray(np.asarray(v, dtype=np.uint64).reshape(-1, 4)[c::nc])
+                    self.write_rows(blk.col(F + S + i), 0, rows)
+                out.append(blk)
+            key["cosets"] = out
+        return key["cosets"]
+
+    def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta) -> DevBlock:
+        """Evaluator::evaluate_h (plonk/evaluation.rs:778-1226) coset by coset from resident coefficient forms,
+        divide_by_vanishing_poly folded into the store, extended_to_coeff on the device (vanishing/prover.rs:72-76):
+        -> the h(X) pieces as a resident block"""
+        import ctypes
+        from ._lib import NttDesc, check, lib
+        from .evaluation import coeff_to_coset_dev
+        dm = self.domain
+        n = dm.n
+        nc = 1 << (dm.extended_k - dm.k)
+        key_cosets = self._key_cosets(pk)
+        F, S = pk.fixed_polys.shape[0], pk.sigma_polys.shape[0]
+        prog = pk.ev.program(n_perm, list(lookup_z_counts), n_shuffles)
+        challenges = [beta % R, gamma % R, theta % R, y % R]
+        d = beta * dm._zeta % R                                               # delta_start, evaluation.rs:1011
+        for _ in range(S):
+            challenges.append(d)
+            d = d * DELTA % R
+        witness = [b for b in (advice, instance, z_block, m_block) if b.count]
+        cos = {id(b): self.alloc(b.count) for b in witness}
+        hext = self._buffer(dm.extended_len())
+        ptrs = lambda b: [cos[id(b)].ptr + i * n * 32 for i in range(b.count)] if b.count else []     # noqa: E731
+        for c in range(nc):
+            g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
+            for b in witness:
+                coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
+            kc = key_cosets[c]
+            kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
+            zp, mp = ptrs(z_block), ptrs(m_block)
+            aux = kp[F + S:F + S + 3] + kp[F:F + S] + zp[:n_perm]
+            pos = n_perm
+            for li, cnt in enumerate(lookup_z_counts):
+                aux += zp[pos:pos + cnt] + [mp[li]]
+                pos += cnt
+            aux += zp[pos:pos + n_shuffles]
+            prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
+                      x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
+                      out_stride=nc, out_offset=c)
+        pieces = dm.quotient_poly_degree
+        hcoef = self.alloc(pieces)
+        z = np.concatenate([dm.g_coset_inv, dm.g_coset])                      # leaving the coset: {zeta^2, zeta}
+        t = NttDesc()
+        t.log_n, t.location = dm.extended_k, 1
+        t.omega, t.divisor = dm.extended_omega_inv.ctypes.data, dm.extended_ifft_divisor.ctypes.data
+        t.coset_out = z.ctypes.data
+        t.n_in = t.in_stride = dm.extended_len()
+        t.n_out = t.out_stride = n * pieces
+        t.columns, t.in_, t.out = 1, hext.ptr, hcoef.ptr
+        check(lib().b2_ntt_exec(ctypes.byref(t)))
+        return hcoef
+
+    # -- evaluation and opening
+    def eval_polynomial(self, col: DevBlock, point: int) -> int:
+        import ctypes
+        from ._lib import check, lib, ptr
+        out = np.empty(4, dtype=np.uint64)
+        pt = _fr.to_mont(point)
+        check(lib().b2_eval_polynomial_dev(ctypes.c_void_p(col.ptr), 1, col.n, col.n, ptr(pt), ptr(out)))
+        return _fr.from_mont(out)
+
+    def poly_combine(self, cols, v: int) -> DevBlock:
+        import ctypes
+        from ._lib import check, lib, ptr
+        out = self.alloc(1)
+        arr = (ctypes.c_void_p * len(cols))(*[c.ptr for c in cols])
+        vm = _fr.to_mont(v)
+        check(lib().b2_poly_combine_dev(arr, len(cols), self.domain.n, ptr(vm), ctypes.c_void_p(out.ptr), None))
+        return out
+
+    def sub_constant(self, col: DevBlock, value: int) -> None:
+        import ctypes
+        from ._lib import check, lib
+        c0 = np.empty(4, dtype=np.uint64)
+        check(lib().b2_memcpy_d2h(ctypes.c_void_p(c0.ctypes.data), ctypes.c_void_p(col.ptr), 32))
+        self.write_rows(col, 0, _fr.to_mont((_fr.from_mont(c0) - value) % R).reshape(1, 4))
+
+    def kate_division_padded(self, col: DevBlock, z: int) -> DevBlock:
+        """kate_division (n - 1 coefficients) into a column of n with a zero on top, so that it commits like one"""
+        import ctypes
+        from ._lib import check, lib, ptr
+        n = self.domain.n
+        out = self.alloc(1)
+        zm = _fr.to_mont(z)
+        check(lib().b2_kate_division_dev(ctypes.c_void_p(col.ptr), n, ptr(zm), ctypes.c_void_p(out.ptr), None))
+        self.write_rows(out, n - 1, np.zeros((1, 4), dtype=np.uint64))
+        return out
+
+
 # --------------------------------------------------------------------------
 # keygen
 # --------------------------------------------------------------------------
@@ -446,7 +872,7 @@ def identity_mapping(m: int, n: int) -> np.ndarray:
     return out
 
 
-def keygen(params, cs, fixed: np.ndarray, mapping, engine: Optional[Engine] = None, zeta: Optional[int] = None,
+def keygen(params, cs, fixed: np.ndarray, mapping, engine=None, zeta: Optional[int] = None,
            transcript_repr: Optional[int] = None) -> ProvingKey:
     """keygen_vk + keygen_pk for a laid-out circuit.  fixed: (num_fixed, n, 4) Lagrange columns; mapping: the
     permutation as (m, n, 2) integers (column position in cs.permutation_columns, row), Assembly.mapping."""
@@ -544,14 +970,15 @@ def _max_bits(counts: np.ndarray) -> int:
 
 
 def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence[Sequence[int]], rng,
-                 sign_bit: int = 7, engine: Optional[Engine] = None, advice_max_bits: int = _fr.NUM_BITS,
+                 sign_bit: int = 7, engine=None, advice_max_bits: int = _fr.NUM_BITS,
                  timings: Optional[dict] = None) -> bytes:
     """plonk::create_proof (GWC multiopen) for one circuit instance, advice given (create_proof_from_witness).
 
-    advice: (num_advice, n, 4) Lagrange columns; consumed (blinding rows are written into it and it ends up in
-    coefficient form).  instances: per instance column the public values (canonical ints), zero padded internally.
-    advice_max_bits: the bound handed to commit_lagrange_with_bound (the reference scans each column for its
-    largest scalar, plonk/prover.rs:945-962, 296; a caller that knows its witness range passes it).
+    advice: (num_advice, n, 4) Lagrange columns in host memory (pinned memory makes the one upload faster); the
+    blinding rows are written into it.  instances: per instance column the public values (canonical ints), zero
+    padded internally.  advice_max_bits: the bound handed to commit_lagrange_with_bound (the reference scans each
+    column for its largest scalar, plonk/prover.rs:945-962, 296; a caller that knows its witness range passes it).
+    engine: ResidentEngine(params, domain) by default; pass one to keep the proving key resident across proofs.
 
     Random values come from `rng` in this order (vector draws):
       1. u16_vec(num_advice * (bf + 1)): advice column i takes [i*(bf+1), (i+1)*(bf+1)) for its last bf+1 rows
@@ -563,7 +990,18 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
     import time
     vk = pk.vk
     cs, domain = vk.cs, vk.domain
-    E = engine or Engine(params, domain)
+    E = engine or ResidentEngine(params, domain)
+    try:
+        return _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time)
+    finally:
+        if engine is None:
+            E.free()
+        else:
+            E.release()
+
+
+def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time) -> bytes:
+    vk = pk.vk
     n, k = domain.n, domain.k
     bf = cs.blinding_factors()
     usable = n - (bf + 1)
@@ -577,20 +1015,26 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
             timings[name] = timings.get(name, 0.0) + now - t_last[0]
             t_last[0] = now
 
+    key = E.key_blocks(pk)
+    fixed_values = key["fixed_values"]
+
     # ---- create_single_instances (plonk/prover.rs:85-173)
     if len(instances) != cs.num_instance:
         raise B2Error(B2_ERR_ARG, "InvalidInstances")
     tr.common_scalar(vk.transcript_repr)
-    instance_values = np.zeros((cs.num_instance, n, 4), dtype=np.uint64)
+    inst_host = np.zeros((cs.num_instance, n, 4), dtype=np.uint64)
     for i, values in enumerate(instances):
         if len(values) > usable:
             raise B2Error(B2_ERR_ARG, "InstanceTooLarge")
         if len(values):
-            instance_values[i, :len(values)] = _mont_vec(values)
+            inst_host[i, :len(values)] = _mont_vec(values)
+    instance_values = E.put(inst_host)
     if cs.num_instance:
-        for c in E.commit_lagrange(instance_values):
+        for c in E.commit_lagrange(instance_values, _fr.NUM_BITS):
             tr.common_point(c)
-    instance_polys = E.lagrange_to_coeff(instance_values.copy()) if cs.num_instance else instance_values
+    instance_polys = E.put(inst_host.copy())
+    if cs.num_instance:
+        E.lagrange_to_coeff(instance_polys)
     lap("instance")
 
     # ---- advice (:964-1010)
@@ -598,80 +1042,81 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
         raise B2Error(B2_ERR_ARG, f"advice must be a C-contiguous uint64 array of shape ({cs.num_advice}, {n}, 4)")
     blind = rng.u16_vec(cs.num_advice * (bf + 1))
     advice[:, usable:] = _mont_vec(blind).reshape(cs.num_advice, bf + 1, 4)
-    for c in E.commit_lagrange(advice, advice_max_bits):
+    adv, points = E.put_and_commit_lagrange(advice, advice_max_bits)
+    for c in points:
         tr.write_point(c)
     theta = tr.squeeze_challenge()
     lap("advice")
 
     # ---- lookups: compress, multiplicities, m commitments (:334-366, logup/prover.rs:70-256)
-    fixed_values = pk.fixed_values
-    ms = np.zeros((len(cs.lookups), n, 4), dtype=np.uint64)
+    n_lookups = len(cs.lookups)
+    m_canon = np.zeros((n_lookups, n, 4), dtype=np.uint64)
     m_bits = 16
     for li, lk in enumerate(cs.lookups):
         lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
-        comp = E.from_mont(E.compress(lists, advice, fixed_values, instance_values, theta)).reshape(len(lists), n, 4)
+        comp = E.compress_canonical(lists, adv, fixed_values, instance_values, theta)
         counts = logup_multiplicity(list(comp[:-1]), comp[-1], usable, n)
         m_bits = max(m_bits, _max_bits(counts[:usable]))
-        canon = np.zeros((n, 4), dtype=np.uint64)
-        canon[:, 0] = counts.astype(np.uint64)
-        canon[usable:, 0] = rng.u16_vec(bf + 1)
-        ms[li] = E.to_mont(canon)
-    if len(cs.lookups):
+        m_canon[li, :, 0] = counts.astype(np.uint64)
+        m_canon[li, usable:, 0] = rng.u16_vec(bf + 1)
+    ms = E.put_canonical(m_canon)
+    if n_lookups:
         for c in E.commit_lagrange(ms, m_bits):
             tr.write_point(c)
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
     lap("lookup_m")
 
-    # ---- z columns (:411-633): permutation, lookups, shuffles -- built on the device, blinded, committed and
-    # brought to coefficient form as ONE batch
-    zs: List[np.ndarray] = []
-    if cs.permutation_columns:
-        chunk_len = cs.degree() - 2
-        n_sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
-        blinds = [rng.fr_vec(bf) for _ in range(n_sets)]
-        zs += E.permutation_commit(cs, pk.sigmas, advice, fixed_values, instance_values, beta, gamma, blinds)
-    n_perm = len(zs)
-    lookup_z_counts = []
+    # ---- z columns (:411-633): permutation, lookups, shuffles -- built where the engine keeps its columns,
+    # blinded, then committed and brought to coefficient form as ONE batch
+    chunk_len = cs.degree() - 2
+    n_perm = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
+    lookup_z_counts = [len(lk["input_expressions_sets"]) for lk in cs.lookups]
+    n_shuffles = len(cs.shuffles)
+    z_block = E.alloc(n_perm + sum(lookup_z_counts) + n_shuffles)
+    zc = E.cols(z_block)
+    m_cols = E.cols(ms)
+    if n_perm:
+        blinds = [rng.fr_vec(bf) for _ in range(n_perm)]
+        E.permutation_z(cs, pk, adv, instance_values, beta, gamma, blinds, zc[:n_perm])
+    pos = n_perm
     for li, lk in enumerate(cs.lookups):
-        raw = E.logup_commit_z(cs, lk, advice, fixed_values, instance_values, ms[li], theta, beta)
-        lookup_z_counts.append(len(raw))
-        for z in raw:
-            zs.append(np.concatenate([z, rng.fr_vec(bf)]))
-    for group in cs.shuffles:
-        z = E.shuffle_commit_product(cs, group, advice, fixed_values, instance_values, theta, beta)
-        zs.append(np.concatenate([z, rng.fr_vec(bf)]))
-    z_polys = np.ascontiguousarray(np.stack(zs)) if zs else np.zeros((0, n, 4), np.uint64)
-    if len(zs):
-        for c in E.commit_lagrange_and_ifft(z_polys):
-            tr.write_point(c)
-    perm_polys = [z_polys[i] for i in range(n_perm)]
-    lookups, pos = [], n_perm
-    if len(cs.lookups):
-        ms = E.lagrange_to_coeff(ms)                                     # lagrange_to_coeff_st(l.0), :497
-    for li, cnt in enumerate(lookup_z_counts):
-        lookups.append({"z": [z_polys[pos + i] for i in range(cnt)], "m": ms[li]})
+        cnt = lookup_z_counts[li]
+        E.logup_z(cs, lk, pk, adv, instance_values, m_cols[li], theta, beta, zc[pos:pos + cnt])
+        for z in zc[pos:pos + cnt]:
+            E.write_rows(z, n - bf, rng.fr_vec(bf))
         pos += cnt
-    shuffle_polys = [z_polys[pos + i] for i in range(len(cs.shuffles))]
+    for gi, group in enumerate(cs.shuffles):
+        E.shuffle_z(cs, group, pk, adv, instance_values, theta, beta, zc[pos + gi])
+        E.write_rows(zc[pos + gi], n - bf, rng.fr_vec(bf))
+    if len(zc):
+        for c in E.commit_lagrange_and_ifft(z_block):
+            tr.write_point(c)
+    if n_lookups:
+        E.lagrange_to_coeff(ms)                                          # lagrange_to_coeff_st(l.0), :497
+    perm_polys = zc[:n_perm]
+    lookups, pos = [], n_perm
+    for li, cnt in enumerate(lookup_z_counts):
+        lookups.append({"z": zc[pos:pos + cnt], "m": m_cols[li]})
+        pos += cnt
+    shuffle_polys = zc[pos:pos + n_shuffles]
     lap("z_columns")
 
     # ---- vanishing commit, y (:635-639, vanishing/prover.rs:41-70)
     random = rng.fr_vec(k)
     a, u = rng.fr_vec(n), rng.u64_vec(n)
     b, v = rng.fr_vec(n), rng.u64_vec(n)
-    kk = np.uint64(k)
-    random_poly = E.fr_vec("mul", E.fr_vec("add", a, random[(u % kk).astype(np.int64)]),
-                           E.fr_vec("add", b, random[(v % kk).astype(np.int64)]))
-    tr.write_point(E.commit(random_poly.reshape(1, n, 4))[0])
+    random_block = E.random_poly(random, a, u, b, v)
+    random_poly = E.cols(random_block)[0]
+    tr.write_point(E.commit(random_block)[0])
     y = tr.squeeze_challenge()
     lap("vanishing_commit")
 
     # ---- h(X) (:640-690, vanishing/prover.rs:64-110)
-    advice_polys = E.lagrange_to_coeff(advice)                           # lagrange_to_coeff_st per column, :643-646
-    h_coeffs = E.evaluate_h(pk, advice_polys, instance_polys, y, beta, gamma, theta, lookups, shuffle_polys, perm_polys)
-    n_pieces = h_coeffs.shape[0] // n                                     # par_chunks_exact(n)
-    h_pieces = np.ascontiguousarray(h_coeffs[:n_pieces * n]).reshape(n_pieces, n, 4)
-    for c in E.commit(h_pieces):
+    E.lagrange_to_coeff(adv)                                             # lagrange_to_coeff_st per column, :643-646
+    h_block = E.evaluate_h_blocks(pk, adv, instance_polys, z_block, ms, n_perm, lookup_z_counts, n_shuffles,
+                                  y, beta, gamma, theta)
+    for c in E.commit(h_block):
         tr.write_point(c)
     x = tr.squeeze_challenge()
     xn = pow(x, n, R)
@@ -680,15 +1125,17 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
     # ---- evaluations (:694-790)
     rot = lambda at: x * pow(domain._omega if at >= 0 else domain._omega_inv, abs(at), R) % R      # noqa: E731
     ev = E.eval_polynomial
+    advice_polys, inst_cols = E.cols(adv), E.cols(instance_polys)
+    fixed_polys, sigma_polys = E.cols(key["fixed_polys"]), E.cols(key["sigma_polys"])
     for col, at in queries["Instance"]:
-        tr.write_scalar(ev(instance_polys[col], rot(at)))
+        tr.write_scalar(ev(inst_cols[col], rot(at)))
     for col, at in queries["Advice"]:
         tr.write_scalar(ev(advice_polys[col], rot(at)))
     for col, at in queries["Fixed"]:
-        tr.write_scalar(ev(pk.fixed_polys[col], rot(at)))
-    h_poly = E.poly_combine([h_pieces[i] for i in reversed(range(n_pieces))], xn)   # fold acc * xn + piece, rev
+        tr.write_scalar(ev(fixed_polys[col], rot(at)))
+    h_poly = E.poly_combine(list(reversed(E.cols(h_block))), xn)       # fold acc * xn + piece over rev pieces
     tr.write_scalar(ev(random_poly, x))
-    for poly in pk.sigma_polys:
+    for poly in sigma_polys:
         tr.write_scalar(ev(poly, x))
     last = -(bf + 1)
     x_next, x_last = rot(1), rot(last)
@@ -710,7 +1157,7 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
     lap("evaluations")
 
     # ---- multiopen queries (:792-838) as (rotation, point, polynomial)
-    qs: List[Tuple[int, int, np.ndarray]] = []
+    qs: List[Tuple[int, int, object]] = []
 
     def open_z_set(polys):
         for z in polys:
@@ -720,7 +1167,7 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
             qs.append((last, x_last, z))
 
     for col, at in queries["Instance"]:
-        qs.append((at, rot(at), instance_polys[col]))
+        qs.append((at, rot(at), inst_cols[col]))
     for col, at in queries["Advice"]:
         qs.append((at, rot(at), advice_polys[col]))
     open_z_set(perm_polys)
@@ -731,21 +1178,21 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
         qs.append((0, x, z))
         qs.append((1, x_next, z))
     for col, at in queries["Fixed"]:
-        qs.append((at, rot(at), pk.fixed_polys[col]))
-    for poly in pk.sigma_polys:
+        qs.append((at, rot(at), fixed_polys[col]))
+    for poly in sigma_polys:
         qs.append((0, x, poly))
     qs.append((0, x, h_poly))
     qs.append((0, x, random_poly))
 
-    gwc_create_proof(E, tr, qs, n)
+    gwc_create_proof(E, tr, qs)
     lap("multiopen")
     return tr.finalize()
 
 
-def gwc_create_proof(E: Engine, tr: Blake2bWrite, queries, n: int) -> None:
+def gwc_create_proof(E, tr: Blake2bWrite, queries) -> None:
     """poly/multiopen/gwc/prover.rs:19-173.  construct_intermediate_sets (gwc.rs:38-62) groups the queries by
     ROTATION (BTreeMap<Rotation, _>, ascending), point = the first query's; per group the polynomials are folded with
-    v on the device (the reference's cuda build does the same for groups of more than four), the folded polynomial
+    v by the engine (the reference's cuda build does the same for groups of more than four), the folded polynomial
     is evaluated and divided by (X - z) there, and all witness polynomials are committed as one batch."""
     v = tr.squeeze_challenge()
     groups: Dict[int, list] = {}
@@ -759,7 +1206,7 @@ def gwc_create_proof(E: Engine, tr: Blake2bWrite, queries, n: int) -> None:
             raise B2Error(B2_ERR_ARG, "assert_eq!(query.get_point(), z)")
         poly_batch = E.poly_combine([q[2] for q in group], v)
         eval_batch = E.eval_polynomial(poly_batch, z)
-        poly_batch[0] = _fr.to_mont((_fr.from_mont(poly_batch[0]) - eval_batch) % R)
-        witnesses.append(E.kate_division(poly_batch, z))
-    for c in E.commit(np.ascontiguousarray(np.stack(witnesses))):
+        E.sub_constant(poly_batch, eval_batch)
+        witnesses.append(E.kate_division_padded(poly_batch, z))
+    for c in E.commit(E.stack(witnesses)):
         tr.write_point(c)

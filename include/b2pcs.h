@@ -66,6 +66,11 @@ int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_
 /* Synthetic bases for benchmarks / property tests: bases[i] = [h(seed, first+i)] G with
  * h = 64-bit splitmix64 hash, generated on the device. */
 int b2_srs_synthetic(size_t n, uint64_t first_index, uint64_t seed, b2_handle_t* out);
+/* bases[i] = [k_i] G for n Montgomery-form Fr scalars resident on the device: the point side of
+ * Params::unsafe_setup (poly/commitment.rs:63-112: g[i] = [s^i] G and g_lagrange[i] = [l_i(s)] G); the scalar side
+ * (powers, batch inversion) is composed from b2_prefix_scan_dev / b2_batch_invert_dev / b2_fr_vec_dev by the host
+ * mirror (commitment.py Params.unsafe_setup).  The new SRS is resident like a registered one. */
+int b2_srs_from_scalars_dev(const void* d_scalars, size_t n, b2_handle_t* out);
 /* Build the window table of a resident SRS: table[w][i] = 2^(window_bits * w) * P_i for every
  * window w (affine, in HBM: 254/window_bits + 1 copies of the SRS).  MSMs against this SRS then
  * drop every scalar digit into ONE shared bucket set: no per-window bucket reduction and no
@@ -328,6 +333,7 @@ int b2_dev_alloc(size_t bytes, void** out);
 int b2_dev_free(void* p);
 int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
 int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
+int b2_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes);
 
 /* ---- diagnostics used by tests / bench -------------------------------------------- */
 /* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a),

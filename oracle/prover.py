@@ -1,4 +1,4 @@
-"""CPU oracle for the whole proof: keygen, create_proof (GWC and SHPLONK-free GWC default) and verify_proof.
+"""CPU oracle for the whole proof: keygen, create_proof and verify_proof (GWC multiopen, the `create_proof` default).
 
 TEST INFRASTRUCTURE ONLY (same rules as oracle/bn254.py and oracle/plonk.py): only tests/,
 __graft_entry__.smoke() and bench.py's cpu_baseline leg may import this file.
@@ -249,6 +249,30 @@ class Params:
     def commit_lagrange(self, poly: Sequence[int]) -> Point:
         assert len(poly) <= self.n
         return msm(poly, self.g_lagrange)
+
+
+class ParamsVerifier:
+    """What verify_proof reads from the parameters (poly/commitment.rs:296-389 ParamsVerifier: g1, s_g2, g_lagrange
+    for the public inputs) without materialising 2 * 2^k points: g_lagrange[i] is computed on demand, so proofs
+    over large domains can be checked when the SRS itself was built on the device (Params.unsafe_setup)."""
+
+    def __init__(self, k: int, s: int):
+        self.k, self.n, self.s = k, 1 << k, s % R
+        self.g1 = o.G1_GEN
+        root = o.FR_ROOT_OF_UNITY
+        for _ in range(k, o.FR_S):
+            root = root * root % R
+        self._root = root
+        self._mult = (pow(s, self.n, R) - 1) * o.fr_inv(self.n % R) % R
+
+    def commit_lagrange(self, poly: Sequence[int]) -> Point:
+        acc: Point = None
+        for i, v in enumerate(poly):
+            if v % R:
+                rp = pow(self._root, i, R)
+                li = self._mult * rp % R * o.fr_inv((self.s - rp) % R) % R          # commitment.rs:85-112
+                acc = o.g1_add(acc, o.g1_mul(o.G1_GEN, li * v % R))
+        return acc
 
 
 # --------------------------------------------------------------------------

@@ -11,6 +11,8 @@ from oracle import bn254 as o
 from oracle import cref
 from oracle import plonk as P
 
+from halo2_gpu_specific_b200.plonk import ArrayBlocks
+
 R = o.R_MOD
 enc, dec = o.fr_encode, o.fr_decode
 
@@ -26,9 +28,13 @@ class _Blinds:
         return self.q.pop(0)
 
 
-class OracleEngine:
+class OracleEngine(ArrayBlocks):
+    """array primitives answered by the oracle; the block protocol on top of them is the package's own ArrayBlocks
+    (the same code the host-API device engine uses)"""
+
     def __init__(self, oracle_params, oracle_domain, oracle_cs):
         self.p, self.d, self.cs = oracle_params, oracle_domain, oracle_cs
+        self.domain = oracle_domain
         self.ev = P.Evaluator.new(oracle_cs)
 
     # -- commitments

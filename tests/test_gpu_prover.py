@@ -32,8 +32,9 @@ def engine_side(k, oparams, cs, fixed, mapping, transcript_repr):
     return params, pk
 
 
+@pytest.mark.parametrize("engine_kind", ["resident", "host_api"])
 @pytest.mark.parametrize("k,seed,rng_seed", [(5, 11, 1), (6, 17, 2)])
-def test_proof_bytes_match_oracle(gpu, k, seed, rng_seed):
+def test_proof_bytes_match_oracle(gpu, k, seed, rng_seed, engine_kind):
     fx = fxm.build(k=k, seed=seed)
     ocs = fx["cs"]
     oparams = PR.Params(k, S_TOXIC)
@@ -54,7 +55,18 @@ def test_proof_bytes_match_oracle(gpu, k, seed, rng_seed):
         want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(rng_seed))
         adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
         launches0 = gpu.lib().b2_launch_count(0)
-        got = HP.create_proof(params, pk, adv, inst, HP.SeededRng(rng_seed))
+        if engine_kind == "resident":
+            eng = HP.ResidentEngine(params, pk.vk.domain)
+            try:
+                got = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(rng_seed), engine=eng)
+                # a second proof on the same engine reuses the resident proving key (and its cosets)
+                again = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(rng_seed), engine=eng)
+                assert again == got
+            finally:
+                eng.free()
+            assert HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(rng_seed)) == got     # default engine
+        else:
+            got = HP.create_proof(params, pk, adv, inst, HP.SeededRng(rng_seed), engine=HP.Engine(params, pk.vk.domain))
         assert gpu.lib().b2_launch_count(0) > launches0
         assert got == want
         assert PR.verify_proof(oparams, opk.vk, inst, got, pairing=(k == 5))
@@ -82,8 +94,20 @@ def test_commit_batch_against_g(gpu):
     try:
         from oracle import cref
         x = cref.random_fr_mont(3 * 127, 0xB2000081).reshape(3, 127, 4)
-        got = [HP.Engine._points(params.commit_batch(x))[i] for i in range(3)]
+        got = HP._points(params.commit_batch(x))
         assert got == [oparams.commit(dec(x[i])) for i in range(3)]
+    finally:
+        params.free()
+
+
+@pytest.mark.parametrize("k", [1, 6, 11])
+def test_unsafe_setup_matches_oracle(gpu, k):
+    """Params::unsafe_setup on the device (poly/commitment.rs:56-124): every point of g and g_lagrange"""
+    oparams = PR.Params(k, S_TOXIC)
+    params = h2.Params.unsafe_setup(k, S_TOXIC, precompute=False)
+    try:
+        assert np.array_equal(params.g.read(), oparams.g)
+        assert np.array_equal(params.g_lagrange.read(), oparams.g_lagrange)
     finally:
         params.free()
 
@@ -97,18 +121,22 @@ def _bench_circuit(k):
     return cs, ocs, fixed, advice, mapping
 
 
-@pytest.mark.parametrize("k,pairing", [(8, True), (14, False), (18, True)])
-def test_benches_plonk_circuit_proof_verifies(gpu, k, pairing):
+@pytest.mark.parametrize("k,pairing,engine_kind", [(8, True, "resident"), (14, False, "host_api"), (18, True, "resident"),
+                                                   (20, False, "resident")])
+def test_benches_plonk_circuit_proof_verifies(gpu, k, pairing, engine_kind):
     """BASELINE config 4: the benches/plonk.rs circuit, full create_proof on the engine, accepted by the oracle
-    verifier.  The verifying key the oracle reads is the one the ENGINE's keygen produced (commitments computed on
-    the device); the oracle side only needs the SRS trapdoor / [s]G2 and the constraint system."""
+    verifier.  The SRS is built on the device (Params.unsafe_setup) and the verifying key the oracle reads is the
+    one the ENGINE's keygen produced (commitments computed on the device); the oracle side only needs the SRS
+    trapdoor / [s]G2 and the constraint system."""
     cs, ocs, fixed, advice, mapping = _bench_circuit(k)
-    oparams = PR.Params(k, S_TOXIC)
-    params = h2.Params(k, oparams.g, oparams.g_lagrange)
+    oparams = PR.Params(k, S_TOXIC) if k <= 8 else PR.ParamsVerifier(k, S_TOXIC)
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
     try:
         pk = HP.keygen(params, cs, fixed, mapping)
         timings = {}
-        proof = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(k), timings=timings)
+        eng = HP.ResidentEngine(params, pk.vk.domain) if engine_kind == "resident" else HP.Engine(params, pk.vk.domain)
+        HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(0), engine=eng)              # warm-up
+        proof = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(k), timings=timings, engine=eng)
         assert len(proof) == 32 * ((3 + 1 + 1 + 4) + (3 + 4 + 1 + 3 + 2) + 2)
         ovk = PR.VerifyingKey(ocs, o.EvaluationDomain(cs.degree(), k), pk.vk.fixed_commitments,
                               pk.vk.permutation_commitments, pk.vk.transcript_repr)
@@ -122,8 +150,10 @@ def test_benches_plonk_circuit_proof_verifies(gpu, k, pairing):
         # a broken witness (one product row off by one) must not verify
         bad = advice.copy()
         bad[2, 4] = enc([5])[0]
-        proof_bad = HP.create_proof(params, pk, bad, [], HP.SeededRng(k))
+        proof_bad = HP.create_proof(params, pk, bad, [], HP.SeededRng(k), engine=eng)
         assert not PR.verify_proof(oparams, ovk, [], proof_bad)
-        print(f"k={k} create_proof phases (s): " + ", ".join(f"{a} {b:.4f}" for a, b in timings.items()))
+        eng.free()
+        print(f"k={k} {engine_kind} create_proof {sum(timings.values()):.4f} s: "
+              + ", ".join(f"{a} {b:.4f}" for a, b in timings.items()))
     finally:
         params.free()
