@@ -156,6 +156,43 @@ __global__ void fr_vec_dev_kernel(const uint4* __restrict__ a, const uint4* __re
     }
 }
 
+// ---- the vanishing argument's random polynomial (halo2_proofs/src/plonk/vanishing/prover.rs:48-63) ----------
+// coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]).  The reference draws a_i, u_i, b_i, v_i from
+// thread_rng inside a rayon loop; here they come from a counter-based generator keyed by one 64-bit seed that the
+// caller's RNG supplies, so the polynomial is reproducible and never exists on the host:
+//   word(j) = mix(seed ^ mix(j)), mix = splitmix64's output function applied to j + golden;
+//   a_i = words 10i .. 10i+3 (top limb masked to 61 bits, taken as Montgomery limbs), u_i = word 10i+4,
+//   b_i = words 10i+5 .. 10i+8 (same), v_i = word 10i+9.
+__device__ __forceinline__ unsigned long long vanish_mix(unsigned long long x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__device__ __forceinline__ Fr vanish_fr(unsigned long long seed, unsigned long long j) {
+    Fr r;
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        unsigned long long w = vanish_mix(seed ^ vanish_mix(j + l));
+        if (l == 3) w &= (1ull << 61) - 1;
+        r.v[2 * l] = (uint32_t)w;
+        r.v[2 * l + 1] = (uint32_t)(w >> 32);
+    }
+    return r;
+}
+__global__ void vanishing_random_poly_kernel(uint4* __restrict__ out, const uint4* __restrict__ random, unsigned k,
+                                             unsigned long long n, unsigned long long seed) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        const Fr a = vanish_fr(seed, 10ull * i), b = vanish_fr(seed, 10ull * i + 5);
+        const unsigned long long u = vanish_mix(seed ^ vanish_mix(10ull * i + 4));
+        const unsigned long long v = vanish_mix(seed ^ vanish_mix(10ull * i + 9));
+        const Fr ra = fp_load<FrParams>(random + 2ull * (u % k)), rb = fp_load<FrParams>(random + 2ull * (v % k));
+        fp_store<FrParams>(out + 2ull * i, fp_mul<FrParams>(fp_add<FrParams>(a, ra), fp_add<FrParams>(b, rb)));
+    }
+}
+
 }  // namespace b2
 
 namespace b2 {

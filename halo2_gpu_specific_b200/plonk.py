@@ -314,6 +314,31 @@ class OsRng:
 #   random_poly, evaluate_h_blocks                       vanishing argument
 #   eval_polynomial, poly_combine, sub_constant, kate_division_padded   evaluation phase and multiopen
 #   key_blocks, release
+def _mix64(x: np.ndarray) -> np.ndarray:
+    """splitmix64's output function of x + golden (uint64 arithmetic wraps)"""
+    x = x + np.uint64(0x9E3779B97F4A7C15)
+    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return x ^ (x >> np.uint64(31))
+
+
+def vanishing_streams(seed: int, n: int):
+    """The four per-coefficient streams of the vanishing argument's random polynomial, from one 64-bit seed:
+    word(j) = mix(seed ^ mix(j)); a_i = words 10i..10i+3 (top limb masked to 61 bits, taken as Montgomery limbs),
+    u_i = word 10i+4, b_i = words 10i+5..10i+8, v_i = word 10i+9.  Same generator as csrc/scan.cuh
+    (vanishing_random_poly_kernel), which the resident engine runs instead."""
+    with np.errstate(over="ignore"):
+        sd = np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
+        j = (np.arange(n, dtype=np.uint64) * np.uint64(10))[:, None] + np.arange(10, dtype=np.uint64)[None, :]
+        w = _mix64(sd ^ _mix64(j))
+    mask = np.uint64((1 << 61) - 1)
+    a = np.ascontiguousarray(w[:, 0:4])
+    b = np.ascontiguousarray(w[:, 5:9])
+    a[:, 3] &= mask
+    b[:, 3] &= mask
+    return a, np.ascontiguousarray(w[:, 4]), b, np.ascontiguousarray(w[:, 9])
+
+
 def _mont_vec(vals: Sequence[int]) -> np.ndarray:
     return np.stack([_fr.to_mont(int(v)) for v in vals]) if len(vals) else np.zeros((0, 4), np.uint64)
 
@@ -366,7 +391,8 @@ class ArrayBlocks:
         z = self.shuffle_commit_product(cs, group, advice, pk.fixed_values, instance, theta, beta)
         out_col[:len(z)] = z
 
-    def random_poly(self, random, a, u, b, v) -> np.ndarray:
+    def random_poly(self, random: np.ndarray, seed: int) -> np.ndarray:
+        a, u, b, v = vanishing_streams(seed, self.domain.n)
         kk = np.uint64(random.shape[0])
         p = self.fr_vec("mul", self.fr_vec("add", a, random[(u % kk).astype(np.int64)]),
                         self.fr_vec("add", b, random[(v % kk).astype(np.int64)]))
@@ -706,15 +732,15 @@ class ResidentEngine:
                                    beta, out_col.ptr)
 
     # -- vanishing argument
-    def random_poly(self, random, a, u, b, v) -> DevBlock:
-        n = self.domain.n
-        kk = np.uint64(random.shape[0])
-        blk = self.put(np.stack([a, random[(u % kk).astype(np.int64)], b, random[(v % kk).astype(np.int64)]]))
-        p = [blk.ptr + i * n * 32 for i in range(4)]
-        self._fr_vec(1, p[0], p[1], n, p[0])
-        self._fr_vec(1, p[2], p[3], n, p[2])
-        self._fr_vec(0, p[0], p[2], n, p[0])
-        return DevBlock(blk.ptr, 1, n)
+    def random_poly(self, random: np.ndarray, seed: int) -> DevBlock:
+        """generated where it is used (b2_vanishing_random_poly_dev): the polynomial never exists on the host"""
+        import ctypes
+        from ._lib import check, lib, ptr
+        out = self.alloc(1)
+        random = np.ascontiguousarray(random, dtype=np.uint64).reshape(-1, 4)
+        check(lib().b2_vanishing_random_poly_dev(seed & 0xFFFFFFFFFFFFFFFF, ptr(random), random.shape[0], self.domain.n,
+                                                 ctypes.c_void_p(out.ptr), None))
+        return out
 
     def key_blocks(self, pk) -> dict:
         """the proving key's columns, resident (made so on first use)"""
@@ -984,8 +1010,9 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
       1. u16_vec(num_advice * (bf + 1)): advice column i takes [i*(bf+1), (i+1)*(bf+1)) for its last bf+1 rows
       2. per lookup: u16_vec(bf + 1), the last rows of m
       3. per permutation set: fr_vec(bf);  4. per lookup, per z: fr_vec(bf);  5. per shuffle group: fr_vec(bf)
-      6. vanishing random polynomial: fr_vec(k), fr_vec(n), u64_vec(n), fr_vec(n), u64_vec(n)
-         (coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]), vanishing/prover.rs:48-63)
+      6. vanishing random polynomial: fr_vec(k) for `random`, u64_vec(1) for the seed of the per-coefficient
+         streams a, u, b, v (vanishing_streams): coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]),
+         vanishing/prover.rs:48-63 -- the reference draws those four per coefficient from thread_rng
     """
     import time
     vk = pk.vk
@@ -1104,9 +1131,7 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
 
     # ---- vanishing commit, y (:635-639, vanishing/prover.rs:41-70)
     random = rng.fr_vec(k)
-    a, u = rng.fr_vec(n), rng.u64_vec(n)
-    b, v = rng.fr_vec(n), rng.u64_vec(n)
-    random_block = E.random_poly(random, a, u, b, v)
+    random_block = E.random_poly(random, int(rng.u64_vec(1)[0]))
     random_poly = E.cols(random_block)[0]
     tr.write_point(E.commit(random_block)[0])
     y = tr.squeeze_challenge()

@@ -361,17 +361,38 @@ class _RngAdapter:
 # --------------------------------------------------------------------------
 # create_proof
 # --------------------------------------------------------------------------
+_M64 = (1 << 64) - 1
+
+
+def _mix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
+    return x ^ (x >> 31)
+
+
 def vanishing_random_poly(domain, rng) -> List[int]:
-    """vanishing/prover.rs:48-63 with the caller's rng (the reference mixes `rng` with thread_rng):
-    random = k field elements; coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]), the four streams
-    drawn as a = fr_vec(n), u = u64_vec(n), b = fr_vec(n), v = u64_vec(n)."""
+    """vanishing/prover.rs:48-63 with the caller's rng: random = k field elements (fr_vec(k));
+    coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]).  The reference draws a_i, u_i, b_i, v_i from
+    thread_rng per coefficient; here they are words of a counter-based generator keyed by one u64 from the rng:
+    word(j) = mix(seed ^ mix(j)), a_i = words 10i..10i+3 as little-endian limbs of a Montgomery representation
+    (top limb masked to 61 bits), u_i = word 10i+4, b_i = words 10i+5..10i+8, v_i = word 10i+9."""
     k, n = domain.k, domain.n
     random = o.fr_decode(rng.fr_vec(k))
-    a = o.fr_decode(rng.fr_vec(n))
-    u = [int(x) for x in rng.u64_vec(n)]
-    b = o.fr_decode(rng.fr_vec(n))
-    v = [int(x) for x in rng.u64_vec(n)]
-    return [(a[i] + random[u[i] % k]) * (b[i] + random[v[i] % k]) % R for i in range(n)]
+    seed = int(rng.u64_vec(1)[0])
+    word = lambda j: _mix64(seed ^ _mix64(j))                                  # noqa: E731
+    rinv = pow(1 << 256, -1, R)
+
+    def fr(j):
+        limbs = [word(j + l) for l in range(4)]
+        limbs[3] &= (1 << 61) - 1
+        return sum(v << (64 * l) for l, v in enumerate(limbs)) * rinv % R
+
+    out = []
+    for i in range(n):
+        a, u, b, v = fr(10 * i), word(10 * i + 4), fr(10 * i + 5), word(10 * i + 9)
+        out.append((a + random[u % k]) * (b + random[v % k]) % R)
+    return out
 
 
 def scalar_bits(v: int) -> int:
@@ -423,7 +444,7 @@ def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]]
       3. per permutation set: fr_vec(bf)                                                                (permutation/prover.rs:156-158)
       4. per lookup, per z: fr_vec(bf)                                                                  (plonk/prover.rs:445-449)
       5. per shuffle group: fr_vec(bf)                                                                  (plonk/prover.rs:518-521)
-      6. vanishing_random_poly                                                                          (vanishing/prover.rs:48-63)
+      6. vanishing_random_poly: fr_vec(k), u64_vec(1)                                                   (vanishing/prover.rs:48-63)
     """
     vk = pk.vk
     cs, domain = vk.cs, vk.domain

@@ -52,7 +52,7 @@ def test_proof_verifies_with_pairing(setup):
     bad[40] ^= 1
     try:
         assert not PR.verify_proof(params, pk.vk, inst, bytes(bad), pairing=True)
-    except PR.TranscriptError:
+    except (PR.TranscriptError, PR.VerifyError):
         pass
 
 
@@ -64,7 +64,7 @@ def test_every_proof_element_is_bound(setup):
         bad[32 * el + 3] ^= 0x10
         try:
             ok = PR.verify_proof(params, pk.vk, inst, bytes(bad))
-        except PR.TranscriptError:
+        except (PR.TranscriptError, PR.VerifyError):
             continue                      # not a curve point / not canonical: rejected while reading
         assert not ok, f"element {el} is not bound by the verifier"
 
