@@ -44,7 +44,7 @@ class NttDesc(ctypes.Structure):
 # every symbol include/b2pcs.h declares (checked by tests/test_abi.py without a GPU)
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_get_device", "b2_synchronize",
-    "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_from_scalars_dev", "b2_memcpy_d2d", "b2_vanishing_random_poly_dev", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
+    "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_from_scalars_dev", "b2_memcpy_d2d", "b2_vanishing_random_poly_dev", "b2_fr_max_bits_dev", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
@@ -74,6 +74,7 @@ def lib() -> ctypes.CDLL:
         L.b2_srs_from_scalars_dev.argtypes = [vp, sz, ctypes.POINTER(u64)]
         L.b2_memcpy_d2d.argtypes = [vp, vp, sz]
         L.b2_vanishing_random_poly_dev.argtypes = [u64, vp, u32, sz, vp, vp]
+        L.b2_fr_max_bits_dev.argtypes = [vp, sz, ctypes.POINTER(u32)]
         L.b2_srs_precompute.argtypes = [u64, u32]
         L.b2_g1_normalize.argtypes = [vp, sz]
         L.b2_srs_len.argtypes = [u64, ctypes.POINTER(sz)]

@@ -333,4 +333,22 @@ int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, 
     return B2_OK;
 }
 
+int b2_fr_max_bits_dev(const void* d_a, size_t n, uint32_t* bits) {
+    if (!bits || (n && !d_a)) return fail(B2_ERR_ARG, "fr_max_bits: bad arguments");
+    *bits = 0;
+    if (n == 0) return B2_OK;
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = ctx->stream;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    CK(cudaMemsetAsync(ctx->out96.p, 0, 4, st));
+    LAUNCH(*ctx, fr_max_bits_kernel, (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sms * 16), 256, 0, st,
+           (const uint4*)d_a, (unsigned long long)n, (unsigned*)ctx->out96.p);
+    CK(cudaMemcpyAsync(bits, ctx->out96.p, 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return B2_OK;
+}
+
 }  // extern "C"

@@ -156,6 +156,25 @@ __global__ void fr_vec_dev_kernel(const uint4* __restrict__ a, const uint4* __re
     }
 }
 
+// ---- largest scalar of a column, in bits (find_max_scalar_bits, halo2_proofs/src/plonk/prover.rs:945-962) ------
+// The reference folds the column with `max` and takes the bit length of the winner's canonical form: the bound it
+// hands to commit_lagrange_with_bound.  Here: de-Montgomery, bit length, warp max, one atomicMax per warp.
+__global__ void fr_max_bits_kernel(const uint4* __restrict__ a, unsigned long long n, unsigned* __restrict__ out) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned best = 0;
+    for (; i < n; i += stride) {
+        const Fr x = fp_from_mont<FrParams>(fp_load<FrParams>(a + 2ull * i));
+        unsigned bits = 0;
+#pragma unroll
+        for (int l = 7; l >= 0; l--)
+            if (bits == 0 && x.v[l]) bits = 32u * l + (32u - (unsigned)__clz(x.v[l]));
+        best = max(best, bits);
+    }
+    best = __reduce_max_sync(0xffffffffu, best);
+    if ((threadIdx.x & 31u) == 0 && best) atomicMax(out, best);
+}
+
 // ---- the vanishing argument's random polynomial (halo2_proofs/src/plonk/vanishing/prover.rs:48-63) ----------
 // coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]).  The reference draws a_i, u_i, b_i, v_i from
 // thread_rng inside a rayon loop; here they come from a counter-based generator keyed by one 64-bit seed that the

@@ -339,6 +339,21 @@ def vanishing_streams(seed: int, n: int):
     return a, np.ascontiguousarray(w[:, 4]), b, np.ascontiguousarray(w[:, 9])
 
 
+def canonical_max_bits(canonical: np.ndarray) -> int:
+    """bit length of the largest value among canonical (n, 4) little-endian limbs"""
+    c = np.asarray(canonical, dtype=np.uint64).reshape(-1, 4)
+    for limb in (3, 2, 1, 0):
+        top = int(c[:, limb].max()) if c.shape[0] else 0
+        if top:
+            return 64 * limb + top.bit_length()
+    return 0
+
+
+def _max_bits(counts: np.ndarray) -> int:
+    """expression_max_bits, logup/prover.rs:493-517"""
+    return max(16, int(counts.max()).bit_length() if counts.size else 0)
+
+
 def _mont_vec(vals: Sequence[int]) -> np.ndarray:
     return np.stack([_fr.to_mont(int(v)) for v in vals]) if len(vals) else np.zeros((0, 4), np.uint64)
 
@@ -367,8 +382,29 @@ class ArrayBlocks:
     def write_rows(col: np.ndarray, row: int, values: np.ndarray) -> None:
         col[row:row + len(values)] = values
 
-    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: int):
-        return host, self.commit_lagrange(host, max_bits)
+    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: Optional[int]):
+        if max_bits is not None:
+            return host, self.commit_lagrange(host, max_bits)
+        points = []                                   # find_max_scalar_bits per column, plonk/prover.rs:945-962, 296
+        for i in range(host.shape[0]):
+            points += self.commit_lagrange(host[i:i + 1], canonical_max_bits(self.from_mont(host[i])))
+        return host, points
+
+    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds):
+        """logup `compress` (logup/prover.rs:70-256) for every lookup: compressed inputs and table on the engine,
+        the multiplicities counted on the host as the reference does -> (block of m columns, bound for their commit)"""
+        n = self.domain.n
+        usable = n - (cs.blinding_factors() + 1)
+        m_canon = np.zeros((len(cs.lookups), n, 4), dtype=np.uint64)
+        m_bits = 16
+        for li, lk in enumerate(cs.lookups):
+            lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
+            comp = self.compress_canonical(lists, advice, pk.fixed_values, instance, theta)
+            counts = logup_multiplicity(list(comp[:-1]), comp[-1], usable, n)
+            m_bits = max(m_bits, _max_bits(counts[:usable]))
+            m_canon[li, :, 0] = counts.astype(np.uint64)
+            m_canon[li, usable:, 0] = blinds[li]
+        return self.put_canonical(m_canon), m_bits
 
     def compress_canonical(self, expression_lists, advice, fixed, instance, theta: int) -> np.ndarray:
         comp = self.compress(expression_lists, advice, fixed, instance, theta)
@@ -648,12 +684,23 @@ class ResidentEngine:
                                                  ptr(d.omega_inv), ptr(d.ifft_divisor), d.k, ptr(out)))
         return _points(out)
 
-    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: int):
+    def put_and_commit_lagrange(self, host: np.ndarray, max_bits: Optional[int]):
         """host columns -> resident block, committed on the way in (copy of column i + 1 overlaps the MSM of column i)"""
         if not (host.flags.c_contiguous and host.dtype == np.uint64 and host.ndim == 3):
             raise B2Error(B2_ERR_ARG, "expected a C-contiguous uint64 (columns, n, 4) array")
-        block = self.alloc(host.shape[0])
-        return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, max_bits, False)
+        if max_bits is not None:
+            block = self.alloc(host.shape[0])
+            return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, max_bits, False)
+        # no bound given: find_max_scalar_bits per column on the device (plonk/prover.rs:945-962, 296)
+        import ctypes
+        from ._lib import check, lib
+        block = self.put(host)
+        points = []
+        for col in self.cols(block):
+            bits = ctypes.c_uint32()
+            check(lib().b2_fr_max_bits_dev(ctypes.c_void_p(col.ptr), col.n, ctypes.byref(bits)))
+            points += self._commit(self.params.g_lagrange, 0, col, bits.value, False)
+        return block, points
 
     def commit_lagrange(self, block: DevBlock, max_bits: int = _fr.NUM_BITS) -> List[Point]:
         return self._commit(self.params.g_lagrange, 0, block, max_bits, False)
@@ -704,6 +751,33 @@ class ResidentEngine:
         for i in range(out.count):                                            # Montgomery -> canonical
             self._fr_vec(0, out.ptr + i * n * 32, one, n, out.ptr + i * n * 32)
         return self.get(out)
+
+    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds):
+        """logup `compress` (logup/prover.rs:70-256) for every lookup without leaving the device: the compressed
+        inputs and table are produced by the expression kernel, sorted and matched there (logup_multiplicity_device),
+        and m(X) is written as a resident column; only the largest count (for the commit bound) returns."""
+        from .grand_product import compress_expressions_dev
+        n = self.domain.n
+        bf = cs.blinding_factors()
+        usable = n - (bf + 1)
+        n_lookups = len(cs.lookups)
+        ms = self.alloc(n_lookups)
+        m_bits = 16
+        one = self._const_column("raw_one", _RAW_ONE)
+        r2 = self._const_column("raw_r2", _RAW_R2)
+        cols = self._columns(pk, advice, instance)
+        for li, lk in enumerate(cs.lookups):
+            lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
+            comp = self.alloc(len(lists))
+            compress_expressions_dev(self.domain, lists, cols, theta, comp.ptr)
+            for i in range(comp.count):                                        # Montgomery -> canonical
+                self._fr_vec(0, comp.ptr + i * n * 32, one, n, comp.ptr + i * n * 32)
+            m_col = ms.col(li)
+            largest = logup_multiplicity_device(comp.ptr, len(lists) - 1, usable, n, m_col.ptr)
+            m_bits = max(m_bits, largest.bit_length())
+            self._fr_vec(0, m_col.ptr, r2, n, m_col.ptr)                       # counts (canonical) -> Montgomery
+            self.write_rows(m_col, usable, _mont_vec(blinds[li]))              # logup/prover.rs:232-236
+        return ms, m_bits
 
     def put_canonical(self, canonical: np.ndarray) -> DevBlock:
         n = self.domain.n
@@ -987,23 +1061,93 @@ def logup_multiplicity(inputs_canonical: Sequence[np.ndarray], table_canonical: 
     return m
 
 
+class _DevArray:
+    """raw device memory as a CUDA-array-interface object (so torch can view it without a copy)"""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<i8"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def logup_multiplicity_device(comp_ptr: int, n_inputs: int, usable: int, n: int, m_ptr: int) -> int:
+    """logup_multiplicity on resident data.  comp_ptr: (n_inputs + 1) columns of n canonical field elements (the
+    compressed inputs, then the compressed table); m_ptr: receives n canonical elements, the counts in rows
+    < usable and zeros above.  Returns the largest count."""
+    import torch
+    from ._lib import check, lib
+    check(lib().b2_synchronize())
+    dev = torch.device("cuda", torch.cuda.current_device())
+    raw = torch.as_tensor(_DevArray(comp_ptr, (n_inputs + 1, n, 4)), device=dev)
+    m = torch.as_tensor(_DevArray(m_ptr, (n, 4)), device=dev)
+    largest = multiplicity_tensors(raw, usable, m)
+    torch.cuda.synchronize(dev)
+    return largest
+
+
+def multiplicity_tensors(raw, usable: int, m) -> int:
+    """The sort / match step of logup/prover.rs:115-184 on int64 tensors holding canonical little-endian limbs
+    (any torch device): raw (n_inputs + 1, n, 4), inputs first, table last; m (n, 4) is overwritten with the counts.
+    Sorting 256-bit keys is plumbing, done with torch: one stable sort per limb over table and inputs together (the
+    table first, so inside a run of equal keys its rows keep their order -- the stable sort of :115-117), then per
+    distinct key the probe sequence of binary_search_by_key (mid = left + size / 2, first Equal probe wins) on the
+    table's run decides which row takes the count.  Returns the largest count."""
+    import torch
+    dev = raw.device
+    n_inputs = raw.shape[0] - 1
+    flip = torch.tensor(-(1 << 63), dtype=torch.int64, device=dev)          # unsigned order on signed int64
+    keys = torch.cat([raw[n_inputs, :usable]] + [raw[i, :usable] for i in range(n_inputs)], dim=0) ^ flip
+    total = keys.shape[0]
+    order = torch.arange(total, device=dev)
+    limbs = [l for l in range(4) if l == 0 or bool((keys[:, l] != flip).any())]    # skip limbs that are zero everywhere
+    for l in limbs:                                                           # least significant limb first
+        order = order[torch.sort(keys[order, l], stable=True).indices]
+    ks = keys[order]
+    new_run = torch.ones(total, dtype=torch.bool, device=dev)
+    new_run[1:] = (ks[1:] != ks[:-1]).any(dim=1)
+    gid = torch.cumsum(new_run.to(torch.int64), 0) - 1                        # run id per sorted position
+    n_groups = int(gid[-1].item()) + 1
+    is_table = order < usable
+    t_count = torch.zeros(n_groups, dtype=torch.int64, device=dev).scatter_add_(0, gid, is_table.to(torch.int64))
+    i_count = torch.zeros(n_groups, dtype=torch.int64, device=dev).scatter_add_(0, gid, (~is_table).to(torch.int64))
+    if bool(((i_count > 0) & (t_count == 0)).any()):
+        raise B2Error(B2_ERR_ARG, "logup binary_search_by_key should hit")
+    table_rows = order[is_table]                                              # table rows in sorted order
+    lo = torch.cumsum(t_count, 0) - t_count                                   # each run's start in that order
+    hi = lo + t_count
+    live = i_count > 0
+    found = torch.full((n_groups,), -1, dtype=torch.int64, device=dev)
+    left = torch.zeros(n_groups, dtype=torch.int64, device=dev)
+    right = torch.full((n_groups,), usable, dtype=torch.int64, device=dev)
+    size = right - left
+    while bool((live & (found < 0)).any()):                                   # <= log2(usable) + 1 rounds
+        todo = live & (found < 0)
+        mid = left + torch.div(size, 2, rounding_mode="floor")
+        less = todo & (mid < lo)
+        greater = todo & (mid >= hi)
+        hit = todo & ~less & ~greater
+        found = torch.where(hit, mid, found)
+        left = torch.where(less, mid + 1, left)
+        right = torch.where(greater, mid, right)
+        size = right - left
+    m.zero_()
+    sel = live.nonzero(as_tuple=True)[0]
+    m[:, 0].scatter_add_(0, table_rows[found[sel]], i_count[sel])
+    return int(i_count.max().item())
+
+
 # --------------------------------------------------------------------------
 # create_proof
 # --------------------------------------------------------------------------
-def _max_bits(counts: np.ndarray) -> int:
-    """expression_max_bits, logup/prover.rs:493-517"""
-    return max(16, int(counts.max()).bit_length() if counts.size else 0)
-
-
 def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence[Sequence[int]], rng,
-                 sign_bit: int = 7, engine=None, advice_max_bits: int = _fr.NUM_BITS,
+                 sign_bit: int = 7, engine=None, advice_max_bits: Optional[int] = None,
                  timings: Optional[dict] = None) -> bytes:
     """plonk::create_proof (GWC multiopen) for one circuit instance, advice given (create_proof_from_witness).
 
     advice: (num_advice, n, 4) Lagrange columns in host memory (pinned memory makes the one upload faster); the
     blinding rows are written into it.  instances: per instance column the public values (canonical ints), zero
-    padded internally.  advice_max_bits: the bound handed to commit_lagrange_with_bound (the reference scans each
-    column for its largest scalar, plonk/prover.rs:945-962, 296; a caller that knows its witness range passes it).
+    padded internally.  advice_max_bits: the bound handed to commit_lagrange_with_bound; None = the engine scans each
+    column for its largest scalar as the reference does (plonk/prover.rs:945-962, 296); a caller that knows its
+    witness range passes it and gets the upload pipelined with the commitments.
     engine: ResidentEngine(params, domain) by default; pass one to keep the proving key resident across proofs.
 
     Random values come from `rng` in this order (vector draws):
@@ -1077,16 +1221,8 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
 
     # ---- lookups: compress, multiplicities, m commitments (:334-366, logup/prover.rs:70-256)
     n_lookups = len(cs.lookups)
-    m_canon = np.zeros((n_lookups, n, 4), dtype=np.uint64)
-    m_bits = 16
-    for li, lk in enumerate(cs.lookups):
-        lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
-        comp = E.compress_canonical(lists, adv, fixed_values, instance_values, theta)
-        counts = logup_multiplicity(list(comp[:-1]), comp[-1], usable, n)
-        m_bits = max(m_bits, _max_bits(counts[:usable]))
-        m_canon[li, :, 0] = counts.astype(np.uint64)
-        m_canon[li, usable:, 0] = rng.u16_vec(bf + 1)
-    ms = E.put_canonical(m_canon)
+    ms, m_bits = E.multiplicity_block(cs, pk, adv, instance_values, theta,
+                                      [rng.u16_vec(bf + 1) for _ in range(n_lookups)])
     if n_lookups:
         for c in E.commit_lagrange(ms, m_bits):
             tr.write_point(c)

@@ -289,6 +289,9 @@ int b2_prefix_scan_dev(int op, const void* d_in, size_t n_in, const void* init, 
                        size_t n_out, void* stream);
 /* d_out[i] = d_a[i] op d_b[i] over Fr on device pointers; op: 0 mul, 1 add, 2 sub.  d_out may alias an input. */
 int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
+/* Bit length of the largest canonical value among n resident Montgomery-form scalars: find_max_scalar_bits
+ * (plonk/prover.rs:945-962), the bound the reference passes to commit_lagrange_with_bound for every advice column. */
+int b2_fr_max_bits_dev(const void* d_a, size_t n, uint32_t* bits);
 /* The vanishing argument's random polynomial (plonk/vanishing/prover.rs:48-63): d_out[i] = (a_i + random[u_i % k]) *
  * (b_i + random[v_i % k]) for i < n, with a_i, u_i, b_i, v_i from a counter-based generator keyed by `seed` (the
  * reference draws them from thread_rng; csrc/scan.cuh states the generator, oracle/prover.py restates it).  random:

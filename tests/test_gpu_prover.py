@@ -157,3 +157,86 @@ def test_benches_plonk_circuit_proof_verifies(gpu, k, pairing, engine_kind):
               + ", ".join(f"{a} {b:.4f}" for a, b in timings.items()))
     finally:
         params.free()
+
+
+def _zk_shape(k, extra_gates, to_mont):
+    import zkwasm_shape_circuit as zk
+    args = zk.constraint_system_args(extra_gates=extra_gates)
+    cs = HP.ConstraintSystem(**args)
+    ocs = P.ConstraintSystem(args["num_fixed"], args["num_advice"], args["num_instance"], degree=5, blinding_factors=5)
+    ocs.gates, ocs.lookups, ocs.shuffles = cs.gates, cs.lookups, cs.shuffles
+    ocs.permutation_columns = cs.permutation_columns
+    fixed, advice, public, mapping = zk.build(k, to_mont, seed=k)
+    return cs, ocs, fixed, advice, public, mapping
+
+
+@pytest.mark.parametrize("k", [7, 14])
+def test_zkwasm_shaped_circuit(gpu, k):
+    """BASELINE config 5's shape with a real witness: 64 advice, 32 fixed, 8 lookups (12 input sets, multiplicities
+    counted on the device), 4 shuffles, 24 permutation columns in 8 sets.  k = 7: bytes == oracle prover;
+    k = 14: accepted by the oracle verifier, rejected with a wrong public input or a broken witness."""
+    from oracle import cref
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, 16, lambda a: cref.to_mont(0, a))
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        eng = HP.ResidentEngine(params, pk.vk.domain)
+        timings = {}
+        HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(1), engine=eng)
+        proof = HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(k), engine=eng, timings=timings)
+        ovk = PR.VerifyingKey(ocs, o.EvaluationDomain(5, k), pk.vk.fixed_commitments, pk.vk.permutation_commitments,
+                              pk.vk.transcript_repr)
+        vparams = PR.ParamsVerifier(k, S_TOXIC)
+        assert PR.verify_proof(vparams, ovk, [public], proof, pairing=(k == 7))
+        assert not PR.verify_proof(vparams, ovk, [[public[0] + 1] + public[1:]], proof)
+        # the host-API engine (numpy multiplicities, batch bound scan on the host) gives the same bytes
+        assert HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(k),
+                               engine=HP.Engine(params, pk.vk.domain)) == proof
+        if k == 7:
+            oparams = PR.Params(k, S_TOXIC)
+            opk = PR.keygen(oparams, ocs, [dec(c) for c in fixed], [[(int(c), int(r)) for c, r in col] for col in mapping],
+                            transcript_repr=pk.vk.transcript_repr)
+            assert PR.create_proof(oparams, opk, [dec(c) for c in advice], [public], HP.SeededRng(k)) == proof
+        bad = advice.copy()
+        bad[50, 9] = enc([1])[0]                              # a lookup input outside the table
+        with pytest.raises(HP.B2Error):
+            HP.create_proof(params, pk, bad, [public], HP.SeededRng(k), engine=eng)
+        bad = advice.copy()
+        bad[2, 9] = enc([12345])[0]                           # a product cell
+        assert not PR.verify_proof(vparams, ovk, [public], HP.create_proof(params, pk, bad, [public], HP.SeededRng(k),
+                                                                           engine=eng))
+        eng.free()
+        print(f"zkwasm shape k={k} create_proof {sum(timings.values()):.4f} s: "
+              + ", ".join(f"{a} {b:.4f}" for a, b in timings.items()))
+    finally:
+        params.free()
+
+
+def test_max_bits_and_device_multiplicity_primitives(gpu):
+    """b2_fr_max_bits_dev (find_max_scalar_bits) and the torch sort / match step on device memory"""
+    import ctypes
+    import random
+    from halo2_gpu_specific_b200.evaluation import DeviceBuffer
+    rng = random.Random(4)
+    n = 1 << 12
+    for bits in (0, 1, 16, 33, 64, 65, 200, 254):
+        vals = [rng.randrange(1 << bits) if bits else 0 for _ in range(n)]
+        if bits:
+            vals[rng.randrange(n)] = (1 << bits) - 1 if bits < 254 else R - 1
+        buf = DeviceBuffer(n).upload(enc(vals))
+        got = ctypes.c_uint32()
+        gpu.check(gpu.lib().b2_fr_max_bits_dev(ctypes.c_void_p(buf.ptr), n, ctypes.byref(got)))
+        assert got.value == max(v.bit_length() for v in vals)
+        buf.free()
+    usable = n - 6
+    pool = [rng.randrange(R) for _ in range(40)] + [0, 1, 2]
+    table = [rng.choice(pool) for _ in range(n)]
+    inputs = [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(3)]
+    want = PR.logup_multiplicity([inputs], table, usable, n)
+    canon = np.array([[o._to_limbs(v) for v in col] for col in inputs + [table]], dtype=np.uint64)
+    comp = DeviceBuffer(4 * n).upload(canon)
+    m = DeviceBuffer(n)
+    largest = HP.logup_multiplicity_device(comp.ptr, 3, usable, n, m.ptr)
+    got_m = m.download()
+    assert got_m[:, 0].tolist() == want and not got_m[:, 1:].any() and largest == max(want)
+    comp.free(); m.free()

@@ -229,3 +229,60 @@ def test_device_engine_refuses_to_run_without_a_gpu():
     adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
     with pytest.raises(HP.B2Error):
         HP.create_proof(HostParams(5), pk, adv, [fx["instance"][0][:4]], HP.SeededRng(1))
+
+
+def test_torch_multiplicity_matches_scalar_restatement():
+    """the resident engine's sort / match step (multiplicity_tensors), run here on CPU tensors, against the scalar
+    restatement: wide keys (all four limbs), narrow keys (one limb), long runs of repeated table values"""
+    import torch
+    rng = random.Random(6)
+    for trial in range(24):
+        n = 128
+        usable = n - 6
+        wide = trial % 2 == 0
+        pool = [rng.randrange(R) if wide else rng.randrange(1 << 40) for _ in range(rng.randrange(1, 20))] + [0, 1]
+        table = [rng.choice(pool) for _ in range(n)]
+        inputs = [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(1 + trial % 3)]
+        want = PR.logup_multiplicity([inputs], table, usable, n)
+        canon = lambda col: [o._to_limbs(v) for v in col]                                   # noqa: E731
+        raw = torch.tensor(np.array([canon(c) for c in inputs] + [canon(table)], dtype=np.uint64).view(np.int64))
+        m = torch.full((n, 4), 7, dtype=torch.int64)
+        largest = HP.multiplicity_tensors(raw, usable, m)
+        assert m[:, 0].tolist() == want and not m[:, 1:].any()
+        assert largest == max(want)
+    raw = torch.tensor(np.array([canon([2] * n), canon([3] * n)], dtype=np.uint64).view(np.int64))
+    with pytest.raises(HP.B2Error):
+        HP.multiplicity_tensors(raw, usable, torch.zeros((n, 4), dtype=torch.int64))
+
+
+def _zk_shape(k, extra_gates):
+    import zkwasm_shape_circuit as zk
+    from oracle import cref
+    args = zk.constraint_system_args(extra_gates=extra_gates)
+    cs = HP.ConstraintSystem(**args)
+    ocs = P.ConstraintSystem(args["num_fixed"], args["num_advice"], args["num_instance"], degree=5, blinding_factors=5)
+    ocs.gates, ocs.lookups, ocs.shuffles = cs.gates, cs.lookups, cs.shuffles
+    ocs.permutation_columns = cs.permutation_columns
+    fixed, advice, public, mapping = zk.build(k, lambda a: cref.to_mont(0, a), seed=k)
+    return cs, ocs, fixed, advice, public, mapping
+
+
+def test_zkwasm_shaped_circuit_proves_and_verifies():
+    """BASELINE config 5's shape (64 advice, 32 fixed, 8 lookups / 12 input sets, 4 shuffles, 24 permutation columns)
+    with a real witness at k = 6: host logic over the oracle-backed engine == oracle prover, and the verifier accepts"""
+    k = 6
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, extra_gates=8)
+    oparams = PR.Params(k, S_TOXIC)
+    omap = [[(int(c), int(r)) for c, r in col] for col in mapping]
+    opk = PR.keygen(oparams, ocs, [dec(c) for c in fixed], omap)
+    eng = OracleEngine(oparams, opk.vk.domain, ocs)
+    pk = HP.keygen(HostParams(k), cs, fixed, mapping, engine=eng, transcript_repr=opk.vk.transcript_repr)
+    want = PR.create_proof(oparams, opk, [dec(c) for c in advice], [public], HP.SeededRng(3))
+    got = HP.create_proof(HostParams(k), pk, advice.copy(), [public], HP.SeededRng(3), engine=eng)
+    assert got == want
+    assert PR.verify_proof(oparams, opk.vk, [public], got)
+    assert not PR.verify_proof(oparams, opk.vk, [[public[0] + 1] + public[1:]], got)
+    bad = advice.copy()
+    bad[2, 9] = enc([12345])[0]                       # a product cell
+    assert not PR.verify_proof(oparams, opk.vk, [public],
+                               HP.create_proof(HostParams(k), pk, bad, [public], HP.SeededRng(3), engine=eng))
