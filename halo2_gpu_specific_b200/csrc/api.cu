@@ -1048,7 +1048,10 @@ int b2_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes) {
     DeviceCtx* dev;
     int rc = dev_get(&dev);
     if (rc) return rc;
+    // a device-to-device cudaMemcpy returns before the copy has run, and the lanes' streams do not wait for the
+    // legacy stream: wait here, so that whatever the caller launches next sees the data
     CK(cudaMemcpy(dst_dev, src_dev, bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     return B2_OK;
 }
 int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits) {
@@ -1662,7 +1665,10 @@ int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes) {
     DeviceCtx* dev;
     int rc = dev_get(&dev);
     if (rc) return rc;
+    // from pageable memory cudaMemcpy may return once the data is staged, before the DMA has landed; the lanes'
+    // streams do not wait for the legacy stream, so wait here
     CK(cudaMemcpy(dst_dev, src_host, bytes, cudaMemcpyHostToDevice));
+    CK(cudaStreamSynchronize(cudaStreamLegacy));
     return B2_OK;
 }
 int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes) {

@@ -26,8 +26,48 @@ import zkwasm_shape_circuit as zk  # noqa: E402
 S_TOXIC = 0x2B200B200B200B200B200B200B200B2001
 
 
+class TracingEngine(HP.ResidentEngine):
+    """--debug: prints a fingerprint of what every opening step produced"""
+
+    def _peek(self, col, rows=(0, 1, 2)):
+        import ctypes
+        out = np.empty((len(rows), 4), dtype=np.uint64)
+        for i, r in enumerate(rows):
+            r = r % col.n
+            _lib.check(_lib.lib().b2_memcpy_d2h(ctypes.c_void_p(out[i:].ctypes.data), ctypes.c_void_p(col.ptr + r * 32), 32))
+        return [hex(int(x[0]))[:10] for x in out]
+
+    def poly_combine(self, cols, v):
+        out = super().poly_combine(cols, v)
+        print(f"[trace] poly_combine m={len(cols)} first={self._peek(cols[0])} last={self._peek(cols[-1])} "
+              f"out={self._peek(out)} out_tail={self._peek(out, (-1, -2))}", flush=True)
+        return out
+
+    def kate_division_padded(self, col, z):
+        out = super().kate_division_padded(col, z)
+        print(f"[trace] kate in={self._peek(col)} out={self._peek(out)} out_tail={self._peek(out, (-1, -2, -3))}", flush=True)
+        return out
+
+    def eval_polynomial(self, col, point):
+        v = super().eval_polynomial(col, point)
+        if getattr(self, "trace_evals", False):
+            print(f"[trace] eval {hex(v)[:12]} of {self._peek(col)}", flush=True)
+        return v
+
+    def stack(self, cols):
+        out = super().stack(cols)
+        print(f"[trace] stack {[self._peek(c) for c in cols]} -> {[self._peek(c) for c in self.cols(out)]}", flush=True)
+        return out
+
+    def commit(self, block):
+        pts = super().commit(block)
+        print(f"[trace] commit count={block.count} -> {[None if p is None else hex(p[0])[:10] for p in pts]}", flush=True)
+        return pts
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--debug", action="store_true")
     ap.add_argument("--k", type=int, default=22)
     ap.add_argument("--reps", type=int, default=2)
     ap.add_argument("--extra-gates", type=int, default=300)
@@ -53,7 +93,7 @@ def main():
     adv = _lib.pinned_empty(advice.shape)
     adv[:] = advice
     del advice
-    eng = HP.ResidentEngine(params, pk.vk.domain)
+    eng = (TracingEngine if a.debug else HP.ResidentEngine)(params, pk.vk.domain)
     L = _lib.lib()
     runs = []
     proof = b""
