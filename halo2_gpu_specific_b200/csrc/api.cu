@@ -998,6 +998,7 @@ int b2_srs_register(const void* bases, size_t n, size_t stride_bytes, b2_handle_
     cudaError_t e;
     if (stride_bytes == 64)
         e = cudaMemcpy(d, bases, n * 64, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     else
         e = cudaMemcpy2D(d, 64, bases, stride_bytes, 64, n, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) {

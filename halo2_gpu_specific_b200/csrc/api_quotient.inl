@@ -391,6 +391,9 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
                 CK(cudaMemcpy(nd.prog, p->instr.data(), p->instr.size() * sizeof(QInstr), cudaMemcpyHostToDevice));
             if (!p->constants.empty())
                 CK(cudaMemcpy(nd.constants, p->constants.data(), p->constants.size() * 8, cudaMemcpyHostToDevice));
+            // small pageable uploads may return before their DMA has landed, and the lane streams do not wait for
+            // the legacy stream
+            CK(cudaStreamSynchronize(cudaStreamLegacy));
             static bool attr_set[MAX_DEV] = {};
             if (!attr_set[dev]) {
                 CK(cudaFuncSetAttribute(quotient_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -199,6 +199,7 @@ int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* ou
     void* d = nullptr;
     CK(cudaMalloc(&d, n * 32));
     cudaError_t e = cudaMemcpy(d, poly, n * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     int rc = e == cudaSuccess ? b2_eval_polynomial_dev(d, 1, n, n, point, out) : fail(B2_ERR_CUDA, "eval_polynomial: upload failed");
     cudaFree(d);
     return rc;
@@ -299,6 +300,7 @@ int b2_poly_combine(const void* const* polys, uint32_t m, uint64_t n, const void
             rc = fail(B2_ERR_CUDA, "poly_combine: upload of polynomial %u failed", j);
     }
     char* d_out = (char*)d + (size_t)m * n * 32;
+    if (rc == B2_OK && cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) rc = fail(B2_ERR_CUDA, "poly_combine: sync failed");
     if (rc == B2_OK) rc = b2_poly_combine_dev(ptrs.data(), m, n, v, d_out, nullptr);
     if (rc == B2_OK && cudaMemcpy(out, d_out, n * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
         rc = fail(B2_ERR_CUDA, "poly_combine: download failed");
@@ -311,6 +313,7 @@ int b2_kate_division(const void* a, uint64_t n, const void* b, void* q) {
     void* d = nullptr;
     CK(cudaMalloc(&d, (size_t)(2 * n) * 32));
     cudaError_t e = cudaMemcpy(d, a, n * 32, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cudaStreamLegacy);
     int rc = e == cudaSuccess ? b2_kate_division_dev(d, n, b, (char*)d + n * 32, nullptr) : fail(B2_ERR_CUDA, "kate_division: upload failed");
     if (rc == B2_OK && cudaMemcpy(q, (char*)d + n * 32, (n - 1) * 32, cudaMemcpyDeviceToHost) != cudaSuccess)
         rc = fail(B2_ERR_CUDA, "kate_division: download failed");
