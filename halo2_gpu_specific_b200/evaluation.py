@@ -174,13 +174,62 @@ class QuotientProgram:
         check(lib().b2_quotient_eval(ctypes.c_uint64(self.handle), ctypes.byref(a)))
 
 
+class BufferPool:
+    """Exact-size free lists of device allocations.  A proof allocates the same few dozen sizes every time (columns,
+    blocks of columns, scratch of the z-column kernels); cudaMalloc / cudaFree of 128 MiB .. 8 GiB blocks cost
+    milliseconds each and synchronise the device, so an engine that proves repeatedly keeps what it freed."""
+
+    def __init__(self):
+        self._free = {}
+        self.cached_bytes = 0
+
+    def take(self, nbytes: int):
+        lst = self._free.get(nbytes)
+        if lst:
+            self.cached_bytes -= nbytes
+            return lst.pop()
+        return None
+
+    def give(self, ptr: int, nbytes: int) -> None:
+        self._free.setdefault(nbytes, []).append(ptr)
+        self.cached_bytes += nbytes
+
+    def trim(self) -> None:
+        for lst in self._free.values():
+            for p in lst:
+                lib().b2_dev_free(ctypes.c_void_p(p))
+        self._free = {}
+        self.cached_bytes = 0
+
+
+_ACTIVE_POOL: Optional[BufferPool] = None
+
+
+def set_active_pool(pool: Optional[BufferPool]) -> Optional[BufferPool]:
+    """route DeviceBuffer allocations / frees through `pool` (None: plain b2_dev_alloc / b2_dev_free); returns the
+    previous setting"""
+    global _ACTIVE_POOL
+    prev, _ACTIVE_POOL = _ACTIVE_POOL, pool
+    return prev
+
+
 class DeviceBuffer:
-    """cudaMalloc'd array of Fr elements (b2_dev_alloc)."""
+    """cudaMalloc'd array of Fr elements (b2_dev_alloc), optionally recycled through the active BufferPool."""
 
     def __init__(self, elems: int):
-        p = ctypes.c_void_p()
-        check(lib().b2_dev_alloc(max(1, elems) * 32, ctypes.byref(p)))
-        self.ptr, self.elems = p.value, elems
+        nbytes = max(1, elems) * 32
+        pool = _ACTIVE_POOL
+        got = pool.take(nbytes) if pool is not None else None
+        if got is None:
+            p = ctypes.c_void_p()
+            rc = lib().b2_dev_alloc(nbytes, ctypes.byref(p))
+            if rc and pool is not None and pool.cached_bytes:
+                pool.trim()                     # out of memory with blocks parked in the pool: release them and retry
+                rc = lib().b2_dev_alloc(nbytes, ctypes.byref(p))
+            check(rc)
+            got = p.value
+        self.ptr, self.elems = got, elems
+        self._pool, self._nbytes = pool, nbytes
 
     def upload(self, a: np.ndarray, offset_elems: int = 0) -> "DeviceBuffer":
         a = np.ascontiguousarray(a, dtype=np.uint64)
@@ -195,7 +244,10 @@ class DeviceBuffer:
 
     def free(self):
         if self.ptr:
-            lib().b2_dev_free(ctypes.c_void_p(self.ptr))
+            if self._pool is not None:
+                self._pool.give(self.ptr, self._nbytes)
+            else:
+                lib().b2_dev_free(ctypes.c_void_p(self.ptr))
             self.ptr = 0
 
 

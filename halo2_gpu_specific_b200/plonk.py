@@ -596,10 +596,35 @@ class ResidentEngine:
     on first use and kept for later proofs (pk.fixed_cosets / permutation cosets are what the reference's CPU
     prover keeps too, plonk/keygen.rs)."""
 
-    def __init__(self, params, domain):
+    _PROFILED = ("put", "put_and_commit_lagrange", "commit_lagrange", "commit_lagrange_and_ifft", "commit",
+                 "lagrange_to_coeff", "multiplicity_block", "permutation_z", "logup_z", "shuffle_z", "random_poly",
+                 "evaluate_h_blocks", "eval_polynomial", "poly_combine", "sub_constant", "kate_division_padded", "stack",
+                 "key_blocks", "release")
+
+    def __init__(self, params, domain, profile: bool = False):
         from ._lib import require_gpu
         require_gpu()
         self.params, self.domain = params, domain
+        self.op_times: dict = {}       # profile=True: seconds and calls per engine operation
+        if profile:
+            import functools
+            import time
+
+            def timed(name, fn):
+                @functools.wraps(fn)
+                def run(*a, **kw):
+                    t0 = time.perf_counter()
+                    try:
+                        return fn(*a, **kw)
+                    finally:
+                        rec = self.op_times.setdefault(name, [0.0, 0])
+                        rec[0] += time.perf_counter() - t0
+                        rec[1] += 1
+                return run
+            for name in self._PROFILED:
+                setattr(self, name, timed(name, getattr(self, name)))
+        from .evaluation import BufferPool
+        self._pool = BufferPool()      # device blocks recycled between the steps of a proof and between proofs
         self._live: list = []          # per-proof device buffers, freed by release()
         self._kept: list = []          # proving-key data and constants, freed by free()
         self._keys: dict = {}          # id(pk) -> resident proving-key data (kept across proofs)
@@ -670,6 +695,7 @@ class ResidentEngine:
             b.free()
         self._kept = []
         self._keys, self._consts = {}, {}
+        self._pool.trim()
 
     # -- commitments
     def _commit(self, srs, host_ptr, block: DevBlock, max_bits: int, ifft: bool) -> List[Point]:
@@ -1161,7 +1187,9 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
     import time
     vk = pk.vk
     cs, domain = vk.cs, vk.domain
+    from .evaluation import set_active_pool
     E = engine or ResidentEngine(params, domain)
+    prev_pool = set_active_pool(getattr(E, "_pool", None))
     try:
         return _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time)
     finally:
@@ -1169,6 +1197,7 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
             E.free()
         else:
             E.release()
+        set_active_pool(prev_pool)
 
 
 def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time) -> bytes:

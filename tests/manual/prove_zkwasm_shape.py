@@ -93,7 +93,7 @@ def main():
     adv = _lib.pinned_empty(advice.shape)
     adv[:] = advice
     del advice
-    eng = (TracingEngine if a.debug else HP.ResidentEngine)(params, pk.vk.domain)
+    eng = (TracingEngine if a.debug else HP.ResidentEngine)(params, pk.vk.domain, profile=True)
     L = _lib.lib()
     runs = []
     proof = b""
@@ -103,7 +103,9 @@ def main():
         t0 = time.perf_counter()
         proof = HP.create_proof(params, pk, adv, [public], HP.SeededRng(100 + it), timings=tm, engine=eng)
         dt = time.perf_counter() - t0
-        runs.append({"wall_s": dt, "phases_s": tm, "gpu_launches": int(L.b2_launch_count(0) - l0)})
+        runs.append({"wall_s": dt, "phases_s": tm, "gpu_launches": int(L.b2_launch_count(0) - l0),
+                     "engine_ops_s": {k2: [round(v[0], 5), v[1]] for k2, v in sorted(eng.op_times.items())}})
+        eng.op_times.clear()
     best = min(runs[1:], key=lambda r: r["wall_s"])
     prog = pk.ev.program(8, list(zk.LOOKUP_SETS), zk.SHUFFLES).info()
     doc = {"workload": "create_proof (GWC), zkWasm-shaped synthetic circuit with a real witness, device-resident engine",
@@ -111,7 +113,7 @@ def main():
                                           "shuffles": zk.SHUFFLES, "perm_cols": zk.PERM_COLS, "degree": 5,
                                           "extra_gates": a.extra_gates},
            "wall_s": best["wall_s"], "phases_s": best["phases_s"], "gpu_launches": best["gpu_launches"],
-           "first_call_s": runs[0]["wall_s"], "all_wall_s": [r["wall_s"] for r in runs[1:]],
+           "engine_ops_s_calls": best["engine_ops_s"], "first_call_s": runs[0]["wall_s"], "all_wall_s": [r["wall_s"] for r in runs[1:]],
            "proof_bytes": len(proof), "h_program": prog, "h2d_bytes": int(adv.nbytes),
            "untimed_s": {"srs_unsafe_setup_on_device": t_srs, "witness_generation": t_witness, "keygen": t_keygen},
            "advice_bound": "per column, scanned on the device (find_max_scalar_bits)"}
