@@ -455,6 +455,19 @@ class ArrayBlocks:
         return np.concatenate([q, np.zeros((1, 4), dtype=np.uint64)])
 
     @staticmethod
+    def sub_low_degree(col: np.ndarray, coeffs: Sequence[int]) -> None:
+        """col -= the polynomial with these (few) coefficients, in place"""
+        for i, c in enumerate(coeffs):
+            col[i] = _fr.to_mont((_fr.from_mont(col[i]) - c) % R)
+
+    def scale(self, col: np.ndarray, s: int) -> np.ndarray:
+        """s * col as a new column (the Horner fold of [col, 0] at s)"""
+        return self.poly_combine([col, np.zeros_like(col)], s)
+
+    def sub_cols(self, a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        return self.fr_vec("sub", a, b).reshape(a.shape)
+
+    @staticmethod
     def stack(cols) -> np.ndarray:
         return np.ascontiguousarray(np.stack(cols))
 
@@ -599,7 +612,7 @@ class ResidentEngine:
     _PROFILED = ("put", "put_and_commit_lagrange", "commit_lagrange", "commit_lagrange_and_ifft", "commit",
                  "lagrange_to_coeff", "multiplicity_block", "permutation_z", "logup_z", "shuffle_z", "random_poly",
                  "evaluate_h_blocks", "eval_polynomial", "poly_combine", "sub_constant", "kate_division_padded", "stack",
-                 "key_blocks", "release")
+                 "sub_low_degree", "scale", "sub_cols", "key_blocks", "release")
 
     def __init__(self, params, domain, profile: bool = False):
         from ._lib import require_gpu
@@ -953,6 +966,27 @@ class ResidentEngine:
         check(lib().b2_memcpy_d2h(ctypes.c_void_p(c0.ctypes.data), ctypes.c_void_p(col.ptr), 32))
         self.write_rows(col, 0, _fr.to_mont((_fr.from_mont(c0) - value) % R).reshape(1, 4))
 
+    def sub_low_degree(self, col: DevBlock, coeffs: Sequence[int]) -> None:
+        """col -= the polynomial with these (few) coefficients, in place: a few dozen bytes each way"""
+        import ctypes
+        from ._lib import check, lib
+        m = len(coeffs)
+        if m == 0:
+            return
+        head = np.empty((m, 4), dtype=np.uint64)
+        check(lib().b2_memcpy_d2h(ctypes.c_void_p(head.ctypes.data), ctypes.c_void_p(col.ptr), m * 32))
+        self.write_rows(col, 0, _mont_vec([(_fr.from_mont(head[i]) - c) % R for i, c in enumerate(coeffs)]))
+
+    def scale(self, col: DevBlock, s: int) -> DevBlock:
+        """s * col as a new column (the Horner fold of [col, 0] at s)"""
+        zero = DevBlock(self._const_column("zero", np.zeros(4, dtype=np.uint64)), 1, self.domain.n)
+        return self.poly_combine([col, zero], s)
+
+    def sub_cols(self, a: DevBlock, b: DevBlock) -> DevBlock:
+        out = self.alloc(1)
+        self._fr_vec(2, a.ptr, b.ptr, self.domain.n, out.ptr)
+        return out
+
     def kate_division_padded(self, col: DevBlock, z: int) -> DevBlock:
         """kate_division (n - 1 coefficients) into a column of n with a zero on top, so that it commits like one"""
         import ctypes
@@ -1166,8 +1200,9 @@ def multiplicity_tensors(raw, usable: int, m) -> int:
 # --------------------------------------------------------------------------
 def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence[Sequence[int]], rng,
                  sign_bit: int = 7, engine=None, advice_max_bits: Optional[int] = None,
-                 timings: Optional[dict] = None) -> bytes:
-    """plonk::create_proof (GWC multiopen) for one circuit instance, advice given (create_proof_from_witness).
+                 timings: Optional[dict] = None, use_gwc: bool = True) -> bytes:
+    """plonk::create_proof (use_gwc=True, GWC multiopen, plonk/prover.rs:1759-1781) or create_proof_with_shplonk
+    (use_gwc=False, :1737-1757) for one circuit instance, advice given (create_proof_from_witness).
 
     advice: (num_advice, n, 4) Lagrange columns in host memory (pinned memory makes the one upload faster); the
     blinding rows are written into it.  instances: per instance column the public values (canonical ints), zero
@@ -1191,7 +1226,8 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
     E = engine or ResidentEngine(params, domain)
     prev_pool = set_active_pool(getattr(E, "_pool", None))
     try:
-        return _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time)
+        return _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time,
+                             use_gwc)
     finally:
         if engine is None:
             E.free()
@@ -1200,7 +1236,7 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
         set_active_pool(prev_pool)
 
 
-def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time) -> bytes:
+def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time, use_gwc) -> bytes:
     vk = pk.vk
     n, k = domain.n, domain.k
     bf = cs.blinding_factors()
@@ -1374,9 +1410,17 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
     qs.append((0, x, h_poly))
     qs.append((0, x, random_poly))
 
-    gwc_create_proof(E, tr, qs)
+    if use_gwc:
+        gwc_create_proof(E, tr, qs)
+    else:
+        shplonk_create_proof(E, tr, qs)
     lap("multiopen")
     return tr.finalize()
+
+
+def create_proof_with_shplonk(params, pk, advice, instances, rng, **kw) -> bytes:
+    """plonk/prover.rs:1737-1757"""
+    return create_proof(params, pk, advice, instances, rng, use_gwc=False, **kw)
 
 
 def gwc_create_proof(E, tr: Blake2bWrite, queries) -> None:
@@ -1400,3 +1444,114 @@ def gwc_create_proof(E, tr: Blake2bWrite, queries) -> None:
         witnesses.append(E.kate_division_padded(poly_batch, z))
     for c in E.commit(E.stack(witnesses)):
         tr.write_point(c)
+
+
+# --------------------------------------------------------------------------
+# SHPLONK (poly/multiopen/shplonk.rs, shplonk/prover.rs)
+# --------------------------------------------------------------------------
+def _poly_key(col) -> int:
+    """identity of a polynomial handle (PolynomialPointer compares addresses, poly/multiopen.rs:150-158)"""
+    return col.ptr if isinstance(col, DevBlock) else col.ctypes.data
+
+
+def lagrange_interpolate(points: Sequence[int], evals: Sequence[int]) -> List[int]:
+    """arithmetic.rs:848-906 on a handful of points (host scalars): coefficients of the interpolant"""
+    m = len(points)
+    coeffs = [0] * m
+    for j in range(m):
+        num, den = [1], 1
+        for i in range(m):
+            if i == j:
+                continue
+            nxt = [0] * (len(num) + 1)
+            for t, c in enumerate(num):
+                nxt[t] = (nxt[t] - c * points[i]) % R
+                nxt[t + 1] = (nxt[t + 1] + c) % R
+            num = nxt
+            den = den * (points[j] - points[i]) % R
+        scale = evals[j] * _fr.inv(den) % R
+        for t, c in enumerate(num):
+            coeffs[t] = (coeffs[t] + c * scale) % R
+    return coeffs
+
+
+def _vanishing_at(roots: Sequence[int], z: int) -> int:
+    """evaluate_vanishing_polynomial, arithmetic.rs:905-923"""
+    acc = 1
+    for p in roots:
+        acc = (z - p) * acc % R
+    return acc
+
+
+def _eval_small(coeffs: Sequence[int], x: int) -> int:
+    acc = 0
+    for c in reversed(coeffs):
+        acc = (acc * x + c) % R
+    return acc
+
+
+def shplonk_create_proof(E, tr: Blake2bWrite, queries) -> None:
+    """poly/multiopen/shplonk/prover.rs:78-234 over the engine.  The per-commitment subtractions of the reference
+    (P - R for the quotient, P - R(u) for the linearisation) are linear, so each rotation set folds its polynomials
+    with y ONCE on the device (F = sum y^j P_j) and the low-degree parts are handled as a few host scalars:
+    N = F - R_fold (first |points| coefficients adjusted in place), Q = N / Z by repeated kate_division,
+    L = N + R_fold - r_fold(u).  Scaling by z_i is the Horner fold of [L, 0] at z_i."""
+    y = tr.squeeze_challenge()
+    # construct_intermediate_sets, shplonk.rs:57-150
+    point_of: Dict[int, int] = {}
+    for q in queries:
+        if point_of.setdefault(q[0], q[1]) != q[1]:
+            raise B2Error(B2_ERR_ARG, "assert_eq!(*point, query.get_point())")
+    super_point_set = [point_of[r] for r in sorted(point_of)]
+    order, rots = [], {}
+    for q in queries:
+        k = _poly_key(q[2])
+        if k not in rots:
+            rots[k] = set()
+            order.append((k, q[2]))
+        rots[k].add(q[0])
+    groups: Dict[tuple, list] = {}
+    for k, poly in order:
+        groups.setdefault(tuple(sorted(rots[k])), []).append(poly)
+    sets = []
+    for rs in sorted(groups):                                  # BTreeMap<BTreeSet<Rotation>, _>: lexicographic
+        points = [point_of[r] for r in rs]
+        polys = groups[rs]
+        lows = [lagrange_interpolate(points, [E.eval_polynomial(p, pt) for pt in points]) for p in polys]   # :33-48
+        sets.append((polys, points, lows))
+    v = tr.squeeze_challenge()
+
+    def fold_small(vals: Sequence[Sequence[int]], c: int) -> List[int]:
+        acc = [0] * len(vals[0])
+        for p in vals:
+            acc = [(a * c + b) % R for a, b in zip(acc, p)]
+        return acc
+
+    numerators, quotients = [], []
+    for polys, points, lows in sets:                           # quotient_contribution, :97-128
+        f = E.poly_combine(polys, y)
+        r_fold = fold_small(lows, y)
+        E.sub_low_degree(f, r_fold)                            # N_i = sum y^j (P_j - R_j)
+        q = f
+        for p in points:                                       # div_by_vanishing, :20-26
+            q = E.kate_division_padded(q, p)
+        numerators.append((f, r_fold))
+        quotients.append(q)
+    h_x = E.poly_combine(quotients, v)
+    tr.write_point(E.commit(E.stack([h_x]))[0])
+    u = tr.squeeze_challenge()
+    zt_eval = _vanishing_at(super_point_set, u)
+    lins, z_diffs = [], []
+    for (polys, points, lows), (f, r_fold) in zip(sets, numerators):     # linearisation_contribution, :163-192
+        z_i = _vanishing_at([p for p in super_point_set if p not in points], u)
+        c_i = fold_small([[_eval_small(low, u)] for low in lows], y)[0]
+        adjust = [(-a) % R for a in r_fold]
+        adjust[0] = (adjust[0] + c_i) % R
+        E.sub_low_degree(f, adjust)                            # L_i = N_i + R_fold - r_fold(u)
+        lins.append(E.scale(f, z_i))
+        z_diffs.append(z_i)
+    l_x = E.sub_cols(E.poly_combine(lins, v), E.scale(h_x, zt_eval))     # :205-211
+    if E.eval_polynomial(l_x, u) != 0:                         # sanity check, :213-216
+        raise B2Error(B2_ERR_ARG, "shplonk: linearisation polynomial does not vanish at u")
+    h2 = E.scale(E.kate_division_padded(l_x, u), _fr.inv(z_diffs[0]))    # :218-224
+    tr.write_point(E.commit(E.stack([h2]))[0])

@@ -434,9 +434,10 @@ def logup_multiplicity(input_sets, table, usable: int, n: int) -> List[int]:
 
 
 def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]], instances: Sequence[Sequence[int]],
-                 rng, sign_bit: int = 7) -> bytes:
+                 rng, sign_bit: int = 7, use_gwc: bool = True) -> bytes:
     """plonk/prover.rs:916-1500 (create_proof_from_witness: the advice columns are given, as read by fetch_witness)
-    with the GWC multiopen (`create_proof`, :1759-1781: use_gwc = true), one circuit instance per proof.
+    with the GWC multiopen (`create_proof`, :1759-1781: use_gwc = true) or SHPLONK (`create_proof_with_shplonk`,
+    :1737-1757: use_gwc = false), one circuit instance per proof.
 
     `rng` supplies every random value, in this order (vector draws; fr_vec returns Montgomery limbs):
       1. u16_vec(num_advice * (bf + 1)): blinding rows of advice column i are [i*(bf+1), (i+1)*(bf+1))   (:973-977)
@@ -597,7 +598,10 @@ def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]]
     qs.append((0, x, h_poly))                                                 # vanishing/prover.rs:135-152
     qs.append((0, x, random_poly))
 
-    gwc_create_proof(params, tr, qs)
+    if use_gwc:
+        gwc_create_proof(params, tr, qs)
+    else:
+        shplonk_create_proof(params, tr, qs)
     return tr.finalize()
 
 
@@ -625,6 +629,139 @@ def gwc_create_proof(params: Params, tr: Blake2bWrite, queries) -> None:
 
 
 # --------------------------------------------------------------------------
+# SHPLONK (poly/multiopen/shplonk.rs, shplonk/prover.rs, shplonk/verifier.rs)
+# --------------------------------------------------------------------------
+def shplonk_intermediate_sets(queries, key_of, eval_of):
+    """shplonk.rs:57-150.  queries: (rotation, point, commitment, ...); key_of(q): the identity of q's commitment
+    (PolynomialPointer / CommitmentReference compare by address); eval_of(q_first_with_that_commitment, rotation).
+    -> ([(commitments [(commitment, evals)], points)], super_point_set)"""
+    rotation_point: Dict[int, int] = {}
+    for q in queries:
+        if rotation_point.setdefault(q[0], q[1]) != q[1]:
+            raise AssertionError("rotation point matching consistency")            # :76
+    super_point_set = [rotation_point[r] for r in sorted(rotation_point)]
+    order: List[Tuple[object, tuple]] = []
+    rots: Dict[object, set] = {}
+    for q in queries:                                                             # :88-101
+        k = key_of(q)
+        if k not in rots:
+            rots[k] = set()
+            order.append((k, q))
+        rots[k].add(q[0])
+    groups: Dict[tuple, list] = {}
+    for k, q in order:                                                            # :109-118 (BTreeMap<BTreeSet<Rotation>, _>)
+        groups.setdefault(tuple(sorted(rots[k])), []).append((k, q))
+    rotation_sets = []
+    for rs in sorted(groups):                                                     # BTreeSet Ord = lexicographic
+        commitments = [(q[2], [eval_of(k, r) for r in rs]) for k, q in groups[rs]]
+        rotation_sets.append((commitments, [rotation_point[r] for r in rs]))
+    return rotation_sets, super_point_set
+
+
+def evaluate_vanishing_polynomial(roots: Sequence[int], z: int) -> int:
+    """arithmetic.rs:905-923"""
+    acc = 1
+    for p in roots:
+        acc = (z - p) * acc % R
+    return acc
+
+
+def _fold_polys(polys: Sequence[Sequence[int]], c: int, n: int) -> List[int]:
+    acc = [0] * n
+    for p in polys:
+        acc = [(a * c + b) % R for a, b in zip(acc, p)]
+    return acc
+
+
+def shplonk_create_proof(params: Params, tr: Blake2bWrite, queries) -> None:
+    """shplonk/prover.rs:78-234"""
+    n = params.n
+    y = tr.squeeze_challenge()
+    polys = {id(q[2]): q[2] for q in queries}
+    point_of = {q[0]: q[1] for q in queries}
+    sets, super_point_set = shplonk_intermediate_sets(
+        queries, lambda q: id(q[2]), lambda k, r: o.eval_polynomial(polys[k], point_of[r]))
+    pad = lambda p: list(p) + [0] * (n - len(p))                                    # noqa: E731
+    ext = [([(poly, pad(o.lagrange_interpolate(points, evals))) for poly, evals in commitments], points)
+           for commitments, points in sets]                                       # :33-48 low_degree_equivalent
+    v = tr.squeeze_challenge()
+    quotients = []
+    for commitments, points in ext:                                               # :97-128
+        numerators = [[(a - b) % R for a, b in zip(poly, low)] for poly, low in commitments]
+        n_x = _fold_polys(numerators, y, n)
+        for p in points:                                                          # div_by_vanishing :20-26
+            n_x = o.kate_division(n_x, p)
+        quotients.append(pad(n_x))
+    h_x = _fold_polys(quotients, v, n)
+    tr.write_point(params.commit(h_x))
+    u = tr.squeeze_challenge()
+    zt_eval = evaluate_vanishing_polynomial(super_point_set, u)
+    lins, z_diffs = [], []
+    for commitments, points in ext:                                               # :163-192
+        z_i = evaluate_vanishing_polynomial([p for p in super_point_set if p not in points], u)
+        inner = []
+        for poly, low in commitments:
+            r_eval = o.eval_polynomial(low, u)
+            inner.append([(poly[0] - r_eval) % R] + list(poly[1:]))
+        l_i = _fold_polys(inner, y, n)
+        lins.append([a * z_i % R for a in l_i])
+        z_diffs.append(z_i)
+    l_x = _fold_polys(lins, v, n)
+    l_x = [(a - b * zt_eval) % R for a, b in zip(l_x, h_x)]
+    assert o.eval_polynomial(l_x, u) == 0                                          # :213-216
+    h2 = o.kate_division(l_x, u)
+    inv = o.fr_inv(z_diffs[0])
+    tr.write_point(params.commit([a * inv % R for a in h2]))
+
+
+def shplonk_verify_proof(params, tr: Blake2bRead, queries) -> Tuple[Point, Point]:
+    """shplonk/verifier.rs:23-104; queries: (rotation, point, commitment terms, eval, key)"""
+    evals = {}
+    for q in queries:
+        evals.setdefault((q[4], q[0]), q[3])
+    sets, super_point_set = shplonk_intermediate_sets(queries, lambda q: q[4], lambda k, r: evals[(k, r)])
+    y = tr.squeeze_challenge()
+    v = tr.squeeze_challenge()
+    try:
+        h1 = tr.read_point()
+        u = tr.squeeze_challenge()
+        h2 = tr.read_point()
+    except TranscriptError:
+        raise VerifyError("SamplingError")
+    z_0_diff_inverse = z_0 = 0
+    outer: List[List[Tuple[int, Point]]] = []
+    r_outer_acc = 0
+    for i, (commitments, points) in enumerate(sets):
+        z_diff_i = evaluate_vanishing_polynomial([p for p in super_point_set if p not in points], u)
+        if i == 0:
+            z_0 = evaluate_vanishing_polynomial(points, u)
+            z_0_diff_inverse = o.fr_inv(z_diff_i)
+            z_diff_i = 1
+        else:
+            z_diff_i = z_diff_i * z_0_diff_inverse % R
+        inner: List[Tuple[int, Point]] = []
+        r_inner_acc = 0
+        for terms, evs in commitments:
+            r_x = o.lagrange_interpolate(points, evs)
+            r_inner_acc = (y * r_inner_acc + o.eval_polynomial(r_x, u)) % R
+            inner.append((1, _g1_lincomb(terms)))                                 # msm.eval() for the h commitment
+        r_outer_acc = (v * r_outer_acc + r_inner_acc * z_diff_i) % R
+        acc = 1
+        scaled = []
+        for s, p in reversed(inner):                                              # combine_with_base(y), msm.rs:136-145
+            scaled.append((s * acc % R * z_diff_i % R, p))
+            acc = acc * y % R
+        outer.append(scaled)
+    acc = 1
+    right_terms: List[Tuple[int, Point]] = []
+    for msm_terms in reversed(outer):                                             # combine_with_base(v), msm.rs:195-204
+        right_terms += [(s * acc % R, p) for s, p in msm_terms]
+        acc = acc * v % R
+    right_terms += [((-r_outer_acc) % R, params.g1), ((-z_0) % R, h1), (u, h2)]
+    return h2, _g1_lincomb(right_terms)
+
+
+# --------------------------------------------------------------------------
 # verify_proof
 # --------------------------------------------------------------------------
 class VerifyError(Exception):
@@ -640,7 +777,7 @@ def _g1_lincomb(terms: Sequence[Tuple[int, Point]]) -> Point:
 
 
 def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[int]], proof: bytes,
-                 sign_bit: int = 7, pairing: bool = False) -> bool:
+                 sign_bit: int = 7, pairing: bool = False, use_gwc: bool = True) -> bool:
     """plonk/verifier.rs:127-507 with SingleVerifier and the GWC multiopen; False = the final check failed,
     VerifyError / TranscriptError = the proof is malformed.  `pairing=True` decides with the optimal-ate pairing
     on [s]G2 (Decider::verify); the default decides with the equivalent G1 equation [s]*left == right."""
@@ -770,37 +907,40 @@ def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[
         h_terms.append((pw, c))
         pw = pw * xn % R
 
-    # ---- verifier queries (:401-488): (rotation, point, commitment terms, eval)
+    # ---- verifier queries (:401-488): (rotation, point, commitment terms, eval, identity of the commitment)
     rot = domain.rotate_omega
     x_next, x_last = rot(x, 1), rot(x, -(bf + 1))
     qs = []
     one = lambda c: [(1, c)]                                                   # noqa: E731
     for (col, at), e in zip(queries["Instance"], instance_evals):
-        qs.append((at, rot(x, at), one(instance_commitments[col]), e))
+        qs.append((at, rot(x, at), one(instance_commitments[col]), e, ("instance", col)))
     for (col, at), e in zip(queries["Advice"], advice_evals):
-        qs.append((at, rot(x, at), one(advice_commitments[col]), e))
-    for st in perm_sets:
-        qs.append((0, x, one(st["c"]), st["eval"]))
-        qs.append((1, x_next, one(st["c"]), st["next"]))
-    for st in list(reversed(perm_sets))[1:]:
-        qs.append((-(bf + 1), x_last, one(st["c"]), st["last"]))
-    for lk in lookups:
-        qs.append((0, x, one(lk["m_c"]), lk["m_eval"]))
-        for st in lk["z"]:
-            qs.append((0, x, one(st["c"]), st["eval"]))
-            qs.append((1, x_next, one(st["c"]), st["next"]))
-        for st in list(reversed(lk["z"]))[1:]:
-            qs.append((-(bf + 1), x_last, one(st["c"]), st["last"]))
-    for sh in shuffles:
-        qs.append((0, x, one(sh["c"]), sh["eval"]))
-        qs.append((1, x_next, one(sh["c"]), sh["next"]))
+        qs.append((at, rot(x, at), one(advice_commitments[col]), e, ("advice", col)))
+    for i, st in enumerate(perm_sets):
+        qs.append((0, x, one(st["c"]), st["eval"], ("perm", i)))
+        qs.append((1, x_next, one(st["c"]), st["next"], ("perm", i)))
+    for i, st in list(reversed(list(enumerate(perm_sets))))[1:]:
+        qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("perm", i)))
+    for li, lk in enumerate(lookups):
+        qs.append((0, x, one(lk["m_c"]), lk["m_eval"], ("lookup_m", li)))
+        for i, st in enumerate(lk["z"]):
+            qs.append((0, x, one(st["c"]), st["eval"], ("lookup_z", li, i)))
+            qs.append((1, x_next, one(st["c"]), st["next"], ("lookup_z", li, i)))
+        for i, st in list(reversed(list(enumerate(lk["z"]))))[1:]:
+            qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("lookup_z", li, i)))
+    for i, sh in enumerate(shuffles):
+        qs.append((0, x, one(sh["c"]), sh["eval"], ("shuffle", i)))
+        qs.append((1, x_next, one(sh["c"]), sh["next"], ("shuffle", i)))
     for (col, at), e in zip(queries["Fixed"], fixed_evals):
-        qs.append((at, rot(x, at), one(vk.fixed_commitments[col]), e))
-    for c, e in zip(vk.permutation_commitments, permutation_evals):
-        qs.append((0, x, one(c), e))
-    qs.append((0, x, h_terms, expected_h_eval))
-    qs.append((0, x, one(random_poly_commitment), random_eval))
+        qs.append((at, rot(x, at), one(vk.fixed_commitments[col]), e, ("fixed", col)))
+    for i, (c, e) in enumerate(zip(vk.permutation_commitments, permutation_evals)):
+        qs.append((0, x, one(c), e, ("sigma", i)))
+    qs.append((0, x, h_terms, expected_h_eval, ("h",)))
+    qs.append((0, x, one(random_poly_commitment), random_eval, ("random",)))
 
+    if not use_gwc:
+        left, right = shplonk_verify_proof(params, tr, qs)
+        return Decider.verify(params, left, right) if pairing else Decider.verify_trapdoor(params, left, right)
     left, right = gwc_verify_proof(params, tr, qs)
     if pairing:
         return Decider.verify(params, left, right)

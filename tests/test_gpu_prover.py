@@ -240,3 +240,49 @@ def test_max_bits_and_device_multiplicity_primitives(gpu):
     got_m = m.download()
     assert got_m[:, 0].tolist() == want and not got_m[:, 1:].any() and largest == max(want)
     comp.free(); m.free()
+
+
+@pytest.mark.parametrize("engine_kind", ["resident", "host_api"])
+def test_shplonk_proof_bytes_match_oracle(gpu, engine_kind):
+    """create_proof_with_shplonk on the engine == oracle bytes; accepted by the oracle's SHPLONK verifier (pairing)"""
+    k = 5
+    fx = fxm.build(k=k, seed=11)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, S_TOXIC)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+    params, pk = engine_side(k, oparams, cs, np.stack([enc(c) for c in fx["fixed"]]),
+                             np.array(fx["mapping"], dtype=np.int64), opk.vk.transcript_repr)
+    try:
+        inst = [fx["instance"][0][:4]]
+        want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(9), use_gwc=False)
+        adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+        eng = (HP.ResidentEngine if engine_kind == "resident" else HP.Engine)(params, pk.vk.domain)
+        got = HP.create_proof_with_shplonk(params, pk, adv, inst, HP.SeededRng(9), engine=eng)
+        eng.free()
+        assert got == want
+        assert PR.verify_proof(oparams, opk.vk, inst, got, use_gwc=False, pairing=True)
+    finally:
+        params.free()
+
+
+def test_shplonk_zkwasm_shape_k14(gpu):
+    from oracle import cref
+    k = 14
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, 16, lambda a: cref.to_mont(0, a))
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        eng = HP.ResidentEngine(params, pk.vk.domain)
+        timings = {}
+        HP.create_proof_with_shplonk(params, pk, advice.copy(), [public], HP.SeededRng(1), engine=eng)
+        proof = HP.create_proof_with_shplonk(params, pk, advice.copy(), [public], HP.SeededRng(2), engine=eng, timings=timings)
+        eng.free()
+        ovk = PR.VerifyingKey(ocs, o.EvaluationDomain(5, k), pk.vk.fixed_commitments, pk.vk.permutation_commitments,
+                              pk.vk.transcript_repr)
+        vparams = PR.ParamsVerifier(k, S_TOXIC)
+        assert PR.verify_proof(vparams, ovk, [public], proof, use_gwc=False)
+        assert not PR.verify_proof(vparams, ovk, [[public[0] + 1] + public[1:]], proof, use_gwc=False)
+        print(f"shplonk zkwasm shape k={k} create_proof {sum(timings.values()):.4f} s, multiopen {timings['multiopen']:.4f} s")
+    finally:
+        params.free()

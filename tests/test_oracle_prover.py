@@ -156,3 +156,38 @@ def test_transcript_known_answers():
     rd.common_scalar(5)
     assert rd.read_point() == (1, 2)
     assert rd.squeeze_challenge() == c
+
+
+def test_shplonk_proof_verifies_and_binds_every_element(setup):
+    """create_proof_with_shplonk + the SHPLONK verifier (poly/multiopen/shplonk/{prover,verifier}.rs)"""
+    fx, params, pk, inst, _ = setup
+    proof = PR.create_proof(params, pk, fx["advice"], inst, SeededRng(1), use_gwc=False)
+    assert PR.verify_proof(params, pk.vk, inst, proof, use_gwc=False)
+    assert PR.verify_proof(params, pk.vk, inst, proof, use_gwc=False, pairing=True)
+    for el in range(len(proof) // 32):
+        bad = bytearray(proof)
+        bad[32 * el + 3] ^= 0x10
+        try:
+            ok = PR.verify_proof(params, pk.vk, inst, bytes(bad), use_gwc=False)
+        except (PR.TranscriptError, PR.VerifyError):
+            continue
+        assert not ok, f"element {el} is not bound by the SHPLONK verifier"
+    assert not PR.verify_proof(params, pk.vk, [[(inst[0][0] + 1) % R] + list(inst[0][1:])], proof, use_gwc=False)
+    # a GWC proof is not a SHPLONK proof
+    gwc = PR.create_proof(params, pk, fx["advice"], inst, SeededRng(1))
+    try:
+        assert not PR.verify_proof(params, pk.vk, inst, gwc, use_gwc=False)
+    except (PR.TranscriptError, PR.VerifyError):
+        pass
+
+
+def test_shplonk_intermediate_sets_grouping():
+    """shplonk.rs:57-150: commitments grouped by their SET of rotations, sets in BTreeSet order, first-appearance
+    order inside a set, super point set ordered by rotation"""
+    pts = {-1: 11, 0: 22, 1: 33}
+    q = lambda r, c: (r, pts[r], c, 100 * r + ord(c))                                     # noqa: E731
+    queries = [q(0, "a"), q(1, "b"), q(0, "b"), q(-1, "c"), q(0, "c"), q(0, "d"), q(1, "e"), q(0, "e")]
+    sets, super_points = PR.shplonk_intermediate_sets(queries, lambda x: x[2], lambda k, r: 100 * r + ord(k))
+    assert super_points == [11, 22, 33]
+    assert [([c for c, _ in cs], p) for cs, p in sets] == [(["c"], [11, 22]), (["a", "d"], [22]), (["b", "e"], [22, 33])]
+    assert sets[2][0][0][1] == [ord("b"), 100 + ord("b")]

@@ -286,3 +286,22 @@ def test_zkwasm_shaped_circuit_proves_and_verifies():
     bad[2, 9] = enc([12345])[0]                       # a product cell
     assert not PR.verify_proof(oparams, opk.vk, [public],
                                HP.create_proof(HostParams(k), pk, bad, [public], HP.SeededRng(3), engine=eng))
+
+
+@pytest.mark.parametrize("k,seed", [(5, 11), (6, 17)])
+def test_shplonk_proof_bytes_match_oracle_and_verify(k, seed):
+    """create_proof_with_shplonk (plonk/prover.rs:1737-1757, poly/multiopen/shplonk/prover.rs): the engine-side
+    formulation (one y-fold per rotation set, low-degree parts as host scalars) gives the oracle's bytes, which
+    restate the reference's per-commitment formulation; the oracle's SHPLONK verifier accepts"""
+    fx, oparams, opk, cs, eng, pk = both_sides(k, seed)
+    inst = [fx["instance"][0][:4]]
+    want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(4), use_gwc=False)
+    adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+    got = HP.create_proof_with_shplonk(HostParams(k), pk, adv, inst, HP.SeededRng(4), engine=eng)
+    assert got == want
+    assert PR.verify_proof(oparams, opk.vk, inst, got, use_gwc=False)
+    assert PR.verify_proof(oparams, opk.vk, inst, got, use_gwc=False, pairing=(k == 5))
+    assert not PR.verify_proof(oparams, opk.vk, [[inst[0][0] + 1] + inst[0][1:]], got, use_gwc=False)
+    gwc = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(4))
+    # same transcript up to the multiopen argument; 2 points (h1, h2) instead of one W per rotation (4 here)
+    assert len(got) == len(gwc) - 64 and got[:len(got) - 64] == gwc[:len(got) - 64]
