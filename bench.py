@@ -23,6 +23,8 @@ all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GP
           integer roofline; its own cpu_baseline (C restatement of the reference's row loop)
   create_proof  N == 1 only: BASELINE config 4, the benches/plonk.rs circuit at k = 18, whole create_proof through
           the prover mirror (plonk.create_proof), wall seconds and per-phase split
+  create_proof_k22  N == 1 only: "k = 22 create_proof wall-time" as a real proof of a zkWasm-shaped circuit (64 advice, 32
+          fixed, 8 lookups, 4 shuffles, 24 permutation columns) on one GPU
   cpu_baseline / --impl reference: the C restatement of the reference's rayon path
           (oracle/cpu_ref.c = arithmetic.rs:20-108, 465-492) on the box's host cores
 
@@ -324,6 +326,10 @@ def run_engine(args):
     if world == 1 and not args.no_proof:
         proof = bench_create_proof(args, _lib, h2)
 
+    proof22 = None
+    if world == 1 and not args.no_proof22:
+        proof22 = bench_create_proof_zkwasm(args, _lib, h2)
+
     if rank == 0:
         hbm_peak, peak_src = _peaks()
         total_pts = n * world * args.steps
@@ -379,6 +385,8 @@ def run_engine(args):
             line["quotient"] = quotient
         if proof:
             line["create_proof"] = proof
+        if proof22:
+            line["create_proof_k22"] = proof22
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args)
         print(json.dumps(line), flush=True)
@@ -614,6 +622,61 @@ def bench_create_proof(args, _lib, h2):
         return {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
 
 
+def bench_create_proof_zkwasm(args, _lib, h2):
+    """BASELINE's third headline number, "k = 22 create_proof wall-time", as a real proof on one GPU: the zkWasm-shaped
+    synthetic circuit of tools/zkwasm_shape_circuit.py (64 advice, 32 fixed, 1 instance, 8 lookups / 12 input sets,
+    4 shuffles, 24 permutation columns, degree 5; a stand-in gate set, zkWasm's own circuit is not available) through
+    plonk.create_proof with the device-resident engine.  Wall clock around the call; the 8 GiB of advice start in pinned
+    host memory; SRS built on the device; proving key resident (second and later proofs).  The same script with the
+    oracle's verifier attached is tests/manual/prove_zkwasm_shape.py.  Never fatal for the main line."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import zkwasm_shape_circuit as zk
+        from halo2_gpu_specific_b200 import plonk as HP
+        k = args.proof22_k
+        params = h2.Params.unsafe_setup(k, 0x2B200B200B200B200B200B200B200B2001)
+        adv = None
+        try:
+            cs = HP.ConstraintSystem(**zk.constraint_system_args(extra_gates=300))
+            dom = h2.EvaluationDomain(cs.degree(), k)
+            fixed, advice, public, mapping = zk.build(k, HP.Engine(params, dom).to_mont, seed=k)
+            pk = HP.keygen(params, cs, fixed, mapping)
+            adv = _lib.pinned_empty(advice.shape)
+            adv[:] = advice
+            del advice, fixed
+            eng = HP.ResidentEngine(params, pk.vk.domain, profile=True)
+            L = _lib.lib()
+            runs = []
+            for it in range(1 + args.proof22_reps):
+                tm = {}
+                eng.op_times.clear()
+                l0 = L.b2_launch_count(0)
+                t0 = time.perf_counter()
+                proof = HP.create_proof(params, pk, adv, [public], HP.SeededRng(it), timings=tm, engine=eng,
+                                        use_gwc=not args.shplonk)
+                runs.append({"wall_s": time.perf_counter() - t0, "phases_s": tm, "launches": int(L.b2_launch_count(0) - l0),
+                             "ops": {a: [round(b[0], 5), b[1]] for a, b in sorted(eng.op_times.items())},
+                             "bytes": len(proof)})
+            eng.free()
+            best = min(runs[1:], key=lambda r: r["wall_s"])
+            return {"metric": f"create_proof wall time, zkWasm-shaped circuit at k={k} "
+                              f"({'SHPLONK' if args.shplonk else 'GWC'}), one GPU",
+                    "value": best["wall_s"], "unit": "s", "higher_is_better": False, "all_s": [r["wall_s"] for r in runs[1:]],
+                    "first_call_s": runs[0]["wall_s"], "phases_s": best["phases_s"], "engine_ops_s_calls": best["ops"],
+                    "gpu_launches": best["launches"], "proof_bytes": best["bytes"], "h2d_bytes": int(adv.nbytes),
+                    "shape": {"A": zk.A, "F": zk.F, "I": zk.I, "lookup_sets": list(zk.LOOKUP_SETS), "shuffles": zk.SHUFFLES,
+                              "perm_cols": zk.PERM_COLS, "degree": 5, "extra_gates": 300},
+                    "h_program": pk.ev.program(8, list(zk.LOOKUP_SETS), zk.SHUFFLES).info(),
+                    "api": "halo2_gpu_specific_b200.plonk.create_proof, ResidentEngine"}
+        finally:
+            if adv is not None:
+                _lib.pinned_free(adv)
+            params.free()
+    except Exception as e:                                # noqa: BLE001
+        import traceback
+        return {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+
+
 def cpu_baseline(args):
     """Bounded sample of the same workload on the host cores (C restatement of the rayon path)."""
     from oracle import cref
@@ -657,6 +720,10 @@ def main():
     ap.add_argument("--no-proof", action="store_true")
     ap.add_argument("--proof-k", type=int, default=18)
     ap.add_argument("--proof-reps", type=int, default=3)
+    ap.add_argument("--no-proof22", action="store_true", help="skip the zkWasm-shaped k=22 real proof (about 40 s of setup)")
+    ap.add_argument("--proof22-k", type=int, default=22)
+    ap.add_argument("--proof22-reps", type=int, default=2)
+    ap.add_argument("--shplonk", action="store_true", help="create_proof_with_shplonk in the proof sections")
     ap.add_argument("--no-precompute", action="store_true", help="plain bases: one bucket set per window + Horner")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "engine":

@@ -1463,6 +1463,10 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     NttPlan* pl = nullptr;
     if (do_ifft && (rc = ntt_get_plan(*ctx, omega_inv, divisor, log_n, &pl))) return rc;
     const size_t col_bytes = n * 32;
+    // B2_MAX_BITS_AUTO: the bound of each column is the bit length of its largest scalar, found on the device right
+    // after the column has landed (find_max_scalar_bits, plonk/prover.rs:945-962, 296)
+    const bool auto_bits = max_bits == B2_MAX_BITS_AUTO;
+    std::vector<char> lane_used(MAX_LANES + 1, 0);          // lanes whose bound flag was reset by an MSM of this batch
     if (max_bits > 254) max_bits = 254;
     const size_t nl = set.lanes.size();
     if ((rc = ctx->h_stage.reserve((size_t)columns * 96))) return rc;
@@ -1487,12 +1491,24 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
         if ((rc = ln->out96.reserve(96))) return rc;
         if (do_ifft && pl->npass > 1 && (rc = ln->ntt_work.reserve(col_bytes))) return rc;
         if (!columns_on_device) CK(cudaMemcpyAsync(dcol, h, col_bytes, cudaMemcpyHostToDevice, st));
-        if (max_bits == 0) {
+        uint32_t col_bits = max_bits;
+        if (auto_bits) {
+            // the host waits for THIS lane's copy + scan only; the MSM it then enqueues runs under the next column's
+            // copy, which goes to another lane
+            if ((rc = ln->scan_tot.reserve(64))) return rc;
+            CK(cudaMemsetAsync(ln->scan_tot.p, 0, 4, st));
+            LAUNCH(*ln, fr_max_bits_kernel, (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ln->sms * 16), 256, 0, st,
+                   (const uint4*)dcol, (unsigned long long)n, (unsigned*)ln->scan_tot.p);
+            CK(cudaMemcpyAsync(&col_bits, ln->scan_tot.p, 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        if (col_bits == 0) {
             if ((rc = write_identity(*ln, ln->out96.p, st))) return rc;
         } else {
             // the bound flag is sticky per lane for the whole batch (reset once, read once)
-            if ((rc = msm_run_split(*ln, s, 0, dcol, n, max_bits, ln->out96.p, st, false, c < nl)))
+            if ((rc = msm_run_split(*ln, s, 0, dcol, n, col_bits, ln->out96.p, st, false, !lane_used[c % nl])))
                 return rc;
+            lane_used[c % nl] = 1;
         }
         CK(cudaMemcpyAsync(h_pts + c * 96, ln->out96.p, 96, cudaMemcpyDeviceToHost, st));
         if (do_ifft) {
@@ -1504,6 +1520,7 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     int bound_flag_any = 0;
     if (max_bits != 0) {
         for (size_t l = 0; l < nl && l < columns; l++) {
+            if (!lane_used[l]) continue;
             int flag = 0;
             CK(cudaMemcpyAsync(&flag, set.lanes[l]->errflag.p, 4, cudaMemcpyDeviceToHost, set.lanes[l]->stream));
             CK(cudaStreamSynchronize(set.lanes[l]->stream));

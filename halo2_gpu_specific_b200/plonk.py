@@ -730,16 +730,10 @@ class ResidentEngine:
         if max_bits is not None:
             block = self.alloc(host.shape[0])
             return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, max_bits, False)
-        # no bound given: find_max_scalar_bits per column on the device (plonk/prover.rs:945-962, 296)
-        import ctypes
-        from ._lib import check, lib
-        block = self.put(host)
-        points = []
-        for col in self.cols(block):
-            bits = ctypes.c_uint32()
-            check(lib().b2_fr_max_bits_dev(ctypes.c_void_p(col.ptr), col.n, ctypes.byref(bits)))
-            points += self._commit(self.params.g_lagrange, 0, col, bits.value, False)
-        return block, points
+        # no bound given: find_max_scalar_bits per column on the device (plonk/prover.rs:945-962, 296), inside the
+        # same pipelined call (B2_MAX_BITS_AUTO): scan of column c after its copy, its MSM under the copy of c + 1
+        block = self.alloc(host.shape[0])
+        return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, 0xFFFFFFFF, False)
 
     def commit_lagrange(self, block: DevBlock, max_bits: int = _fr.NUM_BITS) -> List[Point]:
         return self._commit(self.params.g_lagrange, 0, block, max_bits, False)

@@ -184,6 +184,11 @@ int b2_commit_batch(b2_handle_t srs, void* columns_data, uint64_t columns, size_
  * in place there -- nothing is copied back; with columns_on_device != 0 the columns are read from d_columns and
  * columns_data is ignored.  This is what lets the advice / z columns be uploaded once per proof: their coefficient
  * forms are then consumed on the device by the coset transforms of evaluate_h (plonk/prover.rs:639-661). */
+/* max_bits of b2_commit_batch[_resident]: B2_MAX_BITS_AUTO makes the bound of each column the bit length of its largest
+ * scalar, found on the device right after the column has landed (find_max_scalar_bits + commit_lagrange_with_bound,
+ * plonk/prover.rs:945-962, 293-299), still pipelined: the scan of column c waits for its copy only, its MSM runs under
+ * the copy of column c + 1. */
+#define B2_MAX_BITS_AUTO 0xFFFFFFFFu
 int b2_commit_batch_resident(b2_handle_t srs, const void* columns_data, int columns_on_device, void* d_columns,
                              uint64_t columns, size_t n, uint32_t max_bits, int do_ifft, const void* omega_inv,
                              const void* divisor, uint32_t log_n, void* out_jac96);
