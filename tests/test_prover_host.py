@@ -305,3 +305,41 @@ def test_shplonk_proof_bytes_match_oracle_and_verify(k, seed):
     gwc = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(4))
     # same transcript up to the multiopen argument; 2 points (h1, h2) instead of one W per rotation (4 here)
     assert len(got) == len(gwc) - 64 and got[:len(got) - 64] == gwc[:len(got) - 64]
+
+
+def test_degenerate_shapes_prove_and_verify():
+    """circuits that lack whole arguments: (a) gates only, no permutation / lookup / shuffle / instance;
+    (b) one lookup and nothing else besides a gate"""
+    k = 5
+    n = 1 << k
+    usable = n - 6
+    rng = random.Random(8)
+    oparams = PR.Params(k, S_TOXIC)
+    A, F = ("Advice", 0, 0), ("Fixed", 0, 0)
+    sq = ("Product", F, ("Sum", ("Product", A, A), ("Negated", ("Advice", 1, 0))))
+    for with_lookup in (False, True):
+        lookups = [{"table_expressions": [("Fixed", 1, 0)], "input_expressions_sets": [[[("Advice", 1, 0)]]]}] if with_lookup else []
+        # cs.degree(): 3 for the gate alone, 4 with the lookup (active rows * table * input * z); a larger value would
+        # leave an h(X) piece identically zero, which neither prover can commit to ("points at infinity")
+        degree = 4 if with_lookup else 3
+        cs = HP.ConstraintSystem(2, 2, 0, degree=degree, blinding_factors=5, gates=[[sq]], lookups=lookups)
+        ocs = P.ConstraintSystem(2, 2, 0, degree=degree, blinding_factors=5)
+        ocs.gates, ocs.lookups = cs.gates, cs.lookups
+        a0 = [rng.randrange(R) for _ in range(n)]
+        a1 = [v * v % R for v in a0]
+        fixed = [[1 if r < usable else 0 for r in range(n)], [a1[(r * 7) % usable] for r in range(n)]]
+        advice = [a0, a1]
+        opk = PR.keygen(oparams, ocs, fixed, [])
+        eng = OracleEngine(oparams, opk.vk.domain, ocs)
+        pk = HP.keygen(HostParams(k), cs, np.stack([enc(c) for c in fixed]), np.zeros((0, n, 2), dtype=np.int64), engine=eng,
+                       transcript_repr=opk.vk.transcript_repr)
+        for gwc in (True, False):
+            want = PR.create_proof(oparams, opk, advice, [], HP.SeededRng(2), use_gwc=gwc)
+            got = HP.create_proof(HostParams(k), pk, np.stack([enc(c) for c in advice]), [], HP.SeededRng(2), engine=eng,
+                                  use_gwc=gwc)
+            assert got == want
+            assert PR.verify_proof(oparams, opk.vk, [], got, use_gwc=gwc)
+        bad = [list(a0), list(a1)]
+        bad[1][3] = (bad[1][3] + 1) % R
+        if not with_lookup:
+            assert not PR.verify_proof(oparams, opk.vk, [], PR.create_proof(oparams, opk, bad, [], HP.SeededRng(2)))
