@@ -10,7 +10,9 @@ repository); the gate set is a stand-in whose size is a parameter (`extra_gates`
   a47 = public inputs in its first rows                                             gate  q_inst * (a47 - instance)
   a48 .. a59 = table[random row]             table t = f16 (distinct values)         8 lookups, 12 single-input sets
   a60 .. a63 = permutations of a48 .. a51                                           4 shuffle groups
-  extra gates  q_j * (a*b - c) * (a_x + f_y)    degree 4, satisfied wherever q_j * (a*b - c) is
+  extra gates  q_j * (a*b - c) * (a_x + f_y)    degree 4, satisfied wherever q_j * (a*b - c) is; they sit in the gate of
+               their triple, so the shared factor is short-lived in the quotient program (4 live slots instead of 17
+               when all extras come last: the y-fold visits the polynomials in gate order)
   copies       a[6i][r] = a[6i + 3][r] for r = 0 mod 4, i < 4                        permutation over a0 .. a23
 
 Everything is generated with numpy on small integers; `to_mont` (canonical (m, 4) limbs -> Montgomery) is supplied by
@@ -38,16 +40,14 @@ def _add(a, b): return ("Sum", a, b)               # noqa: E704
 def constraint_system_args(extra_gates: int = 64) -> dict:
     gates = []
     product = lambda j: _sub(_mul(_adv(3 * j), _adv(3 * j + 1)), _adv(3 * j + 2))      # noqa: E731
-    for j in range(TRIPLES):
-        gates.append([_mul(_fix(j), product(j))])
+    for j in range(TRIPLES):                          # one gate per triple: its product constraint and its extras, so
+        polys = [_mul(_fix(j), product(j))]           # that the shared sub-expression q_j * (a*b - c) is short-lived
+        for e in range(j, extra_gates, TRIPLES):
+            x, y = (7 * e + 3) % A, 18 + (e % (F - 18))
+            polys.append(_mul(_mul(_fix(j), product(j)), _add(_adv(x), _fix(y))))
+        gates.append(polys)
     gates.append([_mul(_fix(15), _sub(_sub(_adv(46, 1), _adv(46)), _adv(45)))])
     gates.append([_mul(_fix(17), _sub(_adv(47), ("Instance", 0, 0)))])
-    extra = []
-    for e in range(extra_gates):
-        j, x, y = e % TRIPLES, (7 * e + 3) % A, 18 + (e % (F - 18))
-        extra.append(_mul(_mul(_fix(j), product(j)), _add(_adv(x), _fix(y))))
-    if extra:
-        gates.append(extra)
     lookups, col = [], 48
     for sets in LOOKUP_SETS:
         lookups.append({"table_expressions": [_fix(16)],
