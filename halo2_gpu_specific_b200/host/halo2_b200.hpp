@@ -113,6 +113,19 @@ class Srs {  // bases resident in HBM (replaces the per-call upload of arithmeti
         check(b2_srs_register(bases, n, sizeof(G1Affine), &h_), "b2_srs_register");
         if (precompute) check(b2_srs_precompute(h_, 0), "b2_srs_precompute");
     }
+    // bases[i] = [k_i] G for n Montgomery-form scalars already on the device (b2_srs_from_scalars_dev)
+    static Srs from_scalars_dev(const void* d_scalars, size_t n, bool precompute = true) {
+        Srs s;
+        s.n_ = n;
+        check(b2_srs_from_scalars_dev(d_scalars, n, &s.h_), "b2_srs_from_scalars_dev");
+        if (precompute) check(b2_srs_precompute(s.h_, 0), "b2_srs_precompute");
+        return s;
+    }
+    std::vector<G1Affine> read() const {
+        std::vector<G1Affine> out(n_);
+        check(b2_srs_read(h_, 0, n_, out.data()), "b2_srs_read");
+        return out;
+    }
     Srs(const Srs&) = delete;
     Srs& operator=(const Srs&) = delete;
     Srs(Srs&& o) noexcept : h_(o.h_), n_(o.n_) { o.h_ = 0; }
@@ -277,6 +290,42 @@ class Params {
     Params(uint32_t k_, const std::vector<G1Affine>& g_, const std::vector<G1Affine>& gl_)
         : k(k_), n(1ull << k_), g(g_.data(), g_.size()), g_lagrange(gl_.data(), gl_.size()) {
         if (g_.size() != n || gl_.size() != n) throw std::runtime_error("g / g_lagrange must hold 2^k points");
+    }
+    Params(uint32_t k_, Srs&& g_, Srs&& gl_) : k(k_), n(1ull << k_), g(std::move(g_)), g_lagrange(std::move(gl_)) {
+        if (g.len() != n || g_lagrange.len() != n) throw std::runtime_error("g / g_lagrange must hold 2^k points");
+    }
+    // Params::unsafe_setup (:56-124) on the device for a caller-chosen s: g[i] = [s^i] G (:63-83),
+    // g_lagrange[i] = [(s^n - 1)/n * w^i / (s - w^i)] G (:85-112).  Scalars by prefix product, batch inversion and
+    // element-wise passes on resident vectors; points by one fixed-base multiplication each.
+    static Params unsafe_setup(uint32_t k, const Fr& s, bool precompute = true) {
+        if (k > fr::S) throw std::runtime_error("assert!(k <= Fr::S)");
+        const uint64_t n = 1ull << k;
+        struct Dev {
+            void* p = nullptr;
+            explicit Dev(size_t bytes) { check(b2_dev_alloc(bytes, &p), "b2_dev_alloc"); }
+            ~Dev() { if (p) b2_dev_free(p); }
+        } cst(n * 32), pw(n * 32), den(n * 32);
+        auto fill = [&](const Fr& v) {
+            std::vector<Fr> host(n, v);
+            check(b2_memcpy_h2d(cst.p, host.data(), n * 32), "b2_memcpy_h2d");
+        };
+        auto powers = [&](const Fr& base, void* out) {      // out[i] = base^i
+            fill(base);
+            check(b2_prefix_scan_dev(0, cst.p, n, &fr::ONE, nullptr, out, n, nullptr), "b2_prefix_scan_dev");
+        };
+        powers(s, pw.p);
+        Srs g = Srs::from_scalars_dev(pw.p, n, precompute);
+        Fr root = fr::root_of_unity();
+        for (uint32_t i = k; i < fr::S; i++) root = fr::square(root);
+        powers(root, pw.p);
+        fill(s);
+        check(b2_fr_vec_dev(2, cst.p, pw.p, n, den.p, nullptr), "b2_fr_vec_dev");       // s - w^i
+        check(b2_batch_invert_dev(den.p, n, nullptr), "b2_batch_invert_dev");
+        check(b2_fr_vec_dev(0, pw.p, den.p, n, den.p, nullptr), "b2_fr_vec_dev");       // w^i / (s - w^i)
+        fill(fr::mul(fr::sub(fr::pow_vartime(s, n), fr::ONE), fr::invert(fr::from_u64(n))));
+        check(b2_fr_vec_dev(0, den.p, cst.p, n, den.p, nullptr), "b2_fr_vec_dev");      // * (s^n - 1) / n
+        Srs gl = Srs::from_scalars_dev(den.p, n, precompute);
+        return Params(k, std::move(g), std::move(gl));
     }
     G1 commit(const std::vector<Fr>& poly) const {                 // :129-133
         if (g.len() < poly.size()) throw std::runtime_error("assert!(self.g.len() >= size)");

@@ -53,6 +53,12 @@ int main() {
         gl[i] = mul_gen(scalar);
     }
     Params params(K, g, gl);
+    {   // Params::unsafe_setup on the device gives the same 2 * 2^k points as the loop above
+        Params dev_params = Params::unsafe_setup(K, s);
+        std::vector<G1Affine> dg = dev_params.g.read(), dgl = dev_params.g_lagrange.read();
+        if (std::memcmp(dg.data(), g.data(), n * sizeof(G1Affine)) != 0) { std::printf("FAIL unsafe_setup g\n"); return 1; }
+        if (std::memcmp(dgl.data(), gl.data(), n * sizeof(G1Affine)) != 0) { std::printf("FAIL unsafe_setup g_lagrange\n"); return 1; }
+    }
     std::vector<Fr> a(n);
     for (uint64_t i = 0; i < n; i++) a[i] = fr::from_u64(i);
     std::vector<Fr> b = domain.lagrange_to_coeff(a);

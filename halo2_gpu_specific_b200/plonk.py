@@ -375,6 +375,10 @@ class ArrayBlocks:
         return np.zeros((count, self.domain.n, 4), dtype=np.uint64)
 
     @staticmethod
+    def copy(block: np.ndarray) -> np.ndarray:
+        return block.copy()
+
+    @staticmethod
     def cols(block: np.ndarray) -> list:
         return [block[i] for i in range(block.shape[0])]
 
@@ -661,6 +665,14 @@ class ResidentEngine:
         if count:
             b.upload(host)
         return DevBlock(b.ptr, count, n)
+
+    def copy(self, block: DevBlock) -> DevBlock:
+        import ctypes
+        from ._lib import check, lib
+        out = self.alloc(block.count)
+        if block.count:
+            check(lib().b2_memcpy_d2d(ctypes.c_void_p(out.ptr), ctypes.c_void_p(block.ptr), block.count * block.n * 32))
+        return out
 
     @staticmethod
     def cols(block: DevBlock) -> list:
@@ -1169,7 +1181,9 @@ def multiplicity_tensors(raw, usable: int, m) -> int:
     lo = torch.cumsum(t_count, 0) - t_count                                   # each run's start in that order
     hi = lo + t_count
     live = i_count > 0
-    found = torch.full((n_groups,), -1, dtype=torch.int64, device=dev)
+    # a table value that occurs once is found at its own position whatever the probe sequence; only runs of repeated
+    # table values need the simulation below
+    found = torch.where(live & (t_count == 1), lo, torch.full((n_groups,), -1, dtype=torch.int64, device=dev))
     left = torch.zeros(n_groups, dtype=torch.int64, device=dev)
     right = torch.full((n_groups,), usable, dtype=torch.int64, device=dev)
     size = right - left
@@ -1262,7 +1276,7 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
     if cs.num_instance:
         for c in E.commit_lagrange(instance_values, _fr.NUM_BITS):
             tr.common_point(c)
-    instance_polys = E.put(inst_host.copy())
+    instance_polys = E.copy(instance_values)
     if cs.num_instance:
         E.lagrange_to_coeff(instance_polys)
     lap("instance")
