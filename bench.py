@@ -132,7 +132,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_full = 1 << args.logn
     # calibrate on 2^16, then pick the largest power-of-two sample that keeps the run bounded
-    cal = 1 << 16
+    cal = min(1 << 16, n_full)
     ks = np.zeros((n_full, 4), dtype=np.uint64)
     ks[:, 0] = np.arange(1, n_full + 1, dtype=np.uint64) * np.uint64(0x9E3779B97F4A7C15)
     t0 = time.time()
