@@ -50,16 +50,59 @@ class ConstraintSystem:
     [("Advice"|"Fixed"|"Instance", index)].  degree / blinding_factors are what cs.degree() /
     cs.blinding_factors() return (circuit.rs:1838-1944): computing them needs the front-end's query bookkeeping."""
 
-    def __init__(self, num_fixed: int, num_advice: int, num_instance: int, degree: int, blinding_factors: int = 5,
-                 gates=(), lookups=(), shuffles=(), permutation_columns=(), advice_queries=None, fixed_queries=None,
-                 instance_queries=None):
+    def __init__(self, num_fixed: int, num_advice: int, num_instance: int, degree: Optional[int] = None,
+                 blinding_factors: Optional[int] = 5, gates=(), lookups=(), shuffles=(), permutation_columns=(),
+                 advice_queries=None, fixed_queries=None, instance_queries=None, minimum_degree: Optional[int] = None):
         self.num_fixed, self.num_advice, self.num_instance = num_fixed, num_advice, num_instance
         self.gates = [list(g) for g in gates]
         self.lookups = list(lookups)
         self.shuffles = [list(g) for g in shuffles]
         self.permutation_columns = [tuple(c) for c in permutation_columns]
+        self.minimum_degree = minimum_degree
         self._degree, self._blinding_factors = degree, blinding_factors
         self.advice_queries, self.fixed_queries, self.instance_queries = advice_queries, fixed_queries, instance_queries
+
+    @staticmethod
+    def expression_degree(e) -> int:
+        """Expression::degree (circuit.rs)"""
+        t = e[0]
+        if t == "Constant":
+            return 0
+        if t in ("Fixed", "Advice", "Instance"):
+            return 1
+        if t in ("Negated", "Scaled"):
+            return ConstraintSystem.expression_degree(e[1])
+        if t == "Sum":
+            return max(ConstraintSystem.expression_degree(e[1]), ConstraintSystem.expression_degree(e[2]))
+        if t == "Product":
+            return ConstraintSystem.expression_degree(e[1]) + ConstraintSystem.expression_degree(e[2])
+        raise B2Error(B2_ERR_ARG, f"unknown Expression {e!r}")
+
+    def compute_degree(self) -> int:
+        """ConstraintSystem::degree (circuit.rs:1861-1915): the permutation argument needs 3
+        (permutation.rs:29-62), a logup lookup max(4, 2 + input degree + table degree) (logup.rs:40-60), a shuffle
+        2 + max(input, shuffle degree) (shuffle.rs:52-65), every gate polynomial its own degree; then minimum_degree"""
+        deg = ConstraintSystem.expression_degree
+        degree = 3
+        for lk in self.lookups:
+            inp = max([deg(e) for s in lk["input_expressions_sets"] for i in s for e in i] + [1])
+            tab = max([deg(e) for e in lk["table_expressions"]] + [1])
+            degree = max(degree, 4, 2 + inp + tab)
+        for group in self.shuffles:
+            for a in group:
+                degree = max(degree, 2 + max([deg(e) for e in a["shuffle_expressions"]] + [1]),
+                             2 + max([deg(e) for e in a["input_expressions"]] + [1]))
+        for gate in self.gates:
+            for poly in gate:
+                degree = max(degree, deg(poly))
+        return max(degree, self.minimum_degree or 1)
+
+    def compute_blinding_factors(self) -> int:
+        """ConstraintSystem::blinding_factors (circuit.rs:1919-1944): max(3, most queries of one advice column) + 2"""
+        per_column: Dict[int, int] = {}
+        for col, _ in self.queries()["Advice"]:
+            per_column[col] = per_column.get(col, 0) + 1
+        return max(3, max(per_column.values(), default=1)) + 2
 
     @classmethod
     def like(cls, other) -> "ConstraintSystem":
@@ -70,9 +113,13 @@ class ConstraintSystem:
                    getattr(other, "instance_queries", None))
 
     def degree(self) -> int:
+        if self._degree is None:
+            self._degree = self.compute_degree()
         return self._degree
 
     def blinding_factors(self) -> int:
+        if self._blinding_factors is None:
+            self._blinding_factors = self.compute_blinding_factors()
         return self._blinding_factors
 
     def queries(self) -> Dict[str, List[Tuple[int, int]]]:

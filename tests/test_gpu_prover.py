@@ -100,7 +100,7 @@ def test_commit_batch_against_g(gpu):
         params.free()
 
 
-@pytest.mark.parametrize("k", [1, 6, 11])
+@pytest.mark.parametrize("k", [1, 6, 11, 15])
 def test_unsafe_setup_matches_oracle(gpu, k):
     """Params::unsafe_setup on the device (poly/commitment.rs:56-124): every point of g and g_lagrange"""
     oparams = PR.Params(k, S_TOXIC)

@@ -343,3 +343,23 @@ def test_degenerate_shapes_prove_and_verify():
         bad[1][3] = (bad[1][3] + 1) % R
         if not with_lookup:
             assert not PR.verify_proof(oparams, opk.vk, [], PR.create_proof(oparams, opk, bad, [], HP.SeededRng(2)))
+
+
+def test_degree_and_blinding_factors_rules():
+    """ConstraintSystem::degree / blinding_factors (circuit.rs:1861-1944) computed from the constraint system"""
+    args = bench_circuit.constraint_system_args()
+    args.update(degree=None, blinding_factors=None, minimum_degree=5)          # benches/plonk.rs: set_minimum_degree(5)
+    cs = HP.ConstraintSystem(**args)
+    assert cs.compute_degree() == 5 and cs.degree() == 5 and cs.blinding_factors() == 5
+    args.update(minimum_degree=None)
+    assert HP.ConstraintSystem(**args).degree() == 3                             # gate a*b*sm: degree 3
+    fx = fxm.build(k=5, seed=3)
+    like = HP.ConstraintSystem.like(fx["cs"])
+    assert like.compute_degree() == 4                                            # logup: max(4, 2 + 1 + 1)
+    assert like.compute_blinding_factors() == 5                                  # advice 0 and 2 are queried twice
+    import zkwasm_shape_circuit as zk
+    z = HP.ConstraintSystem(**zk.constraint_system_args(extra_gates=30))
+    assert z.compute_degree() == 4 and z.degree() == 5                           # extras have degree 4; the shape fixes 5
+    A = ("Advice", 0, 0)
+    deg = HP.ConstraintSystem.expression_degree
+    assert deg(("Product", ("Sum", A, ("Constant", 1)), ("Scaled", ("Negated", A), 3))) == 2 and deg(("Constant", 7)) == 0
