@@ -603,7 +603,12 @@ def bench_create_proof(args, _lib, h2):
                 out[kind] = {"value": statistics.median(times), "unit": "s", "all_s": times,
                              "phases_s": {a: statistics.median(b) for a, b in phases.items()},
                              "gpu_launches": launches, "proof_bytes": nbytes}
+            cpu = None
+            if not args.no_cpu:
+                cpu = _cpu_proof_schedule(params, pk, advice, k)
             res = out["resident"]
+            if cpu:
+                res["cpu_baseline"] = cpu
             res.update({
                 "metric": f"create_proof wall time, benches/plonk.rs circuit at k={k} (3 advice, 4 fixed, 1 permutation "
                           f"set, degree 5), GWC multiopen",
@@ -620,6 +625,57 @@ def bench_create_proof(args, _lib, h2):
     except Exception as e:                                # noqa: BLE001 -- reported, never fatal for the MSM line
         import traceback
         return {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+
+
+def _cpu_proof_schedule(params, pk, advice, k):
+    """cpu_baseline of the create_proof section: the MSM / NTT / quotient-row calls that the SAME proof makes on the
+    reference's CPU path (plonk/prover.rs without the cuda feature), issued on the C restatement (oracle/cpu_ref.c) with
+    all host cores: 3 advice + 1 z commitments against g_lagrange, 1 random + 4 h-piece + 2 opening commitments against
+    g, 4 inverse transforms of size 2^k, 4 coset extensions (advice and z; the proving key's cosets exist since keygen),
+    the row loop of evaluate_h over 2^(k+2) rows with this circuit's program, extended_to_coeff.  The field arithmetic
+    of the evaluation phase and of the multiopen folds is not included: a lower bound for the CPU prover."""
+    from halo2_gpu_specific_b200 import _fr
+    from oracle import cref
+    cores = os.cpu_count() or 1
+    dom = pk.vk.domain
+    n = 1 << k
+    g, gl = params.g.read(), params.g_lagrange.read()
+    rnd = cref.random_fr_mont(n, 0xB2000092)
+    enc = lambda v: np.stack([_fr.to_mont(x) for x in v])  # noqa: E731
+    f = pk.ev.flat_h_program(1, [], 0)
+    fixed_ext = [cref.coeff_to_extended(p, k, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega, cores)
+                 for p in pk.fixed_polys]                                  # keygen-time data, untimed
+    sigma_ext = [cref.coeff_to_extended(p, k, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega, cores)
+                 for p in pk.sigma_polys]
+    challenges = [(i + 2) * 0x123456789ABCDEF % _fr.R_MOD for i in range(f["n_challenges"])]
+    t0 = time.perf_counter()
+    cols = [np.ascontiguousarray(advice[i]) for i in range(advice.shape[0])] + [rnd]
+    for c in cols:
+        cref.best_multiexp(c, gl, cores)
+    for _ in range(7):
+        cref.best_multiexp(rnd, g, cores)
+    t_msm = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    coeffs = [cref.ifft(c, dom.omega_inv, dom.ifft_divisor, k, cores) for c in cols]
+    ext = [cref.coeff_to_extended(c, k, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega, cores)
+           for c in coeffs]
+    t_ntt = time.perf_counter() - t1
+    t2 = time.perf_counter()
+    aux = [pk.l0, pk.l_last, pk.l_active_row] + sigma_ext + [ext[3]]
+    h = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"], fixed_ext, ext[:3], [], aux,
+                           enc(challenges), dom.extended_k, 1 << (dom.extended_k - k), x0=_fr.to_mont(1),
+                           step=dom.extended_omega, threads=cores)
+    t_rows = time.perf_counter() - t2
+    t3 = time.perf_counter()
+    cref.extended_to_coeff(h, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega_inv,
+                           dom.extended_ifft_divisor, cores)
+    t_ntt += time.perf_counter() - t3
+    total = time.perf_counter() - t0
+    return {"value": total, "unit": "s", "cores": cores, "kind": "port",
+            "sample": "the 11 MSMs, 4 iNTTs, 4 coset extensions, the evaluate_h row loop and extended_to_coeff of ONE "
+                      "proof of the same circuit on oracle/cpu_ref.c (a lower bound: evaluation-phase and multiopen "
+                      "field arithmetic, transcript and witness handling not included)",
+            "split_s": {"msm": t_msm, "ntt": t_ntt, "evaluate_h_rows": t_rows}}
 
 
 def bench_create_proof_zkwasm(args, _lib, h2):
