@@ -356,11 +356,12 @@ class OsRng:
 # device buffers, the host-API engine plain numpy arrays.  The operations:
 #   put / alloc / cols / write_rows                      data movement
 #   put_and_commit_lagrange, commit_lagrange, commit_lagrange_and_ifft, commit, lagrange_to_coeff
-#   compress_canonical, put_canonical                    logup: compressed expressions out, multiplicities in
+#   multiplicity_block                                   logup: compressed inputs / table -> the m(X) columns
 #   permutation_z, logup_z, shuffle_z                    z columns written into columns of a block
 #   random_poly, evaluate_h_blocks                       vanishing argument
-#   eval_polynomial, poly_combine, sub_constant, kate_division_padded   evaluation phase and multiopen
-#   key_blocks, release
+#   eval_polynomial, poly_combine, sub_constant, kate_division_padded   evaluation phase and multiopen (GWC)
+#   sub_low_degree, scale, sub_cols                      what SHPLONK adds
+#   key_blocks, copy, stack, release, free
 def _mix64(x: np.ndarray) -> np.ndarray:
     """splitmix64's output function of x + golden (uint64 arithmetic wraps)"""
     x = x + np.uint64(0x9E3779B97F4A7C15)
@@ -832,18 +833,6 @@ class ResidentEngine:
         ptrs = lambda b: [b.ptr + i * b.n * 32 for i in range(b.count)]      # noqa: E731
         return _Columns.resident(ptrs(key["fixed_values"]), ptrs(advice), ptrs(instance), self.domain.n)
 
-    def compress_canonical(self, expression_lists, advice, fixed, instance, theta: int, pk=None) -> np.ndarray:
-        from .grand_product import _Columns, compress_expressions_dev
-        n = self.domain.n
-        ptrs = lambda b: [b.ptr + i * b.n * 32 for i in range(b.count)]      # noqa: E731
-        cols = _Columns.resident(ptrs(fixed), ptrs(advice), ptrs(instance), n)
-        out = self.alloc(len(expression_lists))
-        compress_expressions_dev(self.domain, expression_lists, cols, theta, out.ptr)
-        one = self._const_column("raw_one", _RAW_ONE)
-        for i in range(out.count):                                            # Montgomery -> canonical
-            self._fr_vec(0, out.ptr + i * n * 32, one, n, out.ptr + i * n * 32)
-        return self.get(out)
-
     def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds):
         """logup `compress` (logup/prover.rs:70-256) for every lookup without leaving the device: the compressed
         inputs and table are produced by the expression kernel, sorted and matched there (logup_multiplicity_device),
@@ -870,14 +859,6 @@ class ResidentEngine:
             self._fr_vec(0, m_col.ptr, r2, n, m_col.ptr)                       # counts (canonical) -> Montgomery
             self.write_rows(m_col, usable, _mont_vec(blinds[li]))              # logup/prover.rs:232-236
         return ms, m_bits
-
-    def put_canonical(self, canonical: np.ndarray) -> DevBlock:
-        n = self.domain.n
-        block = self.put(canonical)
-        r2 = self._const_column("raw_r2", _RAW_R2)
-        for i in range(block.count):                                          # canonical -> Montgomery
-            self._fr_vec(0, block.ptr + i * n * 32, r2, n, block.ptr + i * n * 32)
-        return block
 
     # -- z columns
     def permutation_z(self, cs, pk, advice, instance, beta, gamma, blinds, out_cols) -> None:
