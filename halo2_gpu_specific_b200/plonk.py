@@ -427,6 +427,18 @@ class ArrayBlocks:
         return block.copy()
 
     @staticmethod
+    def block_count(block: np.ndarray) -> int:
+        return block.shape[0]
+
+    @staticmethod
+    def sub_block(block: np.ndarray, lo: int, hi: int) -> np.ndarray:
+        return block[lo:hi]
+
+    def commit_columns_with_bound(self, block: np.ndarray, max_bits: Optional[int]) -> List[Point]:
+        """commit_lagrange_with_bound per column; max_bits None = find_max_scalar_bits per column first"""
+        return self.put_and_commit_lagrange(block, max_bits)[1] if block.shape[0] else []
+
+    @staticmethod
     def cols(block: np.ndarray) -> list:
         return [block[i] for i in range(block.shape[0])]
 
@@ -725,6 +737,19 @@ class ResidentEngine:
     @staticmethod
     def cols(block: DevBlock) -> list:
         return [block.col(i) for i in range(block.count)]
+
+    @staticmethod
+    def block_count(block: DevBlock) -> int:
+        return block.count
+
+    @staticmethod
+    def sub_block(block: DevBlock, lo: int, hi: int) -> DevBlock:
+        return DevBlock(block.ptr + lo * block.n * 32, hi - lo, block.n)
+
+    def commit_columns_with_bound(self, block: DevBlock, max_bits: Optional[int]) -> List[Point]:
+        """commit_lagrange_with_bound per resident column; max_bits None = the bound of each column is found on
+        the device first (B2_MAX_BITS_AUTO)"""
+        return self._commit(self.params.g_lagrange, 0, block, 0xFFFFFFFF if max_bits is None else max_bits, False)
 
     @staticmethod
     def write_rows(col: DevBlock, row: int, values: np.ndarray) -> None:

@@ -286,3 +286,36 @@ def test_shplonk_zkwasm_shape_k14(gpu):
         print(f"shplonk zkwasm shape k={k} create_proof {sum(timings.values()):.4f} s, multiopen {timings['multiopen']:.4f} s")
     finally:
         params.free()
+
+
+def test_sharded_engine_on_one_rank(gpu):
+    """prover_sharded.ShardedResidentEngine without a process group (world = 1): same bytes as the plain engine; runs
+    the on-device bound scan (B2_MAX_BITS_AUTO with resident columns), sub-blocks and the two-range transform path"""
+    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngine
+    k = 6
+    fx = fxm.build(k=k, seed=17)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, S_TOXIC)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+    params, pk = engine_side(k, oparams, cs, np.stack([enc(c) for c in fx["fixed"]]),
+                             np.array(fx["mapping"], dtype=np.int64), opk.vk.transcript_repr)
+    try:
+        inst = [fx["instance"][0][:4]]
+        adv = np.ascontiguousarray(np.stack([enc(c) for c in fx["advice"]]))
+        want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(5))
+        eng = ShardedResidentEngine(params, pk.vk.domain)
+        got = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(5), engine=eng)
+        # a forced split (as rank 1 of 3 would see it) still transforms every z column on this rank
+        eng._share = lambda count: (count // 3, count - count // 3)
+        eng._gather = lambda local: local
+        z = eng.put(np.ascontiguousarray(np.stack([enc(p) for p in fx["perm_z"]] + [enc(fx["shuffle_z"][0])])))
+        pts = eng.commit_lagrange_and_ifft(z)
+        assert len(pts) == 1
+        d = fx["domain"]
+        want_coeffs = [d.lagrange_to_coeff(p) for p in fx["perm_z"]] + [d.lagrange_to_coeff(fx["shuffle_z"][0])]
+        assert np.array_equal(eng.get(z), np.stack([enc(c) for c in want_coeffs]))
+        eng.free()
+        assert got == want
+    finally:
+        params.free()

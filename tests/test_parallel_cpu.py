@@ -146,3 +146,77 @@ def test_coset_transform_shares_cover_every_polynomial_once():
                 assert len(cosets) == 1 and all(len(parallel.quotient_tasks(nc, n, world, r)) == 1 for r, _, _ in shares)
             else:
                 assert len(shares) == 1
+
+
+def _prover_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch.distributed as dist
+    import plonk_fixture as fxm
+    from halo2_gpu_specific_b200 import plonk as HP
+    from halo2_gpu_specific_b200.prover_sharded import ShardedCommits
+    from oracle import bn254 as o
+    from oracle import prover as PR
+    from oracle_engine import OracleEngine
+
+    class ShardedOracleEngine(ShardedCommits, OracleEngine):
+        pass
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    k = 5
+    fx = fxm.build(k=k, seed=11)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, 0x2B200B200B200B2001)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+
+    class HostParams:
+        pass
+    hp = HostParams()
+    hp.k, hp.n = k, 1 << k
+    eng = ShardedOracleEngine(oparams, opk.vk.domain, ocs)
+    calls = {"msm": 0}
+    inner = eng._msm
+
+    def counting(col, bases):
+        calls["msm"] += 1
+        return inner(col, bases)
+    eng._msm = counting
+    pk = HP.keygen(hp, cs, np.stack([o.fr_encode(c) for c in fx["fixed"]]), np.array(fx["mapping"], dtype=np.int64),
+                   engine=OracleEngine(oparams, opk.vk.domain, ocs), transcript_repr=opk.vk.transcript_repr)
+    adv = np.ascontiguousarray(np.stack([o.fr_encode(c) for c in fx["advice"]]))
+    inst = [fx["instance"][0][:4]]
+    out = {}
+    for gwc in (True, False):
+        calls["msm"] = 0
+        out[gwc] = (HP.create_proof(hp, pk, adv.copy(), inst, HP.SeededRng(3), engine=eng, use_gwc=gwc), calls["msm"])
+    np.save(os.path.join(outdir, f"proof_r{rank}.npy"), np.frombuffer(out[True][0] + out[False][0], dtype=np.uint8))
+    np.save(os.path.join(outdir, f"msms_r{rank}.npy"), np.array([out[True][1], out[False][1]]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_commit_prover_matches_single_process(tmp_path, world):
+    """prover_sharded.ShardedCommits over the oracle-backed engine, gloo: every rank produces the single-process
+    proof bytes (GWC and SHPLONK) while committing only its share of the columns"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import plonk_fixture as fxm
+    from halo2_gpu_specific_b200.plonk import SeededRng
+    from oracle import prover as PR
+    port = _free_port()
+    mp.spawn(_prover_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    fx = fxm.build(k=5, seed=11)
+    oparams = PR.Params(5, 0x2B200B200B200B2001)
+    opk = PR.keygen(oparams, fx["cs"], fx["fixed"], fx["mapping"])
+    inst = [fx["instance"][0][:4]]
+    want = PR.create_proof(oparams, opk, fx["advice"], inst, SeededRng(3)) + \
+        PR.create_proof(oparams, opk, fx["advice"], inst, SeededRng(3), use_gwc=False)
+    msms = []
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"proof_r{r}.npy")).tobytes()
+        assert got == want, f"rank {r}"
+        msms.append(np.load(os.path.join(str(tmp_path), f"msms_r{r}.npy")))
+    total = np.sum(msms, axis=0)
+    # GWC: 1 instance + 9 advice + 2 m + (2 + 3 + 1) z + 1 random + 4 h + 4 openings = 27 MSMs, divided, none duplicated
+    assert total[0] == 27 and max(m[0] for m in msms) <= 27 // world + 7
