@@ -1,0 +1,75 @@
+#!/usr/bin/env python
+"""N-GPU check of prover_sharded.ShardedResidentEngine (one process per GPU, NCCL):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \\
+        tools/sharded_proof_check.py --k 14
+
+Every rank proves the benches/plonk.rs circuit with its commitments divided over the ranks; rank 0 also proves it alone
+and the bytes must agree.  Prints one JSON line on rank 0."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--k", type=int, default=14)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    import halo2_gpu_specific_b200 as h2
+    from halo2_gpu_specific_b200 import _lib
+    from halo2_gpu_specific_b200 import plonk as HP
+    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngine
+    import plonk_bench_circuit as bc
+    _lib.require_gpu()
+    _lib.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    params = h2.Params.unsafe_setup(a.k, 0x2B200B200B200B200B200B200B200B2001)
+    cs = HP.ConstraintSystem(**bc.constraint_system_args())
+    fixed, advice, mapping = bc.build(a.k)
+    pk = HP.keygen(params, cs, fixed, mapping)
+    eng = ShardedResidentEngine(params, pk.vk.domain)
+    HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(0), engine=eng)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    proof = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(1), engine=eng)
+    dt = time.perf_counter() - t0
+    eng.free()
+    ok = True
+    alone_s = None
+    if rank == 0:
+        plain = HP.ResidentEngine(params, pk.vk.domain)
+        HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(0), engine=plain)
+        t0 = time.perf_counter()
+        alone = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(1), engine=plain)
+        alone_s = time.perf_counter() - t0
+        plain.free()
+        ok = alone == proof
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, proof)
+        ok = ok and all(g == proof for g in gathered)
+    if rank == 0:
+        print(json.dumps({"check": "sharded-commit create_proof, benches/plonk.rs circuit", "k": a.k, "n_gpus": world,
+                          "bytes_equal_on_all_ranks_and_to_single_gpu": bool(ok), "sharded_s": dt, "single_gpu_s": alone_s,
+                          "backend": "nccl" if world > 1 else "none"}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    params.free()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
