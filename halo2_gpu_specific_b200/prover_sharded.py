@@ -11,8 +11,11 @@ all-gathered so that each rank can hash all of them.  The witness itself is uplo
 link and stays resident there, because the z columns and evaluate_h need all of it on every rank.
 
 Status: the sharding and gather logic is validated on CPU with gloo (tests/test_parallel_cpu.py: proof bytes of a
-2- and 3-rank run equal the single-process oracle proof); the NCCL run on B200s and its measurement are round-2 work,
-as is splitting evaluate_h by cosets inside the prover (parallel.sharded_evaluate_h has that split for host inputs).
+2- and 3-rank run equal the single-process oracle proof) and on two B200s over NCCL (tools/sharded_proof_check.py,
+profiles/r1_sharded_prover_2gpu.json: every rank's bytes equal the single-GPU proof).  At the size that fitted the
+remaining GPU budget (k = 16, an 12 ms proof) the pickled all-gathers cost more than the divided MSMs save; measuring
+it at zkWasm scale, and splitting evaluate_h by cosets inside the prover (parallel.sharded_evaluate_h has that split
+for host inputs), are round-2 work.
 """
 from __future__ import annotations
 
