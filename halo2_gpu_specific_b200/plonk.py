@@ -920,6 +920,7 @@ class ResidentEngine:
         if key is None:
             key = {name: self.put(getattr(pk, name), keep=True)
                    for name in ("fixed_values", "fixed_polys", "sigmas", "sigma_polys")}
+            key["pk"] = pk          # keeps the key object alive, so that its id cannot be reused while cached
             self._keys[id(pk)] = key
         return key
 
