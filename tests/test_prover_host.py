@@ -363,3 +363,61 @@ def test_degree_and_blinding_factors_rules():
     A = ("Advice", 0, 0)
     deg = HP.ConstraintSystem.expression_degree
     assert deg(("Product", ("Sum", A, ("Constant", 1)), ("Scaled", ("Negated", A), 3))) == 2 and deg(("Constant", 7)) == 0
+
+
+def test_buffer_pool_recycles_and_trims(monkeypatch):
+    """evaluation.BufferPool / DeviceBuffer: exact-size reuse, no allocation in the steady state, trim + retry when the
+    device is out of memory with blocks parked in the pool (driver calls replaced by a fake allocator)"""
+    import ctypes
+    from halo2_gpu_specific_b200 import evaluation as E
+
+    class FakeLib:
+        def __init__(self):
+            self.next, self.live, self.allocs, self.frees, self.capacity = 0x1000, {}, 0, 0, 10 * 32 * 100
+
+        def b2_dev_alloc(self, nbytes, out):
+            if sum(self.live.values()) + nbytes > self.capacity:
+                return -3
+            self.next += 0x10000
+            self.live[self.next] = nbytes
+            ctypes.cast(out, ctypes.POINTER(ctypes.c_void_p))[0] = self.next
+            self.allocs += 1
+            return 0
+
+        def b2_dev_free(self, p):
+            del self.live[p.value]
+            self.frees += 1
+            return 0
+
+        def b2_last_error(self):
+            return b"out of memory"
+
+    fake = FakeLib()
+    monkeypatch.setattr(E, "lib", lambda: fake)
+    from halo2_gpu_specific_b200 import _lib
+    monkeypatch.setattr(_lib, "lib", lambda: fake)
+    pool = E.BufferPool()
+    prev = E.set_active_pool(pool)
+    try:
+        a, b = E.DeviceBuffer(100), E.DeviceBuffer(200)
+        pa, pb = a.ptr, b.ptr
+        a.free(); b.free()
+        assert fake.frees == 0 and pool.cached_bytes == 300 * 32
+        c = E.DeviceBuffer(200)                      # same size: recycled, no driver call
+        assert c.ptr == pb and fake.allocs == 2
+        d = E.DeviceBuffer(100)
+        assert d.ptr == pa and pool.cached_bytes == 0
+        c.free(); d.free()
+        big = E.DeviceBuffer(800)                    # does not fit while 300 elements are parked: trim, retry
+        assert fake.frees == 2 and pool.cached_bytes == 0 and fake.live == {big.ptr: 800 * 32}
+        big.free()
+        with pytest.raises(HP.B2Error):
+            E.DeviceBuffer(2000)                     # genuinely too large
+    finally:
+        E.set_active_pool(prev)
+    e = E.DeviceBuffer(10)                           # no pool: plain alloc / free
+    n = fake.frees
+    e.free()
+    assert fake.frees == n + 1
+    pool.trim()
+    assert not fake.live
