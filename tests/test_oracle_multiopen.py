@@ -106,3 +106,51 @@ def test_multiopen(use_gwc):
         assert not _verify(params, bytes(swapped), vq, use_gwc)
     except (PR.TranscriptError, PR.VerifyError):
         pass
+
+
+def test_intermediate_sets():
+    """shplonk.rs:204-336 test_intermediate_sets: 100 random query lists; every evaluation comes back under its
+    (commitment, point); the grouping does not depend on the point values; the sets cover exactly the queries;
+    shuffling the queries changes neither property"""
+    rng = random.Random(3)
+    for _ in range(100):
+        rotations = [(rng.randrange(R), rot) for rot in range(-4, 5)]            # (point, rotation)
+        rotation_of = {p: r for p, r in rotations}
+        evals = {(c, p): rng.randrange(R) for p, _ in rotations for c in range(8)}
+        queries_0 = []
+        for _q in range(16):
+            c = rng.randrange(8)
+            p, r = rng.choice(rotations)
+            queries_0.append((r, p, c, evals[(c, p)]))
+
+        def sets_of(queries):
+            table = {(q[2], q[0]): q[3] for q in queries}
+            return PR.shplonk_intermediate_sets(queries, lambda q: q[2], lambda k, r: table[(k, r)])[0]
+
+        def check_evals(rotation_sets):
+            for commitments, points in rotation_sets:
+                for com, evs in commitments:
+                    for e, p in zip(evs, points):
+                        assert e == evals[(com, p)]
+
+        def make_queries(rotation_sets):
+            out = []
+            for commitments, points in rotation_sets:
+                for com, evs in commitments:
+                    for p, e in zip(points, evs):
+                        out.append((rotation_of[p], p, com, e))
+            return out
+
+        sets_0 = sets_of(queries_0)
+        check_evals(sets_0)
+        e = rng.randrange(R)
+        moved = [(q[0], e * (q[0] % R) % R, q[2], q[3]) for q in queries_0]         # change points, keep rotations
+        sets_1 = sets_of(moved)
+        assert [[c for c in cs] for cs, _ in sets_0] == [[c for c in cs] for cs, _ in sets_1]
+        rebuilt = make_queries(sets_0)
+        assert set(rebuilt) == set(queries_0)
+        shuffled = list(queries_0)
+        rng.shuffle(shuffled)
+        sets_2 = sets_of(shuffled)
+        check_evals(sets_2)
+        assert set(make_queries(sets_2)) == set(queries_0)
