@@ -421,3 +421,28 @@ def test_buffer_pool_recycles_and_trims(monkeypatch):
     assert fake.frees == n + 1
     pool.trim()
     assert not fake.live
+
+
+def test_small_host_helpers_match_oracle():
+    """lagrange_interpolate (arithmetic.rs:848-906), the vanishing streams' generator and canonical_max_bits against
+    the oracle's independent restatements"""
+    rng = random.Random(12)
+    for m in range(1, 6):
+        pts = rng.sample(range(1, 1 << 60), m)
+        evs = [rng.randrange(R) for _ in range(m)]
+        got = HP.lagrange_interpolate(pts, evs)
+        assert got == o.lagrange_interpolate(pts, evs)
+        for p, e in zip(pts, evs):
+            assert o.eval_polynomial(got, p) == e
+    seed = 0xDEADBEEFCAFEF00D
+    a, u, b, v = HP.vanishing_streams(seed, 16)
+    word = lambda j: PR._mix64(seed ^ PR._mix64(j))                                 # noqa: E731
+    for i in (0, 1, 7, 15):
+        limbs = [word(10 * i + l) for l in range(4)]
+        limbs[3] &= (1 << 61) - 1
+        assert [int(x) for x in a[i]] == limbs
+        assert int(u[i]) == word(10 * i + 4) and int(v[i]) == word(10 * i + 9)
+        assert int(b[i][0]) == word(10 * i + 5)
+    canon = np.array([o._to_limbs(v) for v in (0, 1, 255, 1 << 64, (1 << 130) + 5)], dtype=np.uint64)
+    assert HP.canonical_max_bits(canon) == 131 and HP.canonical_max_bits(canon[:3]) == 8
+    assert HP.canonical_max_bits(canon[:1]) == 0 and HP.canonical_max_bits(np.zeros((0, 4), np.uint64)) == 0
