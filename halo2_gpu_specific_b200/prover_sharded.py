@@ -14,8 +14,8 @@ Status: the sharding and gather logic is validated on CPU with gloo (tests/test_
 2- and 3-rank run equal the single-process oracle proof) and on two B200s over NCCL (tools/sharded_proof_check.py,
 profiles/r1_sharded_prover_2gpu.json: every rank's bytes equal the single-GPU proof).  At the size that fitted the
 remaining GPU budget (k = 16, an 12 ms proof) the pickled all-gathers cost more than the divided MSMs save; measuring
-it at zkWasm scale, and splitting evaluate_h by cosets inside the prover (parallel.sharded_evaluate_h has that split
-for host inputs), are round-2 work.
+it at zkWasm scale is round-2 work, and so is running the coset split of evaluate_h inside the prover on GPUs
+(`ShardedQuotient` below: its division logic is covered on CPU with gloo, its device methods have not run yet).
 """
 from __future__ import annotations
 
@@ -99,6 +99,100 @@ class ShardedCommits:
         return block, self._gather(pts)
 
 
+class ShardedQuotient:
+    """Mixin: evaluate_h divided over the ranks by cosets of the extended domain (a rotation never
+    leaves its coset, so cosets exchange nothing).  Rank r evaluates cosets r, r + world, ... into a zeroed extended
+    buffer; the buffers are summed across ranks (an integer all-reduce of disjoint supports: every row is written by
+    exactly one rank) and every rank brings the sum back to the h(X) pieces.  The engine supplies
+    evaluate_h_cosets / all_reduce_rows / h_pieces."""
+
+    def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta):
+        rank, world = parallel.world()
+        if world == 1:
+            return super().evaluate_h_blocks(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                                             y, beta, gamma, theta)
+        dm = self.domain
+        n_cosets = 1 << (dm.extended_k - dm.k)
+        mine = [c for c in range(n_cosets) if c % world == rank]
+        hext = self.evaluate_h_cosets(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                                      y, beta, gamma, theta, mine)
+        self.all_reduce_rows(hext)
+        return self.h_pieces(hext)
+
+
 class ShardedResidentEngine(ShardedCommits, ResidentEngine):
     """ResidentEngine whose commitments are shared out over the ranks (one process per GPU; call
     torch.cuda.set_device / _lib.set_device(local_rank) and init_process_group("nccl") first)"""
+
+
+class ShardedResidentEngineQ(ShardedQuotient, ShardedCommits, ResidentEngine):
+    """+ evaluate_h divided by cosets.  NOT YET RUN ON GPUS: the three device methods below restate
+    ResidentEngine.evaluate_h_blocks with a coset subset, a zeroed output and an NCCL all-reduce; the division logic
+    itself is covered on CPU (tests/test_parallel_cpu.py) through the test double."""
+
+    def evaluate_h_cosets(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta, cosets):
+        from .evaluation import coeff_to_coset_dev
+        from .plonk import DELTA, DevBlock, R
+        dm = self.domain
+        n = dm.n
+        nc = 1 << (dm.extended_k - dm.k)
+        key_cosets = self._key_cosets(pk)
+        F, S = pk.fixed_polys.shape[0], pk.sigma_polys.shape[0]
+        prog = pk.ev.program(n_perm, list(lookup_z_counts), n_shuffles)
+        challenges = [beta % R, gamma % R, theta % R, y % R]
+        d = beta * dm._zeta % R
+        for _ in range(S):
+            challenges.append(d)
+            d = d * DELTA % R
+        witness = [b for b in (advice, instance, z_block, m_block) if b.count]
+        cos = {id(b): self.alloc(b.count) for b in witness}
+        hext = DevBlock(self._buffer(dm.extended_len()).ptr, 1, dm.extended_len())
+        self._fr_vec(2, hext.ptr, hext.ptr, dm.extended_len(), hext.ptr)          # x - x = 0: a zeroed buffer
+        ptrs = lambda b: [cos[id(b)].ptr + i * n * 32 for i in range(b.count)] if b.count else []     # noqa: E731
+        for c in cosets:
+            g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
+            for b in witness:
+                coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
+            kc = key_cosets[c]
+            kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
+            zp, mp = ptrs(z_block), ptrs(m_block)
+            aux = kp[F + S:F + S + 3] + kp[F:F + S] + zp[:n_perm]
+            pos = n_perm
+            for li, cnt in enumerate(lookup_z_counts):
+                aux += zp[pos:pos + cnt] + [mp[li]]
+                pos += cnt
+            aux += zp[pos:pos + n_shuffles]
+            prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
+                      x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
+                      out_stride=nc, out_offset=c)
+        return hext
+
+    def all_reduce_rows(self, hext) -> None:
+        import torch
+        import torch.distributed as dist
+        from ._lib import check, lib
+        from .plonk import _DevArray
+        check(lib().b2_synchronize())
+        t = torch.as_tensor(_DevArray(hext.ptr, (hext.n, 4)), device=torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+
+    def h_pieces(self, hext):
+        import ctypes
+        import numpy as np
+        from ._lib import NttDesc, check, lib
+        dm = self.domain
+        pieces = dm.quotient_poly_degree
+        hcoef = self.alloc(pieces)
+        z = np.concatenate([dm.g_coset_inv, dm.g_coset])
+        t = NttDesc()
+        t.log_n, t.location = dm.extended_k, 1
+        t.omega, t.divisor = dm.extended_omega_inv.ctypes.data, dm.extended_ifft_divisor.ctypes.data
+        t.coset_out = z.ctypes.data
+        t.n_in = t.in_stride = dm.extended_len()
+        t.n_out = t.out_stride = dm.n * pieces
+        t.columns, t.in_, t.out = 1, hext.ptr, hcoef.ptr
+        check(lib().b2_ntt_exec(ctypes.byref(t)))
+        return hcoef

@@ -133,3 +133,39 @@ class OracleEngine(ArrayBlocks):
 
     def kate_division(self, poly, z):
         return enc(o.kate_division(dec(poly), z))
+
+
+class CosetQuotientDouble:
+    """evaluate_h_cosets / all_reduce_rows / h_pieces for the oracle-backed engine (what prover_sharded.ShardedQuotient
+    asks of an engine): the oracle evaluates the whole extended domain, rows of cosets this rank does not own are
+    zeroed, the sum over ranks goes through torch.distributed on the host (gloo)"""
+
+    def evaluate_h_cosets(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta, cosets):
+        d = self.d
+        ext = lambda p: d.coeff_to_extended(dec(p))                                 # noqa: E731
+        lookups, pos = [], n_perm
+        for li, cnt in enumerate(lookup_z_counts):
+            lookups.append({"z_cosets": [ext(z_block[pos + i]) for i in range(cnt)], "m_coset": ext(m_block[li])})
+            pos += cnt
+        h = P.evaluate_h(self.ev, self.cs, d, [ext(p) for p in pk.fixed_polys], [ext(p) for p in advice],
+                         [ext(p) for p in instance], dec(pk.l0), dec(pk.l_last), dec(pk.l_active_row),
+                         [ext(p) for p in pk.sigma_polys], y, beta, gamma, theta, lookups,
+                         [ext(z_block[pos + i]) for i in range(n_shuffles)], [ext(z_block[i]) for i in range(n_perm)])
+        h = d.divide_by_vanishing_poly(h)
+        nc = 1 << (d.extended_k - d.k)
+        own = set(cosets)
+        return enc([v if (i % nc) in own else 0 for i, v in enumerate(h)])
+
+    def all_reduce_rows(self, hext):
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(hext.view(np.int64))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def h_pieces(self, hext):
+        d = self.d
+        coeffs = d.extended_to_coeff(dec(hext))
+        n = d.n
+        pieces = len(coeffs) // n
+        return np.ascontiguousarray(enc(coeffs[:pieces * n])).reshape(pieces, n, 4)

@@ -154,12 +154,12 @@ def _prover_worker(rank, world, port, outdir):
     import torch.distributed as dist
     import plonk_fixture as fxm
     from halo2_gpu_specific_b200 import plonk as HP
-    from halo2_gpu_specific_b200.prover_sharded import ShardedCommits
+    from halo2_gpu_specific_b200.prover_sharded import ShardedCommits, ShardedQuotient
     from oracle import bn254 as o
     from oracle import prover as PR
-    from oracle_engine import OracleEngine
+    from oracle_engine import CosetQuotientDouble, OracleEngine
 
-    class ShardedOracleEngine(ShardedCommits, OracleEngine):
+    class ShardedOracleEngine(ShardedQuotient, ShardedCommits, CosetQuotientDouble, OracleEngine):
         pass
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
@@ -198,8 +198,9 @@ def _prover_worker(rank, world, port, outdir):
 
 @pytest.mark.parametrize("world", [2, 3])
 def test_sharded_commit_prover_matches_single_process(tmp_path, world):
-    """prover_sharded.ShardedCommits over the oracle-backed engine, gloo: every rank produces the single-process
-    proof bytes (GWC and SHPLONK) while committing only its share of the columns"""
+    """prover_sharded.ShardedCommits + ShardedQuotient over the oracle-backed engine, gloo: every rank produces the
+    single-process proof bytes (GWC and SHPLONK) while committing only its share of the columns and contributing only
+    its cosets of the extended domain to h"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import plonk_fixture as fxm
     from halo2_gpu_specific_b200.plonk import SeededRng
