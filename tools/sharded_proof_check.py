@@ -19,6 +19,10 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--k", type=int, default=14)
+    ap.add_argument("--circuit", default="bench", choices=["bench", "zkwasm"],
+                    help="bench: benches/plonk.rs; zkwasm: tools/zkwasm_shape_circuit.py (64 advice, lookups, shuffles)")
+    ap.add_argument("--split-quotient", action="store_true",
+                    help="also divide evaluate_h by cosets (ShardedResidentEngineQ)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -28,31 +32,39 @@ def main():
     import halo2_gpu_specific_b200 as h2
     from halo2_gpu_specific_b200 import _lib
     from halo2_gpu_specific_b200 import plonk as HP
-    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngine
+    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngine, ShardedResidentEngineQ
     import plonk_bench_circuit as bc
+    import zkwasm_shape_circuit as zk
     _lib.require_gpu()
     _lib.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     params = h2.Params.unsafe_setup(a.k, 0x2B200B200B200B200B200B200B200B2001)
-    cs = HP.ConstraintSystem(**bc.constraint_system_args())
-    fixed, advice, mapping = bc.build(a.k)
+    if a.circuit == "bench":
+        cs = HP.ConstraintSystem(**bc.constraint_system_args())
+        fixed, advice, mapping = bc.build(a.k)
+        public = []
+    else:
+        cs = HP.ConstraintSystem(**zk.constraint_system_args(extra_gates=300))
+        dom = h2.EvaluationDomain(cs.degree(), a.k)
+        fixed, advice, pub, mapping = zk.build(a.k, HP.Engine(params, dom).to_mont, seed=a.k)
+        public = [pub]
     pk = HP.keygen(params, cs, fixed, mapping)
-    eng = ShardedResidentEngine(params, pk.vk.domain)
-    HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(0), engine=eng)
+    eng = (ShardedResidentEngineQ if a.split_quotient else ShardedResidentEngine)(params, pk.vk.domain)
+    HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(0), engine=eng)
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    proof = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(1), engine=eng)
+    proof = HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(1), engine=eng)
     dt = time.perf_counter() - t0
     eng.free()
     ok = True
     alone_s = None
     if rank == 0:
         plain = HP.ResidentEngine(params, pk.vk.domain)
-        HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(0), engine=plain)
+        HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(0), engine=plain)
         t0 = time.perf_counter()
-        alone = HP.create_proof(params, pk, advice.copy(), [], HP.SeededRng(1), engine=plain)
+        alone = HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(1), engine=plain)
         alone_s = time.perf_counter() - t0
         plain.free()
         ok = alone == proof
@@ -61,7 +73,8 @@ def main():
         dist.all_gather_object(gathered, proof)
         ok = ok and all(g == proof for g in gathered)
     if rank == 0:
-        print(json.dumps({"check": "sharded-commit create_proof, benches/plonk.rs circuit", "k": a.k, "n_gpus": world,
+        print(json.dumps({"check": f"sharded create_proof, {a.circuit} circuit, quotient split: {a.split_quotient}", "k": a.k,
+                          "n_gpus": world,
                           "bytes_equal_on_all_ranks_and_to_single_gpu": bool(ok), "sharded_s": dt, "single_gpu_s": alone_s,
                           "backend": "nccl" if world > 1 else "none"}), flush=True)
     if world > 1:
