@@ -12,7 +12,8 @@ link and stays resident there, because the z columns and evaluate_h need all of 
 
 Status: the sharding and gather logic is validated on CPU with gloo (tests/test_parallel_cpu.py: proof bytes of a
 2- and 3-rank run equal the single-process oracle proof) and on two B200s over NCCL (tools/sharded_proof_check.py,
-profiles/r1_sharded_prover_2gpu.json: every rank's bytes equal the single-GPU proof).  At the size that fitted the
+profiles/r1_sharded_prover_2gpu.json: every rank's bytes equal the single-GPU proof; that run gathered the points with
+all_gather_object, the fixed-size tensor gather that replaced it afterwards is covered with gloo).  At the size that fitted the
 remaining GPU budget (k = 16, an 12 ms proof) the pickled all-gathers cost more than the divided MSMs save; measuring
 it at zkWasm scale is round-2 work, and so is running the coset split of evaluate_h inside the prover on GPUs
 (`ShardedQuotient` below: its division logic is covered on CPU with gloo, its device methods have not run yet).
@@ -36,13 +37,38 @@ class ShardedCommits:
         return parallel.column_range(count, world, rank)
 
     @staticmethod
-    def _gather(local: List[Point]) -> List[Point]:
+    def _gather(local: List[Point], count: int) -> List[Point]:
+        """points of this rank's column range -> points of all `count` columns, in column order, on every rank: one
+        all-gather of fixed-size records (flag, x, y as 9 x 64 bits), the same pattern as parallel.all_gather_partials"""
         d = parallel._dist()
         if d is None:
             return list(local)
-        parts: list = [None] * d.get_world_size()
-        d.all_gather_object(parts, list(local))
-        return [p for part in parts for p in part]
+        import numpy as np
+        import torch
+        world = d.get_world_size()
+        part_len = (count + world - 1) // world                     # parallel.shard_range's stride
+        rec = np.zeros((max(1, part_len), 9), dtype=np.uint64)
+        for i, p in enumerate(local):
+            if p is not None:
+                rec[i, 0] = 1
+                for l in range(4):
+                    rec[i, 1 + l] = (p[0] >> (64 * l)) & 0xFFFFFFFFFFFFFFFF
+                    rec[i, 5 + l] = (p[1] >> (64 * l)) & 0xFFFFFFFFFFFFFFFF
+        t = torch.from_numpy(rec.view(np.int64))
+        if d.get_backend() == "nccl":
+            t = t.cuda()
+        out = torch.empty((world * rec.shape[0], 9), dtype=torch.int64, device=t.device)
+        d.all_gather_into_tensor(out, t)
+        rows = out.cpu().numpy().view(np.uint64).reshape(world, rec.shape[0], 9)
+        points: List[Point] = []
+        for c in range(count):
+            r = rows[c // part_len, c % part_len]
+            if not r[0]:
+                points.append(None)
+            else:
+                points.append((sum(int(r[1 + l]) << (64 * l) for l in range(4)),
+                               sum(int(r[5 + l]) << (64 * l) for l in range(4))))
+        return points
 
     _inside = False       # True while this rank works on its own share: nested protocol calls pass straight through
 
@@ -64,7 +90,7 @@ class ShardedCommits:
         lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = super().commit_lagrange(self.sub_block(block, lo, hi), max_bits) if hi > lo else []
-        return self._gather(pts)
+        return self._gather(pts, self.block_count(block))
 
     def commit(self, block) -> List[Point]:
         if self._inside:
@@ -72,7 +98,7 @@ class ShardedCommits:
         lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = super().commit(self.sub_block(block, lo, hi)) if hi > lo else []
-        return self._gather(pts)
+        return self._gather(pts, self.block_count(block))
 
     def commit_lagrange_and_ifft(self, block) -> List[Point]:
         """own share: commitment + inverse transform in one pass; the other columns are needed in coefficient form on
@@ -87,7 +113,7 @@ class ShardedCommits:
                 self.lagrange_to_coeff(self.sub_block(block, 0, lo))
             if hi < count:
                 self.lagrange_to_coeff(self.sub_block(block, hi, count))
-        return self._gather(pts)
+        return self._gather(pts, count)
 
     def put_and_commit_lagrange(self, host, max_bits: Optional[int]):
         if self._inside:
@@ -96,7 +122,7 @@ class ShardedCommits:
         lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = self.commit_columns_with_bound(self.sub_block(block, lo, hi), max_bits) if hi > lo else []
-        return block, self._gather(pts)
+        return block, self._gather(pts, self.block_count(block))
 
 
 class ShardedQuotient:

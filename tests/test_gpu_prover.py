@@ -308,7 +308,7 @@ def test_sharded_engine_on_one_rank(gpu):
         got = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(5), engine=eng)
         # a forced split (as rank 1 of 3 would see it) still transforms every z column on this rank
         eng._share = lambda count: (count // 3, count - count // 3)
-        eng._gather = lambda local: local
+        eng._gather = lambda local, count: local
         z = eng.put(np.ascontiguousarray(np.stack([enc(p) for p in fx["perm_z"]] + [enc(fx["shuffle_z"][0])])))
         pts = eng.commit_lagrange_and_ifft(z)
         assert len(pts) == 1
