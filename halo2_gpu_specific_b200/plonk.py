@@ -15,10 +15,11 @@ front-end (layouter, selector compression, witness synthesis -- the advice colum
 deliver them) and the verifier.
 
 Numbers are (.., 4) uint64 Montgomery arrays (the reference's in-memory Fr); challenges and evaluation points are
-Python ints (canonical).  The numeric work goes through an `Engine` object; the only implementation in this package
-is the device one (it raises without a CUDA device -- there is no CPU fallback).  The parameter exists so that the
-host logic (transcript order, RNG order, query grouping, multiplicities) can be tested on CPU against a test double
-that lives in tests/.
+Python ints (canonical).  The numeric work goes through an engine object that speaks the block protocol described
+above the engine classes: `ResidentEngine` (default: everything stays in HBM), `Engine` (every call copies its operands
+through the host API) and the sharded variants of prover_sharded.py -- all of them device engines that raise without a
+CUDA device; there is no CPU fallback.  The parameter also lets the host logic (transcript order, RNG order, query
+grouping, multiplicities) be tested on CPU against a test double that lives in tests/.
 
 Three inputs cannot be read from the reference tree and are parameters (see oracle/prover.py for the same list):
 the verifying key's transcript scalar (`transcript_repr`), the point compression bit (`sign_bit`) and the source of

@@ -1,8 +1,8 @@
 """Test double for halo2_gpu_specific_b200.plonk.Engine: the same method set answered by the CPU oracle
 (oracle/plonk.py, oracle/bn254.py, oracle/cpu_ref.c).  It exists so that the HOST logic of the prover mirror --
 transcript order, RNG order, query grouping, multiplicities, keygen bookkeeping -- can be checked on CPU against
-oracle/prover.py without a GPU.  It lives in tests/ because only tests may touch the oracle; the package itself
-has a single Engine, the device one."""
+oracle/prover.py without a GPU.  It lives in tests/ because only tests may touch the oracle; the engines of the
+package itself (ResidentEngine, Engine, the sharded variants) all run on the device and refuse to start without one."""
 from __future__ import annotations
 
 import numpy as np
