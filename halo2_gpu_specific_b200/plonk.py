@@ -10,6 +10,8 @@ rank 2: "replace per-column par_iter calls with batched FFI calls; thread the ca
                                    plonk/vanishing/prover.rs:41-153, plonk/permutation/prover.rs:181-304,
                                    plonk/logup/prover.rs:70-256, 420-491, plonk/shuffle/prover.rs:200-240,
                                    poly/multiopen/gwc.rs:38-62, poly/multiopen/gwc/prover.rs:19-173
+  create_proof_with_shplonk        plonk/prover.rs:1737-1757, poly/multiopen/shplonk.rs:57-150,
+                                   poly/multiopen/shplonk/prover.rs:78-234
 All paths relative to /root/reference/halo2_proofs/src.  Out of scope, as in DESIGN.md section 7: the circuit
 front-end (layouter, selector compression, witness synthesis -- the advice columns arrive as fetch_witness would
 deliver them) and the verifier.
