@@ -3,9 +3,9 @@
 points and an Fr NTT at k = 16 through best_multiexp / best_fft -- timed with the C restatement of the reference's rayon path
 (oracle/cpu_ref.c: chunk = n / T, one multiexp_serial per thread, ordered fold; arithmetic.rs:465-492, 546-705) on this
 box's host cores, next to the engine on the same inputs, AND compared bit for bit (this size the oracle finishes in
-milliseconds, so the timed inputs are also a parity case).  Like bench.py's cpu_baseline leg this tool may run oracle/.
+milliseconds, so the timed inputs are also a parity case).  It lives under tests/ because it runs oracle/ (as the CPU baseline and as the checker).
 
-    python tools/config1_point.py [--out file.json]
+    python tests/manual/config1_point.py [--out file.json]
 """
 import argparse
 import json
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import halo2_gpu_specific_b200 as h2  # noqa: E402
 from halo2_gpu_specific_b200 import _lib  # noqa: E402
