@@ -12,6 +12,8 @@ Restates, with Python big ints (MSMs go through the C restatement, oracle/cpu_re
   * permutation / logup / shuffle evaluate + open               plonk/permutation/prover.rs:181-304, plonk/logup/prover.rs:420-491,
                                                                 plonk/shuffle/prover.rs:200-240
   * multiopen::gwc::{create_proof, verify_proof}                poly/multiopen/gwc.rs:38-62, gwc/prover.rs:19-173, gwc/verifier.rs:16-91
+  * multiopen::shplonk::{create_proof, verify_proof}            poly/multiopen/shplonk.rs:57-150, shplonk/prover.rs:78-234,
+                                                                shplonk/verifier.rs:23-104 (PreMSM / combine_with_base: poly/msm.rs:136-204)
   * verify_proof                                                plonk/verifier.rs:127-507 and the argument verifiers
                                                                 (vanishing/verifier.rs, permutation/verifier.rs,
                                                                 logup/verifier.rs, shuffle/verifier.rs)
@@ -20,7 +22,8 @@ All paths relative to /root/reference/halo2_proofs/src.
 
 PARITY STATUS: byte-level parity with the Rust binary is unpinned (the reference cannot be built here and holds
 no golden proofs).  What pins this file is the reference's own acceptance test strategy (examples / tests:
-create_proof -> verify_proof must accept, a tampered proof / instance must not): tests/test_oracle_prover.py.
+create_proof -> verify_proof must accept, a tampered proof / instance must not): tests/test_oracle_prover.py, and the
+reference's multiopen unit tests restated in tests/test_oracle_multiopen.py.
 Three inputs are parameters because they cannot be read from the reference tree:
   * the verifying key's transcript scalar (Rust `{:?}` of PinnedVerificationKey, plonk.rs:100) -- `vk_transcript_repr`
     hashes a description of its own under the same personalisation and feeds it through the same common_scalar call;
