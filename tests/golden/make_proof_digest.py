@@ -21,6 +21,9 @@ params = PR.Params(5, S_TOXIC)
 pk = PR.keygen(params, fx["cs"], fx["fixed"], fx["mapping"])
 proof = PR.create_proof(params, pk, fx["advice"], [fx["instance"][0][:4]], SeededRng(1))
 assert PR.verify_proof(params, pk.vk, [fx["instance"][0][:4]], proof)
-out = {"k5_seed11_rng1_sha256": hashlib.sha256(proof).hexdigest(), "proof_bytes": len(proof)}
+shplonk = PR.create_proof(params, pk, fx["advice"], [fx["instance"][0][:4]], SeededRng(1), use_gwc=False)
+assert PR.verify_proof(params, pk.vk, [fx["instance"][0][:4]], shplonk, use_gwc=False)
+out = {"k5_seed11_rng1_sha256": hashlib.sha256(proof).hexdigest(), "proof_bytes": len(proof),
+       "k5_seed11_rng1_shplonk_sha256": hashlib.sha256(shplonk).hexdigest(), "shplonk_proof_bytes": len(shplonk)}
 json.dump(out, open(os.path.join(HERE, "proof_digest.json"), "w"), indent=1)
 print(out)

@@ -109,6 +109,8 @@ def test_proof_is_deterministic_under_a_fixed_rng_and_frozen(setup):
     golden = os.path.join(os.path.dirname(__file__), "golden", "proof_digest.json")
     want = json.load(open(golden))
     assert hashlib.sha256(proof).hexdigest() == want["k5_seed11_rng1_sha256"]
+    shplonk = PR.create_proof(params, pk, fx["advice"], inst, SeededRng(1), use_gwc=False)
+    assert hashlib.sha256(shplonk).hexdigest() == want["k5_seed11_rng1_shplonk_sha256"]
 
 
 def test_multiplicity_tie_rule():
