@@ -1,0 +1,196 @@
+"""Randomised circuits through the whole prover (CPU): random gate expressions (constants, negation, scaling, sums,
+products, rotations) made satisfiable by construction, a random permutation, a lookup and a shuffle.  For every seed
+the oracle's proof must verify and the prover mirror's host logic (over the oracle-backed engine) must write the same
+bytes -- this walks the corners of Evaluator::add_expression (constant folding, the `0 - b` quirk, operand ordering,
+sub-expression sharing) and of the query bookkeeping that the hand-written fixture does not reach."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bn254 as o
+from oracle import plonk as P
+from oracle import prover as PR
+from oracle_engine import OracleEngine
+
+from halo2_gpu_specific_b200 import plonk as HP
+
+R = o.R_MOD
+enc = o.fr_encode
+S_TOXIC = 0x2B200B200B200B200B200B200B200B2001
+K = 5
+N = 1 << K
+BF = 5
+USABLE = N - BF - 1
+N_IN = 4            # free input columns a0 .. a3
+N_GATES = 3         # target columns a4 .. a6
+N_FIXED_CONST = 2   # f0, f1: random fixed columns usable inside expressions
+
+
+class HostParams:
+    k, n = K, N
+
+
+def random_expression(rng, depth, budget):
+    """a random Expression of degree <= budget over the input columns and the constant fixed columns"""
+    if depth == 0 or budget == 0 or rng.random() < 0.2:
+        if budget == 0 or rng.random() < 0.25:
+            return P.Const(rng.choice([0, 1, 2, R - 1, rng.randrange(R)]))
+        if rng.random() < 0.3:
+            return P.Fixed(rng.randrange(N_FIXED_CONST), rng.choice([0, 0, 1, -1]))
+        return P.Advice(rng.randrange(N_IN), rng.choice([0, 0, 0, 1, -1, 2, -2]))
+    kind = rng.choice(["neg", "scaled", "sum", "sub", "prod", "prod"])
+    if kind == "neg":
+        return P.Neg(random_expression(rng, depth - 1, budget))
+    if kind == "scaled":
+        return P.Scaled(random_expression(rng, depth - 1, budget), rng.choice([0, 1, 3, rng.randrange(R)]))
+    if kind == "sum":
+        return P.Sum(random_expression(rng, depth - 1, budget), random_expression(rng, depth - 1, budget))
+    if kind == "sub":
+        return P.Sub(random_expression(rng, depth - 1, budget), random_expression(rng, depth - 1, budget))
+    left = rng.randint(0, budget)
+    return P.Prod(random_expression(rng, depth - 1, left), random_expression(rng, depth - 1, budget - left))
+
+
+def folds_to_zero(e) -> bool:
+    """does Evaluator::add_expression reduce e to Constant(0)? (evaluation.rs:671-776: Scaled by 0, a zero factor)"""
+    t = e[0]
+    if t == "Constant":
+        return e[1] == 0
+    if t == "Scaled":
+        return e[2] == 0
+    if t == "Product":
+        return folds_to_zero(e[1]) or folds_to_zero(e[2])
+    if t == "Negated":
+        return folds_to_zero(e[1])
+    return False
+
+
+def has_zero_minus(e) -> bool:
+    """`0 - b`: the reference's add_expression returns b instead of -b for it (evaluation.rs:727-728), so the prover's
+    numerator disagrees with the verifier's expression and such a circuit cannot be proven -- see the dedicated test"""
+    if e[0] == "Sum" and e[2][0] == "Negated" and folds_to_zero(e[1]):
+        return True
+    return any(has_zero_minus(c) for c in e[1:] if isinstance(c, tuple) and c and isinstance(c[0], str))
+
+
+def rotations_of(e, acc):
+    if e[0] in ("Fixed", "Advice", "Instance"):
+        acc.add(e[2])
+    elif e[0] in ("Negated", "Scaled"):
+        rotations_of(e[1], acc)
+    elif e[0] in ("Sum", "Product"):
+        rotations_of(e[1], acc)
+        rotations_of(e[2], acc)
+    return acc
+
+
+def build(seed):
+    rng = random.Random(seed)
+    n_adv = N_IN + N_GATES + 3                     # + lookup input, shuffle input, shuffle column
+    n_fix = N_FIXED_CONST + N_GATES + 1            # + one selector per gate + the lookup table
+    cs = P.ConstraintSystem(n_fix, n_adv, 1, degree=5, blinding_factors=BF)
+    fixed = [[rng.randrange(R) for _ in range(N)] for _ in range(n_fix)]
+    advice = [[rng.randrange(R) for _ in range(N)] for _ in range(n_adv)]
+    instance = [[rng.randrange(R) if r < 3 else 0 for r in range(N)]]
+    for g in range(N_GATES):
+        e = random_expression(rng, 3, 3)
+        while has_zero_minus(e) or folds_to_zero(e):     # the gate is q * (e - target): e = 0 would be `0 - b` itself
+            e = random_expression(rng, 3, 3)
+        if g == 0:
+            e = P.Sum(e, P.Instance(0, 0))         # keep the instance column in play
+        rots = rotations_of(e, {0})
+        sel = N_FIXED_CONST + g
+        tgt = N_IN + g
+        for r in range(N):
+            ok = all(0 <= r + t < USABLE for t in rots)
+            fixed[sel][r] = 1 if ok else 0
+            if ok:
+                advice[tgt][r] = P.eval_expr(e, r, N, 1, fixed, advice, instance)
+        cs.gates.append([P.Prod(P.Fixed(sel), P.Sub(e, P.Advice(tgt)))])
+    table = N_FIXED_CONST + N_GATES
+    lk_in, sh_in, sh_out = N_IN + N_GATES, N_IN + N_GATES + 1, N_IN + N_GATES + 2
+    fixed[table] = [(7 * i + 1) % R for i in range(N)]
+    for r in range(USABLE):
+        advice[lk_in][r] = fixed[table][rng.randrange(USABLE)]
+    perm = list(range(USABLE))
+    rng.shuffle(perm)
+    for r in range(USABLE):
+        advice[sh_out][r] = advice[sh_in][perm[r]]
+    cs.lookups.append({"table_expressions": [P.Fixed(table)], "input_expressions_sets": [[[P.Advice(lk_in)]]]})
+    cs.shuffles.append([{"input_expressions": [P.Advice(sh_in)], "shuffle_expressions": [P.Advice(sh_out)]}])
+    # permutation over two input columns, a fixed column and the instance column; copies between cells made equal
+    cs.permutation_columns = [("Advice", 0), ("Advice", 1), ("Fixed", 0), ("Instance", 0)]
+    mapping = P.identity_mapping(4, N)
+    cells = {0: advice[0], 1: advice[1]}
+    # (gate targets were computed from the inputs above, so copies may only touch cells no gate row reads: use rows
+    # whose every selector is off)
+    free_rows = [r for r in range(USABLE) if all(fixed[N_FIXED_CONST + g][r2] == 0
+                                                 for g in range(N_GATES) for r2 in range(max(0, r - 2), min(N, r + 3)))]
+    for _ in range(min(3, len(free_rows) // 2)):
+        ra, rb = rng.sample(free_rows, 2)
+        ca, cb = rng.randrange(2), rng.randrange(2)
+        cells[cb][rb] = cells[ca][ra]
+        P.mapping_copy(mapping, (ca, ra), (cb, rb))
+    if free_rows:                                   # a copy from the fixed and from the instance column
+        r = free_rows[0]
+        advice[0][r] = fixed[0][1]
+        P.mapping_copy(mapping, (0, r), (2, 1))
+        if len(free_rows) > 1:
+            r2 = free_rows[1]
+            advice[1][r2] = instance[0][2]
+            P.mapping_copy(mapping, (1, r2), (3, 2))
+    return cs, fixed, advice, instance, mapping
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_circuit(seed):
+    cs, fixed, advice, instance, mapping = build(seed)
+    oparams = PR.Params(K, S_TOXIC)
+    opk = PR.keygen(oparams, cs, fixed, mapping)
+    inst = [instance[0][:3]]
+    use_gwc = seed % 2 == 0
+    proof = PR.create_proof(oparams, opk, advice, inst, HP.SeededRng(seed), use_gwc=use_gwc)
+    assert PR.verify_proof(oparams, opk.vk, inst, proof, use_gwc=use_gwc), "oracle verifier rejects a satisfied circuit"
+    hcs = HP.ConstraintSystem.like(cs)
+    parts = HP.evaluator_parts(hcs)
+    assert parts["calculations"] == opk.ev.calculations and parts["constants"] == opk.ev.constants
+    assert parts["value_parts"] == opk.ev.value_parts and parts["rotations"] == opk.ev.rotations
+    eng = OracleEngine(oparams, opk.vk.domain, cs)
+    pk = HP.keygen(HostParams, hcs, np.stack([enc(c) for c in fixed]), np.array(mapping, dtype=np.int64), engine=eng,
+                   transcript_repr=opk.vk.transcript_repr)
+    got = HP.create_proof(HostParams, pk, np.ascontiguousarray(np.stack([enc(c) for c in advice])), inst,
+                          HP.SeededRng(seed), engine=eng, use_gwc=use_gwc)
+    assert got == proof
+    # break one gate target: the proof must be rejected
+    bad = [list(c) for c in advice]
+    rows_on = [r for r in range(N) if fixed[N_FIXED_CONST][r]]
+    if rows_on:
+        bad[N_IN][rows_on[0]] = (bad[N_IN][rows_on[0]] + 1) % R
+        assert not PR.verify_proof(oparams, opk.vk, inst, PR.create_proof(oparams, opk, bad, inst, HP.SeededRng(seed),
+                                                                        use_gwc=use_gwc), use_gwc=use_gwc)
+
+
+def test_zero_minus_b_cannot_be_proven():
+    """The quirk restated from the reference (evaluation.rs:727-728: `0 - b` is lowered to `b`): for a witness that
+    satisfies the gate as written, the prover's numerator is not divisible by the vanishing polynomial, so the
+    verifier -- which evaluates the expression as written -- rejects.  Both the oracle and the prover mirror lower the
+    expression the reference's way; the point of this test is that the restatement keeps the quirk instead of fixing it."""
+    cs = P.ConstraintSystem(1, 2, 0, degree=3, blinding_factors=BF)
+    cs.gates.append([P.Prod(P.Fixed(0), P.Sub(P.Sub(P.Const(0), P.Advice(0)), P.Advice(1)))])     # q * ((0 - a) - t)
+    rng = random.Random(1)
+    a = [rng.randrange(R) for _ in range(N)]
+    t = [(-v) % R for v in a]
+    fixed = [[1 if r < USABLE else 0 for r in range(N)]]
+    assert all(P.eval_expr(cs.gates[0][0], r, N, 1, fixed, [a, t], []) == 0 for r in range(USABLE))
+    ev = P.Evaluator.new(cs)
+    assert ("Negate", ("Intermediate", 0)) not in ev.calculations                 # -a is never computed
+    assert HP.evaluator_parts(HP.ConstraintSystem.like(cs))["calculations"] == ev.calculations
+    oparams = PR.Params(K, S_TOXIC)
+    opk = PR.keygen(oparams, cs, fixed, [])
+    proof = PR.create_proof(oparams, opk, [a, t], [], HP.SeededRng(1))
+    assert not PR.verify_proof(oparams, opk.vk, [], proof)
+    # the witness the lowered form accepts (t = +a) is not a witness of the gate as written either; with this one-gate
+    # circuit its numerator is identically zero, so there is no h(X) piece to commit to
+    with pytest.raises(PR.TranscriptError):
+        PR.create_proof(oparams, opk, [a, list(a)], [], HP.SeededRng(1))
