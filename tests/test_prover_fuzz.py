@@ -53,17 +53,12 @@ def random_expression(rng, depth, budget):
 
 
 def folds_to_zero(e) -> bool:
-    """does Evaluator::add_expression reduce e to Constant(0)? (evaluation.rs:671-776: Scaled by 0, a zero factor)"""
-    t = e[0]
-    if t == "Constant":
-        return e[1] == 0
-    if t == "Scaled":
-        return e[2] == 0
-    if t == "Product":
-        return folds_to_zero(e[1]) or folds_to_zero(e[2])
-    if t == "Negated":
-        return folds_to_zero(e[1])
-    return False
+    """does Evaluator::add_expression reduce e to Constant(0)?  (evaluation.rs:671-776: a zero constant, Scaled by 0,
+    a zero factor, 0 + 0, ...: asked of the restated evaluator itself)"""
+    ev = P.Evaluator()
+    ev.add_constant(0)
+    ev.add_constant(1)
+    return ev.add_expression(e) == ("Constant", 0)
 
 
 def has_zero_minus(e) -> bool:
@@ -143,7 +138,7 @@ def build(seed):
     return cs, fixed, advice, instance, mapping
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(24))
 def test_random_circuit(seed):
     cs, fixed, advice, instance, mapping = build(seed)
     oparams = PR.Params(K, S_TOXIC)
