@@ -189,3 +189,56 @@ def test_zero_minus_b_cannot_be_proven():
     # circuit its numerator is identically zero, so there is no h(X) piece to commit to
     with pytest.raises(PR.TranscriptError):
         PR.create_proof(oparams, opk, [a, list(a)], [], HP.SeededRng(1))
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_circuit_lowered_quotient_program(seed):
+    """The C++ lowering of the whole evaluate_h program (b2_quotient_program_create: inlining, dead-code removal,
+    depth-first scheduling, slot allocation, derived challenge powers; host-only code of the product) on the random
+    circuits: the dumped program, interpreted with big ints over the oracle's cosets, must equal the oracle's
+    evaluate_h on every row of the extended domain."""
+    from test_quotient_lowering import interpret
+    cs, fixed, advice, instance, mapping = build(seed)
+    rng = random.Random(1000 + seed)
+    d = o.EvaluationDomain(cs.degree(), K)
+    theta, beta, gamma, y = (rng.randrange(R) for _ in range(4))
+    sigmas = P.permutation_sigmas(cs, d, mapping)
+    perm_z = P.permutation_commit(cs, d, sigmas, advice, fixed, instance, beta, gamma, rng)
+    lookups = []
+    for lk in cs.lookups:
+        input_sets, table, m = P.logup_compress(cs, d, lk, theta, advice, fixed, instance, rng)
+        zs = [P.blind_to_n(z, N, rng) for z in P.logup_commit_z(cs, d, input_sets, table, m, beta)]
+        lookups.append((zs, m))
+    shuffle_z = [P.blind_to_n(P.shuffle_commit_product(cs, d, g, theta, beta, advice, fixed, instance), N, rng)
+                 for g in cs.shuffles]
+    ext = lambda col: d.coeff_to_extended(d.lagrange_to_coeff(col))                     # noqa: E731
+    l0, l_last, l_active = P.lagrange_basis_cosets(cs, d)
+    cz_fixed, cz_adv, cz_inst = [ext(c) for c in fixed], [ext(c) for c in advice], [ext(c) for c in instance]
+    cz_sigma, cz_perm = [ext(c) for c in sigmas], [ext(c) for c in perm_z]
+    cz_lookups = [{"z_cosets": [ext(z) for z in zs], "m_coset": ext(m)} for zs, m in lookups]
+    cz_shuffles = [ext(z) for z in shuffle_z]
+    ev = P.Evaluator.new(cs)
+    want = P.evaluate_h(ev, cs, d, cz_fixed, cz_adv, cz_inst, l0, l_last, l_active, cz_sigma, y, beta, gamma, theta,
+                        cz_lookups, cz_shuffles, cz_perm)
+    hcs = HP.ConstraintSystem.like(cs)
+    Ev = HP.build_evaluator(hcs)
+    prog = Ev.program(len(perm_z), [len(zs) for zs, _ in lookups], len(shuffle_z))
+    aux = [l0, l_last, l_active] + cz_sigma + cz_perm
+    for lk in cz_lookups:
+        aux += lk["z_cosets"] + [lk["m_coset"]]
+    aux += cz_shuffles
+    challenges = [beta, gamma, theta, y]
+    dlt = beta * d.g_coset % R
+    for _ in cs.permutation_columns:
+        challenges.append(dlt)
+        dlt = dlt * P.FR_DELTA % R
+    rotations = list(ev.rotations)
+    for r in (0, 1, -(BF + 1)):
+        if r not in rotations:
+            rotations.append(r)
+    constants = list(ev.constants)
+    got = interpret(prog, rotations, constants, cz_fixed + cz_adv + cz_inst + aux, challenges, d.extended_len(),
+                    1 << (d.extended_k - d.k), 1, d.extended_omega)
+    assert got == want
+    info = prog.info()
+    assert info["n_slots"] <= 24 and info["n_instr"] > 0
