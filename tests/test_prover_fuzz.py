@@ -242,3 +242,29 @@ def test_random_circuit_lowered_quotient_program(seed):
     assert got == want
     info = prog.info()
     assert info["n_slots"] <= 24 and info["n_instr"] > 0
+
+
+def test_random_expressions_through_the_z_column_compiler():
+    """grand_product.ExprCompiler + the C++ lowering on random expression lists (zeros and `0 - b` included: the
+    compression path evaluates expressions as written, evaluate_with_theta has no quirk): the dumped program interpreted
+    at rows = n equals evaluate_with_theta (plonk/evaluation.rs:2330-2398)"""
+    from halo2_gpu_specific_b200.evaluation import QuotientProgram
+    from halo2_gpu_specific_b200.grand_product import ExprCompiler
+    from test_quotient_lowering import interpret
+    rng = random.Random(77)
+    fixed = [[rng.randrange(R) for _ in range(N)] for _ in range(N_FIXED_CONST)]
+    advice = [[rng.randrange(R) for _ in range(N)] for _ in range(N_IN)]
+    instance = [[rng.randrange(R) for _ in range(N)]]
+    for trial in range(40):
+        exprs = [random_expression(rng, 3, 4) for _ in range(rng.randint(1, 3))]
+        if trial % 5 == 0:
+            exprs.append(P.Sub(P.Const(0), P.Advice(1, 1)))
+        if trial % 7 == 0:
+            exprs.append(P.Instance(0, -1))
+        theta = rng.randrange(R)
+        c = ExprCompiler()
+        res = c.emit(("Store", c.compress(exprs)))
+        prog = QuotientProgram(c.rotations, c.constants, c.calcs, res, N_FIXED_CONST, N_IN, 1, 0, 3)
+        got = interpret(prog, c.rotations, c.constants, fixed + advice + instance, [0, 0, theta], N, 1, 1, 1)
+        prog.free()
+        assert got == P.evaluate_with_theta(exprs, N, 1, fixed, advice, instance, theta), trial
