@@ -82,8 +82,12 @@ def rotations_of(e, acc):
 
 def build(seed):
     rng = random.Random(seed)
-    n_adv = N_IN + N_GATES + 3                     # + lookup input, shuffle input, shuffle column
-    n_fix = N_FIXED_CONST + N_GATES + 1            # + one selector per gate + the lookup table
+    # lookup shape: 1-2 input sets of 1-2 inputs, each input a tuple of 1-2 expressions (theta-compressed)
+    lk_width = rng.randint(1, 2)
+    lk_sets = [rng.randint(1, 2) for _ in range(rng.randint(1, 2))]
+    n_lk_cols = sum(lk_sets) * lk_width
+    n_adv = N_IN + N_GATES + n_lk_cols + 2         # + lookup inputs, shuffle input, shuffle column
+    n_fix = N_FIXED_CONST + N_GATES + 2            # + one selector per gate + two table columns
     cs = P.ConstraintSystem(n_fix, n_adv, 1, degree=5, blinding_factors=BF)
     fixed = [[rng.randrange(R) for _ in range(N)] for _ in range(n_fix)]
     advice = [[rng.randrange(R) for _ in range(N)] for _ in range(n_adv)]
@@ -104,15 +108,28 @@ def build(seed):
                 advice[tgt][r] = P.eval_expr(e, r, N, 1, fixed, advice, instance)
         cs.gates.append([P.Prod(P.Fixed(sel), P.Sub(e, P.Advice(tgt)))])
     table = N_FIXED_CONST + N_GATES
-    lk_in, sh_in, sh_out = N_IN + N_GATES, N_IN + N_GATES + 1, N_IN + N_GATES + 2
-    fixed[table] = [(7 * i + 1) % R for i in range(N)]
-    for r in range(USABLE):
-        advice[lk_in][r] = fixed[table][rng.randrange(USABLE)]
+    lk_first = N_IN + N_GATES
+    sh_in, sh_out = lk_first + n_lk_cols, lk_first + n_lk_cols + 1
+    repeat = rng.choice([1, 1, 2, 3])               # repeated table rows: the multiplicity goes to the searched row
+    fixed[table] = [(7 * (i // repeat) + 1) % R for i in range(N)]
+    fixed[table + 1] = [(11 * (i // repeat) + 5) % R for i in range(N)]
+    table_exprs = [P.Fixed(table + w) for w in range(lk_width)]
+    sets, col = [], lk_first
+    for n_inputs in lk_sets:
+        inputs = []
+        for _ in range(n_inputs):
+            for r in range(USABLE):
+                j = rng.randrange(USABLE)
+                for w in range(lk_width):
+                    advice[col + w][r] = fixed[table + w][j]
+            inputs.append([P.Advice(col + w) for w in range(lk_width)])
+            col += lk_width
+        sets.append(inputs)
     perm = list(range(USABLE))
     rng.shuffle(perm)
     for r in range(USABLE):
         advice[sh_out][r] = advice[sh_in][perm[r]]
-    cs.lookups.append({"table_expressions": [P.Fixed(table)], "input_expressions_sets": [[[P.Advice(lk_in)]]]})
+    cs.lookups.append({"table_expressions": table_exprs, "input_expressions_sets": sets})
     cs.shuffles.append([{"input_expressions": [P.Advice(sh_in)], "shuffle_expressions": [P.Advice(sh_out)]}])
     # permutation over two input columns, a fixed column and the instance column; copies between cells made equal
     cs.permutation_columns = [("Advice", 0), ("Advice", 1), ("Fixed", 0), ("Instance", 0)]
