@@ -670,8 +670,8 @@ class DevBlock:
 class ResidentEngine:
     """Device-resident engine: every witness column crosses PCIe once (pipelined with its commitment), every other
     polynomial is born in HBM and stays there -- z columns, multiplicities, the random polynomial, h(X), the folded
-    multiopen polynomials and their quotients; only commitments (96 B), evaluations (32 B) and, for logup, the
-    compressed input / table values (the multiplicities are counted on the host, as in the reference) go back.
+    multiopen polynomials and their quotients; only commitments (96 B), evaluations (32 B) and one count per lookup
+    (the bound for the commitment of m) go back -- the logup multiplicities are sorted and matched on the device too.
     The proving key's polynomials, and their evaluations on every coset of the extended domain, are made resident
     on first use and kept for later proofs (pk.fixed_cosets / permutation cosets are what the reference's CPU
     prover keeps too, plonk/keygen.rs)."""
