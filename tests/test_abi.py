@@ -86,3 +86,23 @@ def test_domain_constants_match_oracle():
                      "ifft_divisor", "extended_ifft_divisor", "barycentric_weight"):
             assert np.array_equal(getattr(d, name), enc(getattr(r, name))), name
         assert np.array_equal(d.t_evaluations, o.fr_encode(r.t_evaluations))
+
+
+def test_rust_ffi_file_covers_the_abi():
+    """integration/b2pcs.rs (generated from include/b2pcs.h by tools/gen_rust_ffi.py) is up to date and declares every
+    symbol the library exports exactly once, with the arity the ctypes prototypes use"""
+    import sys
+    from halo2_gpu_specific_b200 import _lib
+    root = ROOT
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_rust_ffi.py"), "--check"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    text = open(os.path.join(root, "integration", "b2pcs.rs")).read()
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (b2_\w+)\((.*?)\) -> ", text)}
+    L = _lib.lib()
+    for name in _lib.SYMBOLS:
+        assert text.count(f"pub fn {name}(") == 1, name
+        argtypes = getattr(getattr(L, name), "argtypes", None)
+        if argtypes is not None:
+            n_rust = 0 if not decl[name].strip() else decl[name].count(",") + 1
+            assert n_rust == len(argtypes), (name, decl[name], len(argtypes))
+    assert "pub struct B2NttDesc" in text and "pub struct B2QuotientArgs" in text and "B2_MAX_BITS_AUTO: u32 = 0xFFFFFFFF" in text
