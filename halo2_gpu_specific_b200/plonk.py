@@ -1415,7 +1415,14 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
 
     # ---- evaluations (:694-790)
     rot = lambda at: x * pow(domain._omega if at >= 0 else domain._omega_inv, abs(at), R) % R      # noqa: E731
-    ev = E.eval_polynomial
+    known: Dict[Tuple[int, int], int] = {}
+
+    def ev(poly, point: int) -> int:
+        """eval_polynomial, remembered: SHPLONK asks for the same (polynomial, point) pairs again"""
+        key = (_poly_key(poly), point)
+        if key not in known:
+            known[key] = E.eval_polynomial(poly, point)
+        return known[key]
     advice_polys, inst_cols = E.cols(adv), E.cols(instance_polys)
     fixed_polys, sigma_polys = E.cols(key["fixed_polys"]), E.cols(key["sigma_polys"])
     for col, at in queries["Instance"]:
@@ -1478,7 +1485,7 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
     if use_gwc:
         gwc_create_proof(E, tr, qs)
     else:
-        shplonk_create_proof(E, tr, qs)
+        shplonk_create_proof(E, tr, qs, evaluate=ev)
     lap("multiopen")
     return tr.finalize()
 
@@ -1555,12 +1562,13 @@ def _eval_small(coeffs: Sequence[int], x: int) -> int:
     return acc
 
 
-def shplonk_create_proof(E, tr: Blake2bWrite, queries) -> None:
+def shplonk_create_proof(E, tr: Blake2bWrite, queries, evaluate=None) -> None:
     """poly/multiopen/shplonk/prover.rs:78-234 over the engine.  The per-commitment subtractions of the reference
     (P - R for the quotient, P - R(u) for the linearisation) are linear, so each rotation set folds its polynomials
     with y ONCE on the device (F = sum y^j P_j) and the low-degree parts are handled as a few host scalars:
     N = F - R_fold (first |points| coefficients adjusted in place), Q = N / Z by repeated kate_division,
     L = N + R_fold - r_fold(u).  Scaling by z_i is the Horner fold of [L, 0] at z_i."""
+    evaluate = evaluate or E.eval_polynomial       # the prover passes its memo of the evaluations it already wrote
     y = tr.squeeze_challenge()
     # construct_intermediate_sets, shplonk.rs:57-150
     point_of: Dict[int, int] = {}
@@ -1582,7 +1590,7 @@ def shplonk_create_proof(E, tr: Blake2bWrite, queries) -> None:
     for rs in sorted(groups):                                  # BTreeMap<BTreeSet<Rotation>, _>: lexicographic
         points = [point_of[r] for r in rs]
         polys = groups[rs]
-        lows = [lagrange_interpolate(points, [E.eval_polynomial(p, pt) for pt in points]) for p in polys]   # :33-48
+        lows = [lagrange_interpolate(points, [evaluate(p, pt) for pt in points]) for p in polys]            # :33-48
         sets.append((polys, points, lows))
     v = tr.squeeze_challenge()
 
