@@ -39,6 +39,17 @@ def main():
     _lib.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if a.circuit == "zkwasm":
+        # every rank builds the witness and the proving key for itself: refuse to start when the host cannot hold
+        # `world` copies (a box driven out of memory is a lost box)
+        import psutil
+        per_rank = (zk.A + zk.F) * (1 << a.k) * 32 * 3.5 + zk.PERM_COLS * (1 << a.k) * 32 * 4
+        avail = psutil.virtual_memory().available
+        if per_rank * world > 0.8 * avail:
+            if rank == 0:
+                print(json.dumps({"error": f"host memory: {world} ranks x {per_rank / 2**30:.0f} GiB needed, "
+                                           f"{avail / 2**30:.0f} GiB available; use a smaller --k or fewer ranks"}))
+            sys.exit(3)
     params = h2.Params.unsafe_setup(a.k, 0x2B200B200B200B200B200B200B200B2001)
     if a.circuit == "bench":
         cs = HP.ConstraintSystem(**bc.constraint_system_args())
