@@ -259,6 +259,15 @@ def test_random_circuit_lowered_quotient_program(seed):
     assert got == want
     info = prog.info()
     assert info["n_slots"] <= 24 and info["n_instr"] > 0
+    if seed < 6:
+        # the third restatement: oracle/cpu_ref.c's row loop (bench.py's CPU baseline for evaluate_h) on the flat program
+        from oracle import cref
+        f = Ev.flat_h_program(len(perm_z), [len(zs) for zs, _ in lookups], len(shuffle_z))
+        c_out = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"],
+                                   [enc(c) for c in cz_fixed], [enc(c) for c in cz_adv], [enc(c) for c in cz_inst],
+                                   [enc(c) for c in aux], enc(challenges), d.extended_k, 1 << (d.extended_k - d.k),
+                                   x0=enc([1])[0], step=enc([d.extended_omega])[0], threads=2)
+        assert np.array_equal(c_out, enc(want))
 
 
 def test_random_expressions_through_the_z_column_compiler():
