@@ -86,7 +86,7 @@ def build(seed):
     lk_width = rng.randint(1, 2)
     lk_sets = [rng.randint(1, 2) for _ in range(rng.randint(1, 2))]
     n_lk_cols = sum(lk_sets) * lk_width
-    n_adv = N_IN + N_GATES + n_lk_cols + 2         # + lookup inputs, shuffle input, shuffle column
+    n_adv = N_IN + N_GATES + n_lk_cols + 4         # + lookup inputs, shuffle input, shuffle column, 2 copy columns
     n_fix = N_FIXED_CONST + N_GATES + 2            # + one selector per gate + two table columns
     cs = P.ConstraintSystem(n_fix, n_adv, 1, degree=5, blinding_factors=BF)
     fixed = [[rng.randrange(R) for _ in range(N)] for _ in range(n_fix)]
@@ -131,27 +131,28 @@ def build(seed):
         advice[sh_out][r] = advice[sh_in][perm[r]]
     cs.lookups.append({"table_expressions": table_exprs, "input_expressions_sets": sets})
     cs.shuffles.append([{"input_expressions": [P.Advice(sh_in)], "shuffle_expressions": [P.Advice(sh_out)]}])
-    # permutation over two input columns, a fixed column and the instance column; copies between cells made equal
-    cs.permutation_columns = [("Advice", 0), ("Advice", 1), ("Fixed", 0), ("Instance", 0)]
+    # permutation over two advice columns no gate reads, a fixed column and the instance column: random cycles of two
+    # to four cells, some anchored at a fixed or an instance cell (whose value the advice cells must then take)
+    p0, p1 = sh_out + 1, sh_out + 2
+    cs.permutation_columns = [("Advice", p0), ("Advice", p1), ("Fixed", 0), ("Instance", 0)]
     mapping = P.identity_mapping(4, N)
-    cells = {0: advice[0], 1: advice[1]}
-    # (gate targets were computed from the inputs above, so copies may only touch cells no gate row reads: use rows
-    # whose every selector is off)
-    free_rows = [r for r in range(USABLE) if all(fixed[N_FIXED_CONST + g][r2] == 0
-                                                 for g in range(N_GATES) for r2 in range(max(0, r - 2), min(N, r + 3)))]
-    for _ in range(min(3, len(free_rows) // 2)):
-        ra, rb = rng.sample(free_rows, 2)
-        ca, cb = rng.randrange(2), rng.randrange(2)
-        cells[cb][rb] = cells[ca][ra]
-        P.mapping_copy(mapping, (ca, ra), (cb, rb))
-    if free_rows:                                   # a copy from the fixed and from the instance column
-        r = free_rows[0]
-        advice[0][r] = fixed[0][1]
-        P.mapping_copy(mapping, (0, r), (2, 1))
-        if len(free_rows) > 1:
-            r2 = free_rows[1]
-            advice[1][r2] = instance[0][2]
-            P.mapping_copy(mapping, (1, r2), (3, 2))
+    free = [(c, r) for c in (0, 1) for r in range(USABLE)]
+    rng.shuffle(free)
+    for _ in range(rng.randint(2, 6)):
+        kind = rng.choice(["advice", "advice", "fixed", "instance"])
+        if kind == "fixed":
+            anchor, value = (2, rng.randrange(USABLE)), None
+            value = fixed[0][anchor[1]]
+        elif kind == "instance":
+            anchor = (3, rng.randrange(3))
+            value = instance[0][anchor[1]]
+        else:
+            anchor = free.pop()
+            value = advice[(p0, p1)[anchor[0]]][anchor[1]]
+        for _cell in range(rng.randint(1, 3)):
+            c, r = free.pop()
+            advice[(p0, p1)[c]][r] = value
+            P.mapping_copy(mapping, anchor, (c, r))
     return cs, fixed, advice, instance, mapping
 
 
@@ -174,6 +175,15 @@ def test_random_circuit(seed):
     got = HP.create_proof(HostParams, pk, np.ascontiguousarray(np.stack([enc(c) for c in advice])), inst,
                           HP.SeededRng(seed), engine=eng, use_gwc=use_gwc)
     assert got == proof
+    # break one copied cell (a cell whose permutation image is not itself): the proof must be rejected
+    moved = [(c, r) for c in (0, 1) for r in range(USABLE) if tuple(mapping[c][r]) != (c, r)]
+    if moved:
+        c, r = moved[0]
+        col = cs.permutation_columns[c][1]
+        bad = [list(x) for x in advice]
+        bad[col][r] = (bad[col][r] + 1) % R
+        assert not PR.verify_proof(oparams, opk.vk, inst, PR.create_proof(oparams, opk, bad, inst, HP.SeededRng(seed),
+                                                                        use_gwc=use_gwc), use_gwc=use_gwc)
     # break one gate target: the proof must be rejected
     bad = [list(c) for c in advice]
     rows_on = [r for r in range(N) if fixed[N_FIXED_CONST][r]]
