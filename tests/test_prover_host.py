@@ -446,3 +446,43 @@ def test_small_host_helpers_match_oracle():
     canon = np.array([o._to_limbs(v) for v in (0, 1, 255, 1 << 64, (1 << 130) + 5)], dtype=np.uint64)
     assert HP.canonical_max_bits(canon) == 131 and HP.canonical_max_bits(canon[:3]) == 8
     assert HP.canonical_max_bits(canon[:1]) == 0 and HP.canonical_max_bits(np.zeros((0, 4), np.uint64)) == 0
+
+
+def test_cpp_transcript_matches_python(tmp_path):
+    """host/halo2_b200_transcript.hpp (Blake2b from RFC 7693, Blake2bWrite, Challenge255 / from_bytes_wide) against the
+    oracle's and the package's Python transcripts on a random sequence of operations; host-only, no GPU needed"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "transcript_selftest")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(root, "include"),
+                           "-I", os.path.join(root, "halo2_gpu_specific_b200", "host"), "-o", exe,
+                           os.path.join(root, "halo2_gpu_specific_b200", "host", "transcript_selftest.cpp")])
+    rng = random.Random(21)
+    ref, py = PR.Blake2bWrite(), HT.Blake2bWrite()
+    pts = [o.g1_mul(o.G1_GEN, rng.randrange(R)) for _ in range(5)]
+    lines, want = [], []
+    for step in range(300):            # long enough to cross many 128-byte block boundaries
+        op = rng.randrange(5)
+        if op == 0:
+            lines.append("C")
+            c = ref.squeeze_challenge()
+            assert py.squeeze_challenge() == c
+            want.append("C " + enc([c])[0].tobytes().hex())
+        elif op in (1, 2):
+            s = rng.choice([0, 1, R - 1, rng.randrange(R)])
+            lines.append(("S " if op == 1 else "s ") + enc([s])[0].tobytes().hex())
+            (ref.common_scalar if op == 1 else ref.write_scalar)(s)
+            (py.common_scalar if op == 1 else py.write_scalar)(s)
+        else:
+            p = rng.choice(pts)
+            lines.append(("P " if op == 3 else "p ") + o.g1_affine_encode([p])[0].tobytes().hex())
+            (ref.common_point if op == 3 else ref.write_point)(p)
+            (py.common_point if op == 3 else py.write_point)(p)
+    lines.append("P " + bytes(64).hex())                                   # identity: refused, state untouched
+    want.append("E cannot write points at infinity to the transcript")
+    lines.append("C")
+    want.append("C " + enc([ref.squeeze_challenge()])[0].tobytes().hex())
+    want.append("W " + ref.finalize().hex())
+    assert py.finalize() == ref.finalize()
+    out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
+    assert [l for l in out if l] == want
