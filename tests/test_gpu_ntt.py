@@ -144,6 +144,49 @@ def test_full_size_properties_k22(gpu):
     assert got == want
 
 
+def test_best_fft_and_ifft_bit_exact_k22(gpu):
+    """BASELINE size, every output element: best_fft and gpu_ifft at k = 22 against the C restatement
+    (arithmetic.rs:546-705, 515-534) on all host cores"""
+    k = 22
+    n = 1 << k
+    cores = os.cpu_count() or 8
+    om, omi, div = _omega(k), o.fr_inv(_omega(k)), o.fr_inv(n)
+    x = cref.random_fr_mont(n, 0xB2000022)
+    a = x.copy()
+    h2.best_fft(a, enc(om), k)
+    assert np.array_equal(a, cref.best_fft(x, enc(om), k, cores))
+    b = x.copy()
+    h2.gpu_ifft(b, enc(omi), k, enc(div))
+    assert np.array_equal(b, cref.ifft(x, enc(omi), enc(div), k, cores))
+
+
+def test_coset_extend_bit_exact_k22_to_24(gpu):
+    """BASELINE size (the bench runs 22 -> 24): coeff_to_extended and extended_to_coeff of one column, every element
+    against the C restatement (poly/domain.rs:270-350), both candidate zetas on the forward direction"""
+    k = 22
+    n = 1 << k
+    cores = os.cpu_count() or 8
+    c = cref.random_fr_mont(n, 0xB2000024)
+    for zi, zeta in enumerate((o.FR_ZETA_A, o.FR_ZETA_B)):
+        dom = h2.EvaluationDomain(5, k, zeta)
+        assert dom.extended_k == 24
+        ext = dom.coeff_to_extended(c)
+        want = cref.coeff_to_extended(c, k, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega, cores)
+        assert np.array_equal(ext, want)
+        if zi:
+            continue
+        # an arbitrary (not low-degree) extended column: the truncated inverse transform must match element by element
+        y = cref.random_fr_mont(1 << dom.extended_k, 0xB2000025)
+        back = dom.extended_to_coeff(y)
+        wantb = cref.extended_to_coeff(y, dom.extended_k, dom.g_coset, dom.g_coset_inv, dom.extended_omega_inv,
+                                       dom.extended_ifft_divisor, cores)
+        assert back.shape[0] == n * 4
+        assert np.array_equal(back, wantb[: n * 4])
+        del y, back, wantb
+        rt = dom.extended_to_coeff(ext)
+        assert np.array_equal(rt[:n], c) and not rt[n:].any()
+
+
 def test_three_pass_sizes(gpu):
     """k = 25 needs three passes; check with the sparse closed form and a round trip"""
     k = 25

@@ -319,3 +319,31 @@ def test_sharded_engine_on_one_rank(gpu):
         assert got == want
     finally:
         params.free()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_circuits_proof_bytes_match_oracle(gpu, seed):
+    """tests/test_prover_fuzz.py's generator (random gate expressions with constants, negation, scaling and rotations,
+    a permutation over advice / fixed / instance, a lookup and a shuffle, satisfiable by construction) through BOTH
+    device engines: the proof bytes must equal the oracle prover's; GWC and SHPLONK alternate."""
+    import test_prover_fuzz as F
+    oparams = PR.Params(F.K, F.S_TOXIC)
+    params = h2.Params(F.K, oparams.g, oparams.g_lagrange)
+    try:
+        cs, fixed, advice, instance, mapping = F.build(seed)
+        opk = PR.keygen(oparams, cs, fixed, mapping)
+        inst = [instance[0][:3]]
+        gwc = seed % 2 == 0
+        want = PR.create_proof(oparams, opk, advice, inst, HP.SeededRng(seed), use_gwc=gwc)
+        pk = HP.keygen(params, HP.ConstraintSystem.like(cs), np.stack([enc(c) for c in fixed]),
+                       np.array(mapping, dtype=np.int64), transcript_repr=opk.vk.transcript_repr)
+        adv = np.ascontiguousarray(np.stack([enc(c) for c in advice]))
+        for kind in (HP.ResidentEngine, HP.Engine):
+            eng = kind(params, pk.vk.domain)
+            try:
+                got = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(seed), engine=eng, use_gwc=gwc)
+            finally:
+                eng.free()
+            assert got == want, f"seed {seed}, {kind.__name__}"
+    finally:
+        params.free()

@@ -261,3 +261,52 @@ def test_generated_sqr_and_karatsuba_emulation():
     assert counts["sqr"]["mad.lo"] == 100 and counts["mul"]["mad.lo"] == 112
     with open(os.path.join(root, "halo2_gpu_specific_b200", "csrc", "fp_gen.cuh")) as f:
         assert f.read() == gf.render()
+
+
+# ---- public third-party vectors for this curve (alt_bn128 = BN254): EIP-196 ecAdd / ecMul, EIP-197 pairing check ----
+EIP = json.load(open(os.path.join(HERE, "golden", "eip196_197.json")))
+
+
+def _eip_g1(h):
+    x, y = int(h[:64], 16), int(h[64:128], 16)
+    return None if (x, y) == (0, 0) else (x, y)
+
+
+@pytest.mark.parametrize("v", EIP["ecadd"], ids=lambda v: v["name"])
+def test_eip196_ecadd(v):
+    a, b = _eip_g1(v["input"][:128]), _eip_g1(v["input"][128:256])
+    assert o.g1_is_on_curve(a) and o.g1_is_on_curve(b)
+    want = _eip_g1(v["expected"])
+    assert o.g1_add(a, b) == want
+    # the same sum through every MSM restatement (scalars 1, 1), Python and C
+    if a is not None and b is not None:
+        assert o.multiexp_serial([1, 1], [a, b], None) == want
+        got = cref.best_multiexp(o.fr_encode([1, 1]), o.g1_affine_encode([a, b]), 2)
+        assert o.g1_jacobian_decode(got) == want
+
+
+@pytest.mark.parametrize("v", EIP["ecmul"], ids=lambda v: v["name"])
+def test_eip196_ecmul(v):
+    p, k = _eip_g1(v["input"][:128]), int(v["input"][128:192], 16)
+    assert o.g1_is_on_curve(p)
+    want = _eip_g1(v["expected"])
+    assert o.g1_mul(p, k % o.R_MOD) == want
+    assert o.multiexp_serial([k % o.R_MOD], [p], None) == want
+    got = cref.best_multiexp(o.fr_encode([k % o.R_MOD]), o.g1_affine_encode([p]), 1)
+    assert o.g1_jacobian_decode(got) == want
+
+
+@pytest.mark.parametrize("v", EIP["pairing"], ids=lambda v: v["name"])
+def test_eip197_pairing(v):
+    """pins oracle/pairing.py (what the oracle's Decider::verify rests on) to the public pairing-check vectors"""
+    from oracle import pairing as pg
+    h, pairs = v["input"], []
+    for i in range(0, len(h), 384):
+        c = [int(h[i + 64 * j: i + 64 * j + 64], 16) for j in range(6)]
+        p = None if (c[0], c[1]) == (0, 0) else (c[0], c[1])
+        q = ((c[3], c[2]), (c[5], c[4]))                 # EIP-197 encodes the imaginary part first
+        assert o.g1_is_on_curve(p) and pg.g2_is_on_curve(q)
+        pairs.append((p, q))
+    assert pg.pairing_check(pairs) == v["expected"]
+    if v["name"] == "jeff1":
+        assert pairs[1][1] == pg.G2_GEN                  # the oracle's G2 generator is the standard one
