@@ -951,6 +951,28 @@ int run_probe(Lane* ctx, K kernel, double* out) {
 }  // namespace
 
 // ============================================================================ C ABI
+template <int KIND>
+static int run_pipe_probe(Lane* ctx, double* per_s) {
+    cudaStream_t st = ctx->stream;
+    const int iters = 4000, ILP = 8;
+    const int blocks = ctx->sms * 8, threads = 256;
+    unsigned long long* sink = reinterpret_cast<unsigned long long*>(ctx->out96.p);
+    LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, 50, 0x9E3779B1u, 0x85EBCA77u);
+    double best = 0;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, iters, 0x9E3779B1u, 0x85EBCA77u);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        const double rate = (double)blocks * threads * (double)iters * 8.0 * ILP / (ms * 1e-3);
+        if (rate > best) best = rate;
+    }
+    *per_s = best;
+    return B2_OK;
+}
+
 extern "C" {
 
 int b2_version(void) { return 100; }
@@ -1819,6 +1841,18 @@ int b2_dfma_probe(double* dfma_per_s) {
     }
     *dfma_per_s = best;
     return B2_OK;
+}
+
+int b2_pipe_probe(int kind, double* macs_per_s) {
+    if (!macs_per_s || kind < 0 || kind > 2) return fail(B2_ERR_ARG, "pipe_probe: kind 0..2");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    if (kind == 0) return run_pipe_probe<0>(ctx, macs_per_s);
+    if (kind == 1) return run_pipe_probe<1>(ctx, macs_per_s);
+    return run_pipe_probe<2>(ctx, macs_per_s);
 }
 
 int b2_last_timing(double* kernel_ms, double* total_ms) {
