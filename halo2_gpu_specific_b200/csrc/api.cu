@@ -199,6 +199,19 @@ int dev_get(DeviceCtx** out) {
         CK(cudaGetDeviceProperties(&prop, dev));
         CK(cudaFuncSetAttribute(ntt_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+        {
+            const int tw_extra = (64 << NTT_TWSM) + 16;
+            CK(cudaFuncSetAttribute(ntt_pass_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster4_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(ntt_pass_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + tw_extra));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster4_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
+            CK(cudaFuncSetAttribute(ntt_pass_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + tw_extra));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster4_v3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
+        }
         CK(cudaFuncSetAttribute(ntt_pass_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_mont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_mont_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
@@ -843,7 +856,13 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         a.cl_log = !use_clusters ? 0 : (a.m >= 13 ? 2 : (a.m >= 11 ? 1 : 0));
         const uint32_t mloc = a.m - a.cl_log;
         const uint32_t threads = std::max(32u, 1u << (mloc >= NTT_RMAX ? mloc - NTT_RMAX : 0));
-        const size_t smem = ((size_t)32 << mloc);
+        // kernel variant (see ntt.cuh): 0 = strict butterflies, twiddles through L1; 1 = lazy; 2 = lazy + TMA-staged
+        // shared-memory twiddles; 3 = shared-memory twiddles only; 4 = lazy at 5 CTAs per SM (cluster-of-2 tiles only)
+        static const int variant_env = getenv("B2_NTT_VARIANT") ? atoi(getenv("B2_NTT_VARIANT")) : NTT_DEFAULT_VARIANT;
+        int variant = use_shoup ? variant_env : 0;
+        if (variant == 4 && a.cl_log != 1) variant = 1;
+        const bool tw_sm = (variant == 2 || variant == 3);
+        const size_t smem = ((size_t)32 << mloc) + (tw_sm ? ((size_t)64 << NTT_TWSM) + 16 : 0);
         const uint64_t lines = N >> a.m;
         for (uint64_t c0 = 0; c0 < cols; c0 += 65535) {
             const uint64_t cc = std::min<uint64_t>(65535, cols - c0);
@@ -851,8 +870,12 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
             b.in = a.in + 2ull * c0 * a.in_col_stride;
             b.out = a.out + 2ull * c0 * a.out_col_stride;
             if (a.cl_log == 0) {
-                if (use_shoup) LAUNCH(ctx, ntt_pass_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
-                else LAUNCH(ctx, ntt_pass_mont_kernel, dim3((unsigned)lines, (unsigned)cc), threads, smem, st, b);
+                const dim3 grid((unsigned)lines, (unsigned)cc);
+                if (!use_shoup) LAUNCH(ctx, ntt_pass_mont_kernel, grid, threads, smem, st, b);
+                else if (variant == 1) LAUNCH(ctx, ntt_pass_v1_kernel, grid, threads, smem, st, b);
+                else if (variant == 2) LAUNCH(ctx, ntt_pass_v2_kernel, grid, threads, smem, st, b);
+                else if (variant == 3) LAUNCH(ctx, ntt_pass_v3_kernel, grid, threads, smem, st, b);
+                else LAUNCH(ctx, ntt_pass_kernel, grid, threads, smem, st, b);
             } else {
                 cudaLaunchConfig_t cfg;
                 memset(&cfg, 0, sizeof cfg);
@@ -868,7 +891,18 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
                 cfg.attrs = attr;
                 cfg.numAttrs = 1;
                 cudaError_t le;
-                if (use_shoup)
+                if (use_shoup && variant == 1)
+                    le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v1_kernel, b)
+                                         : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_v1_kernel, b);
+                else if (use_shoup && variant == 2)
+                    le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v2_kernel, b)
+                                         : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_v2_kernel, b);
+                else if (use_shoup && variant == 3)
+                    le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v3_kernel, b)
+                                         : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_v3_kernel, b);
+                else if (use_shoup && variant == 4)
+                    le = cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v4_kernel, b);
+                else if (use_shoup)
                     le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
                                          : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);
                 else
@@ -957,11 +991,11 @@ static int run_pipe_probe(Lane* ctx, double* per_s) {
     const int iters = 4000, ILP = 8;
     const int blocks = ctx->sms * 8, threads = 256;
     unsigned long long* sink = reinterpret_cast<unsigned long long*>(ctx->out96.p);
-    LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, 50, 0x9E3779B1u, 0x85EBCA77u);
+    LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, 50, 0x85EBCA77u);
     double best = 0;
     for (int rep = 0; rep < 3; rep++) {
         CK(cudaEventRecord(ctx->ev[12], st));
-        LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, iters, 0x9E3779B1u, 0x85EBCA77u);
+        LAUNCH(*ctx, (pipe_probe_kernel<ILP, KIND>), blocks, threads, 0, st, sink, iters, 0x85EBCA77u);
         CK(cudaEventRecord(ctx->ev[13], st));
         CK(cudaStreamSynchronize(st));
         float ms = 0;
@@ -1844,15 +1878,14 @@ int b2_dfma_probe(double* dfma_per_s) {
 }
 
 int b2_pipe_probe(int kind, double* macs_per_s) {
-    if (!macs_per_s || kind < 0 || kind > 2) return fail(B2_ERR_ARG, "pipe_probe: kind 0..2");
+    if (!macs_per_s || kind < 0 || kind > 1) return fail(B2_ERR_ARG, "pipe_probe: kind 0..1");
     LaneLock ll;
     int rc = ll.acquire();
     if (rc) return rc;
     Lane* ctx = ll.lane;
     if ((rc = ctx->out96.reserve(96))) return rc;
     if (kind == 0) return run_pipe_probe<0>(ctx, macs_per_s);
-    if (kind == 1) return run_pipe_probe<1>(ctx, macs_per_s);
-    return run_pipe_probe<2>(ctx, macs_per_s);
+    return run_pipe_probe<1>(ctx, macs_per_s);
 }
 
 int b2_last_timing(double* kernel_ms, double* total_ms) {

@@ -914,38 +914,37 @@ __global__ void __launch_bounds__(256) shoup_probe_kernel(uint4* sink, int iters
 }
 
 // Raw multiplier-pipe probes, independent of the field code (the roofline's denominator must not be "how fast my own
-// fp_mul runs"): ILP independent accumulator chains of ONE instruction kind, no carries, no loads.
-//   KIND 0: IMAD.WIDE.U32  (mad.wide.u32: 32 x 32 + 64 -> 64, what every limb product of the bignum kernels is)
-//   KIND 1: IMAD           (mad.lo.u32: 32 x 32 + 32 -> 32, the "64 per clock per SM" instruction of the CUDA guide)
-//   KIND 2: IMAD.WIDE.U32 + carry chain (mad.lo.cc / madc.hi pairs over 4 chained column words, fp_mul's addressing mode)
+// fp_mul runs"): ILP independent accumulator chains of ONE instruction kind, no carries between instructions, no loads.
+//   KIND 0: IMAD.WIDE.U32 Rd, Ra, b, Rd  (32 x 32 + 64 -> 64: every limb product of the bignum kernels; written as the
+//           mad.lo.cc / madc.hi pair the field code uses, which ptxas fuses into one IMAD.WIDE -- check with
+//           tools/sass_stats.py pipe_probe)
+//   KIND 1: IMAD Rd, Rd, b, Rc           (32 x 32 + 32 -> 32, the "64 results per clock per SM" instruction of the CUDA
+//           programming guide's throughput table)
+// One multiplicand is the chain's own running value so that ptxas cannot fold the products into additions.
 template <int ILP, int KIND>
-__global__ void __launch_bounds__(256) pipe_probe_kernel(unsigned long long* sink, int iters, uint32_t a, uint32_t b) {
-    unsigned long long acc[ILP];
-#pragma unroll
-    for (int j = 0; j < ILP; j++) acc[j] = threadIdx.x * 0x9E3779B9ull + j;
+__global__ void __launch_bounds__(256) pipe_probe_kernel(unsigned long long* sink, int iters, uint32_t b) {
     uint32_t lo[ILP], hi[ILP];
 #pragma unroll
-    for (int j = 0; j < ILP; j++) { lo[j] = threadIdx.x + j; hi[j] = j; }
+    for (int j = 0; j < ILP; j++) { lo[j] = threadIdx.x * 0x9E3779B9u + j; hi[j] = threadIdx.x + 17 * j + 1; }
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int u = 0; u < 8; u++) {
 #pragma unroll
             for (int j = 0; j < ILP; j++) {
                 if (KIND == 0) {
-                    asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a), "r"(b));
-                } else if (KIND == 1) {
-                    asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[j]) : "r"(a), "r"(b));
+                    asm volatile("{\n\t.reg .u32 x;\n\tmov.u32 x, %1;\n\tmad.lo.cc.u32 %0, x, %2, %0;\n\t"
+                                 "madc.hi.u32 %1, x, %2, %1;\n\t}"
+                                 : "+r"(lo[j]), "+r"(hi[j]) : "r"(b));
                 } else {
-                    asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;"
-                                 : "+r"(lo[j]), "+r"(hi[j]) : "r"(a), "r"(b));
+                    asm volatile("mad.lo.u32 %0, %0, %2, %1;" : "+r"(lo[j]) : "r"(hi[j]), "r"(b));
                 }
             }
         }
     }
-    unsigned long long x = 0;
+    uint32_t x = 0;
 #pragma unroll
-    for (int j = 0; j < ILP; j++) x += acc[j] + lo[j] + ((unsigned long long)hi[j] << 32);
-    if (x == 0x123456789abcdef0ull) *sink = x;
+    for (int j = 0; j < ILP; j++) x += lo[j] ^ hi[j];
+    if (x == 0x9abcdef0u) *sink = x;
 }
 
 // FP64 FMA throughput probe (is the fp64 pipe a usable second multiplier on this part?)

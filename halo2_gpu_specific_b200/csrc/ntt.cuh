@@ -98,44 +98,130 @@ __global__ void ntt_shoup_table_kernel(const Fr* __restrict__ tw_mont, uint4* __
     planes[3 * plane + pos] = make_uint4(wp.v[4], wp.v[5], wp.v[6], wp.v[7]);
 }
 
-__device__ __forceinline__ void ntt_bfly(Fr& a, Fr& b, const Fr& tw) {
-    Fr t = fp_mul<FrParams>(b, tw);
-    b = fp_sub<FrParams>(a, t);
-    a = fp_add<FrParams>(a, t);
+// ---- lazy (Harvey) butterflies: values live in [0, 4r) between stages (4r < 2^256 for BN254's r) -------------
+// if x >= 2r: x -= 2r
+__device__ __forceinline__ void fr_csub_2r(Fr& x) {
+    uint32_t t[8], borrow;
+    asm("sub.cc.u32 %0, %9, %17;\n\t"
+        "subc.cc.u32 %1, %10, %18;\n\t"
+        "subc.cc.u32 %2, %11, %19;\n\t"
+        "subc.cc.u32 %3, %12, %20;\n\t"
+        "subc.cc.u32 %4, %13, %21;\n\t"
+        "subc.cc.u32 %5, %14, %22;\n\t"
+        "subc.cc.u32 %6, %15, %23;\n\t"
+        "subc.cc.u32 %7, %16, %24;\n\t"
+        "subc.u32 %8, 0, 0;"
+        : "=r"(t[0]), "=r"(t[1]), "=r"(t[2]), "=r"(t[3]), "=r"(t[4]), "=r"(t[5]), "=r"(t[6]), "=r"(t[7]), "=r"(borrow)
+        : "r"(x.v[0]), "r"(x.v[1]), "r"(x.v[2]), "r"(x.v[3]), "r"(x.v[4]), "r"(x.v[5]), "r"(x.v[6]), "r"(x.v[7]),
+          "n"(0xe0000002u), "n"(0x87c3eb27u), "n"(0xf372e122u), "n"(0x5067d090u), "n"(0x0302b0bau), "n"(0x70a08b6du),
+          "n"(0xc2634053u), "n"(0x60c89ce5u));
+#pragma unroll
+    for (int i = 0; i < 8; i++) x.v[i] = borrow ? x.v[i] : t[i];
 }
-// Butterfly of stage s (1-based) of a 2^m-point sub-NTT with twiddle w_{2^s}^jj.
-// SHOUP = true: tw is the stage-major four-plane table of ntt_shoup_table_kernel and the product is the 92-MAC
-// constant multiplication of fp_shoup.cuh; false: tw[j] = w_{2^m}^j in Montgomery form, generic product.
-template <bool SHOUP>
-__device__ __forceinline__ void ntt_bfly_tab(Fr& a, Fr& b, const Fr* __restrict__ tw, uint32_t m, uint32_t s, uint32_t jj) {
+// [0, 4r) -> [0, r)
+__device__ __forceinline__ void fr_reduce_4r(Fr& x) {
+    fr_csub_2r(x);
+    fp_reduce_once<FrParams>(x.v);
+}
+// a, t < 2r:  b = a - t + 2r  (in (0, 4r)),  a = a + t  (< 4r); no reductions
+__device__ __forceinline__ void fr_lazy_addsub(Fr& a, Fr& b, const Fr& t) {
+    asm("add.cc.u32 %0, %8, %16;\n\t"
+        "addc.cc.u32 %1, %9, %17;\n\t"
+        "addc.cc.u32 %2, %10, %18;\n\t"
+        "addc.cc.u32 %3, %11, %19;\n\t"
+        "addc.cc.u32 %4, %12, %20;\n\t"
+        "addc.cc.u32 %5, %13, %21;\n\t"
+        "addc.cc.u32 %6, %14, %22;\n\t"
+        "addc.u32 %7, %15, %23;"
+        : "=&r"(b.v[0]), "=&r"(b.v[1]), "=&r"(b.v[2]), "=&r"(b.v[3]), "=&r"(b.v[4]), "=&r"(b.v[5]), "=&r"(b.v[6]),
+          "=&r"(b.v[7])
+        : "r"(a.v[0]), "r"(a.v[1]), "r"(a.v[2]), "r"(a.v[3]), "r"(a.v[4]), "r"(a.v[5]), "r"(a.v[6]), "r"(a.v[7]),
+          "n"(0xe0000002u), "n"(0x87c3eb27u), "n"(0xf372e122u), "n"(0x5067d090u), "n"(0x0302b0bau), "n"(0x70a08b6du),
+          "n"(0xc2634053u), "n"(0x60c89ce5u));
+    asm("sub.cc.u32 %0, %0, %8;\n\t"
+        "subc.cc.u32 %1, %1, %9;\n\t"
+        "subc.cc.u32 %2, %2, %10;\n\t"
+        "subc.cc.u32 %3, %3, %11;\n\t"
+        "subc.cc.u32 %4, %4, %12;\n\t"
+        "subc.cc.u32 %5, %5, %13;\n\t"
+        "subc.cc.u32 %6, %6, %14;\n\t"
+        "subc.u32 %7, %7, %15;"
+        : "+r"(b.v[0]), "+r"(b.v[1]), "+r"(b.v[2]), "+r"(b.v[3]), "+r"(b.v[4]), "+r"(b.v[5]), "+r"(b.v[6]), "+r"(b.v[7])
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]));
+    asm("add.cc.u32 %0, %0, %8;\n\t"
+        "addc.cc.u32 %1, %1, %9;\n\t"
+        "addc.cc.u32 %2, %2, %10;\n\t"
+        "addc.cc.u32 %3, %3, %11;\n\t"
+        "addc.cc.u32 %4, %4, %12;\n\t"
+        "addc.cc.u32 %5, %5, %13;\n\t"
+        "addc.cc.u32 %6, %6, %14;\n\t"
+        "addc.u32 %7, %7, %15;"
+        : "+r"(a.v[0]), "+r"(a.v[1]), "+r"(a.v[2]), "+r"(a.v[3]), "+r"(a.v[4]), "+r"(a.v[5]), "+r"(a.v[6]), "+r"(a.v[7])
+        : "r"(t.v[0]), "r"(t.v[1]), "r"(t.v[2]), "r"(t.v[3]), "r"(t.v[4]), "r"(t.v[5]), "r"(t.v[6]), "r"(t.v[7]));
+}
+
+// Where a sub-NTT's butterfly twiddles come from: the stage-major four-plane Shoup table in global memory, and for
+// the first sm_stages stages (positions 0 .. 2^sm_stages - 2 of every plane) a copy staged into shared memory by one
+// cp.async.bulk per plane at kernel start (TMA bulk copy, completion on an mbarrier).
+struct NttTw {
+    const Fr* g;            // global table (Shoup planes or Montgomery table)
+    const uint4* sm;        // shared-memory copy of the first sm_n entries of each plane (nullptr: none)
+    uint32_t sm_stages;     // stages 1 .. sm_stages are served from shared memory
+    uint32_t sm_n;          // entries per shared plane
+    uint32_t m;             // log size of the whole sub-NTT (plane stride / Montgomery table stride)
+};
+
+// butterfly of stage s with twiddle w_{2^s}^jj; LAZY: inputs and outputs in [0, 4r)
+template <bool SHOUP, bool LAZY>
+__device__ __forceinline__ void ntt_bfly_tw(Fr& a, Fr& b, const NttTw& tw, uint32_t s, uint32_t jj) {
     Fr t;
     if (SHOUP) {
-        const uint4* pl = reinterpret_cast<const uint4*>(tw) + ((1u << (s - 1)) - 1u + jj);
-        const size_t plane = (size_t)1 << m;
-        const uint4 w0 = __ldg(pl), w1 = __ldg(pl + plane), p0 = __ldg(pl + 2 * plane), p1 = __ldg(pl + 3 * plane);
+        const uint32_t pos = (1u << (s - 1)) - 1u + jj;
+        uint4 w0, w1, p0, p1;
+        if (tw.sm != nullptr && s <= tw.sm_stages) {
+            const uint4* pl = tw.sm + pos;
+            w0 = pl[0]; w1 = pl[tw.sm_n]; p0 = pl[2 * tw.sm_n]; p1 = pl[3 * tw.sm_n];
+        } else {
+            const uint4* pl = reinterpret_cast<const uint4*>(tw.g) + pos;
+            const size_t plane = (size_t)1 << tw.m;
+            w0 = __ldg(pl); w1 = __ldg(pl + plane); p0 = __ldg(pl + 2 * plane); p1 = __ldg(pl + 3 * plane);
+        }
         Fr w, wp;
         w.v[0] = w0.x; w.v[1] = w0.y; w.v[2] = w0.z; w.v[3] = w0.w;
         w.v[4] = w1.x; w.v[5] = w1.y; w.v[6] = w1.z; w.v[7] = w1.w;
         wp.v[0] = p0.x; wp.v[1] = p0.y; wp.v[2] = p0.z; wp.v[3] = p0.w;
         wp.v[4] = p1.x; wp.v[5] = p1.y; wp.v[6] = p1.z; wp.v[7] = p1.w;
-        t = fr_mul_shoup(b, w, wp);
+        t = LAZY ? fr_mul_shoup_lazy(b, w, wp) : fr_mul_shoup(b, w, wp);
     } else {
-        t = fp_mul<FrParams>(b, fp_load_nc<FrParams>(tw + ((size_t)jj << (m - s))));
+        t = fp_mul<FrParams>(b, fp_load_nc<FrParams>(tw.g + ((size_t)jj << (tw.m - s))));
     }
-    b = fp_sub<FrParams>(a, t);
-    a = fp_add<FrParams>(a, t);
+    if (LAZY) {
+        fr_csub_2r(t);
+        fr_csub_2r(a);
+        fr_lazy_addsub(a, b, t);
+    } else {
+        b = fp_sub<FrParams>(a, t);
+        a = fp_add<FrParams>(a, t);
+    }
 }
-__device__ __forceinline__ void ntt_bfly1(Fr& a, Fr& b) {  // twiddle == 1
+template <bool LAZY>
+__device__ __forceinline__ void ntt_bfly_one(Fr& a, Fr& b) {  // twiddle == 1
     Fr t = b;
-    b = fp_sub<FrParams>(a, t);
-    a = fp_add<FrParams>(a, t);
+    if (LAZY) {
+        fr_csub_2r(t);
+        fr_csub_2r(a);
+        fr_lazy_addsub(a, b, t);
+    } else {
+        b = fp_sub<FrParams>(a, t);
+        a = fp_add<FrParams>(a, t);
+    }
 }
 
 // One group of R consecutive DIT stages (s0+1 .. s0+R) on the shared-memory tile.
-template <int R, bool FIRST, bool SHOUP>
-__device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* __restrict__ tw, uint32_t m,
+template <int R, bool FIRST, bool SHOUP, bool LAZY>
+__device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const NttTw& tw,
                                          uint32_t mloc, uint32_t s0, uint32_t hs) {
-    // m: log size of the whole sub-NTT (twiddle stride); mloc: log size of the part in this CTA
+    // tw.m: log size of the whole sub-NTT (twiddle stride); mloc: log size of the part in this CTA
     constexpr int E = 1 << R;
     const uint32_t items = 1u << (mloc - R);
     for (uint32_t w = threadIdx.x; w < items; w += blockDim.x) {
@@ -153,10 +239,10 @@ __device__ __forceinline__ void ntt_step(uint4* s_lo4, uint4* s_hi4, const Fr* _
                 if (q & (1 << st)) continue;
                 const int lowq = q & ((1 << st) - 1);
                 if (FIRST && lowq == 0) {
-                    ntt_bfly1(x[q], x[q | (1 << st)]);
+                    ntt_bfly_one<LAZY>(x[q], x[q | (1 << st)]);
                 } else {
                     const uint32_t jj = low + ((uint32_t)lowq << s0);
-                    ntt_bfly_tab<SHOUP>(x[q], x[q | (1 << st)], tw, m, s0 + st + 1, jj);
+                    ntt_bfly_tw<SHOUP, LAZY>(x[q], x[q | (1 << st)], tw, s0 + st + 1, jj);
                 }
             }
         }
@@ -189,7 +275,12 @@ __device__ __forceinline__ uint64_t ntt_digit_reverse(uint64_t v, const uint32_t
 // CTA, the last CL_LOG stages exchange through distributed shared memory.  This keeps 2-3 CTAs
 // resident per SM for 2^12 / 2^13-point digits (a single CTA with a 128 KB tile runs alone on its
 // SM and exposes its load / store latency), and lets k = 25, 26 run in two passes.
-template <int CL_LOG, bool SHOUP>
+// TWSM > 0: the twiddles of the first min(TWSM, m) stages are staged into shared memory with cp.async.bulk (one bulk
+// copy per plane, issued by one thread before the tile is loaded, completion awaited on an mbarrier before the first
+// butterfly that needs them).  Dynamic shared memory: tile (32 B << mloc) | 4 planes x 2^TWSM x 16 B | mbarrier.
+__device__ __forceinline__ uint32_t ntt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int CL_LOG, bool SHOUP, bool LAZY = false, int TWSM = 0>
 __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     namespace cg = cooperative_groups;
     extern __shared__ uint4 ntt_smem[];
@@ -199,6 +290,36 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
     const uint32_t hs = (mloc >= 9) ? (mloc - 3) : 31u;
     uint32_t rank = 0;
     if (CL_LOG > 0) rank = cg::this_cluster().block_rank();
+
+    NttTw tw;
+    tw.g = a.tw_sub;
+    tw.m = m;
+    tw.sm = nullptr;
+    tw.sm_stages = 0;
+    tw.sm_n = 0;
+    if (TWSM > 0 && SHOUP) {
+        const uint32_t st = min(m, (uint32_t)TWSM);
+        uint4* sm_tw = ntt_smem + 2 * Nloc;
+        unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sm_tw + (4u << TWSM));
+        tw.sm = sm_tw;
+        tw.sm_stages = st;
+        tw.sm_n = 1u << TWSM;
+        if (threadIdx.x == 0) {
+            const uint32_t mb = ntt_smem_u32(mbar);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            const uint32_t bytes = 16u << st;                       // per plane: entries 0 .. 2^st - 1
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(4u * bytes) : "memory");
+            const uint4* g = reinterpret_cast<const uint4*>(a.tw_sub);
+#pragma unroll
+            for (int pl = 0; pl < 4; pl++) {
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(ntt_smem_u32(sm_tw + (size_t)pl * tw.sm_n)), "l"(g + ((size_t)pl << m)), "r"(bytes),
+                               "r"(mb)
+                             : "memory");
+            }
+        }
+    }
 
     const uint64_t line = blockIdx.x >> CL_LOG;
     const uint64_t col = blockIdx.y;
@@ -230,23 +351,37 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
         const uint32_t pl = mloc ? (__brev(jl) >> (32 - mloc)) : 0u;
         sm_st(s_lo4, s_hi4, ntt_swz(pl, hs), x);
     }
-    __syncthreads();
+    __syncthreads();   // also publishes the mbarrier initialisation to the waiting threads
+    if (TWSM > 0 && SHOUP) {
+        // twiddle planes have landed (phase 0 of the mbarrier completes when all four bulk copies are in)
+        const uint32_t mb = ntt_smem_u32(ntt_smem + 2 * Nloc + (4u << TWSM));
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "NTT_TW_WAIT:\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+            "@p bra NTT_TW_DONE;\n\t"
+            "bra NTT_TW_WAIT;\n\t"
+            "NTT_TW_DONE:\n\t"
+            "}" ::"r"(mb)
+            : "memory");
+    }
 
     // ---- local DIT stages, three per shared-memory round trip ----
     uint32_t s0 = 0;
     {
         const uint32_t r = mloc < NTT_RMAX ? mloc : NTT_RMAX;
-        if (r == 3) ntt_step<3, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
-        else if (r == 2) ntt_step<2, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
-        else if (r == 1) ntt_step<1, true, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, 0, hs);
+        if (r == 3) ntt_step<3, true, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, 0, hs);
+        else if (r == 2) ntt_step<2, true, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, 0, hs);
+        else if (r == 1) ntt_step<1, true, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, 0, hs);
         s0 = r;
         __syncthreads();
     }
     while (s0 < mloc) {
         const uint32_t r = (mloc - s0) < NTT_RMAX ? (mloc - s0) : NTT_RMAX;
-        if (r == 3) ntt_step<3, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
-        else if (r == 2) ntt_step<2, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
-        else ntt_step<1, false, SHOUP>(s_lo4, s_hi4, a.tw_sub, m, mloc, s0, hs);
+        if (r == 3) ntt_step<3, false, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, s0, hs);
+        else if (r == 2) ntt_step<2, false, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, s0, hs);
+        else ntt_step<1, false, SHOUP, LAZY>(s_lo4, s_hi4, tw, mloc, s0, hs);
         s0 += r;
         __syncthreads();
     }
@@ -276,7 +411,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
                 const uint32_t sw = ntt_swz(i, hs);
                 Fr xa = sm_ld(a_lo, a_hi, sw);
                 Fr xb = sm_ld(b_lo, b_hi, sw);
-                ntt_bfly_tab<SHOUP>(xa, xb, a.tw_sub, m, mloc + q + 1, jj_hi | i);
+                ntt_bfly_tw<SHOUP, LAZY>(xa, xb, tw, mloc + q + 1, jj_hi | i);
                 sm_st(a_lo, a_hi, sw, xa);
                 sm_st(b_lo, b_hi, sw, xb);
             }
@@ -296,6 +431,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
         for (uint32_t il = threadIdx.x; il < Nloc; il += blockDim.x) {
             const uint32_t j = (rank << mloc) | il;
             Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(il, hs));
+            if (LAZY) fr_reduce_4r(x);
             const uint64_t opart = ntt_digit_reverse((H << m) | j, a.mm, (int)a.pass + 1);
             const uint64_t e = (i_next * opart) << shift;
             if (full) {
@@ -320,6 +456,7 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
             Fr x = sm_ld(s_lo4, s_hi4, ntt_swz(il, hs));
             const uint64_t o = ntt_digit_reverse((H << m) | j, a.mm, (int)a.npass);
             if (o >= a.n_out) continue;
+            if (LAZY) fr_reduce_4r(x);
             if (a.scale_out) x = fp_mul<FrParams>(x, a.scale);
             if (a.coset_out) {
                 const uint32_t r3 = (uint32_t)(o % 3ull);
@@ -334,6 +471,23 @@ __device__ __forceinline__ void ntt_pass_impl(const NttPassArgs& a) {
 __global__ void __launch_bounds__(512) ntt_pass_kernel(const NttPassArgs a) { ntt_pass_impl<0, true>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, true>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
+// Variants selected by B2_NTT_VARIANT (A/B measurements; the default is chosen in ntt_run_dev):
+//   1: lazy butterflies   2: lazy + twiddles of stages 1..8 staged into shared memory by TMA bulk copies
+//   3: shared-memory twiddles only   4: lazy, 5 CTAs per SM (<= 102 registers)
+constexpr int NTT_TWSM = 8;
+#ifndef NTT_DEFAULT_VARIANT
+#define NTT_DEFAULT_VARIANT 0
+#endif
+__global__ void __launch_bounds__(512) ntt_pass_v1_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, true, 0>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v1_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v1_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, true, 0>(a); }
+__global__ void __launch_bounds__(512) ntt_pass_v2_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, true, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v2_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v2_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, true, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(512) ntt_pass_v3_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, false, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v3_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, false, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v3_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, false, NTT_TWSM>(a); }
+__global__ void __launch_bounds__(128, 5) ntt_pass_cluster2_v4_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
 // Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
 __global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
 __global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }

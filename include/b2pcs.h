@@ -367,11 +367,9 @@ int b2_shoup_probe(double* muls_per_s);
  * -DB2_FP_GEN (generated variants that measured slower, see csrc/fp.cuh) and return B2_ERR_ARG otherwise. */
 int b2_mul_probe(int kind, double* per_s);
 /* Raw multiplier-pipe rates, independent of the field code (8 independent accumulator chains of one instruction kind
- * per thread, no carries between chains, no loads): per-thread multiply-accumulates per second of
- *   kind 0: IMAD.WIDE.U32 (32 x 32 + 64 -> 64; every limb product of the bignum kernels),
- *   kind 1: IMAD (32 x 32 + 32 -> 32; the "64 results per clock per SM" instruction of the CUDA programming guide),
- *   kind 2: the mad.lo.cc / madc.hi pair that ptxas fuses into IMAD.WIDE with carry-in (fp_mul's addressing mode);
- *           counted as one MAC per pair.
+ * per thread, no carries between instructions, no loads): per-thread multiply-accumulates per second of
+ *   kind 0: IMAD.WIDE.U32 Rd, Ra, b, Rd (32 x 32 + 64 -> 64; every limb product of the bignum kernels),
+ *   kind 1: IMAD (32 x 32 + 32 -> 32; the "64 results per clock per SM" instruction of the CUDA programming guide).
  * The roofline of the integer kernels is reported against kind 0 as well as against b2_imad_probe. */
 int b2_pipe_probe(int kind, double* macs_per_s);
 /* FP64 FMA rate of the device (diagnostic: documents why the fp64 pipe is / is not a usable

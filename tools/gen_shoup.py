@@ -247,6 +247,18 @@ __device__ __forceinline__ Fr fr_mul_shoup(const Fr& a, const Fr& w, const Fr& w
     return r;
 }}
 
+// Lazy form for the Harvey-style NTT butterflies: the same quotient estimate and remainder WITHOUT the final
+// conditional subtractions.  For ANY a < 2^256 (in particular a < 4r): the result is congruent to a * w mod r and
+// lies in [0, 4r) -- t0 = a*w - floor(a*wp / 2^256) * r < r * (1 + a / 2^256) < 2r, and the estimate is at most 2 below
+// the exact floor.  4r < 2^256 for BN254's r, so nothing wraps.
+__device__ __forceinline__ Fr fr_mul_shoup_lazy(const Fr& a, const Fr& w, const Fr& wp) {{
+    uint32_t qe[9], qo[9], q[8], re[8], ro[8];   // qe/qo index = position - 7
+    Fr r;
+{code}
+    r.v[0] = re[0];
+    return r;
+}}
+
 // Shoup companion of a twiddle given in Montgomery form wm = w * 2^256 mod r:
 //   floor(w * 2^256 / r) = (w * 2^256 - wm) / r = wm * (-r^-1) mod 2^256   (the division is exact)
 __device__ __forceinline__ Fr fr_shoup_companion(const Fr& wm) {{
@@ -292,7 +304,26 @@ def selftest(g, n_random=20000):
         q = sum(env[f'q{i}'] << 32 * i for i in range(8))
         assert 0 <= a * w // r - q <= 2
         assert res == a * w - q * r and res < 3 * r, (hex(a), hex(w))
-    return len(cases)
+    # lazy form: unreduced inputs (anything below 2^256; the butterflies keep values below 4r)
+    lazy_edge = [4 * r - 1, 4 * r - 2, 3 * r, 2 * r, 2 * r - 1, BETA - 1, BETA - 2, (1 << 255), 3 * r + 12345]
+    lazy_cases = [(a, w) for a in lazy_edge for w in edge] + \
+                 [(random.randrange(4 * r), random.randrange(r)) for _ in range(n_random)] + \
+                 [(random.randrange(BETA), random.randrange(r)) for _ in range(n_random // 4)]
+    for a, w in lazy_cases:
+        wp = (w << 256) // r
+        env = {}
+        for i in range(8):
+            env[f'a{i}'] = (a >> 32 * i) & M32
+            env[f'w{i}'] = (w >> 32 * i) & M32
+            env[f'wp{i}'] = (wp >> 32 * i) & M32
+            env[f'pp{i}'] = (pp >> 32 * i) & M32
+        emulate(g, env)
+        env['r0'] = env['re0']
+        res = sum(env[f'r{i}'] << 32 * i for i in range(8))
+        q = sum(env[f'q{i}'] << 32 * i for i in range(8))
+        assert 0 <= a * w // r - q <= 2, (hex(a), hex(w))
+        assert res == a * w - q * r and res < 4 * r and res < BETA, (hex(a), hex(w))
+    return len(cases) + len(lazy_cases)
 
 
 if __name__ == '__main__':
