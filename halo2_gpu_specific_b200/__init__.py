@@ -13,6 +13,7 @@ from .arithmetic import (  # noqa: F401
     gpu_fft,
     gpu_ifft,
     gpu_multiexp,
+    gpu_multiexp_async,
     gpu_multiexp_bound,
     gpu_multiexp_bound_and_fft,
     gpu_multiexp_single_gpu_with_bound,
@@ -23,7 +24,7 @@ from .domain import EvaluationDomain  # noqa: F401
 from .evaluation import Evaluator, QuotientProgram  # noqa: F401
 
 __all__ = [
-    "best_fft", "best_multiexp", "best_multiexp_gpu_cond", "gpu_fft", "gpu_ifft", "gpu_multiexp",
+    "best_fft", "best_multiexp", "best_multiexp_gpu_cond", "gpu_fft", "gpu_ifft", "gpu_multiexp", "gpu_multiexp_async",
     "gpu_multiexp_bound", "gpu_multiexp_bound_and_fft", "gpu_multiexp_single_gpu_with_bound",
     "Params", "ParamsVerifier", "EvaluationDomain", "small_multiexp", "Evaluator", "QuotientProgram",
 ]

@@ -48,7 +48,7 @@ SYMBOLS = [
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
-    "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
+    "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_msm_async", "b2_msm_wait", "b2_logup_multiplicity_dev", "b2_eval_polynomials_dev", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
     "b2_g1_decompress", "b2_g1_compress", "b2_srs_register_compressed", "b2_srs_read_compressed",
     "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev", "b2_poly_combine", "b2_poly_combine_dev", "b2_witness_file_columns", "b2_commit_witness_file",
@@ -82,6 +82,9 @@ def lib() -> ctypes.CDLL:
         L.b2_srs_free.argtypes = [u64]
         L.b2_msm.argtypes = [u64, sz, vp, sz, u32, vp]
         L.b2_msm_dev.argtypes = [u64, sz, vp, sz, u32, vp, vp]
+        L.b2_msm_async.argtypes = [u64, sz, vp, sz, u32, vp, ctypes.POINTER(u64)]
+        L.b2_msm_wait.argtypes = [u64]
+        L.b2_logup_multiplicity_dev.argtypes = [vp, u32, vp, u64, u64, vp, ctypes.POINTER(u64)]
         L.b2_best_multiexp.argtypes = [vp, vp, sz, vp]
         L.b2_g1_sum.argtypes = [vp, sz, vp]
         L.b2_g1_sum_dev.argtypes = [vp, sz, vp, vp]
@@ -121,6 +124,7 @@ def lib() -> ctypes.CDLL:
         L.b2_srs_read_compressed.argtypes = [u64, sz, sz, u32, vp]
         L.b2_eval_polynomial.argtypes = [vp, u64, vp, vp]
         L.b2_eval_polynomial_dev.argtypes = [vp, u64, u64, u64, vp, vp]
+        L.b2_eval_polynomials_dev.argtypes = [ctypes.POINTER(vp), u64, u64, vp, vp]
         L.b2_kate_division.argtypes = [vp, u64, vp, vp]
         L.b2_kate_division_dev.argtypes = [vp, u64, vp, vp, vp]
         L.b2_poly_combine_dev.argtypes = [ctypes.POINTER(vp), ctypes.c_uint32, u64, vp, vp, vp]

@@ -98,6 +98,35 @@ def _identity() -> np.ndarray:
     return out
 
 
+class MsmFuture:
+    """A multiexp in flight (b2_msm_async): `result()` blocks until the point is there.  Keeps the scalar array alive."""
+
+    def __init__(self, ticket: int, out: np.ndarray, keep):
+        self._ticket, self._out, self._keep, self._done = ticket, out, keep, False
+
+    def result(self) -> np.ndarray:
+        if not self._done:
+            self._done = True
+            check(lib().b2_msm_wait(self._ticket))
+            self._keep = None
+        return self._out
+
+
+def gpu_multiexp_async(coeffs, srs: "Srs", max_bits: int = _fr.NUM_BITS) -> MsmFuture:
+    """gpu_multiexp_single_gpu_with_bound (arithmetic.rs:334-367) without waiting for the result: the copy of the
+    scalars, the MSM and the read-back are enqueued on a free lane and a future is returned, so ONE caller thread can
+    keep the copy of column c + 1 under the kernels of column c (the reference overlaps them with several rayon
+    workers).  `coeffs` must not be modified until `.result()` returns; pinned memory keeps this call non-blocking."""
+    c = as_fr(coeffs)
+    if c.shape[0] != len(srs):
+        raise B2Error(B2_ERR_ARG, f"coeffs ({c.shape[0]}) and bases ({len(srs)}) differ in length")
+    require_gpu()
+    out = np.zeros(12, dtype=np.uint64)
+    t = ctypes.c_uint64()
+    check(lib().b2_msm_async(srs.handle, srs.offset, ptr(c), c.shape[0], int(max_bits), ptr(out), ctypes.byref(t)))
+    return MsmFuture(t.value, out, c)
+
+
 def gpu_multiexp_single_gpu_with_bound(coeffs, bases: Bases, max_bits: int) -> np.ndarray:
     """arithmetic.rs:334-367.  max_bits == 0 -> identity (:346)."""
     c = as_fr(coeffs)

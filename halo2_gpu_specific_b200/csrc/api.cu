@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@
 #include "quotient.cuh"
 #include "scan.cuh"
 #include "encoding.cuh"
+#include "lookup.cuh"
 
 using namespace b2;
 
@@ -149,6 +151,8 @@ struct Lane {
     Buf qtab, qspill;
     // batch inversion / prefix scans
     Buf scan_tmp, scan_tot;
+    // logup multiplicities: canonical / sorted table keys, row permutations, radix histograms, counts
+    Buf lk_keys, lk_skeys, lk_idx_a, lk_idx_b, lk_hist, lk_offs, lk_counts, lk_flags;
     // pinned landing zone of small device-to-host results (commitments of a batch)
     PinnedBuf h_stage;
     // timing
@@ -204,6 +208,7 @@ int dev_get(DeviceCtx** out) {
             CK(cudaFuncSetAttribute(ntt_pass_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_cluster2_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_cluster2_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_cluster4_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + tw_extra));
             CK(cudaFuncSetAttribute(ntt_pass_cluster2_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
@@ -860,7 +865,7 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         // shared-memory twiddles; 3 = shared-memory twiddles only; 4 = lazy at 5 CTAs per SM (cluster-of-2 tiles only)
         static const int variant_env = getenv("B2_NTT_VARIANT") ? atoi(getenv("B2_NTT_VARIANT")) : NTT_DEFAULT_VARIANT;
         int variant = use_shoup ? variant_env : 0;
-        if (variant == 4 && a.cl_log != 1) variant = 1;
+        if ((variant == 4 || variant == 5) && (a.cl_log != 1 || threads > 128)) variant = 1;
         const bool tw_sm = (variant == 2 || variant == 3);
         const size_t smem = ((size_t)32 << mloc) + (tw_sm ? ((size_t)64 << NTT_TWSM) + 16 : 0);
         const uint64_t lines = N >> a.m;
@@ -902,6 +907,8 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
                                          : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_v3_kernel, b);
                 else if (use_shoup && variant == 4)
                     le = cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v4_kernel, b);
+                else if (use_shoup && variant == 5)
+                    le = cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v5_kernel, b);
                 else if (use_shoup)
                     le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
                                          : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);
@@ -1254,6 +1261,87 @@ int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32
     CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
     ctx->last_total_ms = ms;
     g_last.total_ms = ms;
+    return B2_OK;
+}
+
+// ---- asynchronous host-pointer MSM: one caller thread keeps several MSMs in flight (the copy of column c + 1 runs
+// under the kernels of column c on another lane), as the reference's rayon workers do with several threads
+struct MsmTicket {
+    LaneLock ll;
+    void* out = nullptr;
+    bool identity = false;
+};
+std::mutex g_ticket_mu;
+std::map<uint64_t, MsmTicket*> g_tickets;
+uint64_t g_next_ticket = 1;
+
+int b2_msm_async(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96,
+                 uint64_t* ticket) {
+    if (!out_jac96 || !ticket || (n && !scalars)) return fail(B2_ERR_ARG, "msm_async: null pointer");
+    Srs s;
+    int rc = srs_lookup(srs, &s);
+    if (rc) return rc;
+    if (offset + n > s.n)
+        return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
+    std::unique_ptr<MsmTicket> t(new MsmTicket());
+    if ((rc = t->ll.acquire())) return rc;
+    Lane* ctx = t->ll.lane;
+    if (s.device != ctx->dev->dev)
+        return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
+    cudaStream_t st = ctx->stream;
+    t->out = out_jac96;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    if ((rc = ctx->h_stage.reserve(96))) return rc;
+    if (n == 0 || max_bits == 0) {
+        t->identity = true;
+    } else {
+        if ((rc = ctx->scalars.reserve(n * 32))) return rc;
+        CK(cudaEventRecord(ctx->ev[8], st));
+        CK(cudaMemcpyAsync(ctx->scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, st));
+        if ((rc = msm_run_split(*ctx, s, offset, ctx->scalars.as<char>(), n, max_bits, ctx->out96.p, st, true))) {
+            cudaStreamSynchronize(st);      // nothing of this call may still read the caller's scalars
+            return rc;
+        }
+        // the 96-byte result lands in the lane's pinned staging buffer (a copy into pageable caller memory would
+        // block this call until the kernels are done)
+        CK(cudaMemcpyAsync(ctx->h_stage.p, ctx->out96.p, 96, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev[9], st));
+    }
+    std::lock_guard<std::mutex> lk(g_ticket_mu);
+    const uint64_t id = g_next_ticket++;
+    g_tickets[id] = t.release();
+    *ticket = id;
+    return B2_OK;
+}
+
+int b2_msm_wait(uint64_t ticket) {
+    MsmTicket* raw = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ticket_mu);
+        auto it = g_tickets.find(ticket);
+        if (it == g_tickets.end()) return fail(B2_ERR_HANDLE, "unknown MSM ticket %llu", (unsigned long long)ticket);
+        raw = it->second;
+        g_tickets.erase(it);
+    }
+    std::unique_ptr<MsmTicket> t(raw);       // releases the lane on every path out of here
+    Lane* ctx = t->ll.lane;
+    CK(cudaSetDevice(ctx->dev->dev));
+    if (t->identity) {
+        uint64_t v[12];
+        memset(v, 0, sizeof v);
+        memcpy(v + 4, HQ_ONE, 32);
+        memcpy(t->out, v, 96);
+        return B2_OK;
+    }
+    int rc = check_bound_flag(*ctx, ctx->stream);     // synchronises the lane's stream
+    if (rc) return rc;
+    memcpy(t->out, ctx->h_stage.p, 96);
+    jac_normalise_host(t->out);
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]));
+    ctx->last_total_ms = ms;
+    g_last.total_ms = ms;
+    g_last.lane = ctx;
     return B2_OK;
 }
 
@@ -1909,3 +1997,4 @@ int b2_last_msm_phases(double* phases) {
 #include "api_quotient.inl"
 #include "api_scan.inl"
 #include "api_encoding.inl"
+#include "api_lookup.inl"

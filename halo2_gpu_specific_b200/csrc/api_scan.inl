@@ -161,9 +161,24 @@ int hr_inv(uint64_t r[4], const uint64_t a[4]) {   // a^(r - 2)
 
 extern "C" {
 
+static int eval_polys_impl(const void* d_polys, const void* const* h_ptrs, uint64_t columns, uint64_t stride, uint64_t n,
+                           const void* point, void* out_host);
+
 int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t stride, uint64_t n, const void* point,
                            void* out_host) {
     if (!d_polys || !point || !out_host || n == 0 || stride < n) return fail(B2_ERR_ARG, "eval_polynomial: bad arguments");
+    return eval_polys_impl(d_polys, nullptr, columns, stride, n, point, out_host);
+}
+
+int b2_eval_polynomials_dev(const void* const* d_poly_ptrs, uint64_t count, uint64_t n, const void* point, void* out_host) {
+    if ((count && !d_poly_ptrs) || !point || !out_host || n == 0) return fail(B2_ERR_ARG, "eval_polynomials: bad arguments");
+    for (uint64_t i = 0; i < count; i++)
+        if (!d_poly_ptrs[i]) return fail(B2_ERR_ARG, "eval_polynomials: null polynomial pointer");
+    return eval_polys_impl(nullptr, d_poly_ptrs, count, n, n, point, out_host);
+}
+
+static int eval_polys_impl(const void* d_polys, const void* const* h_ptrs, uint64_t columns, uint64_t stride, uint64_t n,
+                           const void* point, void* out_host) {
     if (columns == 0) return B2_OK;
     if (columns > 65535) return fail(B2_ERR_ARG, "eval_polynomial: at most 65535 polynomials per call");
     LaneLock ll;
@@ -174,11 +189,18 @@ int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t strid
     const uint64_t threads = (n + EVAL_C - 1) / EVAL_C;
     const uint32_t bpc = (uint32_t)((threads + EVAL_T - 1) / EVAL_T);
     const size_t lo_n = (size_t)1 << EVAL_LO, hi_n = (size_t)(threads >> EVAL_LO) + 1;
-    if ((rc = ctx->scan_tmp.reserve((lo_n + hi_n) * 32 + (size_t)columns * bpc * 32 + (size_t)columns * 32))) return rc;
+    if ((rc = ctx->scan_tmp.reserve((lo_n + hi_n) * 32 + (size_t)columns * bpc * 32 + (size_t)columns * 32 +
+                                    (size_t)columns * 8)))
+        return rc;
     Fr* lo = ctx->scan_tmp.as<Fr>();
     Fr* hi = lo + lo_n;
     uint4* partials = reinterpret_cast<uint4*>(hi + hi_n);
     uint4* d_out = partials + 2ull * columns * bpc;
+    const uint4** d_ptrs = nullptr;
+    if (h_ptrs) {
+        d_ptrs = reinterpret_cast<const uint4**>(d_out + 2ull * columns);
+        CK(cudaMemcpyAsync(d_ptrs, h_ptrs, (size_t)columns * 8, cudaMemcpyHostToDevice, st));
+    }
     const Fr x = fr_from_bytes(point);
     Fr one;
     memcpy(one.v, HR_ONE, 32);
@@ -187,7 +209,7 @@ int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t strid
     LAUNCH(*ctx, ntt_pow_table_kernel, (unsigned)((hi_n + 127) / 128), 128, 0, st, hi, x,
            (unsigned long long)EVAL_C << EVAL_LO, (uint32_t)hi_n, 0, one);
     LAUNCH(*ctx, eval_poly_partial_kernel, dim3(bpc, (unsigned)columns), EVAL_T, 0, st, (const uint4*)d_polys,
-           (unsigned long long)stride, (unsigned long long)n, x, lo, hi, partials, bpc);
+           (unsigned long long)stride, (unsigned long long)n, x, lo, hi, partials, bpc, (const uint4* const*)d_ptrs);
     LAUNCH(*ctx, eval_poly_final_kernel, (unsigned)columns, EVAL_T, 0, st, partials, bpc, d_out);
     CK(cudaMemcpyAsync(out_host, d_out, (size_t)columns * 32, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

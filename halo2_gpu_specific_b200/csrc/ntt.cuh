@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_kernel(con
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
 // Variants selected by B2_NTT_VARIANT (A/B measurements; the default is chosen in ntt_run_dev):
 //   1: lazy butterflies   2: lazy + twiddles of stages 1..8 staged into shared memory by TMA bulk copies
-//   3: shared-memory twiddles only   4: lazy, 5 CTAs per SM (<= 102 registers)
+//   3: shared-memory twiddles only   4 / 5: lazy, 5 / 6 CTAs per SM (<= 102 / 85 registers; 2^10-point CTA tiles only)
 constexpr int NTT_TWSM = 8;
 #ifndef NTT_DEFAULT_VARIANT
 #define NTT_DEFAULT_VARIANT 0
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(512) ntt_pass_v3_kernel(const NttPassArgs a) {
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v3_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v3_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(128, 5) ntt_pass_cluster2_v4_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
+__global__ void __launch_bounds__(128, 6) ntt_pass_cluster2_v5_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
 // Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
 __global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
 __global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }

@@ -228,12 +228,14 @@ constexpr int EVAL_LO = 10;
 __global__ void __launch_bounds__(EVAL_T) eval_poly_partial_kernel(const uint4* __restrict__ polys, unsigned long long stride,
                                                                   unsigned long long n, const Fr x, const Fr* __restrict__ lo,
                                                                   const Fr* __restrict__ hi, uint4* __restrict__ partials,
-                                                                  uint32_t blocks_per_col) {
+                                                                  uint32_t blocks_per_col,
+                                                                  const uint4* const* __restrict__ ptrs = nullptr) {
     __shared__ uint4 sm[2 * EVAL_T];
     const uint32_t col = blockIdx.y;
     const unsigned long long t = (unsigned long long)blockIdx.x * EVAL_T + threadIdx.x;
     const unsigned long long i0 = t * EVAL_C;
-    const uint4* a = polys + 2ull * col * stride;
+    // polynomial `col`: column of a strided block, or (ptrs != nullptr) wherever the pointer table says
+    const uint4* a = ptrs ? ptrs[col] : polys + 2ull * col * stride;
     Fr acc = Fr::zero();
     if (i0 < n) {
         const unsigned long long i1 = min(n, i0 + EVAL_C);

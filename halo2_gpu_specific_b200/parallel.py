@@ -71,6 +71,28 @@ def sharded_msm(scalars_shard: np.ndarray, srs_shard, max_bits: int = 254, *,
     return combine(all_gather_partials(partial))
 
 
+class ShardedMsmFuture:
+    """sharded_msm in flight: the local partial is being computed; result() gathers and combines"""
+
+    def __init__(self, fut, combine):
+        self._fut, self._combine = fut, combine
+
+    def result(self) -> np.ndarray:
+        partial = self._fut.result()
+        _, ws = world()
+        if ws == 1:
+            return np.asarray(partial, dtype=np.uint64).reshape(12)
+        return self._combine(all_gather_partials(partial))
+
+
+def sharded_msm_async(scalars_shard: np.ndarray, srs_shard, max_bits: int = 254) -> ShardedMsmFuture:
+    """sharded_msm whose local part does not wait (arithmetic.gpu_multiexp_async): a caller that commits column after
+    column keeps the upload of the next column under the kernels of this one.  Collectives happen in result(), so
+    every rank must call result() on its futures in the same order."""
+    from . import arithmetic
+    return ShardedMsmFuture(arithmetic.gpu_multiexp_async(scalars_shard, srs_shard, max_bits), arithmetic.g1_sum)
+
+
 # ---- evaluate_h over several GPUs -------------------------------------------------------------------
 def quotient_tasks(n_cosets: int, n: int, world_size: int, rank: int):
     """The extended domain in coset-major order (coset 0 rows 0..n-1, coset 1, ...) is cut into world_size equal

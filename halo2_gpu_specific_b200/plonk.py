@@ -678,7 +678,7 @@ class ResidentEngine:
 
     _PROFILED = ("put", "put_and_commit_lagrange", "commit_lagrange", "commit_lagrange_and_ifft", "commit",
                  "lagrange_to_coeff", "multiplicity_block", "permutation_z", "logup_z", "shuffle_z", "random_poly",
-                 "evaluate_h_blocks", "eval_polynomial", "poly_combine", "sub_constant", "kate_division_padded", "stack",
+                 "evaluate_h_blocks", "eval_polynomial", "eval_polynomials", "poly_combine", "sub_constant", "kate_division_padded", "stack",
                  "sub_low_degree", "scale", "sub_cols", "key_blocks", "release")
 
     def __init__(self, params, domain, profile: bool = False):
@@ -872,19 +872,15 @@ class ResidentEngine:
         n_lookups = len(cs.lookups)
         ms = self.alloc(n_lookups)
         m_bits = 16
-        one = self._const_column("raw_one", _RAW_ONE)
-        r2 = self._const_column("raw_r2", _RAW_R2)
         cols = self._columns(pk, advice, instance)
         for li, lk in enumerate(cs.lookups):
             lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
             comp = self.alloc(len(lists))
             compress_expressions_dev(self.domain, lists, cols, theta, comp.ptr)
-            for i in range(comp.count):                                        # Montgomery -> canonical
-                self._fr_vec(0, comp.ptr + i * n * 32, one, n, comp.ptr + i * n * 32)
             m_col = ms.col(li)
-            largest = logup_multiplicity_device(comp.ptr, len(lists) - 1, usable, n, m_col.ptr)
+            largest = logup_multiplicity_device(comp.ptr, len(lists) - 1, comp.ptr + (len(lists) - 1) * n * 32, usable, n,
+                                                m_col.ptr)
             m_bits = max(m_bits, largest.bit_length())
-            self._fr_vec(0, m_col.ptr, r2, n, m_col.ptr)                       # counts (canonical) -> Montgomery
             self.write_rows(m_col, usable, _mont_vec(blinds[li]))              # logup/prover.rs:232-236
         return ms, m_bits
 
@@ -1012,6 +1008,18 @@ class ResidentEngine:
         pt = _fr.to_mont(point)
         check(lib().b2_eval_polynomial_dev(ctypes.c_void_p(col.ptr), 1, col.n, col.n, ptr(pt), ptr(out)))
         return _fr.from_mont(out)
+
+    def eval_polynomials(self, cols, point: int) -> List[int]:
+        """every polynomial of `cols` at one point with one launch (b2_eval_polynomials_dev)"""
+        import ctypes
+        from ._lib import check, lib, ptr
+        if not cols:
+            return []
+        out = np.empty((len(cols), 4), dtype=np.uint64)
+        pt = _fr.to_mont(point)
+        arr = (ctypes.c_void_p * len(cols))(*[c.ptr for c in cols])
+        check(lib().b2_eval_polynomials_dev(arr, len(cols), cols[0].n, ptr(pt), ptr(out)))
+        return [_fr.from_mont(out[i]) for i in range(len(cols))]
 
     def poly_combine(self, cols, v: int) -> DevBlock:
         import ctypes
@@ -1185,79 +1193,25 @@ def logup_multiplicity(inputs_canonical: Sequence[np.ndarray], table_canonical: 
 
 
 class _DevArray:
-    """raw device memory as a CUDA-array-interface object (so torch can view it without a copy)"""
+    """raw device memory as a CUDA-array-interface object (so torch.distributed can move it without a copy)"""
 
     def __init__(self, ptr: int, shape, typestr: str = "<i8"):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2, "strides": None}
 
 
-def logup_multiplicity_device(comp_ptr: int, n_inputs: int, usable: int, n: int, m_ptr: int) -> int:
-    """logup_multiplicity on resident data.  comp_ptr: (n_inputs + 1) columns of n canonical field elements (the
-    compressed inputs, then the compressed table); m_ptr: receives n canonical elements, the counts in rows
-    < usable and zeros above.  Returns the largest count."""
-    import torch
+def logup_multiplicity_device(inputs_ptr: int, n_inputs: int, table_ptr: int, usable: int, n: int, m_ptr: int) -> int:
+    """logup_multiplicity on resident data (b2_logup_multiplicity_dev: radix sort of the table + the reference's binary
+    search per input value, csrc/lookup.cuh).  inputs_ptr: n_inputs columns of n Montgomery-form field elements (the
+    compressed inputs); table_ptr: the compressed table column; m_ptr receives n Montgomery-form elements: the counts in
+    rows < usable, zeros above.  Returns the largest count."""
+    import ctypes
     from ._lib import check, lib
-    check(lib().b2_synchronize())
-    dev = torch.device("cuda", torch.cuda.current_device())
-    raw = torch.as_tensor(_DevArray(comp_ptr, (n_inputs + 1, n, 4)), device=dev)
-    m = torch.as_tensor(_DevArray(m_ptr, (n, 4)), device=dev)
-    largest = multiplicity_tensors(raw, usable, m)
-    torch.cuda.synchronize(dev)
-    return largest
-
-
-def multiplicity_tensors(raw, usable: int, m) -> int:
-    """The sort / match step of logup/prover.rs:115-184 on int64 tensors holding canonical little-endian limbs
-    (any torch device): raw (n_inputs + 1, n, 4), inputs first, table last; m (n, 4) is overwritten with the counts.
-    Sorting 256-bit keys is plumbing, done with torch: one stable sort per limb over table and inputs together (the
-    table first, so inside a run of equal keys its rows keep their order -- the stable sort of :115-117), then per
-    distinct key the probe sequence of binary_search_by_key (mid = left + size / 2, first Equal probe wins) on the
-    table's run decides which row takes the count.  Returns the largest count."""
-    import torch
-    dev = raw.device
-    n_inputs = raw.shape[0] - 1
-    flip = torch.tensor(-(1 << 63), dtype=torch.int64, device=dev)          # unsigned order on signed int64
-    keys = torch.cat([raw[n_inputs, :usable]] + [raw[i, :usable] for i in range(n_inputs)], dim=0) ^ flip
-    total = keys.shape[0]
-    order = torch.arange(total, device=dev)
-    limbs = [l for l in range(4) if l == 0 or bool((keys[:, l] != flip).any())]    # skip limbs that are zero everywhere
-    for l in limbs:                                                           # least significant limb first
-        order = order[torch.sort(keys[order, l], stable=True).indices]
-    ks = keys[order]
-    new_run = torch.ones(total, dtype=torch.bool, device=dev)
-    new_run[1:] = (ks[1:] != ks[:-1]).any(dim=1)
-    gid = torch.cumsum(new_run.to(torch.int64), 0) - 1                        # run id per sorted position
-    n_groups = int(gid[-1].item()) + 1
-    is_table = order < usable
-    t_count = torch.zeros(n_groups, dtype=torch.int64, device=dev).scatter_add_(0, gid, is_table.to(torch.int64))
-    i_count = torch.zeros(n_groups, dtype=torch.int64, device=dev).scatter_add_(0, gid, (~is_table).to(torch.int64))
-    if bool(((i_count > 0) & (t_count == 0)).any()):
-        raise B2Error(B2_ERR_ARG, "logup binary_search_by_key should hit")
-    table_rows = order[is_table]                                              # table rows in sorted order
-    lo = torch.cumsum(t_count, 0) - t_count                                   # each run's start in that order
-    hi = lo + t_count
-    live = i_count > 0
-    # a table value that occurs once is found at its own position whatever the probe sequence; only runs of repeated
-    # table values need the simulation below
-    found = torch.where(live & (t_count == 1), lo, torch.full((n_groups,), -1, dtype=torch.int64, device=dev))
-    left = torch.zeros(n_groups, dtype=torch.int64, device=dev)
-    right = torch.full((n_groups,), usable, dtype=torch.int64, device=dev)
-    size = right - left
-    while bool((live & (found < 0)).any()):                                   # <= log2(usable) + 1 rounds
-        todo = live & (found < 0)
-        mid = left + torch.div(size, 2, rounding_mode="floor")
-        less = todo & (mid < lo)
-        greater = todo & (mid >= hi)
-        hit = todo & ~less & ~greater
-        found = torch.where(hit, mid, found)
-        left = torch.where(less, mid + 1, left)
-        right = torch.where(greater, mid, right)
-        size = right - left
-    m.zero_()
-    sel = live.nonzero(as_tuple=True)[0]
-    m[:, 0].scatter_add_(0, table_rows[found[sel]], i_count[sel])
-    return int(i_count.max().item())
+    largest = ctypes.c_uint64()
+    vp = ctypes.c_void_p
+    check(lib().b2_logup_multiplicity_dev(vp(inputs_ptr), n_inputs, vp(table_ptr), usable, n, vp(m_ptr),
+                                          ctypes.byref(largest)))
+    return int(largest.value)
 
 
 # --------------------------------------------------------------------------
@@ -1425,33 +1379,48 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
         return known[key]
     advice_polys, inst_cols = E.cols(adv), E.cols(instance_polys)
     fixed_polys, sigma_polys = E.cols(key["fixed_polys"]), E.cols(key["sigma_polys"])
+    # The evaluations are written in the reference's order, but no challenge is drawn between them: list the
+    # (polynomial, point) pairs first, evaluate them with ONE engine call per distinct point, then write.
+    wanted: List[Tuple[object, int]] = []
     for col, at in queries["Instance"]:
-        tr.write_scalar(ev(inst_cols[col], rot(at)))
+        wanted.append((inst_cols[col], rot(at)))
     for col, at in queries["Advice"]:
-        tr.write_scalar(ev(advice_polys[col], rot(at)))
+        wanted.append((advice_polys[col], rot(at)))
     for col, at in queries["Fixed"]:
-        tr.write_scalar(ev(fixed_polys[col], rot(at)))
+        wanted.append((fixed_polys[col], rot(at)))
     h_poly = E.poly_combine(list(reversed(E.cols(h_block))), xn)       # fold acc * xn + piece over rev pieces
-    tr.write_scalar(ev(random_poly, x))
+    wanted.append((random_poly, x))
     for poly in sigma_polys:
-        tr.write_scalar(ev(poly, x))
+        wanted.append((poly, x))
     last = -(bf + 1)
     x_next, x_last = rot(1), rot(last)
 
     def eval_z_set(polys):
         for i, z in enumerate(polys):
-            tr.write_scalar(ev(z, x))
-            tr.write_scalar(ev(z, x_next))
+            wanted.append((z, x))
+            wanted.append((z, x_next))
             if i + 1 < len(polys):
-                tr.write_scalar(ev(z, x_last))
+                wanted.append((z, x_last))
 
     eval_z_set(perm_polys)
     for lk in lookups:
-        tr.write_scalar(ev(lk["m"], x))
+        wanted.append((lk["m"], x))
         eval_z_set(lk["z"])
     for z in shuffle_polys:
-        tr.write_scalar(ev(z, x))
-        tr.write_scalar(ev(z, x_next))
+        wanted.append((z, x))
+        wanted.append((z, x_next))
+    eval_many = getattr(E, "eval_polynomials", None)
+    if eval_many is not None:
+        by_point: Dict[int, list] = {}
+        for poly, point in wanted:
+            if (_poly_key(poly), point) not in known:
+                known[(_poly_key(poly), point)] = None
+                by_point.setdefault(point, []).append(poly)
+        for point, polys in by_point.items():
+            for poly, value in zip(polys, eval_many(polys, point)):
+                known[(_poly_key(poly), point)] = value
+    for poly, point in wanted:
+        tr.write_scalar(ev(poly, point))
     lap("evaluations")
 
     # ---- multiopen queries (:792-838) as (rotation, point, polynomial)

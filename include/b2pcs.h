@@ -104,6 +104,17 @@ int b2_srs_read_compressed(b2_handle_t srs, size_t offset, size_t count, uint32_
  * Zero scalars contribute nothing, so the CPU-side zero filtering of
  * commit_lagrange_with_bound (commitment.rs:204-212) is not needed. */
 int b2_msm(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96);
+/* Asynchronous form of b2_msm for ONE caller thread that wants several columns in flight (the reference gets the same
+ * overlap from several rayon workers, plonk/prover.rs:293-299): enqueues the H2D copy of the scalars, the MSM and the
+ * read-back of the point on a free lane and returns a ticket at once; the copy of the next call then runs under the
+ * kernels of this one.  `scalars` must stay valid and unchanged until b2_msm_wait(ticket) returns (pinned host memory
+ * keeps the call non-blocking); b2_msm_wait blocks until the normalised point is in out_jac96 and returns the
+ * call's status (B2_ERR_BOUND if a scalar exceeded max_bits).  Every ticket must be waited on exactly once; a call
+ * blocks while all lanes (B2_LANES, default 3) are held by unfinished tickets. */
+int b2_msm_async(b2_handle_t srs, size_t offset, const void* scalars, size_t n, uint32_t max_bits, void* out_jac96,
+                 uint64_t* ticket);
+int b2_msm_wait(uint64_t ticket);
+
 /* Same with `scalars` and `out_jac96` in device memory, asynchronous on `stream`
  * (a cudaStream_t, NULL = the library's per-device stream).  The device result is a valid
  * Jacobian point but NOT normalised (the host entry points normalise after the read-back;
@@ -310,6 +321,11 @@ int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, 
  * (plonk/prover.rs:693-760) needs numbers, not polynomials. */
 int b2_eval_polynomial_dev(const void* d_polys, uint64_t columns, uint64_t stride, uint64_t n, const void* point,
                            void* out_host);
+/* The same for `count` polynomials that do not sit in one strided block: d_poly_ptrs is a HOST array of device
+ * pointers (n coefficients each); one launch evaluates them all at `point` -- the evaluation phase of create_proof
+ * (plonk/prover.rs:693-790) makes one call per distinct point instead of one per query. */
+int b2_eval_polynomials_dev(const void* const* d_poly_ptrs, uint64_t count, uint64_t n, const void* point, void* out_host);
+
 int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* out);
 /* kate_division (arithmetic.rs:752-773): q = (a(X) - a(b)) / (X - b), n - 1 coefficients; q must not alias a.
  * Used by the multiopen provers (poly/multiopen/gwc/prover.rs:158, shplonk/prover.rs:23). */
@@ -347,6 +363,17 @@ int b2_dev_free(void* p);
 int b2_memcpy_h2d(void* dst_dev, const void* src_host, size_t bytes);
 int b2_memcpy_d2h(void* dst_host, const void* src_dev, size_t bytes);
 int b2_memcpy_d2d(void* dst_dev, const void* src_dev, size_t bytes);
+
+/* ---- logup multiplicities (plonk/logup/prover.rs:117-179) on device-resident columns ------------------------------
+ * d_inputs: n_inputs compressed input columns of n Fr each (Montgomery form, column stride n); d_table: the compressed
+ * table column (n Fr).  Only rows < usable take part.  The table's usable rows are sorted stably by value on the
+ * device (radix sort of the canonical 256-bit values), every input value is located with the probe sequence of the
+ * pinned toolchain's binary_search_by_key (so that a repeated table value credits the same row as the reference) and
+ * d_m receives the multiplicities as n Montgomery-form Fr (zeros in rows >= usable).  *largest_count = the largest
+ * multiplicity (the bound for commit_lagrange_with_bound, :206-212).  B2_ERR_ARG when an input value is not in the
+ * table ("logup binary_search_by_key should hit", :148).  Synchronous; n < 2^31. */
+int b2_logup_multiplicity_dev(const void* d_inputs, uint32_t n_inputs, const void* d_table, uint64_t usable, uint64_t n,
+                              void* d_m, uint64_t* largest_count);
 
 /* ---- diagnostics used by tests / bench -------------------------------------------- */
 /* out[i] = a[i] op b[i] on the device.  field: 0 Fr, 1 Fq.  op: 0 mul, 1 add, 2 sub, 3 sqr(a),

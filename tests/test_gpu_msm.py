@@ -377,3 +377,29 @@ def test_public_eip196_vectors_through_the_engine(gpu):
         assert _affine(h2.best_multiexp(o.fr_encode([1, 1]), o.g1_affine_encode([a, b]))) == want, v["name"]
         enc = np.stack([o.g1_jacobian_encode(a), o.g1_jacobian_encode(b)])
         assert _affine(h2.arithmetic.g1_sum(enc)) == want, v["name"]
+
+
+def test_async_msm_matches_blocking_and_oracle(gpu):
+    """b2_msm_async / b2_msm_wait: several MSMs in flight from one thread (more tickets than lanes are queued by
+    waiting in order), results equal to the blocking call and to the oracle; bound violations surface at wait()"""
+    from halo2_gpu_specific_b200 import _lib
+    n = 1 << 13
+    bases = _bases(n, 0x71)
+    srs = Srs.register(bases).precompute()
+    cols = [cref.random_fr_mont(n, 0x700 + i) for i in range(5)]
+    want = [_want(c, bases) for c in cols]
+    pending, got = [], []
+    for c in cols:
+        if len(pending) == 2:                       # two in flight, as bench.py drives it
+            got.append(_affine(pending.pop(0).result()))
+        pending.append(h2.gpu_multiexp_async(c, srs))
+    got += [_affine(f.result()) for f in pending]
+    assert got == want
+    assert _affine(h2.gpu_multiexp_async(cols[0][:0], srs[:0]).result()) is None
+    small = cref.random_fr_small_mont(n, 5, 16)
+    assert _affine(h2.gpu_multiexp_async(small, srs, 16).result()) == _want(small, bases)
+    with pytest.raises(_lib.B2Error):
+        h2.gpu_multiexp_async(cols[0], srs, 16).result()
+    # the lane is free again after a failed wait
+    assert _affine(h2.gpu_multiexp_async(cols[1], srs).result()) == want[1]
+    srs.free()

@@ -213,7 +213,8 @@ def test_zkwasm_shaped_circuit(gpu, k):
 
 
 def test_max_bits_and_device_multiplicity_primitives(gpu):
-    """b2_fr_max_bits_dev (find_max_scalar_bits) and the torch sort / match step on device memory"""
+    """b2_fr_max_bits_dev (find_max_scalar_bits) and b2_logup_multiplicity_dev (radix sort of the table + the
+    reference's binary search) against the oracle's logup_multiplicity"""
     import ctypes
     import random
     from halo2_gpu_specific_b200.evaluation import DeviceBuffer
@@ -229,17 +230,45 @@ def test_max_bits_and_device_multiplicity_primitives(gpu):
         assert got.value == max(v.bit_length() for v in vals)
         buf.free()
     usable = n - 6
+
+    def check_case(table, inputs, expect_miss=False):
+        mont = np.stack([enc(col) for col in inputs + [table]])
+        comp = DeviceBuffer((len(inputs) + 1) * n).upload(mont)
+        m = DeviceBuffer(n)
+        try:
+            if expect_miss:
+                with pytest.raises(gpu.B2Error):
+                    HP.logup_multiplicity_device(comp.ptr, len(inputs), comp.ptr + len(inputs) * n * 32, usable, n, m.ptr)
+                return
+            want = PR.logup_multiplicity([inputs], table, usable, n)
+            largest = HP.logup_multiplicity_device(comp.ptr, len(inputs), comp.ptr + len(inputs) * n * 32, usable, n, m.ptr)
+            assert dec(m.download()) == want and largest == max(want)
+        finally:
+            comp.free(); m.free()
+
+    # a table that repeats a few full-width values many times: which of the equal rows takes the count is decided by
+    # the probe sequence of binary_search_by_key
     pool = [rng.randrange(R) for _ in range(40)] + [0, 1, 2]
     table = [rng.choice(pool) for _ in range(n)]
-    inputs = [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(3)]
-    want = PR.logup_multiplicity([inputs], table, usable, n)
-    canon = np.array([[o._to_limbs(v) for v in col] for col in inputs + [table]], dtype=np.uint64)
-    comp = DeviceBuffer(4 * n).upload(canon)
-    m = DeviceBuffer(n)
-    largest = HP.logup_multiplicity_device(comp.ptr, 3, usable, n, m.ptr)
-    got_m = m.download()
-    assert got_m[:, 0].tolist() == want and not got_m[:, 1:].any() and largest == max(want)
-    comp.free(); m.free()
+    check_case(table, [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(3)])
+    # distinct full-width values (theta-compressed multi-column tables): one limb decides the order
+    table = [rng.randrange(R) for _ in range(n)]
+    check_case(table, [[rng.choice(table[:usable]) for _ in range(n)] for _ in range(2)])
+    # a 16-bit range table with zero padding (two radix passes, many equal rows)
+    table = [i if i < 3000 else 0 for i in range(n)]
+    check_case(table, [[rng.randrange(3000) if rng.random() < 0.8 else 0 for _ in range(n)]])
+    # different keys that agree on the most significant differing limb: the lower limbs must be sorted too
+    hi = [rng.randrange(1 << 60) << 192 for _ in range(8)]
+    table = [rng.choice(hi) + rng.randrange(1 << 130) for _ in range(n)]
+    check_case(table, [[rng.choice(table[:usable]) for _ in range(n)]])
+    # all rows equal; no inputs at all
+    check_case([7] * n, [[7] * n])
+    check_case(table, [])
+    # an input value that is not in the table (only the blinding rows hold it)
+    table = list(range(n))
+    bad = [5] * n
+    bad[17] = usable + 1
+    check_case(table, [bad], expect_miss=True)
 
 
 @pytest.mark.parametrize("engine_kind", ["resident", "host_api"])
