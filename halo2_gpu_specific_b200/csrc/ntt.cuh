@@ -476,7 +476,7 @@ __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_kernel(con
 //   3: shared-memory twiddles only   4 / 5: lazy, 5 / 6 CTAs per SM (<= 102 / 85 registers; 2^10-point CTA tiles only)
 constexpr int NTT_TWSM = 8;
 #ifndef NTT_DEFAULT_VARIANT
-#define NTT_DEFAULT_VARIANT 0
+#define NTT_DEFAULT_VARIANT 1
 #endif
 __global__ void __launch_bounds__(512) ntt_pass_v1_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, true, 0>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v1_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }

@@ -949,16 +949,25 @@ class ResidentEngine:
         return key["cosets"]
 
     def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
-                          y, beta, gamma, theta) -> DevBlock:
+                          y, beta, gamma, theta, tasks=None, combine=None) -> DevBlock:
         """Evaluator::evaluate_h (plonk/evaluation.rs:778-1226) coset by coset from resident coefficient forms,
         divide_by_vanishing_poly folded into the store, extended_to_coeff on the device (vanishing/prover.rs:72-76):
-        -> the h(X) pieces as a resident block"""
+        -> the h(X) pieces as a resident block.
+
+        tasks: None = the whole extended domain; else (coset, row_begin, row_count) triples (parallel.quotient_tasks):
+        only those rows are evaluated, into a zeroed buffer, and `combine(hext_block)` must complete it before the
+        inverse transform (the multi-GPU split: an all-reduce of disjoint supports, prover_sharded.py)."""
         import ctypes
         from ._lib import NttDesc, check, lib
         from .evaluation import coeff_to_coset_dev
         dm = self.domain
         n = dm.n
         nc = 1 << (dm.extended_k - dm.k)
+        if tasks is None:
+            tasks = [(c, 0, n) for c in range(nc)]
+            partial = False
+        else:
+            partial = True
         key_cosets = self._key_cosets(pk)
         F, S = pk.fixed_polys.shape[0], pk.sigma_polys.shape[0]
         prog = pk.ev.program(n_perm, list(lookup_z_counts), n_shuffles)
@@ -970,11 +979,16 @@ class ResidentEngine:
         witness = [b for b in (advice, instance, z_block, m_block) if b.count]
         cos = {id(b): self.alloc(b.count) for b in witness}
         hext = self._buffer(dm.extended_len())
+        if partial:
+            self._fr_vec(2, hext.ptr, hext.ptr, dm.extended_len(), hext.ptr)          # x - x: a zeroed buffer
         ptrs = lambda b: [cos[id(b)].ptr + i * n * 32 for i in range(b.count)] if b.count else []     # noqa: E731
-        for c in range(nc):
-            g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
-            for b in witness:
-                coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
+        current = None
+        for c, row_begin, row_count in tasks:
+            if c != current:                           # tasks of one coset are adjacent (coset-major order)
+                g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
+                for b in witness:
+                    coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
+                current = c
             kc = key_cosets[c]
             kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
             zp, mp = ptrs(z_block), ptrs(m_block)
@@ -984,9 +998,12 @@ class ResidentEngine:
                 aux += zp[pos:pos + cnt] + [mp[li]]
                 pos += cnt
             aux += zp[pos:pos + n_shuffles]
+            full = row_begin == 0 and row_count == n
             prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
                       x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
-                      out_stride=nc, out_offset=c)
+                      out_stride=nc, out_offset=c, row_begin=0 if full else row_begin, row_count=0 if full else row_count)
+        if combine is not None:
+            combine(DevBlock(hext.ptr, 1, dm.extended_len()))
         pieces = dm.quotient_poly_degree
         hcoef = self.alloc(pieces)
         z = np.concatenate([dm.g_coset_inv, dm.g_coset])                      # leaving the coset: {zeta^2, zeta}
