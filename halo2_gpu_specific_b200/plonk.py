@@ -351,6 +351,39 @@ class OsRng:
         return a
 
 
+class Blake2bRng:
+    """Cryptographic stream for the same interface: BLAKE2b in counter mode keyed by a 256-bit seed (os.urandom by
+    default).  Field elements are sampled by wide reduction (512 bits mod r, bias < 2^-250) and returned in Montgomery
+    form, i.e. uniformly over Fr like the reference's Fr::random.  The multi-GPU prover gives every rank the SAME seed
+    (prover_sharded.synchronized_rng: rank 0 draws it, broadcast), because every rank must blind identically."""
+
+    def __init__(self, seed: Optional[bytes] = None):
+        import hashlib
+        self._seed = bytes(seed) if seed is not None else os.urandom(32)
+        if len(self._seed) != 32:
+            raise B2Error(B2_ERR_ARG, "Blake2bRng: the seed is 32 bytes")
+        self._h, self._ctr = hashlib.blake2b, 0
+
+    def _bytes(self, count: int) -> bytes:
+        out = bytearray()
+        while len(out) < count:
+            out += self._h(self._ctr.to_bytes(8, "little"), key=self._seed, digest_size=64).digest()
+            self._ctr += 1
+        return bytes(out[:count])
+
+    def u64_vec(self, n: int) -> np.ndarray:
+        return np.frombuffer(self._bytes(8 * n), dtype=np.uint64).copy()
+
+    def u16_vec(self, n: int) -> np.ndarray:
+        return np.frombuffer(self._bytes(2 * n), dtype=np.uint16).astype(np.uint64)
+
+    def fr_vec(self, n: int) -> np.ndarray:
+        raw = self._bytes(64 * n)
+        if n == 0:
+            return np.zeros((0, 4), dtype=np.uint64)
+        return np.stack([_fr.to_mont(int.from_bytes(raw[64 * i:64 * i + 64], "little") % R) for i in range(n)])
+
+
 # --------------------------------------------------------------------------
 # engines
 # --------------------------------------------------------------------------
@@ -1001,7 +1034,8 @@ class ResidentEngine:
             full = row_begin == 0 and row_count == n
             prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
                       x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
-                      out_stride=nc, out_offset=c, row_begin=0 if full else row_begin, row_count=0 if full else row_count)
+                      out_stride=nc, out_offset=c if full else c + row_begin * nc,   # row i lands at i * nc + c
+                      row_begin=0 if full else row_begin, row_count=0 if full else row_count)
         if combine is not None:
             combine(DevBlock(hext.ptr, 1, dm.extended_len()))
         pieces = dm.quotient_poly_degree

@@ -126,11 +126,11 @@ class ShardedCommits:
 
 
 class ShardedQuotient:
-    """Mixin: evaluate_h divided over the ranks by cosets of the extended domain (a rotation never
-    leaves its coset, so cosets exchange nothing).  Rank r evaluates cosets r, r + world, ... into a zeroed extended
-    buffer; the buffers are summed across ranks (an integer all-reduce of disjoint supports: every row is written by
-    exactly one rank) and every rank brings the sum back to the h(X) pieces.  The engine supplies
-    evaluate_h_cosets / all_reduce_rows / h_pieces."""
+    """Mixin: evaluate_h divided over the ranks by contiguous row ranges of the coset-major extended domain
+    (parallel.quotient_tasks; SURVEY 8e, DESIGN 5: a rotation never leaves its coset, so cosets exchange nothing).
+    Rank r evaluates its rows into a zeroed extended buffer; the buffers are summed across ranks (an integer
+    all-reduce of disjoint supports: every row is written by exactly one rank, so no limb ever carries) and every
+    rank brings the sum back to the h(X) pieces.  The engine supplies evaluate_h_blocks(..., tasks=, combine=)."""
 
     def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
                           y, beta, gamma, theta):
@@ -139,12 +139,9 @@ class ShardedQuotient:
             return super().evaluate_h_blocks(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
                                              y, beta, gamma, theta)
         dm = self.domain
-        n_cosets = 1 << (dm.extended_k - dm.k)
-        mine = [c for c in range(n_cosets) if c % world == rank]
-        hext = self.evaluate_h_cosets(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
-                                      y, beta, gamma, theta, mine)
-        self.all_reduce_rows(hext)
-        return self.h_pieces(hext)
+        tasks = parallel.quotient_tasks(1 << (dm.extended_k - dm.k), dm.n, world, rank)
+        return super().evaluate_h_blocks(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                                         y, beta, gamma, theta, tasks=tasks, combine=self.all_reduce_rows)
 
 
 class ShardedResidentEngine(ShardedCommits, ResidentEngine):
@@ -153,47 +150,8 @@ class ShardedResidentEngine(ShardedCommits, ResidentEngine):
 
 
 class ShardedResidentEngineQ(ShardedQuotient, ShardedCommits, ResidentEngine):
-    """+ evaluate_h divided by cosets.  NOT YET RUN ON GPUS: the three device methods below restate
-    ResidentEngine.evaluate_h_blocks with a coset subset, a zeroed output and an NCCL all-reduce; the division logic
-    itself is covered on CPU (tests/test_parallel_cpu.py) through the test double."""
-
-    def evaluate_h_cosets(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
-                          y, beta, gamma, theta, cosets):
-        from .evaluation import coeff_to_coset_dev
-        from .plonk import DELTA, DevBlock, R
-        dm = self.domain
-        n = dm.n
-        nc = 1 << (dm.extended_k - dm.k)
-        key_cosets = self._key_cosets(pk)
-        F, S = pk.fixed_polys.shape[0], pk.sigma_polys.shape[0]
-        prog = pk.ev.program(n_perm, list(lookup_z_counts), n_shuffles)
-        challenges = [beta % R, gamma % R, theta % R, y % R]
-        d = beta * dm._zeta % R
-        for _ in range(S):
-            challenges.append(d)
-            d = d * DELTA % R
-        witness = [b for b in (advice, instance, z_block, m_block) if b.count]
-        cos = {id(b): self.alloc(b.count) for b in witness}
-        hext = DevBlock(self._buffer(dm.extended_len()).ptr, 1, dm.extended_len())
-        self._fr_vec(2, hext.ptr, hext.ptr, dm.extended_len(), hext.ptr)          # x - x = 0: a zeroed buffer
-        ptrs = lambda b: [cos[id(b)].ptr + i * n * 32 for i in range(b.count)] if b.count else []     # noqa: E731
-        for c in cosets:
-            g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
-            for b in witness:
-                coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
-            kc = key_cosets[c]
-            kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
-            zp, mp = ptrs(z_block), ptrs(m_block)
-            aux = kp[F + S:F + S + 3] + kp[F:F + S] + zp[:n_perm]
-            pos = n_perm
-            for li, cnt in enumerate(lookup_z_counts):
-                aux += zp[pos:pos + cnt] + [mp[li]]
-                pos += cnt
-            aux += zp[pos:pos + n_shuffles]
-            prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
-                      x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
-                      out_stride=nc, out_offset=c)
-        return hext
+    """+ evaluate_h divided by rows of the extended domain: ResidentEngine.evaluate_h_blocks does the work for the
+    rank's (coset, row range) tasks; what this class adds is the NCCL all-reduce that completes the buffer."""
 
     def all_reduce_rows(self, hext) -> None:
         import torch
@@ -205,20 +163,60 @@ class ShardedResidentEngineQ(ShardedQuotient, ShardedCommits, ResidentEngine):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         torch.cuda.synchronize()
 
-    def h_pieces(self, hext):
-        import ctypes
-        import numpy as np
-        from ._lib import NttDesc, check, lib
-        dm = self.domain
-        pieces = dm.quotient_poly_degree
-        hcoef = self.alloc(pieces)
-        z = np.concatenate([dm.g_coset_inv, dm.g_coset])
-        t = NttDesc()
-        t.log_n, t.location = dm.extended_k, 1
-        t.omega, t.divisor = dm.extended_omega_inv.ctypes.data, dm.extended_ifft_divisor.ctypes.data
-        t.coset_out = z.ctypes.data
-        t.n_in = t.in_stride = dm.extended_len()
-        t.n_out = t.out_stride = dm.n * pieces
-        t.columns, t.in_, t.out = 1, hext.ptr, hcoef.ptr
-        check(lib().b2_ntt_exec(ctypes.byref(t)))
-        return hcoef
+
+# ---- every rank must draw the same randomness ------------------------------------------------------------------
+def synchronized_rng():
+    """The rng of a multi-rank proof: rank 0 draws a 256-bit seed from the OS and broadcasts it; every rank expands
+    it with BLAKE2b in counter mode (plonk.Blake2bRng), so all ranks blind advice / m / z / h identically -- the
+    precondition of ShardedCommits, where a rank commits only its share of columns that every rank evaluates."""
+    import os
+    import numpy as np
+    from .plonk import Blake2bRng
+    d = parallel._dist()
+    if d is None:
+        return Blake2bRng()
+    import torch
+    t = torch.from_numpy(np.frombuffer(os.urandom(32), dtype=np.uint8).copy())
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    d.broadcast(t, src=0)
+    return Blake2bRng(t.cpu().numpy().tobytes())
+
+
+def assert_ranks_agree(data: bytes, what: str = "proof") -> None:
+    """all-gather a 32-byte BLAKE2b digest of `data`; raise on every rank when any two differ (a rank that blinded
+    differently, or was given another witness, produces a transcript no verifier accepts)"""
+    import hashlib
+    import numpy as np
+    from ._lib import B2_ERR_ARG, B2Error
+    d = parallel._dist()
+    if d is None:
+        return
+    import torch
+    t = torch.from_numpy(np.frombuffer(hashlib.blake2b(data, digest_size=32).digest(), dtype=np.uint8).copy())
+    if d.get_backend() == "nccl":
+        t = t.cuda()
+    out = torch.empty(d.get_world_size() * 32, dtype=torch.uint8, device=t.device)
+    d.all_gather_into_tensor(out, t)
+    rows = out.cpu().numpy().reshape(-1, 32)
+    if not (rows == rows[0]).all():
+        raise B2Error(B2_ERR_ARG, f"multi-GPU create_proof: the ranks produced different {what} bytes (every rank "
+                                  "needs the same witness, proving key and rng stream: use synchronized_rng())")
+
+
+def create_proof(params, pk, advice, instances, rng=None, *, engine=None, split_quotient: bool = True, **kw) -> bytes:
+    """plonk.create_proof over the ranks of the default process group: commitments divided by columns, evaluate_h by
+    rows of the extended domain.  rng: None = synchronized_rng(); a caller-supplied rng must produce the same
+    stream on every rank.  The proof is returned only after the ranks' bytes were found equal."""
+    from . import plonk
+    own = engine is None
+    if own:
+        engine = (ShardedResidentEngineQ if split_quotient else ShardedResidentEngine)(params, pk.vk.domain)
+    try:
+        proof = plonk.create_proof(params, pk, advice, instances, rng if rng is not None else synchronized_rng(),
+                                   engine=engine, **kw)
+    finally:
+        if own:
+            engine.free()
+    assert_ranks_agree(proof)
+    return proof

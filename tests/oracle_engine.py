@@ -136,12 +136,16 @@ class OracleEngine(ArrayBlocks):
 
 
 class CosetQuotientDouble:
-    """evaluate_h_cosets / all_reduce_rows / h_pieces for the oracle-backed engine (what prover_sharded.ShardedQuotient
-    asks of an engine): the oracle evaluates the whole extended domain, rows of cosets this rank does not own are
-    zeroed, the sum over ranks goes through torch.distributed on the host (gloo)"""
+    """evaluate_h_blocks(..., tasks=, combine=) / all_reduce_rows for the oracle-backed engine (what
+    prover_sharded.ShardedQuotient asks of an engine): the oracle evaluates the whole extended domain, rows outside
+    this rank's (coset, row_begin, row_count) tasks are zeroed, the sum over ranks goes through torch.distributed on
+    the host (gloo)"""
 
-    def evaluate_h_cosets(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
-                          y, beta, gamma, theta, cosets):
+    def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
+                          y, beta, gamma, theta, tasks=None, combine=None):
+        if tasks is None:
+            return super().evaluate_h_blocks(pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts,
+                                             n_shuffles, y, beta, gamma, theta)
         d = self.d
         ext = lambda p: d.coeff_to_extended(dec(p))                                 # noqa: E731
         lookups, pos = [], n_perm
@@ -154,18 +158,16 @@ class CosetQuotientDouble:
                          [ext(z_block[pos + i]) for i in range(n_shuffles)], [ext(z_block[i]) for i in range(n_perm)])
         h = d.divide_by_vanishing_poly(h)
         nc = 1 << (d.extended_k - d.k)
-        own = set(cosets)
-        return enc([v if (i % nc) in own else 0 for i, v in enumerate(h)])
+        own = {(b + j) * nc + c for c, b, cnt in tasks for j in range(cnt)}          # row i of coset c sits at i * nc + c
+        hext = enc([v if i in own else 0 for i, v in enumerate(h)])
+        combine(hext)
+        coeffs = d.extended_to_coeff(dec(hext))
+        n = d.n
+        pieces = len(coeffs) // n
+        return np.ascontiguousarray(enc(coeffs[:pieces * n])).reshape(pieces, n, 4)
 
     def all_reduce_rows(self, hext):
         import torch
         import torch.distributed as dist
         t = torch.from_numpy(hext.view(np.int64))
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-
-    def h_pieces(self, hext):
-        d = self.d
-        coeffs = d.extended_to_coeff(dec(hext))
-        n = d.n
-        pieces = len(coeffs) // n
-        return np.ascontiguousarray(enc(coeffs[:pieces * n])).reshape(pieces, n, 4)

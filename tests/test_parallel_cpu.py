@@ -221,3 +221,44 @@ def test_sharded_commit_prover_matches_single_process(tmp_path, world):
     total = np.sum(msms, axis=0)
     # GWC: 1 instance + 9 advice + 2 m + (2 + 3 + 1) z + 1 random + 4 h + 4 openings = 27 MSMs, divided, none duplicated
     assert total[0] == 27 and max(m[0] for m in msms) <= 27 // world + 7
+
+
+def _rng_worker(rank, world, port, outdir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from halo2_gpu_specific_b200 import prover_sharded as ps
+    from halo2_gpu_specific_b200._lib import B2Error
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    rng = ps.synchronized_rng()
+    np.save(os.path.join(outdir, f"rng_r{rank}.npy"), np.concatenate([rng.fr_vec(5).reshape(-1), rng.u64_vec(3), rng.u16_vec(2)]))
+    ps.assert_ranks_agree(b"same bytes on every rank")
+    raised = False
+    try:
+        ps.assert_ranks_agree(b"rank %d" % rank)
+    except B2Error:
+        raised = True
+    np.save(os.path.join(outdir, f"raised_r{rank}.npy"), np.array([raised]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_synchronized_rng_and_divergence_check(tmp_path):
+    """prover_sharded.synchronized_rng: rank 0's OS seed reaches every rank, so the BLAKE2b streams are equal;
+    assert_ranks_agree raises on EVERY rank when the ranks' bytes differ (what a per-rank OsRng would cause)"""
+    world = 2
+    mp.spawn(_rng_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    a, b = (np.load(tmp_path / f"rng_r{r}.npy") for r in range(world))
+    assert np.array_equal(a, b) and a.any()
+    assert all(np.load(tmp_path / f"raised_r{r}.npy")[0] for r in range(world))
+
+
+def test_blake2b_rng_is_reproducible_and_uniform_below_r():
+    from halo2_gpu_specific_b200 import _fr
+    from halo2_gpu_specific_b200.plonk import Blake2bRng
+    a, b = Blake2bRng(b"\x07" * 32), Blake2bRng(b"\x07" * 32)
+    va = a.fr_vec(64)
+    assert np.array_equal(va, b.fr_vec(64)) and not np.array_equal(va, Blake2bRng(b"\x08" * 32).fr_vec(64))
+    vals = [_fr.from_mont(v) for v in va]
+    assert all(0 <= v < _fr.R_MOD for v in vals) and len(set(vals)) == 64
+    assert max(vals).bit_length() == 254          # the top third of Fr is reachable (253-bit sampling never gets there)
+    assert Blake2bRng().fr_vec(0).shape == (0, 4)

@@ -3,7 +3,7 @@
 cd "$(dirname "$0")/.."
 O=gpurun_out
 mkdir -p $O
-free -g | head -2; nproc
+(free -g | head -2; nproc; df -h /dev/shm | tail -1) | tee $O/r2_box.txt
 python -m pytest tests -m gpu -x -q 2>&1 | tail -8
 : > $O/r2_ntt_variants_b.jsonl
 for v in 0 1 4 5; do

@@ -23,6 +23,7 @@ def main():
                     help="bench: benches/plonk.rs; zkwasm: tools/zkwasm_shape_circuit.py (64 advice, lookups, shuffles)")
     ap.add_argument("--split-quotient", action="store_true",
                     help="also divide evaluate_h by cosets (ShardedResidentEngineQ)")
+    ap.add_argument("--reps", type=int, default=3)
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -62,21 +63,39 @@ def main():
         public = [pub]
     pk = HP.keygen(params, cs, fixed, mapping)
     eng = (ShardedResidentEngineQ if a.split_quotient else ShardedResidentEngine)(params, pk.vk.domain)
-    HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(0), engine=eng)
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    proof = HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(1), engine=eng)
-    dt = time.perf_counter() - t0
+    from halo2_gpu_specific_b200 import prover_sharded as PS
+    # warm-up through the public multi-rank entry: rank 0's OS seed broadcast, BLAKE2b stream, bytes compared across ranks
+    PS.create_proof(params, pk, advice.copy(), public, None, engine=eng)
+    dt, phases = None, None
+    for rep in range(a.reps):
+        work = advice.copy()
+        if world > 1:
+            dist.barrier()
+        tm = {}
+        t0 = time.perf_counter()
+        proof = HP.create_proof(params, pk, work, public, HP.SeededRng(1), engine=eng, timings=tm)
+        d = time.perf_counter() - t0
+        if world > 1:                                    # a proof is done when the slowest rank is
+            t = torch.tensor([d], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            d = float(t.item())
+        if dt is None or d < dt:
+            dt, phases = d, tm
     eng.free()
     ok = True
     alone_s = None
     if rank == 0:
         plain = HP.ResidentEngine(params, pk.vk.domain)
         HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(0), engine=plain)
-        t0 = time.perf_counter()
-        alone = HP.create_proof(params, pk, advice.copy(), public, HP.SeededRng(1), engine=plain)
-        alone_s = time.perf_counter() - t0
+        alone_phases = None
+        for rep in range(a.reps):
+            work = advice.copy()
+            tm = {}
+            t0 = time.perf_counter()
+            alone = HP.create_proof(params, pk, work, public, HP.SeededRng(1), engine=plain, timings=tm)
+            d = time.perf_counter() - t0
+            if alone_s is None or d < alone_s:
+                alone_s, alone_phases = d, tm
         plain.free()
         ok = alone == proof
     if world > 1:
@@ -87,6 +106,9 @@ def main():
         print(json.dumps({"check": f"sharded create_proof, {a.circuit} circuit, quotient split: {a.split_quotient}", "k": a.k,
                           "n_gpus": world,
                           "bytes_equal_on_all_ranks_and_to_single_gpu": bool(ok), "sharded_s": dt, "single_gpu_s": alone_s,
+                          "sharded_phases_s": phases, "single_gpu_phases_s": alone_phases, "reps": a.reps,
+                          "rng_sync_check": "warm-up proof through prover_sharded.create_proof (broadcast seed, "
+                                            "digest all-gather) passed",
                           "backend": "nccl" if world > 1 else "none"}), flush=True)
     if world > 1:
         dist.barrier()
