@@ -144,7 +144,7 @@ struct Lane {
     std::atomic<uint64_t>* launch_counter = nullptr;
     // MSM workspace
     Buf scalars, codes, sorted, counts, offsets, cursor, buckets, part_pt, part_bucket, block_out, window_sums,
-        out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids, pcounts, poffs, pcursor, ptmp;
+        out96, errflag, tmp_bases, partials, tile_sums, part_pt2, part_bucket2, part_pt3, part_bucket3, part_ids;
     // NTT workspace
     Buf ntt_in, ntt_work, ntt_out;
     // quotient evaluation: per-call tables, spilled slots
@@ -221,7 +221,6 @@ int dev_get(DeviceCtx** out) {
         CK(cudaFuncSetAttribute(ntt_pass_mont_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_mont_cluster2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
         CK(cudaFuncSetAttribute(ntt_pass_mont_cluster4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        CK(cudaFuncSetAttribute(msm_part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, msm_accumulate_kernel, 128, 0));
         int nl = 3;
@@ -526,42 +525,9 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
     if (record_phases) CK(cudaEventRecord(ev[0], st));
     if (reset_flag) CK(cudaMemsetAsync(ctx.errflag.p, 0, 4, st));
     // sort the (bucket, point) entries by bucket
-    // Two-level partitioned sort: measured SLOWER than the global-atomic counting sort on B200 (2^22: 2.3 ms
-    // vs 1.1 ms; its level-1 writes are still one partial sector per entry), so it is opt-in
-    // (B2_MSM_PARTSORT=1) until level 1 stages its runs through shared memory.
-    static const bool part_enabled = getenv("B2_MSM_PARTSORT") && atoi(getenv("B2_MSM_PARTSORT")) == 1;
-    const uint32_t npart = (uint32_t)((nb + PART_BUCKETS - 1) / PART_BUCKETS);
-    const bool use_part = part_enabled && nb >= (1u << 16) && n >= ((size_t)1 << 18) && npart <= PART_MAX;
-    if (use_part) {
-        // two-level partitioned counting sort (local scatters, no global atomics, no global bucket scan)
-        uint32_t tile = (uint32_t)std::max<size_t>(2048, (n + 4095) / 4096);
-        const uint32_t ncta = (uint32_t)((n + tile - 1) / tile);
-        const size_t ncnt = (size_t)npart * ncta;
-        const uint32_t ptiles = (uint32_t)((ncnt + SCAN_TILE - 1) / SCAN_TILE);
-        if ((rc = ctx.pcounts.reserve(ncnt * 4))) return rc;
-        if ((rc = ctx.poffs.reserve((ncnt + 1) * 4))) return rc;
-        if ((rc = ctx.pcursor.reserve(ncnt * 4))) return rc;
-        if ((rc = ctx.tile_sums.reserve((size_t)ptiles * 4 + 16))) return rc;
-        if ((rc = ctx.ptmp.reserve((size_t)g.W * n * 8))) return rc;
-        LAUNCH(ctx, msm_part_count_kernel, ncta, PART_THREADS, npart * 4, st, (const uint4*)d_scalars,
-               ctx.pcounts.as<uint32_t>(), npart, ncta, tile, g, max_bits, ctx.errflag.as<int>());
-        if (record_phases) CK(cudaEventRecord(ev[1], st));
-        LAUNCH(ctx, msm_scan_tile_kernel, ptiles, SCAN_THREADS, 0, st, ctx.pcounts.as<uint32_t>(),
-               ctx.poffs.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)ncnt);
-        LAUNCH(ctx, msm_scan_top_kernel, 1, SCAN_THREADS, 0, st, ctx.tile_sums.as<uint32_t>(), ptiles,
-               ctx.poffs.as<uint32_t>() + ncnt);
-        LAUNCH(ctx, msm_scan_add_kernel, ptiles, SCAN_THREADS, 0, st, ctx.poffs.as<uint32_t>(),
-               ctx.pcursor.as<uint32_t>(), ctx.tile_sums.as<uint32_t>(), (uint32_t)ncnt);
-        if (record_phases) CK(cudaEventRecord(ev[2], st));
-        // sub-tile staged in shared memory: <= 2 scalars per thread and <= 56 KB of entries
-        uint32_t sub = std::min<uint32_t>(2 * PART_THREADS, (56u << 10) / (10u * g.W));
-        const size_t smem_sc = (size_t)(3 * npart + 3) * 4 + (size_t)sub * g.W * 10;
-        LAUNCH(ctx, msm_part_scatter_kernel, ncta, PART_THREADS, smem_sc, st, (const uint4*)d_scalars,
-               ctx.poffs.as<uint32_t>(), npart, ncta, tile, sub, g, ctx.ptmp.as<uint2>());
-        LAUNCH(ctx, msm_part_sort_kernel, npart, 1024, 0, st, ctx.ptmp.as<uint2>(), ctx.poffs.as<uint32_t>(), npart,
-               ncta, (uint32_t)nb, ctx.offsets.as<uint32_t>(), ctx.sorted.as<uint32_t>());
-        if (record_phases) CK(cudaEventRecord(ev[3], st));
-    } else {
+    // (a two-level partitioned counting sort was measured in round 1: 2.3 ms against 1.1 ms at 2^22 for this
+    // global-atomic counting sort, whose scatters already stay in L2; removed)
+    {
         if ((rc = ctx.codes.reserve((size_t)g.W * n * 4))) return rc;
         CK(cudaMemsetAsync(ctx.counts.p, 0, nb * 4, st));
         LAUNCH(ctx, msm_digits_kernel, (unsigned)((n + 255) / 256), 256, 0, st, (const uint4*)d_scalars,
@@ -1904,13 +1870,8 @@ int b2_mul_probe(int kind, double* per_s) {
     switch (kind) {
     case 0: return run_probe(ctx, imad_probe_kernel<4>, per_s);
     case 1: return run_probe(ctx, shoup_probe_kernel<4>, per_s);
-#ifdef B2_FP_GEN
-    case 2: return run_probe(ctx, mul_probe_kernel<4, 2>, per_s);
-    case 3: return run_probe(ctx, mul_probe_kernel<4, 3>, per_s);
-#else
     case 2:
-    case 3: return fail(B2_ERR_ARG, "mul_probe: kinds 2 and 3 need a build with -DB2_FP_GEN (tools/gen_fp.py variants)");
-#endif
+    case 3: return fail(B2_ERR_ARG, "mul_probe: kinds 2 and 3 (generated squaring / Karatsuba) were removed after round 1");
     default: return run_probe(ctx, mul_probe_kernel<4, 4>, per_s);
     }
 }

@@ -337,34 +337,14 @@ __device__ __forceinline__ Fp<P> fp_mul2_sub(const Fp<P>& a, const Fp<P>& b, con
     return fp_mul2_add<P>(a, b, fp_neg<P>(c), d);
 }
 
-// Which product the kernels use: the interleaved one above.  tools/gen_fp.py also generates a Montgomery squaring
-// (100 MACs) and a Karatsuba product (112 MACs) in separated-operand-scanning form (fp_gen.cuh, compiled with
-// -DB2_FP_GEN, selected with -DB2_FP_MUL_KARA / -DB2_FP_SQR_SOS).  Measured on B200 (b2_mul_probe): 62.3 and 67.2
-// G products/s against 68.1 for this one, and msm_accumulate 10.2 ms instead of 8.75: the saved multiplier slots are
-// eaten by ptxas turning the carry-sink additions into IMAD.X on the same pipe and by the longer dependent addition
-// chains (295 / 284 instructions per product instead of 182), so they stay out of the default build.
-#ifdef B2_FP_GEN
-}  // namespace b2
-#include "fp_gen.cuh"
-namespace b2 {
-#endif
-
+// The product the kernels use is the interleaved one above.  A separated-operand-scanning squaring (100 MACs) and a
+// Karatsuba product (112 MACs) were generated and measured on B200 in round 1: 62.3 and 67.2 G products/s against 68.1
+// for this one (ptxas turns the carry-sink additions into IMAD.X on the same pipe and the dependent addition chains
+// grow from 182 to 295 / 284 instructions), so they were removed ("measured and rejected").
 template <class P>
-__device__ __forceinline__ Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) {
-#if defined(B2_FP_GEN) && defined(B2_FP_MUL_KARA)
-    return fp_mul_kara<P>(a, b);
-#else
-    return fp_mul_cios<P>(a, b);
-#endif
-}
+__device__ __forceinline__ Fp<P> fp_mul(const Fp<P>& a, const Fp<P>& b) { return fp_mul_cios<P>(a, b); }
 template <class P>
-__device__ __forceinline__ Fp<P> fp_sqr(const Fp<P>& a) {
-#if defined(B2_FP_GEN) && defined(B2_FP_SQR_SOS)
-    return fp_sqr_sos<P>(a);
-#else
-    return fp_mul<P>(a, a);
-#endif
-}
+__device__ __forceinline__ Fp<P> fp_sqr(const Fp<P>& a) { return fp_mul<P>(a, a); }
 
 // Montgomery form -> canonical integer (multiply by 1)
 template <class P>

@@ -231,179 +231,6 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ codes, uint32_t*
     sorted[base + __popc(peers & ((1u << lane) - 1u))] = entry;
 }
 
-// ---------------------------------------------------------------- 3b. partitioned counting sort
-// Large MSMs: instead of one global atomic and one random 4-byte store per entry, sort in two
-// levels that keep every scatter local.  Level 1 splits the entries by the high bits of the
-// bucket id into partitions of PART_BUCKETS buckets (per-CTA shared-memory histograms, a scan,
-// then CTA-contiguous runs per partition); level 2 counting-sorts each partition inside one CTA
-// (its ~1-2 MB slice of the entry list stays in L2) and emits the bucket offsets on the way, so
-// the global bucket scan disappears too.
-constexpr int PART_LOG = 11;
-constexpr int PART_BUCKETS = 1 << PART_LOG;
-constexpr int PART_THREADS = 256;
-constexpr int PART_MAX = 4096;        // partitions (shared-memory histogram size)
-
-__global__ void __launch_bounds__(PART_THREADS)
-msm_part_count_kernel(const uint4* __restrict__ scalars, uint32_t* __restrict__ pcounts, uint32_t npart,
-                      uint32_t ncta, uint32_t tile, MsmGeom g, uint32_t max_bits, int* __restrict__ err_flag) {
-    extern __shared__ uint32_t part_hist[];
-    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) part_hist[p] = 0;
-    __syncthreads();
-    const uint32_t base = blockIdx.x * tile;
-    for (uint32_t k = threadIdx.x; k < tile; k += blockDim.x) {
-        const uint32_t i = base + k;
-        if (i >= g.n) break;
-        const Fr s = msm_biased_scalar(scalars, i, g, max_bits, err_flag);
-        for (uint32_t w = 0; w < g.W; w++) {
-            const uint32_t code = msm_digit_code(s, w, g);
-            if (code) atomicAdd(&part_hist[(w * g.bucket_stride + ((code >> 1) - 1)) >> PART_LOG], 1u);
-        }
-    }
-    __syncthreads();
-    for (uint32_t p = threadIdx.x; p < npart; p += blockDim.x) pcounts[(size_t)p * ncta + blockIdx.x] = part_hist[p];
-}
-
-// Level 1 scatter, staged: the CTA walks its tile in sub-tiles of `sub` scalars; the entries of a
-// sub-tile are first grouped by partition in shared memory (local histogram, scan, placement), then
-// written out so that consecutive threads store consecutive entries of one partition: full sectors
-// instead of one partial sector per entry.
-// shared memory: hist[npart] | loc_off[npart + 1] | gcur[npart] | stage[sub * W] (uint2) | stage_p[sub * W] (u16)
-__global__ void __launch_bounds__(PART_THREADS)
-msm_part_scatter_kernel(const uint4* __restrict__ scalars, const uint32_t* __restrict__ poffs, uint32_t npart,
-                        uint32_t ncta, uint32_t tile, uint32_t sub, MsmGeom g, uint2* __restrict__ tmp) {
-    extern __shared__ uint32_t part_smem[];
-    uint32_t* hist = part_smem;
-    uint32_t* loc_off = hist + npart;
-    uint32_t* gcur = loc_off + npart + 1;
-    uint2* stage = reinterpret_cast<uint2*>(gcur + npart + ((npart & 1u) ? 0 : 1));   // 8-byte aligned
-    uint16_t* stage_p = reinterpret_cast<uint16_t*>(stage + (size_t)sub * g.W);
-    const uint32_t t = threadIdx.x;
-    for (uint32_t p = t; p < npart; p += blockDim.x) gcur[p] = poffs[(size_t)p * ncta + blockIdx.x];
-    const uint32_t tile_base = blockIdx.x * tile;
-    for (uint32_t s0 = 0; s0 < tile; s0 += sub) {
-        if (tile_base + s0 >= g.n) break;
-        __syncthreads();
-        for (uint32_t p = t; p < npart; p += blockDim.x) hist[p] = 0;
-        __syncthreads();
-        // pass 1: local histogram (scalars stay in registers for pass 2: sub <= 2 * blockDim)
-        Fr sc[2];
-        bool have[2];
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            const uint32_t k = t + u * blockDim.x;
-            const uint32_t i = tile_base + s0 + k;
-            have[u] = (k < sub) && (s0 + k < tile) && (i < g.n);
-            if (!have[u]) continue;
-            sc[u] = msm_biased_scalar(scalars, i, g, 256, nullptr);
-            for (uint32_t w = 0; w < g.W; w++) {
-                const uint32_t code = msm_digit_code(sc[u], w, g);
-                if (code) atomicAdd(&hist[(w * g.bucket_stride + ((code >> 1) - 1)) >> PART_LOG], 1u);
-            }
-        }
-        __syncthreads();
-        // exclusive scan of hist -> loc_off (npart <= 4096; one warp, serial over chunks)
-        if (t < 32) {
-            uint32_t carry = 0;
-            for (uint32_t base = 0; base < npart; base += 32) {
-                const uint32_t v = (base + t < npart) ? hist[base + t] : 0;
-                uint32_t incl = v;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (t >= (uint32_t)d) incl += o;
-                }
-                if (base + t < npart) loc_off[base + t] = carry + incl - v;
-                carry += __shfl_sync(0xffffffffu, incl, 31);
-            }
-            if (t == 0) loc_off[npart] = carry;
-        }
-        __syncthreads();
-        for (uint32_t p = t; p < npart; p += blockDim.x) hist[p] = loc_off[p];   // placement cursors
-        __syncthreads();
-        // pass 2: place the entries, grouped by partition
-#pragma unroll
-        for (int u = 0; u < 2; u++) {
-            if (!have[u]) continue;
-            const uint32_t i = tile_base + s0 + t + u * blockDim.x;
-            for (uint32_t w = 0; w < g.W; w++) {
-                const uint32_t code = msm_digit_code(sc[u], w, g);
-                if (!code) continue;
-                const uint32_t bucket = w * g.bucket_stride + ((code >> 1) - 1);
-                const uint32_t p = bucket >> PART_LOG;
-                const uint32_t pos = atomicAdd(&hist[p], 1u);
-                stage[pos] = make_uint2(bucket & (PART_BUCKETS - 1),
-                                        (w * g.point_stride + g.point_offset + i) | ((code & 1u) << 31));
-                stage_p[pos] = (uint16_t)p;
-            }
-        }
-        __syncthreads();
-        // write out: consecutive threads -> consecutive entries of the same partition
-        const uint32_t total = loc_off[npart];
-        for (uint32_t e = t; e < total; e += blockDim.x) {
-            const uint32_t p = stage_p[e];
-            tmp[gcur[p] + (e - loc_off[p])] = stage[e];
-        }
-        __syncthreads();
-        for (uint32_t p = t; p < npart; p += blockDim.x) gcur[p] += loc_off[p + 1] - loc_off[p];
-    }
-}
-
-// one CTA per partition
-__global__ void __launch_bounds__(1024)
-msm_part_sort_kernel(const uint2* __restrict__ tmp, const uint32_t* __restrict__ poffs, uint32_t npart, uint32_t ncta,
-                     uint32_t nb, uint32_t* __restrict__ offsets, uint32_t* __restrict__ sorted) {
-    __shared__ uint32_t hist[PART_BUCKETS];
-    __shared__ uint32_t wsum[32];
-    const uint32_t p = blockIdx.x;
-    const uint32_t total = poffs[(size_t)npart * ncta];          // E (one past the last count)
-    const uint32_t pstart = poffs[(size_t)p * ncta];
-    const uint32_t pend = (p + 1 < npart) ? poffs[(size_t)(p + 1) * ncta] : total;
-    for (uint32_t j = threadIdx.x; j < PART_BUCKETS; j += blockDim.x) hist[j] = 0;
-    __syncthreads();
-    for (uint32_t e = pstart + threadIdx.x; e < pend; e += blockDim.x) atomicAdd(&hist[tmp[e].x], 1u);
-    __syncthreads();
-    // exclusive scan of 2048 counters with 1024 threads: two per thread
-    const uint32_t t = threadIdx.x;
-    const uint32_t a0 = hist[2 * t], a1 = hist[2 * t + 1];
-    uint32_t v = a0 + a1;
-    // warp scan
-    const uint32_t lane = t & 31, wid = t >> 5;
-    uint32_t incl = v;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= (uint32_t)d) incl += o;
-    }
-    if (lane == 31) wsum[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        uint32_t x = wsum[lane];
-        uint32_t xi = x;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xffffffffu, xi, d);
-            if (lane >= (uint32_t)d) xi += o;
-        }
-        wsum[lane] = xi - x;   // exclusive warp offsets
-    }
-    __syncthreads();
-    const uint32_t excl = wsum[wid] + incl - v;
-    // bucket offsets (global) and scatter cursors (shared)
-    const uint32_t b0 = p * PART_BUCKETS + 2 * t;
-    if (b0 < nb) offsets[b0] = pstart + excl;
-    if (b0 + 1 < nb) offsets[b0 + 1] = pstart + excl + a0;
-    __syncthreads();
-    hist[2 * t] = pstart + excl;
-    hist[2 * t + 1] = pstart + excl + a0;
-    if (p + 1 == npart && t == 0) offsets[nb] = total;
-    __syncthreads();
-    for (uint32_t e = pstart + threadIdx.x; e < pend; e += blockDim.x) {
-        const uint2 ent = tmp[e];
-        const uint32_t pos = atomicAdd(&hist[ent.x], 1u);
-        sorted[pos] = ent.y;
-    }
-}
-
 // ---------------------------------------------------------------- 4. accumulate
 __device__ __forceinline__ Affine msm_load_point(const char* __restrict__ bases, uint32_t stride, uint32_t ent) {
     const uint32_t idx = ent & 0x7fffffffu;
@@ -878,12 +705,7 @@ __global__ void __launch_bounds__(256) mul_probe_kernel(uint4* sink, int iters) 
     for (int i = 0; i < iters; i++) {
 #pragma unroll
         for (int j = 0; j < ILP; j++) {
-#ifdef B2_FP_GEN
-            if (KIND == 2) x[j] = fp_mul_kara<FqParams>(x[j], y);
-            else if (KIND == 3) x[j] = fp_sqr_sos<FqParams>(x[j]);
-            else
-#endif
-                x[j] = fp_mul2_add<FqParams>(x[j], y, y, x[j]);
+            x[j] = fp_mul2_add<FqParams>(x[j], y, y, x[j]);
         }
     }
     Fq acc = x[0];

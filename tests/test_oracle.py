@@ -247,26 +247,6 @@ def test_shoup_generator_emulation_and_committed_header():
         assert f.read() == gs.render(g)
 
 
-def test_generated_sqr_and_karatsuba_emulation():
-    """tools/gen_fp.py (separated-operand-scanning squaring / Karatsuba product; measured slower on B200 and kept out of
-    the default build): the carry chains reproduce a*b*2^-256 mod p for both fields in the PTX emulation, and the
-    committed csrc/fp_gen.cuh is what the generator prints."""
-    import importlib.util
-    import os
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    spec = importlib.util.spec_from_file_location("gen_fp", os.path.join(root, "tools", "gen_fp.py"))
-    gf = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(gf)
-    counts = gf.selftest(n_random=300)
-    assert counts["sqr"]["mad.lo"] == 100 and counts["mul"]["mad.lo"] == 112
-    with open(os.path.join(root, "halo2_gpu_specific_b200", "csrc", "fp_gen.cuh")) as f:
-        assert f.read() == gf.render()
-
-
-# ---- public third-party vectors for this curve (alt_bn128 = BN254): EIP-196 ecAdd / ecMul, EIP-197 pairing check ----
-EIP = json.load(open(os.path.join(HERE, "golden", "eip196_197.json")))
-
-
 def _eip_g1(h):
     x, y = int(h[:64], 16), int(h[64:128], 16)
     return None if (x, y) == (0, 0) else (x, y)
