@@ -1289,15 +1289,45 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
          streams a, u, b, v (vanishing_streams): coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]),
          vanishing/prover.rs:48-63 -- the reference draws those four per coefficient from thread_rng
     """
+    return create_proof_multi(params, pk, [advice], [instances], rng, sign_bit=sign_bit, engine=engine,
+                              advice_max_bits=advice_max_bits, timings=timings, use_gwc=use_gwc)
+
+
+def fold_steps(cs) -> int:
+    """how many times evaluate_h multiplies its accumulator by y for ONE circuit instance (evaluation.rs:839-1220):
+    every gate polynomial, the permutation terms, the lookup terms, the shuffle terms"""
+    t = sum(len(g) for g in cs.gates)
+    if cs.permutation_columns:
+        chunk_len = cs.degree() - 2
+        sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
+        t += 2 + (sets - 1) + sets
+    for lk in cs.lookups:
+        t += 3 + 2 * (len(lk["input_expressions_sets"]) - 1)
+    return t + 3 * len(cs.shuffles)
+
+
+def create_proof_multi(params, pk: ProvingKey, advices: Sequence[np.ndarray],
+                       instances: Sequence[Sequence[Sequence[int]]], rng, sign_bit: int = 7, engine=None,
+                       advice_max_bits: Optional[int] = None, timings: Optional[dict] = None,
+                       use_gwc: bool = True) -> bytes:
+    """ONE proof for `len(advices)` instances of the circuit: `create_proof_ext(circuits: &[ConcreteCircuit],
+    instances: &[&[&[C::Scalar]]])`, plonk/prover.rs:206-222, with the advice of every instance given
+    (create_proof_from_witness, :916-1500).  Every phase runs over all instances before the next challenge is drawn
+    (instance commitments, advice commitments | theta | m commitments | beta, gamma | permutation z of every
+    instance, lookup z of every instance, shuffle z of every instance | ...), evaluate_h folds the instances into one
+    accumulator (evaluation.rs:839-845) and the multiopen queries are listed instance by instance (:1466-1512).
+    Random draws: the order of create_proof, each numbered item once per instance before the next item."""
     import time
     vk = pk.vk
     cs, domain = vk.cs, vk.domain
+    if len(advices) == 0 or len(advices) != len(instances):
+        raise B2Error(B2_ERR_ARG, "InvalidInstances: one list of instance columns per circuit instance")
     from .evaluation import set_active_pool
     E = engine or ResidentEngine(params, domain)
     prev_pool = set_active_pool(getattr(E, "_pool", None))
     try:
-        return _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time,
-                             use_gwc)
+        return _create_proof(E, pk, cs, domain, list(advices), list(instances), rng, sign_bit, advice_max_bits, timings,
+                             time, use_gwc)
     finally:
         if engine is None:
             E.free()
@@ -1306,7 +1336,7 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
         set_active_pool(prev_pool)
 
 
-def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_max_bits, timings, time, use_gwc) -> bytes:
+def _create_proof(E, pk, cs, domain, advices, instances, rng, sign_bit, advice_max_bits, timings, time, use_gwc) -> bytes:
     vk = pk.vk
     n, k = domain.n, domain.k
     bf = cs.blinding_factors()
@@ -1314,6 +1344,7 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
     queries = cs.queries()
     tr = Blake2bWrite(sign_bit)
     t_last = [time.perf_counter()]
+    C = len(advices)
 
     def lap(name: str) -> None:
         if timings is not None:
@@ -1322,82 +1353,106 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
             t_last[0] = now
 
     key = E.key_blocks(pk)
-    fixed_values = key["fixed_values"]
 
     # ---- create_single_instances (plonk/prover.rs:85-173)
-    if len(instances) != cs.num_instance:
-        raise B2Error(B2_ERR_ARG, "InvalidInstances")
     tr.common_scalar(vk.transcript_repr)
-    inst_host = np.zeros((cs.num_instance, n, 4), dtype=np.uint64)
-    for i, values in enumerate(instances):
-        if len(values) > usable:
-            raise B2Error(B2_ERR_ARG, "InstanceTooLarge")
-        if len(values):
-            inst_host[i, :len(values)] = _mont_vec(values)
-    instance_values = E.put(inst_host)
-    if cs.num_instance:
-        for c in E.commit_lagrange(instance_values, _fr.NUM_BITS):
-            tr.common_point(c)
-    instance_polys = E.copy(instance_values)
-    if cs.num_instance:
-        E.lagrange_to_coeff(instance_polys)
+    inst_values, inst_polys = [], []
+    for circuit_instances in instances:
+        if len(circuit_instances) != cs.num_instance:
+            raise B2Error(B2_ERR_ARG, "InvalidInstances")
+        inst_host = np.zeros((cs.num_instance, n, 4), dtype=np.uint64)
+        for i, values in enumerate(circuit_instances):
+            if len(values) > usable:
+                raise B2Error(B2_ERR_ARG, "InstanceTooLarge")
+            if len(values):
+                inst_host[i, :len(values)] = _mont_vec(values)
+        instance_values = E.put(inst_host)
+        if cs.num_instance:
+            for c in E.commit_lagrange(instance_values, _fr.NUM_BITS):
+                tr.common_point(c)
+        instance_polys = E.copy(instance_values)
+        if cs.num_instance:
+            E.lagrange_to_coeff(instance_polys)
+        inst_values.append(instance_values)
+        inst_polys.append(instance_polys)
     lap("instance")
 
     # ---- advice (:964-1010)
-    if advice.shape != (cs.num_advice, n, 4) or advice.dtype != np.uint64 or not advice.flags.c_contiguous:
-        raise B2Error(B2_ERR_ARG, f"advice must be a C-contiguous uint64 array of shape ({cs.num_advice}, {n}, 4)")
-    blind = rng.u16_vec(cs.num_advice * (bf + 1))
-    advice[:, usable:] = _mont_vec(blind).reshape(cs.num_advice, bf + 1, 4)
-    adv, points = E.put_and_commit_lagrange(advice, advice_max_bits)
-    for c in points:
-        tr.write_point(c)
+    advs = []
+    for advice in advices:
+        if advice.shape != (cs.num_advice, n, 4) or advice.dtype != np.uint64 or not advice.flags.c_contiguous:
+            raise B2Error(B2_ERR_ARG, f"advice must be a C-contiguous uint64 array of shape ({cs.num_advice}, {n}, 4)")
+        blind = rng.u16_vec(cs.num_advice * (bf + 1))
+        advice[:, usable:] = _mont_vec(blind).reshape(cs.num_advice, bf + 1, 4)
+        adv, points = E.put_and_commit_lagrange(advice, advice_max_bits)
+        for c in points:
+            tr.write_point(c)
+        advs.append(adv)
     theta = tr.squeeze_challenge()
     lap("advice")
 
     # ---- lookups: compress, multiplicities, m commitments (:334-366, logup/prover.rs:70-256)
     n_lookups = len(cs.lookups)
-    ms, m_bits = E.multiplicity_block(cs, pk, adv, instance_values, theta,
-                                      [rng.u16_vec(bf + 1) for _ in range(n_lookups)])
-    if n_lookups:
-        for c in E.commit_lagrange(ms, m_bits):
-            tr.write_point(c)
+    all_ms = []
+    for adv, instance_values in zip(advs, inst_values):
+        ms, m_bits = E.multiplicity_block(cs, pk, adv, instance_values, theta,
+                                          [rng.u16_vec(bf + 1) for _ in range(n_lookups)])
+        all_ms.append((ms, m_bits))
+    for ms, m_bits in all_ms:
+        if n_lookups:
+            for c in E.commit_lagrange(ms, m_bits):
+                tr.write_point(c)
+    all_ms = [ms for ms, _ in all_ms]
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
     lap("lookup_m")
 
     # ---- z columns (:411-633): permutation, lookups, shuffles -- built where the engine keeps its columns,
-    # blinded, then committed and brought to coefficient form as ONE batch
+    # blinded, then committed and brought to coefficient form as ONE batch per instance; the points go to the
+    # transcript in the reference's order: permutation z of every instance, then lookup z, then shuffle z
     chunk_len = cs.degree() - 2
     n_perm = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
     lookup_z_counts = [len(lk["input_expressions_sets"]) for lk in cs.lookups]
     n_shuffles = len(cs.shuffles)
-    z_block = E.alloc(n_perm + sum(lookup_z_counts) + n_shuffles)
-    zc = E.cols(z_block)
-    m_cols = E.cols(ms)
-    if n_perm:
-        blinds = [rng.fr_vec(bf) for _ in range(n_perm)]
-        E.permutation_z(cs, pk, adv, instance_values, beta, gamma, blinds, zc[:n_perm])
-    pos = n_perm
-    for li, lk in enumerate(cs.lookups):
-        cnt = lookup_z_counts[li]
-        E.logup_z(cs, lk, pk, adv, instance_values, m_cols[li], theta, beta, zc[pos:pos + cnt])
-        for z in zc[pos:pos + cnt]:
-            E.write_rows(z, n - bf, rng.fr_vec(bf))
-        pos += cnt
-    for gi, group in enumerate(cs.shuffles):
-        E.shuffle_z(cs, group, pk, adv, instance_values, theta, beta, zc[pos + gi])
-        E.write_rows(zc[pos + gi], n - bf, rng.fr_vec(bf))
-    if len(zc):
-        for c in E.commit_lagrange_and_ifft(z_block):
+    n_z = n_perm + sum(lookup_z_counts) + n_shuffles
+    z_blocks = [E.alloc(n_z) for _ in range(C)]
+    for ci in range(C):
+        if n_perm:
+            blinds = [rng.fr_vec(bf) for _ in range(n_perm)]
+            E.permutation_z(cs, pk, advs[ci], inst_values[ci], beta, gamma, blinds, E.cols(z_blocks[ci])[:n_perm])
+    for ci in range(C):
+        zc, m_cols, pos = E.cols(z_blocks[ci]), E.cols(all_ms[ci]), n_perm
+        for li, lk in enumerate(cs.lookups):
+            cnt = lookup_z_counts[li]
+            E.logup_z(cs, lk, pk, advs[ci], inst_values[ci], m_cols[li], theta, beta, zc[pos:pos + cnt])
+            for z in zc[pos:pos + cnt]:
+                E.write_rows(z, n - bf, rng.fr_vec(bf))
+            pos += cnt
+    for ci in range(C):
+        zc, pos = E.cols(z_blocks[ci]), n_perm + sum(lookup_z_counts)
+        for gi, group in enumerate(cs.shuffles):
+            E.shuffle_z(cs, group, pk, advs[ci], inst_values[ci], theta, beta, zc[pos + gi])
+            E.write_rows(zc[pos + gi], n - bf, rng.fr_vec(bf))
+    z_points = [E.commit_lagrange_and_ifft(zb) if n_z else [] for zb in z_blocks]
+    for pts in z_points:
+        for c in pts[:n_perm]:
             tr.write_point(c)
-    if n_lookups:
-        E.lagrange_to_coeff(ms)                                          # lagrange_to_coeff_st(l.0), :497
-    perm_polys = zc[:n_perm]
-    lookups, pos = [], n_perm
-    for li, cnt in enumerate(lookup_z_counts):
-        lookups.append({"z": zc[pos:pos + cnt], "m": m_cols[li]})
-        pos += cnt
-    shuffle_polys = zc[pos:pos + n_shuffles]
+    for pts in z_points:
+        for c in pts[n_perm:n_perm + sum(lookup_z_counts)]:
+            tr.write_point(c)
+    for pts in z_points:
+        for c in pts[n_perm + sum(lookup_z_counts):]:
+            tr.write_point(c)
+    per_circuit = []
+    for ci in range(C):
+        if n_lookups:
+            E.lagrange_to_coeff(all_ms[ci])                                  # lagrange_to_coeff_st(l.0), :497
+        zc, m_cols = E.cols(z_blocks[ci]), E.cols(all_ms[ci])
+        lookups, pos = [], n_perm
+        for li, cnt in enumerate(lookup_z_counts):
+            lookups.append({"z": zc[pos:pos + cnt], "m": m_cols[li]})
+            pos += cnt
+        per_circuit.append({"perm": zc[:n_perm], "lookups": lookups, "shuffles": zc[pos:pos + n_shuffles]})
     lap("z_columns")
 
     # ---- vanishing commit, y (:635-639, vanishing/prover.rs:41-70)
@@ -1408,10 +1463,21 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
     y = tr.squeeze_challenge()
     lap("vanishing_commit")
 
-    # ---- h(X) (:640-690, vanishing/prover.rs:64-110)
-    E.lagrange_to_coeff(adv)                                             # lagrange_to_coeff_st per column, :643-646
-    h_block = E.evaluate_h_blocks(pk, adv, instance_polys, z_block, ms, n_perm, lookup_z_counts, n_shuffles,
-                                  y, beta, gamma, theta)
+    # ---- h(X) (:640-690, vanishing/prover.rs:64-110).  The reference folds every instance into one accumulator:
+    # after instance j it holds V_0 y^(jT) + ... + V_j, V_j = the fold of instance j alone from zero, T = fold_steps.
+    # Division by the vanishing polynomial and extended_to_coeff are linear, so the pieces of h are the same Horner
+    # fold (in y^T) of the pieces each instance yields on its own.
+    h_blocks = []
+    for ci in range(C):
+        E.lagrange_to_coeff(advs[ci])                                        # lagrange_to_coeff_st per column, :643-646
+        h_blocks.append(E.evaluate_h_blocks(pk, advs[ci], inst_polys[ci], z_blocks[ci], all_ms[ci], n_perm,
+                                            lookup_z_counts, n_shuffles, y, beta, gamma, theta))
+    if C == 1:
+        h_block = h_blocks[0]
+    else:
+        y_t = pow(y, fold_steps(cs), R)
+        pieces = [E.cols(hb) for hb in h_blocks]
+        h_block = E.stack([E.poly_combine([pieces[ci][p] for ci in range(C)], y_t) for p in range(len(pieces[0]))])
     for c in E.commit(h_block):
         tr.write_point(c)
     x = tr.squeeze_challenge()
@@ -1428,15 +1494,18 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
         if key not in known:
             known[key] = E.eval_polynomial(poly, point)
         return known[key]
-    advice_polys, inst_cols = E.cols(adv), E.cols(instance_polys)
+    all_advice_polys = [E.cols(adv) for adv in advs]
+    all_inst_cols = [E.cols(ip) for ip in inst_polys]
     fixed_polys, sigma_polys = E.cols(key["fixed_polys"]), E.cols(key["sigma_polys"])
     # The evaluations are written in the reference's order, but no challenge is drawn between them: list the
     # (polynomial, point) pairs first, evaluate them with ONE engine call per distinct point, then write.
     wanted: List[Tuple[object, int]] = []
-    for col, at in queries["Instance"]:
-        wanted.append((inst_cols[col], rot(at)))
-    for col, at in queries["Advice"]:
-        wanted.append((advice_polys[col], rot(at)))
+    for inst_cols in all_inst_cols:
+        for col, at in queries["Instance"]:
+            wanted.append((inst_cols[col], rot(at)))
+    for advice_polys in all_advice_polys:
+        for col, at in queries["Advice"]:
+            wanted.append((advice_polys[col], rot(at)))
     for col, at in queries["Fixed"]:
         wanted.append((fixed_polys[col], rot(at)))
     h_poly = E.poly_combine(list(reversed(E.cols(h_block))), xn)       # fold acc * xn + piece over rev pieces
@@ -1453,13 +1522,16 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
             if i + 1 < len(polys):
                 wanted.append((z, x_last))
 
-    eval_z_set(perm_polys)
-    for lk in lookups:
-        wanted.append((lk["m"], x))
-        eval_z_set(lk["z"])
-    for z in shuffle_polys:
-        wanted.append((z, x))
-        wanted.append((z, x_next))
+    for pc in per_circuit:
+        eval_z_set(pc["perm"])
+    for pc in per_circuit:
+        for lk in pc["lookups"]:
+            wanted.append((lk["m"], x))
+            eval_z_set(lk["z"])
+    for pc in per_circuit:
+        for z in pc["shuffles"]:
+            wanted.append((z, x))
+            wanted.append((z, x_next))
     eval_many = getattr(E, "eval_polynomials", None)
     if eval_many is not None:
         by_point: Dict[int, list] = {}
@@ -1474,7 +1546,7 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
         tr.write_scalar(ev(poly, point))
     lap("evaluations")
 
-    # ---- multiopen queries (:792-838) as (rotation, point, polynomial)
+    # ---- multiopen queries (:792-838) as (rotation, point, polynomial), instance by instance
     qs: List[Tuple[int, int, object]] = []
 
     def open_z_set(polys):
@@ -1484,17 +1556,18 @@ def _create_proof(E, pk, cs, domain, advice, instances, rng, sign_bit, advice_ma
         for z in list(reversed(polys))[1:]:
             qs.append((last, x_last, z))
 
-    for col, at in queries["Instance"]:
-        qs.append((at, rot(at), inst_cols[col]))
-    for col, at in queries["Advice"]:
-        qs.append((at, rot(at), advice_polys[col]))
-    open_z_set(perm_polys)
-    for lk in lookups:
-        qs.append((0, x, lk["m"]))
-        open_z_set(lk["z"])
-    for z in shuffle_polys:
-        qs.append((0, x, z))
-        qs.append((1, x_next, z))
+    for ci, pc in enumerate(per_circuit):
+        for col, at in queries["Instance"]:
+            qs.append((at, rot(at), all_inst_cols[ci][col]))
+        for col, at in queries["Advice"]:
+            qs.append((at, rot(at), all_advice_polys[ci][col]))
+        open_z_set(pc["perm"])
+        for lk in pc["lookups"]:
+            qs.append((0, x, lk["m"]))
+            open_z_set(lk["z"])
+        for z in pc["shuffles"]:
+            qs.append((0, x, z))
+            qs.append((1, x_next, z))
     for col, at in queries["Fixed"]:
         qs.append((at, rot(at), fixed_polys[col]))
     for poly in sigma_polys:

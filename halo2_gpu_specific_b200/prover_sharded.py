@@ -116,13 +116,39 @@ class ShardedCommits:
         return self._gather(pts, count)
 
     def put_and_commit_lagrange(self, host, max_bits: Optional[int]):
+        """The advice columns: rank r brings ONLY its share of the columns across its PCIe link (committing them on
+        the way in, copy of column i + 1 under the MSM of column i), then the ranks hand each other their shares over
+        NVLink (`exchange_columns`: one broadcast per rank), because evaluate_h and the z columns read every advice
+        column on every rank.  Host->device traffic per rank drops from the whole witness to 1/world of it.  Engines
+        without put_share_and_commit (the host-API engine) upload everything and divide only the commitments."""
         if self._inside:
             return super().put_and_commit_lagrange(host, max_bits)
+        count = host.shape[0]
+        lo, hi = self._share(count)
+        _, world = parallel.world()
+        if world > 1 and hasattr(self, "put_share_and_commit"):
+            block = self.alloc(count)
+            with self._local():
+                pts = self.put_share_and_commit(block, host, lo, hi, max_bits) if hi > lo else []
+            self.exchange_columns(block)
+            return block, self._gather(pts, count)
         block = self.put(host)
-        lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = self.commit_columns_with_bound(self.sub_block(block, lo, hi), max_bits) if hi > lo else []
-        return block, self._gather(pts, self.block_count(block))
+        return block, self._gather(pts, count)
+
+    def exchange_columns(self, block) -> None:
+        """every rank's column range of `block` (parallel.column_range) -> every rank: one broadcast per owning rank"""
+        d = parallel._dist()
+        if d is None:
+            return
+        count, world = self.block_count(block), d.get_world_size()
+        self.before_collective()
+        for r in range(world):
+            lo, hi = parallel.column_range(count, world, r)
+            if hi > lo:
+                d.broadcast(self.as_tensor(self.sub_block(block, lo, hi)), src=r)
+        self.after_collective()
 
 
 class ShardedQuotient:
@@ -144,24 +170,52 @@ class ShardedQuotient:
                                          y, beta, gamma, theta, tasks=tasks, combine=self.all_reduce_rows)
 
 
-class ShardedResidentEngine(ShardedCommits, ResidentEngine):
+class _ResidentCollectives:
+    """what the sharding mixins ask of the device-resident engine: device blocks as torch tensors (no copy), the
+    engine's lanes drained before NCCL touches the memory and NCCL's stream drained after"""
+
+    @staticmethod
+    def as_tensor(block):
+        import torch
+        from .plonk import _DevArray
+        return torch.as_tensor(_DevArray(block.ptr, (max(1, block.count) * block.n, 4)),
+                               device=torch.device("cuda", torch.cuda.current_device()))
+
+    @staticmethod
+    def before_collective() -> None:
+        from ._lib import check, lib
+        check(lib().b2_synchronize())
+
+    @staticmethod
+    def after_collective() -> None:
+        import torch
+        torch.cuda.synchronize()
+
+    def put_share_and_commit(self, block, host, lo: int, hi: int, max_bits: Optional[int]):
+        """columns [lo, hi) of `host` -> the same columns of the resident `block`, committed on the way in"""
+        import numpy as np
+        from ._lib import B2_ERR_ARG, B2Error
+        if not (host.flags.c_contiguous and host.dtype == np.uint64 and host.ndim == 3):
+            raise B2Error(B2_ERR_ARG, "expected a C-contiguous uint64 (columns, n, 4) array")
+        own = self.sub_block(block, lo, hi)
+        return self._commit(self.params.g_lagrange, host[lo:hi].ctypes.data, own,
+                            0xFFFFFFFF if max_bits is None else max_bits, False)
+
+    def all_reduce_rows(self, hext) -> None:
+        import torch.distributed as dist
+        self.before_collective()
+        dist.all_reduce(self.as_tensor(hext), op=dist.ReduceOp.SUM)
+        self.after_collective()
+
+
+class ShardedResidentEngine(ShardedCommits, _ResidentCollectives, ResidentEngine):
     """ResidentEngine whose commitments are shared out over the ranks (one process per GPU; call
     torch.cuda.set_device / _lib.set_device(local_rank) and init_process_group("nccl") first)"""
 
 
-class ShardedResidentEngineQ(ShardedQuotient, ShardedCommits, ResidentEngine):
+class ShardedResidentEngineQ(ShardedQuotient, ShardedCommits, _ResidentCollectives, ResidentEngine):
     """+ evaluate_h divided by rows of the extended domain: ResidentEngine.evaluate_h_blocks does the work for the
-    rank's (coset, row range) tasks; what this class adds is the NCCL all-reduce that completes the buffer."""
-
-    def all_reduce_rows(self, hext) -> None:
-        import torch
-        import torch.distributed as dist
-        from ._lib import check, lib
-        from .plonk import _DevArray
-        check(lib().b2_synchronize())
-        t = torch.as_tensor(_DevArray(hext.ptr, (hext.n, 4)), device=torch.device("cuda", torch.cuda.current_device()))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
+    rank's (coset, row range) tasks; the NCCL all-reduce (_ResidentCollectives.all_reduce_rows) completes the buffer."""
 
 
 # ---- every rank must draw the same randomness ------------------------------------------------------------------

@@ -501,16 +501,18 @@ def shuffle_commit_product(cs, domain, group, theta, beta, advice, fixed, instan
 # --------------------------------------------------------------------------
 def evaluate_h(ev: Evaluator, cs: ConstraintSystem, domain: EvaluationDomain, fixed_cosets, advice_cosets,
                instance_cosets, l0, l_last, l_active_row, sigma_cosets, y, beta, gamma, theta,
-               lookups, shuffles, permutation_sets, zeta: Optional[int] = None) -> List[int]:
+               lookups, shuffles, permutation_sets, zeta: Optional[int] = None,
+               values: Optional[List[int]] = None) -> List[int]:
     """lookups: [{"z_cosets": [...], "m_coset": [...]}], shuffles: [product_coset], permutation_sets:
-    [z coset per set]; all cosets are extended-domain evaluation lists.  One proof (the reference
-    loops over `advice.iter()` = proofs of a batch; one iteration is restated)."""
+    [z coset per set]; all cosets are extended-domain evaluation lists.  One circuit instance: the reference loops
+    over `advice.iter()` = the instances of a batch (evaluation.rs:839-845) with ONE accumulator; `values` is that
+    accumulator as the previous instance left it (None = zeros, the first instance)."""
     size = domain.extended_len()
     rot_scale = 1 << (domain.extended_k - domain.k)
     ext_omega = domain.extended_omega
     zeta = domain.g_coset if zeta is None else zeta
     fixed, advice, instance = fixed_cosets, advice_cosets, instance_cosets
-    values = [0] * size
+    values = [0] * size if values is None else list(values)
     n_lookups = len(cs.lookups)
     table_values = [[0] * size for _ in range(n_lookups)]
     input_product = [[0] * size for _ in range(n_lookups)]

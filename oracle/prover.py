@@ -438,16 +438,39 @@ def logup_multiplicity(input_sets, table, usable: int, n: int) -> List[int]:
 
 def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]], instances: Sequence[Sequence[int]],
                  rng, sign_bit: int = 7, use_gwc: bool = True) -> bytes:
+    """one circuit instance per proof: create_proof_multi with lists of one"""
+    return create_proof_multi(params, pk, [advice], [instances], rng, sign_bit, use_gwc)
+
+
+def fold_steps(cs) -> int:
+    """how many times evaluate_h multiplies its accumulator by y for ONE circuit instance (evaluation.rs:839-1220):
+    every gate polynomial, the permutation terms, the lookup terms, the shuffle terms"""
+    t = sum(len(g) for g in cs.gates)
+    if cs.permutation_columns:
+        chunk_len = cs.degree() - 2
+        sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
+        t += 2 + (sets - 1) + sets
+    for lk in cs.lookups:
+        t += 3 + 2 * (len(lk["input_expressions_sets"]) - 1)
+    return t + 3 * len(cs.shuffles)
+
+
+def create_proof_multi(params: Params, pk: ProvingKey, advices: Sequence[Sequence[Sequence[int]]],
+                       instances: Sequence[Sequence[Sequence[int]]], rng, sign_bit: int = 7,
+                       use_gwc: bool = True) -> bytes:
     """plonk/prover.rs:916-1500 (create_proof_from_witness: the advice columns are given, as read by fetch_witness)
     with the GWC multiopen (`create_proof`, :1759-1781: use_gwc = true) or SHPLONK (`create_proof_with_shplonk`,
-    :1737-1757: use_gwc = false), one circuit instance per proof.
+    :1737-1757: use_gwc = false), for `len(advices)` instances of the same circuit in ONE proof
+    (`circuits: &[ConcreteCircuit], instances: &[&[&[C::Scalar]]]`, plonk/prover.rs:206-222): every phase loops over
+    the circuit instances before the next challenge is drawn, and evaluate_h folds them into one h(X)
+    (evaluation.rs:839-845).
 
     `rng` supplies every random value, in this order (vector draws; fr_vec returns Montgomery limbs):
-      1. u16_vec(num_advice * (bf + 1)): blinding rows of advice column i are [i*(bf+1), (i+1)*(bf+1))   (:973-977)
-      2. per lookup: u16_vec(bf + 1) for the blinding rows of m                                         (logup/prover.rs:232-236)
-      3. per permutation set: fr_vec(bf)                                                                (permutation/prover.rs:156-158)
-      4. per lookup, per z: fr_vec(bf)                                                                  (plonk/prover.rs:445-449)
-      5. per shuffle group: fr_vec(bf)                                                                  (plonk/prover.rs:518-521)
+      1. per circuit: u16_vec(num_advice * (bf + 1)): blinding rows of advice column i are [i*(bf+1), (i+1)*(bf+1))   (:973-977)
+      2. per circuit, per lookup: u16_vec(bf + 1) for the blinding rows of m                            (logup/prover.rs:232-236)
+      3. per circuit, per permutation set: fr_vec(bf)                                                   (permutation/prover.rs:156-158)
+      4. per circuit, per lookup, per z: fr_vec(bf)                                                     (plonk/prover.rs:445-449)
+      5. per circuit, per shuffle group: fr_vec(bf)                                                     (plonk/prover.rs:518-521)
       6. vanishing_random_poly: fr_vec(k), u64_vec(1)                                                   (vanishing/prover.rs:48-63)
     """
     vk = pk.vk
@@ -458,82 +481,104 @@ def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]]
     queries = vk.queries
     tr = Blake2bWrite(sign_bit)
     lag2coeff = domain.lagrange_to_coeff
+    C = len(advices)
+    if len(instances) != C:
+        raise ValueError("InvalidInstances")
 
     # ---- create_single_instances :85-173
-    if len(instances) != cs.num_instance:
-        raise ValueError("InvalidInstances")
     tr.common_scalar(vk.transcript_repr)                                       # vk.hash_into
-    instance_values = []
-    for values in instances:
-        if len(values) > usable:
-            raise ValueError("InstanceTooLarge")
-        instance_values.append([v % R for v in values] + [0] * (n - len(values)))
-    for poly in instance_values:
-        tr.common_point(params.commit_lagrange(poly))                          # :124-137
-    instance_polys = [lag2coeff(p) for p in instance_values]
+    inst_values, inst_polys = [], []
+    for circuit_instances in instances:
+        if len(circuit_instances) != cs.num_instance:
+            raise ValueError("InvalidInstances")
+        vals = []
+        for values in circuit_instances:
+            if len(values) > usable:
+                raise ValueError("InstanceTooLarge")
+            vals.append([v % R for v in values] + [0] * (n - len(values)))
+        for poly in vals:
+            tr.common_point(params.commit_lagrange(poly))                      # :124-137
+        inst_values.append(vals)
+        inst_polys.append([lag2coeff(p) for p in vals])
 
     # ---- advice :964-1010
-    assert len(advice) == cs.num_advice
-    blind = [int(v) for v in rng.u16_vec(cs.num_advice * (bf + 1))]
-    advice_values = []
-    for i, col in enumerate(advice):
-        col = [v % R for v in col[:usable]] + blind[i * (bf + 1):(i + 1) * (bf + 1)]
-        assert len(col) == n
-        advice_values.append(col)
-    for col in advice_values:
-        tr.write_point(params.commit_lagrange(col))                            # commit_lagrange_with_bound: same point
+    adv_values = []
+    for advice in advices:
+        assert len(advice) == cs.num_advice
+        blind = [int(v) for v in rng.u16_vec(cs.num_advice * (bf + 1))]
+        cols = []
+        for i, col in enumerate(advice):
+            col = [v % R for v in col[:usable]] + blind[i * (bf + 1):(i + 1) * (bf + 1)]
+            assert len(col) == n
+            cols.append(col)
+        for col in cols:
+            tr.write_point(params.commit_lagrange(col))                        # commit_lagrange_with_bound: same point
+        adv_values.append(cols)
     theta = tr.squeeze_challenge()
 
     # ---- lookups: compress, m commitments (:334-366)
     adapter = _RngAdapter(rng, bf, bf + 1)
-    lookups = []
-    for lk in cs.lookups:
-        comp = lambda ex: P.evaluate_with_theta(ex, n, 1, pk.fixed_values, advice_values, instance_values, theta)  # noqa: E731
-        input_sets = [[comp(inp) for inp in s] for s in lk["input_expressions_sets"]]
-        table = comp(lk["table_expressions"])
-        m = logup_multiplicity(input_sets, table, usable, n)
-        for i in range(usable, n):
-            m[i] = adapter.randrange(1 << 16)
-        lookups.append({"input_sets": input_sets, "table": table, "m": m})
-    for lk in lookups:
-        tr.write_point(params.commit_lagrange(lk["m"]))
+    all_lookups = []
+    for advice_values, instance_values in zip(adv_values, inst_values):
+        lookups = []
+        for lk in cs.lookups:
+            comp = lambda ex: P.evaluate_with_theta(ex, n, 1, pk.fixed_values, advice_values, instance_values, theta)  # noqa: E731
+            input_sets = [[comp(inp) for inp in s] for s in lk["input_expressions_sets"]]
+            table = comp(lk["table_expressions"])
+            m = logup_multiplicity(input_sets, table, usable, n)
+            for i in range(usable, n):
+                m[i] = adapter.randrange(1 << 16)
+            lookups.append({"input_sets": input_sets, "table": table, "m": m})
+        all_lookups.append(lookups)
+    for lookups in all_lookups:
+        for lk in lookups:
+            tr.write_point(params.commit_lagrange(lk["m"]))
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
 
-    # ---- z columns (:411-633); transcript order: permutation, lookups, shuffles
-    perm_z = P.permutation_commit(cs, domain, pk.sigmas, advice_values, pk.fixed_values, instance_values, beta, gamma,
-                                  adapter) if cs.permutation_columns else []
-    for lk in lookups:
-        zs = P.logup_commit_z(cs, domain, lk["input_sets"], lk["table"], lk["m"], beta)
-        lk["z"] = [P.blind_to_n(z, n, adapter) for z in zs]
-    shuffle_z = [P.blind_to_n(P.shuffle_commit_product(cs, domain, g, theta, beta, advice_values, pk.fixed_values,
-                                                       instance_values), n, adapter) for g in cs.shuffles]
-    for z in perm_z:
-        tr.write_point(params.commit_lagrange(z))
-    for lk in lookups:
-        for z in lk["z"]:
+    # ---- z columns (:411-633); transcript order: permutations of every circuit, lookups of every circuit, shuffles
+    all_perm_z = [P.permutation_commit(cs, domain, pk.sigmas, av, pk.fixed_values, iv, beta, gamma, adapter)
+                  if cs.permutation_columns else [] for av, iv in zip(adv_values, inst_values)]
+    for lookups in all_lookups:
+        for lk in lookups:
+            zs = P.logup_commit_z(cs, domain, lk["input_sets"], lk["table"], lk["m"], beta)
+            lk["z"] = [P.blind_to_n(z, n, adapter) for z in zs]
+    all_shuffle_z = [[P.blind_to_n(P.shuffle_commit_product(cs, domain, g, theta, beta, av, pk.fixed_values, iv), n, adapter)
+                      for g in cs.shuffles] for av, iv in zip(adv_values, inst_values)]
+    for perm_z in all_perm_z:
+        for z in perm_z:
             tr.write_point(params.commit_lagrange(z))
-    for z in shuffle_z:
-        tr.write_point(params.commit_lagrange(z))
-    perm_polys = [lag2coeff(z) for z in perm_z]
-    for lk in lookups:
-        lk["z_polys"] = [lag2coeff(z) for z in lk["z"]]
-        lk["m_poly"] = lag2coeff(lk["m"])
-    shuffle_polys = [lag2coeff(z) for z in shuffle_z]
+    for lookups in all_lookups:
+        for lk in lookups:
+            for z in lk["z"]:
+                tr.write_point(params.commit_lagrange(z))
+    for shuffle_z in all_shuffle_z:
+        for z in shuffle_z:
+            tr.write_point(params.commit_lagrange(z))
+    all_perm_polys = [[lag2coeff(z) for z in perm_z] for perm_z in all_perm_z]
+    for lookups in all_lookups:
+        for lk in lookups:
+            lk["z_polys"] = [lag2coeff(z) for z in lk["z"]]
+            lk["m_poly"] = lag2coeff(lk["m"])
+    all_shuffle_polys = [[lag2coeff(z) for z in shuffle_z] for shuffle_z in all_shuffle_z]
 
     # ---- vanishing commit, y (:635-639)
     random_poly = vanishing_random_poly(domain, rng)
     tr.write_point(params.commit(random_poly))
     y = tr.squeeze_challenge()
 
-    # ---- h(X) (:640-690, vanishing/prover.rs:64-110)
-    advice_polys = [lag2coeff(c) for c in advice_values]
+    # ---- h(X) (:640-690, vanishing/prover.rs:64-110): one accumulator folded through every circuit instance
+    adv_polys = [[lag2coeff(c) for c in cols] for cols in adv_values]
     ext = domain.coeff_to_extended
-    h = P.evaluate_h(pk.ev, cs, domain, [ext(p) for p in pk.fixed_polys], [ext(p) for p in advice_polys],
-                     [ext(p) for p in instance_polys], pk.l0, pk.l_last, pk.l_active_row,
-                     [ext(p) for p in pk.sigma_polys], y, beta, gamma, theta,
-                     [{"z_cosets": [ext(z) for z in lk["z_polys"]], "m_coset": ext(lk["m_poly"])} for lk in lookups],
-                     [ext(p) for p in shuffle_polys], [ext(p) for p in perm_polys])
+    fixed_cosets, sigma_cosets = [ext(p) for p in pk.fixed_polys], [ext(p) for p in pk.sigma_polys]
+    h = None
+    for ci in range(C):
+        lookups = all_lookups[ci]
+        h = P.evaluate_h(pk.ev, cs, domain, fixed_cosets, [ext(p) for p in adv_polys[ci]],
+                         [ext(p) for p in inst_polys[ci]], pk.l0, pk.l_last, pk.l_active_row,
+                         sigma_cosets, y, beta, gamma, theta,
+                         [{"z_cosets": [ext(z) for z in lk["z_polys"]], "m_coset": ext(lk["m_poly"])} for lk in lookups],
+                         [ext(p) for p in all_shuffle_polys[ci]], [ext(p) for p in all_perm_polys[ci]], values=h)
     h_coeffs = domain.extended_to_coeff(domain.divide_by_vanishing_poly(h))
     h_pieces = [h_coeffs[i:i + n] for i in range(0, len(h_coeffs) - n + 1, n)]  # par_chunks_exact(n)
     for piece in h_pieces:
@@ -544,10 +589,12 @@ def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]]
     # ---- evaluations (:694-790)
     rot = domain.rotate_omega
     ev = o.eval_polynomial
-    for col, at in queries["Instance"]:
-        tr.write_scalar(ev(instance_polys[col], rot(x, at)))
-    for col, at in queries["Advice"]:
-        tr.write_scalar(ev(advice_polys[col], rot(x, at)))
+    for instance_polys in inst_polys:
+        for col, at in queries["Instance"]:
+            tr.write_scalar(ev(instance_polys[col], rot(x, at)))
+    for advice_polys in adv_polys:
+        for col, at in queries["Advice"]:
+            tr.write_scalar(ev(advice_polys[col], rot(x, at)))
     for col, at in queries["Fixed"]:
         tr.write_scalar(ev(pk.fixed_polys[col], rot(x, at)))
     h_poly = [0] * n                                                          # vanishing/prover.rs:119-123
@@ -557,43 +604,48 @@ def create_proof(params: Params, pk: ProvingKey, advice: Sequence[Sequence[int]]
     for poly in pk.sigma_polys:                                               # permutation/prover.rs:194-205
         tr.write_scalar(ev(poly, x))
     x_next, x_last = rot(x, 1), rot(x, -(bf + 1))
-    for i, z in enumerate(perm_polys):                                        # permutation/prover.rs:208-252
-        tr.write_scalar(ev(z, x))
-        tr.write_scalar(ev(z, x_next))
-        if i + 1 < len(perm_polys):
-            tr.write_scalar(ev(z, x_last))
-    for lk in lookups:                                                        # logup/prover.rs:421-447
-        tr.write_scalar(ev(lk["m_poly"], x))
-        for i, z in enumerate(lk["z_polys"]):
+    for perm_polys in all_perm_polys:
+        for i, z in enumerate(perm_polys):                                    # permutation/prover.rs:208-252
             tr.write_scalar(ev(z, x))
             tr.write_scalar(ev(z, x_next))
-            if i + 1 < len(lk["z_polys"]):
+            if i + 1 < len(perm_polys):
                 tr.write_scalar(ev(z, x_last))
-    for z in shuffle_polys:                                                   # shuffle/prover.rs:201-215
-        tr.write_scalar(ev(z, x))
-        tr.write_scalar(ev(z, x_next))
+    for lookups in all_lookups:
+        for lk in lookups:                                                    # logup/prover.rs:421-447
+            tr.write_scalar(ev(lk["m_poly"], x))
+            for i, z in enumerate(lk["z_polys"]):
+                tr.write_scalar(ev(z, x))
+                tr.write_scalar(ev(z, x_next))
+                if i + 1 < len(lk["z_polys"]):
+                    tr.write_scalar(ev(z, x_last))
+    for shuffle_polys in all_shuffle_polys:
+        for z in shuffle_polys:                                               # shuffle/prover.rs:201-215
+            tr.write_scalar(ev(z, x))
+            tr.write_scalar(ev(z, x_next))
 
-    # ---- queries for the multiopen argument (:792-838): (rotation, point, polynomial)
+    # ---- queries for the multiopen argument (:792-838): (rotation, point, polynomial), circuit by circuit
     qs: List[Tuple[int, int, List[int]]] = []
-    for col, at in queries["Instance"]:
-        qs.append((at, rot(x, at), instance_polys[col]))
-    for col, at in queries["Advice"]:
-        qs.append((at, rot(x, at), advice_polys[col]))
-    for z in perm_polys:                                                      # permutation/prover.rs:257-303
-        qs.append((0, x, z))
-        qs.append((1, x_next, z))
-    for z in list(reversed(perm_polys))[1:]:
-        qs.append((-(bf + 1), x_last, z))
-    for lk in lookups:                                                        # logup/prover.rs:451-491
-        qs.append((0, x, lk["m_poly"]))
-        for z in lk["z_polys"]:
+    for ci in range(C):
+        for col, at in queries["Instance"]:
+            qs.append((at, rot(x, at), inst_polys[ci][col]))
+        for col, at in queries["Advice"]:
+            qs.append((at, rot(x, at), adv_polys[ci][col]))
+        perm_polys = all_perm_polys[ci]
+        for z in perm_polys:                                                  # permutation/prover.rs:257-303
             qs.append((0, x, z))
             qs.append((1, x_next, z))
-        for z in list(reversed(lk["z_polys"]))[1:]:
+        for z in list(reversed(perm_polys))[1:]:
             qs.append((-(bf + 1), x_last, z))
-    for z in shuffle_polys:                                                   # shuffle/prover.rs:219-239
-        qs.append((0, x, z))
-        qs.append((1, x_next, z))
+        for lk in all_lookups[ci]:                                            # logup/prover.rs:451-491
+            qs.append((0, x, lk["m_poly"]))
+            for z in lk["z_polys"]:
+                qs.append((0, x, z))
+                qs.append((1, x_next, z))
+            for z in list(reversed(lk["z_polys"]))[1:]:
+                qs.append((-(bf + 1), x_last, z))
+        for z in all_shuffle_polys[ci]:                                       # shuffle/prover.rs:219-239
+            qs.append((0, x, z))
+            qs.append((1, x_next, z))
     for col, at in queries["Fixed"]:
         qs.append((at, rot(x, at), pk.fixed_polys[col]))
     for poly in pk.sigma_polys:                                               # permutation/prover.rs:182-192
@@ -781,58 +833,78 @@ def _g1_lincomb(terms: Sequence[Tuple[int, Point]]) -> Point:
 
 def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[int]], proof: bytes,
                  sign_bit: int = 7, pairing: bool = False, use_gwc: bool = True) -> bool:
-    """plonk/verifier.rs:127-507 with SingleVerifier and the GWC multiopen; False = the final check failed,
-    VerifyError / TranscriptError = the proof is malformed.  `pairing=True` decides with the optimal-ate pairing
-    on [s]G2 (Decider::verify); the default decides with the equivalent G1 equation [s]*left == right."""
+    """one circuit instance per proof: verify_proof_multi with a list of one"""
+    return verify_proof_multi(params, vk, [instances], proof, sign_bit, pairing, use_gwc)
+
+
+def verify_proof_multi(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[Sequence[int]]], proof: bytes,
+                       sign_bit: int = 7, pairing: bool = False, use_gwc: bool = True) -> bool:
+    """plonk/verifier.rs:127-507 with SingleVerifier, for `len(instances)` instances of the circuit in one proof
+    (`instances: &[&[&[C::Scalar]]]`); False = the final check failed, VerifyError / TranscriptError = the proof is
+    malformed.  `pairing=True` decides with the optimal-ate pairing on [s]G2 (Decider::verify); the default decides
+    with the equivalent G1 equation [s]*left == right."""
     cs, domain = vk.cs, vk.domain
     n = params.n
     bf = cs.blinding_factors()
     queries = vk.queries
-    if len(instances) != cs.num_instance:
-        raise VerifyError("InvalidInstances")
-    instance_commitments = []
-    for inst in instances:                                                    # :148-162
-        if len(inst) > n - (bf + 1):
-            raise VerifyError("InstanceTooLarge")
-        instance_commitments.append(params.commit_lagrange([v % R for v in inst]))
+    C = len(instances)
+    all_instance_commitments = []
+    for circuit_instances in instances:
+        if len(circuit_instances) != cs.num_instance:
+            raise VerifyError("InvalidInstances")
+        cm = []
+        for inst in circuit_instances:                                        # :148-162
+            if len(inst) > n - (bf + 1):
+                raise VerifyError("InstanceTooLarge")
+            cm.append(params.commit_lagrange([v % R for v in inst]))
+        all_instance_commitments.append(cm)
     tr = Blake2bRead(proof, sign_bit)
     tr.common_scalar(vk.transcript_repr)                                      # :167
-    for c in instance_commitments:
-        tr.common_point(c)
-    advice_commitments = [tr.read_point() for _ in range(cs.num_advice)]
+    for cm in all_instance_commitments:
+        for c in cm:
+            tr.common_point(c)
+    all_advice_commitments = [[tr.read_point() for _ in range(cs.num_advice)] for _ in range(C)]
     theta = tr.squeeze_challenge()
-    m_commitments = [tr.read_point() for _ in cs.lookups]
+    all_m_commitments = [[tr.read_point() for _ in cs.lookups] for _ in range(C)]
     beta = tr.squeeze_challenge()
     gamma = tr.squeeze_challenge()
     chunk_len = cs.degree() - 2
     n_sets = (len(cs.permutation_columns) + chunk_len - 1) // chunk_len
-    perm_commitments = [tr.read_point() for _ in range(n_sets)]
-    lookup_z_commitments = [[tr.read_point() for _ in lk["input_expressions_sets"]] for lk in cs.lookups]
-    shuffle_commitments = [tr.read_point() for _ in cs.shuffles]
+    all_perm_commitments = [[tr.read_point() for _ in range(n_sets)] for _ in range(C)]
+    all_lookup_z_commitments = [[[tr.read_point() for _ in lk["input_expressions_sets"]] for lk in cs.lookups]
+                                for _ in range(C)]
+    all_shuffle_commitments = [[tr.read_point() for _ in cs.shuffles] for _ in range(C)]
     random_poly_commitment = tr.read_point()
     y = tr.squeeze_challenge()
     h_commitments = [tr.read_point() for _ in range(domain.quotient_poly_degree)]
     x = tr.squeeze_challenge()
-    instance_evals = [tr.read_scalar() for _ in queries["Instance"]]
-    advice_evals = [tr.read_scalar() for _ in queries["Advice"]]
+    all_instance_evals = [[tr.read_scalar() for _ in queries["Instance"]] for _ in range(C)]
+    all_advice_evals = [[tr.read_scalar() for _ in queries["Advice"]] for _ in range(C)]
     fixed_evals = [tr.read_scalar() for _ in queries["Fixed"]]
     random_eval = tr.read_scalar()
     permutation_evals = [tr.read_scalar() for _ in vk.permutation_commitments]
-    perm_sets = []
-    for i, c in enumerate(perm_commitments):                                  # permutation/verifier.rs:74-101
-        e, ne = tr.read_scalar(), tr.read_scalar()
-        le = tr.read_scalar() if i + 1 < len(perm_commitments) else None
-        perm_sets.append({"c": c, "eval": e, "next": ne, "last": le})
-    lookups = []
-    for mc, zcs in zip(m_commitments, lookup_z_commitments):                  # logup/verifier.rs:70-101
-        m_eval = tr.read_scalar()
-        zsets = []
-        for i, c in enumerate(zcs):
+    all_perm_sets = []
+    for perm_commitments in all_perm_commitments:
+        perm_sets = []
+        for i, c in enumerate(perm_commitments):                              # permutation/verifier.rs:74-101
             e, ne = tr.read_scalar(), tr.read_scalar()
-            le = tr.read_scalar() if i + 1 < len(zcs) else None
-            zsets.append({"c": c, "eval": e, "next": ne, "last": le})
-        lookups.append({"m_c": mc, "m_eval": m_eval, "z": zsets})
-    shuffles = [{"c": c, "eval": tr.read_scalar(), "next": tr.read_scalar()} for c in shuffle_commitments]
+            le = tr.read_scalar() if i + 1 < len(perm_commitments) else None
+            perm_sets.append({"c": c, "eval": e, "next": ne, "last": le})
+        all_perm_sets.append(perm_sets)
+    all_lookups = []
+    for m_commitments, lookup_z_commitments in zip(all_m_commitments, all_lookup_z_commitments):
+        lookups = []
+        for mc, zcs in zip(m_commitments, lookup_z_commitments):              # logup/verifier.rs:70-101
+            m_eval = tr.read_scalar()
+            zsets = []
+            for i, c in enumerate(zcs):
+                e, ne = tr.read_scalar(), tr.read_scalar()
+                le = tr.read_scalar() if i + 1 < len(zcs) else None
+                zsets.append({"c": c, "eval": e, "next": ne, "last": le})
+            lookups.append({"m_c": mc, "m_eval": m_eval, "z": zsets})
+        all_lookups.append(lookups)
+    all_shuffles = [[{"c": c, "eval": tr.read_scalar(), "next": tr.read_scalar()} for c in shuffle_commitments]
+                    for shuffle_commitments in all_shuffle_commitments]
 
     # ---- expected h(x) (:280-399)
     xn = pow(x, n, R)
@@ -842,66 +914,69 @@ def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[
     l_blind = sum(l_evals[1:1 + bf]) % R
     l_0 = l_evals[1 + bf]
     active = (1 - (l_last + l_blind)) % R
-    ee = lambda e: eval_expression_at_queries(e, queries, fixed_evals, advice_evals, instance_evals)  # noqa: E731
-    comp = lambda exprs: _fold([ee(e) for e in exprs], theta)                 # noqa: E731
-
-    def col_eval(column):
-        kind, idx = column
-        evals = {"Fixed": fixed_evals, "Advice": advice_evals, "Instance": instance_evals}[kind]
-        return evals[queries[kind].index((idx, 0))]                          # get_any_query_index(column, cur)
-
     exprs: List[int] = []
-    for gate in cs.gates:
-        for poly in gate:
-            exprs.append(ee(poly))
-    # permutation/verifier.rs:105-203
-    if perm_sets:
-        exprs.append(l_0 * (1 - perm_sets[0]["eval"]) % R)
-        last = perm_sets[-1]["eval"]
-        exprs.append((last * last - last) * l_last % R)
-        for i in range(1, len(perm_sets)):
-            exprs.append((perm_sets[i]["eval"] - perm_sets[i - 1]["last"]) * l_0 % R)
-        for ci, st in enumerate(perm_sets):
-            columns = cs.permutation_columns[ci * chunk_len:(ci + 1) * chunk_len]
-            pevals = permutation_evals[ci * chunk_len:(ci + 1) * chunk_len]
-            left = st["next"]
-            for column, pe in zip(columns, pevals):
-                left = left * ((col_eval(column) + beta * pe + gamma) % R) % R
-            right = st["eval"]
-            cur_delta = beta * x % R * pow(P.FR_DELTA, ci * chunk_len, R) % R
-            for column in columns:
-                right = right * ((col_eval(column) + cur_delta + gamma) % R) % R
-                cur_delta = cur_delta * P.FR_DELTA % R
-            exprs.append((left - right) * active % R)
-    # logup/verifier.rs:104-218
-    for lk, arg in zip(lookups, cs.lookups):
-        zs = lk["z"]
-        exprs.append(l_0 * zs[0]["eval"] % R)
-        exprs.append(l_last * zs[-1]["eval"] % R)
-        phi = [(comp(inp) + beta) % R for inp in arg["input_expressions_sets"][0]]
-        tau = (comp(arg["table_expressions"]) + beta) % R
-        product_fi = _prod(phi)
-        sum_inv = sum(o.fr_inv(p) if p else 0 for p in phi) % R
-        left = (tau * (zs[0]["next"] - zs[0]["eval"]) + lk["m_eval"]) % R * product_fi % R
-        right = tau * product_fi % R * sum_inv % R
-        exprs.append((left - right) * active % R)
-        for i in range(1, len(zs)):
-            exprs.append(l_0 * (zs[i]["eval"] - zs[i - 1]["last"]) % R)
-        for zset, iset in list(zip(zs, arg["input_expressions_sets"]))[1:]:
-            phi = [(comp(inp) + beta) % R for inp in iset]
+    for ci in range(C):
+        advice_evals, instance_evals = all_advice_evals[ci], all_instance_evals[ci]
+        perm_sets, lookups, shuffles = all_perm_sets[ci], all_lookups[ci], all_shuffles[ci]
+        ee = lambda e: eval_expression_at_queries(e, queries, fixed_evals, advice_evals, instance_evals)  # noqa: E731
+        comp = lambda exprs: _fold([ee(e) for e in exprs], theta)             # noqa: E731
+
+        def col_eval(column):
+            kind, idx = column
+            evals = {"Fixed": fixed_evals, "Advice": advice_evals, "Instance": instance_evals}[kind]
+            return evals[queries[kind].index((idx, 0))]                      # get_any_query_index(column, cur)
+
+        for gate in cs.gates:
+            for poly in gate:
+                exprs.append(ee(poly))
+        # permutation/verifier.rs:105-203
+        if perm_sets:
+            exprs.append(l_0 * (1 - perm_sets[0]["eval"]) % R)
+            last = perm_sets[-1]["eval"]
+            exprs.append((last * last - last) * l_last % R)
+            for i in range(1, len(perm_sets)):
+                exprs.append((perm_sets[i]["eval"] - perm_sets[i - 1]["last"]) * l_0 % R)
+            for si, st in enumerate(perm_sets):
+                columns = cs.permutation_columns[si * chunk_len:(si + 1) * chunk_len]
+                pevals = permutation_evals[si * chunk_len:(si + 1) * chunk_len]
+                left = st["next"]
+                for column, pe in zip(columns, pevals):
+                    left = left * ((col_eval(column) + beta * pe + gamma) % R) % R
+                right = st["eval"]
+                cur_delta = beta * x % R * pow(P.FR_DELTA, si * chunk_len, R) % R
+                for column in columns:
+                    right = right * ((col_eval(column) + cur_delta + gamma) % R) % R
+                    cur_delta = cur_delta * P.FR_DELTA % R
+                exprs.append((left - right) * active % R)
+        # logup/verifier.rs:104-218
+        for lk, arg in zip(lookups, cs.lookups):
+            zs = lk["z"]
+            exprs.append(l_0 * zs[0]["eval"] % R)
+            exprs.append(l_last * zs[-1]["eval"] % R)
+            phi = [(comp(inp) + beta) % R for inp in arg["input_expressions_sets"][0]]
+            tau = (comp(arg["table_expressions"]) + beta) % R
             product_fi = _prod(phi)
             sum_inv = sum(o.fr_inv(p) if p else 0 for p in phi) % R
-            exprs.append((zset["next"] - zset["eval"] - sum_inv) * product_fi % R * active % R)
-    # shuffle/verifier.rs:58-121
-    for sh, group in zip(shuffles, cs.shuffles):
-        exprs.append(l_0 * (1 - sh["eval"]) % R)
-        exprs.append(l_last * (sh["eval"] * sh["eval"] - sh["eval"]) % R)
-        ps, pi = 1, 1
-        for i, a in enumerate(group):
-            ch = pow(beta, 1 + i, R)
-            ps = ps * ((comp(a["shuffle_expressions"]) + ch) % R) % R
-            pi = pi * ((comp(a["input_expressions"]) + ch) % R) % R
-        exprs.append((sh["next"] * ps - sh["eval"] * pi) * active % R)
+            left = (tau * (zs[0]["next"] - zs[0]["eval"]) + lk["m_eval"]) % R * product_fi % R
+            right = tau * product_fi % R * sum_inv % R
+            exprs.append((left - right) * active % R)
+            for i in range(1, len(zs)):
+                exprs.append(l_0 * (zs[i]["eval"] - zs[i - 1]["last"]) % R)
+            for zset, iset in list(zip(zs, arg["input_expressions_sets"]))[1:]:
+                phi = [(comp(inp) + beta) % R for inp in iset]
+                product_fi = _prod(phi)
+                sum_inv = sum(o.fr_inv(p) if p else 0 for p in phi) % R
+                exprs.append((zset["next"] - zset["eval"] - sum_inv) * product_fi % R * active % R)
+        # shuffle/verifier.rs:58-121
+        for sh, group in zip(shuffles, cs.shuffles):
+            exprs.append(l_0 * (1 - sh["eval"]) % R)
+            exprs.append(l_last * (sh["eval"] * sh["eval"] - sh["eval"]) % R)
+            ps, pi = 1, 1
+            for i, a in enumerate(group):
+                ch = pow(beta, 1 + i, R)
+                ps = ps * ((comp(a["shuffle_expressions"]) + ch) % R) % R
+                pi = pi * ((comp(a["input_expressions"]) + ch) % R) % R
+            exprs.append((sh["next"] * ps - sh["eval"] * pi) * active % R)
     expected_h_eval = _fold(exprs, y) * o.fr_inv((xn - 1) % R) % R          # vanishing/verifier.rs:88-96
 
     # h_commitment MSM: sum xn^i * h_i (vanishing/verifier.rs:98-106)
@@ -915,25 +990,27 @@ def verify_proof(params: Params, vk: VerifyingKey, instances: Sequence[Sequence[
     x_next, x_last = rot(x, 1), rot(x, -(bf + 1))
     qs = []
     one = lambda c: [(1, c)]                                                   # noqa: E731
-    for (col, at), e in zip(queries["Instance"], instance_evals):
-        qs.append((at, rot(x, at), one(instance_commitments[col]), e, ("instance", col)))
-    for (col, at), e in zip(queries["Advice"], advice_evals):
-        qs.append((at, rot(x, at), one(advice_commitments[col]), e, ("advice", col)))
-    for i, st in enumerate(perm_sets):
-        qs.append((0, x, one(st["c"]), st["eval"], ("perm", i)))
-        qs.append((1, x_next, one(st["c"]), st["next"], ("perm", i)))
-    for i, st in list(reversed(list(enumerate(perm_sets))))[1:]:
-        qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("perm", i)))
-    for li, lk in enumerate(lookups):
-        qs.append((0, x, one(lk["m_c"]), lk["m_eval"], ("lookup_m", li)))
-        for i, st in enumerate(lk["z"]):
-            qs.append((0, x, one(st["c"]), st["eval"], ("lookup_z", li, i)))
-            qs.append((1, x_next, one(st["c"]), st["next"], ("lookup_z", li, i)))
-        for i, st in list(reversed(list(enumerate(lk["z"]))))[1:]:
-            qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("lookup_z", li, i)))
-    for i, sh in enumerate(shuffles):
-        qs.append((0, x, one(sh["c"]), sh["eval"], ("shuffle", i)))
-        qs.append((1, x_next, one(sh["c"]), sh["next"], ("shuffle", i)))
+    for ci in range(C):
+        perm_sets, lookups, shuffles = all_perm_sets[ci], all_lookups[ci], all_shuffles[ci]
+        for (col, at), e in zip(queries["Instance"], all_instance_evals[ci]):
+            qs.append((at, rot(x, at), one(all_instance_commitments[ci][col]), e, ("instance", ci, col)))
+        for (col, at), e in zip(queries["Advice"], all_advice_evals[ci]):
+            qs.append((at, rot(x, at), one(all_advice_commitments[ci][col]), e, ("advice", ci, col)))
+        for i, st in enumerate(perm_sets):
+            qs.append((0, x, one(st["c"]), st["eval"], ("perm", ci, i)))
+            qs.append((1, x_next, one(st["c"]), st["next"], ("perm", ci, i)))
+        for i, st in list(reversed(list(enumerate(perm_sets))))[1:]:
+            qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("perm", ci, i)))
+        for li, lk in enumerate(lookups):
+            qs.append((0, x, one(lk["m_c"]), lk["m_eval"], ("lookup_m", ci, li)))
+            for i, st in enumerate(lk["z"]):
+                qs.append((0, x, one(st["c"]), st["eval"], ("lookup_z", ci, li, i)))
+                qs.append((1, x_next, one(st["c"]), st["next"], ("lookup_z", ci, li, i)))
+            for i, st in list(reversed(list(enumerate(lk["z"]))))[1:]:
+                qs.append((-(bf + 1), x_last, one(st["c"]), st["last"], ("lookup_z", ci, li, i)))
+        for i, sh in enumerate(shuffles):
+            qs.append((0, x, one(sh["c"]), sh["eval"], ("shuffle", ci, i)))
+            qs.append((1, x_next, one(sh["c"]), sh["next"], ("shuffle", ci, i)))
     for (col, at), e in zip(queries["Fixed"], fixed_evals):
         qs.append((at, rot(x, at), one(vk.fixed_commitments[col]), e, ("fixed", col)))
     for i, (c, e) in enumerate(zip(vk.permutation_commitments, permutation_evals)):

@@ -167,7 +167,24 @@ class CosetQuotientDouble:
         return np.ascontiguousarray(enc(coeffs[:pieces * n])).reshape(pieces, n, 4)
 
     def all_reduce_rows(self, hext):
-        import torch
         import torch.distributed as dist
-        t = torch.from_numpy(hext.view(np.int64))
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        dist.all_reduce(self.as_tensor(hext), op=dist.ReduceOp.SUM)
+
+    # -- what ShardedCommits.put_and_commit_lagrange / exchange_columns ask for (gloo on host arrays)
+    @staticmethod
+    def as_tensor(block):
+        import torch
+        return torch.from_numpy(block.view(np.int64))
+
+    @staticmethod
+    def before_collective():
+        pass
+
+    @staticmethod
+    def after_collective():
+        pass
+
+    def put_share_and_commit(self, block, host, lo, hi, max_bits):
+        """only this rank's columns are copied in: the others stay zero until exchange_columns delivers them"""
+        block[lo:hi] = host[lo:hi]
+        return self.commit_columns_with_bound(block[lo:hi], max_bits)

@@ -501,3 +501,39 @@ def test_cpp_transcript_matches_python(tmp_path):
     assert py.finalize() == ref.finalize()
     out = subprocess.run([exe], input="\n".join(lines) + "\n", capture_output=True, text=True, check=True).stdout.split("\n")
     assert [l for l in out if l] == want
+
+
+def _two_instances(k, seed):
+    """a second satisfying witness for the same proving key: the fixture with another seed differs in the advice and
+    instance columns and in rows of fixed column 5 beyond the usable range, which no constraint reads"""
+    fx, oparams, opk, cs, eng, pk = both_sides(k, seed)
+    fx2 = fxm.build(k=k, seed=seed + 100)
+    usable = (1 << k) - cs.blinding_factors() - 1
+    assert all(a[:usable] == b[:usable] for a, b in zip(fx["fixed"], fx2["fixed"])) and fx["mapping"] == fx2["mapping"]
+    advs = [fx["advice"], fx2["advice"]]
+    insts = [[fx["instance"][0][:4]], [fx2["instance"][0][:4]]]
+    return oparams, opk, cs, eng, pk, advs, insts
+
+
+@pytest.mark.parametrize("use_gwc", [True, False])
+def test_multi_circuit_proof_bytes_match_oracle_and_verify(use_gwc):
+    """create_proof_ext(circuits: &[C], instances: &[&[&[Fr]]]) (plonk/prover.rs:206-222): two instances of the
+    circuit in one proof.  The oracle folds both through ONE evaluate_h accumulator as the reference does; the prover
+    mirror evaluates each instance on its own and folds the h pieces with y^fold_steps -- the bytes must agree, the
+    oracle verifier must accept them and must reject the instances in the other order."""
+    k = 5
+    oparams, opk, cs, eng, pk, advs, insts = _two_instances(k, 11)
+    assert HP.fold_steps(cs) == PR.fold_steps(opk.vk.cs)
+    want = PR.create_proof_multi(oparams, opk, advs, insts, HP.SeededRng(5), use_gwc=use_gwc)
+    got = HP.create_proof_multi(HostParams(k), pk, [np.ascontiguousarray(np.stack([enc(c) for c in a])) for a in advs],
+                                insts, HP.SeededRng(5), engine=eng, use_gwc=use_gwc)
+    assert got == want
+    assert PR.verify_proof_multi(oparams, opk.vk, insts, got, use_gwc=use_gwc)
+    assert PR.verify_proof_multi(oparams, opk.vk, insts, got, use_gwc=use_gwc, pairing=True)
+    assert not PR.verify_proof_multi(oparams, opk.vk, insts[::-1], got, use_gwc=use_gwc)
+    single = PR.create_proof(oparams, opk, advs[0], insts[0], HP.SeededRng(5), use_gwc=use_gwc)
+    assert len(got) > len(single)
+    with pytest.raises(HP.B2Error):
+        HP.create_proof_multi(HostParams(k), pk, [], [], HP.SeededRng(5), engine=eng)
+    with pytest.raises(HP.B2Error):
+        HP.create_proof_multi(HostParams(k), pk, [np.zeros((9, 32, 4), dtype=np.uint64)], insts, HP.SeededRng(5), engine=eng)
