@@ -51,6 +51,11 @@ METRIC = "BN254 G1 MSM throughput at 2^22 points per GPU"
 UNIT = "Mpts/s"
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu --set full
+# exports under profiles/ (key: kernel, log2 n, window tables); None for configurations that were not captured
+NCU_TRAFFIC = {("msm_accumulate", 22, True): 7.513166e9 + 83.072e6}
+
+
 def _peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -325,6 +330,8 @@ def run_engine(args):
     # --- IMAD peak probe (integer roofline denominator), before the timed region
     macs, muls = ctypes.c_double(), ctypes.c_double()
     _lib.check(L.b2_imad_probe(ctypes.byref(macs), ctypes.byref(muls)))
+    raw_wide = ctypes.c_double()                     # independent of the field code: bare IMAD.WIDE.U32 chains, no carries
+    _lib.check(L.b2_pipe_probe(0, ctypes.byref(raw_wide)))
 
     for _ in range(args.warmup):
         step_resident()
@@ -471,6 +478,8 @@ def run_engine(args):
         mac_per_launch = 128.0 * 10.0 * n * windows          # 10 mul-equivalents per mixed add
         achieved = mac_per_launch / (acc * 1e-3) / 1e12
         peak = float(macs.value) / 1e12
+        sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+        sm_hz = float((clocks or {}).get("sm_max_mhz") or 1965.0) * 1e6
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
@@ -504,9 +513,18 @@ def run_engine(args):
             "roofline": {
                 "kernel": "msm_accumulate_kernel", "bound": "int", "achieved": achieved, "peak": peak, "unit": "TMAC/s",
                 "frac": achieved / peak,
-                "traffic": 7.59e9 if (args.logn == 22 and not args.no_precompute) else None,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from ncu --set full "
-                                "(profiles/r1_ncu_summary.md); algorithmic gather bytes 3.7e9: DRAM is ~10 % busy",
+                "frac_vs": {
+                    "montgomery_product_probe": achieved / peak,
+                    "raw_imad_wide_probe": achieved / (raw_wide.value / 1e12),
+                    "nominal_64_per_clk_per_sm": achieved / (sm_hz * 64 * sms / 1e12),
+                    "note": "raw probe = b2_pipe_probe(0) in this run: 8 independent IMAD.WIDE.U32 chains per thread, "
+                            f"{raw_wide.value / 1e12:.2f} T/s = {raw_wide.value / (sm_hz * sms):.1f} "
+                            "per clock per SM (the 32 x 32 + 64 form runs at half the 64 / clk / SM of plain IMAD; "
+                            "SASS and ncu pipe counters of the probe: profiles/r2_ncu_summary.md)"},
+                "traffic": NCU_TRAFFIC.get(("msm_accumulate", args.logn, not args.no_precompute)),
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one launch, from the committed "
+                                "ncu --set full export profiles/r2_ncu_msm_accumulate.raw.csv (7.513 GB read + 0.083 GB "
+                                "written at 2^22 with window tables); algorithmic gather bytes 3.7e9: DRAM is ~13 % busy",
                 "model": f"128 MACs x 10 mul-equivalents x n x W = {mac_per_launch:.3e} 32x32->64 MACs per launch "
                          f"(SURVEY 8d), duration {acc:.3f} ms (CUDA events, mean of {len(acc_ms)}); the kernel issues "
                          "9.44 product-equivalents per mixed add (the two products of Y3 share one reduction), so "

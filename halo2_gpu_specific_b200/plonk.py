@@ -490,14 +490,17 @@ class ArrayBlocks:
             points += self.commit_lagrange(host[i:i + 1], canonical_max_bits(self.from_mont(host[i])))
         return host, points
 
-    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds):
+    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds, only=None):
         """logup `compress` (logup/prover.rs:70-256) for every lookup: compressed inputs and table on the engine,
-        the multiplicities counted on the host as the reference does -> (block of m columns, bound for their commit)"""
+        the multiplicities counted on the host as the reference does -> (block of m columns, bound for their commit).
+        only: the lookup indices to work on (the multi-GPU prover divides them); the other columns are left zero."""
         n = self.domain.n
         usable = n - (cs.blinding_factors() + 1)
         m_canon = np.zeros((len(cs.lookups), n, 4), dtype=np.uint64)
         m_bits = 16
         for li, lk in enumerate(cs.lookups):
+            if only is not None and li not in only:
+                continue
             lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
             comp = self.compress_canonical(lists, advice, pk.fixed_values, instance, theta)
             counts = logup_multiplicity(list(comp[:-1]), comp[-1], usable, n)
@@ -894,10 +897,11 @@ class ResidentEngine:
         ptrs = lambda b: [b.ptr + i * b.n * 32 for i in range(b.count)]      # noqa: E731
         return _Columns.resident(ptrs(key["fixed_values"]), ptrs(advice), ptrs(instance), self.domain.n)
 
-    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds):
+    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds, only=None):
         """logup `compress` (logup/prover.rs:70-256) for every lookup without leaving the device: the compressed
         inputs and table are produced by the expression kernel, sorted and matched there (logup_multiplicity_device),
-        and m(X) is written as a resident column; only the largest count (for the commit bound) returns."""
+        and m(X) is written as a resident column; only the largest count (for the commit bound) returns.
+        only: the lookup indices to work on (the multi-GPU prover divides them); other columns are left untouched."""
         from .grand_product import compress_expressions_dev
         n = self.domain.n
         bf = cs.blinding_factors()
@@ -907,6 +911,8 @@ class ResidentEngine:
         m_bits = 16
         cols = self._columns(pk, advice, instance)
         for li, lk in enumerate(cs.lookups):
+            if only is not None and li not in only:
+                continue
             lists = [inp for s in lk["input_expressions_sets"] for inp in s] + [lk["table_expressions"]]
             comp = self.alloc(len(lists))
             compress_expressions_dev(self.domain, lists, cols, theta, comp.ptr)
@@ -1420,19 +1426,30 @@ def _create_proof(E, pk, cs, domain, advices, instances, rng, sign_bit, advice_m
         if n_perm:
             blinds = [rng.fr_vec(bf) for _ in range(n_perm)]
             E.permutation_z(cs, pk, advs[ci], inst_values[ci], beta, gamma, blinds, E.cols(z_blocks[ci])[:n_perm])
+    # A multi-GPU engine builds only the z columns it will commit (owns_columns) and receives the others, already in
+    # coefficient form, inside commit_lagrange_and_ifft; the z columns of one lookup are chained (z_i starts where
+    # z_(i-1) ended), so a lookup is built whole by every rank that owns one of them.  The random draws do not depend
+    # on ownership: every rank consumes the same stream.
+    owns = getattr(E, "owns_columns", None) or (lambda block, lo, hi: True)
     for ci in range(C):
         zc, m_cols, pos = E.cols(z_blocks[ci]), E.cols(all_ms[ci]), n_perm
         for li, lk in enumerate(cs.lookups):
             cnt = lookup_z_counts[li]
-            E.logup_z(cs, lk, pk, advs[ci], inst_values[ci], m_cols[li], theta, beta, zc[pos:pos + cnt])
+            mine = owns(z_blocks[ci], pos, pos + cnt)
+            if mine:
+                E.logup_z(cs, lk, pk, advs[ci], inst_values[ci], m_cols[li], theta, beta, zc[pos:pos + cnt])
             for z in zc[pos:pos + cnt]:
-                E.write_rows(z, n - bf, rng.fr_vec(bf))
+                blind = rng.fr_vec(bf)
+                if mine:
+                    E.write_rows(z, n - bf, blind)
             pos += cnt
     for ci in range(C):
         zc, pos = E.cols(z_blocks[ci]), n_perm + sum(lookup_z_counts)
         for gi, group in enumerate(cs.shuffles):
-            E.shuffle_z(cs, group, pk, advs[ci], inst_values[ci], theta, beta, zc[pos + gi])
-            E.write_rows(zc[pos + gi], n - bf, rng.fr_vec(bf))
+            blind = rng.fr_vec(bf)
+            if owns(z_blocks[ci], pos + gi, pos + gi + 1):
+                E.shuffle_z(cs, group, pk, advs[ci], inst_values[ci], theta, beta, zc[pos + gi])
+                E.write_rows(zc[pos + gi], n - bf, blind)
     z_points = [E.commit_lagrange_and_ifft(zb) if n_z else [] for zb in z_blocks]
     for pts in z_points:
         for c in pts[:n_perm]:

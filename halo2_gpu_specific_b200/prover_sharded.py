@@ -101,19 +101,54 @@ class ShardedCommits:
         return self._gather(pts, self.block_count(block))
 
     def commit_lagrange_and_ifft(self, block) -> List[Point]:
-        """own share: commitment + inverse transform in one pass; the other columns are needed in coefficient form on
-        this rank too (evaluate_h reads every z polynomial), so they are only transformed"""
+        """own share: commitment + inverse transform in one pass; the other columns arrive from their owners in
+        coefficient form (exchange_columns) -- evaluate_h reads every z polynomial on every rank.  The owners are also
+        the only ranks that built those columns (owns_columns)."""
         if self._inside:
             return super().commit_lagrange_and_ifft(block)
         count = self.block_count(block)
         lo, hi = self._share(count)
         with self._local():
             pts = super().commit_lagrange_and_ifft(self.sub_block(block, lo, hi)) if hi > lo else []
-            if lo > 0:
-                self.lagrange_to_coeff(self.sub_block(block, 0, lo))
-            if hi < count:
-                self.lagrange_to_coeff(self.sub_block(block, hi, count))
+        self.exchange_columns(block)
         return self._gather(pts, count)
+
+    def owns_columns(self, block, lo: int, hi: int) -> bool:
+        """does this rank commit (hence build) any of the columns [lo, hi) of `block`?"""
+        mine_lo, mine_hi = self._share(self.block_count(block))
+        return lo < mine_hi and mine_lo < hi
+
+    def lagrange_to_coeff(self, block):
+        """wide blocks (the advice columns): every rank transforms its share and the shares are exchanged over
+        NVLink; narrow blocks are cheaper to transform everywhere than to move"""
+        _, world = parallel.world()
+        count = self.block_count(block)
+        if self._inside or world == 1 or count < 4 * world:
+            return super().lagrange_to_coeff(block)
+        lo, hi = self._share(count)
+        with self._local():
+            if hi > lo:
+                super().lagrange_to_coeff(self.sub_block(block, lo, hi))
+        self.exchange_columns(block)
+        return block
+
+    def multiplicity_block(self, cs, pk, advice, instance, theta: int, blinds, only=None):
+        """the lookups are divided like the columns of the m block (so a rank counts exactly the m columns it will
+        commit), the columns exchanged and the commit bound maximised over the ranks"""
+        d = parallel._dist()
+        n_lookups = len(cs.lookups)
+        if self._inside or d is None or n_lookups == 0:
+            return super().multiplicity_block(cs, pk, advice, instance, theta, blinds, only)
+        lo, hi = self._share(n_lookups)
+        with self._local():
+            ms, bits = super().multiplicity_block(cs, pk, advice, instance, theta, blinds, only=range(lo, hi))
+        self.exchange_columns(ms)
+        import torch
+        t = torch.tensor([bits], dtype=torch.int64)
+        if d.get_backend() == "nccl":
+            t = t.cuda()
+        d.all_reduce(t, op=d.ReduceOp.MAX)
+        return ms, int(t.item())
 
     def put_and_commit_lagrange(self, host, max_bits: Optional[int]):
         """The advice columns: rank r brings ONLY its share of the columns across its PCIe link (committing them on

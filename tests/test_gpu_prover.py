@@ -376,3 +376,34 @@ def test_random_circuits_proof_bytes_match_oracle(gpu, seed):
             assert got == want, f"seed {seed}, {kind.__name__}"
     finally:
         params.free()
+
+
+@pytest.mark.parametrize("engine_kind", ["resident", "host_api"])
+@pytest.mark.parametrize("use_gwc", [True, False])
+def test_multi_circuit_proof_bytes_match_oracle(gpu, engine_kind, use_gwc):
+    """create_proof_ext(circuits: &[C], instances: &[&[&[Fr]]]) (plonk/prover.rs:206-222) on the device: two instances
+    of the fixture circuit in one proof; bytes equal to the oracle's, which folds both through one evaluate_h
+    accumulator as the reference does, and accepted by the oracle's multi-instance verifier"""
+    k, seed = 5, 11
+    fx, fx2 = fxm.build(k=k, seed=seed), fxm.build(k=k, seed=seed + 100)
+    ocs = fx["cs"]
+    oparams = PR.Params(k, S_TOXIC)
+    opk = PR.keygen(oparams, ocs, fx["fixed"], fx["mapping"])
+    cs = HP.ConstraintSystem.like(ocs)
+    params, pk = engine_side(k, oparams, cs, np.stack([enc(c) for c in fx["fixed"]]),
+                             np.array(fx["mapping"], dtype=np.int64), opk.vk.transcript_repr)
+    try:
+        advs = [fx["advice"], fx2["advice"]]
+        insts = [[fx["instance"][0][:4]], [fx2["instance"][0][:4]]]
+        want = PR.create_proof_multi(oparams, opk, advs, insts, HP.SeededRng(9), use_gwc=use_gwc)
+        dev_advs = [np.ascontiguousarray(np.stack([enc(c) for c in a])) for a in advs]
+        eng = (HP.ResidentEngine if engine_kind == "resident" else HP.Engine)(params, pk.vk.domain)
+        try:
+            got = HP.create_proof_multi(params, pk, dev_advs, insts, HP.SeededRng(9), engine=eng, use_gwc=use_gwc)
+        finally:
+            eng.free()
+        assert got == want
+        assert PR.verify_proof_multi(oparams, opk.vk, insts, got, use_gwc=use_gwc, pairing=use_gwc)
+        assert not PR.verify_proof_multi(oparams, opk.vk, insts[::-1], got, use_gwc=use_gwc)
+    finally:
+        params.free()
