@@ -247,6 +247,10 @@ def test_shoup_generator_emulation_and_committed_header():
         assert f.read() == gs.render(g)
 
 
+# ---- public third-party vectors for this curve (alt_bn128 = BN254): EIP-196 ecAdd / ecMul, EIP-197 pairing check ----
+EIP = json.load(open(os.path.join(HERE, "golden", "eip196_197.json")))
+
+
 def _eip_g1(h):
     x, y = int(h[:64], 16), int(h[64:128], 16)
     return None if (x, y) == (0, 0) else (x, y)
