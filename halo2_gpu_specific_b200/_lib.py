@@ -48,7 +48,7 @@ SYMBOLS = [
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
-    "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_msm_async", "b2_msm_wait", "b2_logup_multiplicity_dev", "b2_eval_polynomials_dev", "b2_dfma_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
+    "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_msm_async", "b2_msm_wait", "b2_logup_multiplicity_dev", "b2_eval_polynomials_dev", "b2_dfma_probe", "b2_mixed_probe", "b2_affine_batch_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
     "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
     "b2_g1_decompress", "b2_g1_compress", "b2_srs_register_compressed", "b2_srs_read_compressed",
     "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev", "b2_poly_combine", "b2_poly_combine_dev", "b2_witness_file_columns", "b2_commit_witness_file",
@@ -111,6 +111,9 @@ def lib() -> ctypes.CDLL:
         L.b2_mul_probe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
         L.b2_dfma_probe.argtypes = [ctypes.POINTER(ctypes.c_double)]
         L.b2_pipe_probe.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.b2_mixed_probe.argtypes = [u32, u32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        L.b2_affine_batch_probe.argtypes = [sz, u32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                            vp, vp, vp, sz]
         L.b2_last_timing.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
         L.b2_last_msm_phases.argtypes = [ctypes.POINTER(ctypes.c_double)]
         L.b2_msm_config.argtypes = [u64, sz, u32, ctypes.POINTER(u32), ctypes.POINTER(u32), ctypes.POINTER(u32)]

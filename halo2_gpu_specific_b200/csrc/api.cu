@@ -26,6 +26,7 @@
 
 #include "../../include/b2pcs.h"
 #include "msm.cuh"
+#include "probe_mixed.cuh"
 #include "ntt.cuh"
 #include "quotient.cuh"
 #include "scan.cuh"
@@ -1935,6 +1936,83 @@ int b2_pipe_probe(int kind, double* macs_per_s) {
     if ((rc = ctx->out96.reserve(96))) return rc;
     if (kind == 0) return run_pipe_probe<0>(ctx, macs_per_s);
     return run_pipe_probe<1>(ctx, macs_per_s);
+}
+
+int b2_mixed_probe(uint32_t imad_mask, uint32_t dfma_mask, int int_kind, int iters_int, int iters_f64, double* ms_out) {
+    if (!ms_out || (imad_mask & dfma_mask) || int_kind < 0 || int_kind > 1 || iters_int < 0 || iters_f64 < 0)
+        return fail(B2_ERR_ARG, "mixed_probe: disjoint warp masks (8 warps per block), int_kind 0..1");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    if ((rc = ctx->out96.reserve(96))) return rc;
+    cudaStream_t st = ctx->stream;
+    const int blocks = ctx->sms * 2, threads = 256;   // 2 blocks x 8 warps per SM = 4 warps per scheduler
+    LAUNCH(*ctx, mixed_probe_kernel<2>, blocks, threads, 0, st, ctx->out96.as<uint4>(), 10, 10, imad_mask, dfma_mask,
+           int_kind);
+    double best = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, mixed_probe_kernel<2>, blocks, threads, 0, st, ctx->out96.as<uint4>(), iters_int, iters_f64,
+               imad_mask, dfma_mask, int_kind);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        if (ms < best) best = ms;
+    }
+    *ms_out = best;
+    return B2_OK;
+}
+
+int b2_affine_batch_probe(size_t n_pairs, uint32_t B, double* batch_ms, double* xyzz_ms, void* host_p, void* host_q,
+                          void* host_out, size_t n_copy) {
+    if (!batch_ms || !xyzz_ms || B == 0 || n_pairs == 0 || n_pairs % B || n_copy > n_pairs)
+        return fail(B2_ERR_ARG, "affine_batch_probe: n_pairs must be a multiple of B");
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = ctx->stream;
+    const uint32_t nthreads = (uint32_t)(n_pairs / B);
+    char *P = nullptr, *Q = nullptr, *out = nullptr, *xo = nullptr;
+    uint4* prefix = nullptr;
+    auto cleanup = [&]() { cudaFree(P); cudaFree(Q); cudaFree(out); cudaFree(xo); cudaFree(prefix); };
+    if (cudaMalloc(&P, n_pairs * 64) != cudaSuccess || cudaMalloc(&Q, n_pairs * 64) != cudaSuccess ||
+        cudaMalloc(&out, n_pairs * 64) != cudaSuccess || cudaMalloc(&xo, (size_t)nthreads * 128) != cudaSuccess ||
+        cudaMalloc(&prefix, n_pairs * 32) != cudaSuccess) {
+        cleanup();
+        cudaGetLastError();
+        return fail(B2_ERR_OOM, "affine_batch_probe: device allocation");
+    }
+    const unsigned gp = (unsigned)((n_pairs + 127) / 128), gt = (nthreads + 127) / 128;
+    LAUNCH(*ctx, srs_synth_kernel, gp, 128, 0, st, P, (unsigned long long)n_pairs, 0ull, 0x1111ull);
+    LAUNCH(*ctx, srs_synth_kernel, gp, 128, 0, st, Q, (unsigned long long)n_pairs, 0ull, 0x2222ull);
+    double best_b = 1e30, best_x = 1e30;
+    for (int rep = 0; rep < 3; rep++) {
+        float ms = 0;
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, affine_batch_probe_kernel, gt, 128, 0, st, P, Q, out, prefix, B, nthreads);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        if (ms < best_b) best_b = ms;
+        CK(cudaEventRecord(ctx->ev[12], st));
+        LAUNCH(*ctx, xyzz_pair_probe_kernel, gt, 128, 0, st, P, Q, xo, B, nthreads);
+        CK(cudaEventRecord(ctx->ev[13], st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaEventElapsedTime(&ms, ctx->ev[12], ctx->ev[13]));
+        if (ms < best_x) best_x = ms;
+    }
+    *batch_ms = best_b;
+    *xyzz_ms = best_x;
+    cudaError_t e = cudaSuccess;
+    if (n_copy && host_p) e = cudaMemcpy(host_p, P, n_copy * 64, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && n_copy && host_q) e = cudaMemcpy(host_q, Q, n_copy * 64, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && n_copy && host_out) e = cudaMemcpy(host_out, out, n_copy * 64, cudaMemcpyDeviceToHost);
+    cleanup();
+    if (e != cudaSuccess) return fail(B2_ERR_CUDA, "affine_batch_probe: %s", cudaGetErrorString(e));
+    return B2_OK;
 }
 
 int b2_last_timing(double* kernel_ms, double* total_ms) {

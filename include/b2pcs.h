@@ -402,6 +402,18 @@ int b2_pipe_probe(int kind, double* macs_per_s);
 /* FP64 FMA rate of the device (diagnostic: documents why the fp64 pipe is / is not a usable
  * second multiplier for the bignum kernels on this part). */
 int b2_dfma_probe(double* dfma_per_s);
+/* Two-pipe probe (diagnostic): blocks of 8 warps, 2 blocks per SM; warps whose bit is set in imad_mask run
+ * `iters_int` x 2 Montgomery products (int_kind 0) or the same number of raw IMAD.WIDE (int_kind 1), warps in dfma_mask run
+ * `iters_f64` x 64 DFMA, the rest exit.  Returns the best kernel time of three launches in ms.  Comparing (mask_i, 0),
+ * (0, mask_d) and (mask_i, mask_d) shows whether the fp64 pipe runs next to the wide-integer multiplier. */
+int b2_mixed_probe(uint32_t imad_mask, uint32_t dfma_mask, int int_kind, int iters_int, int iters_f64, double* ms_out);
+/* Batched-affine addition probe (diagnostic): n_pairs additions P[i] + Q[i] of synthetic affine points, B
+ * consecutive pairs per thread with one shared inversion (Montgomery's trick, prefix products parked in global memory),
+ * against the same points through the XYZZ mixed add the MSM uses (two mixed adds per pair into a running bucket).
+ * Times are kernel ms (best of three).  The first n_copy points P, Q and sums (64-byte affine) are copied to the host
+ * buffers when those are not NULL, so that a test can check the sums. */
+int b2_affine_batch_probe(size_t n_pairs, uint32_t B, double* batch_ms, double* xyzz_ms, void* host_p, void* host_q,
+                          void* host_out, size_t n_copy);
 /* Timing of the last b2_msm / b2_ntt_exec / b2_commit_batch on this device, CUDA events
  * on the launching stream: kernel-only ms and (host variants) total ms incl. copies. */
 int b2_last_timing(double* kernel_ms, double* total_ms);

@@ -403,3 +403,18 @@ def test_async_msm_matches_blocking_and_oracle(gpu):
     # the lane is free again after a failed wait
     assert _affine(h2.gpu_multiexp_async(cols[1], srs).result()) == want[1]
     srs.free()
+
+
+def test_affine_batch_probe_sums_match_oracle(gpu):
+    """the batched-affine addition probe (Montgomery's trick, one inversion per thread; DESIGN.md 4 'measured') computes
+    the group law: every sum P + Q it returns equals the oracle's"""
+    import ctypes
+    from halo2_gpu_specific_b200 import _lib
+    n, B, m = 4096, 64, 192
+    P, Q, S = (np.zeros((m, 8), dtype=np.uint64) for _ in range(3))
+    b_ms, x_ms = ctypes.c_double(), ctypes.c_double()
+    _lib.check(_lib.lib().b2_affine_batch_probe(n, B, ctypes.byref(b_ms), ctypes.byref(x_ms), P.ctypes.data,
+                                                Q.ctypes.data, S.ctypes.data, m))
+    p, q, s = o.g1_affine_decode(P), o.g1_affine_decode(Q), o.g1_affine_decode(S)
+    assert all(o.g1_is_on_curve(x) and x is not None for x in p + q)
+    assert [o.g1_add(a, b) for a, b in zip(p, q)] == s

@@ -335,15 +335,21 @@ def test_sharded_engine_on_one_rank(gpu):
         want = PR.create_proof(oparams, opk, fx["advice"], inst, HP.SeededRng(5))
         eng = ShardedResidentEngine(params, pk.vk.domain)
         got = HP.create_proof(params, pk, adv.copy(), inst, HP.SeededRng(5), engine=eng)
-        # a forced split (as rank 1 of 3 would see it) still transforms every z column on this rank
+        # a forced split (as rank 1 of 3 would see it): this rank commits and transforms exactly its own column range
+        # [lo, hi); the other columns would arrive in coefficient form from their owners (exchange_columns, a no-op
+        # without a process group), so here they must still hold their Lagrange values
         eng._share = lambda count: (count // 3, count - count // 3)
         eng._gather = lambda local, count: local
-        z = eng.put(np.ascontiguousarray(np.stack([enc(p) for p in fx["perm_z"]] + [enc(fx["shuffle_z"][0])])))
+        cols = fx["perm_z"] + [fx["shuffle_z"][0]]
+        lo, hi = eng._share(len(cols))
+        assert 0 < lo < hi < len(cols)
+        z = eng.put(np.ascontiguousarray(np.stack([enc(p) for p in cols])))
         pts = eng.commit_lagrange_and_ifft(z)
-        assert len(pts) == 1
+        assert len(pts) == hi - lo
+        assert pts == [oparams.commit_lagrange(c) for c in cols[lo:hi]]
         d = fx["domain"]
-        want_coeffs = [d.lagrange_to_coeff(p) for p in fx["perm_z"]] + [d.lagrange_to_coeff(fx["shuffle_z"][0])]
-        assert np.array_equal(eng.get(z), np.stack([enc(c) for c in want_coeffs]))
+        want_rows = [enc(d.lagrange_to_coeff(c)) if lo <= i < hi else enc(c) for i, c in enumerate(cols)]
+        assert np.array_equal(eng.get(z), np.stack(want_rows))
         eng.free()
         assert got == want
     finally:
