@@ -44,7 +44,7 @@ class NttDesc(ctypes.Structure):
 # every symbol include/b2pcs.h declares (checked by tests/test_abi.py without a GPU)
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_get_device", "b2_synchronize",
-    "b2_launch_count", "b2_srs_register", "b2_srs_synthetic", "b2_srs_from_scalars_dev", "b2_memcpy_d2d", "b2_vanishing_random_poly_dev", "b2_fr_max_bits_dev", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
+    "b2_launch_count", "b2_stream_create", "b2_stream_synchronize", "b2_stream_destroy", "b2_srs_register", "b2_srs_synthetic", "b2_srs_from_scalars_dev", "b2_memcpy_d2d", "b2_vanishing_random_poly_dev", "b2_fr_max_bits_dev", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
     "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
@@ -69,6 +69,9 @@ def lib() -> ctypes.CDLL:
         L.b2_launch_count.restype = ctypes.c_uint64
         L.b2_launch_count.argtypes = [ctypes.c_int]
         vp, sz, u32, u64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint32, ctypes.c_uint64
+        L.b2_stream_create.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+        L.b2_stream_synchronize.argtypes = [ctypes.c_void_p]
+        L.b2_stream_destroy.argtypes = [ctypes.c_void_p]
         L.b2_srs_register.argtypes = [vp, sz, sz, ctypes.POINTER(u64)]
         L.b2_srs_synthetic.argtypes = [sz, u64, u64, ctypes.POINTER(u64)]
         L.b2_srs_from_scalars_dev.argtypes = [vp, sz, ctypes.POINTER(u64)]

@@ -1008,6 +1008,24 @@ int b2_synchronize(void) {
     CK(cudaDeviceSynchronize());
     return B2_OK;
 }
+int b2_stream_create(void** stream) {
+    if (!stream) return fail(B2_ERR_ARG, "stream_create: null pointer");
+    DeviceCtx* dev;
+    int rc = dev_get(&dev);
+    if (rc) return rc;
+    cudaStream_t st;
+    CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    *stream = (void*)st;
+    return B2_OK;
+}
+int b2_stream_synchronize(void* stream) {
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    return B2_OK;
+}
+int b2_stream_destroy(void* stream) {
+    if (stream) CK(cudaStreamDestroy((cudaStream_t)stream));
+    return B2_OK;
+}
 uint64_t b2_launch_count(int reset) {
     DeviceCtx* dev;
     if (dev_get(&dev)) return 0;

@@ -171,14 +171,6 @@ struct NttTw {
     uint32_t m;             // log size of the whole sub-NTT (plane stride / Montgomery table stride)
 };
 
-// NTT_MUL_NOINLINE: the butterflies CALL one copy of the Shoup product instead of inlining 24 copies (the pass kernel is
-// 144 KB of SASS with everything inlined and shows instruction-fetch stalls; A/B measurement, tools/r2_call8.sh)
-#ifdef NTT_MUL_NOINLINE
-__device__ __noinline__ Fr fr_mul_shoup_lazy_call(const Fr a, const Fr w, const Fr wp) { return fr_mul_shoup_lazy(a, w, wp); }
-#else
-__device__ __forceinline__ Fr fr_mul_shoup_lazy_call(const Fr& a, const Fr& w, const Fr& wp) { return fr_mul_shoup_lazy(a, w, wp); }
-#endif
-
 // butterfly of stage s with twiddle w_{2^s}^jj; LAZY: inputs and outputs in [0, 4r)
 template <bool SHOUP, bool LAZY>
 __device__ __forceinline__ void ntt_bfly_tw(Fr& a, Fr& b, const NttTw& tw, uint32_t s, uint32_t jj) {
@@ -199,7 +191,7 @@ __device__ __forceinline__ void ntt_bfly_tw(Fr& a, Fr& b, const NttTw& tw, uint3
         w.v[4] = w1.x; w.v[5] = w1.y; w.v[6] = w1.z; w.v[7] = w1.w;
         wp.v[0] = p0.x; wp.v[1] = p0.y; wp.v[2] = p0.z; wp.v[3] = p0.w;
         wp.v[4] = p1.x; wp.v[5] = p1.y; wp.v[6] = p1.z; wp.v[7] = p1.w;
-        t = LAZY ? fr_mul_shoup_lazy_call(b, w, wp) : fr_mul_shoup(b, w, wp);
+        t = LAZY ? fr_mul_shoup_lazy(b, w, wp) : fr_mul_shoup(b, w, wp);
     } else {
         t = fp_mul<FrParams>(b, fp_load_nc<FrParams>(tw.g + ((size_t)jj << (tw.m - s))));
     }

@@ -577,9 +577,10 @@ def interleave_cosets_dev(domain, d_compact: int, d_ext: int) -> None:
         prog.free()
 
 
-def coeff_to_coset_dev(domain, d_coeffs: int, columns: int, gen: int, d_out: int) -> None:
+def coeff_to_coset_dev(domain, d_coeffs: int, columns: int, gen: int, d_out: int, stream: int = 0) -> None:
     """Evaluations of `columns` device-resident polynomials (2^k coefficients each) on the coset gen * <omega>:
-    one size-2^k transform per column with x[i] *= gen^i fused into its first pass (b2_ntt_desc.coset_gen)."""
+    one size-2^k transform per column with x[i] *= gen^i fused into its first pass (b2_ntt_desc.coset_gen).
+    stream: a CUDA stream (b2_stream_create) makes the call asynchronous on it."""
     g = _fr.to_mont(gen)
     d = NttDesc()
     d.log_n, d.location = domain.k, 1
@@ -588,6 +589,7 @@ def coeff_to_coset_dev(domain, d_coeffs: int, columns: int, gen: int, d_out: int
     d.n_in = d.in_stride = d.n_out = d.out_stride = domain.n
     d.columns = columns
     d.in_, d.out = d_coeffs, d_out
+    d.stream = stream or None
     check(lib().b2_ntt_exec(ctypes.byref(d)))
 
 

@@ -745,6 +745,8 @@ class ResidentEngine:
         self._kept: list = []          # proving-key data and constants, freed by free()
         self._keys: dict = {}          # id(pk) -> resident proving-key data (kept across proofs)
         self._consts: dict = {}
+        self._early: dict = {}         # advice block ptr -> (coefficient forms, [coset evaluations]) made during the upload
+        self._side = 0                 # side stream of the early transforms (created on first use)
 
     # -- memory
     def _buffer(self, elems: int, keep: bool = False):
@@ -821,6 +823,8 @@ class ResidentEngine:
 
     def release(self) -> None:
         """free what the last proof allocated; the proving key stays resident"""
+        self._drain_side()
+        self._early = {}
         for b in self._live:
             b.free()
         self._live = []
@@ -833,6 +837,10 @@ class ResidentEngine:
         self._kept = []
         self._keys, self._consts = {}, {}
         self._pool.trim()
+        if self._side:
+            from ._lib import lib
+            lib().b2_stream_destroy(self._side)
+            self._side = 0
 
     # -- commitments
     def _commit(self, srs, host_ptr, block: DevBlock, max_bits: int, ifft: bool) -> List[Point]:
@@ -851,13 +859,66 @@ class ResidentEngine:
         """host columns -> resident block, committed on the way in (copy of column i + 1 overlaps the MSM of column i)"""
         if not (host.flags.c_contiguous and host.dtype == np.uint64 and host.ndim == 3):
             raise B2Error(B2_ERR_ARG, "expected a C-contiguous uint64 (columns, n, 4) array")
-        if max_bits is not None:
-            block = self.alloc(host.shape[0])
-            return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, max_bits, False)
         # no bound given: find_max_scalar_bits per column on the device (plonk/prover.rs:945-962, 296), inside the
         # same pipelined call (B2_MAX_BITS_AUTO): scan of column c after its copy, its MSM under the copy of c + 1
-        block = self.alloc(host.shape[0])
-        return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, 0xFFFFFFFF, False)
+        bits = 0xFFFFFFFF if max_bits is None else max_bits
+        count, n = host.shape[0], host.shape[1]
+        block = self.alloc(count)
+        nc = 1 << (self.domain.extended_k - self.domain.k)
+        if not self.EARLY_TRANSFORMS or count < 8 or (nc + 1) * count * n * 32 > self.EARLY_TRANSFORM_BYTES:
+            return block, self._commit(self.params.g_lagrange, host.ctypes.data, block, bits, False)
+        # The upload is bound by PCIe and leaves the multiplier pipe idle about half of the time, while evaluate_h will
+        # later need every advice polynomial on every coset of the extended domain -- transforms that depend on the
+        # witness only, not on any challenge.  So the columns go up in groups, and while group g + 1 crosses PCIe the
+        # side stream turns group g into coefficient form and into its coset evaluations (lagrange_to_coeff and
+        # evaluate_h_blocks pick them up from self._early).
+        coeff = self.alloc(count)
+        cosets = [self.alloc(count) for _ in range(nc)]
+        step = max(2, count // 8)
+        points: List[Point] = []
+        for lo in range(0, count, step):
+            hi = min(count, lo + step)
+            points += self._commit(self.params.g_lagrange, host.ctypes.data + lo * n * 32, self.sub_block(block, lo, hi),
+                                   bits, False)
+            self._early_transforms(block, coeff, cosets, lo, hi)
+        self._early[block.ptr] = (coeff, cosets)
+        return block, points
+
+    EARLY_TRANSFORMS = True                  # class switch (the sharded engines divide the columns differently)
+    EARLY_TRANSFORM_BYTES = 64 << 30         # HBM the early coefficient forms + coset evaluations may take
+
+    def _side_stream(self) -> int:
+        if not self._side:
+            import ctypes
+            from ._lib import check, lib
+            st = ctypes.c_void_p()
+            check(lib().b2_stream_create(ctypes.byref(st)))
+            self._side = st.value
+        return self._side
+
+    def _drain_side(self) -> None:
+        if self._side:
+            from ._lib import check, lib
+            check(lib().b2_stream_synchronize(self._side))
+
+    def _early_transforms(self, block: DevBlock, coeff: DevBlock, cosets, lo: int, hi: int) -> None:
+        """columns [lo, hi) of a Lagrange block -> coefficient forms and coset evaluations, asynchronously"""
+        import ctypes
+        from ._lib import NttDesc, check, lib
+        from .evaluation import coeff_to_coset_dev
+        dm, st = self.domain, self._side_stream()
+        off = lo * dm.n * 32
+        d = NttDesc()
+        d.log_n, d.location = dm.k, 1
+        d.omega, d.divisor = dm.omega_inv.ctypes.data, dm.ifft_divisor.ctypes.data
+        d.n_in = d.n_out = d.in_stride = d.out_stride = dm.n
+        d.columns = hi - lo
+        d.in_, d.out = block.ptr + off, coeff.ptr + off
+        d.stream = st
+        check(lib().b2_ntt_exec(ctypes.byref(d)))
+        for c, cos in enumerate(cosets):
+            g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
+            coeff_to_coset_dev(dm, coeff.ptr + off, hi - lo, g_c, cos.ptr + off, stream=st)
 
     def commit_lagrange(self, block: DevBlock, max_bits: int = _fr.NUM_BITS) -> List[Point]:
         return self._commit(self.params.g_lagrange, 0, block, max_bits, False)
@@ -872,6 +933,13 @@ class ResidentEngine:
     def lagrange_to_coeff(self, block: DevBlock) -> DevBlock:
         import ctypes
         from ._lib import NttDesc, check, lib
+        early = self._early.get(block.ptr)
+        if early is not None and early[0].count == block.count:
+            # the coefficient forms were made while the columns were uploaded (put_and_commit_lagrange)
+            self._drain_side()
+            check(lib().b2_memcpy_d2d(ctypes.c_void_p(block.ptr), ctypes.c_void_p(early[0].ptr),
+                                      block.count * block.n * 32))
+            return block
         if block.count:
             dm = self.domain
             d = NttDesc()
@@ -1015,7 +1083,10 @@ class ResidentEngine:
         for _ in range(S):
             challenges.append(d)
             d = d * DELTA % R
-        witness = [b for b in (advice, instance, z_block, m_block) if b.count]
+        early = self._early.get(advice.ptr)        # the advice polynomials' coset evaluations may exist already
+        if early is not None:
+            self._drain_side()
+        witness = [b for b in (advice, instance, z_block, m_block) if b.count and not (b is advice and early)]
         cos = {id(b): self.alloc(b.count) for b in witness}
         hext = self._buffer(dm.extended_len())
         if partial:
@@ -1031,6 +1102,7 @@ class ResidentEngine:
             kc = key_cosets[c]
             kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
             zp, mp = ptrs(z_block), ptrs(m_block)
+            ap = [early[1][c].ptr + i * n * 32 for i in range(advice.count)] if early else ptrs(advice)
             aux = kp[F + S:F + S + 3] + kp[F:F + S] + zp[:n_perm]
             pos = n_perm
             for li, cnt in enumerate(lookup_z_counts):
@@ -1038,7 +1110,7 @@ class ResidentEngine:
                 pos += cnt
             aux += zp[pos:pos + n_shuffles]
             full = row_begin == 0 and row_count == n
-            prog.eval(dm.k, 1, kp[:F], ptrs(advice), ptrs(instance), aux, challenges, hext.ptr,
+            prog.eval(dm.k, 1, kp[:F], ap, ptrs(instance), aux, challenges, hext.ptr,
                       x0=pow(dm._ext_omega, c, R), x_step=dm._omega, scale=dm.t_evaluations[c:c + 1],
                       out_stride=nc, out_offset=c if full else c + row_begin * nc,   # row i lands at i * nc + c
                       row_begin=0 if full else row_begin, row_count=0 if full else row_count)

@@ -32,6 +32,8 @@ class ShardedCommits:
     default process group by contiguous column ranges; every method returns the points of ALL columns, in column order,
     on every rank."""
 
+    EARLY_TRANSFORMS = False    # the ranks divide the advice columns and their transforms among themselves instead
+
     def _share(self, count: int):
         rank, world = parallel.world()
         return parallel.column_range(count, world, rank)

@@ -55,6 +55,13 @@ int b2_device_count(void);
 int b2_set_device(int device);
 int b2_get_device(void);
 int b2_synchronize(void);
+/* A stream of the current device for the `stream` arguments of the _dev entry points, for callers that do not bring
+ * their own CUDA runtime (the Python mirror; a Rust host would pass its own cudaStream_t).  Work a _dev call enqueues
+ * on it runs asynchronously to the library's own lanes: the prover uses one to transform the advice columns already
+ * uploaded while the next ones still cross PCIe. */
+int b2_stream_create(void** stream);
+int b2_stream_synchronize(void* stream);
+int b2_stream_destroy(void* stream);
 /* number of kernels this library launched on the current device since the last reset */
 uint64_t b2_launch_count(int reset);
 

@@ -413,3 +413,32 @@ def test_multi_circuit_proof_bytes_match_oracle(gpu, engine_kind, use_gwc):
         assert not PR.verify_proof_multi(oparams, opk.vk, insts[::-1], got, use_gwc=use_gwc)
     finally:
         params.free()
+
+
+def test_early_advice_transforms_do_not_change_the_proof(gpu):
+    """ResidentEngine turns the advice columns into coefficient form and coset evaluations on a side stream while the
+    later columns are still being uploaded (EARLY_TRANSFORMS); the proof bytes are those of the plain schedule, twice
+    in a row on the same engine (buffers recycled through the pool)"""
+    from oracle import cref
+    k = 9
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, 4, lambda a: cref.to_mont(0, a))
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        plain = HP.ResidentEngine(params, pk.vk.domain)
+        plain.EARLY_TRANSFORMS = False
+        want = HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(3), engine=plain)
+        assert not plain._early
+        plain.free()
+        eng = HP.ResidentEngine(params, pk.vk.domain)
+        seen = []
+        orig = eng._early_transforms
+        eng._early_transforms = lambda *a: (seen.append(a[3:]), orig(*a))[1]
+        for _ in range(2):
+            assert HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(3), engine=eng) == want
+        assert len(seen) == 2 * 8 and seen[0] == (0, 8)          # 64 advice columns in 8 groups, per proof
+        assert HP.create_proof_with_shplonk(params, pk, advice.copy(), [public], HP.SeededRng(4), engine=eng) == \
+            HP.create_proof_with_shplonk(params, pk, advice.copy(), [public], HP.SeededRng(4), engine=HP.Engine(params, pk.vk.domain))
+        eng.free()
+    finally:
+        params.free()

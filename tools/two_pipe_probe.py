@@ -28,6 +28,11 @@ def main():
     _lib.set_device(0)
     L = _lib.lib()
     out = {"mixed": [], "affine_batch": []}
+    if "--affine-only" in sys.argv:          # one configuration, for an ncu capture of the two kernels
+        b, x = ctypes.c_double(), ctypes.c_double()
+        _lib.check(L.b2_affine_batch_probe(1 << 24, 256, ctypes.byref(b), ctypes.byref(x), None, None, None, 0))
+        print(json.dumps({"batch_ms": b.value, "xyzz_ms": x.value}))
+        return
     for kind, kname in ((0, "montgomery_products"), (1, "raw_imad_wide")):
         for imask, dmask, label in ((0x0f, 0xf0, "4 int + 4 fp64 warps per block"),
                                     (0x3f, 0xc0, "6 int + 2 fp64"),
