@@ -160,6 +160,7 @@ struct Lane {
     cudaEvent_t ev[16];
     cudaEvent_t busy;            // last work enqueued on a caller-provided stream (async _dev calls)
     bool busy_valid = false;
+    cudaStream_t busy_stream = nullptr;   // the caller stream that recorded `busy`
     double last_kernel_ms = 0, last_total_ms = 0;
     double phases[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -236,7 +237,9 @@ int dev_get(DeviceCtx** out) {
             l.sms = prop.multiProcessorCount;
             l.acc_blocks_per_sm = nb > 0 ? nb : 1;
             l.launch_counter = &c.launches;
-            CK(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+            // one step above the default (= lowest) priority: the small kernels of a pipelined batch (bound scans,
+            // digit sorts) must not queue behind a caller's background work on a b2_stream_create stream
+            CK(cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, -1));
             for (auto& e : l.ev) CK(cudaEventCreate(&e));
             CK(cudaEventCreateWithFlags(&l.busy, cudaEventDisableTiming));
             c.lane_free[i] = true;
@@ -248,22 +251,46 @@ int dev_get(DeviceCtx** out) {
     return B2_OK;
 }
 
-// RAII: take a free lane of the current device (blocks while all are busy)
+// RAII: take a free lane of the current device (blocks while all are taken).
+// A lane may still carry asynchronous work that a _dev call enqueued on a caller's stream (its `busy` event): whoever
+// takes it next orders after that work, so a synchronous pipeline that was handed such a lane would stall behind the
+// caller's background stream.  Selection therefore goes: (1) for an asynchronous caller, the lane that already carries
+// work of the same stream (ordering is free there); (2) a lane without pending asynchronous work -- asynchronous
+// callers search from the top, synchronous ones from the bottom, so they stay out of each other's way; (3) any free lane.
 struct LaneLock {
     Lane* lane = nullptr;
-    int acquire() {
+    static bool pending(Lane& l) {
+        if (!l.busy_valid) return false;
+        if (cudaEventQuery(l.busy) == cudaErrorNotReady) return true;
+        cudaGetLastError();
+        l.busy_valid = false;
+        return false;
+    }
+    static int pick(DeviceCtx* c, cudaStream_t for_stream, bool idle_only) {
+        if (for_stream)
+            for (int i = 0; i < c->nlanes; i++)
+                if (c->lane_free[i] && c->lanes[i].busy_valid && c->lanes[i].busy_stream == for_stream) return i;
+        for (int j = 0; j < c->nlanes; j++) {
+            const int i = for_stream ? c->nlanes - 1 - j : j;
+            if (c->lane_free[i] && !pending(c->lanes[i])) return i;
+        }
+        if (idle_only) return -1;
+        for (int i = 0; i < c->nlanes; i++)
+            if (c->lane_free[i]) return i;
+        return -1;
+    }
+    int acquire(cudaStream_t for_stream = nullptr) {
         DeviceCtx* c;
         int rc = dev_get(&c);
         if (rc) return rc;
         std::unique_lock<std::mutex> lk(c->mu);
         for (;;) {
-            for (int i = 0; i < c->nlanes; i++)
-                if (c->lane_free[i]) {
-                    c->lane_free[i] = false;
-                    lane = &c->lanes[i];
-                    break;
-                }
-            if (lane) break;
+            const int i = pick(c, for_stream, false);
+            if (i >= 0) {
+                c->lane_free[i] = false;
+                lane = &c->lanes[i];
+                break;
+            }
             c->cv.wait(lk);
         }
         lk.unlock();
@@ -274,15 +301,14 @@ struct LaneLock {
         g_last.lane = lane;
         return B2_OK;
     }
-    // non-blocking: returns false when every lane is taken
+    // non-blocking, for the extra lanes of a pipeline: only a lane without pending asynchronous work
     bool try_acquire(DeviceCtx* c) {
         std::unique_lock<std::mutex> lk(c->mu);
-        for (int i = 0; i < c->nlanes; i++)
-            if (c->lane_free[i]) {
-                c->lane_free[i] = false;
-                lane = &c->lanes[i];
-                break;
-            }
+        const int i = pick(c, nullptr, true);
+        if (i >= 0) {
+            c->lane_free[i] = false;
+            lane = &c->lanes[i];
+        }
         lk.unlock();
         if (!lane) return false;
         if (lane->busy_valid) cudaStreamWaitEvent(lane->stream, lane->busy, 0);
@@ -297,6 +323,7 @@ struct LaneLock {
         if (user == lane->stream) return B2_OK;
         CK(cudaEventRecord(lane->busy, user));
         lane->busy_valid = true;
+        lane->busy_stream = user;
         return B2_OK;
     }
     ~LaneLock() {
@@ -424,8 +451,8 @@ struct LaneSet {
     LaneLock primary;
     LaneLock extra[MAX_LANES];
     std::vector<Lane*> lanes;
-    int acquire(int want) {
-        int rc = primary.acquire();
+    int acquire(int want, cudaStream_t for_stream = nullptr) {
+        int rc = primary.acquire(for_stream);
         if (rc) return rc;
         lanes.push_back(primary.lane);
         for (int i = 0; i + 1 < want && i < MAX_LANES; i++)
@@ -1396,7 +1423,7 @@ int b2_ntt_exec(const b2_ntt_desc* d) {
     if (d->location > 3) return fail(B2_ERR_ARG, "ntt: location must be 0..3");
     const bool wants_pipeline = d->location != 1 && d->columns > 1;
     LaneSet set;
-    int rc = set.acquire(wants_pipeline ? MAX_LANES : 1);
+    int rc = set.acquire(wants_pipeline ? MAX_LANES : 1, d->location == 1 ? (cudaStream_t)d->stream : nullptr);
     if (rc) return rc;
     Lane* ctx = set.primary.lane;
     NttPlan* pl;
