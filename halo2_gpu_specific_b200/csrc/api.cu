@@ -1230,7 +1230,7 @@ int b2_msm_dev(b2_handle_t srs, size_t offset, const void* d_scalars, size_t n, 
     if (rc) return rc;
     if (offset + n > s.n) return fail(B2_ERR_ARG, "msm: %zu scalars at offset %zu exceed SRS length %zu", n, offset, s.n);
     LaneLock ll;
-    if ((rc = ll.acquire())) return rc;
+    if ((rc = ll.acquire((cudaStream_t)stream))) return rc;
     Lane* ctx = ll.lane;
     if (s.device != ctx->dev->dev)
         return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);

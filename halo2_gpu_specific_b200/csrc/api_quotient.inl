@@ -372,7 +372,7 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
     if (row_begin >= rows || row_count > rows - row_begin) return fail(B2_ERR_ARG, "quotient_eval: row range outside the domain");
 
     LaneLock ll;
-    if ((rc = ll.acquire())) return rc;
+    if ((rc = ll.acquire((cudaStream_t)args->stream))) return rc;
     Lane* ctx = ll.lane;
     cudaStream_t st = args->stream ? (cudaStream_t)args->stream : ctx->stream;
     if ((rc = ll.order_after_busy(st))) return rc;

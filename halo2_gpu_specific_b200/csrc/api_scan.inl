@@ -55,7 +55,7 @@ extern "C" {
 int b2_batch_invert_dev(void* d_a, size_t n, void* stream) {
     if (!d_a && n) return fail(B2_ERR_ARG, "batch_invert: null pointer");
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : ll.lane->stream;
     if ((rc = ll.order_after_busy(st))) return rc;
@@ -84,7 +84,7 @@ int b2_prefix_scan_dev(int op, const void* d_in, size_t n_in, const void* init, 
                        size_t n_out, void* stream) {
     if (op < 0 || op > 1 || !d_out || (n_in && !d_in)) return fail(B2_ERR_ARG, "prefix_scan: bad arguments");
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     cudaStream_t st = stream ? (cudaStream_t)stream : ll.lane->stream;
     if ((rc = ll.order_after_busy(st))) return rc;
@@ -128,7 +128,7 @@ int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_ou
     if (op < 0 || op > 2 || (n && (!d_a || !d_b || !d_out))) return fail(B2_ERR_ARG, "fr_vec_dev: bad arguments");
     if (n == 0) return B2_OK;
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     Lane* ctx = ll.lane;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -230,7 +230,7 @@ int b2_eval_polynomial(const void* poly, uint64_t n, const void* point, void* ou
 int b2_kate_division_dev(const void* d_a, uint64_t n, const void* b, void* d_q, void* stream) {
     if (!d_a || !b || !d_q || n < 2) return fail(B2_ERR_ARG, "kate_division: bad arguments");
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     Lane* ctx = ll.lane;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -291,7 +291,7 @@ int b2_poly_combine_dev(const void* const* d_polys, uint32_t m, uint64_t n, cons
     for (uint32_t j = 0; j < m; j++)
         if (!d_polys[j]) return fail(B2_ERR_ARG, "poly_combine: null polynomial %u", j);
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     Lane* ctx = ll.lane;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -346,7 +346,7 @@ int b2_kate_division(const void* a, uint64_t n, const void* b, void* q) {
 int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, size_t n, void* d_out, void* stream) {
     if (!random || !d_out || k == 0 || k > 64 || n == 0) return fail(B2_ERR_ARG, "vanishing_random_poly: bad arguments");
     LaneLock ll;
-    int rc = ll.acquire();
+    int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
     Lane* ctx = ll.lane;
     cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;

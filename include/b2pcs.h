@@ -82,7 +82,12 @@ int b2_srs_from_scalars_dev(const void* d_scalars, size_t n, b2_handle_t* out);
  * window w (affine, in HBM: 254/window_bits + 1 copies of the SRS).  MSMs against this SRS then
  * drop every scalar digit into ONE shared bucket set: no per-window bucket reduction and no
  * doublings at the end, and the window can be wider (fewer point additions).  window_bits = 0
- * picks it from the SRS length (20 for 2^21..2^24 points).  Optional; results are identical. */
+ * picks it from the SRS length (16 at 2^16, 17 at 2^18, 20 for 2^20..2^24, 22 from 2^25).  Optional; results are identical.
+ * Memory: (254/window_bits + 1) * n * 64 bytes on top of the SRS -- 3.25 GiB per basis at n = 2^22 (13 windows),
+ * 48 GiB at n = 2^26 (12 windows).  When that allocation fails the call returns B2_ERR_OOM and changes nothing: the SRS
+ * stays registered and MSMs against it run from the plain bases (one bucket set per window of at most 16 bits + Horner:
+ * more point additions per scalar and a bucket reduction per window), so a caller may treat the error as "no table" and go on.  B2_ERR_ARG when
+ * windows * n would not fit the 31-bit point index of the sort entries (n > 2^27 / windows). */
 int b2_srs_precompute(b2_handle_t srs, uint32_t window_bits);
 int b2_srs_len(b2_handle_t srs, size_t* n);
 int b2_srs_read(b2_handle_t srs, size_t offset, size_t count, void* out_affine64);
