@@ -487,8 +487,14 @@ __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v2_kernel(
 __global__ void __launch_bounds__(512) ntt_pass_v3_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v3_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v3_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, false, NTT_TWSM>(a); }
-__global__ void __launch_bounds__(128, 5) ntt_pass_cluster2_v4_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
-__global__ void __launch_bounds__(128, 6) ntt_pass_cluster2_v5_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
+#ifndef NTT_V4_MINB
+#define NTT_V4_MINB 5
+#endif
+#ifndef NTT_V5_MINB
+#define NTT_V5_MINB 6
+#endif
+__global__ void __launch_bounds__(128, NTT_V4_MINB) ntt_pass_cluster2_v4_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
+__global__ void __launch_bounds__(128, NTT_V5_MINB) ntt_pass_cluster2_v5_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
 // Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
 __global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
 __global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }
