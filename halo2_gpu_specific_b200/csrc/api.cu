@@ -525,9 +525,13 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
     // digits stay below 2^max_bits, so the reduction only has to visit that prefix of the bucket set
     uint32_t b_used = g.B;
     if (g.W == 1 && max_bits < g.c - 1) b_used = 1u << max_bits;
-    // buckets per reduce thread: enough blocks to fill the chip, fewer adds per bucket when there are many
+    // buckets per reduce thread: enough blocks to fill the chip, fewer adds per bucket when there are many.  Swept on
+    // B200 (profiles/r2_msm_rm.jsonl): at 2^19 buckets rm = 2 / 4 / 8 / 16 give a 1.76 / 1.14 / 0.91 / 0.55 ms reduce --
+    // every block pays ~45 dependent point operations for its scan, tree and offset multiple, so fewer, longer blocks
+    // that still fit one wave win; at 2^16 buckets rm = 2 (0.27 ms) beats 16 (0.43 ms).
     uint32_t rm = b_used >> 15;
     rm = rm < 2 ? 2 : (rm > 16 ? 16 : rm);
+
     const uint32_t bpw = (b_used + MSM_RT * rm - 1) / (MSM_RT * rm);
     const uint32_t ntiles = (uint32_t)((nb + SCAN_TILE - 1) / SCAN_TILE);
 
@@ -1616,6 +1620,21 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     Lane* ctx = set.primary.lane;
     if (s.device != ctx->dev->dev)
         return fail(B2_ERR_ARG, "SRS lives on device %d, current device is %d", s.device, ctx->dev->dev);
+    // An error in the middle of the batch (an allocation that fails, a CUDA error) must not return while other lanes
+    // still copy from / into the caller's host buffers: whatever leaves this function early drains the lanes first
+    // and clears their sticky bound flags, so the caller may free its buffers and the next call starts clean.
+    struct Drain {
+        LaneSet& set;
+        bool armed = true;
+        ~Drain() {
+            if (!armed) return;
+            for (Lane* l : set.lanes) {
+                cudaStreamSynchronize(l->stream);
+                if (l->errflag.p) cudaMemset(l->errflag.p, 0, 8);
+            }
+            cudaGetLastError();
+        }
+    } drain{set};
     NttPlan* pl = nullptr;
     if (do_ifft && (rc = ntt_get_plan(*ctx, omega_inv, divisor, log_n, &pl))) return rc;
     const size_t col_bytes = n * 32;
@@ -1692,6 +1711,7 @@ static int commit_batch_impl(b2_handle_t srs, void* columns_data, uint64_t colum
     ctx->last_kernel_ms = 0;
     g_last.total_ms = ms;
     g_last.kernel_ms = 0;
+    drain.armed = false;      // everything has been synchronised above
     memcpy(out_jac96, h_pts, (size_t)columns * 96);
     for (uint64_t c = 0; c < columns; c++) jac_normalise_host((char*)out_jac96 + c * 96);
     if (bound_flag_any) return fail(B2_ERR_BOUND, "a scalar exceeds the max_bits bound");

@@ -346,9 +346,11 @@ class OsRng:
         return np.frombuffer(os.urandom(2 * n), dtype=np.uint16).astype(np.uint64)
 
     def fr_vec(self, n: int) -> np.ndarray:
-        a = np.frombuffer(os.urandom(32 * n), dtype=np.uint64).reshape(n, 4).copy()
-        a[:, 3] &= np.uint64((1 << 61) - 1)
-        return a
+        """uniform over Fr like Fr::random: 512 bits of OS entropy per element reduced mod r (bias < 2^-250)"""
+        raw = os.urandom(64 * n)
+        if n == 0:
+            return np.zeros((0, 4), dtype=np.uint64)
+        return np.stack([_fr.to_mont(int.from_bytes(raw[64 * i:64 * i + 64], "little") % R) for i in range(n)])
 
 
 class Blake2bRng:
@@ -1216,7 +1218,17 @@ class VerifyingKey:
             h.update(len(s).to_bytes(8, "little"))
             h.update(s)
             transcript_repr = int.from_bytes(h.digest(), "little")
+            global _WARNED_DEFAULT_REPR
+            if not _WARNED_DEFAULT_REPR:
+                import warnings
+                _WARNED_DEFAULT_REPR = True
+                warnings.warn("keygen without transcript_repr: the key is hashed from this package's own description of "
+                              "it, so the proofs verify under the in-repository verifier only; pass the scalar the Rust "
+                              "side derives from the pinned key (plonk.rs:91-109) for interoperable proofs", stacklevel=3)
         self.transcript_repr = transcript_repr % R
+
+
+_WARNED_DEFAULT_REPR = False
 
 
 class ProvingKey:
