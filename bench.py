@@ -470,6 +470,10 @@ def run_engine(args):
     if world == 1 and not args.no_proof22:
         proof22 = bench_create_proof_zkwasm(args, _lib, h2)
 
+    sharded_proof = None
+    if world > 1 and not args.no_proof:
+        sharded_proof = bench_sharded_proof(args, torch, dist, _lib, h2, rank, world)
+
     if rank == 0:
         hbm_peak, peak_src = _peaks()
         total_pts = n_total * args.steps
@@ -547,6 +551,8 @@ def run_engine(args):
             line["create_proof"] = proof
         if proof22:
             line["create_proof_k22"] = proof22
+        if sharded_proof is not None:
+            line["sharded_create_proof"] = sharded_proof
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(args, srs, h_scalars, res_dev)
         print(json.dumps(line), flush=True)
@@ -960,6 +966,91 @@ def bench_create_proof_zkwasm(args, _lib, h2):
         return {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
 
 
+def bench_sharded_proof(args, torch, dist, _lib, h2, rank, world):
+    """N > 1: the REAL prover divided over the ranks (prover_sharded: advice upload, lookups, z columns, advice transforms
+    and evaluate_h rows shared out; NCCL exchanges) on the zkWasm-shaped circuit at k = --sharded-proof-k, next to the
+    same proof on one GPU (rank 0, plain ResidentEngine).  The driver-visible parity of the multi-GPU prover: every
+    rank's proof bytes are compared with each other and with the single-GPU proof.  Never fatal for the main line; every
+    rank must call it (collectives inside)."""
+    k = args.sharded_proof_k
+    failed = None
+    out = None
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import zkwasm_shape_circuit as zk
+        from halo2_gpu_specific_b200 import plonk as HP
+        from halo2_gpu_specific_b200 import prover_sharded as PS
+        params = h2.Params.unsafe_setup(k, 0x2B200B200B200B200B200B200B200B2001)
+        adv = None
+        try:
+            cs = HP.ConstraintSystem(**zk.constraint_system_args(extra_gates=64))
+            dom = h2.EvaluationDomain(cs.degree(), k)
+            fixed, advice, public, mapping = zk.build(k, HP.Engine(params, dom).to_mont, seed=k)
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                pk = HP.keygen(params, cs, fixed, mapping)
+            adv = _lib.pinned_empty(advice.shape)
+            adv[:] = advice
+            del advice, fixed
+            setup_ok = True
+        except Exception as e:                            # noqa: BLE001
+            setup_ok, failed = False, {"error": f"setup on rank {rank}: {type(e).__name__}: {e}"}
+        # a rank whose setup failed must not leave the others waiting in a collective: agree first
+        flag = torch.tensor([1 if setup_ok else 0], dtype=torch.int64, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if adv is not None:
+                _lib.pinned_free(adv)
+            params.free()
+            return failed or {"error": "setup failed on another rank"}
+        try:
+            eng = PS.ShardedResidentEngineQ(params, pk.vk.domain)
+            PS.create_proof(params, pk, adv, [public], None, engine=eng)     # warm-up: synchronized rng + digest check
+            best, phases, proof = None, None, None
+            for _ in range(2):
+                dist.barrier()
+                tm = {}
+                t0 = time.perf_counter()
+                proof = HP.create_proof(params, pk, adv, [public], HP.SeededRng(1), engine=eng, timings=tm)
+                d = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+                dist.all_reduce(d, op=dist.ReduceOp.MAX)
+                if best is None or float(d.item()) < best:
+                    best, phases = float(d.item()), tm
+            eng.free()
+            alone_s, same, alone_err = None, True, None
+            if rank == 0:
+                try:
+                    plain = HP.ResidentEngine(params, pk.vk.domain)
+                    HP.create_proof(params, pk, adv, [public], HP.SeededRng(0), engine=plain)
+                    for _ in range(2):
+                        t0 = time.perf_counter()
+                        alone = HP.create_proof(params, pk, adv, [public], HP.SeededRng(1), engine=plain)
+                        d = time.perf_counter() - t0
+                        alone_s = d if alone_s is None else min(alone_s, d)
+                    plain.free()
+                    same = alone == proof
+                except Exception as e:                    # noqa: BLE001  (the other ranks wait in the gather below)
+                    same, alone_err = False, f"{type(e).__name__}: {e}"
+            gathered = [None] * world
+            dist.all_gather_object(gathered, proof)
+            same = bool(same and all(g == proof for g in gathered))
+            out = {"metric": f"create_proof wall time, zkWasm-shaped circuit at k={k} (GWC), divided over {world} GPUs",
+                   "value": best, "unit": "s", "higher_is_better": False, "n_ranks": world, "single_gpu_s": alone_s,
+                   "bytes_equal_on_all_ranks_and_to_single_gpu": same, "phases_s": phases, "proof_bytes": len(proof),
+                   "api": "halo2_gpu_specific_b200.prover_sharded (ShardedResidentEngineQ), one process per GPU, NCCL"}
+            if alone_err:
+                out["single_gpu_error"] = alone_err
+        finally:
+            if adv is not None:
+                _lib.pinned_free(adv)
+            params.free()
+    except Exception as e:                                # noqa: BLE001
+        import traceback
+        failed = {"error": f"{type(e).__name__}: {e}", "trace": traceback.format_exc()[-600:]}
+    return out if failed is None else failed
+
+
 def cpu_baseline(args, srs=None, scalars=None, engine_point=None):
     """The same workload on the host cores (C restatement of the rayon path, oracle/cpu_ref.c): the full MSM of the
     timed step (the engine's own synthetic bases read back from HBM, the same scalars), a few repetitions -- the
@@ -1020,6 +1111,8 @@ def main():
     ap.add_argument("--no-proof22", action="store_true", help="skip the zkWasm-shaped k=22 real proof (about 40 s of setup)")
     ap.add_argument("--proof22-k", type=int, default=22)
     ap.add_argument("--proof22-reps", type=int, default=2)
+    ap.add_argument("--sharded-proof-k", type=int, default=18,
+                    help="N > 1: size of the zkWasm-shaped circuit proved by all ranks together (sharded_create_proof)")
     ap.add_argument("--shplonk", action="store_true", help="create_proof_with_shplonk in the proof sections")
     ap.add_argument("--no-precompute", action="store_true", help="plain bases: one bucket set per window + Horner")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],

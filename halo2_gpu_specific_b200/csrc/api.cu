@@ -298,7 +298,6 @@ struct LaneLock {
             cudaError_t e = cudaStreamWaitEvent(lane->stream, lane->busy, 0);
             if (e != cudaSuccess) return fail(B2_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
         }
-        g_last.lane = lane;
         return B2_OK;
     }
     // non-blocking, for the extra lanes of a pipeline: only a lane without pending asynchronous work
@@ -554,7 +553,10 @@ int msm_run(Lane& ctx, const MsmBases& mb, const void* d_scalars, size_t n, uint
     if ((rc = ctx.errflag.reserve(16))) return rc;
 
     cudaEvent_t* ev = ctx.ev;
-    if (record_phases) CK(cudaEventRecord(ev[0], st));
+    if (record_phases) {
+        g_last.lane = &ctx;      // b2_last_msm_phases reads the events of the lane that ran the last recorded MSM
+        CK(cudaEventRecord(ev[0], st));
+    }
     if (reset_flag) CK(cudaMemsetAsync(ctx.errflag.p, 0, 4, st));
     // sort the (bucket, point) entries by bucket
     // (a two-level partitioned counting sort was measured in round 1: 2.3 ms against 1.1 ms at 2^22 for this

@@ -418,3 +418,42 @@ def test_affine_batch_probe_sums_match_oracle(gpu):
     p, q, s = o.g1_affine_decode(P), o.g1_affine_decode(Q), o.g1_affine_decode(S)
     assert all(o.g1_is_on_curve(x) and x is not None for x in p + q)
     assert [o.g1_add(a, b) for a, b in zip(p, q)] == s
+
+
+def test_caller_stream_msm_sum_and_phase_events(gpu):
+    """what bench.py's multi-GPU step does on one rank: b2_msm_dev on a caller's stream, b2_g1_sum_dev on the same stream
+    (it takes another lane: caller-stream calls keep to the lane that carries their stream's work), then the phase
+    events of THE MSM's lane are read -- and a second caller-stream MSM lands on the same lane as the first"""
+    import ctypes
+    from halo2_gpu_specific_b200 import _lib
+    L = _lib.lib()
+    n = 1 << 12
+    scalars = cref.random_fr_mont(n, 0xC0FFEE)
+    bases = _bases(n, 77)
+    srs = Srs.register(bases)
+    try:
+        want = _want(scalars, bases)
+        d_s, d_p, d_o, st = (ctypes.c_void_p() for _ in range(4))
+        _lib.check(L.b2_dev_alloc(n * 32, ctypes.byref(d_s)))
+        _lib.check(L.b2_dev_alloc(2 * 96, ctypes.byref(d_p)))
+        _lib.check(L.b2_dev_alloc(96, ctypes.byref(d_o)))
+        _lib.check(L.b2_memcpy_h2d(d_s, ctypes.c_void_p(scalars.ctypes.data), n * 32))
+        _lib.check(L.b2_stream_create(ctypes.byref(st)))
+        half = n // 2
+        for rep in range(2):
+            _lib.check(L.b2_msm_dev(srs.handle, 0, d_s, half, 254, d_p, st))
+            _lib.check(L.b2_msm_dev(srs.handle, half, ctypes.c_void_p(d_s.value + half * 32), n - half, 254,
+                                    ctypes.c_void_p(d_p.value + 96), st))
+            _lib.check(L.b2_g1_sum_dev(d_p, 2, d_o, st))
+            _lib.check(L.b2_stream_synchronize(st))
+            ph = _lib.last_msm_phases()
+            assert ph["total"] > 0 and ph["accumulate"] > 0
+        out = np.zeros(12, dtype=np.uint64)
+        _lib.check(L.b2_memcpy_d2h(ctypes.c_void_p(out.ctypes.data), d_o, 96))
+        _lib.check(L.b2_g1_normalize(ctypes.c_void_p(out.ctypes.data), 1))
+        assert _affine(out) == want
+        _lib.check(L.b2_stream_destroy(st))
+        for p in (d_s, d_p, d_o):
+            L.b2_dev_free(p)
+    finally:
+        srs.free()
