@@ -248,10 +248,13 @@ __device__ __forceinline__ Affine msm_load_point(const char* __restrict__ bases,
 #ifndef MSM_ACC_MIN_BLOCKS
 #define MSM_ACC_MIN_BLOCKS 4
 #endif
+#ifndef MSM_PREFETCH
+#define MSM_PREFETCH 2      // sectors of the next point requested ahead: 0 none, 1 the first, 2 both (A/B: profiles/r2_ncu_summary.md)
+#endif
 __device__ __forceinline__ void msm_prefetch_point(const char* __restrict__ bases, uint32_t stride, uint32_t ent) {
     const char* p = bases + (size_t)(ent & 0x7fffffffu) * stride;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+    if (MSM_PREFETCH >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (MSM_PREFETCH >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
 }
 
 // Partial-record convention (shared with msm_partial_reduce_kernel): every producer thread owns

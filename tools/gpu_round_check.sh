@@ -1,25 +1,15 @@
 #!/bin/bash
-# One gpurun call that validates the whole tree on a B200: the GPU test suite, smoke() and the default bench line
-# (which includes the real proofs).  Usage: gpurun --timeout 840 -- bash tools/gpu_round_check.sh
-mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/smi.txt 2>&1
-timeout 300 python -m pytest tests -q -x -m gpu > gpurun_out/gpu_suite.log 2>&1
-echo "suite rc=$?"
-tail -4 gpurun_out/gpu_suite.log
-timeout 90 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
-echo "smoke rc=$?"
-tail -2 gpurun_out/smoke.log
-timeout 420 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
-echo "bench rc=$?"
-python - <<'P'
+# What the driver runs at round end, in one call: the whole GPU suite, smoke(), the default bench line.
+cd "$(dirname "$0")/.."
+O=gpurun_out; mkdir -p $O
+python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $O/r2_gpu_suite_final.log
+python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee $O/r2_smoke_final.log
+python bench.py > $O/r2_bench_final.json 2> $O/r2_bench_final.err
+echo "bench rc=$?"; tail -c 300 $O/r2_bench_final.err
+python - <<'PY'
 import json
-try:
-    d = json.loads(open("gpurun_out/bench_final.json").read().strip().splitlines()[-1])
-    cp, c22 = d.get("create_proof", {}), d.get("create_proof_k22", {})
-    print("bench value", d["value"], "e2e", d["e2e"]["value"], "roofline", d["roofline"]["frac"], "ntt", d.get("ntt", {}).get("value"),
-          "quotient", d.get("quotient", {}).get("value"), "create_proof", cp.get("value"), cp.get("error"))
-    print("k22", c22.get("value"), c22.get("all_s"), c22.get("phases_s"), c22.get("error"), c22.get("trace"))
-except Exception as e:
-    print("bench parse failed", e)
-P
-tail -3 gpurun_out/bench_final.err
+d = json.loads(open('gpurun_out/r2_bench_final.json').read().strip().splitlines()[-1])
+print({k: d.get(k) for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'gpu_launches')})
+print('e2e', d['e2e']['value'], 'parity', d['parity_check']['ok'], 'roofline', d['roofline']['frac'], d['roofline']['frac_vs'].get('raw_imad_wide_probe'))
+print('ntt', d['ntt']['value'], 'proof18', d['create_proof'].get('value'), 'proof22', d['create_proof_k22'].get('value'), 'cpu', d['cpu_baseline']['value'])
+PY
