@@ -248,13 +248,14 @@ __device__ __forceinline__ Affine msm_load_point(const char* __restrict__ bases,
 #ifndef MSM_ACC_MIN_BLOCKS
 #define MSM_ACC_MIN_BLOCKS 4
 #endif
-#ifndef MSM_PREFETCH
-#define MSM_PREFETCH 2      // sectors of the next point requested ahead: 0 none, 1 the first, 2 both (A/B: profiles/r2_ncu_summary.md)
-#endif
+// The next point is requested two iterations ahead (both 32-byte sectors).  DRAM traffic of this kernel is 2.05x the
+// gathered bytes (7.5 GB for 54.5 M points of 64 B) and that factor is the memory system's, not the prefetch's: it is the
+// same with one prefetched sector, with none (7.28 GB, kernel 1.4 % slower) and under L2 fetch-granularity hints of
+// 32 / 64 / 128 bytes (profiles/r2_ncu_summary.md 4); HBM is 13 % busy, so it costs nothing.
 __device__ __forceinline__ void msm_prefetch_point(const char* __restrict__ bases, uint32_t stride, uint32_t ent) {
     const char* p = bases + (size_t)(ent & 0x7fffffffu) * stride;
-    if (MSM_PREFETCH >= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    if (MSM_PREFETCH >= 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
 }
 
 // Partial-record convention (shared with msm_partial_reduce_kernel): every producer thread owns
