@@ -442,3 +442,32 @@ def test_early_advice_transforms_do_not_change_the_proof(gpu):
         eng.free()
     finally:
         params.free()
+
+
+def test_early_advice_transforms_with_two_circuit_instances(gpu):
+    """create_proof_multi over two witnesses of the zkWasm-shaped circuit: each instance's 64 advice columns take the
+    early-transform path (two entries in the engine's table, two sets of coset evaluations alive at once); bytes as
+    without it, and the host-API engine agrees"""
+    import zkwasm_shape_circuit as zk
+    from oracle import cref
+    k = 8
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, 4, lambda a: cref.to_mont(0, a))
+    _, advice2, public2, _ = zk.build(k, lambda a: cref.to_mont(0, a), seed=k + 100)
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        advs = lambda: [advice.copy(), advice2.copy()]               # noqa: E731
+        insts = [[public], [public2]]
+        plain = HP.ResidentEngine(params, pk.vk.domain)
+        plain.EARLY_TRANSFORMS = False
+        want = HP.create_proof_multi(params, pk, advs(), insts, HP.SeededRng(11), engine=plain)
+        plain.free()
+        eng = HP.ResidentEngine(params, pk.vk.domain)
+        got = HP.create_proof_multi(params, pk, advs(), insts, HP.SeededRng(11), engine=eng)
+        assert len(eng._early) == 0            # released with the proof's buffers
+        eng.free()
+        assert got == want
+        host = HP.Engine(params, pk.vk.domain)
+        assert HP.create_proof_multi(params, pk, advs(), insts, HP.SeededRng(11), engine=host) == want
+    finally:
+        params.free()
