@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 10: lane selection keeps pipelines off lanes with pending caller-stream work; early advice transforms
 # measured again; ncu launch list of the bench's MSM step
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests/test_gpu_prover.py tests/test_gpu_msm.py tests/test_gpu_ntt.py -m gpu -x -q 2>&1 | tail -5 | tee $O/r2_gpu_c10.log

@@ -1,5 +1,5 @@
 #!/bin/bash
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 : > $O/r2_lane_rotation.jsonl
 python tools/lane_rotation_check.py >> $O/r2_lane_rotation.jsonl 2>&1

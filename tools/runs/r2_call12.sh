@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 12: NTT with batched tile loads / inter-pass twiddle loads (4 or 8 rows in flight per thread)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 python -m pytest tests/test_gpu_ntt.py tests/test_gpu_poly.py tests/test_gpu_quotient.py -m gpu -x -q 2>&1 | tail -3
 B2PCS_LIB=$PWD/halo2_gpu_specific_b200/variants/libb2pcs_lq8.so python -m pytest tests/test_gpu_ntt.py -m gpu -x -q 2>&1 | tail -2

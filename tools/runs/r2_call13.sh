@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 13: NTT A/B -- batched tile loads only, batched inter-pass twiddle loads only, two butterflies per
 # trip in the lone stage and the cluster stage
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 V=$PWD/halo2_gpu_specific_b200/variants
 B2PCS_LIB=$V/libb2pcs_bBFLY.so python -m pytest tests/test_gpu_ntt.py -m gpu -x -q 2>&1 | tail -2

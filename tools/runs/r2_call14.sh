@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 14: NTT register budget -- 3 CTAs per SM at 156 registers, 2 at 180 (does ptxas buy ILP with them?)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 V=$PWD/halo2_gpu_specific_b200/variants
 : > $O/r2_ntt_variants_f.jsonl

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 15: buckets per reduce thread (B2_MSM_RM) against the reduce kernel's latency chain
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 : > $O/r2_msm_rm.jsonl
 for rm in 0 2 4 8 16; do

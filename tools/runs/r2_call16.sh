@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 16: NTT with two stages per shared-memory round trip (4 elements per thread) at 4 and 6 warps per scheduler
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 V=$PWD/halo2_gpu_specific_b200/variants
 : > $O/r2_ntt_variants_g.jsonl

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 18: msm_accumulate DRAM traffic against the prefetch depth (0 / 1 / 2 sectors of the next point)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 V=$PWD/halo2_gpu_specific_b200/variants
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sector_hit_rate.pct,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed

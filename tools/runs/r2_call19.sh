@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 19: L2 fetch granularity hint (cudaLimitMaxL2FetchGranularity) against the 2x DRAM over-fetch of the
 # MSM's 64-byte gathers; NTT throughput under the same setting
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum
 for g in 128 64 32; do

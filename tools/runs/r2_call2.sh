@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 2: pipe probes (+ ncu pipe counters), NTT kernel variants (parity + timing), ncu --set full captures
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python tools/pipe_probe.py > $O/r2_pipe_probe.json 2> $O/r2_pipe_probe.err

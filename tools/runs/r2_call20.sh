@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 20: lane count against the k = 22 proof (the early advice transforms occupy one lane)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 for l in 3 4 6; do
   B2_LANES=$l python bench.py --steps 3 --warmup 3 --no-strong --no-quotient --no-ntt --no-proof --no-cpu > $O/_lanes.json 2> $O/_lanes.err

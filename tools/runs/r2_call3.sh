@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 3: full GPU suite, NTT register variants, ncu --set full captures exported to CSV on the box
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 (free -g | head -2; nproc; df -h /dev/shm | tail -1) | tee $O/r2_box.txt

@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 4 (2 GPUs): the real sharded prover (commitments by column, evaluate_h by rows) on a zkWasm-shaped circuit
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 N=${N:-2}

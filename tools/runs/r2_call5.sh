@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 5 (N GPUs): sharded prover with the witness divided over the ranks' PCIe links + NVLink exchange
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 N=${N:-2}

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 6: full GPU suite on the current tree, two-pipe probe (fp64 next to IMAD.WIDE?), batched-affine probe,
 # pipe probes, default bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee $O/r2_gpu_suite_c6.log

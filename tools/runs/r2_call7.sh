@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 7 (2 GPUs): whole GPU suite incl. the multi-device tests, bench.py as the driver launches it at N = 2
 # (own arm and reference arm)
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests -m gpu -q 2>&1 | tail -12 | tee $O/r2_gpu_suite_c7_2gpu.log

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2, GPU call 8: NTT A/B (default / called Shoup product / single-CTA 2^11 tiles), ncu pipe counters of the raw
 # probes, ncu --set full of the batched-affine probe kernels
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 : > $O/r2_ntt_variants_c.jsonl

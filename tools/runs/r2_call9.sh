@@ -1,6 +1,6 @@
 #!/bin/bash
 # round 2, GPU call 9: prover tests with the early advice transforms, k = 22 proof with and without them, default bench
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 O=gpurun_out
 mkdir -p $O
 python -m pytest tests/test_gpu_prover.py -m gpu -x -q 2>&1 | tail -5 | tee $O/r2_gpu_prover_c9.log

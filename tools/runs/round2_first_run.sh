@@ -1,7 +1,7 @@
 #!/bin/bash
 # What DESIGN.md section 8 lists as the first GPU session of round 2, as commands.
-#   1 GPU :  gpurun --timeout 600 -- bash tools/round2_first_run.sh single
-#   N GPUs:  gpurun --gpus N --timeout 600 -- bash tools/round2_first_run.sh multi N
+#   1 GPU :  gpurun --timeout 600 -- bash tools/runs/round2_first_run.sh single
+#   N GPUs:  gpurun --gpus N --timeout 600 -- bash tools/runs/round2_first_run.sh multi N
 mkdir -p gpurun_out
 case "$1" in
   single)
