@@ -10,10 +10,18 @@ all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GP
 ("weak" scaling): at N ranks the job is one MSM of N * 2^22 points.
 
   value   whole-job points/s with the scalars already resident in HBM; device time (CUDA events
-          on the launching stream, max over ranks)
-  e2e     same metric through the public host API (arithmetic.best_multiexp on a pinned host
-          column against the resident Srs): H2D of the scalars and D2H of the point are inside
-          the timed region
+          on the launching stream, max over ranks).  The steps are independent MSMs (one column
+          each), issued on --value-streams caller streams in turn (default 2) so that the digit
+          sort of one runs under the bucket reduction of the previous; the first stream forks the
+          others after the start event and joins them before the end event
+  e2e     same metric through the public host API (b2_msm_async on a pinned host column against
+          the resident Srs, one caller thread, up to --e2e-depth columns in flight): H2D of the
+          scalars and D2H of the point are inside the timed region; the blocking call is reported
+          next to it
+  parity_check  the N-rank result against the closed form [sum s_i h_i mod r] G, after the timed region
+  strong_scaling  one MSM of fixed total size 2^18 .. 2^26 split over the ranks
+  sharded_create_proof  N > 1 only: the real prover divided over the ranks (zkWasm-shaped circuit, k = 18), every
+          rank's proof bytes compared with each other and with a single-GPU proof
   roofline  dominant kernel (msm_accumulate): integer-pipe roofline, measured with CUDA events
           inside this run; peak = this run's own carry-chained IMAD.WIDE probe
   ntt     N == 1 only: 64 columns of a k=22 forward NTT, device resident: Melem/s, HBM GB/s vs
@@ -310,13 +318,50 @@ def run_engine(args):
     sp = ctypes.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
 
+    # The steps are independent MSMs (the prover commits column after column), so the device-resident loop issues them on
+    # --value-streams caller streams in turn (default 2): each stream's calls keep to a lane of their own, and the digit
+    # sort of MSM i + 1 (bound by L2 atomics) runs under the bucket reduction of MSM i (a latency chain that leaves the
+    # SMs idle).  With N > 1 the gather + sum of every step goes to one more stream, ordered after its MSM by an event.
+    # --value-streams 1 is the plain single-stream loop.
+    lanes_streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(max(0, args.value_streams - 1))]
+    coll_stream = torch.cuda.Stream(device=dev) if (world > 1 and len(lanes_streams) > 1) else stream
+    # partial results rotate through more buffers than there are streams: the gather of step i (a NCCL kernel that has to
+    # find room on SMs the next MSM's accumulate kernel fills) must not hold back the MSM that reuses step i's buffer
+    n_part = 1 if len(lanes_streams) == 1 else 4 * len(lanes_streams)
+    partials = [d_partial] + [torch.zeros(12, dtype=torch.int64, device=dev) for _ in range(n_part - 1)]
+    msm_done = [torch.cuda.Event() for _ in range(n_part)]
+    gathered = [None for _ in range(n_part)]
+    step_no = [0]
+    last_partial = [d_partial]
+
     def step_resident():
+        j = step_no[0] % n_part
+        s, part = lanes_streams[step_no[0] % len(lanes_streams)], partials[j]
+        step_no[0] += 1
+        last_partial[0] = part
+        if gathered[j] is not None:
+            s.wait_event(gathered[j])              # the previous partial in this buffer has been gathered
         _lib.check(L.b2_msm_dev(srs.handle, 0, ctypes.c_void_p(d_scalars.data_ptr()), n, 254,
-                                ctypes.c_void_p(d_partial.data_ptr()), sp))
+                                ctypes.c_void_p(part.data_ptr()), ctypes.c_void_p(s.cuda_stream)))
         if world > 1:
-            dist.all_gather_into_tensor(d_gather, d_partial)
-            _lib.check(L.b2_g1_sum_dev(ctypes.c_void_p(d_gather.data_ptr()), world,
-                                       ctypes.c_void_p(d_result.data_ptr()), sp))
+            if coll_stream is not s:
+                msm_done[j].record(s)
+                coll_stream.wait_event(msm_done[j])
+            with torch.cuda.stream(coll_stream):
+                dist.all_gather_into_tensor(d_gather, part)
+                _lib.check(L.b2_g1_sum_dev(ctypes.c_void_p(d_gather.data_ptr()), world,
+                                           ctypes.c_void_p(d_result.data_ptr()), ctypes.c_void_p(coll_stream.cuda_stream)))
+                if coll_stream is not s:
+                    gathered[j] = torch.cuda.Event()
+                    gathered[j].record(coll_stream)
+
+    def fork_streams():                            # everything after this point on `stream` precedes the other streams' work
+        for s in lanes_streams[1:] + ([coll_stream] if coll_stream is not stream else []):
+            s.wait_stream(stream)
+
+    def join_streams():                            # `stream` has seen the end of every step
+        for s in lanes_streams[1:] + ([coll_stream] if coll_stream is not stream else []):
+            stream.wait_stream(s)
 
     def step_e2e():
         return parallel.sharded_msm(h_scalars, srs, 254)
@@ -345,8 +390,10 @@ def run_engine(args):
     phase_sum = {}
     barrier()
     ev0.record(stream)
+    fork_streams()
     for _ in range(args.steps):
         step_resident()
+    join_streams()
     ev1.record(stream)
     barrier()
     launches = int(L.b2_launch_count(0))
@@ -369,15 +416,17 @@ def run_engine(args):
 
     # --- e2e through the public host API: ONE caller thread, every step copies its pinned host column to the device
     # (H2D) and reads its point back (D2H); the asynchronous form of the call (gpu_multiexp_async -> b2_msm_async) lets
-    # the copy of step i + 1 run under the kernels of step i, two steps in flight
+    # the copies of the next steps run under the kernels of step i, up to --e2e-depth steps in flight
     def run_e2e_pipelined(steps):
-        res, pending = None, None
+        from collections import deque
+        res, inflight = None, deque()
         for _ in range(steps):
-            fut = parallel.sharded_msm_async(h_scalars, srs, 254)
-            if pending is not None:
-                res = pending.result()
-            pending = fut
-        return pending.result() if pending is not None else res
+            if len(inflight) == args.e2e_depth:
+                res = inflight.popleft().result()
+            inflight.append(parallel.sharded_msm_async(h_scalars, srs, 254))
+        while inflight:
+            res = inflight.popleft().result()
+        return res
 
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
@@ -420,7 +469,7 @@ def run_engine(args):
     # consistency: the host-API result equals the device-resident result (same inputs)
     step_resident()
     torch.cuda.synchronize()
-    res_dev = np.ascontiguousarray((d_result if world > 1 else d_partial).cpu().numpy().view(np.uint64))
+    res_dev = np.ascontiguousarray((d_result if world > 1 else last_partial[0]).cpu().numpy().view(np.uint64))
     _lib.check(L.b2_g1_normalize(_lib.ptr(res_dev), 1))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-API results differ"
 
@@ -497,12 +546,18 @@ def run_engine(args):
                 "srs_window_table": not args.no_precompute, "parallelism": f"range-shard x{world}",
                 "cache": "inputs larger than L2: scalars 128 MiB + bases 256 MiB + sort buffers 512 MiB per step",
                 "timing": "CUDA events on the launching stream, max over ranks",
+                "value_streams": args.value_streams,
+                "value_loop": (f"the steps are independent MSMs issued on {args.value_streams} caller streams in turn (the sort of "
+                               "MSM i + 1 runs under the bucket reduction of MSM i); the events bracket all of them on the "
+                               "first stream, which forks the others after the start event and joins them before the end "
+                               "event" if args.value_streams > 1 else "one caller stream, the MSMs run back to back"),
             },
             "e2e": {"value": total_pts / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": n * 32, "d2h_bytes_per_step": 96,
                     "api": "halo2_gpu_specific_b200.parallel.sharded_msm_async (pinned host column -> b2_msm_async -> "
-                           "96 B), one caller thread, two steps in flight: the H2D copy of step i + 1 overlaps the kernels "
-                           "of step i; every step still copies its own 2^logn x 32 B in and its point out",
+                           f"96 B), one caller thread, up to {args.e2e_depth} steps in flight (one lane each): the H2D copies "
+                           "of the next steps overlap the kernels of step i; every step still copies its own 2^logn x 32 B "
+                           "in and reads its point out",
                     "blocking_call": {"value": total_pts / (e2e_sync_ms * 1e-3) / 1e6, "unit": UNIT,
                                       "ms_per_step": e2e_sync_ms / args.steps,
                                       "api": "parallel.sharded_msm -> b2_msm (copy, then compute, then read-back)"}},
@@ -536,6 +591,10 @@ def run_engine(args):
                 "peak_source": "b2_imad_probe in this run: carry-chained IMAD.WIDE Montgomery products, "
                                f"{muls.value / 1e9:.1f} G modmul/s x 128",
                 "share_of_step": acc / phases_avg.get("total", acc),
+                "share_note": "accumulate kernel time over the time of ONE MSM run alone (library phase events; the ncu "
+                              "launch list serialises the same way).  In the timed loop the MSMs of different caller streams "
+                              f"overlap at their heads and tails, so a step takes {dev_ms / args.steps:.3f} ms there and the "
+                              f"kernel is {acc / (dev_ms / args.steps):.3f} of it",
             },
             "msm_phases_ms": phases_avg,
             "clocks": clocks,
@@ -1111,6 +1170,10 @@ def main():
     ap.add_argument("--no-proof22", action="store_true", help="skip the zkWasm-shaped k=22 real proof (about 40 s of setup)")
     ap.add_argument("--proof22-k", type=int, default=22)
     ap.add_argument("--proof22-reps", type=int, default=2)
+    ap.add_argument("--value-streams", type=int, default=2, choices=[1, 2, 3],
+                    help="caller streams the device-resident loop issues its MSMs on in turn (1 = one stream, serial)")
+    ap.add_argument("--e2e-depth", type=int, default=3, choices=[1, 2, 3],
+                    help="b2_msm_async tickets one caller thread keeps in flight in the e2e loop (<= B2_LANES)")
     ap.add_argument("--sharded-proof-k", type=int, default=18,
                     help="N > 1: size of the zkWasm-shaped circuit proved by all ranks together (sharded_create_proof)")
     ap.add_argument("--shplonk", action="store_true", help="create_proof_with_shplonk in the proof sections")
