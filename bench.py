@@ -6,8 +6,10 @@
 A "step" is one pass of the commitment hot path over one synthetic column per GPU: one MSM of
 2^22 uniformly random Fr scalars against that rank's resident point-range shard of the SRS
 (north_star: "MSM point ranges per GPU with one partial G1 point combined per rank"), the NCCL
-all-gather of one 96-byte partial per rank, and the sum of the partials.  Per-GPU work is fixed
-("weak" scaling): at N ranks the job is one MSM of N * 2^22 points.
+all-gather of one 96-byte partial per rank, and the sum of the partials -- gathered and summed
+for a block of steps at a time (--gather-every; inside the timed region), as the sharded prover
+gathers the points of a block of columns.  Per-GPU work is fixed ("weak" scaling): at N ranks
+every step is one MSM of N * 2^22 points.
 
   value   whole-job points/s with the scalars already resident in HBM; device time (CUDA events
           on the launching stream, max over ranks).  The steps are independent MSMs (one column
@@ -309,9 +311,6 @@ def run_engine(args):
     h_scalars = _lib.pinned_empty((n, 4))
     random_montgomery_scalars(n, seed + rank, pinned=h_scalars)
     d_scalars = torch.from_numpy(h_scalars.view(np.int64)).to(dev)
-    d_partial = torch.zeros(12, dtype=torch.int64, device=dev)
-    d_gather = torch.zeros(12 * world, dtype=torch.int64, device=dev)
-    d_result = torch.zeros(12, dtype=torch.int64, device=dev)
     # a real (non-default) stream: the library launches on it, torch's events and NCCL order on it
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
@@ -321,47 +320,61 @@ def run_engine(args):
     # The steps are independent MSMs (the prover commits column after column), so the device-resident loop issues them on
     # --value-streams caller streams in turn (default 2): each stream's calls keep to a lane of their own, and the digit
     # sort of MSM i + 1 (bound by L2 atomics) runs under the bucket reduction of MSM i (a latency chain that leaves the
-    # SMs idle).  With N > 1 the gather + sum of every step goes to one more stream, ordered after its MSM by an event.
-    # --value-streams 1 is the plain single-stream loop.
+    # SMs idle).  --value-streams 1 is the plain single-stream loop.
+    # With N > 1 the partials of --gather-every consecutive steps (default: all steps of the loop) form a block that is
+    # all-gathered in ONE collective and summed in one launch -- what the sharded prover does with the points of a block
+    # of columns (prover_sharded.ShardedCommits._gather): a NCCL kernel per step has to find room on SMs that the next
+    # MSM's accumulate kernel fills, and holds the overlap back.  --gather-every 1 is the per-step gather.
     lanes_streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(max(0, args.value_streams - 1))]
-    coll_stream = torch.cuda.Stream(device=dev) if (world > 1 and len(lanes_streams) > 1) else stream
-    # partial results rotate through more buffers than there are streams: the gather of step i (a NCCL kernel that has to
-    # find room on SMs the next MSM's accumulate kernel fills) must not hold back the MSM that reuses step i's buffer
-    n_part = 1 if len(lanes_streams) == 1 else 4 * len(lanes_streams)
-    partials = [d_partial] + [torch.zeros(12, dtype=torch.int64, device=dev) for _ in range(n_part - 1)]
-    msm_done = [torch.cuda.Event() for _ in range(n_part)]
-    gathered = [None for _ in range(n_part)]
-    step_no = [0]
-    last_partial = [d_partial]
+    G = max(1, args.gather_every if args.gather_every > 0 else max(args.steps, args.warmup, 1))
+    blocks = [torch.zeros((G, 12), dtype=torch.int64, device=dev) for _ in range(2)]     # double-buffered
+    g_all = torch.zeros((world, G, 12), dtype=torch.int64, device=dev)
+    g_sums = torch.zeros((G, 12), dtype=torch.int64, device=dev)
+    st = {"block": 0, "fill": 0, "step": 0, "last": None}
+    flushed = [None, None]                          # event: block b has been gathered (its rows may be overwritten)
+
+    def flush_gather():
+        """all-gather + sums of the rows filled since the last flush, on `stream`, after every lane stream's MSMs"""
+        rows = st["fill"]
+        if rows == 0:
+            return
+        b = st["block"]
+        for s_ in lanes_streams[1:]:
+            stream.wait_stream(s_)
+        if world > 1:
+            dist.all_gather_into_tensor(g_all.view(-1), blocks[b].view(-1))             # current stream == `stream`
+            _lib.check(L.b2_g1_sum_groups_dev(ctypes.c_void_p(g_all.data_ptr()), world, G,
+                                              ctypes.c_void_p(g_sums.data_ptr()), sp))
+            st["last"] = g_sums[rows - 1]
+        else:
+            st["last"] = blocks[b][rows - 1]
+        flushed[b] = torch.cuda.Event()
+        flushed[b].record(stream)
+        st["block"], st["fill"] = 1 - b, 0
 
     def step_resident():
-        j = step_no[0] % n_part
-        s, part = lanes_streams[step_no[0] % len(lanes_streams)], partials[j]
-        step_no[0] += 1
-        last_partial[0] = part
-        if gathered[j] is not None:
-            s.wait_event(gathered[j])              # the previous partial in this buffer has been gathered
+        if st["fill"] == G:
+            flush_gather()
+        b, row = st["block"], st["fill"]
+        s_ = lanes_streams[st["step"] % len(lanes_streams)]
+        st["step"] += 1
+        st["fill"] += 1
+        if row == 0 and flushed[b] is not None:
+            for t_ in lanes_streams[1:]:
+                t_.wait_event(flushed[b])           # the block's previous contents have been gathered
         _lib.check(L.b2_msm_dev(srs.handle, 0, ctypes.c_void_p(d_scalars.data_ptr()), n, 254,
-                                ctypes.c_void_p(part.data_ptr()), ctypes.c_void_p(s.cuda_stream)))
-        if world > 1:
-            if coll_stream is not s:
-                msm_done[j].record(s)
-                coll_stream.wait_event(msm_done[j])
-            with torch.cuda.stream(coll_stream):
-                dist.all_gather_into_tensor(d_gather, part)
-                _lib.check(L.b2_g1_sum_dev(ctypes.c_void_p(d_gather.data_ptr()), world,
-                                           ctypes.c_void_p(d_result.data_ptr()), ctypes.c_void_p(coll_stream.cuda_stream)))
-                if coll_stream is not s:
-                    gathered[j] = torch.cuda.Event()
-                    gathered[j].record(coll_stream)
+                                ctypes.c_void_p(blocks[b][row].data_ptr()), ctypes.c_void_p(s_.cuda_stream)))
+
+    def result_tensor():
+        flush_gather()
+        return st["last"]
 
     def fork_streams():                            # everything after this point on `stream` precedes the other streams' work
-        for s in lanes_streams[1:] + ([coll_stream] if coll_stream is not stream else []):
-            s.wait_stream(stream)
+        for s_ in lanes_streams[1:]:
+            s_.wait_stream(stream)
 
-    def join_streams():                            # `stream` has seen the end of every step
-        for s in lanes_streams[1:] + ([coll_stream] if coll_stream is not stream else []):
-            stream.wait_stream(s)
+    def join_streams():                            # `stream` has seen the end of every step, gathers and sums included
+        flush_gather()
 
     def step_e2e():
         return parallel.sharded_msm(h_scalars, srs, 254)
@@ -380,6 +393,7 @@ def run_engine(args):
 
     for _ in range(args.warmup):
         step_resident()
+    flush_gather()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -406,6 +420,7 @@ def run_engine(args):
     # accumulate-kernel duration: measure it over several steps through the phase events
     for _ in range(min(args.steps, 5)):
         step_resident()
+        flush_gather()
         torch.cuda.synchronize()
         p = _lib.last_msm_phases()
         acc_ms.append(p["accumulate"])
@@ -468,8 +483,9 @@ def run_engine(args):
 
     # consistency: the host-API result equals the device-resident result (same inputs)
     step_resident()
+    res_t = result_tensor()
     torch.cuda.synchronize()
-    res_dev = np.ascontiguousarray((d_result if world > 1 else last_partial[0]).cpu().numpy().view(np.uint64))
+    res_dev = np.ascontiguousarray(res_t.cpu().numpy().view(np.uint64))
     _lib.check(L.b2_g1_normalize(_lib.ptr(res_dev), 1))
     assert np.array_equal(res_dev, res_e2e), "device-resident and host-API results differ"
 
@@ -547,6 +563,9 @@ def run_engine(args):
                 "cache": "inputs larger than L2: scalars 128 MiB + bases 256 MiB + sort buffers 512 MiB per step",
                 "timing": "CUDA events on the launching stream, max over ranks",
                 "value_streams": args.value_streams,
+                "gather": ("one all-gather + one grouped sum per block of "
+                           f"{args.gather_every if args.gather_every > 0 else args.steps} steps, inside the timed region (the "
+                           "sharded prover gathers the points of a block of columns the same way)") if world > 1 else None,
                 "value_loop": (f"the steps are independent MSMs issued on {args.value_streams} caller streams in turn (the sort of "
                                "MSM i + 1 runs under the bucket reduction of MSM i); the events bracket all of them on the "
                                "first stream, which forks the others after the start event and joins them before the end "
@@ -1172,6 +1191,9 @@ def main():
     ap.add_argument("--proof22-reps", type=int, default=2)
     ap.add_argument("--value-streams", type=int, default=2, choices=[1, 2, 3],
                     help="caller streams the device-resident loop issues its MSMs on in turn (1 = one stream, serial)")
+    ap.add_argument("--gather-every", type=int, default=0,
+                    help="N > 1: steps whose partials are all-gathered and summed together (0 = all steps of the loop, 1 = "
+                         "a collective per step)")
     ap.add_argument("--e2e-depth", type=int, default=3, choices=[1, 2, 3],
                     help="b2_msm_async tickets one caller thread keeps in flight in the e2e loop (<= B2_LANES)")
     ap.add_argument("--sharded-proof-k", type=int, default=18,

@@ -45,7 +45,7 @@ class NttDesc(ctypes.Structure):
 SYMBOLS = [
     "b2_version", "b2_last_error", "b2_device_count", "b2_set_device", "b2_get_device", "b2_synchronize",
     "b2_launch_count", "b2_stream_create", "b2_stream_synchronize", "b2_stream_destroy", "b2_srs_register", "b2_srs_synthetic", "b2_srs_from_scalars_dev", "b2_memcpy_d2d", "b2_vanishing_random_poly_dev", "b2_fr_max_bits_dev", "b2_srs_precompute", "b2_srs_len", "b2_srs_read", "b2_srs_free",
-    "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
+    "b2_msm", "b2_msm_dev", "b2_best_multiexp", "b2_g1_sum", "b2_g1_normalize", "b2_g1_sum_dev", "b2_g1_sum_groups_dev", "b2_ntt_exec", "b2_best_fft", "b2_gpu_ifft",
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_msm_async", "b2_msm_wait", "b2_logup_multiplicity_dev", "b2_eval_polynomials_dev", "b2_dfma_probe", "b2_mixed_probe", "b2_affine_batch_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
@@ -91,6 +91,7 @@ def lib() -> ctypes.CDLL:
         L.b2_best_multiexp.argtypes = [vp, vp, sz, vp]
         L.b2_g1_sum.argtypes = [vp, sz, vp]
         L.b2_g1_sum_dev.argtypes = [vp, sz, vp, vp]
+        L.b2_g1_sum_groups_dev.argtypes = [vp, sz, sz, vp, vp]
         L.b2_ntt_exec.argtypes = [ctypes.POINTER(NttDesc)]
         L.b2_best_fft.argtypes = [vp, vp, u32]
         L.b2_gpu_ifft.argtypes = [vp, vp, u32, vp]

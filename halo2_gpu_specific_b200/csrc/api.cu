@@ -1406,6 +1406,19 @@ int b2_g1_normalize(void* jac96, size_t count) {
     return B2_OK;
 }
 
+int b2_g1_sum_groups_dev(const void* d_jac96, size_t count, size_t groups, void* d_out_jac96, void* stream) {
+    if (!d_out_jac96 || (count && groups && !d_jac96)) return fail(B2_ERR_ARG, "g1_sum_groups_dev: null pointer");
+    if (groups == 0) return B2_OK;
+    LaneLock ll;
+    int rc = ll.acquire();
+    if (rc) return rc;
+    Lane* ctx = ll.lane;
+    cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+    LAUNCH(*ctx, g1_sum_groups_kernel, (unsigned)((groups + 31) / 32), 32, 0, st, (const char*)d_jac96, (uint32_t)count,
+           (uint32_t)groups, (char*)d_out_jac96);
+    return B2_OK;   // uses no lane workspace
+}
+
 int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream) {
     if (!d_out_jac96 || (count && !d_jac96)) return fail(B2_ERR_ARG, "g1_sum_dev: null pointer");
     LaneLock ll;

@@ -557,6 +557,20 @@ __global__ void g1_sum_kernel(const char* __restrict__ pts, uint32_t count, char
     xyzz_store_jacobian(out, acc);
 }
 
+// `groups` independent sums at once: out[g] = sum_r pts[r * groups + g], r < count (the layout an all-gather of every
+// rank's `groups` partials produces: rank-major).  One thread per group.
+__global__ void g1_sum_groups_kernel(const char* __restrict__ pts, uint32_t count, uint32_t groups, char* __restrict__ out) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= groups) return;
+    XYZZ acc = XYZZ::identity();
+    for (uint32_t r = 0; r < count; r++) {
+        const char* p = pts + ((size_t)r * groups + g) * 96;
+        XYZZ o = xyzz_from_jacobian(fp_load<FqParams>(p), fp_load<FqParams>(p + 32), fp_load<FqParams>(p + 64));
+        xyzz_add_ni(acc, o);
+    }
+    xyzz_store_jacobian(out + (size_t)g * 96, acc);
+}
+
 // ---------------------------------------------------------------- SRS window tables
 // table[w * n + i] = 2^(c*w) * P_i (affine).  One launch per window: c doublings in XYZZ, then
 // one shared field inversion per thread for its PRE_K points (Montgomery's trick).

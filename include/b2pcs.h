@@ -144,6 +144,9 @@ int b2_g1_normalize(void* jac96, size_t count);
 /* Same as b2_g1_sum with device pointers, asynchronous on `stream` (NULL = the library stream),
  * result not normalised: used after the NCCL all-gather of one partial per rank. */
 int b2_g1_sum_dev(const void* d_jac96, size_t count, void* d_out_jac96, void* stream);
+/* `groups` such sums in one launch: out[g] = sum over r < count of jac96[r * groups + g] -- the rank-major layout that ONE
+ * all-gather of every rank's `groups` partials (a block of columns committed by point range) leaves behind. */
+int b2_g1_sum_groups_dev(const void* d_jac96, size_t count, size_t groups, void* d_out_jac96, void* stream);
 
 /* ---- NTT -------------------------------------------------------------------------- */
 typedef struct b2_ntt_desc {

@@ -457,3 +457,32 @@ def test_caller_stream_msm_sum_and_phase_events(gpu):
             L.b2_dev_free(p)
     finally:
         srs.free()
+
+
+def test_g1_sum_groups_dev(gpu):
+    """b2_g1_sum_groups_dev: the sums of a rank-major block of partials (what ONE all-gather of every rank's partials for
+    a block of columns leaves behind), identities and a P + (-P) column included"""
+    import ctypes
+    from halo2_gpu_specific_b200 import _lib
+    L = _lib.lib()
+    ranks, groups = 3, 5
+    pts = [[o.g1_mul(o.G1_GEN, 7 + 11 * r + 3 * g) for g in range(groups)] for r in range(ranks)]
+    pts[1][2] = None                                   # an identity partial
+    pts[0][4], pts[1][4], pts[2][4] = o.g1_mul(o.G1_GEN, 5), o.g1_neg(o.g1_mul(o.G1_GEN, 5)), None   # sums to the identity
+    flat = np.stack([o.g1_jacobian_encode(pts[r][g]) for r in range(ranks) for g in range(groups)]).astype(np.uint64)
+    d_in, d_out = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.b2_dev_alloc(flat.nbytes, ctypes.byref(d_in)))
+    _lib.check(L.b2_dev_alloc(groups * 96, ctypes.byref(d_out)))
+    _lib.check(L.b2_memcpy_h2d(d_in, ctypes.c_void_p(flat.ctypes.data), flat.nbytes))
+    _lib.check(L.b2_g1_sum_groups_dev(d_in, ranks, groups, d_out, None))
+    _lib.check(L.b2_synchronize())
+    out = np.zeros((groups, 12), dtype=np.uint64)
+    _lib.check(L.b2_memcpy_d2h(ctypes.c_void_p(out.ctypes.data), d_out, out.nbytes))
+    _lib.check(L.b2_g1_normalize(ctypes.c_void_p(out.ctypes.data), groups))
+    for g in range(groups):
+        want = None
+        for r in range(ranks):
+            want = o.g1_add(want, pts[r][g])
+        assert _affine(out[g]) == want
+    L.b2_dev_free(d_in)
+    L.b2_dev_free(d_out)
