@@ -847,7 +847,10 @@ def bench_quotient(args, _lib, h2, modmuls_per_s):
                          "achieved": muls * 128.0 * rows / (eval_ms * 1e-3) / 1e12, "peak": modmuls_per_s * 128 / 1e12,
                          "frac": muls * rows / (eval_ms * 1e-3) / modmuls_per_s,
                          "model": f"{muls} field multiplications per row x 128 MACs (SURVEY 8d accounting); "
-                                  f"additions and operand decode are not counted"},
+                                  f"additions and operand decode are not counted.  The host fuses a * b +- c * d into one "
+                                  f"instruction with ONE Montgomery reduction (192 + 8 MACs for two products): the pipe "
+                                  f"does less than the model counts, so the fraction can approach 1 while the pipe "
+                                  f"itself stays at its ~82 % (B2_Q_NO_FUSE=1 runs the plain form)"},
     }
     if not args.no_cpu:
         # CPU: the C restatement of the reference's row loop (Calculation::evaluate, plonk/evaluation.rs:846-1001) on a

@@ -18,7 +18,7 @@ struct QProgram {
     // lowered program
     std::vector<QInstr> instr;
     uint32_t result = 0;
-    uint32_t n_slots = 0, n_mul = 0, n_addsub = 0;
+    uint32_t n_slots = 0, n_mul = 0, n_addsub = 0, n_fused = 0;   // n_mul counts both products of a fused instruction
     bool uses_x = false;
     std::vector<int32_t> rotations;
     std::vector<uint64_t> constants;                         // 4 limbs each
@@ -172,73 +172,107 @@ struct QLower {
         uint32_t res = 0;
         if (!src(d.result, d.n_calcs, &res)) return false;
 
+        // From here on a node has up to four operands (the fused two-product form).
+        struct Node { uint32_t op; uint32_t w[4]; };
+        auto nops = [](uint32_t op) -> int { return (op == Q_NEG || op == Q_COPY) ? 1 : (op >= Q_MUL2ADD ? 4 : 2); };
+        auto is_v = [](uint32_t w) { return (w >> 28) == QK_SLOT; };
+        std::vector<Node> node(n_vreg);
+        for (uint32_t v = 0; v < n_vreg; v++) node[v] = Node{raw[v].op_dst & 0xffu, {raw[v].a, raw[v].b, 0, 0}};
+
+        // Fusion of a * b +- c * d.  Uses are counted over the instructions the result depends on; a product read only by
+        // one ADD / SUB whose other operand is such a product too disappears into that instruction (evaluate_h is sums
+        // of products: gate polynomials, the permutation and lookup terms).  B2_Q_NO_FUSE=1 keeps the plain form (A/B).
+        static const bool no_fuse = getenv("B2_Q_NO_FUSE") != nullptr;
+        if (!no_fuse) {
+            std::vector<char> reach(n_vreg, 0);
+            std::vector<uint32_t> work;
+            if (is_v(res)) { reach[res & 0xfffffu] = 1; work.push_back(res & 0xfffffu); }
+            std::vector<uint32_t> uses(n_vreg, 0);
+            if (is_v(res)) uses[res & 0xfffffu]++;
+            while (!work.empty()) {
+                const uint32_t v = work.back();
+                work.pop_back();
+                for (int k = 0; k < nops(node[v].op); k++) {
+                    const uint32_t w = node[v].w[k];
+                    if (!is_v(w)) continue;
+                    uses[w & 0xfffffu]++;
+                    if (!reach[w & 0xfffffu]) { reach[w & 0xfffffu] = 1; work.push_back(w & 0xfffffu); }
+                }
+            }
+            for (uint32_t v = 0; v < n_vreg; v++) {
+                if (!reach[v] || (node[v].op != Q_ADD && node[v].op != Q_SUB)) continue;
+                const uint32_t wa = node[v].w[0], wb = node[v].w[1];
+                if (!is_v(wa) || !is_v(wb)) continue;
+                const uint32_t va = wa & 0xfffffu, vb = wb & 0xfffffu;
+                if (va == vb || node[va].op != Q_MUL || node[vb].op != Q_MUL || uses[va] != 1 || uses[vb] != 1) continue;
+                node[v] = Node{node[v].op == Q_ADD ? (uint32_t)Q_MUL2ADD : (uint32_t)Q_MUL2SUB,
+                               {node[va].w[0], node[va].w[1], node[vb].w[0], node[vb].w[1]}};
+            }
+        }
+
         // Scheduling.  The reference computes every Calculation first and folds the value parts
         // afterwards (evaluation.rs:877-907), which keeps one value per gate alive until the fold.  The
-        // raw list is a DAG in SSA form (virtual register v is defined by raw[v]), so it is re-emitted
+        // raw list is a DAG in SSA form (virtual register v is defined by node[v]), so it is re-emitted
         // in depth-first post-order from the result: each term is computed right before it is folded
         // and the live width drops from O(#gates) to the depth of one expression (plus shared
         // subexpressions).  The larger operand subtree goes first (Sethi-Ullman).  Instructions the
         // result does not depend on are never visited (dead-code elimination).
         std::vector<uint32_t> weight(n_vreg, 1);
-        auto wt = [&](uint32_t w) -> uint32_t { return (w >> 28) == QK_SLOT ? weight[w & 0xfffffu] : 0u; };
+        auto wt = [&](uint32_t w) -> uint32_t { return is_v(w) ? weight[w & 0xfffffu] : 0u; };
         for (uint32_t v = 0; v < n_vreg; v++) {
-            const uint32_t op = raw[v].op_dst & 0xffu;
-            uint64_t t = 1 + (uint64_t)wt(raw[v].a) + ((op != Q_NEG && op != Q_COPY) ? wt(raw[v].b) : 0);
+            uint64_t t = 1;
+            for (int k = 0; k < nops(node[v].op); k++) t += wt(node[v].w[k]);
             weight[v] = (uint32_t)std::min<uint64_t>(t, 1u << 30);
         }
         std::vector<char> state(n_vreg, 0);   // 0 unvisited, 1 operands pushed, 2 emitted
-        std::vector<QInstr> kept;
+        std::vector<uint32_t> kept;           // virtual registers in emission order
         std::vector<uint32_t> stack;
-        if ((res >> 28) == QK_SLOT) stack.push_back(res & 0xfffffu);
+        if (is_v(res)) stack.push_back(res & 0xfffffu);
         while (!stack.empty()) {
             const uint32_t v = stack.back();
             if (state[v] == 2) { stack.pop_back(); continue; }
             if (state[v] == 1) {
-                kept.push_back(raw[v]);
+                kept.push_back(v);
                 state[v] = 2;
                 stack.pop_back();
                 continue;
             }
             state[v] = 1;
-            const uint32_t op = raw[v].op_dst & 0xffu;
-            const bool binary = op != Q_NEG && op != Q_COPY;
-            uint32_t first = raw[v].a, second = binary ? raw[v].b : 0xffffffffu;
-            if (binary && wt(second) > wt(first)) std::swap(first, second);
-            // pushed in reverse: `first` is processed first
-            if (second != 0xffffffffu && (second >> 28) == QK_SLOT && state[second & 0xfffffu] == 0)
-                stack.push_back(second & 0xfffffu);
-            if ((first >> 28) == QK_SLOT && state[first & 0xfffffu] == 0) stack.push_back(first & 0xfffffu);
+            // operands by decreasing weight; pushed in reverse, so the heaviest is processed first
+            uint32_t ord[4];
+            const int n = nops(node[v].op);
+            for (int k = 0; k < n; k++) ord[k] = node[v].w[k];
+            std::stable_sort(ord, ord + n, [&](uint32_t x, uint32_t y) { return wt(x) > wt(y); });
+            for (int k = n - 1; k >= 0; k--)
+                if (is_v(ord[k]) && state[ord[k] & 0xfffffu] == 0) stack.push_back(ord[k] & 0xfffffu);
         }
         // last use of every live virtual register
         std::vector<uint32_t> last(n_vreg, 0);
-        auto use = [&](uint32_t w, uint32_t at) { if ((w >> 28) == QK_SLOT) last[w & 0xfffffu] = at; };
-        for (uint32_t j = 0; j < kept.size(); j++) {
-            const uint32_t op = kept[j].op_dst & 0xffu;
-            use(kept[j].a, j);
-            if (op != Q_NEG && op != Q_COPY) use(kept[j].b, j);
-        }
+        auto use = [&](uint32_t w, uint32_t at) { if (is_v(w)) last[w & 0xfffffu] = at; };
+        for (uint32_t j = 0; j < kept.size(); j++)
+            for (int k = 0; k < nops(node[kept[j]].op); k++) use(node[kept[j]].w[k], j);
         use(res, (uint32_t)kept.size());
         // slot allocation
         std::vector<uint32_t> slot_of(n_vreg, 0xffffffffu), free_slots;
         uint32_t n_slots = 0;
         auto remap = [&](uint32_t w) {
-            return (w >> 28) == QK_SLOT ? q_operand(QK_SLOT, slot_of[w & 0xfffffu], 0) : w;
+            return is_v(w) ? q_operand(QK_SLOT, slot_of[w & 0xfffffu], 0) : w;
         };
         auto release = [&](uint32_t w, uint32_t at) {
-            if ((w >> 28) != QK_SLOT) return;
+            if (!is_v(w)) return;
             const uint32_t v = w & 0xfffffu;
             if (last[v] == at && slot_of[v] != 0xffffffffu) {
                 free_slots.push_back(slot_of[v]);
-                last[v] = 0xffffffffu;   // released once, even when both operands name it
+                last[v] = 0xffffffffu;   // released once, even when several operands name it
             }
         };
         for (uint32_t j = 0; j < kept.size(); j++) {
-            QInstr in = kept[j];
-            const uint32_t op = in.op_dst & 0xffu, dst = in.op_dst >> 8;
-            const bool binary = op != Q_NEG && op != Q_COPY;
-            const uint32_t a = remap(in.a), b = binary ? remap(in.b) : 0;
-            release(in.a, j);
-            if (binary) release(in.b, j);
+            const uint32_t dst = kept[j];
+            const Node& nd = node[dst];
+            const int n = nops(nd.op);
+            uint32_t m[4] = {0, 0, 0, 0};
+            for (int k = 0; k < n; k++) m[k] = remap(nd.w[k]);
+            for (int k = 0; k < n; k++) release(nd.w[k], j);
             uint32_t s;
             if (!free_slots.empty()) {
                 s = free_slots.back();
@@ -247,12 +281,26 @@ struct QLower {
                 s = n_slots++;
             }
             slot_of[dst] = s;
-            in.op_dst = op | (s << 8);
-            in.a = a;
-            in.b = b;
+            QInstr in;
+            in.op_dst = nd.op | (s << 8);
+            in.a = m[0];
+            in.b = m[1];
+            in.pad = m[2];
             p.instr.push_back(in);
-            if (op == Q_MUL) p.n_mul++;
-            else if (op == Q_ADD || op == Q_SUB || op == Q_NEG) p.n_addsub++;
+            if (n == 4) {
+                QInstr ext;
+                ext.op_dst = Q_EXT;
+                ext.a = m[3];
+                ext.b = 0;
+                ext.pad = 0;
+                p.instr.push_back(ext);
+                p.n_mul += 2;
+                p.n_fused++;
+            } else if (nd.op == Q_MUL) {
+                p.n_mul++;
+            } else if (nd.op == Q_ADD || nd.op == Q_SUB || nd.op == Q_NEG) {
+                p.n_addsub++;
+            }
         }
         p.result = remap(res);
         p.n_slots = n_slots ? n_slots : 1;
@@ -342,7 +390,7 @@ int b2_quotient_program_dump(b2_handle_t program, uint32_t* instr_words, size_t 
         instr_words[4 * i] = p->instr[i].op_dst;
         instr_words[4 * i + 1] = p->instr[i].a;
         instr_words[4 * i + 2] = p->instr[i].b;
-        instr_words[4 * i + 3] = 0;
+        instr_words[4 * i + 3] = p->instr[i].pad;
     }
     for (size_t i = 0; i < p->derived.size(); i++) {
         derived_pairs[2 * i] = p->derived[i].first;

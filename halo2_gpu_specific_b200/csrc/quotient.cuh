@@ -19,7 +19,11 @@
 
 namespace b2 {
 
-enum QOp : uint32_t { Q_ADD = 0, Q_SUB = 1, Q_MUL = 2, Q_NEG = 3, Q_COPY = 4 };
+// Q_MUL2ADD / Q_MUL2SUB: a * b +- c * d under ONE Montgomery reduction (fp_mul2_add, 1.44 product-equivalents instead of
+// 2 + an addition).  The host fuses an ADD / SUB whose operands are two products nobody else reads -- gates are sums of
+// products, so this is a quarter of all products of a zkWasm-sized program.  Such an instruction takes two QInstr
+// entries: {op | dst, a, b, c} and {Q_EXT, d}.
+enum QOp : uint32_t { Q_ADD = 0, Q_SUB = 1, Q_MUL = 2, Q_NEG = 3, Q_COPY = 4, Q_MUL2ADD = 5, Q_MUL2SUB = 6, Q_EXT = 7 };
 enum QKind : uint32_t {
     QK_CONST = 0,   // constants[index]
     QK_SLOT = 1,    // intermediate in slot `index`
@@ -36,7 +40,7 @@ __host__ __device__ __forceinline__ uint32_t q_operand(uint32_t kind, uint32_t i
 struct QInstr {          // 16 bytes, read with one uniform 128-bit load
     uint32_t op_dst;     // op | dst_slot << 8
     uint32_t a, b;       // operand words
-    uint32_t pad;
+    uint32_t pad;        // third operand of a fused instruction (the fourth sits in the following Q_EXT entry's `a`)
 };
 
 constexpr int Q_THREADS = 128;
@@ -128,6 +132,13 @@ __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a)
                 r = fp_neg<FrParams>(x);
             } else if (op == Q_COPY) {
                 r = x;
+            } else if (op >= Q_MUL2ADD) {
+                const uint4 ext = __ldg(a.prog + pc + 1);
+                pc++;
+                const Fr y = q_fetch<SMEM>(ins.z, a, slots, row, x_here);
+                const Fr c = q_fetch<SMEM>(ins.w, a, slots, row, x_here);
+                const Fr d = q_fetch<SMEM>(ext.y, a, slots, row, x_here);
+                r = (op == Q_MUL2ADD) ? fp_mul2_add<FrParams>(x, y, c, d) : fp_mul2_sub<FrParams>(x, y, c, d);
             } else {
                 Fr y = q_fetch<SMEM>(ins.z, a, slots, row, x_here);
                 if (op == Q_MUL) r = fp_mul<FrParams>(x, y);

@@ -123,7 +123,8 @@ class QuotientProgram:
         return dict(zip(("n_instr", "n_slots", "n_mul", "n_addsub"), (x.value for x in v)))
 
     def dump(self):
-        """(instructions as (op, dst, a_word, b_word), result word, derived (challenge, power) pairs)"""
+        """(instructions, result word, derived (challenge, power) pairs); an instruction is (op, dst, a_word, b_word),
+        or (op, dst, a, b, c, d) for the fused a * b +- c * d (op 5 / 6: its extension entry is folded in here)"""
         n = self.info()["n_instr"]
         words = np.zeros(max(1, n) * 4, dtype=np.uint32)
         der = np.zeros(2 * 4096, dtype=np.uint32)
@@ -131,8 +132,17 @@ class QuotientProgram:
         check(lib().b2_quotient_program_dump(ctypes.c_uint64(self.handle), ctypes.c_void_p(words.ctypes.data), words.size,
                                              ctypes.byref(res), ctypes.c_void_p(der.ctypes.data), der.size,
                                              ctypes.byref(nd)))
-        instr = [(int(words[4 * i]) & 0xff, int(words[4 * i]) >> 8, int(words[4 * i + 1]), int(words[4 * i + 2]))
-                 for i in range(n)]
+        instr, i = [], 0
+        while i < n:
+            op, dst = int(words[4 * i]) & 0xff, int(words[4 * i]) >> 8
+            if op in (5, 6):
+                assert i + 1 < n and int(words[4 * i + 4]) & 0xff == 7, "fused instruction without its extension entry"
+                instr.append((op, dst, int(words[4 * i + 1]), int(words[4 * i + 2]), int(words[4 * i + 3]),
+                              int(words[4 * i + 5])))
+                i += 2
+            else:
+                instr.append((op, dst, int(words[4 * i + 1]), int(words[4 * i + 2])))
+                i += 1
         return instr, res.value, [(int(der[2 * i]), int(der[2 * i + 1])) for i in range(nd.value)]
 
     def free(self):

@@ -273,10 +273,11 @@ int b2_quotient_program_free(b2_handle_t program);
 int b2_quotient_program_info(b2_handle_t program, uint32_t* n_instr, uint32_t* n_slots, uint32_t* n_mul,
                              uint32_t* n_addsub);
 
-/* Diagnostic: the lowered program (4 words per instruction: op | dst_slot << 8, operand a, operand b, 0;
+/* Diagnostic: the lowered program (4 words per instruction: op | dst_slot << 8, operand a, operand b, operand c;
  * operand word = kind << 28 | rotation << 20 | index with kind 0 constant, 1 slot, 2 column (fixed, advice,
  * instance, aux concatenated), 3 challenge (derived powers appended after the caller's), 4 coset x; ops
- * 0 add, 1 sub, 2 mul, 3 neg, 4 copy) and the (challenge, power) pairs of the derived challenge entries.
+ * 0 add, 1 sub, 2 mul, 3 neg, 4 copy, 5 / 6 the fused a * b +- c * d whose fourth operand d is word a of the
+ * following entry (op 7, never executed by itself)) and the (challenge, power) pairs of the derived challenge entries.
  * Lets the host-side lowering be checked without a GPU. */
 int b2_quotient_program_dump(b2_handle_t program, uint32_t* instr_words, size_t instr_capacity, uint32_t* result_word,
                              uint32_t* derived_pairs, size_t derived_capacity, uint32_t* n_derived);

@@ -161,12 +161,16 @@ def test_large_random_program_spot_rows(gpu):
                 return ch[idx]
             return x0 * pow(step, row, R) % R
 
-        for op, dst, a, b in instr:
+        for ins in instr:
+            op, dst, a, b = ins[:4]
             va = fetch(a)
             if op == 3:
                 r = (-va) % R
             elif op == 4:
                 r = va
+            elif op in (5, 6):                         # fused a * b +- c * d
+                vc, vd = fetch(ins[4]), fetch(ins[5])
+                r = (va * fetch(b) + (vc * vd if op == 5 else -vc * vd)) % R
             else:
                 vb = fetch(b)
                 r = (va * vb) % R if op == 2 else ((va + vb) % R if op == 0 else (va - vb) % R)

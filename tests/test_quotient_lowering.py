@@ -46,12 +46,16 @@ def interpret(prog, rotations, constants, columns, challenges, rows, rot_scale, 
                 return ch[idx]
             return x
 
-        for op, dst, a, b in instr:
+        for ins in instr:
+            op, dst, a, b = ins[:4]
             va = fetch(a)
             if op == 3:
                 r = (-va) % R
             elif op == 4:
                 r = va
+            elif op in (5, 6):                         # fused a * b +- c * d
+                vc, vd = fetch(ins[4]), fetch(ins[5])
+                r = (va * fetch(b) + (vc * vd if op == 5 else -vc * vd)) % R
             else:
                 vb = fetch(b)
                 r = (va * vb) % R if op == 2 else ((va + vb) % R if op == 0 else (va - vb) % R)
@@ -73,6 +77,8 @@ def test_lowered_program_matches_oracle(fx):
     prog = Ev.program(len(fx["perm_z"]), [len(l["z"]) for l in fx["lookups_lagrange"]], len(fx["shuffle_z"]))
     info = prog.info()
     assert info["n_slots"] < info["n_instr"] and info["n_mul"] > 0
+    ops = [ins[0] for ins in prog.dump()[0]]
+    assert ops.count(5) > 0 and ops.count(6) > 0, "the fixture must exercise both fused forms (a*b + c*d, a*b - c*d)"
     d = fx["domain"]
     aux = [cz["l0"], cz["l_last"], cz["l_active_row"]] + cz["sigma"] + cz["perm_z"]
     for lk in cz["lookups"]:

@@ -119,7 +119,7 @@ def main():
     wide, modmul = ctypes.c_double(), ctypes.c_double()
     _lib.check(_lib.lib().b2_imad_probe(ctypes.byref(wide), ctypes.byref(modmul)))
     instr, _, _ = prog.dump()
-    col_reads = sum(1 for op, dst, a, b in instr for w in ((a, b) if op < 3 else (a,)) if (w >> 28) == 2)
+    col_reads = sum(1 for ins in instr for w in (ins[2:] if ins[0] not in (3, 4) else ins[2:3]) if (w >> 28) == 2)
     muls = info["n_mul"] + 2   # + coset point + vanishing scale
     res = {
         "k": args.k, "extended_k": ext_k, "rows": rows, "columns_resident": ncols,
