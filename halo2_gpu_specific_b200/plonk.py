@@ -874,17 +874,25 @@ class ResidentEngine:
         # witness only, not on any challenge.  So the columns go up in groups, and while group g + 1 crosses PCIe the
         # side stream turns group g into coefficient form and into its coset evaluations (lagrange_to_coeff and
         # evaluate_h_blocks pick them up from self._early).
+        return block, self.put_columns_with_early_transforms(block, host, 0, count, bits, range(nc))
+
+    def put_columns_with_early_transforms(self, block: DevBlock, host: np.ndarray, lo: int, hi: int, bits: int,
+                                          coset_ids) -> List[Point]:
+        """columns [lo, hi) of `host` -> the same columns of `block`, committed on the way in, in groups; behind every
+        group the side stream makes its coefficient forms and its evaluations on the cosets `coset_ids`.  Registers the
+        results under the block: lagrange_to_coeff and evaluate_h_blocks use what is there and compute the rest."""
+        count, n = block.count, block.n
         coeff = self.alloc(count)
-        cosets = [self.alloc(count) for _ in range(nc)]
-        step = max(2, count // 8)
+        cosets = {c: self.alloc(count) for c in coset_ids}
+        step = max(2, (hi - lo + 7) // 8)
         points: List[Point] = []
-        for lo in range(0, count, step):
-            hi = min(count, lo + step)
-            points += self._commit(self.params.g_lagrange, host.ctypes.data + lo * n * 32, self.sub_block(block, lo, hi),
-                                   bits, False)
-            self._early_transforms(block, coeff, cosets, lo, hi)
-        self._early[block.ptr] = (coeff, cosets)
-        return block, points
+        for g_lo in range(lo, hi, step):
+            g_hi = min(hi, g_lo + step)
+            points += self._commit(self.params.g_lagrange, host.ctypes.data + g_lo * n * 32,
+                                   self.sub_block(block, g_lo, g_hi), bits, False)
+            self._early_transforms(block, coeff, cosets, g_lo, g_hi)
+        self._early[block.ptr] = {"coeff": coeff, "lo": lo, "hi": hi, "cosets": cosets}
+        return points
 
     EARLY_TRANSFORMS = True                  # class switch (the sharded engines divide the columns differently)
     EARLY_TRANSFORM_BYTES = 64 << 30         # HBM the early coefficient forms + coset evaluations may take
@@ -918,7 +926,7 @@ class ResidentEngine:
         d.in_, d.out = block.ptr + off, coeff.ptr + off
         d.stream = st
         check(lib().b2_ntt_exec(ctypes.byref(d)))
-        for c, cos in enumerate(cosets):
+        for c, cos in cosets.items():
             g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
             coeff_to_coset_dev(dm, coeff.ptr + off, hi - lo, g_c, cos.ptr + off, stream=st)
 
@@ -935,21 +943,34 @@ class ResidentEngine:
     def lagrange_to_coeff(self, block: DevBlock) -> DevBlock:
         import ctypes
         from ._lib import NttDesc, check, lib
-        early = self._early.get(block.ptr)
-        if early is not None and early[0].count == block.count:
-            # the coefficient forms were made while the columns were uploaded (put_and_commit_lagrange)
+        cb = block.n * 32
+        early, e_lo, e_hi = None, 0, 0
+        for base, e in self._early.items():
+            # `block` may be the registered block itself or a run of its columns (the sharded engines pass their share)
+            if base <= block.ptr < base + e["coeff"].count * cb and (block.ptr - base) % cb == 0:
+                first = (block.ptr - base) // cb
+                e_lo, e_hi = max(e["lo"], first) - first, min(e["hi"], first + block.count) - first
+                if e_hi > e_lo:
+                    early = (e, first)
+                break
+        runs = [(0, block.count)]
+        if early is not None:
+            # these coefficient forms were made while the columns were uploaded (put_columns_with_early_transforms)
+            e, first = early
             self._drain_side()
-            check(lib().b2_memcpy_d2d(ctypes.c_void_p(block.ptr), ctypes.c_void_p(early[0].ptr),
-                                      block.count * block.n * 32))
-            return block
-        if block.count:
-            dm = self.domain
+            check(lib().b2_memcpy_d2d(ctypes.c_void_p(block.ptr + e_lo * cb),
+                                      ctypes.c_void_p(e["coeff"].ptr + (first + e_lo) * cb), (e_hi - e_lo) * cb))
+            runs = [(0, e_lo), (e_hi, block.count)]
+        dm = self.domain
+        for lo, hi in runs:
+            if hi <= lo:
+                continue
             d = NttDesc()
             d.log_n, d.location = dm.k, 1
             d.omega, d.divisor = dm.omega_inv.ctypes.data, dm.ifft_divisor.ctypes.data
             d.n_in = d.n_out = d.in_stride = d.out_stride = dm.n
-            d.columns = block.count
-            d.in_ = d.out = block.ptr
+            d.columns = hi - lo
+            d.in_ = d.out = block.ptr + lo * cb
             check(lib().b2_ntt_exec(ctypes.byref(d)))
         return block
 
@@ -1088,23 +1109,35 @@ class ResidentEngine:
         early = self._early.get(advice.ptr)        # the advice polynomials' coset evaluations may exist already
         if early is not None:
             self._drain_side()
-        witness = [b for b in (advice, instance, z_block, m_block) if b.count and not (b is advice and early)]
-        cos = {id(b): self.alloc(b.count) for b in witness}
+        witness = [b for b in (advice, instance, z_block, m_block) if b.count]
+        # (the advice block's coset evaluations live in the early buffers where those exist for the coset at hand)
+        cos = {id(b): self.alloc(b.count) for b in witness
+               if not (b is advice and early and all(c in early["cosets"] for c, _, _ in tasks))}
         hext = self._buffer(dm.extended_len())
         if partial:
             self._fr_vec(2, hext.ptr, hext.ptr, dm.extended_len(), hext.ptr)          # x - x: a zeroed buffer
         ptrs = lambda b: [cos[id(b)].ptr + i * n * 32 for i in range(b.count)] if b.count else []     # noqa: E731
-        current = None
+        current, adv_cos = None, None
         for c, row_begin, row_count in tasks:
             if c != current:                           # tasks of one coset are adjacent (coset-major order)
                 g_c = dm._zeta * pow(dm._ext_omega, c, R) % R
                 for b in witness:
+                    if b is advice and early and c in early["cosets"]:
+                        # columns [lo, hi) of this coset were evaluated during the upload; the others (a sharded
+                        # engine's peers uploaded them) are computed now, into the same buffer
+                        adv_cos = early["cosets"][c]
+                        for r_lo, r_hi in ((0, early["lo"]), (early["hi"], b.count)):
+                            if r_hi > r_lo:
+                                coeff_to_coset_dev(dm, b.ptr + r_lo * n * 32, r_hi - r_lo, g_c, adv_cos.ptr + r_lo * n * 32)
+                        continue
+                    if b is advice:
+                        adv_cos = cos[id(b)]
                     coeff_to_coset_dev(dm, b.ptr, b.count, g_c, cos[id(b)].ptr)
                 current = c
             kc = key_cosets[c]
             kp = [kc.ptr + i * n * 32 for i in range(kc.count)]
             zp, mp = ptrs(z_block), ptrs(m_block)
-            ap = [early[1][c].ptr + i * n * 32 for i in range(advice.count)] if early else ptrs(advice)
+            ap = [adv_cos.ptr + i * n * 32 for i in range(advice.count)] if advice.count else []
             aux = kp[F + S:F + S + 3] + kp[F:F + S] + zp[:n_perm]
             pos = n_perm
             for li, cnt in enumerate(lookup_z_counts):

@@ -195,6 +195,12 @@ class ShardedQuotient:
     all-reduce of disjoint supports: every row is written by exactly one rank, so no limb ever carries) and every
     rank brings the sum back to the h(X) pieces.  The engine supplies evaluate_h_blocks(..., tasks=, combine=)."""
 
+    def early_coset_ids(self):
+        """the cosets this rank evaluates rows of (what its early transforms of the advice share are good for)"""
+        rank, world = parallel.world()
+        dm = self.domain
+        return [c for c, _, _ in parallel.quotient_tasks(1 << (dm.extended_k - dm.k), dm.n, world, rank)]
+
     def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
                           y, beta, gamma, theta):
         rank, world = parallel.world()
@@ -234,9 +240,19 @@ class _ResidentCollectives:
         from ._lib import B2_ERR_ARG, B2Error
         if not (host.flags.c_contiguous and host.dtype == np.uint64 and host.ndim == 3):
             raise B2Error(B2_ERR_ARG, "expected a C-contiguous uint64 (columns, n, 4) array")
+        bits = 0xFFFFFFFF if max_bits is None else max_bits
+        dm = self.domain
+        nc = 1 << (dm.extended_k - dm.k)
+        ids = sorted(set(self.early_coset_ids())) if hasattr(self, "early_coset_ids") else list(range(nc))
+        if self.EARLY_SHARE_TRANSFORMS and hi - lo >= 4 and (len(ids) + 1) * block.count * dm.n * 32 <= self.EARLY_TRANSFORM_BYTES:
+            # the rank's link is busy for as long as its share is on the way and its multiplier idles: the coefficient
+            # forms of the share (what lagrange_to_coeff would make later) and the share's evaluations on the cosets this
+            # rank will work on in evaluate_h are made behind the upload (ResidentEngine.put_columns_with_early_transforms)
+            return self.put_columns_with_early_transforms(block, host, lo, hi, bits, ids)
         own = self.sub_block(block, lo, hi)
-        return self._commit(self.params.g_lagrange, host[lo:hi].ctypes.data, own,
-                            0xFFFFFFFF if max_bits is None else max_bits, False)
+        return self._commit(self.params.g_lagrange, host[lo:hi].ctypes.data, own, bits, False)
+
+    EARLY_SHARE_TRANSFORMS = True
 
     def all_reduce_rows(self, hext) -> None:
         import torch.distributed as dist

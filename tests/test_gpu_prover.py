@@ -471,3 +471,39 @@ def test_early_advice_transforms_with_two_circuit_instances(gpu):
         assert HP.create_proof_multi(params, pk, advs(), insts, HP.SeededRng(11), engine=host) == want
     finally:
         params.free()
+
+
+def test_early_transforms_of_a_column_share(gpu):
+    """what a rank of the sharded prover does with its share of the advice columns (put_share_and_commit: groups of
+    columns committed on the way in, coefficient forms and coset evaluations of THOSE columns made behind the upload),
+    on one GPU: columns [16, 40) go that way, the others arrive plainly (as a peer's would); lagrange_to_coeff and
+    evaluate_h_blocks must combine the early results with what they compute themselves -- same proof bytes"""
+    from oracle import cref
+    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngineQ
+    k = 8
+    cs, ocs, fixed, advice, public, mapping = _zk_shape(k, 4, lambda a: cref.to_mont(0, a))
+    params = h2.Params.unsafe_setup(k, S_TOXIC)
+    try:
+        pk = HP.keygen(params, cs, fixed, mapping)
+        plain = HP.ResidentEngine(params, pk.vk.domain)
+        plain.EARLY_TRANSFORMS = False
+        want = HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(21), engine=plain)
+        plain.free()
+        eng = ShardedResidentEngineQ(params, pk.vk.domain)          # no process group: world = 1
+        lo, hi = 16, 40
+
+        def put(host, max_bits):
+            bits = 0xFFFFFFFF if max_bits is None else max_bits
+            block = eng.alloc(host.shape[0])
+            mid = eng.put_share_and_commit(block, host, lo, hi, max_bits)
+            assert block.ptr in eng._early and (eng._early[block.ptr]["lo"], eng._early[block.ptr]["hi"]) == (lo, hi)
+            first = eng._commit(params.g_lagrange, host[:lo].ctypes.data, eng.sub_block(block, 0, lo), bits, False)
+            last = eng._commit(params.g_lagrange, host[hi:].ctypes.data, eng.sub_block(block, hi, host.shape[0]), bits, False)
+            return block, first + mid + last
+
+        eng.put_and_commit_lagrange = put
+        for _ in range(2):
+            assert HP.create_proof(params, pk, advice.copy(), [public], HP.SeededRng(21), engine=eng) == want
+        eng.free()
+    finally:
+        params.free()
