@@ -209,8 +209,6 @@ int dev_get(DeviceCtx** out) {
             const int tw_extra = (64 << NTT_TWSM) + 16;
             CK(cudaFuncSetAttribute(ntt_pass_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_cluster2_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            CK(cudaFuncSetAttribute(ntt_pass_cluster2_v5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_cluster4_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             CK(cudaFuncSetAttribute(ntt_pass_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024 + tw_extra));
             CK(cudaFuncSetAttribute(ntt_pass_cluster2_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024 + tw_extra));
@@ -862,10 +860,10 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
         const uint32_t mloc = a.m - a.cl_log;
         const uint32_t threads = std::max(32u, 1u << (mloc >= NTT_RMAX ? mloc - NTT_RMAX : 0));
         // kernel variant (see ntt.cuh): 0 = strict butterflies, twiddles through L1; 1 = lazy; 2 = lazy + TMA-staged
-        // shared-memory twiddles; 3 = shared-memory twiddles only; 4 = lazy at 5 CTAs per SM (cluster-of-2 tiles only)
+        // shared-memory twiddles; 3 = shared-memory twiddles only
         static const int variant_env = getenv("B2_NTT_VARIANT") ? atoi(getenv("B2_NTT_VARIANT")) : NTT_DEFAULT_VARIANT;
         int variant = use_shoup ? variant_env : 0;
-        if ((variant == 4 || variant == 5) && (a.cl_log != 1 || threads > 128)) variant = 1;
+        if (variant < 0 || variant > 3) variant = 1;
         const bool tw_sm = (variant == 2 || variant == 3);
         const size_t smem = ((size_t)32 << mloc) + (tw_sm ? ((size_t)64 << NTT_TWSM) + 16 : 0);
         const uint64_t lines = N >> a.m;
@@ -905,10 +903,6 @@ int ntt_run_dev(Lane& ctx, NttPlan* pl, const void* d_in, uint64_t in_stride, ui
                 else if (use_shoup && variant == 3)
                     le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v3_kernel, b)
                                          : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_v3_kernel, b);
-                else if (use_shoup && variant == 4)
-                    le = cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v4_kernel, b);
-                else if (use_shoup && variant == 5)
-                    le = cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_v5_kernel, b);
                 else if (use_shoup)
                     le = (a.cl_log == 1) ? cudaLaunchKernelEx(&cfg, ntt_pass_cluster2_kernel, b)
                                          : cudaLaunchKernelEx(&cfg, ntt_pass_cluster4_kernel, b);

@@ -473,7 +473,9 @@ __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_kernel(con
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_kernel(const NttPassArgs a) { ntt_pass_impl<2, true>(a); }
 // Variants selected by B2_NTT_VARIANT (A/B measurements; the default is chosen in ntt_run_dev):
 //   1: lazy butterflies   2: lazy + twiddles of stages 1..8 staged into shared memory by TMA bulk copies
-//   3: shared-memory twiddles only   4 / 5: lazy, 5 / 6 CTAs per SM (<= 102 / 85 registers; 2^10-point CTA tiles only)
+//   3: shared-memory twiddles only
+// (register-capped builds of variant 1 -- 5 / 6 CTAs per SM at <= 102 / 85 registers, 3 / 2 CTAs at 156 / 180 -- were
+// measured in round 2 and removed: throughput follows the warp count up to 4 CTAs and spills beyond, profiles/r2_ncu_summary.md)
 constexpr int NTT_TWSM = 8;
 #ifndef NTT_DEFAULT_VARIANT
 #define NTT_DEFAULT_VARIANT 1
@@ -487,14 +489,6 @@ __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v2_kernel(
 __global__ void __launch_bounds__(512) ntt_pass_v3_kernel(const NttPassArgs a) { ntt_pass_impl<0, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster2_v3_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, false, NTT_TWSM>(a); }
 __global__ void __launch_bounds__(256, NTT_CL_MINB) ntt_pass_cluster4_v3_kernel(const NttPassArgs a) { ntt_pass_impl<2, true, false, NTT_TWSM>(a); }
-#ifndef NTT_V4_MINB
-#define NTT_V4_MINB 5
-#endif
-#ifndef NTT_V5_MINB
-#define NTT_V5_MINB 6
-#endif
-__global__ void __launch_bounds__(128, NTT_V4_MINB) ntt_pass_cluster2_v4_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
-__global__ void __launch_bounds__(128, NTT_V5_MINB) ntt_pass_cluster2_v5_kernel(const NttPassArgs a) { ntt_pass_impl<1, true, true, 0>(a); }
 // Montgomery-twiddle variants (B2_NTT_SHOUP=0: A/B measurements)
 __global__ void __launch_bounds__(512) ntt_pass_mont_kernel(const NttPassArgs a) { ntt_pass_impl<0, false>(a); }
 __global__ void __launch_bounds__(256) ntt_pass_mont_cluster2_kernel(const NttPassArgs a) { ntt_pass_impl<1, false>(a); }
