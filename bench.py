@@ -1098,6 +1098,7 @@ def bench_sharded_proof(args, torch, dist, _lib, h2, rank, world):
                 dist.all_reduce(d, op=dist.ReduceOp.MAX)
                 if best is None or float(d.item()) < best:
                     best, phases = float(d.item()), tm
+            by_range = getattr(eng, "range_commits", 0) // 3          # warm-up + two timed proofs
             eng.free()
             alone_s, same, alone_err = None, True, None
             if rank == 0:
@@ -1119,6 +1120,7 @@ def bench_sharded_proof(args, torch, dist, _lib, h2, rank, world):
             out = {"metric": f"create_proof wall time, zkWasm-shaped circuit at k={k} (GWC), divided over {world} GPUs",
                    "value": best, "unit": "s", "higher_is_better": False, "n_ranks": world, "single_gpu_s": alone_s,
                    "bytes_equal_on_all_ranks_and_to_single_gpu": same, "phases_s": phases, "proof_bytes": len(proof),
+                   "columns_committed_by_point_range": by_range,
                    "api": "halo2_gpu_specific_b200.prover_sharded (ShardedResidentEngineQ), one process per GPU, NCCL"}
             if alone_err:
                 out["single_gpu_error"] = alone_err

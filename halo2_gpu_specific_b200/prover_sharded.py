@@ -10,13 +10,18 @@ pool does, plonk/prover.rs:293-299: no collective at all") -- and the resulting 
 all-gathered so that each rank can hash all of them.  The witness itself is uploaded by every rank over its own PCIe
 link and stays resident there, because the z columns and evaluate_h need all of it on every rank.
 
-Status: the sharding and gather logic is validated on CPU with gloo (tests/test_parallel_cpu.py: proof bytes of a
-2- and 3-rank run equal the single-process oracle proof) and on two B200s over NCCL (tools/sharded_proof_check.py,
-profiles/r1_sharded_prover_2gpu.json: every rank's bytes equal the single-GPU proof; that run gathered the points with
-all_gather_object, the fixed-size tensor gather that replaced it afterwards is covered with gloo).  At the size that fitted the
-remaining GPU budget (k = 16, an 12 ms proof) the pickled all-gathers cost more than the divided MSMs save; measuring
-it at zkWasm scale is round-2 work, and so is running the coset split of evaluate_h inside the prover on GPUs
-(`ShardedQuotient` below: its division logic is covered on CPU with gloo, its device methods have not run yet).
+Blocks with fewer columns than the ranks can share evenly -- the instance polynomial, the vanishing argument's random
+polynomial, the h(X) pieces, the multiopen witness polynomials: the "few big MSMs" of SURVEY 8(e) -- are divided the
+other way, option (i) there and what gpu_multiexp_bound does inside one process (arithmetic.rs:413-440): every rank
+multiplies the point range [rank * ceil(n / N), ...) of EVERY column of the block, the Jacobian partials (96 bytes per
+column and rank) are all-gathered in one collective and summed (`commit_by_point_range`; the choice between the two
+divisions is a cost model of the measured MSM times, `_by_point_range`).
+
+Status: the sharding and gather logic of both divisions is validated on CPU with gloo (tests/test_parallel_cpu.py:
+proof bytes of a 2- and 3-rank run equal the single-process oracle proof) and on 2, 4 and 8 B200s over NCCL
+(tools/sharded_proof_check.py, profiles/r2_sharded_proof_*.json: every rank's bytes equal the single-GPU proof at
+k = 18 .. 22, coset split of evaluate_h included); `bench.py` at N > 1 proves a k = 18 circuit with all ranks together
+and compares every rank's bytes with the single-GPU proof (`sharded_create_proof`), which is how the driver sees it.
 """
 from __future__ import annotations
 
@@ -86,9 +91,58 @@ class ShardedCommits:
                 self._inside = prev
         return scope()
 
+    # -- few big MSMs: divided by point range (SURVEY 8(e) option (i); arithmetic.rs:413-440)
+    RANGE_SHARD: Optional[bool] = None      # None: by the cost model below; True / False: always / never (tests, A/B runs)
+
+    @staticmethod
+    def _msm_ms(points: int) -> float:
+        """one MSM of `points` full-width scalars on one B200, ms: fit of the measured sweep (2^18: 1.20, 2^20: 3.22,
+        2^22: 10.57; profiles/r2_bench_1gpu_final.json strong_scaling) -- a fixed sort / bucket-reduction part plus the
+        point additions"""
+        return 0.6 + 10.0 * points / (1 << 22)
+
+    def _by_point_range(self, count: int, max_bits: int) -> bool:
+        """divide the `count` columns of a block by point range instead of by column?  Column-parallel costs
+        ceil(count / N) whole MSMs on the busiest rank, the range division `count` MSMs of n / N points on every rank:
+        it wins when ranks would idle (count < N: one instance column, the random polynomial, h pieces on 8 ranks) and
+        loses when the fixed part of an MSM, paid `count` times, outweighs the idle ranks.  Bounded commits stay
+        column-parallel (their bound check lives in the batch call)."""
+        _, world = parallel.world()
+        if world == 1 or count == 0 or max_bits < _fr.NUM_BITS or not hasattr(self, "msm_partials"):
+            return False
+        if self.RANGE_SHARD is not None:
+            return bool(self.RANGE_SHARD)
+        n = self.domain.n
+        return count * self._msm_ms(-(-n // world)) < -(-count // world) * self._msm_ms(n)
+
+    def commit_by_point_range(self, basis: str, block, max_bits: int = _fr.NUM_BITS) -> List[Point]:
+        """every column of `block` against params.<basis> ("g" or "g_lagrange") with the POINTS divided over the ranks:
+        rank r multiplies scalars and bases [r * ceil(n / N), (r + 1) * ceil(n / N)) of every column
+        (parallel.shard_range, the reference's part_len rule), ONE all-gather moves the N x count Jacobian partials
+        (rank-major, 96 bytes each) and every rank adds them up.  The engine supplies msm_partials (block, range ->
+        (count, 12) int64 tensor of un-normalised Jacobian points) and sum_partials ((N * count, 12) rank-major ->
+        points)."""
+        d = parallel._dist()
+        import torch
+        rank, world = parallel.world()
+        count, n = self.block_count(block), self.domain.n
+        lo, hi = parallel.shard_range(n, world, rank)
+        with self._local():
+            part = self.msm_partials(basis, block, lo, hi, max_bits)
+        if tuple(part.shape) != (count, 12) or part.dtype != torch.int64:
+            raise ValueError("msm_partials must return a (count, 12) int64 tensor")
+        gathered = torch.empty((world * count, 12), dtype=torch.int64, device=part.device)
+        self.before_collective()
+        d.all_gather_into_tensor(gathered, part.contiguous())
+        self.after_collective()
+        self.range_commits = getattr(self, "range_commits", 0) + count
+        return self.sum_partials(gathered, world, count)
+
     def commit_lagrange(self, block, max_bits: int = _fr.NUM_BITS) -> List[Point]:
         if self._inside:
             return super().commit_lagrange(block, max_bits)
+        if self._by_point_range(self.block_count(block), max_bits):
+            return self.commit_by_point_range("g_lagrange", block, max_bits)
         lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = super().commit_lagrange(self.sub_block(block, lo, hi), max_bits) if hi > lo else []
@@ -97,6 +151,8 @@ class ShardedCommits:
     def commit(self, block) -> List[Point]:
         if self._inside:
             return super().commit(block)
+        if self._by_point_range(self.block_count(block), _fr.NUM_BITS):
+            return self.commit_by_point_range("g", block)
         lo, hi = self._share(self.block_count(block))
         with self._local():
             pts = super().commit(self.sub_block(block, lo, hi)) if hi > lo else []
@@ -253,6 +309,37 @@ class _ResidentCollectives:
         return self._commit(self.params.g_lagrange, host[lo:hi].ctypes.data, own, bits, False)
 
     EARLY_SHARE_TRANSFORMS = True
+
+    def msm_partials(self, basis: str, block, lo: int, hi: int, max_bits: int):
+        """points [lo, hi) of every column of the resident `block` against the same range of params.<basis> (the window
+        table covers the whole SRS, b2_msm_dev takes the offset): one asynchronous MSM per column on the library's
+        lanes, results (Jacobian, not normalised) left in device memory for the all-gather"""
+        import ctypes
+        import torch
+        from ._lib import check, lib
+        srs = getattr(self.params, basis)
+        vp, L = ctypes.c_void_p, lib()
+        out = torch.empty((block.count, 12), dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        for i in range(block.count):
+            check(L.b2_msm_dev(srs.handle, lo, vp(block.ptr + (i * block.n + lo) * 32), hi - lo, int(max_bits),
+                               vp(out.data_ptr() + 96 * i), None))
+        return out
+
+    def sum_partials(self, gathered, world: int, count: int) -> List[Point]:
+        """(world * count, 12) rank-major partials on the device -> the `count` points: one launch
+        (b2_g1_sum_groups_dev), 96 bytes per column read back and normalised on the host as every commit entry does"""
+        import ctypes
+        import numpy as np
+        import torch
+        from ._lib import check, lib
+        from .plonk import _points
+        vp, L = ctypes.c_void_p, lib()
+        sums = torch.empty((count, 12), dtype=torch.int64, device=gathered.device)
+        check(L.b2_g1_sum_groups_dev(vp(gathered.data_ptr()), world, count, vp(sums.data_ptr()), None))
+        check(L.b2_synchronize())
+        host = np.ascontiguousarray(sums.cpu().numpy().view(np.uint64).reshape(count, 12))
+        check(L.b2_g1_normalize(vp(host.ctypes.data), count))
+        return _points(host)
 
     def all_reduce_rows(self, hext) -> None:
         import torch.distributed as dist

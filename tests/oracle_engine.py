@@ -184,6 +184,22 @@ class CosetQuotientDouble:
     def after_collective():
         pass
 
+    # -- what ShardedCommits.commit_by_point_range asks for: partial MSMs over a point range, and their sum
+    def msm_partials(self, basis, block, lo, hi, max_bits):
+        import torch
+        bases = getattr(self.p, basis)
+        out = np.zeros((block.shape[0], 12), dtype=np.uint64)
+        for i, col in enumerate(block):
+            out[i] = cref.best_multiexp(np.ascontiguousarray(col[lo:hi]), bases[lo:hi]) if hi > lo else \
+                o.g1_jacobian_encode(None)
+        self.partial_ranges = getattr(self, "partial_ranges", []) + [(lo, hi, block.shape[0])]
+        return torch.from_numpy(out.view(np.int64))
+
+    def sum_partials(self, gathered, world, count):
+        rows = gathered.numpy().view(np.uint64).reshape(world, count, 12)
+        return [o.g1_affine_decode(cref.jac_to_affine(cref.jac_sum(np.ascontiguousarray(rows[:, c]))))[0]
+                for c in range(count)]
+
     def put_share_and_commit(self, block, host, lo, hi, max_bits):
         """only this rank's columns are copied in: the others stay zero until exchange_columns delivers them"""
         block[lo:hi] = host[lo:hi]

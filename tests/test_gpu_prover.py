@@ -473,6 +473,40 @@ def test_early_advice_transforms_with_two_circuit_instances(gpu):
         params.free()
 
 
+def test_point_range_commit_pieces_on_one_gpu(gpu):
+    """the device halves of prover_sharded.ShardedCommits.commit_by_point_range (SURVEY 8(e) option (i)) without a
+    process group: the partial MSMs of every column over the three point ranges a 3-rank run would use
+    (msm_partials: b2_msm_dev at an offset into the window table), stacked rank-major as the all-gather leaves them,
+    summed in one launch (sum_partials: b2_g1_sum_groups_dev) -- equal to the whole-column commitments, for both bases,
+    with an empty range, a zero column and a column that leaves one rank an identity partial"""
+    import torch
+    from halo2_gpu_specific_b200 import parallel
+    from halo2_gpu_specific_b200.prover_sharded import ShardedResidentEngineQ
+    from oracle import cref
+    k = 11
+    n = 1 << k
+    oparams = PR.Params(k, S_TOXIC)
+    params = h2.Params(k, oparams.g, oparams.g_lagrange)
+    try:
+        eng = ShardedResidentEngineQ(params, h2.EvaluationDomain(5, k))
+        cols = np.stack([cref.random_fr_mont(n, 0x7A0 + i) for i in range(3)] + [np.zeros((n, 4), dtype=np.uint64)] * 2)
+        cols[4, 5] = enc([7])[0]                       # column 4: two lone scalars that fall into different ranks' ranges,
+        cols[4, n - 3] = enc([o.R_MOD - 1])[0]         # so one rank's partial of it is the identity
+        block = eng.put(np.ascontiguousarray(cols))
+        for basis, whole in (("g", eng.commit(block)), ("g_lagrange", eng.commit_lagrange(block))):
+            for world in (3, 1):
+                parts = [eng.msm_partials(basis, block, *parallel.shard_range(n, world, r), 254) for r in range(world)]
+                parts.append(eng.msm_partials(basis, block, n, n, 254))       # a rank beyond the data: identities
+                gathered = torch.cat(parts).contiguous()
+                assert eng.sum_partials(gathered, world + 1, block.count) == whole
+            assert whole[3] is None and whole[4] is not None
+        want = [oparams.commit(c) for c in [o.fr_decode(cols[0]), o.fr_decode(cols[4])]]
+        assert [eng.commit(block)[0], eng.commit(block)[4]] == want
+        eng.free()
+    finally:
+        params.free()
+
+
 def test_early_transforms_of_a_column_share(gpu):
     """what a rank of the sharded prover does with its share of the advice columns (put_share_and_commit: groups of
     columns committed on the way in, coefficient forms and coset evaluations of THOSE columns made behind the upload),

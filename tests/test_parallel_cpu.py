@@ -148,7 +148,7 @@ def test_coset_transform_shares_cover_every_polynomial_once():
                 assert len(shares) == 1
 
 
-def _prover_worker(rank, world, port, outdir):
+def _prover_worker(rank, world, port, outdir, range_shard=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
@@ -160,7 +160,7 @@ def _prover_worker(rank, world, port, outdir):
     from oracle_engine import CosetQuotientDouble, OracleEngine
 
     class ShardedOracleEngine(ShardedQuotient, ShardedCommits, CosetQuotientDouble, OracleEngine):
-        pass
+        RANGE_SHARD = range_shard      # None: the cost model (column-parallel at this size); True: every full-width block
 
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     k = 5
@@ -192,6 +192,7 @@ def _prover_worker(rank, world, port, outdir):
         out[gwc] = (HP.create_proof(hp, pk, adv.copy(), inst, HP.SeededRng(3), engine=eng, use_gwc=gwc), calls["msm"])
     np.save(os.path.join(outdir, f"proof_r{rank}.npy"), np.frombuffer(out[True][0] + out[False][0], dtype=np.uint8))
     np.save(os.path.join(outdir, f"msms_r{rank}.npy"), np.array([out[True][1], out[False][1]]))
+    np.save(os.path.join(outdir, f"ranges_r{rank}.npy"), np.array(getattr(eng, "partial_ranges", []), dtype=np.int64).reshape(-1, 3))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -206,7 +207,7 @@ def test_sharded_commit_prover_matches_single_process(tmp_path, world):
     from halo2_gpu_specific_b200.plonk import SeededRng
     from oracle import prover as PR
     port = _free_port()
-    mp.spawn(_prover_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_prover_worker, args=(world, port, str(tmp_path), False), nprocs=world, join=True)   # columns only
     fx = fxm.build(k=5, seed=11)
     oparams = PR.Params(5, 0x2B200B200B200B2001)
     opk = PR.keygen(oparams, fx["cs"], fx["fixed"], fx["mapping"])
@@ -221,6 +222,61 @@ def test_sharded_commit_prover_matches_single_process(tmp_path, world):
     total = np.sum(msms, axis=0)
     # GWC: 1 instance + 9 advice + 2 m + (2 + 3 + 1) z + 1 random + 4 h + 4 openings = 27 MSMs, divided, none duplicated
     assert total[0] == 27 and max(m[0] for m in msms) <= 27 // world + 7
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_range_sharded_commits_match_single_process(tmp_path, world):
+    """SURVEY 8(e) option (i) inside the prover (prover_sharded.ShardedCommits.commit_by_point_range): with the range
+    division forced for every full-width block, each rank multiplies its point range [r * ceil(n / N), ...) of every
+    column (arithmetic.rs:426 part_len rule), the partials are all-gathered rank-major and summed -- and the proof
+    bytes (GWC and SHPLONK) are still the single-process oracle prover's on every rank"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import plonk_fixture as fxm
+    from halo2_gpu_specific_b200 import parallel
+    from halo2_gpu_specific_b200.plonk import SeededRng
+    from oracle import prover as PR
+    mp.spawn(_prover_worker, args=(world, _free_port(), str(tmp_path), True), nprocs=world, join=True)
+    fx = fxm.build(k=5, seed=11)
+    oparams = PR.Params(5, 0x2B200B200B200B2001)
+    opk = PR.keygen(oparams, fx["cs"], fx["fixed"], fx["mapping"])
+    inst = [fx["instance"][0][:4]]
+    want = PR.create_proof(oparams, opk, fx["advice"], inst, SeededRng(3)) + \
+        PR.create_proof(oparams, opk, fx["advice"], inst, SeededRng(3), use_gwc=False)
+    for r in range(world):
+        assert np.load(os.path.join(str(tmp_path), f"proof_r{r}.npy")).tobytes() == want, f"rank {r}"
+        ranges = np.load(os.path.join(str(tmp_path), f"ranges_r{r}.npy"))
+        # the instance column, the random polynomial, the h pieces and the multiopen witnesses went by point range, and
+        # every call used this rank's range of the 32 points
+        assert len(ranges) >= 8 and {(int(a), int(b)) for a, b, _ in ranges} == {parallel.shard_range(32, world, r)}
+        assert sum(int(c) for _, _, c in ranges) >= 1 + 1 + 4 + 4
+
+
+def test_range_division_cost_model():
+    """_by_point_range: one column on several ranks goes by point range at proof sizes, blocks that divide evenly stay
+    column-parallel, and bounded commits (their bound check lives in the batch call) never take the range path"""
+    from halo2_gpu_specific_b200 import parallel
+    from halo2_gpu_specific_b200.prover_sharded import ShardedCommits
+
+    class E(ShardedCommits):
+        msm_partials = sum_partials = None
+
+        class domain:
+            n = 1 << 22
+
+    e = E()
+    saved = parallel.world
+    try:
+        for world, expect in ((1, {}), (2, {1: True, 2: False, 3: True, 4: False, 24: False}),
+                              (8, {1: True, 4: True, 8: False, 24: False, 64: False})):
+            parallel.world = lambda w=world: (0, w)
+            for count, by_range in expect.items():
+                assert e._by_point_range(count, 254) is by_range, (world, count)
+            assert e._by_point_range(1, 16) is False and e._by_point_range(0, 254) is False
+        parallel.world = lambda: (0, 8)
+        E.domain.n = 1 << 10            # small circuits: the fixed part of an MSM dominates, columns stay whole ... except
+        assert e._by_point_range(4, 254) is False and e._by_point_range(1, 254) is True    # ... when 7 ranks would idle
+    finally:
+        parallel.world = saved
 
 
 def _rng_worker(rank, world, port, outdir):

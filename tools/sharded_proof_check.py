@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--split-quotient", action="store_true",
                     help="also divide evaluate_h by cosets (ShardedResidentEngineQ)")
     ap.add_argument("--reps", type=int, default=3)
+    ap.add_argument("--range-shard", default="auto", choices=["auto", "on", "off"],
+                    help="few-column blocks (instance, random polynomial, h pieces, multiopen witnesses) divided by point "
+                         "range: by the cost model / always / never (ShardedCommits.RANGE_SHARD)")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,6 +70,7 @@ def main():
     del advice, fixed
     advice = pinned
     eng = (ShardedResidentEngineQ if a.split_quotient else ShardedResidentEngine)(params, pk.vk.domain)
+    eng.RANGE_SHARD = {"auto": None, "on": True, "off": False}[a.range_shard]
     from halo2_gpu_specific_b200 import prover_sharded as PS
     # warm-up through the public multi-rank entry: rank 0's OS seed broadcast, BLAKE2b stream, bytes compared across ranks
     PS.create_proof(params, pk, advice, public, None, engine=eng)
@@ -85,6 +89,7 @@ def main():
             d = float(t.item())
         if dt is None or d < dt:
             dt, phases = d, tm
+    range_commits = getattr(eng, "range_commits", 0)
     eng.free()
     ok = True
     alone_s = None
@@ -108,7 +113,8 @@ def main():
         ok = ok and all(g == proof for g in gathered)
     if rank == 0:
         print(json.dumps({"check": f"sharded create_proof, {a.circuit} circuit, quotient split: {a.split_quotient}", "k": a.k,
-                          "n_gpus": world,
+                          "n_gpus": world, "range_shard": a.range_shard,
+                          "columns_committed_by_point_range": range_commits // (a.reps + 1),
                           "bytes_equal_on_all_ranks_and_to_single_gpu": bool(ok), "sharded_s": dt, "single_gpu_s": alone_s,
                           "sharded_phases_s": phases, "single_gpu_phases_s": alone_phases, "reps": a.reps,
                           "rng_sync_check": "warm-up proof through prover_sharded.create_proof (broadcast seed, "
