@@ -49,7 +49,7 @@ SYMBOLS = [
     "b2_coeff_to_extended", "b2_extended_to_coeff", "b2_divide_by_vanishing_poly", "b2_msm_and_ifft",
     "b2_commit_batch", "b2_commit_batch_resident", "b2_host_alloc", "b2_host_free", "b2_host_register", "b2_host_unregister", "b2_dev_alloc", "b2_dev_free", "b2_memcpy_h2d",
     "b2_memcpy_d2h", "b2_field_vec", "b2_imad_probe", "b2_shoup_probe", "b2_mul_probe", "b2_pipe_probe", "b2_msm_async", "b2_msm_wait", "b2_logup_multiplicity_dev", "b2_eval_polynomials_dev", "b2_dfma_probe", "b2_mixed_probe", "b2_affine_batch_probe", "b2_last_timing", "b2_last_msm_phases", "b2_msm_config",
-    "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_dump", "b2_quotient_eval",
+    "b2_quotient_program_create", "b2_quotient_program_free", "b2_quotient_program_info", "b2_quotient_program_slot_classes", "b2_quotient_program_dump", "b2_quotient_eval",
     "b2_g1_decompress", "b2_g1_compress", "b2_srs_register_compressed", "b2_srs_read_compressed",
     "b2_eval_polynomial", "b2_eval_polynomial_dev", "b2_kate_division", "b2_kate_division_dev", "b2_poly_combine", "b2_poly_combine_dev", "b2_witness_file_columns", "b2_commit_witness_file",
     "b2_batch_invert", "b2_batch_invert_dev", "b2_prefix_scan", "b2_prefix_scan_dev", "b2_fr_vec_dev",
@@ -124,6 +124,7 @@ def lib() -> ctypes.CDLL:
         L.b2_quotient_program_create.argtypes = [vp, ctypes.POINTER(u64)]
         L.b2_quotient_program_free.argtypes = [u64]
         L.b2_quotient_program_info.argtypes = [u64] + [ctypes.POINTER(u32)] * 4
+        L.b2_quotient_program_slot_classes.argtypes = [u64] + [ctypes.POINTER(u32)] * 2
         L.b2_quotient_eval.argtypes = [u64, vp]
         L.b2_g1_decompress.argtypes = [vp, sz, u32, vp]
         L.b2_g1_compress.argtypes = [vp, sz, u32, vp]

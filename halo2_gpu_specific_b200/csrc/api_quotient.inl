@@ -10,15 +10,28 @@
 //     at evaluation time, evaluation.rs:205-211);
 //   * instructions whose value never reaches `result` are dropped;
 //   * intermediates get shared-memory slots from their live ranges (a slot is recycled after
-//     the last read of its value, and a destination may reuse the slot of its own operand).
+//     the last read of its value, and a destination may reuse the slot of its own operand);
+//   * when the live width would cost resident CTAs (more than Q_SHARED_TARGET = 7 slots), the values
+//     with the longest live ranges -- sub-expressions a circuit shares between gates that sit far
+//     apart in its gate list -- move to a second slot class in global memory (one coalesced,
+//     L2-resident 32-byte round trip per use instead of 32 B x 128 threads of shared memory for
+//     most of the program); slot indices below n_slots_shared are shared memory, the rest global.
 
 namespace {
+
+constexpr size_t Q_SMEM_LIMIT = 200 * 1024;
+// Shared-memory slots a program may use before long-lived values go to the global class: a slot is 4 KB per CTA
+// (128 threads x 32 B) and the kernel's registers (70 - 72) allow 7 CTAs per SM, so up to 7 slots (7 x (28 + 1) KB of the
+// 228 KB) cost no occupancy; 17 slots are 3 CTAs per SM and 27 % of the kernel's throughput.
+constexpr uint32_t Q_SHARED_TARGET = 7;
+constexpr uint32_t Q_GLOBAL_MIN_LIVE = 24;   // instructions between definition and last use below which a value stays shared
 
 struct QProgram {
     // lowered program
     std::vector<QInstr> instr;
     uint32_t result = 0;
     uint32_t n_slots = 0, n_mul = 0, n_addsub = 0, n_fused = 0;   // n_mul counts both products of a fused instruction
+    uint32_t n_slots_shared = 0;       // slots [0, n_slots_shared) live in shared memory, [n_slots_shared, n_slots) in global
     bool uses_x = false;
     std::vector<int32_t> rotations;
     std::vector<uint64_t> constants;                         // 4 limbs each
@@ -252,59 +265,112 @@ struct QLower {
         for (uint32_t j = 0; j < kept.size(); j++)
             for (int k = 0; k < nops(node[kept[j]].op); k++) use(node[kept[j]].w[k], j);
         use(res, (uint32_t)kept.size());
-        // slot allocation
-        std::vector<uint32_t> slot_of(n_vreg, 0xffffffffu), free_slots;
-        uint32_t n_slots = 0;
+        // slot allocation, two classes: shared memory, and (hybrid programs only) global memory for long-lived values.
+        // allocate(glob, emit): runs the allocator over the schedule with the values flagged in `glob` in the global
+        // class; returns the two widths and, with emit, appends the instructions (global slot g is written as
+        // Q_GLOBAL_FLAG | g until the shared width is known, then renumbered to n_shared + g).
+        constexpr uint32_t Q_GLOBAL_FLAG = 1u << 19;
+        std::vector<uint32_t> slot_of(n_vreg, 0xffffffffu);
         auto remap = [&](uint32_t w) {
             return is_v(w) ? q_operand(QK_SLOT, slot_of[w & 0xfffffu], 0) : w;
         };
-        auto release = [&](uint32_t w, uint32_t at) {
-            if (!is_v(w)) return;
-            const uint32_t v = w & 0xfffffu;
-            if (last[v] == at && slot_of[v] != 0xffffffffu) {
-                free_slots.push_back(slot_of[v]);
-                last[v] = 0xffffffffu;   // released once, even when several operands name it
+        auto allocate = [&](const std::vector<char>& glob, bool emit, uint32_t* n_sh, uint32_t* n_gl) {
+            std::vector<uint32_t> lastc(last), free_sh, free_gl;
+            std::fill(slot_of.begin(), slot_of.end(), 0xffffffffu);
+            uint32_t ns = 0, ng = 0;
+            auto release = [&](uint32_t w, uint32_t at) {
+                if (!is_v(w)) return;
+                const uint32_t v = w & 0xfffffu;
+                if (lastc[v] == at && slot_of[v] != 0xffffffffu) {
+                    ((slot_of[v] & Q_GLOBAL_FLAG) ? free_gl : free_sh).push_back(slot_of[v]);
+                    lastc[v] = 0xffffffffu;   // released once, even when several operands name it
+                }
+            };
+            for (uint32_t j = 0; j < kept.size(); j++) {
+                const uint32_t dst = kept[j];
+                const Node& nd = node[dst];
+                const int n = nops(nd.op);
+                uint32_t m[4] = {0, 0, 0, 0};
+                for (int k = 0; k < n; k++) m[k] = remap(nd.w[k]);
+                for (int k = 0; k < n; k++) release(nd.w[k], j);
+                std::vector<uint32_t>& fr = glob[dst] ? free_gl : free_sh;
+                uint32_t s;
+                if (!fr.empty()) {
+                    s = fr.back();
+                    fr.pop_back();
+                } else {
+                    s = glob[dst] ? (Q_GLOBAL_FLAG | ng++) : ns++;
+                }
+                slot_of[dst] = s;
+                if (!emit) continue;
+                QInstr in;
+                in.op_dst = nd.op | (s << 8);
+                in.a = m[0];
+                in.b = m[1];
+                in.pad = m[2];
+                p.instr.push_back(in);
+                if (n == 4) {
+                    QInstr ext;
+                    ext.op_dst = Q_EXT;
+                    ext.a = m[3];
+                    ext.b = 0;
+                    ext.pad = 0;
+                    p.instr.push_back(ext);
+                    p.n_mul += 2;
+                    p.n_fused++;
+                } else if (nd.op == Q_MUL) {
+                    p.n_mul++;
+                } else if (nd.op == Q_ADD || nd.op == Q_SUB || nd.op == Q_NEG) {
+                    p.n_addsub++;
+                }
             }
+            *n_sh = ns;
+            *n_gl = ng;
         };
-        for (uint32_t j = 0; j < kept.size(); j++) {
-            const uint32_t dst = kept[j];
-            const Node& nd = node[dst];
-            const int n = nops(nd.op);
-            uint32_t m[4] = {0, 0, 0, 0};
-            for (int k = 0; k < n; k++) m[k] = remap(nd.w[k]);
-            for (int k = 0; k < n; k++) release(nd.w[k], j);
-            uint32_t s;
-            if (!free_slots.empty()) {
-                s = free_slots.back();
-                free_slots.pop_back();
-            } else {
-                s = n_slots++;
-            }
-            slot_of[dst] = s;
-            QInstr in;
-            in.op_dst = nd.op | (s << 8);
-            in.a = m[0];
-            in.b = m[1];
-            in.pad = m[2];
-            p.instr.push_back(in);
-            if (n == 4) {
-                QInstr ext;
-                ext.op_dst = Q_EXT;
-                ext.a = m[3];
-                ext.b = 0;
-                ext.pad = 0;
-                p.instr.push_back(ext);
-                p.n_mul += 2;
-                p.n_fused++;
-            } else if (nd.op == Q_MUL) {
-                p.n_mul++;
-            } else if (nd.op == Q_ADD || nd.op == Q_SUB || nd.op == Q_NEG) {
-                p.n_addsub++;
+        std::vector<char> glob(n_vreg, 0);
+        uint32_t n_sh = 0, n_gl = 0;
+        allocate(glob, false, &n_sh, &n_gl);
+        // B2_Q_HYBRID=0 keeps every slot in shared memory (A/B runs); default: hybrid when the width costs occupancy
+        const char* hybrid_env = getenv("B2_Q_HYBRID");     // read per program: tests lower the same circuit both ways
+        const bool hybrid = !(hybrid_env && atoi(hybrid_env) == 0);
+        if (hybrid && n_sh > Q_SHARED_TARGET) {
+            // candidates by decreasing live length; values read again within Q_GLOBAL_MIN_LIVE instructions stay shared
+            std::vector<uint32_t> def_pos(n_vreg, 0);
+            for (uint32_t j = 0; j < kept.size(); j++) def_pos[kept[j]] = j;
+            std::vector<uint32_t> cand;
+            for (uint32_t v : kept)
+                if (last[v] > def_pos[v] && last[v] - def_pos[v] >= Q_GLOBAL_MIN_LIVE) cand.push_back(v);
+            std::stable_sort(cand.begin(), cand.end(),
+                             [&](uint32_t x, uint32_t y) { return last[x] - def_pos[x] > last[y] - def_pos[y]; });
+            for (size_t i = 0; i < cand.size() && n_sh > Q_SHARED_TARGET; i++) {
+                glob[cand[i]] = 1;
+                allocate(glob, false, &n_sh, &n_gl);
             }
         }
+        allocate(glob, true, &n_sh, &n_gl);
+        if (n_sh >= Q_GLOBAL_FLAG || n_gl >= Q_GLOBAL_FLAG) { err = "too many live intermediates"; return false; }
+        if (n_sh == 0) n_sh = 1;
+        // global slot g -> n_sh + g, in destinations and operands
+        auto fix_slot = [&](uint32_t s) { return (s & Q_GLOBAL_FLAG) ? n_sh + (s & (Q_GLOBAL_FLAG - 1u)) : s; };
+        auto fix_operand = [&](uint32_t w) {
+            return (w >> 28) == QK_SLOT ? q_operand(QK_SLOT, fix_slot(w & 0xfffffu), 0) : w;
+        };
+        for (QInstr& in : p.instr) {
+            const uint32_t op = in.op_dst & 0xffu;
+            if (op == Q_EXT) {
+                in.a = fix_operand(in.a);
+                continue;
+            }
+            in.op_dst = op | (fix_slot(in.op_dst >> 8) << 8);
+            in.a = fix_operand(in.a);
+            if (op != Q_NEG && op != Q_COPY) in.b = fix_operand(in.b);
+            if (op >= Q_MUL2ADD) in.pad = fix_operand(in.pad);
+        }
+        for (uint32_t& so : slot_of)
+            if (so != 0xffffffffu) so = fix_slot(so);
         p.result = remap(res);
-        p.n_slots = n_slots ? n_slots : 1;
-        if (p.n_slots >= (1u << 20)) { err = "too many live intermediates"; return false; }
+        p.n_slots_shared = n_sh;
+        p.n_slots = n_sh + n_gl;
         return true;
     }
 };
@@ -316,8 +382,6 @@ int qprog_lookup(b2_handle_t h, QProgram** out) {
     *out = it->second;
     return B2_OK;
 }
-
-constexpr size_t Q_SMEM_LIMIT = 200 * 1024;
 
 }  // namespace
 
@@ -376,6 +440,15 @@ int b2_quotient_program_info(b2_handle_t program, uint32_t* n_instr, uint32_t* n
     if (n_slots) *n_slots = p->n_slots;
     if (n_mul) *n_mul = p->n_mul;
     if (n_addsub) *n_addsub = p->n_addsub;
+    return B2_OK;
+}
+
+int b2_quotient_program_slot_classes(b2_handle_t program, uint32_t* n_shared, uint32_t* n_global) {
+    QProgram* p;
+    int rc = qprog_lookup(program, &p);
+    if (rc) return rc;
+    if (n_shared) *n_shared = p->n_slots_shared;
+    if (n_global) *n_global = p->n_slots - p->n_slots_shared;
     return B2_OK;
 }
 
@@ -445,6 +518,8 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
             static bool attr_set[MAX_DEV] = {};
             if (!attr_set[dev]) {
                 CK(cudaFuncSetAttribute(quotient_eval_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)Q_SMEM_LIMIT));
+                CK(cudaFuncSetAttribute(quotient_eval_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)Q_SMEM_LIMIT));
                 attr_set[dev] = true;
             }
@@ -523,18 +598,33 @@ int b2_quotient_eval(b2_handle_t program, const b2_quotient_args* args) {
     a.out_offset = args->out_offset;
     a.row_begin = row_begin;
     a.row_count = row_count;
-    const size_t smem = (size_t)p->n_slots * Q_THREADS * 32;
+    a.n_slots_shared = p->n_slots_shared;
+    const size_t slot_bytes = (size_t)Q_THREADS * 32;
+    const size_t smem = (size_t)p->n_slots_shared * slot_bytes;
     const unsigned long long blocks_all = (row_count + Q_THREADS - 1) / Q_THREADS;
     const char* force_spill = getenv("B2_Q_FORCE_SPILL");   // tests: exercise the global-slot variant
     CK(cudaEventRecord(ctx->ev[12], st));
-    if (smem <= Q_SMEM_LIMIT && !(force_spill && atoi(force_spill) == 1)) {
-        LAUNCH(*ctx, quotient_eval_kernel<true>, (unsigned)blocks_all, Q_THREADS, smem, st, a);
-    } else {
-        // live width beyond shared memory: slots in a global scratch (L2-resident), grid-stride over rows
+    if (smem > Q_SMEM_LIMIT || (force_spill && atoi(force_spill) == 1)) {
+        // live width beyond shared memory: every slot in a global scratch (L2-resident), grid-stride over rows
         const unsigned blocks = (unsigned)std::min<unsigned long long>(blocks_all, (unsigned long long)ctx->sms * 8);
-        if ((rc = ctx->qspill.reserve((size_t)blocks * smem))) return rc;
+        if ((rc = ctx->qspill.reserve((size_t)blocks * p->n_slots * slot_bytes))) return rc;
         a.slot_spill = ctx->qspill.as<uint4>();
         LAUNCH(*ctx, quotient_eval_kernel<false>, blocks, Q_THREADS, 0, st, a);
+    } else if (p->n_slots == p->n_slots_shared) {
+        LAUNCH(*ctx, quotient_eval_kernel<true>, (unsigned)blocks_all, Q_THREADS, smem, st, a);
+    } else {
+        // two slot classes: the long-lived values of this program sit in a per-CTA global scratch, so the grid is one
+        // wave of resident CTAs striding over the rows (the scratch is CTAs x global slots x 4 KB, L2-resident)
+        auto* hybrid_kernel = quotient_eval_kernel<true, true>;
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hybrid_kernel, Q_THREADS, smem));
+        if (per_sm < 1) per_sm = 1;
+        const unsigned blocks =
+            (unsigned)std::min<unsigned long long>(blocks_all, (unsigned long long)ctx->sms * (unsigned)per_sm);
+        const size_t n_global = p->n_slots - p->n_slots_shared;
+        if ((rc = ctx->qspill.reserve((size_t)blocks * n_global * slot_bytes))) return rc;
+        a.slot_spill = ctx->qspill.as<uint4>();
+        LAUNCH(*ctx, hybrid_kernel, blocks, Q_THREADS, smem, st, a);
     }
     CK(cudaEventRecord(ctx->ev[13], st));
     if (args->stream) return ll.mark_busy(st);

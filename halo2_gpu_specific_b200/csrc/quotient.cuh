@@ -63,30 +63,50 @@ struct QArgs {
     uint4* out;
     unsigned long long out_stride;   // result of row i goes to out[out_offset + i * out_stride]
     unsigned long long out_offset;
-    uint4* slot_spill;            // global slots when they do not fit in shared memory
+    uint4* slot_spill;            // global slots: all of them when they do not fit in shared memory, or the global class
+    uint32_t n_slots_shared;      // hybrid programs: slots below this index are shared memory, the others global
     unsigned long long row_begin; // rows [row_begin, row_begin + row_count) are evaluated (a rank's share);
     unsigned long long row_count; // result of row i still goes to out[out_offset + (i - row_begin) * out_stride]
 };
 
-template <bool SMEM>
+// HYB (with SMEM): two slot classes -- slots below n_sh in shared memory, slots from n_sh on in a per-CTA global scratch
+// (the values the host found live across most of the program).  The class test is uniform over the CTA (every thread
+// runs the same instruction), so it costs a compare and no divergence.
+template <bool SMEM, bool HYB = false>
 struct QSlots {
     uint4* lo;
     uint4* hi;
+    uint4* glo;
+    uint4* ghi;
+    uint32_t n_sh;
     __device__ __forceinline__ Fr load(uint32_t s) const {
-        const uint4 a = lo[(size_t)s * Q_THREADS], b = hi[(size_t)s * Q_THREADS];
+        uint4 a, b;
+        if (HYB && s >= n_sh) {
+            a = glo[(size_t)(s - n_sh) * Q_THREADS];
+            b = ghi[(size_t)(s - n_sh) * Q_THREADS];
+        } else {
+            a = lo[(size_t)s * Q_THREADS];
+            b = hi[(size_t)s * Q_THREADS];
+        }
         Fr r;
         r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
         r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
         return r;
     }
     __device__ __forceinline__ void store(uint32_t s, const Fr& x) const {
-        lo[(size_t)s * Q_THREADS] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
-        hi[(size_t)s * Q_THREADS] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+        const uint4 a = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]), b = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+        if (HYB && s >= n_sh) {
+            glo[(size_t)(s - n_sh) * Q_THREADS] = a;
+            ghi[(size_t)(s - n_sh) * Q_THREADS] = b;
+        } else {
+            lo[(size_t)s * Q_THREADS] = a;
+            hi[(size_t)s * Q_THREADS] = b;
+        }
     }
 };
 
-template <bool SMEM>
-__device__ __forceinline__ Fr q_fetch(uint32_t w, const QArgs& a, const QSlots<SMEM>& slots, unsigned long long row,
+template <bool SMEM, bool HYB>
+__device__ __forceinline__ Fr q_fetch(uint32_t w, const QArgs& a, const QSlots<SMEM, HYB>& slots, unsigned long long row,
                                       const Fr& x_here) {
     const uint32_t kind = w >> 28, index = w & 0xfffffu;
     switch (kind) {
@@ -102,11 +122,20 @@ __device__ __forceinline__ Fr q_fetch(uint32_t w, const QArgs& a, const QSlots<S
     }
 }
 
-template <bool SMEM>
+template <bool SMEM, bool HYB = false>
 __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a) {
     extern __shared__ uint4 q_smem[];
-    QSlots<SMEM> slots;
-    if (SMEM) {
+    QSlots<SMEM, HYB> slots;
+    slots.glo = slots.ghi = nullptr;
+    slots.n_sh = a.n_slots_shared;
+    if (SMEM && HYB) {
+        const uint32_t n_gl = a.n_slots - a.n_slots_shared;
+        slots.lo = q_smem + threadIdx.x;
+        slots.hi = q_smem + (size_t)a.n_slots_shared * Q_THREADS + threadIdx.x;
+        uint4* base = a.slot_spill + (size_t)blockIdx.x * n_gl * Q_THREADS * 2;
+        slots.glo = base + threadIdx.x;
+        slots.ghi = base + (size_t)n_gl * Q_THREADS + threadIdx.x;
+    } else if (SMEM) {
         slots.lo = q_smem + threadIdx.x;
         slots.hi = q_smem + (size_t)a.n_slots * Q_THREADS + threadIdx.x;
     } else {
@@ -126,7 +155,7 @@ __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a)
         for (uint32_t pc = 0; pc < a.n_instr; pc++) {
             const uint4 ins = __ldg(a.prog + pc);
             const uint32_t op = ins.x & 0xffu, dst = ins.x >> 8;
-            Fr x = q_fetch<SMEM>(ins.y, a, slots, row, x_here);
+            Fr x = q_fetch<SMEM, HYB>(ins.y, a, slots, row, x_here);
             Fr r;
             if (op == Q_NEG) {
                 r = fp_neg<FrParams>(x);
@@ -135,19 +164,19 @@ __global__ void __launch_bounds__(Q_THREADS) quotient_eval_kernel(const QArgs a)
             } else if (op >= Q_MUL2ADD) {
                 const uint4 ext = __ldg(a.prog + pc + 1);
                 pc++;
-                const Fr y = q_fetch<SMEM>(ins.z, a, slots, row, x_here);
-                const Fr c = q_fetch<SMEM>(ins.w, a, slots, row, x_here);
-                const Fr d = q_fetch<SMEM>(ext.y, a, slots, row, x_here);
+                const Fr y = q_fetch<SMEM, HYB>(ins.z, a, slots, row, x_here);
+                const Fr c = q_fetch<SMEM, HYB>(ins.w, a, slots, row, x_here);
+                const Fr d = q_fetch<SMEM, HYB>(ext.y, a, slots, row, x_here);
                 r = (op == Q_MUL2ADD) ? fp_mul2_add<FrParams>(x, y, c, d) : fp_mul2_sub<FrParams>(x, y, c, d);
             } else {
-                Fr y = q_fetch<SMEM>(ins.z, a, slots, row, x_here);
+                Fr y = q_fetch<SMEM, HYB>(ins.z, a, slots, row, x_here);
                 if (op == Q_MUL) r = fp_mul<FrParams>(x, y);
                 else if (op == Q_ADD) r = fp_add<FrParams>(x, y);
                 else r = fp_sub<FrParams>(x, y);
             }
             slots.store(dst, r);
         }
-        Fr res = q_fetch<SMEM>(a.result, a, slots, row, x_here);
+        Fr res = q_fetch<SMEM, HYB>(a.result, a, slots, row, x_here);
         if (a.scale != nullptr) res = fp_mul<FrParams>(res, fp_load_nc<FrParams>(a.scale + (row & a.scale_mask)));
         fp_store<FrParams>(a.out + 2ull * (a.out_offset + rel * a.out_stride), res);
     }

@@ -120,7 +120,11 @@ class QuotientProgram:
     def info(self):
         v = [ctypes.c_uint32() for _ in range(4)]
         check(lib().b2_quotient_program_info(ctypes.c_uint64(self.handle), *[ctypes.byref(x) for x in v]))
-        return dict(zip(("n_instr", "n_slots", "n_mul", "n_addsub"), (x.value for x in v)))
+        out = dict(zip(("n_instr", "n_slots", "n_mul", "n_addsub"), (x.value for x in v)))
+        sh, gl = ctypes.c_uint32(), ctypes.c_uint32()
+        check(lib().b2_quotient_program_slot_classes(ctypes.c_uint64(self.handle), ctypes.byref(sh), ctypes.byref(gl)))
+        out["n_slots_shared"], out["n_slots_global"] = sh.value, gl.value
+        return out
 
     def dump(self):
         """(instructions, result word, derived (challenge, power) pairs); an instruction is (op, dst, a_word, b_word),

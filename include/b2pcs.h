@@ -272,6 +272,12 @@ int b2_quotient_program_free(b2_handle_t program);
 /* lowered instruction count, shared-memory slots per row, field multiplications / additions per row */
 int b2_quotient_program_info(b2_handle_t program, uint32_t* n_instr, uint32_t* n_slots, uint32_t* n_mul,
                              uint32_t* n_addsub);
+/* The two slot classes of the lowered program: n_slots = n_shared + n_global.  A program whose live width would cost
+ * resident CTAs (more than 7 shared-memory slots of 4 KB per CTA) keeps its longest-lived values -- sub-expressions the
+ * circuit shares between gates far apart in its gate list (evaluation.rs:877-907 keeps every such value for the whole
+ * row) -- in a per-CTA global scratch instead; n_global = 0 for every other program.  B2_Q_HYBRID=0 in the environment
+ * puts every slot into shared memory (A/B runs). */
+int b2_quotient_program_slot_classes(b2_handle_t program, uint32_t* n_shared, uint32_t* n_global);
 
 /* Diagnostic: the lowered program (4 words per instruction: op | dst_slot << 8, operand a, operand b, operand c;
  * operand word = kind << 28 | rotation << 20 | index with kind 0 constant, 1 slot, 2 column (fixed, advice,

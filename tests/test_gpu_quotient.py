@@ -219,6 +219,53 @@ def test_zkwasm_shape_program_full_compare(gpu):
     buf.free(); out.free()
 
 
+@pytest.mark.parametrize("log_rows,row_range", [(18, None), (13, None), (18, (5000, 200000))])
+def test_global_slot_class_matches_c_restatement(gpu, monkeypatch, log_rows, row_range):
+    """a program with long-lived shared values (tools/quotient_bench.py long_lived): the lowering keeps 7 slots in shared
+    memory and the rest in the per-CTA global scratch (quotient_eval_kernel<true, true>, one wave of resident CTAs
+    striding over the rows: 2^18 rows are several trips per CTA, 2^13 less than one wave); every row against the C
+    restatement of Calculation::evaluate, and against the same circuit lowered with every slot in shared memory"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import quotient_bench as qb
+    from oracle import cref
+    shape = dict(A=12, F=6, gates=24, lookups=(2, 1), shuffles=1, perm_cols=6, long_lived=14)
+    ev, lookups, shuffles, n_sets = qb.synthetic_evaluator(**shape)
+    f = ev.flat_h_program(n_sets, list(lookups), shuffles)
+    prog = ev.program(n_sets, list(lookups), shuffles)
+    info = prog.info()
+    assert info["n_slots_shared"] <= 7 and info["n_slots_global"] >= 6
+    monkeypatch.setenv("B2_Q_HYBRID", "0")
+    plain = qb.synthetic_evaluator(**shape)[0].program(n_sets, list(lookups), shuffles)
+    monkeypatch.delenv("B2_Q_HYBRID")
+    assert plain.info()["n_slots_global"] == 0
+    rows = 1 << log_rows
+    ncols = prog.n_fixed + prog.n_advice + prog.n_instance + prog.n_aux
+    cols = cref.random_fr_mont(rows * ncols, 0xB20000BB).reshape(ncols, rows, 4)
+    rng = random.Random(6)
+    challenges = [rng.randrange(R) for _ in range(prog.n_challenges)]
+    x0, step = rng.randrange(R), rng.randrange(R)
+    buf = E.DeviceBuffer(rows * ncols).upload(cols)
+    out, out2 = E.DeviceBuffer(rows), E.DeviceBuffer(rows)
+    ptrs = [buf.ptr + c * rows * 32 for c in range(ncols)]
+    nf, na, ni = prog.n_fixed, prog.n_advice, prog.n_instance
+    kw = {} if row_range is None else dict(row_begin=row_range[0], row_count=row_range[1])
+    for p, dst in ((prog, out), (plain, out2)):
+        p.eval(log_rows, 4, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+               dst.ptr, x0=x0, x_step=step, **kw)
+    got, got_plain = out.download(), out2.download()
+    want = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"], list(cols[:nf]),
+                              list(cols[nf:nf + na]), list(cols[nf + na:nf + na + ni]), list(cols[nf + na + ni:]),
+                              enc(challenges), log_rows, 4, x0=enc([x0])[0], step=enc([step])[0], threads=8)
+    if row_range is not None:          # the result of row i lands at out[i - row_begin]
+        want = want[row_range[0]:row_range[0] + row_range[1]]
+        got, got_plain = got[:row_range[1]], got_plain[:row_range[1]]
+    assert np.array_equal(got, want)
+    assert np.array_equal(got_plain, want)
+    buf.free(); out.free(); out2.free()
+    prog.free(); plain.free()
+
+
 def test_sharded_path_single_rank(gpu):
     """parallel.sharded_evaluate_h with one rank: compact task output, interleave, extended_to_coeff"""
     from halo2_gpu_specific_b200 import parallel

@@ -189,3 +189,60 @@ def test_c_restatement_matches_python_oracle(fx):
                              d.extended_k, 1 << (d.extended_k - d.k), x0=enc([1])[0], step=enc([d.extended_omega])[0],
                              threads=3)
     assert np.array_equal(got, enc(want))
+
+
+def test_long_lived_values_move_to_the_global_slot_class(monkeypatch):
+    """A program whose gates share sub-expressions far apart (tools/quotient_bench.py long_lived: the first gates'
+    values are read again by extra gates at the end of the list, so the y-fold keeps them alive across the whole
+    program): with every slot in shared memory the live width costs resident CTAs; the lowering moves the
+    longest-lived values to the global class until at most 7 shared slots remain (b2_quotient_program_slot_classes).
+    Both lowerings are interpreted with big ints on every row and must agree with each other and with the C
+    restatement of Calculation::evaluate on the flat program."""
+    import os
+    import random
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import quotient_bench as qb
+    from oracle import cref
+    ev, lookups, shuffles, n_sets = qb.synthetic_evaluator(A=12, F=6, gates=24, lookups=(2, 1), shuffles=1, perm_cols=6,
+                                                           long_lived=14)
+    monkeypatch.setenv("B2_Q_HYBRID", "0")
+    plain = ev.program(n_sets, list(lookups), shuffles)
+    ev2, _, _, _ = qb.synthetic_evaluator(A=12, F=6, gates=24, lookups=(2, 1), shuffles=1, perm_cols=6, long_lived=14)
+    monkeypatch.delenv("B2_Q_HYBRID")
+    hybrid = ev2.program(n_sets, list(lookups), shuffles)
+    ip, ih = plain.info(), hybrid.info()
+    assert ip["n_slots_global"] == 0 and ip["n_slots_shared"] == ip["n_slots"] > 7 + 6
+    assert ih["n_slots_shared"] <= 7 and ih["n_slots_global"] >= 6
+    assert ih["n_slots"] == ih["n_slots_shared"] + ih["n_slots_global"]
+    assert (ih["n_instr"], ih["n_mul"], ih["n_addsub"]) == (ip["n_instr"], ip["n_mul"], ip["n_addsub"])
+    # a program without such values is left alone
+    ev3, lk3, sh3, ns3 = qb.synthetic_evaluator(A=12, F=6, gates=24, lookups=(2, 1), shuffles=1, perm_cols=6)
+    assert ev3.program(ns3, list(lk3), sh3).info()["n_slots_global"] == 0
+    log_rows, rot_scale = 4, 2
+    rows = 1 << log_rows
+    ncols = plain.n_fixed + plain.n_advice + plain.n_instance + plain.n_aux
+    cols_m = cref.random_fr_mont(rows * ncols, 0xB20000AA).reshape(ncols, rows, 4)
+    cols = [o.fr_decode(c) for c in cols_m]
+    rng = random.Random(8)
+    challenges = [rng.randrange(R) for _ in range(plain.n_challenges)]
+    x0, step = rng.randrange(R), rng.randrange(R)
+    f = ev.flat_h_program(n_sets, list(lookups), shuffles)
+    a = interpret(plain, f["rotations"], f["constants"], cols, challenges, rows, rot_scale, x0, step)
+    b = interpret(hybrid, f["rotations"], f["constants"], cols, challenges, rows, rot_scale, x0, step)
+    assert a == b
+    nf, na, ni = plain.n_fixed, plain.n_advice, plain.n_instance
+    enc = o.fr_encode
+    want = cref.quotient_eval(f["rotations"], enc(f["constants"]), f["calcs"], f["result"], list(cols_m[:nf]),
+                              list(cols_m[nf:nf + na]), list(cols_m[nf + na:nf + na + ni]), list(cols_m[nf + na + ni:]),
+                              enc(challenges), log_rows, rot_scale, x0=enc([x0])[0], step=enc([step])[0], threads=2)
+    assert np.array_equal(enc(b), want)
+    # the global class holds the long-lived values: every global slot is written once per row and read later
+    instr, _, _ = hybrid.dump()
+    writes = {}
+    for pos, ins in enumerate(instr):
+        if ins[1] >= ih["n_slots_shared"]:
+            writes.setdefault(ins[1], []).append(pos)
+    assert len(writes) == ih["n_slots_global"]
+    plain.free(); hybrid.free()

@@ -25,8 +25,11 @@ from halo2_gpu_specific_b200 import evaluation as E  # noqa: E402
 
 
 def synthetic_evaluator(A=64, F=32, I=1, gates=96, lookups=(2, 2, 2, 2, 1, 1, 1, 1), shuffles=4, perm_cols=24,
-                        degree=5, seed=1):
-    """Calculation lists in the reference's form (what Evaluator::new would hand over), no CSE needed."""
+                        degree=5, seed=1, long_lived=0):
+    """Calculation lists in the reference's form (what Evaluator::new would hand over), no CSE needed.
+    long_lived: that many of the first gates' products are read again by extra gates at the END of the gate list -- a
+    circuit whose gates share sub-expressions far apart (the y-fold keeps each such value alive across the whole
+    program: what the engine's global slot class is for)."""
     rng = random.Random(seed)
     rotations = [0, 1, -1, 2]
     constants = [0, 1, 2, 7]
@@ -50,6 +53,8 @@ def synthetic_evaluator(A=64, F=32, I=1, gates=96, lookups=(2, 2, 2, 2, 1, 1, 1,
             t = emit(("Mul", emit(("Mul", a, b)), c))
             t = emit(("Sub", emit(("Add", t, emit(("Mul", d, ("Constant", 3))))), e))
         value_parts.append(emit(("Mul", q, t)))
+    for g in range(min(long_lived, gates)):   # q_g * t_g * (advice + fixed): reads gate g's value again, at the end
+        value_parts.append(emit(("Mul", value_parts[g], emit(("Add", col("Advice", A), col("Fixed", F))))))
     lookup_results = []
     for sets in lookups:
         def compressed(width):
@@ -77,6 +82,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--k", type=int, default=20)
     ap.add_argument("--gates", type=int, default=96)
+    ap.add_argument("--long-lived", type=int, default=0,
+                    help="extra gates at the end of the gate list that read the first gates' values again (A/B of the "
+                         "global slot class: run with B2_Q_HYBRID=0 and without)")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--pipeline", action="store_true",
@@ -86,7 +94,7 @@ def main():
     args = ap.parse_args()
     _lib.require_gpu()
     _lib.set_device(0)
-    ev, lookups, shuffles, n_sets = synthetic_evaluator(gates=args.gates)
+    ev, lookups, shuffles, n_sets = synthetic_evaluator(gates=args.gates, long_lived=args.long_lived)
     prog = ev.program(n_sets, lookups, shuffles)
     info = prog.info()
     ext_k = args.k + 2
