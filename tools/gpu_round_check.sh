@@ -2,7 +2,7 @@
 # What the driver runs at round end, in one call: the whole GPU suite, smoke(), the default bench line.
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $O/r2_gpu_suite_final.log
+python -m pytest tests -m gpu -q 2>&1 | tail -25 | tee $O/r2_gpu_suite_final.log
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 | tee $O/r2_smoke_final.log
 python bench.py > $O/r2_bench_final.json 2> $O/r2_bench_final.err
 echo "bench rc=$?"; tail -c 300 $O/r2_bench_final.err

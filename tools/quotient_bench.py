@@ -124,6 +124,22 @@ def main():
         times.append(_lib.last_timing()[0])
     times = times[2:]
     ms = float(np.median(times))
+    ab = None
+    if args.long_lived and os.environ.get("B2_Q_HYBRID") is None:
+        # the same circuit lowered with every slot in shared memory, on the same resident columns
+        os.environ["B2_Q_HYBRID"] = "0"
+        plain = synthetic_evaluator(gates=args.gates, long_lived=args.long_lived)[0].program(n_sets, lookups, shuffles)
+        del os.environ["B2_Q_HYBRID"]
+        out2 = E.DeviceBuffer(rows)
+        t2 = []
+        for _ in range(args.reps + 2):
+            plain.eval(ext_k, 4, ptrs[:nf], ptrs[nf:nf + na], ptrs[nf + na:nf + na + ni], ptrs[nf + na + ni:], challenges,
+                       out2.ptr, x0=1, x_step=dom._ext_omega, scale=dom.t_evaluations)
+            t2.append(_lib.last_timing()[0])
+        same = bool(np.array_equal(out.download(), out2.download()))
+        ab = {"all_slots_shared": {"program": plain.info(), "kernel_ms": float(np.median(t2[2:]))},
+              "results_equal": same, "speedup_of_the_global_slot_class": float(np.median(t2[2:])) / ms}
+        out2.free()
     wide, modmul = ctypes.c_double(), ctypes.c_double()
     _lib.check(_lib.lib().b2_imad_probe(ctypes.byref(wide), ctypes.byref(modmul)))
     instr, _, _ = prog.dump()
@@ -138,6 +154,8 @@ def main():
         "column_GBps": col_reads * 32 * rows / (ms * 1e-3) / 1e9,
         "upload_s": upload_s,
     }
+    if ab is not None:
+        res["ab_global_slot_class"] = ab
     print(json.dumps(res))
     if args.json:
         with open(args.json, "w") as f:
