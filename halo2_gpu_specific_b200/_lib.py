@@ -76,7 +76,7 @@ def lib() -> ctypes.CDLL:
         L.b2_srs_synthetic.argtypes = [sz, u64, u64, ctypes.POINTER(u64)]
         L.b2_srs_from_scalars_dev.argtypes = [vp, sz, ctypes.POINTER(u64)]
         L.b2_memcpy_d2d.argtypes = [vp, vp, sz]
-        L.b2_vanishing_random_poly_dev.argtypes = [u64, vp, u32, sz, vp, vp]
+        L.b2_vanishing_random_poly_dev.argtypes = [vp, vp, u32, sz, vp, vp]
         L.b2_fr_max_bits_dev.argtypes = [vp, sz, ctypes.POINTER(u32)]
         L.b2_srs_precompute.argtypes = [u64, u32]
         L.b2_g1_normalize.argtypes = [vp, sz]

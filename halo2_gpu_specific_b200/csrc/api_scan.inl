@@ -343,8 +343,11 @@ int b2_kate_division(const void* a, uint64_t n, const void* b, void* q) {
     return rc;
 }
 
-int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, size_t n, void* d_out, void* stream) {
-    if (!random || !d_out || k == 0 || k > 64 || n == 0) return fail(B2_ERR_ARG, "vanishing_random_poly: bad arguments");
+int b2_vanishing_random_poly_dev(const void* key32, const void* random, uint32_t k, size_t n, void* d_out, void* stream) {
+    if (!key32 || !random || !d_out || k == 0 || k > 64 || n == 0 || n > (1ull << 30))
+        return fail(B2_ERR_ARG, "vanishing_random_poly: bad arguments");
+    VanishKey key;
+    memcpy(key.k, key32, 32);       // little-endian words, as RFC 8439 lays a key out
     LaneLock ll;
     int rc = ll.acquire((cudaStream_t)stream);
     if (rc) return rc;
@@ -353,7 +356,7 @@ int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, 
     if ((rc = ctx->out96.reserve((size_t)k * 32))) return rc;      // the k "random" elements, staged on the device
     CK(cudaMemcpyAsync(ctx->out96.p, random, (size_t)k * 32, cudaMemcpyHostToDevice, st));
     LAUNCH(*ctx, vanishing_random_poly_kernel, (unsigned)std::min<size_t>((n + 255) / 256, (size_t)ctx->sms * 16), 256, 0, st,
-           (uint4*)d_out, (const uint4*)ctx->out96.p, (unsigned)k, (unsigned long long)n, (unsigned long long)seed);
+           (uint4*)d_out, (const uint4*)ctx->out96.p, (unsigned)k, (unsigned long long)n, key);
     CK(cudaStreamSynchronize(st));
     return B2_OK;
 }

@@ -8,6 +8,7 @@
 #pragma once
 #include "fp.cuh"
 #include "fp_shoup.cuh"
+#include "chacha.cuh"
 
 namespace b2 {
 
@@ -177,36 +178,43 @@ __global__ void fr_max_bits_kernel(const uint4* __restrict__ a, unsigned long lo
 
 // ---- the vanishing argument's random polynomial (halo2_proofs/src/plonk/vanishing/prover.rs:48-63) ----------
 // coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]).  The reference draws a_i, u_i, b_i, v_i from
-// thread_rng inside a rayon loop; here they come from a counter-based generator keyed by one 64-bit seed that the
-// caller's RNG supplies, so the polynomial is reproducible and never exists on the host:
-//   word(j) = mix(seed ^ mix(j)), mix = splitmix64's output function applied to j + golden;
-//   a_i = words 10i .. 10i+3 (top limb masked to 61 bits, taken as Montgomery limbs), u_i = word 10i+4,
-//   b_i = words 10i+5 .. 10i+8 (same), v_i = word 10i+9.
-__device__ __forceinline__ unsigned long long vanish_mix(unsigned long long x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-__device__ __forceinline__ Fr vanish_fr(unsigned long long seed, unsigned long long j) {
-    Fr r;
+// thread_rng (ChaCha under a 256-bit key) inside a rayon loop; here they come from a counter-based generator of the
+// same strength keyed by 256 bits that the caller's RNG supplies, so the polynomial is reproducible under a fixed RNG,
+// unpredictable under a real one, and never exists on the host.
+// The generator (restated in oracle/prover.py and halo2_gpu_specific_b200/plonk.py vanishing_streams): ChaCha20 key
+// stream (RFC 8439 block function, nonce 0) under a 256-bit key from the caller's rng; coefficient i takes blocks
+// 3i, 3i + 1, 3i + 2: a_i = (block 3i as a 512-bit little-endian integer) mod r, b_i = (block 3i + 1) mod r -- uniform
+// over Fr up to 2^-250, like Fr::random -- and u_i, v_i = the first two little-endian 64-bit words of block 3i + 2.
+struct VanishKey {
+    uint32_t k[8];
+};
+// x mod r in Montgomery form for a 512-bit x = lo + hi * 2^256 given as 16 little-endian words:
+// lo * R = mont(R^2, lo), hi * 2^256 * R = mont(R^3, hi).  The raw halves (any 256-bit value) are the SECOND operand:
+// the interleaved product keeps its accumulator below (first operand) + r whatever the second one is.
+__device__ __forceinline__ Fr vanish_wide_fr(const uint32_t (&w)[16]) {
+    Fr lo, hi, r3;
 #pragma unroll
-    for (int l = 0; l < 4; l++) {
-        unsigned long long w = vanish_mix(seed ^ vanish_mix(j + l));
-        if (l == 3) w &= (1ull << 61) - 1;
-        r.v[2 * l] = (uint32_t)w;
-        r.v[2 * l + 1] = (uint32_t)(w >> 32);
+    for (int l = 0; l < 8; l++) {
+        lo.v[l] = w[l];
+        hi.v[l] = w[8 + l];
     }
-    return r;
+    r3.v[0] = 0xb4bf0040u; r3.v[1] = 0x5e94d8e1u; r3.v[2] = 0x1cfbb6b8u; r3.v[3] = 0x2a489cbeu;      // 2^768 mod r
+    r3.v[4] = 0xa19fcfedu; r3.v[5] = 0x893cc664u; r3.v[6] = 0x7fcc657cu; r3.v[7] = 0x0cf8594bu;
+    return fp_add<FrParams>(fp_mul<FrParams>(Fr::r2(), lo), fp_mul<FrParams>(r3, hi));
 }
 __global__ void vanishing_random_poly_kernel(uint4* __restrict__ out, const uint4* __restrict__ random, unsigned k,
-                                             unsigned long long n, unsigned long long seed) {
+                                             unsigned long long n, const VanishKey key) {
     unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
-        const Fr a = vanish_fr(seed, 10ull * i), b = vanish_fr(seed, 10ull * i + 5);
-        const unsigned long long u = vanish_mix(seed ^ vanish_mix(10ull * i + 4));
-        const unsigned long long v = vanish_mix(seed ^ vanish_mix(10ull * i + 9));
+        uint32_t w[16];
+        chacha20_block(key.k, (uint32_t)(3ull * i), 0u, 0u, 0u, w);
+        const Fr a = vanish_wide_fr(w);
+        chacha20_block(key.k, (uint32_t)(3ull * i + 1ull), 0u, 0u, 0u, w);
+        const Fr b = vanish_wide_fr(w);
+        chacha20_block(key.k, (uint32_t)(3ull * i + 2ull), 0u, 0u, 0u, w);
+        const unsigned long long u = (unsigned long long)w[0] | ((unsigned long long)w[1] << 32);
+        const unsigned long long v = (unsigned long long)w[2] | ((unsigned long long)w[3] << 32);
         const Fr ra = fp_load<FrParams>(random + 2ull * (u % k)), rb = fp_load<FrParams>(random + 2ull * (v % k));
         fp_store<FrParams>(out + 2ull * i, fp_mul<FrParams>(fp_add<FrParams>(a, ra), fp_add<FrParams>(b, rb)));
     }

@@ -400,29 +400,51 @@ class Blake2bRng:
 #   eval_polynomial, poly_combine, sub_constant, kate_division_padded   evaluation phase and multiopen (GWC)
 #   sub_low_degree, scale, sub_cols                      what SHPLONK adds
 #   key_blocks, copy, stack, release, free
-def _mix64(x: np.ndarray) -> np.ndarray:
-    """splitmix64's output function of x + golden (uint64 arithmetic wraps)"""
-    x = x + np.uint64(0x9E3779B97F4A7C15)
-    x = (x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
-    x = (x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
-    return x ^ (x >> np.uint64(31))
 
 
-def vanishing_streams(seed: int, n: int):
-    """The four per-coefficient streams of the vanishing argument's random polynomial, from one 64-bit seed:
-    word(j) = mix(seed ^ mix(j)); a_i = words 10i..10i+3 (top limb masked to 61 bits, taken as Montgomery limbs),
-    u_i = word 10i+4, b_i = words 10i+5..10i+8, v_i = word 10i+9.  Same generator as csrc/scan.cuh
-    (vanishing_random_poly_kernel), which the resident engine runs instead."""
+def chacha20_blocks(key: bytes, first: int, count: int) -> np.ndarray:
+    """ChaCha20 key stream blocks first .. first + count - 1 (RFC 8439 block function, nonce 0) under a 32-byte key,
+    as a (count, 16) array of little-endian 32-bit words; vectorised over the blocks.  The same function as
+    csrc/chacha.cuh, which the device runs."""
+    if len(key) != 32:
+        raise B2Error(B2_ERR_ARG, "chacha20: the key is 32 bytes")
+    kw = np.frombuffer(key, dtype="<u4")
+    s = np.zeros((16, count), dtype=np.uint32)
+    s[0], s[1], s[2], s[3] = 0x61707865, 0x3320646E, 0x79622D32, 0x6B206574
+    for i in range(8):
+        s[4 + i] = kw[i]
+    s[12] = (np.arange(count, dtype=np.uint64) + np.uint64(first)).astype(np.uint32)
+    x = s.copy()
+
+    def rotl(v, c):
+        return (v << np.uint32(c)) | (v >> np.uint32(32 - c))
+
+    def qr(a, b, c, d):
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16)                             # noqa: E702
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12)                             # noqa: E702
+        x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8)                              # noqa: E702
+        x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7)                              # noqa: E702
+
     with np.errstate(over="ignore"):
-        sd = np.uint64(seed & 0xFFFFFFFFFFFFFFFF)
-        j = (np.arange(n, dtype=np.uint64) * np.uint64(10))[:, None] + np.arange(10, dtype=np.uint64)[None, :]
-        w = _mix64(sd ^ _mix64(j))
-    mask = np.uint64((1 << 61) - 1)
-    a = np.ascontiguousarray(w[:, 0:4])
-    b = np.ascontiguousarray(w[:, 5:9])
-    a[:, 3] &= mask
-    b[:, 3] &= mask
-    return a, np.ascontiguousarray(w[:, 4]), b, np.ascontiguousarray(w[:, 9])
+        for _ in range(10):
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)      # noqa: E702
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)      # noqa: E702
+        x += s
+    return np.ascontiguousarray(x.T)
+
+
+def vanishing_streams(key: bytes, n: int):
+    """The four per-coefficient streams of the vanishing argument's random polynomial from 256 bits of the caller's
+    rng: ChaCha20 key stream under `key`, coefficient i takes blocks 3i, 3i + 1, 3i + 2; a_i = (block 3i as a 512-bit
+    little-endian integer) mod r, b_i = (block 3i + 1) mod r, u_i / v_i = the first two 64-bit words of block 3i + 2.
+    Returns (a_lo, a_hi, u, b_lo, b_hi, v): the 256-bit halves as (n, 4) little-endian 64-bit limbs (the reduction
+    mod r is field arithmetic: a = a_lo + a_hi * 2^256), u and v as uint64.  Same generator as csrc/scan.cuh
+    (vanishing_random_poly_kernel), which the device engines run instead."""
+    w = chacha20_blocks(key, 0, 3 * n).reshape(n, 3, 16)
+    limbs = lambda words: np.ascontiguousarray(words).view("<u8").astype(np.uint64).reshape(n, 4)     # noqa: E731
+    third = np.ascontiguousarray(w[:, 2, :4]).view("<u8").astype(np.uint64).reshape(n, 2)
+    return (limbs(w[:, 0, :8]), limbs(w[:, 0, 8:]), np.ascontiguousarray(third[:, 0]),
+            limbs(w[:, 1, :8]), limbs(w[:, 1, 8:]), np.ascontiguousarray(third[:, 1]))
 
 
 def canonical_max_bits(canonical: np.ndarray) -> int:
@@ -532,11 +554,16 @@ class ArrayBlocks:
         z = self.shuffle_commit_product(cs, group, advice, pk.fixed_values, instance, theta, beta)
         out_col[:len(z)] = z
 
-    def random_poly(self, random: np.ndarray, seed: int) -> np.ndarray:
-        a, u, b, v = vanishing_streams(seed, self.domain.n)
+    def random_poly(self, random: np.ndarray, key: bytes) -> np.ndarray:
+        """host restatement of vanishing_random_poly_kernel over the engine's element-wise field operations (the test
+        double answers them with the oracle; the host-API device engine overrides this with the kernel itself)"""
+        a_lo, a_hi, u, b_lo, b_hi, v = vanishing_streams(key, self.domain.n)
         kk = np.uint64(random.shape[0])
-        p = self.fr_vec("mul", self.fr_vec("add", a, random[(u % kk).astype(np.int64)]),
-                        self.fr_vec("add", b, random[(v % kk).astype(np.int64)]))
+        # x mod r in Montgomery form: mont(R^2, lo) + mont(R^3, hi); the raw halves go second (fp_mul's bound)
+        wide = lambda lo, hi: self.fr_vec("add", self.fr_vec("mul", np.broadcast_to(_RAW_R2, lo.shape), lo),      # noqa: E731
+                                          self.fr_vec("mul", np.broadcast_to(_RAW_R3, hi.shape), hi))
+        p = self.fr_vec("mul", self.fr_vec("add", wide(a_lo, a_hi), random[(u % kk).astype(np.int64)]),
+                        self.fr_vec("add", wide(b_lo, b_hi), random[(v % kk).astype(np.int64)]))
         return p.reshape(1, -1, 4)
 
     def evaluate_h_blocks(self, pk, advice, instance, z_block, m_block, n_perm, lookup_z_counts, n_shuffles,
@@ -599,6 +626,23 @@ class Engine(ArrayBlocks):
         self.params, self.domain = params, domain
 
     _points = staticmethod(_points)
+
+    def random_poly(self, random: np.ndarray, key: bytes) -> np.ndarray:
+        """the device makes it (b2_vanishing_random_poly_dev), this engine's contract brings it back to the host"""
+        import ctypes
+        from ._lib import check, lib, ptr
+        from .evaluation import DeviceBuffer
+        n = self.domain.n
+        random = np.ascontiguousarray(random, dtype=np.uint64).reshape(-1, 4)
+        kb = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+        if kb.size != 32:
+            raise B2Error(B2_ERR_ARG, "random_poly: the key is 32 bytes")
+        buf = DeviceBuffer(n)
+        try:
+            check(lib().b2_vanishing_random_poly_dev(ptr(kb), ptr(random), random.shape[0], n, ctypes.c_void_p(buf.ptr), None))
+            return buf.download().reshape(1, n, 4)
+        finally:
+            buf.free()
 
     # -- commitments
     def commit_lagrange(self, cols: np.ndarray, max_bits: int = _fr.NUM_BITS) -> List[Point]:
@@ -691,6 +735,7 @@ class Engine(ArrayBlocks):
 
 _RAW_ONE = np.array([1, 0, 0, 0], dtype=np.uint64)                                     # canonical 1 (not Montgomery)
 _RAW_R2 = np.array([(pow(2, 512, R) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
+_RAW_R3 = np.array([(pow(2, 768, R) >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(4)], dtype=np.uint64)
 
 
 class DevBlock:
@@ -1033,13 +1078,16 @@ class ResidentEngine:
                                    beta, out_col.ptr)
 
     # -- vanishing argument
-    def random_poly(self, random: np.ndarray, seed: int) -> DevBlock:
+    def random_poly(self, random: np.ndarray, key: bytes) -> DevBlock:
         """generated where it is used (b2_vanishing_random_poly_dev): the polynomial never exists on the host"""
         import ctypes
         from ._lib import check, lib, ptr
         out = self.alloc(1)
         random = np.ascontiguousarray(random, dtype=np.uint64).reshape(-1, 4)
-        check(lib().b2_vanishing_random_poly_dev(seed & 0xFFFFFFFFFFFFFFFF, ptr(random), random.shape[0], self.domain.n,
+        kb = np.frombuffer(bytes(key), dtype=np.uint8).copy()
+        if kb.size != 32:
+            raise B2Error(B2_ERR_ARG, "random_poly: the key is 32 bytes")
+        check(lib().b2_vanishing_random_poly_dev(ptr(kb), ptr(random), random.shape[0], self.domain.n,
                                                  ctypes.c_void_p(out.ptr), None))
         return out
 
@@ -1408,9 +1456,9 @@ def create_proof(params, pk: ProvingKey, advice: np.ndarray, instances: Sequence
       1. u16_vec(num_advice * (bf + 1)): advice column i takes [i*(bf+1), (i+1)*(bf+1)) for its last bf+1 rows
       2. per lookup: u16_vec(bf + 1), the last rows of m
       3. per permutation set: fr_vec(bf);  4. per lookup, per z: fr_vec(bf);  5. per shuffle group: fr_vec(bf)
-      6. vanishing random polynomial: fr_vec(k) for `random`, u64_vec(1) for the seed of the per-coefficient
-         streams a, u, b, v (vanishing_streams): coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]),
-         vanishing/prover.rs:48-63 -- the reference draws those four per coefficient from thread_rng
+      6. vanishing random polynomial: fr_vec(k) for `random`, u64_vec(4) = the 256-bit ChaCha20 key of the
+         per-coefficient streams a, u, b, v (vanishing_streams): coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]),
+         vanishing/prover.rs:48-63 -- the reference draws those four per coefficient from thread_rng (ChaCha too)
     """
     return create_proof_multi(params, pk, [advice], [instances], rng, sign_bit=sign_bit, engine=engine,
                               advice_max_bits=advice_max_bits, timings=timings, use_gwc=use_gwc)
@@ -1591,7 +1639,7 @@ def _create_proof(E, pk, cs, domain, advices, instances, rng, sign_bit, advice_m
 
     # ---- vanishing commit, y (:635-639, vanishing/prover.rs:41-70)
     random = rng.fr_vec(k)
-    random_block = E.random_poly(random, int(rng.u64_vec(1)[0]))
+    random_block = E.random_poly(random, np.asarray(rng.u64_vec(4), dtype="<u8").tobytes())
     random_poly = E.cols(random_block)[0]
     tr.write_point(E.commit(random_block)[0])
     y = tr.squeeze_challenge()

@@ -331,10 +331,13 @@ int b2_fr_vec_dev(int op, const void* d_a, const void* d_b, size_t n, void* d_ou
  * (plonk/prover.rs:945-962), the bound the reference passes to commit_lagrange_with_bound for every advice column. */
 int b2_fr_max_bits_dev(const void* d_a, size_t n, uint32_t* bits);
 /* The vanishing argument's random polynomial (plonk/vanishing/prover.rs:48-63): d_out[i] = (a_i + random[u_i % k]) *
- * (b_i + random[v_i % k]) for i < n, with a_i, u_i, b_i, v_i from a counter-based generator keyed by `seed` (the
- * reference draws them from thread_rng; csrc/scan.cuh states the generator, oracle/prover.py restates it).  random:
- * k Montgomery field elements on the HOST (the reference's `random` vector, k = domain.k() <= 64).  Synchronous. */
-int b2_vanishing_random_poly_dev(uint64_t seed, const void* random, uint32_t k, size_t n, void* d_out, void* stream);
+ * (b_i + random[v_i % k]) for i < n, with a_i, u_i, b_i, v_i from a counter-based generator keyed by the 32 bytes at
+ * `key32` (the reference draws them from thread_rng, i.e. ChaCha under a 256-bit key; here: the ChaCha20 key stream
+ * of RFC 8439 under that key, nonce 0 -- blocks 3i and 3i + 1 reduced mod r as 512-bit little-endian integers are a_i
+ * and b_i, the first two 64-bit words of block 3i + 2 are u_i and v_i; csrc/scan.cuh + csrc/chacha.cuh state the
+ * generator, oracle/prover.py restates it).  random: k Montgomery field elements on the HOST (the reference's `random`
+ * vector, k = domain.k() <= 64).  n <= 2^30.  Synchronous. */
+int b2_vanishing_random_poly_dev(const void* key32, const void* random, uint32_t k, size_t n, void* d_out, void* stream);
 
 /* ---- polynomial evaluation / division on resident coefficient forms --------------------- */
 /* eval_polynomial (arithmetic.rs:707-735): out[c] = sum_i poly_c[i] * point^i for `columns` polynomials of n

@@ -364,36 +364,44 @@ class _RngAdapter:
 # --------------------------------------------------------------------------
 # create_proof
 # --------------------------------------------------------------------------
-_M64 = (1 << 64) - 1
 
 
-def _mix64(x: int) -> int:
-    x = (x + 0x9E3779B97F4A7C15) & _M64
-    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
-    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & _M64
-    return x ^ (x >> 31)
+def chacha20_block(key: bytes, counter: int, nonce=(0, 0, 0)) -> bytes:
+    """RFC 8439 section 2.3: one 64-byte key stream block (scalar restatement; the product's vectorised one is
+    halo2_gpu_specific_b200/plonk.py chacha20_blocks, the device's csrc/chacha.cuh)"""
+    M = 0xFFFFFFFF
+    rotl = lambda v, c: ((v << c) & M) | (v >> (32 - c))                       # noqa: E731
+    s = [0x61707865, 0x3320646E, 0x79622D32, 0x6B206574] + \
+        [int.from_bytes(key[4 * i:4 * i + 4], "little") for i in range(8)] + [counter & M] + [w & M for w in nonce]
+    x = list(s)
+
+    def qr(a, b, c, d):
+        x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 16)                 # noqa: E702
+        x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 12)                 # noqa: E702
+        x[a] = (x[a] + x[b]) & M; x[d] = rotl(x[d] ^ x[a], 8)                  # noqa: E702
+        x[c] = (x[c] + x[d]) & M; x[b] = rotl(x[b] ^ x[c], 7)                  # noqa: E702
+
+    for _ in range(10):
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15)   # noqa: E702
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14)   # noqa: E702
+    return b"".join(((a + b) & M).to_bytes(4, "little") for a, b in zip(x, s))
 
 
 def vanishing_random_poly(domain, rng) -> List[int]:
     """vanishing/prover.rs:48-63 with the caller's rng: random = k field elements (fr_vec(k));
     coeff[i] = (a_i + random[u_i % k]) * (b_i + random[v_i % k]).  The reference draws a_i, u_i, b_i, v_i from
-    thread_rng per coefficient; here they are words of a counter-based generator keyed by one u64 from the rng:
-    word(j) = mix(seed ^ mix(j)), a_i = words 10i..10i+3 as little-endian limbs of a Montgomery representation
-    (top limb masked to 61 bits), u_i = word 10i+4, b_i = words 10i+5..10i+8, v_i = word 10i+9."""
+    thread_rng (ChaCha under a 256-bit key) per coefficient; here they come from the ChaCha20 key stream (RFC 8439,
+    nonce 0) under the 256-bit key u64_vec(4) of the rng: a_i = block 3i as a 512-bit little-endian integer mod r,
+    b_i = block 3i + 1 likewise, u_i and v_i the first two little-endian 64-bit words of block 3i + 2."""
     k, n = domain.k, domain.n
     random = o.fr_decode(rng.fr_vec(k))
-    seed = int(rng.u64_vec(1)[0])
-    word = lambda j: _mix64(seed ^ _mix64(j))                                  # noqa: E731
-    rinv = pow(1 << 256, -1, R)
-
-    def fr(j):
-        limbs = [word(j + l) for l in range(4)]
-        limbs[3] &= (1 << 61) - 1
-        return sum(v << (64 * l) for l, v in enumerate(limbs)) * rinv % R
-
+    key = b"".join(int(w).to_bytes(8, "little") for w in rng.u64_vec(4))
     out = []
     for i in range(n):
-        a, u, b, v = fr(10 * i), word(10 * i + 4), fr(10 * i + 5), word(10 * i + 9)
+        a = int.from_bytes(chacha20_block(key, 3 * i), "little") % R
+        b = int.from_bytes(chacha20_block(key, 3 * i + 1), "little") % R
+        third = chacha20_block(key, 3 * i + 2)
+        u, v = int.from_bytes(third[:8], "little"), int.from_bytes(third[8:16], "little")
         out.append((a + random[u % k]) * (b + random[v % k]) % R)
     return out
 
@@ -471,7 +479,7 @@ def create_proof_multi(params: Params, pk: ProvingKey, advices: Sequence[Sequenc
       3. per circuit, per permutation set: fr_vec(bf)                                                   (permutation/prover.rs:156-158)
       4. per circuit, per lookup, per z: fr_vec(bf)                                                     (plonk/prover.rs:445-449)
       5. per circuit, per shuffle group: fr_vec(bf)                                                     (plonk/prover.rs:518-521)
-      6. vanishing_random_poly: fr_vec(k), u64_vec(1)                                                   (vanishing/prover.rs:48-63)
+      6. vanishing_random_poly: fr_vec(k), u64_vec(4)                                                   (vanishing/prover.rs:48-63)
     """
     vk = pk.vk
     cs, domain = vk.cs, vk.domain

@@ -449,18 +449,53 @@ def test_small_host_helpers_match_oracle():
         assert got == o.lagrange_interpolate(pts, evs)
         for p, e in zip(pts, evs):
             assert o.eval_polynomial(got, p) == e
-    seed = 0xDEADBEEFCAFEF00D
-    a, u, b, v = HP.vanishing_streams(seed, 16)
-    word = lambda j: PR._mix64(seed ^ PR._mix64(j))                                 # noqa: E731
+    key = bytes(range(100, 132))
+    a_lo, a_hi, u, b_lo, b_hi, v = HP.vanishing_streams(key, 16)
+    val = lambda limbs: sum(int(x) << (64 * l) for l, x in enumerate(limbs))          # noqa: E731
     for i in (0, 1, 7, 15):
-        limbs = [word(10 * i + l) for l in range(4)]
-        limbs[3] &= (1 << 61) - 1
-        assert [int(x) for x in a[i]] == limbs
-        assert int(u[i]) == word(10 * i + 4) and int(v[i]) == word(10 * i + 9)
-        assert int(b[i][0]) == word(10 * i + 5)
+        blk = [PR.chacha20_block(key, 3 * i + j) for j in range(3)]
+        assert val(a_lo[i]) + (val(a_hi[i]) << 256) == int.from_bytes(blk[0], "little")
+        assert val(b_lo[i]) + (val(b_hi[i]) << 256) == int.from_bytes(blk[1], "little")
+        assert int(u[i]) == int.from_bytes(blk[2][:8], "little") and int(v[i]) == int.from_bytes(blk[2][8:16], "little")
     canon = np.array([o._to_limbs(v) for v in (0, 1, 255, 1 << 64, (1 << 130) + 5)], dtype=np.uint64)
     assert HP.canonical_max_bits(canon) == 131 and HP.canonical_max_bits(canon[:3]) == 8
     assert HP.canonical_max_bits(canon[:1]) == 0 and HP.canonical_max_bits(np.zeros((0, 4), np.uint64)) == 0
+
+
+def test_chacha20_three_implementations_agree():
+    """The generator of the vanishing argument's random polynomial: RFC 8439's block-function vector (2.3.2), and on
+    random keys / counters the oracle's scalar restatement, the package's vectorised one, the HOST BUILD OF THE DEVICE
+    SOURCE (csrc/chacha.cuh through host/chacha_selftest.cpp) and an independent library (cryptography's ChaCha20)"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "halo2_gpu_specific_b200", "host", "chacha_selftest")
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build()
+    rfc_key = bytes(range(32))
+    want = bytes.fromhex("10f1e7e4d13b5915500fdd1fa32071c4c7d1f4c733c068030422aa9ac3d46c4e"
+                         "d2826446079faa0914c2d705d98b02a2b5129cd1de164eb9cbd083e8a2503c4e")
+    assert PR.chacha20_block(rfc_key, 1, (0x09000000, 0x4A000000, 0)) == want
+    out = subprocess.run([exe, rfc_key.hex(), "1", "1", "0x09000000", "0x4a000000", "0"], capture_output=True, text=True,
+                         check=True).stdout.split()
+    assert bytes.fromhex(out[0]) == want
+    rng = random.Random(20)
+    for first, count in ((0, 7), (3 * ((1 << 22) - 2), 6), ((1 << 32) - 3, 3)):
+        key = bytes(rng.randrange(256) for _ in range(32))
+        scalar = [PR.chacha20_block(key, first + j) for j in range(count)]
+        vec = HP.chacha20_blocks(key, first, count)
+        assert [vec[j].astype("<u4").tobytes() for j in range(count)] == scalar
+        dev_src = subprocess.run([exe, key.hex(), str(first), str(count)], capture_output=True, text=True,
+                                 check=True).stdout.split()
+        assert [bytes.fromhex(h) for h in dev_src] == scalar
+        try:
+            from cryptography.hazmat.primitives.ciphers import Cipher, algorithms
+        except ImportError:
+            continue
+        for j in range(count):
+            nonce16 = ((first + j) & 0xFFFFFFFF).to_bytes(4, "little") + bytes(12)
+            ks = Cipher(algorithms.ChaCha20(key, nonce16), mode=None).encryptor().update(bytes(64))
+            assert ks == scalar[j]
 
 
 def test_cpp_transcript_matches_python(tmp_path):
