@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/../.."
 O=gpurun_out; mkdir -p $O
 timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29521 \
-  bench.py --gpus 2 --steps 10 --warmup 3 --no-ntt --no-cpu --no-quotient --no-proof --no-proof22 --no-strong \
+  bench.py --gpus 2 --steps 10 --warmup 3 --no-ntt --no-cpu --no-quotient --no-proof22 --no-strong \
   > $O/r2_bench_2gpu_final.json 2> $O/r2_bench_2gpu_final.err
 echo "bench N=2 rc=$?"; tail -c 400 $O/r2_bench_2gpu_final.err
 python - <<'PY'
