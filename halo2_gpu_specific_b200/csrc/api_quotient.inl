@@ -333,16 +333,21 @@ struct QLower {
         // B2_Q_HYBRID=0 keeps every slot in shared memory (A/B runs); default: hybrid when the width costs occupancy
         const char* hybrid_env = getenv("B2_Q_HYBRID");     // read per program: tests lower the same circuit both ways
         const bool hybrid = !(hybrid_env && atoi(hybrid_env) == 0);
-        if (hybrid && n_sh > Q_SHARED_TARGET) {
+        // test knobs (host-only): a smaller target / shorter minimum live range push small programs through the
+        // two-class allocator (tests/test_prover_fuzz.py)
+        uint32_t shared_target = Q_SHARED_TARGET, min_live = Q_GLOBAL_MIN_LIVE;
+        if (const char* e = getenv("B2_Q_SHARED_TARGET")) shared_target = (uint32_t)std::max(1, atoi(e));
+        if (const char* e = getenv("B2_Q_GLOBAL_MIN_LIVE")) min_live = (uint32_t)std::max(1, atoi(e));
+        if (hybrid && n_sh > shared_target) {
             // candidates by decreasing live length; values read again within Q_GLOBAL_MIN_LIVE instructions stay shared
             std::vector<uint32_t> def_pos(n_vreg, 0);
             for (uint32_t j = 0; j < kept.size(); j++) def_pos[kept[j]] = j;
             std::vector<uint32_t> cand;
             for (uint32_t v : kept)
-                if (last[v] > def_pos[v] && last[v] - def_pos[v] >= Q_GLOBAL_MIN_LIVE) cand.push_back(v);
+                if (last[v] > def_pos[v] && last[v] - def_pos[v] >= min_live) cand.push_back(v);
             std::stable_sort(cand.begin(), cand.end(),
                              [&](uint32_t x, uint32_t y) { return last[x] - def_pos[x] > last[y] - def_pos[y]; });
-            for (size_t i = 0; i < cand.size() && n_sh > Q_SHARED_TARGET; i++) {
+            for (size_t i = 0; i < cand.size() && n_sh > shared_target; i++) {
                 glob[cand[i]] = 1;
                 allocate(glob, false, &n_sh, &n_gl);
             }

@@ -218,13 +218,19 @@ def test_zero_minus_b_cannot_be_proven():
         PR.create_proof(oparams, opk, [a, list(a)], [], HP.SeededRng(1))
 
 
+@pytest.mark.parametrize("two_classes", [False, True])
 @pytest.mark.parametrize("seed", range(12))
-def test_random_circuit_lowered_quotient_program(seed):
+def test_random_circuit_lowered_quotient_program(seed, two_classes, monkeypatch):
     """The C++ lowering of the whole evaluate_h program (b2_quotient_program_create: inlining, dead-code removal,
     depth-first scheduling, slot allocation, derived challenge powers; host-only code of the product) on the random
-    circuits: the dumped program, interpreted with big ints over the oracle's cosets, must equal the oracle's
+    circuits -- also with the shared-slot target lowered to 2, so that these small programs go through the two-class
+    allocator (values with live ranges of 3+ instructions move to the global class until 2 shared slots remain):
+    the dumped program, interpreted with big ints over the oracle's cosets, must equal the oracle's
     evaluate_h on every row of the extended domain."""
     from test_quotient_lowering import interpret
+    if two_classes:
+        monkeypatch.setenv("B2_Q_SHARED_TARGET", "2")
+        monkeypatch.setenv("B2_Q_GLOBAL_MIN_LIVE", "3")
     cs, fixed, advice, instance, mapping = build(seed)
     rng = random.Random(1000 + seed)
     d = o.EvaluationDomain(cs.degree(), K)
@@ -269,6 +275,11 @@ def test_random_circuit_lowered_quotient_program(seed):
     assert got == want
     info = prog.info()
     assert info["n_slots"] <= 24 and info["n_instr"] > 0
+    assert info["n_slots"] == info["n_slots_shared"] + info["n_slots_global"]
+    if two_classes:
+        assert info["n_slots_global"] > 0 or info["n_slots_shared"] <= 2
+    else:
+        assert info["n_slots_global"] == 0 or info["n_slots"] > 7
     if seed < 6:
         # the third restatement: oracle/cpu_ref.c's row loop (bench.py's CPU baseline for evaluate_h) on the flat program
         from oracle import cref
