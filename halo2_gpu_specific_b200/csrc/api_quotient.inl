@@ -11,7 +11,7 @@
 //   * instructions whose value never reaches `result` are dropped;
 //   * intermediates get shared-memory slots from their live ranges (a slot is recycled after
 //     the last read of its value, and a destination may reuse the slot of its own operand);
-//   * when the live width would cost resident CTAs (more than Q_SHARED_TARGET = 7 slots), the values
+//   * when the live width costs more resident CTAs than a second slot class does (10 or more slots), the values
 //     with the longest live ranges -- sub-expressions a circuit shares between gates that sit far
 //     apart in its gate list -- move to a second slot class in global memory (one coalesced,
 //     L2-resident 32-byte round trip per use instead of 32 B x 128 threads of shared memory for
@@ -24,6 +24,11 @@ constexpr size_t Q_SMEM_LIMIT = 200 * 1024;
 // (128 threads x 32 B) and the kernel's registers (70 - 72) allow 7 CTAs per SM, so up to 7 slots (7 x (28 + 1) KB of the
 // 228 KB) cost no occupancy; 17 slots are 3 CTAs per SM and 27 % of the kernel's throughput.
 constexpr uint32_t Q_SHARED_TARGET = 7;
+// ... but the global class has a price too (a persistent one-wave grid, a class test per slot access, the round trips):
+// measured (profiles/r2_quotient_slot_classes_ll*.json) a program of 8 live values is 5 % SLOWER as 7 + 1 than with all 8
+// in shared memory at 6 CTAs per SM, one of 10 is 2 % faster as 7 + 3 (all shared: 5 CTAs), one of 18 is 1.35x faster,
+// one of 34 2.9x.  So the second class is used from 10 live values on.
+constexpr uint32_t Q_HYBRID_FROM = 10;
 constexpr uint32_t Q_GLOBAL_MIN_LIVE = 24;   // instructions between definition and last use below which a value stays shared
 
 struct QProgram {
@@ -335,10 +340,13 @@ struct QLower {
         const bool hybrid = !(hybrid_env && atoi(hybrid_env) == 0);
         // test knobs (host-only): a smaller target / shorter minimum live range push small programs through the
         // two-class allocator (tests/test_prover_fuzz.py)
-        uint32_t shared_target = Q_SHARED_TARGET, min_live = Q_GLOBAL_MIN_LIVE;
-        if (const char* e = getenv("B2_Q_SHARED_TARGET")) shared_target = (uint32_t)std::max(1, atoi(e));
+        uint32_t shared_target = Q_SHARED_TARGET, hybrid_from = Q_HYBRID_FROM, min_live = Q_GLOBAL_MIN_LIVE;
+        if (const char* e = getenv("B2_Q_SHARED_TARGET")) {
+            shared_target = (uint32_t)std::max(1, atoi(e));
+            hybrid_from = shared_target + 1;
+        }
         if (const char* e = getenv("B2_Q_GLOBAL_MIN_LIVE")) min_live = (uint32_t)std::max(1, atoi(e));
-        if (hybrid && n_sh > shared_target) {
+        if (hybrid && n_sh >= hybrid_from) {
             // candidates by decreasing live length; values read again within Q_GLOBAL_MIN_LIVE instructions stay shared
             std::vector<uint32_t> def_pos(n_vreg, 0);
             for (uint32_t j = 0; j < kept.size(); j++) def_pos[kept[j]] = j;

@@ -272,10 +272,11 @@ int b2_quotient_program_free(b2_handle_t program);
 /* lowered instruction count, shared-memory slots per row, field multiplications / additions per row */
 int b2_quotient_program_info(b2_handle_t program, uint32_t* n_instr, uint32_t* n_slots, uint32_t* n_mul,
                              uint32_t* n_addsub);
-/* The two slot classes of the lowered program: n_slots = n_shared + n_global.  A program whose live width would cost
- * resident CTAs (more than 7 shared-memory slots of 4 KB per CTA) keeps its longest-lived values -- sub-expressions the
- * circuit shares between gates far apart in its gate list (evaluation.rs:877-907 keeps every such value for the whole
- * row) -- in a per-CTA global scratch instead; n_global = 0 for every other program.  B2_Q_HYBRID=0 in the environment
+/* The two slot classes of the lowered program: n_slots = n_shared + n_global.  A program of 10 or more live values
+ * (shared-memory slots of 4 KB per CTA: from there on the lost resident CTAs cost more than global round trips, measured)
+ * keeps 7 slots in shared memory and its longest-lived values -- sub-expressions the circuit shares between gates far
+ * apart in its gate list (evaluation.rs:877-907 keeps every such value for the whole row) -- in a per-CTA global
+ * scratch; n_global = 0 for every other program.  B2_Q_HYBRID=0 in the environment
  * puts every slot into shared memory (A/B runs). */
 int b2_quotient_program_slot_classes(b2_handle_t program, uint32_t* n_shared, uint32_t* n_global);
 

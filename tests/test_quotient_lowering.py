@@ -195,7 +195,7 @@ def test_long_lived_values_move_to_the_global_slot_class(monkeypatch):
     """A program whose gates share sub-expressions far apart (tools/quotient_bench.py long_lived: the first gates'
     values are read again by extra gates at the end of the list, so the y-fold keeps them alive across the whole
     program): with every slot in shared memory the live width costs resident CTAs; the lowering moves the
-    longest-lived values to the global class until at most 7 shared slots remain (b2_quotient_program_slot_classes).
+    longest-lived values to the global class (from 10 live values on) until at most 7 shared slots remain (b2_quotient_program_slot_classes).
     Both lowerings are interpreted with big ints on every row and must agree with each other and with the C
     restatement of Calculation::evaluate on the flat program."""
     import os
@@ -217,9 +217,14 @@ def test_long_lived_values_move_to_the_global_slot_class(monkeypatch):
     assert ih["n_slots_shared"] <= 7 and ih["n_slots_global"] >= 6
     assert ih["n_slots"] == ih["n_slots_shared"] + ih["n_slots_global"]
     assert (ih["n_instr"], ih["n_mul"], ih["n_addsub"]) == (ip["n_instr"], ip["n_mul"], ip["n_addsub"])
-    # a program without such values is left alone
+    # a program without such values is left alone, and so is one of fewer than 10 live values (measured: 8 values are
+    # faster all in shared memory at 6 CTAs per SM than as 7 + 1)
     ev3, lk3, sh3, ns3 = qb.synthetic_evaluator(A=12, F=6, gates=24, lookups=(2, 1), shuffles=1, perm_cols=6)
     assert ev3.program(ns3, list(lk3), sh3).info()["n_slots_global"] == 0
+    for ll, classes in ((6, (8, 0)), (7, (9, 0)), (8, (7, 3))):
+        e4, lk4, sh4, ns4 = qb.synthetic_evaluator(gates=96, long_lived=ll)
+        i4 = e4.program(ns4, list(lk4), sh4).info()
+        assert (i4["n_slots_shared"], i4["n_slots_global"]) == classes
     log_rows, rot_scale = 4, 2
     rows = 1 << log_rows
     ncols = plain.n_fixed + plain.n_advice + plain.n_instance + plain.n_aux
