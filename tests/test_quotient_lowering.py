@@ -251,3 +251,28 @@ def test_long_lived_values_move_to_the_global_slot_class(monkeypatch):
             writes.setdefault(ins[1], []).append(pos)
     assert len(writes) == ih["n_slots_global"]
     plain.free(); hybrid.free()
+
+
+def test_gate_order_of_the_proof_circuit_and_the_slot_classes():
+    """the stand-in circuit of the k = 22 proof (tools/zkwasm_shape_circuit.py) in both gate orders: with each extra
+    gate next to the gate whose factor it shares the lowered evaluate_h program needs 5 live values; with the extra
+    gates after all product gates -- the same constraints -- every shared factor stays alive across the y-fold, 17
+    values, of which the lowering keeps 7 in shared memory and 10 in the global class.  Same instruction and product
+    counts either way: the gate order is the front-end's choice and must not cost the engine its resident CTAs."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import zkwasm_shape_circuit as zk
+    from halo2_gpu_specific_b200 import plonk as HP
+    infos = []
+    for at_end in (False, True):
+        cs = HP.ConstraintSystem(**zk.constraint_system_args(extra_gates=300, extras_at_end=at_end))
+        n_perm = (len(cs.permutation_columns) + cs.degree() - 3) // (cs.degree() - 2)
+        prog = HP.build_evaluator(cs).program(n_perm, [len(lk["input_expressions_sets"]) for lk in cs.lookups],
+                                              len(cs.shuffles))
+        infos.append(prog.info())
+        prog.free()
+    near, far = infos
+    assert (near["n_slots_shared"], near["n_slots_global"]) == (5, 0)
+    assert (far["n_slots_shared"], far["n_slots_global"]) == (7, 10)
+    assert (near["n_instr"], near["n_mul"], near["n_addsub"]) == (far["n_instr"], far["n_mul"], far["n_addsub"])

@@ -37,15 +37,22 @@ def _sub(a, b): return ("Sum", a, ("Negated", b))  # noqa: E704
 def _add(a, b): return ("Sum", a, b)               # noqa: E704
 
 
-def constraint_system_args(extra_gates: int = 64) -> dict:
+def constraint_system_args(extra_gates: int = 64, extras_at_end: bool = False) -> dict:
+    """extras_at_end: the extra gates follow ALL product gates instead of sitting next to the gate whose factor they
+    share -- the same constraints in another gate order, which keeps every shared factor q_j * (a*b - c) alive across
+    the whole y-fold (17 live values in the lowered evaluate_h program instead of 5: the case the quotient kernel's
+    global slot class is for)"""
     gates = []
     product = lambda j: _sub(_mul(_adv(3 * j), _adv(3 * j + 1)), _adv(3 * j + 2))      # noqa: E731
+    late = []
     for j in range(TRIPLES):                          # one gate per triple: its product constraint and its extras, so
         polys = [_mul(_fix(j), product(j))]           # that the shared sub-expression q_j * (a*b - c) is short-lived
         for e in range(j, extra_gates, TRIPLES):
             x, y = (7 * e + 3) % A, 18 + (e % (F - 18))
-            polys.append(_mul(_mul(_fix(j), product(j)), _add(_adv(x), _fix(y))))
+            (late if extras_at_end else polys).append(_mul(_mul(_fix(j), product(j)), _add(_adv(x), _fix(y))))
         gates.append(polys)
+    if late:
+        gates.append(late)
     gates.append([_mul(_fix(15), _sub(_sub(_adv(46, 1), _adv(46)), _adv(45)))])
     gates.append([_mul(_fix(17), _sub(_adv(47), ("Instance", 0, 0)))])
     lookups, col = [], 48
