@@ -224,18 +224,20 @@ def test_sharded_commit_prover_matches_single_process(tmp_path, world):
     assert total[0] == 27 and max(m[0] for m in msms) <= 27 // world + 7
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_range_sharded_commits_match_single_process(tmp_path, world):
+@pytest.mark.parametrize("world,forced", [(2, True), (3, True), (4, None)])
+def test_range_sharded_commits_match_single_process(tmp_path, world, forced):
     """SURVEY 8(e) option (i) inside the prover (prover_sharded.ShardedCommits.commit_by_point_range): with the range
     division forced for every full-width block, each rank multiplies its point range [r * ceil(n / N), ...) of every
     column (arithmetic.rs:426 part_len rule), the partials are all-gathered rank-major and summed -- and the proof
-    bytes (GWC and SHPLONK) are still the single-process oracle prover's on every rank"""
+    bytes (GWC and SHPLONK) are still the single-process oracle prover's on every rank.  forced = None: four ranks with
+    the cost model choosing (one-column blocks by range, the others by column).  Five ranks (uneven ranges of the 32
+    points) were run offline with the same result."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import plonk_fixture as fxm
     from halo2_gpu_specific_b200 import parallel
     from halo2_gpu_specific_b200.plonk import SeededRng
     from oracle import prover as PR
-    mp.spawn(_prover_worker, args=(world, _free_port(), str(tmp_path), True), nprocs=world, join=True)
+    mp.spawn(_prover_worker, args=(world, _free_port(), str(tmp_path), forced), nprocs=world, join=True)
     fx = fxm.build(k=5, seed=11)
     oparams = PR.Params(5, 0x2B200B200B200B2001)
     opk = PR.keygen(oparams, fx["cs"], fx["fixed"], fx["mapping"])
@@ -247,8 +249,11 @@ def test_range_sharded_commits_match_single_process(tmp_path, world):
         ranges = np.load(os.path.join(str(tmp_path), f"ranges_r{r}.npy"))
         # the instance column, the random polynomial, the h pieces and the multiopen witnesses went by point range, and
         # every call used this rank's range of the 32 points
-        assert len(ranges) >= 8 and {(int(a), int(b)) for a, b, _ in ranges} == {parallel.shard_range(32, world, r)}
-        assert sum(int(c) for _, _, c in ranges) >= 1 + 1 + 4 + 4
+        assert {(int(a), int(b)) for a, b, _ in ranges} == {parallel.shard_range(32, world, r)}
+        if forced:
+            assert len(ranges) >= 8 and sum(int(c) for _, _, c in ranges) >= 1 + 1 + 4 + 4
+        else:                                # instance + random polynomial (GWC), + SHPLONK's one-column blocks
+            assert len(ranges) >= 4 and all(int(c) == 1 for _, _, c in ranges)
 
 
 def test_range_division_cost_model():
