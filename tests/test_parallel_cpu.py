@@ -284,6 +284,20 @@ def test_range_division_cost_model():
         parallel.world = saved
 
 
+def test_range_division_cost_model_follows_the_committed_sweep():
+    """ShardedCommits._msm_ms, the time model behind the choice between the two divisions, against the measured
+    single-GPU MSM sweep committed with the round's bench line (profiles/r2_bench_1gpu_final.json, strong_scaling):
+    within 5 % at every size from 2^18 to 2^26"""
+    import json
+    from halo2_gpu_specific_b200.prover_sharded import ShardedCommits
+    line = json.load(open(os.path.join(ROOT, "profiles", "r2_bench_1gpu_final.json")))
+    sizes = line["strong_scaling"]["sizes"]
+    assert len(sizes) >= 5
+    for name, rec in sizes.items():
+        n = 1 << int(name.split("^")[1])
+        assert abs(ShardedCommits._msm_ms(n) / rec["ms"] - 1) < 0.05, name
+
+
 def _rng_worker(rank, world, port, outdir):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
